@@ -1,0 +1,15 @@
+"""ilqr.jl_b200 — B200-native batched iLQR hot path behind iLQR.jl's solver interface.
+
+Only what the path needs lives here: csrc/ (sm_100a CUDA kernels + the C ABI of
+include/ilqr_b200.h) and host.py (the host-side mirror of the reference's
+fit / backward_pass / forward_pass).  There is no CPU implementation in this
+package: importing works anywhere, but every compute call requires the CUDA
+library and a B200.
+"""
+from . import _abi, _build
+from ._abi import Problem, load_library
+from ._build import build
+from .host import BatchSolver, IlqrError, backward_pass, fit, forward_pass, two_link_problem
+
+__all__ = ["BatchSolver", "IlqrError", "Problem", "backward_pass", "build", "fit", "forward_pass", "load_library",
+           "two_link_problem"]

@@ -1,0 +1,556 @@
+// capi.cu — the C ABI declared in include/ilqr_b200.h.
+// Host-side orchestration only: buffer ownership, layout conversion at the
+// boundary, kernel launches, and the batched mirror of fit's control loop
+// (src/forward_pass.jl:148-179 of the reference).  No CPU compute path exists:
+// every numerical result comes from the CUDA kernels or the call fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/ilqr_b200.h"
+#include "internal.cuh"
+
+using namespace ilqr;
+
+struct ilqr_handle {
+  ilqr_problem prob{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevState st{};
+  TwoLinkP mp{};
+  CostP cp{};
+  // TF (boundary-layout) staging on device
+  double* stage_x = nullptr;   // [B][n*N]
+  double* stage_u = nullptr;   // [B][m*H]
+  double* stage_big = nullptr; // [B][m*n*H] (lazy; K downloads)
+  double* scratch_b = nullptr; // [S] doubles
+  int32_t* pinned_i32 = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+  int64_t launches = 0;
+  bool loaded = false, have_gains = false, have_candidate = false;
+  // cumulative profile since the last upload
+  double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int32_t n_active_host = 0;   // active trajectories at the next launch (host copy)
+  bool pend_bwd = false, pend_fwd = false;
+  std::string err;
+};
+
+namespace {
+
+std::string g_create_err;
+
+#define CK(h, call)                                                                             \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+      return ILQR_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+int32_t fail(ilqr_handle* h, int32_t code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+template <class T> cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
+
+int32_t check_launch(ilqr_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, ILQR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return ILQR_OK;
+}
+
+void free_all(ilqr_handle* h) {
+  DevState& s = h->st;
+  for (int i = 0; i < 2; ++i) { cudaFree(s.x[i]); cudaFree(s.u[i]); }
+  cudaFree(s.xtraj); cudaFree(s.duff); cudaFree(s.K);
+  cudaFree(s.prev_cost); cudaFree(s.new_cost); cudaFree(s.alpha); cudaFree(s.du2);
+  cudaFree(s.cost_trace); cudaFree(s.alpha_trace); cudaFree(s.du2_trace);
+  cudaFree(s.status); cudaFree(s.iters); cudaFree(s.active); cudaFree(s.cur); cudaFree(s.bar); cudaFree(s.n_active);
+  cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
+  if (h->pinned_i32) cudaFreeHost(h->pinned_i32);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+int32_t ensure_xtraj(ilqr_handle* h) {
+  if (!h->st.xtraj) {
+    const size_t N = h->prob.H + 1;
+    CK(h, dalloc(&h->st.xtraj, N * h->prob.n * (size_t)h->st.S));
+  }
+  return ILQR_OK;
+}
+
+// after the TF staging buffers hold x_init/u_init (and optionally x_traj in stage_big? no: separate pass)
+int32_t finish_upload(ilqr_handle* h) {
+  const ilqr_problem& p = h->prob;
+  launch_reset_state(h->st, h->stream);
+  launch_tf_to_bf(h->stage_x, h->st.x[0], p.B, p.H + 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_u, h->st.u[0], p.B, p.H, p.m, h->st.S, h->stream);
+  h->launches += 3;
+  if (int32_t rc = check_launch(h, "upload kernels")) return rc;
+  h->loaded = true; h->have_gains = false; h->have_candidate = false;
+  for (auto& v : h->prof) v = 0.0;
+  h->n_active_host = p.B; h->pend_bwd = h->pend_fwd = false;
+  return ILQR_OK;
+}
+
+// fold the event times of the passes launched since the last sync into the profile (stream must be idle)
+void accumulate_profile(ilqr_handle* h) {
+  float ms = 0.f;
+  if (h->pend_bwd && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) {
+    if (h->prof[2] == 0) h->prof[5] = ms;
+    h->prof[0] += ms; h->prof[2] += 1; h->prof[4] += h->n_active_host;
+  }
+  if (h->pend_fwd && cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) {
+    if (h->prof[3] == 0) h->prof[6] = ms;
+    h->prof[1] += ms; h->prof[3] += 1;
+  }
+  h->pend_bwd = h->pend_fwd = false;
+}
+
+int32_t upload_xtraj(ilqr_handle* h, const double* src, cudaMemcpyKind kind) {
+  const ilqr_problem& p = h->prob;
+  const size_t N = p.H + 1;
+  if (!src) {
+    if (h->st.xtraj) { cudaFree(h->st.xtraj); h->st.xtraj = nullptr; }
+    return ILQR_OK;
+  }
+  if (int32_t rc = ensure_xtraj(h)) return rc;
+  // reuse stage_x as the TF staging for x_traj (before x_init lands there)
+  CK(h, cudaMemcpyAsync(h->stage_x, src, sizeof(double) * N * p.n * p.B, kind, h->stream));
+  launch_tf_to_bf(h->stage_x, h->st.xtraj, p.B, p.H + 1, p.n, h->st.S, h->stream);
+  h->launches += 1;
+  return check_launch(h, "x_traj transpose");
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t ilqr_abi_version(void) { return ILQR_ABI_VERSION; }
+
+int32_t ilqr_problem_two_link(ilqr_problem* p, int32_t H, int32_t B) {
+  if (!p) return ILQR_ERR_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->abi_version = ILQR_ABI_VERSION;
+  p->model_id = ILQR_MODEL_TWO_LINK;
+  p->n = 4; p->m = 2; p->H = H; p->B = B;
+  p->n_alpha = 32; p->trace_iters = 0; p->device = 0; p->variant = ILQR_VARIANT_AUTO;
+  // test/2_link_example/2_link_helper_functions.jl:4-16, same operation order
+  const double l1 = std::sqrt(2.) / 2., l2 = std::sqrt(2.) / 2.;
+  const double r1 = 0.5 * l1, r2 = 0.5 * l2;
+  const double m1 = 1.0, m2 = 1.0;
+  const double Iz1 = 1.0 / 12.0 * m1 * (l1 * l1), Iz2 = 1.0 / 12.0 * m2 * (l2 * l2);
+  p->model_params[0] = Iz1 + Iz2 + m1 * (r1 * r1) + m2 * (l1 * l1 + r2 * r2);  // α
+  p->model_params[1] = m2 * l1 * r2;                                             // β
+  p->model_params[2] = Iz2 + m2 * (r2 * r2);                                     // δ
+  p->dt = 0.01;
+  p->reg = 0.01;  // src/backward_pass.jl:214
+  // InverseKinematics(target_tool_loc = [0.6, -0.5])  :17-26
+  const double x = 0.6, y = -0.5;
+  const double q2 = std::acos((x * x + y * y - l1 * l1 - l2 * l2) / (2 * l1 * l2));
+  const double q1 = std::atan2(y, x) - std::atan2(l2 * std::sin(q2), l1 + l2 * std::cos(q2));
+  p->x_target[0] = q1; p->x_target[1] = q2;
+  // immediate_cost :82-97 (velocity_penalty is not added), final_cost :100-108
+  p->w_x[0] = 1.0; p->w_x[1] = 1.0; p->w_u[0] = 1.0; p->w_u[1] = 1.0;
+  p->w_xf[0] = 1.0; p->w_xf[1] = 1.0;
+  return ILQR_OK;
+}
+
+const char* ilqr_last_error(const ilqr_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
+  if (!p || !out) return fail(nullptr, ILQR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (p->abi_version != ILQR_ABI_VERSION) return fail(nullptr, ILQR_ERR_INVALID, "abi_version mismatch");
+  if (p->model_id != ILQR_MODEL_TWO_LINK || p->n != 4 || p->m != 2)
+    return fail(nullptr, ILQR_ERR_INVALID, "unsupported model (only ILQR_MODEL_TWO_LINK, n=4, m=2)");
+  if (p->H < 1 || p->B < 1 || p->n_alpha < 1 || p->n_alpha > 64 || p->trace_iters < 0)
+    return fail(nullptr, ILQR_ERR_INVALID, "bad H/B/n_alpha/trace_iters");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= p->device)
+    return fail(nullptr, ILQR_ERR_NO_DEVICE, "no CUDA device (libilqr_b200 has no CPU path)");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, ILQR_ERR_NO_DEVICE, "device is not sm_100-class; kernels are built for sm_100a only");
+
+  ilqr_handle* h = new (std::nothrow) ilqr_handle();
+  if (!h) return fail(nullptr, ILQR_ERR_INVALID, "out of host memory");
+  h->prob = *p; h->device = p->device;
+#define CKC(call)                                                                               \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+      free_all(h); delete h; return ILQR_ERR_CUDA;                                              \
+    }                                                                                           \
+  } while (0)
+  CKC(cudaSetDevice(p->device));
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CKC(cudaEventCreate(&e));
+  DevState& s = h->st;
+  const size_t N = p->H + 1, H = p->H, n = p->n, m = p->m;
+  s.S = ((int64_t)p->B + 31) / 32 * 32;
+  s.nslots = p->B; s.H = p->H; s.n = p->n; s.m = p->m; s.n_alpha = p->n_alpha; s.trace_iters = p->trace_iters;
+  s.reg = p->reg;
+  const size_t S = (size_t)s.S;
+  for (int i = 0; i < 2; ++i) { CKC(dalloc(&s.x[i], N * n * S)); CKC(dalloc(&s.u[i], H * m * S)); }
+  CKC(dalloc(&s.duff, H * m * S)); CKC(dalloc(&s.K, H * m * n * S));
+  CKC(dalloc(&s.prev_cost, S)); CKC(dalloc(&s.new_cost, S)); CKC(dalloc(&s.alpha, S)); CKC(dalloc(&s.du2, S));
+  if (p->trace_iters > 0) {
+    CKC(dalloc(&s.cost_trace, (size_t)p->trace_iters * S)); CKC(dalloc(&s.alpha_trace, (size_t)p->trace_iters * S));
+    CKC(dalloc(&s.du2_trace, (size_t)p->trace_iters * S));
+  }
+  CKC(dalloc(&s.status, S)); CKC(dalloc(&s.iters, S)); CKC(dalloc(&s.active, S)); CKC(dalloc(&s.cur, S));
+  CKC(dalloc(&s.bar, S)); CKC(dalloc(&s.n_active, 1));
+  CKC(dalloc(&h->stage_x, N * n * (size_t)p->B)); CKC(dalloc(&h->stage_u, H * m * (size_t)p->B));
+  CKC(dalloc(&h->scratch_b, S));
+  CKC(cudaHostAlloc((void**)&h->pinned_i32, 64, cudaHostAllocDefault));
+  // padded slots must never hold NaN garbage that a kernel could trip on
+  for (int i = 0; i < 2; ++i) { CKC(cudaMemsetAsync(s.x[i], 0, sizeof(double) * N * n * S, h->stream));
+                                CKC(cudaMemsetAsync(s.u[i], 0, sizeof(double) * H * m * S, h->stream)); }
+  CKC(cudaMemsetAsync(s.duff, 0, sizeof(double) * H * m * S, h->stream));
+  CKC(cudaMemsetAsync(s.K, 0, sizeof(double) * H * m * n * S, h->stream));
+  launch_reset_state(s, h->stream);
+  CKC(cudaStreamSynchronize(h->stream));
+#undef CKC
+  h->mp.alpha = p->model_params[0]; h->mp.beta = p->model_params[1]; h->mp.delta = p->model_params[2];
+  h->mp.dt = p->dt; h->mp.twobeta = 2 * p->model_params[1];
+  for (int i = 0; i < kMaxN; ++i) { h->cp.x_target[i] = p->x_target[i]; h->cp.w_x[i] = p->w_x[i]; h->cp.w_xf[i] = p->w_xf[i]; }
+  for (int i = 0; i < kMaxM; ++i) h->cp.w_u[i] = p->w_u[i];
+  *out = h;
+  return ILQR_OK;
+}
+
+int32_t ilqr_destroy(ilqr_handle* h) {
+  if (!h) return ILQR_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_all(h);
+  delete h;
+  return ILQR_OK;
+}
+
+int32_t ilqr_upload(ilqr_handle* h, const double* x_init, const double* u_init, const double* x_traj) {
+  if (!h || !x_init || !u_init) return fail(h, ILQR_ERR_INVALID, "null argument");
+  const ilqr_problem& p = h->prob;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = upload_xtraj(h, x_traj, cudaMemcpyHostToDevice)) return rc;
+  const size_t N = p.H + 1;
+  CK(h, cudaMemcpyAsync(h->stage_x, x_init, sizeof(double) * N * p.n * p.B, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * p.B, cudaMemcpyHostToDevice, h->stream));
+  if (int32_t rc = finish_upload(h)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_upload_device(ilqr_handle* h, const double* d_x, const double* d_u, const double* d_xt) {
+  if (!h || !d_x || !d_u) return fail(h, ILQR_ERR_INVALID, "null argument");
+  const ilqr_problem& p = h->prob;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = upload_xtraj(h, d_xt, cudaMemcpyDeviceToDevice)) return rc;
+  launch_reset_state(h->st, h->stream);
+  launch_tf_to_bf(d_x, h->st.x[0], p.B, p.H + 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(d_u, h->st.u[0], p.B, p.H, p.m, h->st.S, h->stream);
+  h->launches += 3;
+  if (int32_t rc = check_launch(h, "upload_device kernels")) return rc;
+  h->loaded = true; h->have_gains = false; h->have_candidate = false;
+  for (auto& v : h->prof) v = 0.0;
+  h->n_active_host = p.B; h->pend_bwd = h->pend_fwd = false;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_upload_x0(ilqr_handle* h, const double* x0, const double* u_init, const double* x_traj) {
+  if (!h || !x0 || !u_init) return fail(h, ILQR_ERR_INVALID, "null argument");
+  const ilqr_problem& p = h->prob;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = upload_xtraj(h, x_traj, cudaMemcpyHostToDevice)) return rc;
+  // x0[n,B] is a TF array with T = 1: stage it in stage_x, transpose into x[1] (free scratch), roll out into x[0]
+  CK(h, cudaMemcpyAsync(h->stage_x, x0, sizeof(double) * p.n * p.B, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * p.B, cudaMemcpyHostToDevice, h->stream));
+  launch_reset_state(h->st, h->stream);
+  launch_tf_to_bf(h->stage_x, h->st.x[1], p.B, 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_u, h->st.u[0], p.B, p.H, p.m, h->st.S, h->stream);
+  launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
+  h->launches += 4;
+  if (int32_t rc = check_launch(h, "upload_x0 kernels")) return rc;
+  h->loaded = true; h->have_gains = false; h->have_candidate = false;
+  for (auto& v : h->prof) v = 0.0;
+  h->n_active_host = p.B; h->pend_bwd = h->pend_fwd = false;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_upload_gains(ilqr_handle* h, const double* duff, const double* K) {
+  if (!h || !duff || !K) return fail(h, ILQR_ERR_INVALID, "null argument");
+  if (!h->loaded) return fail(h, ILQR_ERR_STATE, "upload_gains before upload");
+  const ilqr_problem& p = h->prob;
+  const size_t H = p.H, n = p.n, m = p.m, B = p.B;
+  CK(h, cudaSetDevice(h->device));
+  if (!h->stage_big) CK(h, dalloc(&h->stage_big, H * m * n * B));
+  // stage_u currently mirrors nothing the solver still needs (u lives in BF buffers)
+  CK(h, cudaMemcpyAsync(h->stage_u, duff, sizeof(double) * H * m * B, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->stage_big, K, sizeof(double) * H * m * n * B, cudaMemcpyHostToDevice, h->stream));
+  launch_tf_to_bf(h->stage_u, h->st.duff, p.B, p.H, p.m, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_big, h->st.K, p.B, p.H, p.m * p.n, h->st.S, h->stream);
+  h->launches += 2;
+  if (int32_t rc = check_launch(h, "upload_gains kernels")) return rc;
+  h->have_gains = true;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+static int32_t backward_async(ilqr_handle* h) {
+  if (!h->loaded) return fail(h, ILQR_ERR_STATE, "backward_pass before upload");
+  cudaEventRecord(h->ev[0], h->stream);
+  launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
+  cudaEventRecord(h->ev[1], h->stream);
+  h->launches += 1;
+  h->have_gains = true; h->pend_bwd = true;
+  return check_launch(h, "backward kernel");
+}
+
+static int32_t forward_async(ilqr_handle* h) {
+  if (!h->have_gains) return fail(h, ILQR_ERR_STATE, "forward_pass before backward_pass");
+  cudaEventRecord(h->ev[2], h->stream);
+  launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
+  cudaEventRecord(h->ev[3], h->stream);
+  h->launches += 1;
+  h->have_candidate = true; h->ev_valid = true; h->pend_fwd = true;
+  return check_launch(h, "forward kernel");
+}
+
+static int32_t commit_async(ilqr_handle* h, double tol) {
+  if (!h->have_candidate) return fail(h, ILQR_ERR_STATE, "commit before forward_pass");
+  launch_commit(h->st, tol, h->stream);
+  h->launches += 1;
+  h->have_gains = false; h->have_candidate = false;
+  return check_launch(h, "commit kernel");
+}
+
+static int32_t read_n_active(ilqr_handle* h, int32_t* n_active) {
+  CK(h, cudaMemcpyAsync(h->pinned_i32, h->st.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  accumulate_profile(h);
+  h->n_active_host = h->pinned_i32[0];
+  if (n_active) *n_active = h->pinned_i32[0];
+  return ILQR_OK;
+}
+
+int32_t ilqr_backward_pass(ilqr_handle* h) {
+  if (!h) return ILQR_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = backward_async(h)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_forward_pass(ilqr_handle* h, const double* prev_cost) {
+  if (!h) return ILQR_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  if (prev_cost) {
+    CK(h, cudaMemcpyAsync(h->scratch_b, prev_cost, sizeof(double) * h->prob.B, cudaMemcpyHostToDevice, h->stream));
+    launch_set_prev_cost(h->st, h->scratch_b, h->stream);
+    h->launches += 1;
+  }
+  if (int32_t rc = forward_async(h)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_commit(ilqr_handle* h, double tol, int32_t* n_active) {
+  if (!h) return ILQR_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = commit_async(h, tol)) return rc;
+  return read_n_active(h, n_active);
+}
+
+int32_t ilqr_set_active(ilqr_handle* h, const int32_t* active) {
+  if (!h || !active) return fail(h, ILQR_ERR_INVALID, "null argument");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemcpyAsync(h->st.active, active, sizeof(int32_t) * h->prob.B, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_iterate(ilqr_handle* h, double tol, int32_t* n_active) {
+  if (!h) return ILQR_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = backward_async(h)) return rc;
+  if (int32_t rc = forward_async(h)) return rc;
+  if (int32_t rc = commit_async(h, tol)) return rc;
+  return read_n_active(h, n_active);
+}
+
+static int32_t fit_loop(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_run) {
+  int32_t it = 0, na = h->prob.B;
+  for (it = 1; it <= max_iter; ++it) {
+    if (int32_t rc = backward_async(h)) return rc;
+    if (int32_t rc = forward_async(h)) return rc;
+    if (int32_t rc = commit_async(h, tol)) return rc;
+    if (int32_t rc = read_n_active(h, &na)) return rc;
+    if (na == 0) break;
+  }
+  if (na > 0) {
+    launch_finalize_max_iter(h->st, h->stream);
+    h->launches += 1;
+    it = max_iter;
+  }
+  if (iters_run) *iters_run = it;
+  return check_launch(h, "fit");
+}
+
+int32_t ilqr_fit(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_run) {
+  if (!h) return ILQR_ERR_INVALID;
+  if (!h->loaded) return fail(h, ILQR_ERR_STATE, "fit before upload");
+  if (max_iter < 1) return fail(h, ILQR_ERR_INVALID, "max_iter < 1");
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = fit_loop(h, max_iter, tol, iters_run)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+// Stage `which` in boundary layout on device; returns pointer + byte size.
+static int32_t stage_array(ilqr_handle* h, int32_t which, const void** d_ptr, size_t* bytes) {
+  const ilqr_problem& p = h->prob;
+  const DevState& s = h->st;
+  const size_t B = p.B, N = p.H + 1, H = p.H, n = p.n, m = p.m;
+  switch (which) {
+    case ILQR_X:
+    case ILQR_XBAR:
+      launch_bf_to_tf(s.x[0], s.x[1], which == ILQR_X ? s.cur : s.bar, h->stage_x, p.B, p.H + 1, p.n, s.S, h->stream);
+      h->launches++; *d_ptr = h->stage_x; *bytes = sizeof(double) * N * n * B; break;
+    case ILQR_U:
+    case ILQR_UBAR:
+      launch_bf_to_tf(s.u[0], s.u[1], which == ILQR_U ? s.cur : s.bar, h->stage_u, p.B, p.H, p.m, s.S, h->stream);
+      h->launches++; *d_ptr = h->stage_u; *bytes = sizeof(double) * H * m * B; break;
+    case ILQR_DUFF:
+      launch_bf_to_tf(s.duff, nullptr, nullptr, h->stage_u, p.B, p.H, p.m, s.S, h->stream);
+      h->launches++; *d_ptr = h->stage_u; *bytes = sizeof(double) * H * m * B; break;
+    case ILQR_K:
+      if (!h->stage_big) CK(h, dalloc(&h->stage_big, H * m * n * B));
+      launch_bf_to_tf(s.K, nullptr, nullptr, h->stage_big, p.B, p.H, p.m * p.n, s.S, h->stream);
+      h->launches++; *d_ptr = h->stage_big; *bytes = sizeof(double) * H * m * n * B; break;
+    case ILQR_NEW_COST: *d_ptr = s.new_cost; *bytes = sizeof(double) * B; break;
+    case ILQR_PREV_COST: *d_ptr = s.prev_cost; *bytes = sizeof(double) * B; break;
+    case ILQR_ALPHA: *d_ptr = s.alpha; *bytes = sizeof(double) * B; break;
+    case ILQR_DU2: *d_ptr = s.du2; *bytes = sizeof(double) * B; break;
+    case ILQR_COST_TRACE:
+    case ILQR_ALPHA_TRACE:
+    case ILQR_DU2_TRACE: {
+      if (p.trace_iters <= 0) return fail(h, ILQR_ERR_INVALID, "trace_iters == 0");
+      const double* src = which == ILQR_COST_TRACE ? s.cost_trace : which == ILQR_ALPHA_TRACE ? s.alpha_trace : s.du2_trace;
+      // [trace_iters][S] is a BF array with ncomp = 1, T = trace_iters; fits in stage_x when trace_iters <= N*n
+      double* dst = h->stage_x;
+      if ((size_t)p.trace_iters > N * n) {
+        if (!h->stage_big) CK(h, dalloc(&h->stage_big, H * m * n * B));
+        if ((size_t)p.trace_iters > H * m * n) return fail(h, ILQR_ERR_INVALID, "trace_iters too large to stage");
+        dst = h->stage_big;
+      }
+      launch_bf_to_tf(src, nullptr, nullptr, dst, p.B, p.trace_iters, 1, s.S, h->stream);
+      h->launches++; *d_ptr = dst; *bytes = sizeof(double) * (size_t)p.trace_iters * B; break;
+    }
+    case ILQR_STATUS: *d_ptr = s.status; *bytes = sizeof(int32_t) * B; break;
+    case ILQR_ITERS: *d_ptr = s.iters; *bytes = sizeof(int32_t) * B; break;
+    case ILQR_ACTIVE: *d_ptr = s.active; *bytes = sizeof(int32_t) * B; break;
+    default: return fail(h, ILQR_ERR_INVALID, "unknown array id");
+  }
+  return check_launch(h, "download staging");
+}
+
+int32_t ilqr_download(ilqr_handle* h, int32_t which, void* dst) {
+  if (!h || !dst) return fail(h, ILQR_ERR_INVALID, "null argument");
+  if (!h->loaded) return fail(h, ILQR_ERR_STATE, "download before upload");
+  CK(h, cudaSetDevice(h->device));
+  const void* src; size_t bytes;
+  if (int32_t rc = stage_array(h, which, &src, &bytes)) return rc;
+  CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_download_device(ilqr_handle* h, int32_t which, void* d_dst) {
+  if (!h || !d_dst) return fail(h, ILQR_ERR_INVALID, "null argument");
+  if (!h->loaded) return fail(h, ILQR_ERR_STATE, "download before upload");
+  CK(h, cudaSetDevice(h->device));
+  const void* src; size_t bytes;
+  if (int32_t rc = stage_array(h, which, &src, &bytes)) return rc;
+  CK(h, cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, const double* x_traj, int32_t max_iter,
+                   double tol, double* x_out, double* u_out, double* cost_out, int32_t* iters_out,
+                   int32_t* status_out) {
+  if (!h || !x_init || !u_init || !x_out || !u_out) return fail(h, ILQR_ERR_INVALID, "null argument");
+  const ilqr_problem& p = h->prob;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = upload_xtraj(h, x_traj, cudaMemcpyHostToDevice)) return rc;
+  const size_t N = p.H + 1, B = p.B;
+  CK(h, cudaMemcpyAsync(h->stage_x, x_init, sizeof(double) * N * p.n * B, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * B, cudaMemcpyHostToDevice, h->stream));
+  if (int32_t rc = finish_upload(h)) return rc;
+  if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;
+  const void* src; size_t bytes;
+  if (int32_t rc = stage_array(h, ILQR_X, &src, &bytes)) return rc;
+  CK(h, cudaMemcpyAsync(x_out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (int32_t rc = stage_array(h, ILQR_U, &src, &bytes)) return rc;
+  CK(h, cudaMemcpyAsync(u_out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (cost_out) CK(h, cudaMemcpyAsync(cost_out, h->st.prev_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+  if (iters_out) CK(h, cudaMemcpyAsync(iters_out, h->st.iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+  if (status_out) CK(h, cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+int32_t ilqr_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return ILQR_ERR_INVALID;
+  return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? ILQR_OK : ILQR_ERR_CUDA;
+}
+int32_t ilqr_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? ILQR_OK : ILQR_ERR_CUDA; }
+
+int64_t ilqr_launch_count(const ilqr_handle* h) { return h ? h->launches : 0; }
+
+int32_t ilqr_last_kernel_ms(ilqr_handle* h, float* bwd_ms, float* fwd_ms) {
+  if (!h) return ILQR_ERR_INVALID;
+  if (!h->ev_valid) return fail(h, ILQR_ERR_STATE, "no passes recorded");
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (bwd_ms) CK(h, cudaEventElapsedTime(bwd_ms, h->ev[0], h->ev[1]));
+  if (fwd_ms) CK(h, cudaEventElapsedTime(fwd_ms, h->ev[2], h->ev[3]));
+  return ILQR_OK;
+}
+
+int32_t ilqr_profile(ilqr_handle* h, double* out8) {
+  if (!h || !out8) return ILQR_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  accumulate_profile(h);
+  for (int i = 0; i < 8; ++i) out8[i] = h->prof[i];
+  return ILQR_OK;
+}
+
+int32_t ilqr_set_variant(ilqr_handle* h, int32_t variant) {
+  if (!h) return ILQR_ERR_INVALID;
+  if (variant < ILQR_VARIANT_AUTO || variant > ILQR_VARIANT_WARP_PER_TRAJ) return fail(h, ILQR_ERR_INVALID, "bad variant");
+  h->prob.variant = variant;
+  return ILQR_OK;
+}
+
+int32_t ilqr_sync(ilqr_handle* h) {
+  if (!h) return ILQR_ERR_INVALID;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+void* ilqr_stream(ilqr_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// internal.cuh — shared declarations between the kernel TUs and the C-ABI TU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "two_link.cuh"
+
+namespace ilqr {
+
+constexpr int kMaxN = 16, kMaxM = 8;
+
+// Diagonal-weighted quadratic cost of ilqr_problem.
+struct CostP {
+  double x_target[kMaxN], w_x[kMaxN], w_u[kMaxM], w_xf[kMaxN];
+};
+
+// Device-resident solver state in the batch-fastest ("BF") layout used by the
+// lane-per-trajectory kernels: element (k, c) of trajectory-slot s lives at
+// (k*ncomp + c)*S + s, so a warp's 32 lanes (32 consecutive slots) touch one
+// contiguous 256 B line per load.
+struct DevState {
+  double* x[2];      // iterate ping-pong, [N*n][S]
+  double* u[2];      // [H*m][S]
+  double* xtraj;     // [N*n][S] or nullptr (= zeros)
+  double* duff;      // [H*m][S]
+  double* K;         // [H*m*n][S], component index i + m*j
+  double* prev_cost; // [S]
+  double* new_cost;
+  double* alpha;
+  double* du2;
+  double* cost_trace;   // [trace_iters][S] (nullable)
+  double* alpha_trace;
+  double* du2_trace;
+  int32_t* status;   // [S]
+  int32_t* iters;
+  int32_t* active;
+  int32_t* cur;      // which of x[2]/u[2] holds the slot's current iterate
+  int32_t* bar;      // which holds the last forward-pass candidate
+  int32_t* n_active; // device counter written by commit
+  int64_t S;         // slot stride (B rounded up to 32)
+  int32_t nslots;    // B
+  int32_t H, n, m, n_alpha, trace_iters;
+  double reg;
+};
+
+// kernels_lpt.cu — lane-per-trajectory (throughput) mapping
+void launch_bwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
+void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
+void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0 /*[n][S] BF*/,
+                                  cudaStream_t s);
+void launch_commit(const DevState& st, double tol, cudaStream_t s);
+void launch_finalize_max_iter(const DevState& st, cudaStream_t s);
+void launch_reset_state(const DevState& st, cudaStream_t s);
+void launch_set_prev_cost(const DevState& st, const double* d_prev, cudaStream_t s);
+
+// layout.cu — boundary (Julia, time-fastest "TF") <-> BF transposes
+// TF: src[b*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + b]
+void launch_tf_to_bf(const double* tf, double* bf, int B, int T, int ncomp, int64_t S, cudaStream_t s);
+// sel (nullable): per-slot choice between bf0 and bf1
+void launch_bf_to_tf(const double* bf0, const double* bf1, const int32_t* sel, double* tf, int B, int T, int ncomp,
+                     int64_t S, cudaStream_t s);
+
+}  // namespace ilqr

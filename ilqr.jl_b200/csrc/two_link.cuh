@@ -1,0 +1,198 @@
+// two_link.cuh — device math of the reference's 2-link plugin
+// (test/2_link_example/2_link_helper_functions.jl, paths relative to /root/reference).
+//
+//   dynamicsf :49-79      RK4 (Δt) of θ̈ = M(θ)⁻¹ (u − C(θ,θ̇) θ̇), zero-order-hold u
+//   InertiaMatrix :29-33  M = [α+2β cosθ₂, δ+β cosθ₂; δ+β cosθ₂, δ]
+//   CoriolisMatrix :36-47 with its single-index sum `k in length(θ)` ⇒
+//                         C = −β sinθ₂ θ̇₂ [1 ½; ½ 0]   (closed form)
+//
+// The reference obtains A = ∂f/∂x, B = ∂f/∂u with ForwardDiff
+// (src/backward_pass.jl:32-37).  Here they are the exact analytic derivatives
+// of the same discrete RK4 map, chained stage by stage:
+//   D₁=ΔtΦ₁, D₂=ΔtΦ₂(I+D₁/2), D₃=ΔtΦ₃(I+D₂/2), D₄=ΔtΦ₄(I+D₃), A = I+(D₁+2D₂+2D₃+D₄)/6
+//   E₁=ΔtΨ₁, E₂=Δt(Φ₂E₁/2+Ψ₂), E₃=Δt(Φ₃E₂/2+Ψ₃), E₄=Δt(Φ₄E₃+Ψ₄), B = (E₁+2E₂+2E₃+E₄)/6
+// with Φ = ∂fc/∂state, Ψ = ∂fc/∂u of the continuous dynamics at each stage point.
+// ∂fc/∂θ₁ ≡ 0, so column 0 of every D is zero and A[:,0] = e₀ exactly.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ilqr {
+
+struct TwoLinkP {
+  double alpha, beta, delta, dt;
+  double twobeta;  // 2β  (2_link_helper_functions.jl:30: α+2*β*cos(θ₂))
+};
+
+// One evaluation of the joint accelerations and what the Jacobians reuse.
+struct TLStage {
+  double acc0, acc1;      // θ̈
+  double a, b, idet;      // M = [a b; b δ], 1/det(M)
+  double s2, c2;          // sin θ₂, cos θ₂
+};
+
+__device__ __forceinline__ void tl_accel(const TwoLinkP& p, double th2, double w1, double w2, double u1, double u2,
+                                         TLStage& o) {
+  double s2, c2;
+  sincos(th2, &s2, &c2);
+  const double a = fma(p.twobeta, c2, p.alpha);
+  const double b = fma(p.beta, c2, p.delta);
+  const double det = fma(a, p.delta, -(b * b));
+  const double idet = 1.0 / det;
+  // h = C θ̇ = −β s₂ w₂ (w₁ + ½w₂, ½w₁)
+  const double tw2 = (-p.beta * s2) * w2;
+  const double h1 = tw2 * fma(0.5, w2, w1);
+  const double h2 = tw2 * (0.5 * w1);
+  const double r1 = u1 - h1, r2 = u2 - h2;
+  o.acc0 = (p.delta * r1 - b * r2) * idet;
+  o.acc1 = (a * r2 - b * r1) * idet;
+  o.a = a; o.b = b; o.idet = idet; o.s2 = s2; o.c2 = c2;
+}
+
+// x⁺ = f(x,u): the reference's RK4 step, same stage order and the same
+// x + (1/6)(k1 + 2k2 + 2k3 + k4) combination (:72-78).
+__device__ __forceinline__ void tl_step(const TwoLinkP& p, const double x[4], const double u[2], double xn[4]) {
+  const double dt = p.dt;
+  TLStage st;
+  double k1[4], k2[4], k3[4], k4[4];
+  tl_accel(p, x[1], x[2], x[3], u[0], u[1], st);
+  k1[0] = dt * x[2]; k1[1] = dt * x[3]; k1[2] = dt * st.acc0; k1[3] = dt * st.acc1;
+  {
+    const double w1 = fma(0.5, k1[2], x[2]), w2 = fma(0.5, k1[3], x[3]);
+    tl_accel(p, fma(0.5, k1[1], x[1]), w1, w2, u[0], u[1], st);
+    k2[0] = dt * w1; k2[1] = dt * w2; k2[2] = dt * st.acc0; k2[3] = dt * st.acc1;
+  }
+  {
+    const double w1 = fma(0.5, k2[2], x[2]), w2 = fma(0.5, k2[3], x[3]);
+    tl_accel(p, fma(0.5, k2[1], x[1]), w1, w2, u[0], u[1], st);
+    k3[0] = dt * w1; k3[1] = dt * w2; k3[2] = dt * st.acc0; k3[3] = dt * st.acc1;
+  }
+  {
+    const double w1 = x[2] + k3[2], w2 = x[3] + k3[3];
+    tl_accel(p, x[1] + k3[1], w1, w2, u[0], u[1], st);
+    k4[0] = dt * w1; k4[1] = dt * w2; k4[2] = dt * st.acc0; k4[3] = dt * st.acc1;
+  }
+  const double sixth = 1.0 / 6.0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xn[c] = fma(sixth, ((k1[c] + 2.0 * k2[c]) + 2.0 * k3[c]) + k4[c], x[c]);
+}
+
+// Stage Jacobian rows of the accelerations: phi[r][j] = ∂acc_r/∂(θ₂,w₁,w₂)[j];
+// mi = M⁻¹ entries (i11, i12, i22) = ∂acc/∂u.
+__device__ __forceinline__ void tl_stage_jac(const TwoLinkP& p, const TLStage& st, double w1, double w2,
+                                             double phi[2][3], double mi[3]) {
+  const double i11 = p.delta * st.idet, i12 = -st.b * st.idet, i22 = st.a * st.idet;
+  mi[0] = i11; mi[1] = i12; mi[2] = i22;
+  const double t = -p.beta * st.s2;   // ∂M/∂θ₂ = t [2 1; 1 0]
+  const double tc = -p.beta * st.c2;  // ∂h/∂θ₂ = tc w₂ (w₁+½w₂, ½w₁)
+  const double hw = fma(0.5, w2, w1);
+  // v = ∂M/∂θ₂·acc + ∂h/∂θ₂ ;  ∂acc/∂θ₂ = −M⁻¹ v
+  const double v1 = fma(t, fma(2.0, st.acc0, st.acc1), tc * w2 * hw);
+  const double v2 = fma(t, st.acc0, tc * w2 * (0.5 * w1));
+  phi[0][0] = -(i11 * v1 + i12 * v2);
+  phi[1][0] = -(i12 * v1 + i22 * v2);
+  // ∂h/∂w₁ = t w₂ (1, ½)
+  const double a1 = t * w2, a2 = 0.5 * a1;
+  phi[0][1] = -(i11 * a1 + i12 * a2);
+  phi[1][1] = -(i12 * a1 + i22 * a2);
+  // ∂h/∂w₂ = t (w₁ + w₂, ½w₁)
+  const double b1 = t * (w1 + w2), b2 = t * (0.5 * w1);
+  phi[0][2] = -(i11 * b1 + i12 * b2);
+  phi[1][2] = -(i12 * b1 + i22 * b2);
+}
+
+// One link of the RK4 Jacobian chain.  X (4×3: state rows × columns θ₂,w₁,w₂)
+// and Y (4×2: state rows × u columns) are the previous stage's (I + c·D) and
+// c·E; outputs D = ΔtΦX, E = Δt(ΦY + Ψ).
+__device__ __forceinline__ void tl_chain(double dt, const double phi[2][3], const double mi[3], const double X[4][3],
+                                         const double Y[4][2], double D[4][3], double E[4][2]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    D[0][j] = dt * X[2][j];
+    D[1][j] = dt * X[3][j];
+    D[2][j] = dt * fma(phi[0][2], X[3][j], fma(phi[0][1], X[2][j], phi[0][0] * X[1][j]));
+    D[3][j] = dt * fma(phi[1][2], X[3][j], fma(phi[1][1], X[2][j], phi[1][0] * X[1][j]));
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double m0 = (j == 0) ? mi[0] : mi[1];
+    const double m1 = (j == 0) ? mi[1] : mi[2];
+    E[0][j] = dt * Y[2][j];
+    E[1][j] = dt * Y[3][j];
+    E[2][j] = dt * (fma(phi[0][2], Y[3][j], fma(phi[0][1], Y[2][j], phi[0][0] * Y[1][j])) + m0);
+    E[3][j] = dt * (fma(phi[1][2], Y[3][j], fma(phi[1][1], Y[2][j], phi[1][0] * Y[1][j])) + m1);
+  }
+}
+
+// A = ∂f/∂x (4×4, row-major A[r][c]) and Bm = ∂f/∂u (4×2) at (x,u).
+// (replaces linearize_dynamics, src/backward_pass.jl:25-40, for this plugin)
+__device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4], const double u[2], double A[4][4],
+                                             double Bm[4][2]) {
+  const double dt = p.dt;
+  TLStage st;
+  double phi[2][3], mi[3];
+  double D[4][3], E[4][2], X[4][3], Y[4][2], SD[4][3], SE[4][2];
+
+  // ---- stage 1 at s₁ = x : D₁ = ΔtΦ₁, E₁ = ΔtΨ₁ (X₀ = I, Y₀ = 0 folded by hand)
+  tl_accel(p, x[1], x[2], x[3], u[0], u[1], st);
+  tl_stage_jac(p, st, x[2], x[3], phi, mi);
+  const double k1_1 = dt * x[3], k1_2 = dt * st.acc0, k1_3 = dt * st.acc1;
+  D[0][0] = 0.0; D[0][1] = dt;  D[0][2] = 0.0;
+  D[1][0] = 0.0; D[1][1] = 0.0; D[1][2] = dt;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { D[2][j] = dt * phi[0][j]; D[3][j] = dt * phi[1][j]; }
+  E[0][0] = 0.0; E[0][1] = 0.0; E[1][0] = 0.0; E[1][1] = 0.0;
+  E[2][0] = dt * mi[0]; E[2][1] = dt * mi[1]; E[3][0] = dt * mi[1]; E[3][1] = dt * mi[2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { SD[r][j] = D[r][j]; X[r][j] = 0.5 * D[r][j] + ((r == j + 1) ? 1.0 : 0.0); }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { SE[r][j] = E[r][j]; Y[r][j] = 0.5 * E[r][j]; }
+  }
+
+  // ---- stage 2 at s₂ = x + k₁/2
+  double w1 = fma(0.5, k1_2, x[2]), w2 = fma(0.5, k1_3, x[3]);
+  tl_accel(p, fma(0.5, k1_1, x[1]), w1, w2, u[0], u[1], st);
+  tl_stage_jac(p, st, w1, w2, phi, mi);
+  const double k2_1 = dt * w2, k2_2 = dt * st.acc0, k2_3 = dt * st.acc1;
+  tl_chain(dt, phi, mi, X, Y, D, E);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { SD[r][j] = fma(2.0, D[r][j], SD[r][j]); X[r][j] = 0.5 * D[r][j] + ((r == j + 1) ? 1.0 : 0.0); }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { SE[r][j] = fma(2.0, E[r][j], SE[r][j]); Y[r][j] = 0.5 * E[r][j]; }
+  }
+
+  // ---- stage 3 at s₃ = x + k₂/2
+  w1 = fma(0.5, k2_2, x[2]); w2 = fma(0.5, k2_3, x[3]);
+  tl_accel(p, fma(0.5, k2_1, x[1]), w1, w2, u[0], u[1], st);
+  tl_stage_jac(p, st, w1, w2, phi, mi);
+  const double k3_1 = dt * w2, k3_2 = dt * st.acc0, k3_3 = dt * st.acc1;
+  tl_chain(dt, phi, mi, X, Y, D, E);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { SD[r][j] = fma(2.0, D[r][j], SD[r][j]); X[r][j] = D[r][j] + ((r == j + 1) ? 1.0 : 0.0); }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { SE[r][j] = fma(2.0, E[r][j], SE[r][j]); Y[r][j] = E[r][j]; }
+  }
+
+  // ---- stage 4 at s₄ = x + k₃
+  w1 = x[2] + k3_2; w2 = x[3] + k3_3;
+  tl_accel(p, x[1] + k3_1, w1, w2, u[0], u[1], st);
+  tl_stage_jac(p, st, w1, w2, phi, mi);
+  tl_chain(dt, phi, mi, X, Y, D, E);
+
+  const double sixth = 1.0 / 6.0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    A[r][0] = (r == 0) ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A[r][j + 1] = fma(sixth, SD[r][j] + D[r][j], (r == j + 1) ? 1.0 : 0.0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) Bm[r][j] = sixth * (SE[r][j] + E[r][j]);
+  }
+}
+
+}  // namespace ilqr

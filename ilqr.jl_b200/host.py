@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+The reference (aabouman/iLQR.jl, paths relative to /root/reference) exposes
+  fit(x_init, u_init, dynamicsf, immediate_cost, final_cost; x_traj, max_iter, tol)   src/forward_pass.jl:148
+  backward_pass(x, u, dynamicsf, immediate_cost, final_cost) -> (δuff, K)              src/backward_pass.jl:324
+  forward_pass(x, u, x_traj, δuff, K, prev_cost, dynamicsf, immediate_cost, final_cost) src/forward_pass.jl:55
+The three callbacks are replaced by one `problem` (model id + parameters, see
+include/ilqr_b200.h); everything else keeps its name, argument meaning and
+error behaviour (the reference's @assert → AssertionError).  Arrays are the
+reference's shapes x[N,n], u[H,m], K[H,m,n] or their batched forms with a
+trailing batch axis.  Every call goes through the C ABI of libilqr_b200.so —
+the same entry points a Julia host binds with ccall (julia/iLQRB200.jl).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _abi
+from ._abi import Problem
+
+
+class IlqrError(RuntimeError):
+    pass
+
+
+def two_link_problem(H, B=1, n_alpha=32, trace_iters=0, device=0, reg=None, variant=_abi.VARIANT_AUTO):
+    """The reference's 2-link plugin (test/2_link_example/2_link_helper_functions.jl) as an ilqr_problem."""
+    lib = _abi.load_library()
+    p = Problem()
+    rc = lib.ilqr_problem_two_link(ctypes.byref(p), int(H), int(B))
+    if rc != 0:
+        raise IlqrError("ilqr_problem_two_link failed")
+    p.n_alpha = n_alpha
+    p.trace_iters = trace_iters
+    p.device = device
+    p.variant = variant
+    if reg is not None:
+        p.reg = reg
+    return p
+
+
+def _f64(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+class BatchSolver:
+    """One ilqr_handle: device-resident batch + the passes of the hot path."""
+
+    def __init__(self, problem):
+        self._lib = _abi.load_library()
+        self.problem = problem
+        self._h = ctypes.c_void_p()
+        rc = self._lib.ilqr_create(ctypes.byref(problem), ctypes.byref(self._h))
+        if rc != 0:
+            raise IlqrError("ilqr_create: %s" % self._lib.ilqr_last_error(None).decode())
+        self.n, self.m, self.H, self.B = problem.n, problem.m, problem.H, problem.B
+        self.N = self.H + 1
+
+    # -- plumbing ---------------------------------------------------------
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise IlqrError("%s failed (%d): %s" % (what, rc, self._lib.ilqr_last_error(self._h).decode()))
+
+    def close(self):
+        if self._h:
+            self._lib.ilqr_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _shape(self, a, lead):
+        a = _f64(a)
+        if a.ndim == len(lead):
+            a = a.reshape(tuple(lead) + (1,), order="F")
+        assert a.shape == tuple(lead) + (self.B,), "expected %s, got %s" % (tuple(lead) + (self.B,), a.shape)
+        return a
+
+    # -- data movement ----------------------------------------------------
+    def upload(self, x_init, u_init, x_traj=None):
+        x = self._shape(x_init, (self.N, self.n))
+        u = self._shape(u_init, (self.H, self.m))
+        xt = None if x_traj is None else self._shape(x_traj, (self.N, self.n))
+        self._ck(self._lib.ilqr_upload(self._h, x.ctypes.data, u.ctypes.data, None if xt is None else xt.ctypes.data),
+                 "ilqr_upload")
+
+    def upload_x0(self, x0, u_init, x_traj=None):
+        x0 = self._shape(x0, (self.n,))
+        u = self._shape(u_init, (self.H, self.m))
+        xt = None if x_traj is None else self._shape(x_traj, (self.N, self.n))
+        self._ck(self._lib.ilqr_upload_x0(self._h, x0.ctypes.data, u.ctypes.data,
+                                          None if xt is None else xt.ctypes.data), "ilqr_upload_x0")
+
+    def upload_device(self, d_x, d_u, d_xtraj=None):
+        """d_* are raw device addresses (int) of boundary-layout fp64 arrays."""
+        self._ck(self._lib.ilqr_upload_device(self._h, d_x, d_u, d_xtraj), "ilqr_upload_device")
+
+    def upload_gains(self, duff, K):
+        d = self._shape(duff, (self.H, self.m))
+        k = self._shape(K, (self.H, self.m, self.n))
+        self._ck(self._lib.ilqr_upload_gains(self._h, d.ctypes.data, k.ctypes.data), "ilqr_upload_gains")
+
+    _SHAPES = {
+        _abi.X: lambda s: (s.N, s.n, s.B), _abi.XBAR: lambda s: (s.N, s.n, s.B),
+        _abi.U: lambda s: (s.H, s.m, s.B), _abi.UBAR: lambda s: (s.H, s.m, s.B),
+        _abi.DUFF: lambda s: (s.H, s.m, s.B), _abi.K: lambda s: (s.H, s.m, s.n, s.B),
+        _abi.NEW_COST: lambda s: (s.B,), _abi.PREV_COST: lambda s: (s.B,), _abi.ALPHA: lambda s: (s.B,),
+        _abi.DU2: lambda s: (s.B,),
+        _abi.COST_TRACE: lambda s: (s.problem.trace_iters, s.B), _abi.ALPHA_TRACE: lambda s: (s.problem.trace_iters, s.B),
+        _abi.DU2_TRACE: lambda s: (s.problem.trace_iters, s.B),
+        _abi.STATUS: lambda s: (s.B,), _abi.ITERS: lambda s: (s.B,), _abi.ACTIVE: lambda s: (s.B,),
+    }
+
+    def download(self, which):
+        shape = self._SHAPES[which](self)
+        dtype = np.int32 if which in (_abi.STATUS, _abi.ITERS, _abi.ACTIVE) else np.float64
+        out = np.empty(shape, dtype=dtype, order="F")
+        self._ck(self._lib.ilqr_download(self._h, which, out.ctypes.data), "ilqr_download")
+        return out
+
+    def download_device(self, which, d_dst):
+        self._ck(self._lib.ilqr_download_device(self._h, which, d_dst), "ilqr_download_device")
+
+    # -- the hot path -----------------------------------------------------
+    def backward_pass(self):
+        self._ck(self._lib.ilqr_backward_pass(self._h), "ilqr_backward_pass")
+
+    def forward_pass(self, prev_cost=None):
+        pc = None
+        if prev_cost is not None:
+            pc = np.ascontiguousarray(np.broadcast_to(np.asarray(prev_cost, dtype=np.float64), (self.B,)))
+        self._ck(self._lib.ilqr_forward_pass(self._h, None if pc is None else pc.ctypes.data), "ilqr_forward_pass")
+
+    def commit(self, tol):
+        na = ctypes.c_int32()
+        self._ck(self._lib.ilqr_commit(self._h, float(tol), ctypes.byref(na)), "ilqr_commit")
+        return na.value
+
+    def set_active(self, mask):
+        m = np.ascontiguousarray(np.asarray(mask).astype(np.int32))
+        assert m.shape == (self.B,)
+        self._ck(self._lib.ilqr_set_active(self._h, m.ctypes.data), "ilqr_set_active")
+
+    def iterate(self, tol):
+        na = ctypes.c_int32()
+        self._ck(self._lib.ilqr_iterate(self._h, float(tol), ctypes.byref(na)), "ilqr_iterate")
+        return na.value
+
+    def fit(self, max_iter=100, tol=1e-6):
+        it = ctypes.c_int32()
+        self._ck(self._lib.ilqr_fit(self._h, int(max_iter), float(tol), ctypes.byref(it)), "ilqr_fit")
+        return it.value
+
+    def solve(self, x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, out=None):
+        """Host in → host out (ilqr_solve).  Returns dict(x,u,cost,iters,status)."""
+        x = self._shape(x_init, (self.N, self.n))
+        u = self._shape(u_init, (self.H, self.m))
+        xt = None if x_traj is None else self._shape(x_traj, (self.N, self.n))
+        if out is None:
+            out = dict(x=np.empty_like(x), u=np.empty_like(u), cost=np.empty(self.B),
+                       iters=np.empty(self.B, dtype=np.int32), status=np.empty(self.B, dtype=np.int32))
+        self._ck(self._lib.ilqr_solve(self._h, x.ctypes.data, u.ctypes.data, None if xt is None else xt.ctypes.data,
+                                      int(max_iter), float(tol), out["x"].ctypes.data, out["u"].ctypes.data,
+                                      out["cost"].ctypes.data, out["iters"].ctypes.data, out["status"].ctypes.data),
+                 "ilqr_solve")
+        return out
+
+    # -- introspection ----------------------------------------------------
+    def launch_count(self):
+        return int(self._lib.ilqr_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        b, f = ctypes.c_float(), ctypes.c_float()
+        self._ck(self._lib.ilqr_last_kernel_ms(self._h, ctypes.byref(b), ctypes.byref(f)), "ilqr_last_kernel_ms")
+        return b.value, f.value
+
+    def profile(self):
+        """dict of the cumulative device-time profile since the last upload (ilqr_profile)."""
+        out = (ctypes.c_double * 8)()
+        self._ck(self._lib.ilqr_profile(self._h, out), "ilqr_profile")
+        return dict(bwd_ms=out[0], fwd_ms=out[1], bwd_launches=int(out[2]), fwd_launches=int(out[3]),
+                    traj_iters=out[4], first_bwd_ms=out[5], first_fwd_ms=out[6])
+
+    def stream_ptr(self):
+        return int(self._lib.ilqr_stream(self._h) or 0)
+
+    def set_variant(self, v):
+        self._ck(self._lib.ilqr_set_variant(self._h, v), "ilqr_set_variant")
+
+    def sync(self):
+        self._ck(self._lib.ilqr_sync(self._h), "ilqr_sync")
+
+
+def _batch_of(x):
+    x = _f64(x)
+    return (x.shape[2] if x.ndim == 3 else 1), x.ndim == 2
+
+
+def _problem_for(problem, H, B):
+    p = Problem.from_buffer_copy(problem)
+    p.H, p.B = H, B
+    return p
+
+
+def backward_pass(x, u, problem):
+    """backward_pass(x, u, dynamicsf, immediate_cost, final_cost) → (δuff, K)   src/backward_pass.jl:324-357"""
+    x = _f64(x); u = _f64(u)
+    N, M = x.shape[0], u.shape[0]
+    assert N == M + 1                                   # src/backward_pass.jl:329
+    B, single = _batch_of(x)
+    with BatchSolver(_problem_for(problem, M, B)) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        duff, K, st = s.download(_abi.DUFF), s.download(_abi.K), s.download(_abi.STATUS)
+    assert not np.any(st & _abi.STATUS_NAN_GAINS)       # :353-354
+    return (duff[..., 0], K[..., 0]) if single else (duff, K)
+
+
+def forward_pass(x, u, x_traj, duff, K, prev_cost, problem):
+    """forward_pass(x, u, x_traj, δuff, K, prev_cost, …) → (x̄, ū, new_cost)   src/forward_pass.jl:55-93
+
+    The reference's `while true` halving is bounded at problem.n_alpha candidates;
+    exhausting them raises (the reference would loop forever)."""
+    x = _f64(x); u = _f64(u)
+    N, M = x.shape[0], u.shape[0]
+    assert N == M + 1                                   # src/forward_pass.jl:62
+    B, single = _batch_of(x)
+    with BatchSolver(_problem_for(problem, M, B)) as s:
+        s.upload(x, u, x_traj)
+        s.upload_gains(duff, K)
+        s.forward_pass(prev_cost)
+        xb, ub = s.download(_abi.XBAR), s.download(_abi.UBAR)
+        cost, alpha, st = s.download(_abi.NEW_COST), s.download(_abi.ALPHA), s.download(_abi.STATUS)
+    if np.any(alpha == 0.0):
+        raise IlqrError("line search exhausted n_alpha candidates (reference: infinite loop, src/forward_pass.jl:70)")
+    assert not np.any(st & _abi.STATUS_NAN_ROLLOUT)     # :89-90
+    return (xb[..., 0], ub[..., 0], float(cost[0])) if single else (xb, ub, cost)
+
+
+def fit(x_init, u_init, problem, x_traj=None, max_iter=100, tol=1e-6, info=None):
+    """fit(x_init, u_init, dynamicsf, immediate_cost, final_cost; x_traj, max_iter, tol) → (x̄, ū)
+    src/forward_pass.jl:148-179.  `info` (optional dict) receives cost/iters/status per trajectory."""
+    x = _f64(x_init); u = _f64(u_init)
+    N, M = x.shape[0], u.shape[0]
+    assert N == M + 1, "size(x_init)[2] == size(u_init)[1], (# of states is 1 more than # of inputs in trajectory)"
+    B, single = _batch_of(x)
+    with BatchSolver(_problem_for(problem, M, B)) as s:
+        out = s.solve(x, u, x_traj, max_iter=max_iter, tol=tol)
+    assert not np.any(out["status"] & _abi.STATUS_NOT_DECREASED)   # src/forward_pass.jl:168
+    if info is not None:
+        info.update(cost=out["cost"], iters=out["iters"], status=out["status"])
+    return (out["x"][..., 0], out["u"][..., 0]) if single else (out["x"], out["u"])

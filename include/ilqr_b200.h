@@ -1,0 +1,212 @@
+/* ilqr_b200.h — C ABI of libilqr_b200.so, the B200-native batched iLQR hot path.
+ *
+ * Drop-in boundary for aabouman/iLQR.jl (reference paths relative to
+ * /root/reference).  The reference has no FFI of its own; its API for this
+ * path is three Julia functions plus three user callbacks:
+ *
+ *   iLQR.fit(x_init, u_init, dynamicsf, immediate_cost, final_cost;
+ *            x_traj, max_iter, tol)                 src/forward_pass.jl:148-179
+ *   iLQR.backward_pass(x, u, f, l, lf) -> (δuff, K)  src/backward_pass.jl:324-357
+ *   iLQR.forward_pass(x, u, x_traj, δuff, K, prev_cost, f, l, lf)
+ *                      -> (x̄, ū, new_cost)           src/forward_pass.jl:55-93
+ *
+ * Julia closures cannot run on the GPU, so the callback triple
+ * (dynamicsf, immediate_cost, final_cost) is re-expressed as a model id plus a
+ * POD parameter block (ilqr_problem).  A Julia host reaches every entry point
+ * below with `ccall` (see INTEGRATION.md and julia/iLQRB200.jl).
+ *
+ * Array layout at the boundary = Julia column-major batch arrays with the
+ * batch as the trailing (slowest) dimension:
+ *   x[N,n,B]   element (k,c,b) at  k + N*(c + n*b)          N = H+1
+ *   u[H,m,B]   element (k,i,b) at  k + H*(i + m*b)
+ *   δuff[H,m,B], K[H,m,n,B]  element (k,i,j,b) at k + H*(i + m*(j + n*b))
+ * so a single-problem call is the B = 1 special case with the byte layout of
+ * the reference's own x[N×n], u[H×m], K[H×m×n] (src/backward_pass.jl:332-333).
+ * All floating point is IEEE fp64.
+ *
+ * Every function returns 0 on success and a negative ilqr_error otherwise
+ * (message via ilqr_last_error).  The reference's @assert failures
+ * (src/backward_pass.jl:353-354, src/forward_pass.jl:89-90,168) become
+ * per-trajectory status bits instead of aborting the batch.
+ *
+ * Threading: one handle = one device + one stream; calls on a handle are
+ * synchronous with respect to the host unless stated; handles are independent.
+ */
+#ifndef ILQR_B200_H
+#define ILQR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ILQR_ABI_VERSION 1
+#define ILQR_MAX_N 16
+#define ILQR_MAX_M 8
+
+/* model ids: which (dynamicsf, immediate_cost, final_cost) triple runs on device */
+enum ilqr_model {
+  /* test/2_link_example/2_link_helper_functions.jl:4-108 — planar 2-link arm,
+   * RK4, n=4, m=2.  model_params = {alpha, beta, delta} (lines :12-14). */
+  ILQR_MODEL_TWO_LINK = 1
+};
+
+/* per-trajectory status bits (int32) */
+enum ilqr_status {
+  ILQR_STATUS_OK = 0,
+  ILQR_STATUS_NAN_GAINS = 1,     /* src/backward_pass.jl:353-354 */
+  ILQR_STATUS_NAN_ROLLOUT = 2,   /* src/forward_pass.jl:89-90 */
+  ILQR_STATUS_LS_EXHAUSTED = 4,  /* no α=2^-j, j<n_alpha, gave prev-new>0 (reference: loops forever, :70) */
+  ILQR_STATUS_NOT_DECREASED = 8, /* src/forward_pass.jl:168 */
+  ILQR_STATUS_CONVERGED = 16,    /* Σ(ū⁺-ū)² <= tol reached (src/forward_pass.jl:171) */
+  ILQR_STATUS_MAX_ITER = 32      /* max_iter exhausted without convergence */
+};
+
+enum ilqr_error {
+  ILQR_OK = 0,
+  ILQR_ERR_INVALID = -1,    /* bad argument / unsupported problem */
+  ILQR_ERR_CUDA = -2,       /* CUDA runtime error */
+  ILQR_ERR_NO_DEVICE = -3,  /* no usable B200-class device */
+  ILQR_ERR_STATE = -4       /* call out of order (e.g. forward before backward) */
+};
+
+/* kernel mapping */
+enum ilqr_variant {
+  ILQR_VARIANT_AUTO = 0,           /* choose by active-trajectory count */
+  ILQR_VARIANT_LANE_PER_TRAJ = 1,  /* one thread per trajectory, batch-fastest layout (throughput) */
+  ILQR_VARIANT_WARP_PER_TRAJ = 2   /* one warp per trajectory, time-fastest layout (latency) */
+};
+
+/* which array ilqr_download / ilqr_device_ptr refers to */
+enum ilqr_array {
+  ILQR_X = 0,        /* current iterate x  [N,n,B]  (what fit returns) */
+  ILQR_U = 1,        /* current iterate u  [H,m,B] */
+  ILQR_XBAR = 2,     /* last forward-pass candidate x̄ [N,n,B] */
+  ILQR_UBAR = 3,     /* last forward-pass candidate ū [H,m,B] */
+  ILQR_DUFF = 4,     /* δuff [H,m,B] */
+  ILQR_K = 5,        /* K [H,m,n,B] */
+  ILQR_NEW_COST = 6, /* [B] cost of the last accepted candidate */
+  ILQR_PREV_COST = 7,/* [B] */
+  ILQR_ALPHA = 8,    /* [B] accepted step size of the last forward pass (0 if none) */
+  ILQR_DU2 = 9,      /* [B] Σ(ū-u)² of the last forward pass */
+  ILQR_COST_TRACE = 10,  /* [trace_iters,B] cost per iteration (NaN where not run) */
+  ILQR_ALPHA_TRACE = 11, /* [trace_iters,B] */
+  ILQR_DU2_TRACE = 12,   /* [trace_iters,B] */
+  ILQR_STATUS = 13,  /* int32 [B] */
+  ILQR_ITERS = 14,   /* int32 [B] iterations executed */
+  ILQR_ACTIVE = 15   /* int32 [B] 1 = still iterating */
+};
+
+/* Replaces the (dynamicsf, immediate_cost, final_cost) closures and fit's
+ * keyword arguments.  Costs are the diagonal-weighted quadratics every plugin
+ * in the reference uses:
+ *   l(x,u) = Σ_c w_x[c]·(x_target[c]-x[c])² + Σ_i w_u[i]·u[i]²
+ *   lf(x)  = Σ_c w_xf[c]·(x_target[c]-x[c])²
+ * (2-link: 2_link_helper_functions.jl:82-108 → w_x = w_xf = (1,1,0,0), w_u = (1,1),
+ *  x_target = (θ*₁, θ*₂, ·, ·) from InverseKinematics :19-26.) */
+typedef struct ilqr_problem {
+  int32_t abi_version;    /* = ILQR_ABI_VERSION */
+  int32_t model_id;       /* enum ilqr_model */
+  int32_t n, m;           /* state / control dimension */
+  int32_t H;              /* horizon (N = H+1 knot points) */
+  int32_t B;              /* batch: number of independent trajectories */
+  int32_t n_alpha;        /* line-search candidates α = 2^-j, j = 0..n_alpha-1 (reference: unbounded) */
+  int32_t trace_iters;    /* rows of the per-iteration traces kept on device (0 = none) */
+  int32_t device;         /* CUDA device ordinal */
+  int32_t variant;        /* enum ilqr_variant */
+  double dt;              /* integrator step Δt (2_link_helper_functions.jl:15) */
+  double reg;             /* constant regulariser on H (src/backward_pass.jl:214: 0.01) */
+  double model_params[32];
+  double x_target[ILQR_MAX_N];
+  double w_x[ILQR_MAX_N];
+  double w_u[ILQR_MAX_M];
+  double w_xf[ILQR_MAX_N];
+} ilqr_problem;
+
+typedef struct ilqr_handle ilqr_handle;
+
+int32_t ilqr_abi_version(void);
+
+/* Fill `p` with the reference's 2-link problem (constants computed exactly as
+ * 2_link_helper_functions.jl:4-26 does) for horizon H and batch B. */
+int32_t ilqr_problem_two_link(ilqr_problem* p, int32_t H, int32_t B);
+
+int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out);
+int32_t ilqr_destroy(ilqr_handle* h);
+const char* ilqr_last_error(const ilqr_handle* h); /* h may be NULL: last create error */
+
+/* Load a batch (host pointers, layouts above; x_traj may be NULL = zeros, the
+ * default of fit's keyword, src/forward_pass.jl:151) and reset the solver
+ * state to fit's start: prev_cost = Inf, iter = 0 (src/forward_pass.jl:159-160). */
+int32_t ilqr_upload(ilqr_handle* h, const double* x_init, const double* u_init, const double* x_traj);
+/* Same with device pointers (inputs already resident in HBM). */
+int32_t ilqr_upload_device(ilqr_handle* h, const double* d_x_init, const double* d_u_init, const double* d_x_traj);
+/* Problem-setup helper (animate_2_link.jl:11-16): x_init = open-loop rollout of
+ * u_init from x0[n,B]; then as ilqr_upload. */
+int32_t ilqr_upload_x0(ilqr_handle* h, const double* x0, const double* u_init, const double* x_traj);
+
+/* Load gains computed elsewhere (host pointers, δuff[H,m,B], K[H,m,n,B]) so that
+ * ilqr_forward_pass can be called with the reference's own argument list
+ * forward_pass(x, u, x_traj, δuff, K, prev_cost, …) (src/forward_pass.jl:55-60). */
+int32_t ilqr_upload_gains(ilqr_handle* h, const double* duff, const double* K);
+
+/* backward_pass (src/backward_pass.jl:324-357) on every active trajectory:
+ * linearisation + cost expansion + Riccati recursion → δuff, K on device. */
+int32_t ilqr_backward_pass(ilqr_handle* h);
+
+/* forward_pass (src/forward_pass.jl:55-93) on every active trajectory: closed-
+ * loop rollout, all step sizes α = 2^-j evaluated, largest α with
+ * prev_cost - new_cost > 0 kept → x̄, ū, new_cost, alpha, du2 on device.
+ * prev_cost: host [B] or NULL to use the device-resident value (Inf after upload). */
+int32_t ilqr_forward_pass(ilqr_handle* h, const double* prev_cost);
+
+/* The tail of fit's loop body (src/forward_pass.jl:168-175) on device:
+ * prev_cost = new_cost; trajectories with du2 <= tol are frozen at the iterate
+ * BEFORE this forward pass and marked CONVERGED; the others take (x̄,ū).
+ * n_active (nullable) receives how many trajectories are still iterating. */
+int32_t ilqr_commit(ilqr_handle* h, double tol, int32_t* n_active);
+
+/* Host-owned convergence control: overwrite the active mask (int32 [B]). */
+int32_t ilqr_set_active(ilqr_handle* h, const int32_t* active);
+
+/* backward + forward + commit in one call. */
+int32_t ilqr_iterate(ilqr_handle* h, double tol, int32_t* n_active);
+
+/* fit (src/forward_pass.jl:148-179) for the whole batch with per-trajectory
+ * convergence; trajectories still active after max_iter get MAX_ITER and keep
+ * their newest iterate.  iters_run (nullable): batch iterations executed. */
+int32_t ilqr_fit(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_run);
+
+/* Copy a result array to host memory in the boundary layout. */
+int32_t ilqr_download(ilqr_handle* h, int32_t which, void* dst);
+/* Same into device memory (boundary layout, fp64 / int32). */
+int32_t ilqr_download_device(ilqr_handle* h, int32_t which, void* d_dst);
+
+/* One call, host in → host out: upload, fit, download (x,u) [+ nullable
+ * final cost [B], iters [B], status [B]].  This is what a Julia `fit` wrapper
+ * over a batch calls; copies are pipelined with compute. */
+int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, const double* x_traj,
+                   int32_t max_iter, double tol, double* x_out, double* u_out, double* cost_out,
+                   int32_t* iters_out, int32_t* status_out);
+
+/* Page-locked host buffers for callers that want full-speed PCIe copies. */
+int32_t ilqr_host_alloc(void** out, uint64_t bytes);
+int32_t ilqr_host_free(void* p);
+
+/* Introspection used by benchmarks and tests. */
+int64_t ilqr_launch_count(const ilqr_handle* h);      /* kernels launched by this handle so far */
+int32_t ilqr_last_kernel_ms(ilqr_handle* h, float* bwd_ms, float* fwd_ms); /* CUDA-event time of the last passes */
+/* Cumulative device-time profile since the last upload (CUDA events on the handle's stream):
+ * out[0] Σ backward-kernel ms, out[1] Σ forward-kernel ms, out[2] backward launches,
+ * out[3] forward launches, out[4] Σ over launches of active trajectories (trajectory-iterations),
+ * out[5] first-iteration backward ms, out[6] first-iteration forward ms, out[7] reserved. */
+int32_t ilqr_profile(ilqr_handle* h, double* out8);
+int32_t ilqr_set_variant(ilqr_handle* h, int32_t variant);
+int32_t ilqr_sync(ilqr_handle* h);
+void* ilqr_stream(ilqr_handle* h);                    /* the cudaStream_t of this handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILQR_B200_H */

@@ -1,0 +1,205 @@
+// oracle_capi.cpp — C entry points over ilqr_oracle.hpp for ctypes (tests,
+// smoke, bench cpu_baseline only).  TEST INFRASTRUCTURE, not product code.
+// All arrays use the Julia column-major layouts documented in the header;
+// batch arrays put the batch as the trailing (slowest) dimension.
+#include "ilqr_oracle.hpp"
+
+#include <atomic>
+#include <cstring>
+#include <thread>
+
+using namespace oracle;
+
+namespace {
+const TwoLink& plugin() { static TwoLink p; return p; }
+using S2 = Solver<TwoLink>;
+
+struct DumpCtx {
+  int H; int max_dump;
+  double *duff, *K, *xb, *ub;   // [max_dump] stacked per iteration, may be null
+};
+void dump_obs(void* vctx, int iter, const double* duff, const double* K, const double* xb, const double* ub) {
+  auto* c = static_cast<DumpCtx*>(vctx);
+  if (iter > c->max_dump) return;
+  const int H = c->H, N = H + 1, i = iter - 1;
+  if (c->duff) std::memcpy(c->duff + (size_t)i * H * 2, duff, sizeof(double) * H * 2);
+  if (c->K) std::memcpy(c->K + (size_t)i * H * 8, K, sizeof(double) * H * 8);
+  if (c->xb) std::memcpy(c->xb + (size_t)i * N * 4, xb, sizeof(double) * N * 4);
+  if (c->ub) std::memcpy(c->ub + (size_t)i * H * 2, ub, sizeof(double) * H * 2);
+}
+}  // namespace
+
+extern "C" {
+
+// out[0..5] = alpha, beta, delta, dt, theta*_1, theta*_2
+void oracle_two_link_constants(double* out) {
+  const TwoLink& p = plugin();
+  out[0] = p.alpha; out[1] = p.beta; out[2] = p.delta; out[3] = p.dt;
+  out[4] = p.target_joint[0]; out[5] = p.target_joint[1];
+}
+
+void oracle_two_link_dynamics(const double* x, const double* u, double* xn) {
+  Vec<double, 4> xv; Vec<double, 2> uv;
+  for (int i = 0; i < 4; ++i) xv[i] = x[i];
+  for (int i = 0; i < 2; ++i) uv[i] = u[i];
+  auto y = plugin().dynamicsf(xv, uv);
+  for (int i = 0; i < 4; ++i) xn[i] = y[i];
+}
+
+void oracle_two_link_continuous_dynamics(const double* x, const double* u, double* xdot) {
+  Vec<double, 4> xv; Vec<double, 2> uv;
+  for (int i = 0; i < 4; ++i) xv[i] = x[i];
+  for (int i = 0; i < 2; ++i) uv[i] = u[i];
+  auto y = plugin().continuous_dynamics(xv, uv);
+  for (int i = 0; i < 4; ++i) xdot[i] = y[i];
+}
+
+// A[4x4], B[4x2] column-major
+void oracle_two_link_linearize(const double* x, const double* u, double* A, double* B) {
+  S2 s(plugin());
+  S2::VX xv; S2::VU uv;
+  for (int i = 0; i < 4; ++i) xv[i] = x[i];
+  for (int i = 0; i < 2; ++i) uv[i] = u[i];
+  S2::MXX Am; S2::MXU Bm; s.linearize_dynamics(xv, uv, Am, Bm);
+  std::memcpy(A, Am.a.data(), sizeof(double) * 16);
+  std::memcpy(B, Bm.a.data(), sizeof(double) * 8);
+}
+
+// q, qv[4], rv[2], Q[4x4], P[2x4], R[2x2] (column-major)
+void oracle_two_link_cost_quad(const double* x, const double* u, double* q, double* qv, double* rv, double* Q,
+                               double* P, double* R) {
+  S2 s(plugin());
+  S2::VX xv; S2::VU uv;
+  for (int i = 0; i < 4; ++i) xv[i] = x[i];
+  for (int i = 0; i < 2; ++i) uv[i] = u[i];
+  S2::VX qvv; S2::VU rvv; S2::MXX Qm; S2::MUX Pm; S2::MUU Rm;
+  s.immediate_cost_quadratization(xv, uv, *q, qvv, rvv, Qm, Pm, Rm);
+  std::memcpy(qv, qvv.a.data(), sizeof(double) * 4);
+  std::memcpy(rv, rvv.a.data(), sizeof(double) * 2);
+  std::memcpy(Q, Qm.a.data(), sizeof(double) * 16);
+  std::memcpy(P, Pm.a.data(), sizeof(double) * 8);
+  std::memcpy(R, Rm.a.data(), sizeof(double) * 4);
+}
+
+void oracle_two_link_final_cost_quad(const double* x, double* q, double* qv, double* Q) {
+  S2 s(plugin());
+  S2::VX xv; for (int i = 0; i < 4; ++i) xv[i] = x[i];
+  S2::VX qvv; S2::MXX Qm;
+  s.final_cost_quadratization(xv, *q, qvv, Qm);
+  std::memcpy(qv, qvv.a.data(), sizeof(double) * 4);
+  std::memcpy(Q, Qm.a.data(), sizeof(double) * 16);
+}
+
+// zero-input style open-loop rollout: x[N×4] from x0[4] and u[H×2]
+// (test/2_link_example/animate_2_link.jl:11-16)
+void oracle_two_link_rollout(int H, const double* x0, const double* u, double* x) {
+  const int N = H + 1;
+  Vec<double, 4> xv; for (int c = 0; c < 4; ++c) { xv[c] = x0[c]; x[0 + N * c] = x0[c]; }
+  for (int k = 0; k < H; ++k) {
+    Vec<double, 2> uv; uv[0] = u[k]; uv[1] = u[k + H];
+    xv = plugin().dynamicsf(xv, uv);
+    for (int c = 0; c < 4; ++c) x[(k + 1) + N * c] = xv[c];
+  }
+}
+
+int32_t oracle_two_link_backward_pass(int H, const double* x, const double* u, double reg, double* duff, double* K) {
+  S2 s(plugin()); s.reg = reg;
+  return s.backward_pass(H, x, u, duff, K);
+}
+
+double oracle_two_link_total_cost(int H, const double* x, const double* u, const double* x_traj) {
+  S2 s(plugin());
+  return s.total_cost(H, x, u, x_traj);
+}
+
+int32_t oracle_two_link_forward_pass(int H, const double* x, const double* u, const double* x_traj, const double* duff,
+                                     const double* K, double prev_cost, int jmax, double* xb, double* ub,
+                                     double* new_cost, double* alpha) {
+  S2 s(plugin()); s.jmax = jmax;
+  return s.forward_pass(H, x, u, x_traj, duff, K, prev_cost, xb, ub, new_cost, alpha);
+}
+
+// One candidate rollout at a given alpha; returns its total cost.
+double oracle_two_link_rollout_candidate(int H, const double* x, const double* u, const double* x_traj,
+                                         const double* duff, const double* K, double alpha, double* xb, double* ub) {
+  S2 s(plugin());
+  return s.rollout(H, x, u, x_traj, duff, K, alpha, xb, ub);
+}
+
+// fit on one trajectory.  x,u are in/out (returned iterate).  Traces have
+// max_iter entries (unused entries untouched).  dump_* (nullable) receive the
+// first max_dump iterations' gains and candidate trajectories.
+int32_t oracle_two_link_fit(int H, double* x, double* u, const double* x_traj, int max_iter, double tol, double reg,
+                            int jmax, double* cost, double* alpha, double* du2, int32_t* iters, int32_t* converged,
+                            int max_dump, double* dump_duff, double* dump_K, double* dump_xb, double* dump_ub) {
+  S2 s(plugin()); s.reg = reg; s.jmax = jmax;
+  DumpCtx ctx{H, max_dump, dump_duff, dump_K, dump_xb, dump_ub};
+  auto tr = s.fit(H, x, u, x_traj, max_iter, tol, max_dump > 0 ? dump_obs : nullptr, &ctx);
+  for (int i = 0; i < tr.iters; ++i) {
+    if (cost) cost[i] = tr.cost[i];
+    if (alpha) alpha[i] = tr.alpha[i];
+    if (du2) du2[i] = tr.du2[i];
+  }
+  *iters = tr.iters; *converged = tr.converged ? 1 : 0;
+  return tr.status;
+}
+
+// Batched fit: x[N,4,B], u[H,2,B] in/out; x_traj nullable [N,4,B].
+// cost/alpha/du2 traces are [max_iter,B] (column per trajectory) and nullable.
+// nthreads std::threads pull trajectories from an atomic counter.
+void oracle_two_link_fit_batch(int B, int H, double* x, double* u, const double* x_traj, int max_iter, double tol,
+                               double reg, int jmax, int nthreads, double* cost, double* alpha, double* du2,
+                               int32_t* iters, int32_t* converged, int32_t* status) {
+  const int N = H + 1;
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    S2 s(plugin()); s.reg = reg; s.jmax = jmax;
+    for (;;) {
+      int b = next.fetch_add(1);
+      if (b >= B) break;
+      auto tr = s.fit(H, x + (size_t)b * N * 4, u + (size_t)b * H * 2, x_traj ? x_traj + (size_t)b * N * 4 : nullptr,
+                      max_iter, tol);
+      for (int i = 0; i < tr.iters; ++i) {
+        if (cost) cost[(size_t)b * max_iter + i] = tr.cost[i];
+        if (alpha) alpha[(size_t)b * max_iter + i] = tr.alpha[i];
+        if (du2) du2[(size_t)b * max_iter + i] = tr.du2[i];
+      }
+      iters[b] = tr.iters; converged[b] = tr.converged ? 1 : 0; status[b] = tr.status;
+    }
+  };
+  if (nthreads <= 1) { work(); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work);
+  for (auto& t : th) t.join();
+}
+
+// ---- discrete-LQR known-answer support (solver core on a linear plugin) ----
+// n=3, m=2.  A[3x3], B[3x2], Q, R, Qf column-major.  Runs ONE backward pass
+// around (x,u) and returns gains.
+int32_t oracle_lq32_backward_pass(int H, const double* A, const double* B, const double* Q, const double* R,
+                                  const double* Qf, const double* x, const double* u, double reg, double* duff,
+                                  double* K) {
+  LinearQuadratic<3, 2> p;
+  std::memcpy(p.A.a.data(), A, sizeof(double) * 9); std::memcpy(p.B.a.data(), B, sizeof(double) * 6);
+  std::memcpy(p.Q.a.data(), Q, sizeof(double) * 9); std::memcpy(p.R.a.data(), R, sizeof(double) * 4);
+  std::memcpy(p.Qf.a.data(), Qf, sizeof(double) * 9);
+  Solver<LinearQuadratic<3, 2>> s(p); s.reg = reg;
+  return s.backward_pass(H, x, u, duff, K);
+}
+
+int32_t oracle_lq32_fit(int H, const double* A, const double* B, const double* Q, const double* R, const double* Qf,
+                        double* x, double* u, int max_iter, double tol, double reg, double* cost, int32_t* iters) {
+  LinearQuadratic<3, 2> p;
+  std::memcpy(p.A.a.data(), A, sizeof(double) * 9); std::memcpy(p.B.a.data(), B, sizeof(double) * 6);
+  std::memcpy(p.Q.a.data(), Q, sizeof(double) * 9); std::memcpy(p.R.a.data(), R, sizeof(double) * 4);
+  std::memcpy(p.Qf.a.data(), Qf, sizeof(double) * 9);
+  Solver<LinearQuadratic<3, 2>> s(p); s.reg = reg;
+  auto tr = s.fit(H, x, u, nullptr, max_iter, tol);
+  for (int i = 0; i < tr.iters; ++i) cost[i] = tr.cost[i];
+  *iters = tr.iters;
+  return tr.status;
+}
+
+int oracle_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Never import this from the product
+package (ilqr.jl_b200/).
+
+Arrays follow the Julia column-major layouts: x[N,n] is passed as a Fortran-
+ordered (N,n) NumPy array, K[H,m,n] as Fortran (H,m,n); batched arrays carry
+the batch as the trailing dimension ((N,n,B) Fortran order).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ilqr_oracle.hpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.oracle_two_link_total_cost.restype = ctypes.c_double
+        _LIB.oracle_two_link_rollout_candidate.restype = ctypes.c_double
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _f(a, shape=None):
+    a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+def constants():
+    out = np.zeros(6)
+    lib().oracle_two_link_constants(_p(out))
+    return dict(alpha=out[0], beta=out[1], delta=out[2], dt=out[3], theta_star=out[4:6].copy())
+
+
+def dynamics(x, u):
+    x = _f(x, (4,)); u = _f(u, (2,)); y = np.zeros(4)
+    lib().oracle_two_link_dynamics(_p(x), _p(u), _p(y))
+    return y
+
+
+def continuous_dynamics(x, u):
+    x = _f(x, (4,)); u = _f(u, (2,)); y = np.zeros(4)
+    lib().oracle_two_link_continuous_dynamics(_p(x), _p(u), _p(y))
+    return y
+
+
+def linearize(x, u):
+    x = _f(x, (4,)); u = _f(u, (2,))
+    A = np.zeros((4, 4), order="F"); B = np.zeros((4, 2), order="F")
+    lib().oracle_two_link_linearize(_p(x), _p(u), _p(A), _p(B))
+    return A, B
+
+
+def cost_quad(x, u):
+    x = _f(x, (4,)); u = _f(u, (2,))
+    q = ctypes.c_double()
+    qv = np.zeros(4); rv = np.zeros(2)
+    Q = np.zeros((4, 4), order="F"); P = np.zeros((2, 4), order="F"); R = np.zeros((2, 2), order="F")
+    lib().oracle_two_link_cost_quad(_p(x), _p(u), ctypes.byref(q), _p(qv), _p(rv), _p(Q), _p(P), _p(R))
+    return q.value, qv, rv, Q, P, R
+
+
+def final_cost_quad(x):
+    x = _f(x, (4,))
+    q = ctypes.c_double(); qv = np.zeros(4); Q = np.zeros((4, 4), order="F")
+    lib().oracle_two_link_final_cost_quad(_p(x), ctypes.byref(q), _p(qv), _p(Q))
+    return q.value, qv, Q
+
+
+def rollout(x0, u):
+    u = _f(u); H = u.shape[0]
+    x = np.zeros((H + 1, 4), order="F")
+    lib().oracle_two_link_rollout(H, _p(_f(x0, (4,))), _p(u), _p(x))
+    return x
+
+
+def backward_pass(x, u, reg=0.01):
+    u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 4))
+    d = np.zeros((H, 2), order="F"); K = np.zeros((H, 2, 4), order="F")
+    st = lib().oracle_two_link_backward_pass(H, _p(x), _p(u), ctypes.c_double(reg), _p(d), _p(K))
+    return d, K, st
+
+
+def total_cost(x, u, x_traj=None):
+    u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 4))
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 4))
+    return lib().oracle_two_link_total_cost(H, _p(x), _p(u), _p(xt))
+
+
+def forward_pass(x, u, d, K, prev_cost, jmax=32, x_traj=None):
+    u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 4)); d = _f(d, (H, 2)); K = _f(K, (H, 2, 4))
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 4))
+    xb = np.zeros((H + 1, 4), order="F"); ub = np.zeros((H, 2), order="F")
+    c = ctypes.c_double(); a = ctypes.c_double()
+    st = lib().oracle_two_link_forward_pass(H, _p(x), _p(u), _p(xt), _p(d), _p(K), ctypes.c_double(prev_cost), jmax,
+                                            _p(xb), _p(ub), ctypes.byref(c), ctypes.byref(a))
+    return xb, ub, c.value, a.value, st
+
+
+def rollout_candidate(x, u, d, K, alpha, x_traj=None):
+    u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 4)); d = _f(d, (H, 2)); K = _f(K, (H, 2, 4))
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 4))
+    xb = np.zeros((H + 1, 4), order="F"); ub = np.zeros((H, 2), order="F")
+    c = lib().oracle_two_link_rollout_candidate(H, _p(x), _p(u), _p(xt), _p(d), _p(K), ctypes.c_double(alpha),
+                                                _p(xb), _p(ub))
+    return xb, ub, c
+
+
+def fit(x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, reg=0.01, jmax=32, max_dump=0):
+    """Returns dict(x,u,cost,alpha,du2,iters,converged,status[,dump_*])."""
+    u = _f(u_init).copy(order="F"); H = u.shape[0]; x = _f(x_init, (H + 1, 4)).copy(order="F")
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 4))
+    cost = np.full(max_iter, np.nan); alpha = np.full(max_iter, np.nan); du2 = np.full(max_iter, np.nan)
+    it = ctypes.c_int32(); cv = ctypes.c_int32()
+    dd = dK = dx = du = None
+    if max_dump > 0:
+        dd = np.zeros((H, 2, max_dump), order="F"); dK = np.zeros((H, 2, 4, max_dump), order="F")
+        dx = np.zeros((H + 1, 4, max_dump), order="F"); du = np.zeros((H, 2, max_dump), order="F")
+    st = lib().oracle_two_link_fit(H, _p(x), _p(u), _p(xt), max_iter, ctypes.c_double(tol), ctypes.c_double(reg), jmax,
+                                   _p(cost), _p(alpha), _p(du2), ctypes.byref(it), ctypes.byref(cv), max_dump,
+                                   _p(dd), _p(dK), _p(dx), _p(du))
+    out = dict(x=x, u=u, cost=cost[: it.value], alpha=alpha[: it.value], du2=du2[: it.value], iters=it.value,
+               converged=bool(cv.value), status=st)
+    if max_dump > 0:
+        out.update(dump_duff=dd, dump_K=dK, dump_xbar=dx, dump_ubar=du)
+    return out
+
+
+def fit_batch(x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, reg=0.01, jmax=32, nthreads=1, traces=True):
+    """x_init (N,4,B), u_init (H,2,B) Fortran-ordered.  Returns dict."""
+    u = _f(u_init).copy(order="F"); H, _, B = u.shape
+    x = _f(x_init, (H + 1, 4, B)).copy(order="F")
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 4, B))
+    cost = alpha = du2 = None
+    if traces:
+        cost = np.full((max_iter, B), np.nan, order="F"); alpha = np.full((max_iter, B), np.nan, order="F")
+        du2 = np.full((max_iter, B), np.nan, order="F")
+    iters = np.zeros(B, dtype=np.int32); conv = np.zeros(B, dtype=np.int32); status = np.zeros(B, dtype=np.int32)
+    lib().oracle_two_link_fit_batch(B, H, _p(x), _p(u), _p(xt), max_iter, ctypes.c_double(tol), ctypes.c_double(reg),
+                                    jmax, nthreads, _p(cost), _p(alpha), _p(du2),
+                                    iters.ctypes.data_as(_ip), conv.ctypes.data_as(_ip), status.ctypes.data_as(_ip))
+    return dict(x=x, u=u, cost=cost, alpha=alpha, du2=du2, iters=iters, converged=conv.astype(bool), status=status)
+
+
+def lq32_backward_pass(A, B, Q, R, Qf, x, u, reg=0.01):
+    u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 3))
+    d = np.zeros((H, 2), order="F"); K = np.zeros((H, 2, 3), order="F")
+    st = lib().oracle_lq32_backward_pass(H, _p(_f(A)), _p(_f(B)), _p(_f(Q)), _p(_f(R)), _p(_f(Qf)), _p(x), _p(u),
+                                         ctypes.c_double(reg), _p(d), _p(K))
+    return d, K, st
+
+
+def lq32_fit(A, B, Q, R, Qf, x, u, max_iter=10, tol=1e-6, reg=0.01):
+    u = _f(u).copy(order="F"); H = u.shape[0]; x = _f(x, (H + 1, 3)).copy(order="F")
+    cost = np.full(max_iter, np.nan); it = ctypes.c_int32()
+    st = lib().oracle_lq32_fit(H, _p(_f(A)), _p(_f(B)), _p(_f(Q)), _p(_f(R)), _p(_f(Qf)), _p(x), _p(u), max_iter,
+                               ctypes.c_double(tol), ctypes.c_double(reg), _p(cost), ctypes.byref(it))
+    return x, u, cost[: it.value], it.value, st
+
+
+def hardware_threads():
+    return int(lib().oracle_hardware_threads())

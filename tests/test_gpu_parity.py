@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Tolerances are BASELINE.json's: per-iterate costs, gains and
+final trajectories within 1e-9 relative; converged cost within 1e-8."""
+import os
+
+import numpy as np
+import pytest
+
+import ilqr_b200
+from ilqr_b200 import _abi
+from helpers import RTOL, RTOL_CONVERGED_COST, config2_batch, rel_err, rel_err_per_traj, stress_batch
+from oracle import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _solver(H, B, **kw):
+    return ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, B, **kw))
+
+
+@pytest.mark.parametrize("B,H", [(1, 200), (33, 200), (64, 37), (5, 1)])
+def test_backward_pass_gains(B, H):
+    """δuff, K of one backward pass (src/backward_pass.jl:324-357), ragged batch sizes, H=1 edge."""
+    _, x, u = config2_batch(B, H, seed=B + H)
+    rng = np.random.default_rng(7)
+    u = np.asfortranarray(u + 0.3 * rng.normal(size=u.shape))
+    for b in range(B):
+        x[:, :, b] = orc.rollout(x[0, :, b], u[:, :, b])
+    with _solver(H, B) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        d, K, st = s.download(_abi.DUFF), s.download(_abi.K), s.download(_abi.STATUS)
+    assert not st.any()
+    for b in range(B):
+        d0, K0, st0 = orc.backward_pass(x[:, :, b], u[:, :, b])
+        assert rel_err(d[:, :, b], d0) < RTOL and rel_err(K[:, :, :, b], K0) < RTOL
+
+
+def test_mirror_functions_single_trajectory():
+    """backward_pass / forward_pass with the reference's own argument lists, B = 1."""
+    H = 120
+    _, x, u = config2_batch(1, H, seed=5)
+    x, u = x[:, :, 0], u[:, :, 0]
+    p = ilqr_b200.two_link_problem(H)
+    d, K = ilqr_b200.backward_pass(x, u, p)
+    d0, K0, _ = orc.backward_pass(x, u)
+    assert d.shape == (H, 2) and K.shape == (H, 2, 4)
+    assert rel_err(d, d0) < RTOL and rel_err(K, K0) < RTOL
+    xb, ub, c = ilqr_b200.forward_pass(x, u, np.zeros_like(x), d0, K0, np.inf, p)
+    xb0, ub0, c0, a0, _ = orc.forward_pass(x, u, d0, K0, np.inf)
+    assert rel_err(xb, xb0) < RTOL and rel_err(ub, ub0) < RTOL and abs(c - c0) < RTOL * abs(c0)
+
+
+def test_forward_pass_line_search_and_x_traj():
+    """Forward pass on inputs where α = ½ is selected, with a non-zero x_traj (src/forward_pass.jl:55-93,190)."""
+    B, H = 24, 200
+    _, x, u = stress_batch(B, H, seed=2)
+    rng = np.random.default_rng(3)
+    xt = np.asfortranarray(0.05 * rng.normal(size=x.shape))
+    gains = [orc.backward_pass(x[:, :, b], u[:, :, b]) for b in range(B)]
+    d = np.asfortranarray(np.stack([g[0] for g in gains], axis=-1))
+    K = np.asfortranarray(np.stack([g[1] for g in gains], axis=-1))
+    # prev_cost = cost of the α=1 candidate ⇒ α=1 is rejected (Δ = 0 is not > 0) and the halving branch runs
+    prev = np.array([orc.rollout_candidate(x[:, :, b], u[:, :, b], d[:, :, b], K[:, :, :, b], 1.0, xt[:, :, b])[2]
+                     for b in range(B)])
+    with _solver(H, B) as s:
+        s.upload(x, u, xt)
+        s.upload_gains(d, K)
+        s.forward_pass(prev)
+        xb, ub = s.download(_abi.XBAR), s.download(_abi.UBAR)
+        c, a, du2 = s.download(_abi.NEW_COST), s.download(_abi.ALPHA), s.download(_abi.DU2)
+    n_ls = 0
+    for b in range(B):
+        xb0, ub0, c0, a0, st0 = orc.forward_pass(x[:, :, b], u[:, :, b], d[:, :, b], K[:, :, :, b], prev[b], 32, xt[:, :, b])
+        if st0 & 4:
+            assert a[b] == 0.0 and np.isnan(c[b])
+            continue
+        assert a[b] == a0, (b, a[b], a0)
+        n_ls += a0 < 1.0
+        assert rel_err(xb[:, :, b], xb0) < RTOL and rel_err(ub[:, :, b], ub0) < RTOL
+        assert abs(c[b] - c0) < RTOL * abs(c0)
+        assert abs(du2[b] - np.sum((ub0 - u[:, :, b]) ** 2)) < 1e-9 * max(du2[b], 1e-30)
+    assert n_ls > 0
+
+
+def test_fit_config2_per_iterate(tmp_path):
+    """fit on config-2 inputs: per-iteration cost / α / du2 traces, iteration counts, returned iterate."""
+    B, H, MAXIT = 48, 200, 100
+    _, x, u = config2_batch(B, H, seed=0)
+    ref = orc.fit_batch(x, u, max_iter=MAXIT, nthreads=os.cpu_count() or 1)
+    with _solver(H, B, trace_iters=MAXIT) as s:
+        s.upload(x, u)
+        s.fit(MAXIT, 1e-6)
+        xs, us = s.download(_abi.X), s.download(_abi.U)
+        ct, at, dt2 = s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE), s.download(_abi.DU2_TRACE)
+        it, st = s.download(_abi.ITERS), s.download(_abi.STATUS)
+    decisions = int(np.sum(it != ref["iters"]))
+    assert decisions == 0, "iteration-count (branch decision) mismatches: %d" % decisions
+    for b in range(B):
+        n = it[b]
+        assert np.allclose(ct[:n, b], ref["cost"][:n, b], rtol=RTOL, atol=0)
+        assert np.array_equal(at[:n, b], ref["alpha"][:n, b])
+        assert np.allclose(dt2[:n, b], ref["du2"][:n, b], rtol=1e-6, atol=1e-12)
+        assert np.all(np.isnan(ct[n:, b]))
+        conv = bool(st[b] & _abi.STATUS_CONVERGED)
+        assert conv == bool(ref["converged"][b]) and bool(st[b] & _abi.STATUS_MAX_ITER) == (not conv)
+        assert abs(ct[n - 1, b] - ref["cost"][n - 1, b]) < RTOL_CONVERGED_COST * abs(ref["cost"][n - 1, b])
+    assert rel_err_per_traj(xs, ref["x"]).max() < RTOL and rel_err_per_traj(us, ref["u"]).max() < RTOL
+
+
+def test_fit_stress_line_search_per_iterate():
+    """Same on the stress distribution, where α = ½ is accepted in many iterations."""
+    B, H, MAXIT = 16, 200, 60
+    _, x, u = stress_batch(B, H, seed=4)
+    ref = orc.fit_batch(x, u, max_iter=MAXIT, nthreads=os.cpu_count() or 1)
+    assert np.nansum(ref["alpha"] < 1) > 0
+    with _solver(H, B, trace_iters=MAXIT) as s:
+        s.upload(x, u)
+        s.fit(MAXIT, 1e-6)
+        xs, us = s.download(_abi.X), s.download(_abi.U)
+        ct, at = s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE)
+        it = s.download(_abi.ITERS)
+    assert np.array_equal(it, ref["iters"])
+    for b in range(B):
+        n = it[b]
+        assert np.array_equal(at[:n, b], ref["alpha"][:n, b])
+        assert np.allclose(ct[:n, b], ref["cost"][:n, b], rtol=RTOL, atol=0)
+    assert rel_err_per_traj(xs, ref["x"]).max() < RTOL and rel_err_per_traj(us, ref["u"]).max() < RTOL
+
+
+def test_stepwise_host_controlled_loop_equals_fit():
+    """backward / forward / commit driven from the host (what the Julia `fit` loop does) == ilqr_fit,
+    and per-iterate gains / candidates equal the golden fixture."""
+    g = np.load(os.path.join(GOLD, "two_link_H50.npz"))
+    x, u = np.asfortranarray(g["x_init"]), np.asfortranarray(g["u_init"])
+    H, B = u.shape[0], u.shape[2]
+    nd = g["dump_duff"].shape[2]
+    with _solver(H, B) as s:
+        s.upload(x, u)
+        for i in range(int(g["max_iter"])):
+            s.backward_pass()
+            if i < nd:
+                act = s.download(_abi.ACTIVE).astype(bool)
+                d, K = s.download(_abi.DUFF), s.download(_abi.K)
+                for b in np.flatnonzero(act):
+                    assert rel_err(d[:, :, b], g["dump_duff"][:, :, i, b]) < RTOL
+                    assert rel_err(K[:, :, :, b], g["dump_K"][:, :, :, i, b]) < RTOL
+            s.forward_pass()
+            if i < nd:
+                xb, ub = s.download(_abi.XBAR), s.download(_abi.UBAR)
+                for b in np.flatnonzero(act):
+                    assert rel_err(xb[:, :, b], g["dump_xbar"][:, :, i, b]) < RTOL
+                    assert rel_err(ub[:, :, b], g["dump_ubar"][:, :, i, b]) < RTOL
+            if s.commit(float(g["tol"])) == 0:
+                break
+        xs, us, it = s.download(_abi.X), s.download(_abi.U), s.download(_abi.ITERS)
+    assert np.array_equal(it, g["iters"])
+    assert rel_err_per_traj(xs, g["x"]).max() < RTOL and rel_err_per_traj(us, g["u"]).max() < RTOL
+    x2, u2 = ilqr_b200.fit(x, u, ilqr_b200.two_link_problem(H), max_iter=int(g["max_iter"]), tol=float(g["tol"]))
+    assert np.array_equal(x2, xs) and np.array_equal(u2, us)
+
+
+def test_upload_x0_rollout_and_device_upload():
+    import torch
+    B, H = 40, 90
+    x0, x, u = config2_batch(B, H, seed=9)
+    with _solver(H, B) as s:
+        s.upload_x0(np.asfortranarray(x0.T), u)
+        xs = s.download(_abi.X)
+        assert rel_err(xs, x) < 1e-12
+        tx = torch.from_numpy(np.ascontiguousarray(np.transpose(x, (2, 1, 0)))).cuda()   # [B][n][N] == Fortran [N,n,B]
+        tu = torch.from_numpy(np.ascontiguousarray(np.transpose(u, (2, 1, 0)))).cuda()
+        s.upload_device(tx.data_ptr(), tu.data_ptr())
+        assert np.array_equal(s.download(_abi.X), x) and np.array_equal(s.download(_abi.U), u)
+        out = torch.empty_like(tx)
+        s.download_device(_abi.X, out.data_ptr())
+        assert torch.equal(out, tx)
+
+
+def test_full_size_properties():
+    """BASELINE config-2 size (B = 65,536, H = 200): size-independent properties instead of the oracle —
+    costs strictly decrease per trajectory, a sub-sample matches the oracle, re-solving from the
+    solution converges immediately with the same cost (idempotence), batch order does not matter."""
+    B, H = 65536, 200
+    rng = np.random.default_rng(0)
+    x0 = np.asfortranarray(rng.random((B, 4)).T)
+    u = np.zeros((H, 2, B), order="F")
+    with _solver(H, B, trace_iters=100) as s:
+        s.upload_x0(x0, u)
+        xin = s.download(_abi.X)
+        s.fit(100, 1e-6)
+        ct, it, st = s.download(_abi.COST_TRACE), s.download(_abi.ITERS), s.download(_abi.STATUS)
+        xs, us = s.download(_abi.X), s.download(_abi.U)
+        assert not np.any(st & (1 | 2 | 4 | 8))
+        d = np.diff(ct, axis=0)
+        assert np.all((d < 0) | np.isnan(d))
+        sub = rng.choice(B, 24, replace=False)
+        ref = orc.fit_batch(xin[:, :, sub], u[:, :, sub], nthreads=os.cpu_count() or 1)
+        assert np.array_equal(it[sub], ref["iters"])
+        assert rel_err_per_traj(xs[:, :, sub], ref["x"]).max() < RTOL
+        final = ct[it - 1, np.arange(B)]
+        assert np.allclose(final[sub], ref["cost"][ref["iters"] - 1, np.arange(24)], rtol=RTOL_CONVERGED_COST)
+        # permutation invariance on a slice
+        perm = rng.permutation(4096)
+    with _solver(H, 4096) as s2:
+        s2.upload(xin[:, :, :4096][:, :, perm], u[:, :, :4096])
+        s2.fit(100, 1e-6)
+        assert np.array_equal(s2.download(_abi.X), xs[:, :, :4096][:, :, perm])
+        assert np.array_equal(s2.download(_abi.ITERS), it[:4096][perm])
