@@ -5,6 +5,7 @@
 // every numerical result comes from the CUDA kernels or the call fails.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -34,6 +35,9 @@ struct ilqr_handle {
   // cumulative profile since the last upload
   double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int32_t n_active_host = 0;   // active trajectories at the next launch (host copy)
+  bool compaction = true;      // retire + re-pack finished trajectories between iterations
+  double* ab_scratch = nullptr; // [H*20][S] linearisations for the split backward pass (lazy)
+  int32_t split_below = 20000; // use the split backward pass when nslots <= this
   bool pend_bwd = false, pend_fwd = false;
   std::string err;
 };
@@ -71,6 +75,10 @@ void free_all(ilqr_handle* h) {
   cudaFree(s.prev_cost); cudaFree(s.new_cost); cudaFree(s.alpha); cudaFree(s.du2);
   cudaFree(s.cost_trace); cudaFree(s.alpha_trace); cudaFree(s.du2_trace);
   cudaFree(s.status); cudaFree(s.iters); cudaFree(s.active); cudaFree(s.cur); cudaFree(s.bar); cudaFree(s.n_active);
+  cudaFree(s.traj); cudaFree(s.r_prev_cost); cudaFree(s.r_new_cost); cudaFree(s.r_alpha); cudaFree(s.r_du2);
+  cudaFree(s.r_status); cudaFree(s.r_iters); cudaFree(s.r_active);
+  cudaFree(s.retire_list); cudaFree(s.move_src); cudaFree(s.move_dst); cudaFree(s.n_move);
+  cudaFree(h->ab_scratch);
   cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
   if (h->pinned_i32) cudaFreeHost(h->pinned_i32);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -88,9 +96,10 @@ int32_t ensure_xtraj(ilqr_handle* h) {
 // after the TF staging buffers hold x_init/u_init (and optionally x_traj in stage_big? no: separate pass)
 int32_t finish_upload(ilqr_handle* h) {
   const ilqr_problem& p = h->prob;
+  h->st.nslots = p.B;
   launch_reset_state(h->st, h->stream);
-  launch_tf_to_bf(h->stage_x, h->st.x[0], p.B, p.H + 1, p.n, h->st.S, h->stream);
-  launch_tf_to_bf(h->stage_u, h->st.u[0], p.B, p.H, p.m, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_x, h->st.x[0], nullptr, p.B, p.H + 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream);
   h->launches += 3;
   if (int32_t rc = check_launch(h, "upload kernels")) return rc;
   h->loaded = true; h->have_gains = false; h->have_candidate = false;
@@ -123,7 +132,7 @@ int32_t upload_xtraj(ilqr_handle* h, const double* src, cudaMemcpyKind kind) {
   if (int32_t rc = ensure_xtraj(h)) return rc;
   // reuse stage_x as the TF staging for x_traj (before x_init lands there)
   CK(h, cudaMemcpyAsync(h->stage_x, src, sizeof(double) * N * p.n * p.B, kind, h->stream));
-  launch_tf_to_bf(h->stage_x, h->st.xtraj, p.B, p.H + 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_x, h->st.xtraj, nullptr, p.B, p.H + 1, p.n, h->st.S, h->stream);
   h->launches += 1;
   return check_launch(h, "x_traj transpose");
 }
@@ -196,7 +205,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   DevState& s = h->st;
   const size_t N = p->H + 1, H = p->H, n = p->n, m = p->m;
   s.S = ((int64_t)p->B + 31) / 32 * 32;
-  s.nslots = p->B; s.H = p->H; s.n = p->n; s.m = p->m; s.n_alpha = p->n_alpha; s.trace_iters = p->trace_iters;
+  s.nslots = p->B; s.B = p->B; s.H = p->H; s.n = p->n; s.m = p->m; s.n_alpha = p->n_alpha; s.trace_iters = p->trace_iters;
   s.reg = p->reg;
   const size_t S = (size_t)s.S;
   for (int i = 0; i < 2; ++i) { CKC(dalloc(&s.x[i], N * n * S)); CKC(dalloc(&s.u[i], H * m * S)); }
@@ -208,8 +217,12 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   }
   CKC(dalloc(&s.status, S)); CKC(dalloc(&s.iters, S)); CKC(dalloc(&s.active, S)); CKC(dalloc(&s.cur, S));
   CKC(dalloc(&s.bar, S)); CKC(dalloc(&s.n_active, 1));
+  CKC(dalloc(&s.traj, S)); CKC(dalloc(&s.r_prev_cost, S)); CKC(dalloc(&s.r_new_cost, S)); CKC(dalloc(&s.r_alpha, S));
+  CKC(dalloc(&s.r_du2, S)); CKC(dalloc(&s.r_status, S)); CKC(dalloc(&s.r_iters, S)); CKC(dalloc(&s.r_active, S));
+  CKC(dalloc(&s.retire_list, S)); CKC(dalloc(&s.move_src, S)); CKC(dalloc(&s.move_dst, S)); CKC(dalloc(&s.n_move, 1));
   CKC(dalloc(&h->stage_x, N * n * (size_t)p->B)); CKC(dalloc(&h->stage_u, H * m * (size_t)p->B));
   CKC(dalloc(&h->scratch_b, S));
+  s.out_x = h->stage_x; s.out_u = h->stage_u;
   CKC(cudaHostAlloc((void**)&h->pinned_i32, 64, cudaHostAllocDefault));
   // padded slots must never hold NaN garbage that a kernel could trip on
   for (int i = 0; i < 2; ++i) { CKC(cudaMemsetAsync(s.x[i], 0, sizeof(double) * N * n * S, h->stream));
@@ -219,6 +232,8 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   launch_reset_state(s, h->stream);
   CKC(cudaStreamSynchronize(h->stream));
 #undef CKC
+  if (const char* e = getenv("ILQR_SPLIT_BELOW")) h->split_below = atoi(e);
+  if (const char* e = getenv("ILQR_COMPACTION")) h->compaction = atoi(e) != 0;
   h->mp.alpha = p->model_params[0]; h->mp.beta = p->model_params[1]; h->mp.delta = p->model_params[2];
   h->mp.dt = p->dt; h->mp.twobeta = 2 * p->model_params[1];
   for (int i = 0; i < kMaxN; ++i) { h->cp.x_target[i] = p->x_target[i]; h->cp.w_x[i] = p->w_x[i]; h->cp.w_xf[i] = p->w_xf[i]; }
@@ -254,9 +269,10 @@ int32_t ilqr_upload_device(ilqr_handle* h, const double* d_x, const double* d_u,
   const ilqr_problem& p = h->prob;
   CK(h, cudaSetDevice(h->device));
   if (int32_t rc = upload_xtraj(h, d_xt, cudaMemcpyDeviceToDevice)) return rc;
+  h->st.nslots = p.B;
   launch_reset_state(h->st, h->stream);
-  launch_tf_to_bf(d_x, h->st.x[0], p.B, p.H + 1, p.n, h->st.S, h->stream);
-  launch_tf_to_bf(d_u, h->st.u[0], p.B, p.H, p.m, h->st.S, h->stream);
+  launch_tf_to_bf(d_x, h->st.x[0], nullptr, p.B, p.H + 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(d_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream);
   h->launches += 3;
   if (int32_t rc = check_launch(h, "upload_device kernels")) return rc;
   h->loaded = true; h->have_gains = false; h->have_candidate = false;
@@ -274,9 +290,10 @@ int32_t ilqr_upload_x0(ilqr_handle* h, const double* x0, const double* u_init, c
   // x0[n,B] is a TF array with T = 1: stage it in stage_x, transpose into x[1] (free scratch), roll out into x[0]
   CK(h, cudaMemcpyAsync(h->stage_x, x0, sizeof(double) * p.n * p.B, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * p.B, cudaMemcpyHostToDevice, h->stream));
+  h->st.nslots = p.B;
   launch_reset_state(h->st, h->stream);
-  launch_tf_to_bf(h->stage_x, h->st.x[1], p.B, 1, p.n, h->st.S, h->stream);
-  launch_tf_to_bf(h->stage_u, h->st.u[0], p.B, p.H, p.m, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_x, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream);
   launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
   h->launches += 4;
   if (int32_t rc = check_launch(h, "upload_x0 kernels")) return rc;
@@ -294,11 +311,10 @@ int32_t ilqr_upload_gains(ilqr_handle* h, const double* duff, const double* K) {
   const size_t H = p.H, n = p.n, m = p.m, B = p.B;
   CK(h, cudaSetDevice(h->device));
   if (!h->stage_big) CK(h, dalloc(&h->stage_big, H * m * n * B));
-  // stage_u currently mirrors nothing the solver still needs (u lives in BF buffers)
-  CK(h, cudaMemcpyAsync(h->stage_u, duff, sizeof(double) * H * m * B, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->stage_big, duff, sizeof(double) * H * m * B, cudaMemcpyHostToDevice, h->stream));
+  launch_tf_to_bf(h->stage_big, h->st.duff, h->st.traj, h->st.nslots, p.H, p.m, h->st.S, h->stream);
   CK(h, cudaMemcpyAsync(h->stage_big, K, sizeof(double) * H * m * n * B, cudaMemcpyHostToDevice, h->stream));
-  launch_tf_to_bf(h->stage_u, h->st.duff, p.B, p.H, p.m, h->st.S, h->stream);
-  launch_tf_to_bf(h->stage_big, h->st.K, p.B, p.H, p.m * p.n, h->st.S, h->stream);
+  launch_tf_to_bf(h->stage_big, h->st.K, h->st.traj, h->st.nslots, p.H, p.m * p.n, h->st.S, h->stream);
   h->launches += 2;
   if (int32_t rc = check_launch(h, "upload_gains kernels")) return rc;
   h->have_gains = true;
@@ -308,10 +324,13 @@ int32_t ilqr_upload_gains(ilqr_handle* h, const double* duff, const double* K) {
 
 static int32_t backward_async(ilqr_handle* h) {
   if (!h->loaded) return fail(h, ILQR_ERR_STATE, "backward_pass before upload");
+  const bool split = h->st.nslots <= h->split_below;
+  if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
   cudaEventRecord(h->ev[0], h->stream);
-  launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
+  if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->stream);
+  else launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[1], h->stream);
-  h->launches += 1;
+  h->launches += split ? 2 : 1;
   h->have_gains = true; h->pend_bwd = true;
   return check_launch(h, "backward kernel");
 }
@@ -338,8 +357,17 @@ static int32_t read_n_active(ilqr_handle* h, int32_t* n_active) {
   CK(h, cudaMemcpyAsync(h->pinned_i32, h->st.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   accumulate_profile(h);
-  h->n_active_host = h->pinned_i32[0];
-  if (n_active) *n_active = h->pinned_i32[0];
+  const int32_t na = h->pinned_i32[0];
+  h->n_active_host = na;
+  if (n_active) *n_active = na;
+  // retire + re-pack once enough slots have finished to free whole warps
+  const int32_t finished = h->st.nslots - na;
+  if (h->compaction && finished > 0 && (na == 0 || finished >= 32) && finished * 16 >= h->st.nslots) {
+    launch_compact(h->st, na, h->stream);
+    h->st.nslots = na;
+    h->launches += 3;
+    return check_launch(h, "compaction kernels");
+  }
   return ILQR_OK;
 }
 
@@ -374,9 +402,12 @@ int32_t ilqr_commit(ilqr_handle* h, double tol, int32_t* n_active) {
 int32_t ilqr_set_active(ilqr_handle* h, const int32_t* active) {
   if (!h || !active) return fail(h, ILQR_ERR_INVALID, "null argument");
   CK(h, cudaSetDevice(h->device));
-  CK(h, cudaMemcpyAsync(h->st.active, active, sizeof(int32_t) * h->prob.B, cudaMemcpyHostToDevice, h->stream));
+  // scratch_b ([S] doubles) is large enough for [B] int32
+  CK(h, cudaMemcpyAsync(h->scratch_b, active, sizeof(int32_t) * h->prob.B, cudaMemcpyHostToDevice, h->stream));
+  launch_set_active_by_traj(h->st, (const int32_t*)h->scratch_b, h->stream);
+  h->launches += 1;
   CK(h, cudaStreamSynchronize(h->stream));
-  return ILQR_OK;
+  return check_launch(h, "set_active kernel");
 }
 
 int32_t ilqr_iterate(ilqr_handle* h, double tol, int32_t* n_active) {
@@ -390,11 +421,17 @@ int32_t ilqr_iterate(ilqr_handle* h, double tol, int32_t* n_active) {
 
 static int32_t fit_loop(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_run) {
   int32_t it = 0, na = h->prob.B;
+  static const bool trace_timing = getenv("ILQR_TRACE_TIMING") != nullptr;
   for (it = 1; it <= max_iter; ++it) {
+    const int32_t na_before = h->n_active_host, slots_before = h->st.nslots;
+    const double b0 = h->prof[0], f0 = h->prof[1];
     if (int32_t rc = backward_async(h)) return rc;
     if (int32_t rc = forward_async(h)) return rc;
     if (int32_t rc = commit_async(h, tol)) return rc;
     if (int32_t rc = read_n_active(h, &na)) return rc;
+    if (trace_timing)
+      fprintf(stderr, "[ilqr] iter %3d active %6d slots %6d bwd %.3f ms fwd %.3f ms\n", it, na_before, slots_before,
+              h->prof[0] - b0, h->prof[1] - f0);
     if (na == 0) break;
   }
   if (na > 0) {
@@ -402,6 +439,8 @@ static int32_t fit_loop(ilqr_handle* h, int32_t max_iter, double tol, int32_t* i
     h->launches += 1;
     it = max_iter;
   }
+  launch_flush_live(h->st, true, h->stream);   // every result now sits in the per-trajectory mirrors
+  h->launches += 3;
   if (iters_run) *iters_run = it;
   return check_launch(h, "fit");
 }
@@ -416,49 +455,59 @@ int32_t ilqr_fit(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_ru
   return ILQR_OK;
 }
 
-// Stage `which` in boundary layout on device; returns pointer + byte size.
+// Stage `which` in boundary layout (indexed by original trajectory) on device; returns pointer + byte size.
+// Finished trajectories were retired to the mirrors already; live slots are flushed here.
 static int32_t stage_array(ilqr_handle* h, int32_t which, const void** d_ptr, size_t* bytes) {
   const ilqr_problem& p = h->prob;
   const DevState& s = h->st;
   const size_t B = p.B, N = p.H + 1, H = p.H, n = p.n, m = p.m;
+  auto need_big = [&]() -> int32_t {
+    if (!h->stage_big) CK(h, dalloc(&h->stage_big, H * m * n * B));
+    return ILQR_OK;
+  };
   switch (which) {
     case ILQR_X:
-    case ILQR_XBAR:
-      launch_bf_to_tf(s.x[0], s.x[1], which == ILQR_X ? s.cur : s.bar, h->stage_x, p.B, p.H + 1, p.n, s.S, h->stream);
-      h->launches++; *d_ptr = h->stage_x; *bytes = sizeof(double) * N * n * B; break;
+      launch_bf_to_tf(s.x[0], s.x[1], s.cur, s.out_x, s.traj, s.nslots, p.H + 1, p.n, s.S, h->stream);
+      h->launches++; *d_ptr = s.out_x; *bytes = sizeof(double) * N * n * B; break;
     case ILQR_U:
+      launch_bf_to_tf(s.u[0], s.u[1], s.cur, s.out_u, s.traj, s.nslots, p.H, p.m, s.S, h->stream);
+      h->launches++; *d_ptr = s.out_u; *bytes = sizeof(double) * H * m * B; break;
+    case ILQR_XBAR:   // valid for live slots between forward_pass and commit; zeros elsewhere
     case ILQR_UBAR:
-      launch_bf_to_tf(s.u[0], s.u[1], which == ILQR_U ? s.cur : s.bar, h->stage_u, p.B, p.H, p.m, s.S, h->stream);
-      h->launches++; *d_ptr = h->stage_u; *bytes = sizeof(double) * H * m * B; break;
     case ILQR_DUFF:
-      launch_bf_to_tf(s.duff, nullptr, nullptr, h->stage_u, p.B, p.H, p.m, s.S, h->stream);
-      h->launches++; *d_ptr = h->stage_u; *bytes = sizeof(double) * H * m * B; break;
-    case ILQR_K:
-      if (!h->stage_big) CK(h, dalloc(&h->stage_big, H * m * n * B));
-      launch_bf_to_tf(s.K, nullptr, nullptr, h->stage_big, p.B, p.H, p.m * p.n, s.S, h->stream);
-      h->launches++; *d_ptr = h->stage_big; *bytes = sizeof(double) * H * m * n * B; break;
-    case ILQR_NEW_COST: *d_ptr = s.new_cost; *bytes = sizeof(double) * B; break;
-    case ILQR_PREV_COST: *d_ptr = s.prev_cost; *bytes = sizeof(double) * B; break;
-    case ILQR_ALPHA: *d_ptr = s.alpha; *bytes = sizeof(double) * B; break;
-    case ILQR_DU2: *d_ptr = s.du2; *bytes = sizeof(double) * B; break;
+    case ILQR_K: {
+      if (int32_t rc = need_big()) return rc;
+      const int T = which == ILQR_XBAR ? p.H + 1 : p.H;
+      const int nc = which == ILQR_XBAR ? p.n : which == ILQR_K ? p.m * p.n : p.m;
+      *bytes = sizeof(double) * (size_t)T * nc * B;
+      CK(h, cudaMemsetAsync(h->stage_big, 0, *bytes, h->stream));
+      if (which == ILQR_XBAR) launch_bf_to_tf(s.x[0], s.x[1], s.bar, h->stage_big, s.traj, s.nslots, T, nc, s.S, h->stream);
+      else if (which == ILQR_UBAR) launch_bf_to_tf(s.u[0], s.u[1], s.bar, h->stage_big, s.traj, s.nslots, T, nc, s.S, h->stream);
+      else if (which == ILQR_DUFF) launch_bf_to_tf(s.duff, nullptr, nullptr, h->stage_big, s.traj, s.nslots, T, nc, s.S, h->stream);
+      else launch_bf_to_tf(s.K, nullptr, nullptr, h->stage_big, s.traj, s.nslots, T, nc, s.S, h->stream);
+      h->launches++; *d_ptr = h->stage_big; break;
+    }
+    case ILQR_NEW_COST: case ILQR_PREV_COST: case ILQR_ALPHA: case ILQR_DU2:
+    case ILQR_STATUS: case ILQR_ITERS: case ILQR_ACTIVE:
+      launch_flush_live(s, false, h->stream);
+      h->launches++;
+      *bytes = (which >= ILQR_STATUS ? sizeof(int32_t) : sizeof(double)) * B;
+      *d_ptr = which == ILQR_NEW_COST ? (const void*)s.r_new_cost : which == ILQR_PREV_COST ? (const void*)s.r_prev_cost
+             : which == ILQR_ALPHA ? (const void*)s.r_alpha : which == ILQR_DU2 ? (const void*)s.r_du2
+             : which == ILQR_STATUS ? (const void*)s.r_status : which == ILQR_ITERS ? (const void*)s.r_iters
+             : (const void*)s.r_active;
+      break;
     case ILQR_COST_TRACE:
     case ILQR_ALPHA_TRACE:
     case ILQR_DU2_TRACE: {
       if (p.trace_iters <= 0) return fail(h, ILQR_ERR_INVALID, "trace_iters == 0");
+      if ((size_t)p.trace_iters > H * m * n) return fail(h, ILQR_ERR_INVALID, "trace_iters too large to stage");
+      if (int32_t rc = need_big()) return rc;
       const double* src = which == ILQR_COST_TRACE ? s.cost_trace : which == ILQR_ALPHA_TRACE ? s.alpha_trace : s.du2_trace;
-      // [trace_iters][S] is a BF array with ncomp = 1, T = trace_iters; fits in stage_x when trace_iters <= N*n
-      double* dst = h->stage_x;
-      if ((size_t)p.trace_iters > N * n) {
-        if (!h->stage_big) CK(h, dalloc(&h->stage_big, H * m * n * B));
-        if ((size_t)p.trace_iters > H * m * n) return fail(h, ILQR_ERR_INVALID, "trace_iters too large to stage");
-        dst = h->stage_big;
-      }
-      launch_bf_to_tf(src, nullptr, nullptr, dst, p.B, p.trace_iters, 1, s.S, h->stream);
-      h->launches++; *d_ptr = dst; *bytes = sizeof(double) * (size_t)p.trace_iters * B; break;
+      // [trace_iters][S] indexed by trajectory is a BF array with ncomp = 1, T = trace_iters
+      launch_bf_to_tf(src, nullptr, nullptr, h->stage_big, nullptr, p.B, p.trace_iters, 1, s.S, h->stream);
+      h->launches++; *d_ptr = h->stage_big; *bytes = sizeof(double) * (size_t)p.trace_iters * B; break;
     }
-    case ILQR_STATUS: *d_ptr = s.status; *bytes = sizeof(int32_t) * B; break;
-    case ILQR_ITERS: *d_ptr = s.iters; *bytes = sizeof(int32_t) * B; break;
-    case ILQR_ACTIVE: *d_ptr = s.active; *bytes = sizeof(int32_t) * B; break;
     default: return fail(h, ILQR_ERR_INVALID, "unknown array id");
   }
   return check_launch(h, "download staging");
@@ -498,14 +547,11 @@ int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, c
   CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * B, cudaMemcpyHostToDevice, h->stream));
   if (int32_t rc = finish_upload(h)) return rc;
   if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;
-  const void* src; size_t bytes;
-  if (int32_t rc = stage_array(h, ILQR_X, &src, &bytes)) return rc;
-  CK(h, cudaMemcpyAsync(x_out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
-  if (int32_t rc = stage_array(h, ILQR_U, &src, &bytes)) return rc;
-  CK(h, cudaMemcpyAsync(u_out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
-  if (cost_out) CK(h, cudaMemcpyAsync(cost_out, h->st.prev_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
-  if (iters_out) CK(h, cudaMemcpyAsync(iters_out, h->st.iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
-  if (status_out) CK(h, cudaMemcpyAsync(status_out, h->st.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(x_out, h->st.out_x, sizeof(double) * N * p.n * B, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(u_out, h->st.out_u, sizeof(double) * p.H * p.m * B, cudaMemcpyDeviceToHost, h->stream));
+  if (cost_out) CK(h, cudaMemcpyAsync(cost_out, h->st.r_prev_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+  if (iters_out) CK(h, cudaMemcpyAsync(iters_out, h->st.r_iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+  if (status_out) CK(h, cudaMemcpyAsync(status_out, h->st.r_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   return ILQR_OK;
 }

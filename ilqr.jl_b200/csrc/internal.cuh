@@ -36,15 +36,26 @@ struct DevState {
   int32_t* active;
   int32_t* cur;      // which of x[2]/u[2] holds the slot's current iterate
   int32_t* bar;      // which holds the last forward-pass candidate
+  int32_t* traj;     // [S] original trajectory index living in this slot
   int32_t* n_active; // device counter written by commit
+  // per-TRAJECTORY result mirrors (index = original trajectory), written when a slot retires / is flushed
+  double* r_prev_cost; double* r_new_cost; double* r_alpha; double* r_du2;
+  int32_t* r_status; int32_t* r_iters; int32_t* r_active;
+  double* out_x;     // [B][n*N] boundary layout: final iterate of retired trajectories
+  double* out_u;     // [B][m*H]
+  // compaction work lists
+  int32_t* retire_list; int32_t* move_src; int32_t* move_dst; int32_t* n_move;
   int64_t S;         // slot stride (B rounded up to 32)
-  int32_t nslots;    // B
+  int32_t nslots;    // live slots: [0, nslots) (shrinks as finished trajectories are retired)
+  int32_t B;         // trajectories
   int32_t H, n, m, n_alpha, trace_iters;
   double reg;
 };
 
 // kernels_lpt.cu — lane-per-trajectory (throughput) mapping
 void launch_bwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
+// split backward pass (time-parallel linearisation + Riccati) for small active sets; AB: [H*20][S] scratch
+void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, double* AB, cudaStream_t s);
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0 /*[n][S] BF*/,
                                   cudaStream_t s);
@@ -53,11 +64,20 @@ void launch_finalize_max_iter(const DevState& st, cudaStream_t s);
 void launch_reset_state(const DevState& st, cudaStream_t s);
 void launch_set_prev_cost(const DevState& st, const double* d_prev, cudaStream_t s);
 
+// compaction (kernels_lpt.cu): retire finished slots to the per-trajectory mirrors, then fill the holes
+// below new_nslots with live slots from above it.
+void launch_compact(const DevState& st, int new_nslots, cudaStream_t s);
+// copy every live slot's scalars (and optionally its current iterate) to the per-trajectory mirrors
+void launch_flush_live(const DevState& st, bool with_iterates, cudaStream_t s);
+void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaStream_t s);
+
 // layout.cu — boundary (Julia, time-fastest "TF") <-> BF transposes
-// TF: src[b*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + b]
-void launch_tf_to_bf(const double* tf, double* bf, int B, int T, int ncomp, int64_t S, cudaStream_t s);
+// TF: src[t*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + s]
+// slot_traj (nullable): t = slot_traj[s] (live slots only); otherwise t = s.  nslots = number of slots moved.
+void launch_tf_to_bf(const double* tf, double* bf, const int32_t* slot_traj, int nslots, int T, int ncomp, int64_t S,
+                     cudaStream_t s);
 // sel (nullable): per-slot choice between bf0 and bf1
-void launch_bf_to_tf(const double* bf0, const double* bf1, const int32_t* sel, double* tf, int B, int T, int ncomp,
-                     int64_t S, cudaStream_t s);
+void launch_bf_to_tf(const double* bf0, const double* bf1, const int32_t* sel, double* tf, const int32_t* slot_traj,
+                     int nslots, int T, int ncomp, int64_t S, cudaStream_t s);
 
 }  // namespace ilqr

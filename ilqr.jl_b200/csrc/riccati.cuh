@@ -11,6 +11,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "fastmath.cuh"
+
 namespace ilqr {
 
 // Solve the m×m system (−Hr) X = RHS for the small m used here.
@@ -20,7 +22,7 @@ template <int M, int C>
 __device__ __forceinline__ void neg_solve(const double Hr[M][M], const double rhs[M][C], double out[M][C]) {
   if constexpr (M == 2) {
     const double det = fma(Hr[0][0], Hr[1][1], -(Hr[0][1] * Hr[1][0]));
-    const double nid = -1.0 / det;
+    const double nid = -rcp_nr(det);
     const double i00 = Hr[1][1] * nid, i01 = -Hr[0][1] * nid, i10 = -Hr[1][0] * nid, i11 = Hr[0][0] * nid;
 #pragma unroll
     for (int c = 0; c < C; ++c) {

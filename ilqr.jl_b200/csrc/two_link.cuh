@@ -16,6 +16,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "fastmath.cuh"
+
 namespace ilqr {
 
 struct TwoLinkP {
@@ -33,11 +35,11 @@ struct TLStage {
 __device__ __forceinline__ void tl_accel(const TwoLinkP& p, double th2, double w1, double w2, double u1, double u2,
                                          TLStage& o) {
   double s2, c2;
-  sincos(th2, &s2, &c2);
+  sincos_bf(th2, &s2, &c2);
   const double a = fma(p.twobeta, c2, p.alpha);
   const double b = fma(p.beta, c2, p.delta);
   const double det = fma(a, p.delta, -(b * b));
-  const double idet = 1.0 / det;
+  const double idet = rcp_nr(det);
   // h = C θ̇ = −β s₂ w₂ (w₁ + ½w₂, ½w₁)
   const double tw2 = (-p.beta * s2) * w2;
   const double h1 = tw2 * fma(0.5, w2, w1);

@@ -61,9 +61,10 @@ def test_forward_pass_line_search_and_x_traj():
     gains = [orc.backward_pass(x[:, :, b], u[:, :, b]) for b in range(B)]
     d = np.asfortranarray(np.stack([g[0] for g in gains], axis=-1))
     K = np.asfortranarray(np.stack([g[1] for g in gains], axis=-1))
-    # prev_cost = cost of the α=1 candidate ⇒ α=1 is rejected (Δ = 0 is not > 0) and the halving branch runs
+    # prev_cost a hair below the cost of the α=1 candidate ⇒ α=1 is robustly rejected (Δcost < 0) in both
+    # implementations and the halving branch runs (src/forward_pass.jl:79-82)
     prev = np.array([orc.rollout_candidate(x[:, :, b], u[:, :, b], d[:, :, b], K[:, :, :, b], 1.0, xt[:, :, b])[2]
-                     for b in range(B)])
+                     for b in range(B)]) * (1 - 1e-7)
     with _solver(H, B) as s:
         s.upload(x, u, xt)
         s.upload_gains(d, K)
@@ -159,6 +160,26 @@ def test_stepwise_host_controlled_loop_equals_fit():
     assert rel_err_per_traj(xs, g["x"]).max() < RTOL and rel_err_per_traj(us, g["u"]).max() < RTOL
     x2, u2 = ilqr_b200.fit(x, u, ilqr_b200.two_link_problem(H), max_iter=int(g["max_iter"]), tol=float(g["tol"]))
     assert np.array_equal(x2, xs) and np.array_equal(u2, us)
+
+
+def test_compaction_many_stages():
+    """Retire + re-pack runs many times on a ragged batch; every trajectory must still equal the oracle,
+    by original index, including the per-trajectory traces."""
+    B, H, MAXIT = 700, 200, 100
+    _, x, u = config2_batch(B, H, seed=21)
+    ref = orc.fit_batch(x, u, max_iter=MAXIT, nthreads=os.cpu_count() or 1)
+    assert len(np.unique(ref["iters"])) > 5
+    with _solver(H, B, trace_iters=MAXIT) as s:
+        s.upload(x, u)
+        s.fit(MAXIT, 1e-6)
+        xs, us, it, st = s.download(_abi.X), s.download(_abi.U), s.download(_abi.ITERS), s.download(_abi.STATUS)
+        ct, pc = s.download(_abi.COST_TRACE), s.download(_abi.PREV_COST)
+        assert not s.download(_abi.ACTIVE).any()
+    assert np.array_equal(it, ref["iters"])
+    assert rel_err_per_traj(xs, ref["x"]).max() < RTOL and rel_err_per_traj(us, ref["u"]).max() < RTOL
+    last = ref["cost"][ref["iters"] - 1, np.arange(B)]
+    assert np.allclose(pc, last, rtol=RTOL_CONVERGED_COST) and np.allclose(ct[it - 1, np.arange(B)], last, rtol=RTOL_CONVERGED_COST)
+    assert np.array_equal((st & _abi.STATUS_CONVERGED) != 0, ref["converged"])
 
 
 def test_upload_x0_rollout_and_device_upload():

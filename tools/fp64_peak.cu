@@ -1,0 +1,64 @@
+// fp64_peak.cu — DFMA micro-benchmark: measured FP64-pipe peak (the roofline denominator that
+// MEASURED_PEAKS.json does not carry) and the dependent-issue latency of DFMA / sincos / division.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_peak tools/fp64_peak.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int ILP>
+__global__ void dfma_throughput(double* out, int iters, double a, double b) {
+  double acc[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += acc[i];
+  if (s == 12345.678) out[0] = s;
+}
+
+__global__ void latency_kernel(double* out, long long* cycles, int iters, double a, double b, int mode) {
+  double x = a;
+  long long t0 = clock64();
+  if (mode == 0) for (int i = 0; i < iters; ++i) x = fma(x, a, b);
+  if (mode == 1) for (int i = 0; i < iters; ++i) { double s, c; sincos(x, &s, &c); x = s + c; }
+  if (mode == 2) for (int i = 0; i < iters; ++i) x = 1.0 / (x + b);
+  if (mode == 3) for (int i = 0; i < iters; ++i) x = x + b;
+  if (mode == 4) for (int i = 0; i < iters; ++i) x = x * a;
+  long long t1 = clock64();
+  out[threadIdx.x] = x;
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  double* out; cudaMalloc(&out, 1 << 20);
+  long long* cyc; cudaMalloc(&cyc, 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 1 << 14;
+  float best = 1e30f;
+  const int blocks = p.multiProcessorCount * 4, threads = 512;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    dfma_throughput<8><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double flops = 2.0 * 8 * iters * (double)blocks * threads;
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  printf("{\"device\": \"%s\", \"sms\": %d, \"fp64_dfma_tflops\": %.3f, \"ms\": %.4f, \"clock_khz_attr\": %d",
+         p.name, p.multiProcessorCount, flops / (best * 1e-3) / 1e12, best, clk);
+  const char* names[5] = {"dfma", "sincos", "div", "dadd", "dmul"};
+  for (int mode = 0; mode < 5; ++mode) {
+    latency_kernel<<<1, 32>>>(out, cyc, 4096, 0.999, 0.001, mode);
+    cudaDeviceSynchronize();
+    latency_kernel<<<1, 32>>>(out, cyc, 4096, 0.999, 0.001, mode);
+    long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    printf(", \"lat_%s_cycles\": %.1f", names[mode], c / 4096.0);
+  }
+  printf("}\n");
+  return 0;
+}
