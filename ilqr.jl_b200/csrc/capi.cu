@@ -200,6 +200,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
     }                                                                                           \
   } while (0)
   CKC(cudaSetDevice(p->device));
+  init_kernel_attributes();
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CKC(cudaEventCreate(&e));
   DevState& s = h->st;

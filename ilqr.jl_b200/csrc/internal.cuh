@@ -14,16 +14,17 @@ struct CostP {
   double x_target[kMaxN], w_x[kMaxN], w_u[kMaxM], w_xf[kMaxN];
 };
 
-// Device-resident solver state in the batch-fastest ("BF") layout used by the
+// Device-resident solver state in the [k][slot][component] layout used by the
 // lane-per-trajectory kernels: element (k, c) of trajectory-slot s lives at
-// (k*ncomp + c)*S + s, so a warp's 32 lanes (32 consecutive slots) touch one
-// contiguous 256 B line per load.
+// (k*S + s)*ncomp + c, so the slab a warp (32 consecutive slots) needs for one time
+// step is one contiguous run (a single TMA bulk copy) and a lane's own components
+// are one 128-bit-vectorisable group.
 struct DevState {
-  double* x[2];      // iterate ping-pong, [N*n][S]
-  double* u[2];      // [H*m][S]
-  double* xtraj;     // [N*n][S] or nullptr (= zeros)
-  double* duff;      // [H*m][S]
-  double* K;         // [H*m*n][S], component index i + m*j
+  double* x[2];      // iterate ping-pong, [N][S][n]
+  double* u[2];      // [H][S][m]
+  double* xtraj;     // [N][S][n] or nullptr (= zeros)
+  double* duff;      // [H][S][m]
+  double* K;         // [H][S][m*n], component index i + m*j
   double* prev_cost; // [S]
   double* new_cost;
   double* alpha;
@@ -53,6 +54,7 @@ struct DevState {
 };
 
 // kernels_lpt.cu — lane-per-trajectory (throughput) mapping
+void init_kernel_attributes();   // opt-in dynamic shared memory sizes; call once per process/device
 void launch_bwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 // split backward pass (time-parallel linearisation + Riccati) for small active sets; AB: [H*20][S] scratch
 void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, double* AB, cudaStream_t s);

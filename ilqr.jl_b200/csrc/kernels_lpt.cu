@@ -1,42 +1,95 @@
-// kernels_lpt.cu — lane-per-trajectory kernels (throughput mapping) for the
-// 2-link model, n = 4, m = 2.  One thread owns one trajectory end to end; the
-// 32 lanes of a warp own 32 consecutive trajectory slots, so every load and
-// store of the batch-fastest layout is one coalesced 256 B line and no data
-// is exchanged between lanes.  All per-timestep n×n and n×m blocks (S, A, B,
-// G, K …) live in registers.
+// kernels_lpt.cu — lane-per-trajectory kernels for the 2-link model (n = 4, m = 2).
+//
+// Mapping: one thread owns one trajectory end to end; the 32 lanes of a warp own 32 consecutive
+// trajectory slots.  Device layout is [k][slot][component] (layout.cu), so
+//   * everything a warp needs for time step k is one contiguous slab per array (x: 1 KB,
+//     u / δuff: 512 B, K: 2 KB).  One elected lane streams the slabs of the next D steps into a
+//     shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier), so no registers are
+//     spent on prefetch and the loads of step k+D are in flight during step k;
+//   * a lane's own part of a slab is a 16/32/64-byte vector (LDS.128 in, STG.128 out);
+//   * no data is exchanged between lanes; all n×n / n×m blocks (S, A, B, G, K …) stay in registers.
 //
 // Reference functions restated here (paths relative to /root/reference):
-//   backward_pass  src/backward_pass.jl:324-357  → bwd_lpt_two_link
+//   backward_pass  src/backward_pass.jl:324-357  → bwd_lpt_two_link (fused) or lin_ + ric_ (split)
 //   forward_pass   src/forward_pass.jl:55-93     → fwd_lpt_two_link
 //   total_cost     src/forward_pass.jl:182-196   (fused into the rollout)
 //   fit loop tail  src/forward_pass.jl:168-175   → commit_kernel
 #include "internal.cuh"
 #include "riccati.cuh"
+#include "tma.cuh"
 
 namespace ilqr {
 
 namespace {
 
-constexpr int NX = 4, NU = 2;
-constexpr int kBlock = 128;
+constexpr int NX = 4, NU = 2, NK = NU * NX;
+constexpr int kWarps = 4, kBlock = kWarps * 32;
+constexpr int kAB = 20;   // 12 entries of A[:,1..3] + 8 of B (split backward pass)
 
 // status bits (mirror include/ilqr_b200.h)
 constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2, ST_LS_EXHAUSTED = 4, ST_NOT_DECREASED = 8, ST_CONVERGED = 16,
                   ST_MAX_ITER = 32;
 
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+template <int C> __device__ __forceinline__ void ldv(const double* __restrict__ p, double* v) {
+#pragma unroll
+  for (int i = 0; i < C; i += 2) { const double2 t = *reinterpret_cast<const double2*>(p + i); v[i] = t.x; v[i + 1] = t.y; }
+}
+template <int C> __device__ __forceinline__ void stv(double* __restrict__ p, const double* v) {
+#pragma unroll
+  for (int i = 0; i < C; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(v[i], v[i + 1]);
+}
+
+// Which of the two iterate buffers the ACTIVE lanes of this warp read: all active trajectories flip
+// together in commit_kernel, so they share one value; take it from the first active lane.
+__device__ __forceinline__ int warp_cur(const DevState& st, int s, bool act, unsigned amask) {
+  const int mine = act ? st.cur[s] : 0;
+  return __shfl_sync(0xffffffffu, mine, __ffs(amask) - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused backward pass: linearisation + cost expansion + Riccati step per time step, k = H-1 … 0.
+// Ring: D stages of {x slab 1 KB, u slab 512 B} per warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBwdStages = 4;
+constexpr int kBwdStageDoubles = 32 * (NX + NU);
+
 __global__ void __launch_bounds__(kBlock)
 bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
                  const __grid_constant__ CostP cp) {
-  const int s = blockIdx.x * kBlock + threadIdx.x;
-  if (s >= st.nslots) return;
-  if (!st.active[s]) return;
+  __shared__ __align__(128) double ring_all[kWarps][kBwdStages][kBwdStageDoubles];
+  __shared__ __align__(8) uint64_t bars_all[kWarps][kBwdStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = (blockIdx.x * kWarps + warp) * 32, s = s0 + lane;
+  if (s0 >= st.nslots) return;
+  const bool act = s < st.nslots && st.active[s];
+  const unsigned amask = __ballot_sync(0xffffffffu, act);
+  if (amask == 0) return;
   const int64_t S = st.S;
   const int H = st.H;
-  const int cur = st.cur[s];
-  const double* __restrict__ X = st.x[cur] + s;
-  const double* __restrict__ U = st.u[cur] + s;
-  double* __restrict__ Dff = st.duff + s;
-  double* __restrict__ Kg = st.K + s;
+  const int cur = warp_cur(st, s, act, amask);
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  double (*ring)[kBwdStageDoubles] = ring_all[warp];
+  uint64_t* bars = bars_all[warp];
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kBwdStages; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](int k, int stage) {   // lane 0 only
+    mbar_arrive_expect_tx(&bars[stage], kBwdStageDoubles * 8);
+    tma_load_1d(&ring[stage][0], X + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][32 * NX], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kBwdStages; ++i)
+      if (H - 1 - i >= 0) issue(H - 1 - i, i);
+  }
 
   double Qd[NX], Rd[NU], qt[NX];
 #pragma unroll
@@ -46,70 +99,59 @@ bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
 
   // terminal expansion: final_cost_quadratization (src/backward_pass.jl:134-153)
   double sv[NX], Sm[NX][NX];
+  {
+    double xN[NX];
+    ldv<NX>(X + ((int64_t)H * S + s) * NX, xN);
 #pragma unroll
-  for (int c = 0; c < NX; ++c) {
-    const double xc = X[(int64_t)(H * NX + c) * S];
-    sv[c] = -2.0 * cp.w_xf[c] * (qt[c] - xc);
+    for (int c = 0; c < NX; ++c) {
+      sv[c] = -2.0 * cp.w_xf[c] * (qt[c] - xN[c]);
 #pragma unroll
-    for (int j = 0; j < NX; ++j) Sm[c][j] = (c == j) ? 2.0 * cp.w_xf[c] : 0.0;
+      for (int j = 0; j < NX; ++j) Sm[c][j] = (c == j) ? 2.0 * cp.w_xf[c] : 0.0;
+    }
   }
-
-  double xk[NX], uk[NU];
-#pragma unroll
-  for (int c = 0; c < NX; ++c) xk[c] = X[(int64_t)((H - 1) * NX + c) * S];
-#pragma unroll
-  for (int i = 0; i < NU; ++i) uk[i] = U[(int64_t)((H - 1) * NU + i) * S];
 
   bool bad = false;
 #pragma unroll 1
-  for (int k = H - 1; k >= 0; --k) {
-    // prefetch the next (earlier) knot point while this one is processed
-    double xn[NX], un[NU];
-    const int kp = (k > 0) ? k - 1 : 0;
+  for (int k = H - 1, it = 0; k >= 0; --k, ++it) {
+    const int stage = it % kBwdStages;
+    mbar_wait(&bars[stage], (it / kBwdStages) & 1);
+    double xk[NX], uk[NU];
+    ldv<NX>(&ring[stage][lane * NX], xk);
+    ldv<NU>(&ring[stage][32 * NX + lane * NU], uk);
+    __syncwarp();
+    if (lane == 0 && k - kBwdStages >= 0) issue(k - kBwdStages, stage);
+    if (act) {
+      double A[NX][NX], Bm[NX][NU];
+      tl_linearize(mp, xk, uk, A, Bm);
+      double qv[NX], rv[NU];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) xn[c] = X[(int64_t)(kp * NX + c) * S];
+      for (int c = 0; c < NX; ++c) qv[c] = -Qd[c] * (qt[c] - xk[c]);
 #pragma unroll
-    for (int i = 0; i < NU; ++i) un[i] = U[(int64_t)(kp * NU + i) * S];
-
-    double A[NX][NX], Bm[NX][NU];
-    tl_linearize(mp, xk, uk, A, Bm);
-    double qv[NX], rv[NU];
+      for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
+      double d[NU], Kk[NU][NX];
+      riccati_step<NX, NU>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
+      double kv[NK];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) qv[c] = -Qd[c] * (qt[c] - xk[c]);
+      for (int i = 0; i < NU; ++i) {
+        bad |= isnan(d[i]);
 #pragma unroll
-    for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
-
-    double d[NU], Kk[NU][NX];
-    riccati_step<NX, NU>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
-
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      Dff[(int64_t)(k * NU + i) * S] = d[i];
-      bad |= isnan(d[i]);
-#pragma unroll
-      for (int j = 0; j < NX; ++j) {
-        Kg[(int64_t)(k * NU * NX + i + NU * j) * S] = Kk[i][j];
-        bad |= isnan(Kk[i][j]);
+        for (int j = 0; j < NX; ++j) { kv[i + NU * j] = Kk[i][j]; bad |= isnan(Kk[i][j]); }
       }
+      stv<NU>(st.duff + ((int64_t)k * S + s) * NU, d);
+      stv<NK>(st.K + ((int64_t)k * S + s) * NK, kv);
     }
-#pragma unroll
-    for (int c = 0; c < NX; ++c) xk[c] = xn[c];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) uk[i] = un[i];
   }
-  if (bad) st.status[s] |= ST_NAN_GAINS;
+  if (act && bad) st.status[s] |= ST_NAN_GAINS;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Split backward pass for SMALL active sets (the heavy tail of the iteration-count distribution).
 // With few trajectories left the fused kernel is latency bound: one warp per SM sub-partition
 // walks 200 dependent steps of linearise + Riccati.  The linearisation of step k depends only on
-// (x_k, u_k) (src/backward_pass.jl:340), so here it runs time-parallel — one thread per
+// (x_k, u_k) (src/backward_pass.jl:340), so it runs time-parallel — one thread per
 // (trajectory, k) — and parks A (its three non-trivial columns) and B in HBM (20 doubles per
 // step, cheap when the set is small); the sequential Riccati kernel then only streams them.
 // ---------------------------------------------------------------------------------------------
-constexpr int kAB = 20;   // 12 entries of A[:,1..3] + 8 of B
-
 __global__ void __launch_bounds__(kBlock)
 lin_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp, double* __restrict__ AB) {
   const int s = blockIdx.x * kBlock + threadIdx.x;
@@ -118,219 +160,257 @@ lin_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
   if (!st.active[s]) return;
   const int64_t S = st.S;
   const int cur = st.cur[s];
-  const double* __restrict__ X = st.x[cur] + s;
-  const double* __restrict__ U = st.u[cur] + s;
   double xk[NX], uk[NU];
-#pragma unroll
-  for (int c = 0; c < NX; ++c) xk[c] = X[(int64_t)(k * NX + c) * S];
-#pragma unroll
-  for (int i = 0; i < NU; ++i) uk[i] = U[(int64_t)(k * NU + i) * S];
+  ldv<NX>(st.x[cur] + ((int64_t)k * S + s) * NX, xk);
+  ldv<NU>(st.u[cur] + ((int64_t)k * S + s) * NU, uk);
   double A[NX][NX], Bm[NX][NU];
   tl_linearize(mp, xk, uk, A, Bm);
-  double* __restrict__ out = AB + (int64_t)k * kAB * S + s;
+  double ab[kAB];
 #pragma unroll
   for (int r = 0; r < NX; ++r) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) out[(int64_t)(r * 3 + j) * S] = A[r][j + 1];
+    for (int j = 0; j < 3; ++j) ab[r * 3 + j] = A[r][j + 1];
 #pragma unroll
-    for (int j = 0; j < NU; ++j) out[(int64_t)(12 + r * NU + j) * S] = Bm[r][j];
+    for (int j = 0; j < NU; ++j) ab[12 + r * NU + j] = Bm[r][j];
   }
+  stv<kAB>(AB + ((int64_t)k * S + s) * kAB, ab);
 }
+
+constexpr int kRicStages = 3;
+constexpr int kRicStageDoubles = 32 * (kAB + NX + NU);
 
 __global__ void __launch_bounds__(kBlock)
 ric_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ CostP cp, const double* __restrict__ AB) {
-  const int s = blockIdx.x * kBlock + threadIdx.x;
-  if (s >= st.nslots) return;
-  if (!st.active[s]) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double (*ring)[kRicStageDoubles] =
+      reinterpret_cast<double (*)[kRicStageDoubles]>(smem_raw) + warp * kRicStages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarps * kRicStages * kRicStageDoubles) +
+                   warp * kRicStages;
+  const int s0 = (blockIdx.x * kWarps + warp) * 32, s = s0 + lane;
+  if (s0 >= st.nslots) return;
+  const bool act = s < st.nslots && st.active[s];
+  const unsigned amask = __ballot_sync(0xffffffffu, act);
+  if (amask == 0) return;
   const int64_t S = st.S;
   const int H = st.H;
-  const int cur = st.cur[s];
-  const double* __restrict__ X = st.x[cur] + s;
-  const double* __restrict__ U = st.u[cur] + s;
-  double* __restrict__ Dff = st.duff + s;
-  double* __restrict__ Kg = st.K + s;
+  const int cur = warp_cur(st, s, act, amask);
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kRicStages; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](int k, int stage) {
+    mbar_arrive_expect_tx(&bars[stage], kRicStageDoubles * 8);
+    tma_load_1d(&ring[stage][0], AB + ((int64_t)k * S + s0) * kAB, 32 * kAB * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][32 * kAB], X + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][32 * (kAB + NX)], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kRicStages; ++i)
+      if (H - 1 - i >= 0) issue(H - 1 - i, i);
+  }
   double Qd[NX], Rd[NU], qt[NX];
 #pragma unroll
   for (int c = 0; c < NX; ++c) { Qd[c] = 2.0 * cp.w_x[c]; qt[c] = cp.x_target[c]; }
 #pragma unroll
   for (int i = 0; i < NU; ++i) Rd[i] = 2.0 * cp.w_u[i];
   double sv[NX], Sm[NX][NX];
-#pragma unroll
-  for (int c = 0; c < NX; ++c) {
-    const double xc = X[(int64_t)(H * NX + c) * S];
-    sv[c] = -2.0 * cp.w_xf[c] * (qt[c] - xc);
-#pragma unroll
-    for (int j = 0; j < NX; ++j) Sm[c][j] = (c == j) ? 2.0 * cp.w_xf[c] : 0.0;
-  }
-  double ab[kAB], xk[NX], uk[NU];
   {
-    const double* __restrict__ in = AB + (int64_t)(H - 1) * kAB * S + s;
+    double xN[NX];
+    ldv<NX>(X + ((int64_t)H * S + s) * NX, xN);
 #pragma unroll
-    for (int e = 0; e < kAB; ++e) ab[e] = in[(int64_t)e * S];
+    for (int c = 0; c < NX; ++c) {
+      sv[c] = -2.0 * cp.w_xf[c] * (qt[c] - xN[c]);
 #pragma unroll
-    for (int c = 0; c < NX; ++c) xk[c] = X[(int64_t)((H - 1) * NX + c) * S];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) uk[i] = U[(int64_t)((H - 1) * NU + i) * S];
+      for (int j = 0; j < NX; ++j) Sm[c][j] = (c == j) ? 2.0 * cp.w_xf[c] : 0.0;
+    }
   }
   bool bad = false;
 #pragma unroll 1
-  for (int k = H - 1; k >= 0; --k) {
-    double abn[kAB], xn[NX], un[NU];
-    const int kp = (k > 0) ? k - 1 : 0;
-    {
-      const double* __restrict__ in = AB + (int64_t)kp * kAB * S + s;
+  for (int k = H - 1, it = 0; k >= 0; --k, ++it) {
+    const int stage = it % kRicStages;
+    mbar_wait(&bars[stage], (it / kRicStages) & 1);
+    double ab[kAB], xk[NX], uk[NU];
+    ldv<kAB>(&ring[stage][lane * kAB], ab);
+    ldv<NX>(&ring[stage][32 * kAB + lane * NX], xk);
+    ldv<NU>(&ring[stage][32 * (kAB + NX) + lane * NU], uk);
+    __syncwarp();
+    if (lane == 0 && k - kRicStages >= 0) issue(k - kRicStages, stage);
+    if (act) {
+      double A[NX][NX], Bm[NX][NU], qv[NX], rv[NU];
 #pragma unroll
-      for (int e = 0; e < kAB; ++e) abn[e] = in[(int64_t)e * S];
+      for (int r = 0; r < NX; ++r) {
+        A[r][0] = (r == 0) ? 1.0 : 0.0;
 #pragma unroll
-      for (int c = 0; c < NX; ++c) xn[c] = X[(int64_t)(kp * NX + c) * S];
+        for (int j = 0; j < 3; ++j) A[r][j + 1] = ab[r * 3 + j];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) un[i] = U[(int64_t)(kp * NU + i) * S];
-    }
-    double A[NX][NX], Bm[NX][NU], qv[NX], rv[NU];
-#pragma unroll
-    for (int r = 0; r < NX; ++r) {
-      A[r][0] = (r == 0) ? 1.0 : 0.0;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) A[r][j + 1] = ab[r * 3 + j];
-#pragma unroll
-      for (int j = 0; j < NU; ++j) Bm[r][j] = ab[12 + r * NU + j];
-    }
-#pragma unroll
-    for (int c = 0; c < NX; ++c) qv[c] = -Qd[c] * (qt[c] - xk[c]);
-#pragma unroll
-    for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
-    double d[NU], Kk[NU][NX];
-    riccati_step<NX, NU>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      Dff[(int64_t)(k * NU + i) * S] = d[i];
-      bad |= isnan(d[i]);
-#pragma unroll
-      for (int j = 0; j < NX; ++j) {
-        Kg[(int64_t)(k * NU * NX + i + NU * j) * S] = Kk[i][j];
-        bad |= isnan(Kk[i][j]);
+        for (int j = 0; j < NU; ++j) Bm[r][j] = ab[12 + r * NU + j];
       }
+#pragma unroll
+      for (int c = 0; c < NX; ++c) qv[c] = -Qd[c] * (qt[c] - xk[c]);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
+      double d[NU], Kk[NU][NX];
+      riccati_step<NX, NU>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
+      double kv[NK];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        bad |= isnan(d[i]);
+#pragma unroll
+        for (int j = 0; j < NX; ++j) { kv[i + NU * j] = Kk[i][j]; bad |= isnan(Kk[i][j]); }
+      }
+      stv<NU>(st.duff + ((int64_t)k * S + s) * NU, d);
+      stv<NK>(st.K + ((int64_t)k * S + s) * NK, kv);
     }
-#pragma unroll
-    for (int e = 0; e < kAB; ++e) ab[e] = abn[e];
-#pragma unroll
-    for (int c = 0; c < NX; ++c) xk[c] = xn[c];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) uk[i] = un[i];
   }
-  if (bad) st.status[s] |= ST_NAN_GAINS;
+  if (act && bad) st.status[s] |= ST_NAN_GAINS;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Forward pass: closed-loop rollout + line search.  The α = 1 candidate is rolled out for the whole
+// warp; lanes whose candidate is rejected (prev − new ≤ 0 or NaN) go round again with α/2 while the
+// lanes that accepted idle (their stores are predicated off), so the warp stays convergent for the
+// TMA ring.  Ring: D stages of {x 1 KB, u 512 B, δuff 512 B, K 2 KB [, x_traj 1 KB]} per warp.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_XT> struct FwdCfg {
+  static constexpr int kStages = HAS_XT ? 3 : 4;
+  static constexpr int kStageDoubles = 32 * (NX + NU + NU + NK + (HAS_XT ? NX : 0));
+  static constexpr size_t kSmem = sizeof(double) * kWarps * kStages * kStageDoubles + sizeof(uint64_t) * kWarps * kStages;
+};
 
 template <bool HAS_XT>
 __global__ void __launch_bounds__(kBlock)
 fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
                  const __grid_constant__ CostP cp) {
-  const int s = blockIdx.x * kBlock + threadIdx.x;
-  if (s >= st.nslots) return;
-  if (!st.active[s]) return;
+  using Cfg = FwdCfg<HAS_XT>;
+  constexpr int D = Cfg::kStages, SD = Cfg::kStageDoubles;
+  constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU, oT = oK + 32 * NK;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double (*ring)[SD] = reinterpret_cast<double (*)[SD]>(smem_raw) + warp * D;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarps * D * SD) + warp * D;
+  const int s0 = (blockIdx.x * kWarps + warp) * 32, s = s0 + lane;
+  if (s0 >= st.nslots) return;
+  const bool act = s < st.nslots && st.active[s];
+  const unsigned amask = __ballot_sync(0xffffffffu, act);
+  if (amask == 0) return;
   const int64_t S = st.S;
   const int H = st.H;
-  const int cur = st.cur[s];
-  const double* __restrict__ X = st.x[cur] + s;
-  const double* __restrict__ U = st.u[cur] + s;
-  const double* __restrict__ Dff = st.duff + s;
-  const double* __restrict__ Kg = st.K + s;
-  const double* __restrict__ XT = HAS_XT ? st.xtraj + s : nullptr;
-  double* __restrict__ Xo = st.x[cur ^ 1] + s;
-  double* __restrict__ Uo = st.u[cur ^ 1] + s;
+  const int cur = warp_cur(st, s, act, amask);
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  double* __restrict__ Xo = st.x[cur ^ 1];
+  double* __restrict__ Uo = st.u[cur ^ 1];
 
-  const double prev = st.prev_cost[s];
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](int k, int stage) {
+    mbar_arrive_expect_tx(&bars[stage], SD * 8);
+    tma_load_1d(&ring[stage][oX], X + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oU], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oD], st.duff + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oK], st.K + ((int64_t)k * S + s0) * NK, 32 * NK * 8, &bars[stage]);
+    if constexpr (HAS_XT) tma_load_1d(&ring[stage][oT], st.xtraj + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+  };
+
+  const double prev = act ? st.prev_cost[s] : 0.0;
   double x0[NX];
-#pragma unroll
-  for (int c = 0; c < NX; ++c) x0[c] = X[(int64_t)c * S];
+  ldv<NX>(X + (int64_t)s * NX, x0);
 
-  double alpha = 1.0, cost = 0.0, du2 = 0.0;
-  bool accepted = false;
-  double xb[NX];
-  for (int j = 0; j < st.n_alpha; ++j) {
-#pragma unroll
-    for (int c = 0; c < NX; ++c) { xb[c] = x0[c]; Xo[(int64_t)c * S] = x0[c]; }
-    cost = 0.0; du2 = 0.0;
-    // software-pipelined loads: step k+1's operands are in flight during step k
-    double xk[NX], uk[NU], dk[NU], Kk[NU * NX];
-#pragma unroll
-    for (int c = 0; c < NX; ++c) xk[c] = x0[c];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) { uk[i] = U[(int64_t)i * S]; dk[i] = Dff[(int64_t)i * S]; }
-#pragma unroll
-    for (int e = 0; e < NU * NX; ++e) Kk[e] = Kg[(int64_t)e * S];
+  double alpha = 1.0, acc_cost = qnan(), acc_du2 = qnan(), acc_alpha = 0.0;
+  bool searching = act, bad = false;
+  int fills = 0;   // ring uses so far (stage = fills % D, parity = (fills / D) & 1), warp-uniform
 #pragma unroll 1
-    for (int k = 0; k < H; ++k) {
-      double xk1[NX], uk1[NU], dk1[NU], Kk1[NU * NX], xt[NX];
-      const int kn = (k + 1 < H) ? k + 1 : k;
+  for (int j = 0; j < st.n_alpha; ++j) {
+    if (!__any_sync(0xffffffffu, searching)) break;
+    if (lane == 0) {
 #pragma unroll
-      for (int c = 0; c < NX; ++c) xk1[c] = X[(int64_t)(kn * NX + c) * S];
+      for (int i = 0; i < D; ++i)
+        if (i < H) issue(i, (fills + i) % D);
+    }
+    double xb[NX];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) { uk1[i] = U[(int64_t)(kn * NU + i) * S]; dk1[i] = Dff[(int64_t)(kn * NU + i) * S]; }
-#pragma unroll
-      for (int e = 0; e < NU * NX; ++e) Kk1[e] = Kg[(int64_t)(kn * NU * NX + e) * S];
-      if constexpr (HAS_XT) {
-#pragma unroll
-        for (int c = 0; c < NX; ++c) xt[c] = XT[(int64_t)(k * NX + c) * S];
-      } else {
+    for (int c = 0; c < NX; ++c) xb[c] = x0[c];
+    if (searching) stv<NX>(Xo + (int64_t)s * NX, xb);
+    double cost = 0.0, du2 = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < H; ++k, ++fills) {
+      const int stage = fills % D;
+      mbar_wait(&bars[stage], (fills / D) & 1);
+      double xk[NX], uk[NU], dk[NU], Kk[NK], xt[NX];
+      ldv<NX>(&ring[stage][oX + lane * NX], xk);
+      ldv<NU>(&ring[stage][oU + lane * NU], uk);
+      ldv<NU>(&ring[stage][oD + lane * NU], dk);
+      ldv<NK>(&ring[stage][oK + lane * NK], Kk);
+      if constexpr (HAS_XT) ldv<NX>(&ring[stage][oT + lane * NX], xt);
+      else {
 #pragma unroll
         for (int c = 0; c < NX; ++c) xt[c] = 0.0;
       }
-
-      // ū = u + α δuff + K (x̄ − x)      (src/forward_pass.jl:72-73)
-      double dx[NX], ub[NU];
+      __syncwarp();
+      if (lane == 0 && k + D < H) issue(k + D, stage);
+      if (searching) {
+        // ū = u + α δuff + K (x̄ − x)      (src/forward_pass.jl:72-73)
+        double dx[NX], ub[NU];
 #pragma unroll
-      for (int c = 0; c < NX; ++c) dx[c] = xb[c] - xk[c];
+        for (int c = 0; c < NX; ++c) dx[c] = xb[c] - xk[c];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        double kdx = Kk[i] * dx[0];
+        for (int i = 0; i < NU; ++i) {
+          double kdx = Kk[i] * dx[0];
 #pragma unroll
-        for (int c = 1; c < NX; ++c) kdx = fma(Kk[i + NU * c], dx[c], kdx);
-        ub[i] = fma(alpha, dk[i], uk[i]) + kdx;
-        Uo[(int64_t)(k * NU + i) * S] = ub[i];
-        const double e = ub[i] - uk[i];
-        du2 = fma(e, e, du2);
+          for (int c = 1; c < NX; ++c) kdx = fma(Kk[i + NU * c], dx[c], kdx);
+          ub[i] = fma(alpha, dk[i], uk[i]) + kdx;
+          const double e = ub[i] - uk[i];
+          du2 = fma(e, e, du2);
+        }
+        stv<NU>(Uo + ((int64_t)k * S + s) * NU, ub);
+        // running cost l(x̄ − x_traj, ū), summed left to right (src/forward_pass.jl:189-191)
+        double lx = 0.0, lu = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - (xb[c] - xt[c]); lx = fma(cp.w_x[c] * e, e, lx); }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) lu = fma(cp.w_u[i] * ub[i], ub[i], lu);
+        cost += lx + lu;
+        // x̄⁺ = f(x̄, ū)                    (src/forward_pass.jl:74)
+        double xnext[NX];
+        tl_step(mp, xb, ub, xnext);
+#pragma unroll
+        for (int c = 0; c < NX; ++c) xb[c] = xnext[c];
+        stv<NX>(Xo + ((int64_t)(k + 1) * S + s) * NX, xb);
       }
-      // running cost l(x̄ − x_traj, ū), summed left to right (src/forward_pass.jl:189-191)
-      double lx = 0.0, lu = 0.0;
-#pragma unroll
-      for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - (xb[c] - xt[c]); lx = fma(cp.w_x[c] * e, e, lx); }
-#pragma unroll
-      for (int i = 0; i < NU; ++i) lu = fma(cp.w_u[i] * ub[i], ub[i], lu);
-      cost += lx + lu;
-      // x̄⁺ = f(x̄, ū)                    (src/forward_pass.jl:74)
-      double xnext[NX];
-      tl_step(mp, xb, ub, xnext);
-#pragma unroll
-      for (int c = 0; c < NX; ++c) { xb[c] = xnext[c]; Xo[(int64_t)((k + 1) * NX + c) * S] = xnext[c]; }
-#pragma unroll
-      for (int c = 0; c < NX; ++c) xk[c] = xk1[c];
-#pragma unroll
-      for (int i = 0; i < NU; ++i) { uk[i] = uk1[i]; dk[i] = dk1[i]; }
-#pragma unroll
-      for (int e = 0; e < NU * NX; ++e) Kk[e] = Kk1[e];
     }
-    double lf = 0.0;
+    if (searching) {
+      double lf = 0.0;
 #pragma unroll
-    for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - xb[c]; lf = fma(cp.w_xf[c] * e, e, lf); }
-    cost += lf;
-    if (prev - cost > 0.0) { accepted = true; break; }   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
+      for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - xb[c]; lf = fma(cp.w_xf[c] * e, e, lf); }
+      cost += lf;
+      if (prev - cost > 0.0) {   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
+        searching = false;
+        acc_cost = cost; acc_du2 = du2; acc_alpha = alpha;
+#pragma unroll
+        for (int c = 0; c < NX; ++c) bad |= isnan(xb[c]);
+      }
+    }
     alpha *= 0.5;
   }
-  st.bar[s] = cur ^ 1;
-  if (accepted) {
-    bool bad = false;
-#pragma unroll
-    for (int c = 0; c < NX; ++c) bad |= isnan(xb[c]);
+  if (act) {
+    st.bar[s] = cur ^ 1;
     if (bad) st.status[s] |= ST_NAN_ROLLOUT;
-    st.new_cost[s] = cost; st.alpha[s] = alpha; st.du2[s] = du2;
-  } else {
-    st.new_cost[s] = __longlong_as_double(0x7ff8000000000000LL); st.alpha[s] = 0.0;
-    st.du2[s] = __longlong_as_double(0x7ff8000000000000LL);
+    st.new_cost[s] = acc_cost; st.alpha[s] = acc_alpha; st.du2[s] = acc_du2;
   }
 }
 
-// Open-loop rollout of u from x0 (animate_2_link.jl:14-16): x[cur] filled.
+// Open-loop rollout of u from x0 (animate_2_link.jl:14-16): x[cur] filled.  x0: [slot][4].
 __global__ void __launch_bounds__(kBlock)
 rollout_init_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
                       const double* __restrict__ x0) {
@@ -338,18 +418,18 @@ rollout_init_two_link(const __grid_constant__ DevState st, const __grid_constant
   if (s >= st.nslots) return;
   const int64_t S = st.S;
   const int cur = st.cur[s];
-  double* __restrict__ X = st.x[cur] + s;
-  const double* __restrict__ U = st.u[cur] + s;
+  double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
   double xb[NX];
-#pragma unroll
-  for (int c = 0; c < NX; ++c) { xb[c] = x0[(int64_t)c * S + s]; X[(int64_t)c * S] = xb[c]; }
+  ldv<NX>(x0 + (int64_t)s * NX, xb);
+  stv<NX>(X + (int64_t)s * NX, xb);
   for (int k = 0; k < st.H; ++k) {
     double ub[NU], xn[NX];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) ub[i] = U[(int64_t)(k * NU + i) * S];
+    ldv<NU>(U + ((int64_t)k * S + s) * NU, ub);
     tl_step(mp, xb, ub, xn);
 #pragma unroll
-    for (int c = 0; c < NX; ++c) { xb[c] = xn[c]; X[(int64_t)((k + 1) * NX + c) * S] = xn[c]; }
+    for (int c = 0; c < NX; ++c) xb[c] = xn[c];
+    stv<NX>(X + ((int64_t)(k + 1) * S + s) * NX, xb);
   }
 }
 
@@ -395,12 +475,13 @@ __global__ void finalize_max_iter_kernel(const __grid_constant__ DevState st) {
 __global__ void reset_state_kernel(const __grid_constant__ DevState st) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= st.S) return;
-  const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  st.prev_cost[s] = __longlong_as_double(0x7ff0000000000000LL);  // Inf (src/forward_pass.jl:159)
+  const double nan = qnan();
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);   // src/forward_pass.jl:159
+  st.prev_cost[s] = inf;
   st.new_cost[s] = nan; st.alpha[s] = nan; st.du2[s] = nan;
   st.status[s] = 0; st.iters[s] = 0; st.cur[s] = 0; st.bar[s] = 1; st.traj[s] = s;
   st.active[s] = (s < st.nslots) ? 1 : 0;
-  st.r_prev_cost[s] = __longlong_as_double(0x7ff0000000000000LL);
+  st.r_prev_cost[s] = inf;
   st.r_new_cost[s] = nan; st.r_alpha[s] = nan; st.r_du2[s] = nan;
   st.r_status[s] = 0; st.r_iters[s] = 0; st.r_active[s] = (s < st.nslots) ? 1 : 0;
   if (st.cost_trace)
@@ -416,13 +497,14 @@ __global__ void set_prev_cost_kernel(const __grid_constant__ DevState st, const 
   if (s < st.nslots) st.prev_cost[s] = prev[st.traj[s]];
 }
 
+// host-owned convergence control may only switch trajectories OFF (active slots must share `cur`)
 __global__ void set_active_by_traj_kernel(const __grid_constant__ DevState st, const int32_t* __restrict__ mask) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < st.nslots) st.active[s] = mask[st.traj[s]] ? 1 : 0;
+  if (s < st.nslots && !mask[st.traj[s]]) st.active[s] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Compaction.  Iteration counts are heavy tailed (6…100 on config 2), so finished trajectories
+// Compaction.  Iteration counts are heavy tailed (5…100 on config 2), so finished trajectories
 // are retired to the per-trajectory result mirrors and the holes they leave below the new slot
 // count are filled with still-active slots from above it: the kernels then run over a dense
 // prefix [0, nslots) and whole warps drop out as the batch converges.
@@ -463,19 +545,31 @@ __global__ void __launch_bounds__(1024) compact_plan_kernel(const __grid_constan
   if (t == 1023) *st.n_move = sc[1][1023];
 }
 
-// one warp per retiring slot: current iterate → out_x/out_u (boundary layout, by trajectory), scalars → mirrors
+// one warp per retiring slot: current iterate → out_x/out_u (boundary layout, by trajectory), scalars → mirrors.
+// Lanes run over k: each reads its (k, slot) vector (one full 32 B sector) and the warp writes 32
+// consecutive doubles of every component row.
 __global__ void __launch_bounds__(128) retire_kernel(const __grid_constant__ DevState st, int n_retire) {
   const int w = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n_retire) return;
   const int s = st.retire_list[w], t = st.traj[s], c = st.cur[s];
   const int64_t S = st.S;
-  const int N = st.H + 1, n = st.n, H = st.H, m = st.m;
-  const double* __restrict__ X = st.x[c] + s;
-  const double* __restrict__ U = st.u[c] + s;
-  double* __restrict__ ox = st.out_x + (int64_t)t * n * N;
-  double* __restrict__ ou = st.out_u + (int64_t)t * m * H;
-  for (int j = lane; j < n * N; j += 32) { const int cc = j / N, k = j - cc * N; ox[j] = X[(int64_t)(k * n + cc) * S]; }
-  for (int j = lane; j < m * H; j += 32) { const int cc = j / H, k = j - cc * H; ou[j] = U[(int64_t)(k * m + cc) * S]; }
+  const int N = st.H + 1, H = st.H;
+  const double* __restrict__ X = st.x[c];
+  const double* __restrict__ U = st.u[c];
+  double* __restrict__ ox = st.out_x + (int64_t)t * NX * N;
+  double* __restrict__ ou = st.out_u + (int64_t)t * NU * H;
+  for (int k = lane; k < N; k += 32) {
+    double v[NX];
+    ldv<NX>(X + ((int64_t)k * S + s) * NX, v);
+#pragma unroll
+    for (int cc = 0; cc < NX; ++cc) ox[cc * N + k] = v[cc];
+  }
+  for (int k = lane; k < H; k += 32) {
+    double v[NU];
+    ldv<NU>(U + ((int64_t)k * S + s) * NU, v);
+#pragma unroll
+    for (int cc = 0; cc < NU; ++cc) ou[cc * H + k] = v[cc];
+  }
   if (lane == 0) copy_scalars_to_mirror(st, s, t, 0);
 }
 
@@ -485,14 +579,22 @@ __global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ DevSt
   if (w >= *st.n_move) return;
   const int src = st.move_src[w], dst = st.move_dst[w], c = st.cur[src];
   const int64_t S = st.S;
-  const int rows_x = (st.H + 1) * st.n, rows_u = st.H * st.m;
+  const int N = st.H + 1, H = st.H;
   double* __restrict__ X = st.x[c];
   double* __restrict__ U = st.u[c];
-  for (int r = lane; r < rows_x; r += 32) X[(int64_t)r * S + dst] = X[(int64_t)r * S + src];
-  for (int r = lane; r < rows_u; r += 32) U[(int64_t)r * S + dst] = U[(int64_t)r * S + src];
-  if (st.xtraj) {
-    double* __restrict__ XT = st.xtraj;
-    for (int r = lane; r < rows_x; r += 32) XT[(int64_t)r * S + dst] = XT[(int64_t)r * S + src];
+  for (int k = lane; k < N; k += 32) {
+    double v[NX];
+    ldv<NX>(X + ((int64_t)k * S + src) * NX, v);
+    stv<NX>(X + ((int64_t)k * S + dst) * NX, v);
+    if (st.xtraj) {
+      ldv<NX>(st.xtraj + ((int64_t)k * S + src) * NX, v);
+      stv<NX>(st.xtraj + ((int64_t)k * S + dst) * NX, v);
+    }
+  }
+  for (int k = lane; k < H; k += 32) {
+    double v[NU];
+    ldv<NU>(U + ((int64_t)k * S + src) * NU, v);
+    stv<NU>(U + ((int64_t)k * S + dst) * NU, v);
   }
   if (lane == 0) {
     st.prev_cost[dst] = st.prev_cost[src]; st.new_cost[dst] = st.new_cost[src];
@@ -510,7 +612,19 @@ __global__ void flush_scalars_kernel(const __grid_constant__ DevState st) {
 
 inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 
+template <class K> void opt_in_smem(K kernel, size_t bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+constexpr size_t kRicSmem = sizeof(double) * kWarps * kRicStages * kRicStageDoubles + sizeof(uint64_t) * kWarps * kRicStages;
+
 }  // namespace
+
+void init_kernel_attributes() {
+  opt_in_smem(fwd_lpt_two_link<false>, FwdCfg<false>::kSmem);
+  opt_in_smem(fwd_lpt_two_link<true>, FwdCfg<true>::kSmem);
+  opt_in_smem(ric_lpt_two_link, kRicSmem);
+}
 
 void launch_bwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
   if (st.nslots <= 0) return;
@@ -520,12 +634,12 @@ void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const Cos
   if (st.nslots <= 0) return;
   dim3 grid(grid_for(st.nslots, kBlock), st.H);
   lin_lpt_two_link<<<grid, kBlock, 0, s>>>(st, mp, AB);
-  ric_lpt_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, cp, AB);
+  ric_lpt_two_link<<<grid_for(st.nslots, kBlock), kBlock, kRicSmem, s>>>(st, cp, AB);
 }
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
   if (st.nslots <= 0) return;
-  if (st.xtraj) fwd_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, cp);
-  else fwd_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, cp);
+  if (st.xtraj) fwd_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp);
+  else fwd_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp);
 }
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0, cudaStream_t s) {
   rollout_init_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, d_x0);

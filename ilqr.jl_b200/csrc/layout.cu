@@ -1,60 +1,72 @@
 // layout.cu — boundary layout <-> device layout.
 //
-// Boundary ("TF", time-fastest) = the reference's Julia column-major arrays
-// with the batch trailing: x[N,n,B] ⇒ trajectory b is one contiguous slab of
-// ncomp·T doubles, element (k,c) at c·T + k (src/backward_pass.jl:332-333 for
-// the single-trajectory shapes).  Device ("BF", batch-fastest): element (k,c)
-// of slot b at (k·ncomp + c)·S + b.  Both directions go through a 32×33 shared
-// tile so that global reads and writes are both full 256 B lines.
+// Boundary ("TF", time-fastest) = the reference's Julia column-major arrays with the batch
+// trailing: x[N,n,B] ⇒ trajectory t is one contiguous slab of ncomp·T doubles, element (k,c) at
+// c·T + k (single-trajectory shapes: src/backward_pass.jl:332-333).
+// Device ("KSC") = [k][slot][component]: element (k,c) of slot s at (k·S + s)·ncomp + c.
+//   * the 32 lanes of a warp own 32 consecutive slots ⇒ the slab a warp needs for time step k
+//     is ONE contiguous run of 32·ncomp doubles (1 KB for x) — a single TMA bulk copy;
+//   * a lane's own components are one 16/32/64-byte vector ⇒ LDG/STG.128.
+// Both directions go through a padded shared tile so global reads and writes are both
+// contiguous runs (128 B along k on the boundary side, 32·ncomp·8 B on the device side).
 #include "internal.cuh"
 
 namespace ilqr {
 namespace {
 
-constexpr int TILE = 32, ROWS = 8;
+constexpr int TS = 32;   // slots per tile
+constexpr int TK = 16;   // time steps per tile
+constexpr int kThreads = 256;
 
-// grid: (ceil(L/32), ceil(B/32)), block (32, 8); L = ncomp*T
-__global__ void tf_to_bf_kernel(const double* __restrict__ tf, double* __restrict__ bf,
-                                const int32_t* __restrict__ slot_traj, int B, int T, int ncomp, int64_t S) {
-  __shared__ double tile[TILE][TILE + 1];
-  const int L = ncomp * T;
-  const int j0 = blockIdx.x * TILE, b0 = blockIdx.y * TILE;
-  for (int r = threadIdx.y; r < TILE; r += ROWS) {
-    const int b = b0 + r, j = j0 + threadIdx.x;
-    if (b < B && j < L) tile[r][threadIdx.x] = tf[(int64_t)(slot_traj ? slot_traj[b] : b) * L + j];
+// dynamic smem: TK rows of (TS*ncomp + 1) doubles
+__global__ void __launch_bounds__(kThreads)
+tf_to_ksc_kernel(const double* __restrict__ tf, double* __restrict__ ksc, const int32_t* __restrict__ slot_traj,
+                 int nslots, int T, int ncomp, int64_t S) {
+  extern __shared__ double tile[];
+  const int row = TS * ncomp + 1;
+  const int k0 = blockIdx.x * TK, s0 = blockIdx.y * TS;
+  const int L = ncomp * T, E = TS * TK * ncomp;
+  for (int idx = threadIdx.x; idx < E; idx += kThreads) {
+    const int kk = idx % TK, rest = idx / TK, c = rest % ncomp, sl = rest / ncomp;
+    const int k = k0 + kk, s = s0 + sl;
+    if (k < T && s < nslots) {
+      const int64_t t = slot_traj ? slot_traj[s] : s;
+      tile[kk * row + sl * ncomp + c] = tf[t * L + (int64_t)c * T + k];
+    }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < TILE; r += ROWS) {
-    const int j = j0 + r, b = b0 + threadIdx.x;
-    if (b < B && j < L) {
-      const int c = j / T, k = j - c * T;
-      bf[(int64_t)(k * ncomp + c) * S + b] = tile[threadIdx.x][r];
-    }
+  for (int idx = threadIdx.x; idx < E; idx += kThreads) {
+    const int within = idx % (TS * ncomp), kk = idx / (TS * ncomp);
+    const int sl = within / ncomp;
+    const int k = k0 + kk, s = s0 + sl;
+    if (k < T && s < nslots) ksc[((int64_t)k * S + s0) * ncomp + within] = tile[kk * row + within];
   }
 }
 
-__global__ void bf_to_tf_kernel(const double* __restrict__ bf0, const double* __restrict__ bf1,
-                                const int32_t* __restrict__ sel, double* __restrict__ tf,
-                                const int32_t* __restrict__ slot_traj, int B, int T, int ncomp, int64_t S) {
-  __shared__ double tile[TILE][TILE + 1];
-  const int L = ncomp * T;
-  const int j0 = blockIdx.x * TILE, b0 = blockIdx.y * TILE;
-  {
-    const int b = b0 + threadIdx.x;
-    const double* src = bf0;
-    if (sel && b < B && sel[b]) src = bf1;
-    for (int r = threadIdx.y; r < TILE; r += ROWS) {
-      const int j = j0 + r;
-      if (b < B && j < L) {
-        const int c = j / T, k = j - c * T;
-        tile[r][threadIdx.x] = src[(int64_t)(k * ncomp + c) * S + b];
-      }
+__global__ void __launch_bounds__(kThreads)
+ksc_to_tf_kernel(const double* __restrict__ b0, const double* __restrict__ b1, const int32_t* __restrict__ sel,
+                 double* __restrict__ tf, const int32_t* __restrict__ slot_traj, int nslots, int T, int ncomp, int64_t S) {
+  extern __shared__ double tile[];
+  const int row = TS * ncomp + 1;
+  const int k0 = blockIdx.x * TK, s0 = blockIdx.y * TS;
+  const int L = ncomp * T, E = TS * TK * ncomp;
+  for (int idx = threadIdx.x; idx < E; idx += kThreads) {
+    const int within = idx % (TS * ncomp), kk = idx / (TS * ncomp);
+    const int sl = within / ncomp;
+    const int k = k0 + kk, s = s0 + sl;
+    if (k < T && s < nslots) {
+      const double* src = (sel && sel[s]) ? b1 : b0;
+      tile[kk * row + within] = src[((int64_t)k * S + s0) * ncomp + within];
     }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < TILE; r += ROWS) {
-    const int b = b0 + r, j = j0 + threadIdx.x;
-    if (b < B && j < L) tf[(int64_t)(slot_traj ? slot_traj[b] : b) * L + j] = tile[threadIdx.x][r];
+  for (int idx = threadIdx.x; idx < E; idx += kThreads) {
+    const int kk = idx % TK, rest = idx / TK, c = rest % ncomp, sl = rest / ncomp;
+    const int k = k0 + kk, s = s0 + sl;
+    if (k < T && s < nslots) {
+      const int64_t t = slot_traj ? slot_traj[s] : s;
+      tf[t * L + (int64_t)c * T + k] = tile[kk * row + sl * ncomp + c];
+    }
   }
 }
 
@@ -63,17 +75,17 @@ __global__ void bf_to_tf_kernel(const double* __restrict__ bf0, const double* __
 void launch_tf_to_bf(const double* tf, double* bf, const int32_t* slot_traj, int nslots, int T, int ncomp, int64_t S,
                      cudaStream_t s) {
   if (nslots <= 0) return;
-  const int L = ncomp * T;
-  dim3 grid((L + TILE - 1) / TILE, (nslots + TILE - 1) / TILE), block(TILE, ROWS);
-  tf_to_bf_kernel<<<grid, block, 0, s>>>(tf, bf, slot_traj, nslots, T, ncomp, S);
+  dim3 grid((T + TK - 1) / TK, (nslots + TS - 1) / TS);
+  const size_t smem = sizeof(double) * TK * (TS * ncomp + 1);
+  tf_to_ksc_kernel<<<grid, kThreads, smem, s>>>(tf, bf, slot_traj, nslots, T, ncomp, S);
 }
 
 void launch_bf_to_tf(const double* bf0, const double* bf1, const int32_t* sel, double* tf, const int32_t* slot_traj,
                      int nslots, int T, int ncomp, int64_t S, cudaStream_t s) {
   if (nslots <= 0) return;
-  const int L = ncomp * T;
-  dim3 grid((L + TILE - 1) / TILE, (nslots + TILE - 1) / TILE), block(TILE, ROWS);
-  bf_to_tf_kernel<<<grid, block, 0, s>>>(bf0, bf1, sel, tf, slot_traj, nslots, T, ncomp, S);
+  dim3 grid((T + TK - 1) / TK, (nslots + TS - 1) / TS);
+  const size_t smem = sizeof(double) * TK * (TS * ncomp + 1);
+  ksc_to_tf_kernel<<<grid, kThreads, smem, s>>>(bf0, bf1, sel, tf, slot_traj, nslots, T, ncomp, S);
 }
 
 }  // namespace ilqr
