@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipelined", action="store_true")
     return ap.parse_args()
 
 
@@ -253,6 +254,53 @@ def run_b200(args):
                 "share_of_step": dom_ms / ms_total,
                 "both_kernels_GBps_first_iteration": (BWD_BYTES + FWD_BYTES) * B / (full_iter_ms * 1e-3) / 1e9 if full_iter_ms else None}
 
+    # FP64-pipe view of the same launches (the nominal bound of this path): DFMA-class
+    # instructions per trajectory-step counted from SASS (tools/sass_mix.py), 2 flops each
+    fp64_peak_tf = None
+    try:
+        fp64_peak_tf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_dfma_tflops"]
+    except Exception:
+        pass
+    FP64_INSTR = {"bwd": 997, "fwd": 273}
+    flops = 2.0 * FP64_INSTR[dom] * H * prof_acc["traj_iters"]
+    roofline["fp64"] = {"achieved_tflops": flops / (dom_ms * 1e-3) / 1e12 if dom_ms else None,
+                        "peak_tflops": fp64_peak_tf, "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
+                        "fp64_instr_per_trajectory_step": FP64_INSTR[dom],
+                        "note": "whole-fit average incl. the latency-bound tail; first-iteration (full batch) figures in profiles/"}
+    if fp64_peak_tf and roofline["fp64"]["achieved_tflops"]:
+        roofline["fp64"]["frac"] = roofline["fp64"]["achieved_tflops"] / fp64_peak_tf
+
+    # pipelined throughput: the same K steps with up to 4 batches in flight on 4 handles (tails overlap bulks)
+    pipelined = None
+    if not args.no_pipelined:
+        import threading
+        nh = 4
+        extra = [ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, B, device=local)) for _ in range(nh - 1)]
+        pool = [s] + extra
+
+        def worker(sv, n):
+            for _ in range(n):
+                sv.upload_device(dx.data_ptr(), du.data_ptr())
+                sv.fit(MAX_ITER, TOL)
+
+        ksteps = max(nh, (args.steps + nh - 1) // nh * nh)
+        for rep in range(2):   # first repetition warms the extra handles up
+            barrier()
+            th = [threading.Thread(target=worker, args=(sv, ksteps // nh)) for sv in pool]
+            t0 = time.perf_counter()
+            [t.start() for t in th]
+            [t.join() for t in th]
+            barrier()
+            dtp = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dtp], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtp = float(t.item())
+        pipelined = {"value": world * B * ksteps / dtp, "unit": UNIT, "batches_in_flight": nh, "steps": ksteps,
+                     "ms_per_step": 1e3 * dtp / ksteps, "timing": "host wall clock around barrier+synchronize"}
+        for sv in extra:
+            sv.close()
+
     # end to end through the host-facing call with pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -302,7 +350,7 @@ def run_b200(args):
             "mean_iterations_per_trajectory": float(iters.double().mean().item()),
             "converged_fraction": float(((torch.from_numpy(status) & 16) != 0).double().mean().item()),
             "mean_final_cost": float(cost.mean().item()),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pipelined": pipelined, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))
     s.close()

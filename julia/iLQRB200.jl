@@ -1,0 +1,117 @@
+# iLQRB200.jl — the reference-side binding a maintainer of aabouman/iLQR.jl would add.
+# Thin `ccall` stubs over include/ilqr_b200.h (libilqr_b200.so).  Julia keeps problem setup, the
+# outer loop, the convergence test and the asserts of `fit` (src/forward_pass.jl:148-179); the GPU
+# runs `backward_pass` (src/backward_pass.jl:324-357) and `forward_pass` (src/forward_pass.jl:55-93)
+# on a whole batch of problems.  NOTE: Julia is not available in the build image, so this file is
+# kept deliberately thin and has not been executed; tests/ drive the identical ABI through ctypes.
+module iLQRB200
+
+const lib = get(ENV, "ILQR_B200_LIB", "libilqr_b200.so")
+
+# mirrors `struct ilqr_problem` field for field
+struct Problem
+    abi_version::Int32
+    model_id::Int32
+    n::Int32
+    m::Int32
+    H::Int32
+    B::Int32
+    n_alpha::Int32
+    trace_iters::Int32
+    device::Int32
+    variant::Int32
+    dt::Float64
+    reg::Float64
+    model_params::NTuple{32,Float64}
+    x_target::NTuple{16,Float64}
+    w_x::NTuple{16,Float64}
+    w_u::NTuple{8,Float64}
+    w_xf::NTuple{16,Float64}
+end
+
+const X, U, XBAR, UBAR, DUFF, K, NEW_COST, PREV_COST, ALPHA, DU2 = Int32.(0:9)
+const STATUS, ITERS, ACTIVE = Int32(13), Int32(14), Int32(15)
+
+check(rc, h) = rc == 0 || error(unsafe_string(ccall((:ilqr_last_error, lib), Cstring, (Ptr{Cvoid},), h)))
+
+"The 2-link plugin of test/2_link_example/2_link_helper_functions.jl as a device-side problem."
+function two_link_problem(H::Integer, B::Integer)
+    p = Ref{Problem}()
+    ccall((:ilqr_problem_two_link, lib), Int32, (Ptr{Problem}, Int32, Int32), p, H, B) == 0 || error("problem")
+    return p[]
+end
+
+mutable struct Solver
+    h::Ptr{Cvoid}
+    p::Problem
+    function Solver(p::Problem)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:ilqr_create, lib), Int32, (Ptr{Problem}, Ptr{Ptr{Cvoid}}), Ref(p), h)
+        rc == 0 || error(unsafe_string(ccall((:ilqr_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+        s = new(h[], p)
+        finalizer(s -> ccall((:ilqr_destroy, lib), Int32, (Ptr{Cvoid},), s.h), s)
+        return s
+    end
+end
+
+upload!(s::Solver, x::Array{Float64,3}, u::Array{Float64,3}, x_traj = nothing) =
+    check(ccall((:ilqr_upload, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                s.h, x, u, x_traj === nothing ? C_NULL : x_traj), s.h)
+
+function download(s::Solver, which::Int32, dims...; T = Float64)
+    out = Array{T}(undef, dims...)
+    check(ccall((:ilqr_download, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), s.h, which, out), s.h)
+    return out
+end
+
+"backward_pass(x, u, …) → (δuff[H,m,B], K[H,m,n,B])   (src/backward_pass.jl:324)"
+function backward_pass(s::Solver)
+    check(ccall((:ilqr_backward_pass, lib), Int32, (Ptr{Cvoid},), s.h), s.h)
+    p = s.p
+    st = download(s, STATUS, p.B; T = Int32)
+    @assert !any(st .& 1 .!= 0)          # src/backward_pass.jl:353-354
+    return (download(s, DUFF, p.H, p.m, p.B), download(s, K, p.H, p.m, p.n, p.B))
+end
+
+"forward_pass(x, u, x_traj, δuff, K, prev_cost, …) → (x̄, ū, new_cost)   (src/forward_pass.jl:55)"
+function forward_pass(s::Solver, prev_cost::Vector{Float64})
+    check(ccall((:ilqr_forward_pass, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), s.h, prev_cost), s.h)
+    p = s.p
+    st = download(s, STATUS, p.B; T = Int32)
+    @assert !any(st .& 2 .!= 0)          # src/forward_pass.jl:89-90
+    return (download(s, XBAR, p.H + 1, p.n, p.B), download(s, UBAR, p.H, p.m, p.B), download(s, NEW_COST, p.B))
+end
+
+"""
+    fit(x_init[N,n,B], u_init[H,m,B], problem; x_traj, max_iter = 100, tol = 1e-6) → (x̄, ū)
+
+Batched `iLQR.fit` (src/forward_pass.jl:148-179).  The loop, the convergence test
+`sum((ū⁺ - ū).^2) <= tol` (per trajectory) and the monotone-cost assert stay here on the host;
+`ilqr_commit` applies the decision on the device (converged trajectories keep the iterate from
+BEFORE the last forward pass, exactly as the reference's `break` before the update does).
+"""
+function fit(x_init::Array{Float64,3}, u_init::Array{Float64,3}, p::Problem;
+             x_traj = nothing, max_iter::Int64 = 100, tol::Float64 = 1e-6)
+    N, n, B = size(x_init); M, m, _ = size(u_init)
+    @assert(N == M + 1, "size(x_init)[2] == size(u_init)[1], (# of states is 1 more than # of inputs in trajectory)")
+    s = Solver(p)
+    upload!(s, x_init, u_init, x_traj)
+    n_active = Ref{Int32}(B)
+    for iter = 1:max_iter
+        check(ccall((:ilqr_backward_pass, lib), Int32, (Ptr{Cvoid},), s.h), s.h)
+        check(ccall((:ilqr_forward_pass, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), s.h, C_NULL), s.h)
+        check(ccall((:ilqr_commit, lib), Int32, (Ptr{Cvoid}, Float64, Ptr{Int32}), s.h, tol, n_active), s.h)
+        n_active[] == 0 && break
+    end
+    st = download(s, STATUS, B; T = Int32)
+    @assert !any(st .& 8 .!= 0)          # src/forward_pass.jl:168  prev_cost > new_cost
+    return (download(s, X, N, n, B), download(s, U, M, m, B))
+end
+
+# single-problem convenience with the reference's exact shapes x[N×n], u[H×m]
+fit(x_init::Matrix{Float64}, u_init::Matrix{Float64}, p::Problem; kw...) = begin
+    (x, u) = fit(reshape(x_init, size(x_init)..., 1), reshape(u_init, size(u_init)..., 1), p; kw...)
+    (x[:, :, 1], u[:, :, 1])
+end
+
+end # module

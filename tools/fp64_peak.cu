@@ -5,7 +5,8 @@
 #include <cuda_runtime.h>
 
 template <int ILP>
-__global__ void dfma_throughput(double* out, int iters, double a, double b) {
+__global__ void dfma_throughput(double* out, int iters, double a, double b, int active_lanes) {
+  if ((threadIdx.x & 31) >= active_lanes) return;
   double acc[ILP];
 #pragma unroll
   for (int i = 0; i < ILP; ++i) acc[i] = threadIdx.x * 1e-3 + i;
@@ -42,7 +43,7 @@ int main() {
   const int blocks = p.multiProcessorCount * 4, threads = 512;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(e0);
-    dfma_throughput<8><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    dfma_throughput<8><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9, 32);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (rep > 0 && ms < best) best = ms;
@@ -51,6 +52,18 @@ int main() {
   int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   printf("{\"device\": \"%s\", \"sms\": %d, \"fp64_dfma_tflops\": %.3f, \"ms\": %.4f, \"clock_khz_attr\": %d",
          p.name, p.multiProcessorCount, flops / (best * 1e-3) / 1e12, best, clk);
+  // does a half-empty warp issue DFMA faster?  (per-warp-instruction time with 16 / 8 active lanes)
+  for (int lanes : {32, 16, 8}) {
+    float b2 = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      dfma_throughput<8><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9, lanes);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (ms < b2) b2 = ms;
+    }
+    printf(", \"ms_lanes%d\": %.4f", lanes, b2);
+  }
   const char* names[5] = {"dfma", "sincos", "div", "dadd", "dmul"};
   for (int mode = 0; mode < 5; ++mode) {
     latency_kernel<<<1, 32>>>(out, cyc, 4096, 0.999, 0.001, mode);
