@@ -38,6 +38,7 @@ struct ilqr_handle {
   bool compaction = true;      // retire + re-pack finished trajectories between iterations
   double* ab_scratch = nullptr; // [H*20][S] linearisations for the split backward pass (lazy)
   int32_t split_below = 20000; // use the split backward pass when nslots <= this
+  int32_t coop_below = 8192;   // ... and the warp-cooperative Riccati kernel when nslots <= this
   bool pend_bwd = false, pend_fwd = false;
   std::string err;
 };
@@ -234,6 +235,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   CKC(cudaStreamSynchronize(h->stream));
 #undef CKC
   if (const char* e = getenv("ILQR_SPLIT_BELOW")) h->split_below = atoi(e);
+  if (const char* e = getenv("ILQR_COOP_BELOW")) h->coop_below = atoi(e);
   if (const char* e = getenv("ILQR_COMPACTION")) h->compaction = atoi(e) != 0;
   h->mp.alpha = p->model_params[0]; h->mp.beta = p->model_params[1]; h->mp.delta = p->model_params[2];
   h->mp.dt = p->dt; h->mp.twobeta = 2 * p->model_params[1];
@@ -328,7 +330,7 @@ static int32_t backward_async(ilqr_handle* h) {
   const bool split = h->st.nslots <= h->split_below;
   if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
   cudaEventRecord(h->ev[0], h->stream);
-  if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->stream);
+  if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->st.nslots <= h->coop_below, h->stream);
   else launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[1], h->stream);
   h->launches += split ? 2 : 1;

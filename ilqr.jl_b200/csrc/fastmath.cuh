@@ -85,4 +85,66 @@ ILQR_FM_INLINE void sincos_bf(double x, double* sp, double* cp) {
   *cp = ((i + 1) & 2) ? -c0 : c0;
 }
 
+// L-wide versions: the same arithmetic on L independent arguments, written statement by statement
+// across the L lanes so that independent dependency chains sit next to each other in program
+// order.  A warp issues in order, so this is what lets one warp overlap the chains (the RK4 stages
+// are paired this way in two_link.cuh); results are bit-identical to the scalar versions.
+template <int L> ILQR_FM_INLINE void rcp_nr_n(const double x[L], double y[L]) {
+  double e[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) y[l] = fm_rcp_seed(x[l]);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+#pragma unroll
+    for (int l = 0; l < L; ++l) e[l] = fm_fma(-x[l], y[l], 1.0);
+#pragma unroll
+    for (int l = 0; l < L; ++l) y[l] = fm_fma(y[l], e[l], y[l]);
+  }
+}
+
+template <int L> ILQR_FM_INLINE void sincos_bf_n(const double x[L], double sp[L], double cp[L]) {
+  const double kMagic = 6755399441055744.0;
+  double t[L], q[L], r[L], z[L], z2[L], z4[L], ps[L], pc[L], sr[L], cr[L];
+  int i[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) t[l] = fm_fma(x[l], 0.6366197723675814, kMagic);
+#pragma unroll
+  for (int l = 0; l < L; ++l) { i[l] = fm_loint(t[l]); q[l] = t[l] - kMagic; }
+#pragma unroll
+  for (int l = 0; l < L; ++l) r[l] = fm_fma(-q[l], 1.5707963267948966, x[l]);
+#pragma unroll
+  for (int l = 0; l < L; ++l) r[l] = fm_fma(-q[l], 6.123233995736766e-17, r[l]);
+#pragma unroll
+  for (int l = 0; l < L; ++l) r[l] = fm_fma(-q[l], -1.4973849048591698e-33, r[l]);
+#pragma unroll
+  for (int l = 0; l < L; ++l) z[l] = r[l] * r[l];
+#pragma unroll
+  for (int l = 0; l < L; ++l) z2[l] = z[l] * z[l];
+#pragma unroll
+  for (int l = 0; l < L; ++l) z4[l] = z2[l] * z2[l];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const double s12 = fm_fma(z[l], 8.33333333332248946124e-03, -1.66666666666666324348e-01);
+    const double s34 = fm_fma(z[l], 2.75573137070700676789e-06, -1.98412698298579493134e-04);
+    const double s56 = fm_fma(z[l], 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    const double c12 = fm_fma(z[l], -1.38888888888741095749e-03, 4.16666666666666019037e-02);
+    const double c34 = fm_fma(z[l], -2.75573143513906633035e-07, 2.48015872894767294178e-05);
+    const double c56 = fm_fma(z[l], -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    ps[l] = fm_fma(z4[l], s56, fm_fma(z2[l], s34, s12));
+    pc[l] = fm_fma(z4[l], c56, fm_fma(z2[l], c34, c12));
+  }
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    sr[l] = fm_fma(r[l] * z[l], ps[l], r[l]);
+    cr[l] = fm_fma(z2[l], pc[l], fm_fma(-0.5, z[l], 1.0));
+  }
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const double s0 = (i[l] & 1) ? cr[l] : sr[l];
+    const double c0 = (i[l] & 1) ? sr[l] : cr[l];
+    sp[l] = (i[l] & 2) ? -s0 : s0;
+    cp[l] = ((i[l] + 1) & 2) ? -c0 : c0;
+  }
+}
+
 }  // namespace ilqr

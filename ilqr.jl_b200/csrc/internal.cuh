@@ -57,7 +57,9 @@ struct DevState {
 void init_kernel_attributes();   // opt-in dynamic shared memory sizes; call once per process/device
 void launch_bwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 // split backward pass (time-parallel linearisation + Riccati) for small active sets; AB: [H*20][S] scratch
-void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, double* AB, cudaStream_t s);
+// coop: warp-cooperative Riccati (4 lanes per trajectory) instead of the thread-local one
+void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, double* AB, bool coop,
+                               cudaStream_t s);
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0 /*[n][S] BF*/,
                                   cudaStream_t s);

@@ -129,7 +129,7 @@ bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
 #pragma unroll
       for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
       double d[NU], Kk[NU][NX];
-      riccati_step<NX, NU>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
+      riccati_step<NX, NU, true>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
       double kv[NK];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
@@ -152,28 +152,41 @@ bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
 // (trajectory, k) — and parks A (its three non-trivial columns) and B in HBM (20 doubles per
 // step, cheap when the set is small); the sequential Riccati kernel then only streams them.
 // ---------------------------------------------------------------------------------------------
+constexpr int kLinSteps = 8;   // time steps per thread: fewer, fatter blocks (block launch cost amortised)
+
 __global__ void __launch_bounds__(kBlock)
 lin_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp, double* __restrict__ AB) {
   const int s = blockIdx.x * kBlock + threadIdx.x;
-  const int k = blockIdx.y;
   if (s >= st.nslots) return;
   if (!st.active[s]) return;
   const int64_t S = st.S;
   const int cur = st.cur[s];
+  const int k0 = blockIdx.y * kLinSteps, k1 = min(k0 + kLinSteps, st.H);
   double xk[NX], uk[NU];
-  ldv<NX>(st.x[cur] + ((int64_t)k * S + s) * NX, xk);
-  ldv<NU>(st.u[cur] + ((int64_t)k * S + s) * NU, uk);
-  double A[NX][NX], Bm[NX][NU];
-  tl_linearize(mp, xk, uk, A, Bm);
-  double ab[kAB];
+  ldv<NX>(st.x[cur] + ((int64_t)k0 * S + s) * NX, xk);
+  ldv<NU>(st.u[cur] + ((int64_t)k0 * S + s) * NU, uk);
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    double xn[NX], un[NU];
+    const int kn = (k + 1 < k1) ? k + 1 : k;
+    ldv<NX>(st.x[cur] + ((int64_t)kn * S + s) * NX, xn);
+    ldv<NU>(st.u[cur] + ((int64_t)kn * S + s) * NU, un);
+    double A[NX][NX], Bm[NX][NU];
+    tl_linearize(mp, xk, uk, A, Bm);
+    double ab[kAB];
 #pragma unroll
-  for (int r = 0; r < NX; ++r) {
+    for (int r = 0; r < NX; ++r) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) ab[r * 3 + j] = A[r][j + 1];
+      for (int j = 0; j < 3; ++j) ab[r * 3 + j] = A[r][j + 1];
 #pragma unroll
-    for (int j = 0; j < NU; ++j) ab[12 + r * NU + j] = Bm[r][j];
+      for (int j = 0; j < NU; ++j) ab[12 + r * NU + j] = Bm[r][j];
+    }
+    stv<kAB>(AB + ((int64_t)k * S + s) * kAB, ab);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) xk[c] = xn[c];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) uk[i] = un[i];
   }
-  stv<kAB>(AB + ((int64_t)k * S + s) * kAB, ab);
 }
 
 constexpr int kRicStages = 3;
@@ -257,7 +270,7 @@ ric_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Co
 #pragma unroll
       for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
       double d[NU], Kk[NU][NX];
-      riccati_step<NX, NU>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
+      riccati_step<NX, NU, true>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
       double kv[NK];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
@@ -270,6 +283,223 @@ ric_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Co
     }
   }
   if (act && bad) st.status[s] |= ST_NAN_GAINS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative Riccati recursion for the latency-bound tail: FOUR lanes per trajectory, eight
+// trajectories per warp.  A lone warp doing the recursion thread-locally is issue bound (~370 fp64
+// instructions per step in one in-order stream).  Here lane j of a group owns COLUMN j of the
+// matrix work: SA[:,j] = S·A[:,j], G[:,j] = Bᵀ·SA[:,j], K[:,j], W[:,j] = H·K[:,j] + G[:,j],
+// 𝐒⁺[:,j], 𝐬⁺[j].  S and 𝐬 are kept replicated in the four lanes; the small m×m pieces (H, its
+// inverse, g, δu) are computed redundantly, so only K, G (after the solve) and the new 𝐒, 𝐬 columns
+// cross lanes — through a 4-lane shared-memory exchange (two STS.128/LDS.128 rounds per step).
+// Per lane ~150 fp64 instructions per step instead of ~370, and 4× as many warps to spread over
+// the idle SMs.  Same five-term update as riccati_step (src/backward_pass.jl:262-273).
+// ---------------------------------------------------------------------------------------------
+constexpr int kCoopTraj = 8;
+constexpr int kCoopStages = 4;
+constexpr int kCoopStageDoubles = kCoopTraj * (kAB + NX + NU);   // 208 doubles = 1664 B
+constexpr int kCoopXch = kCoopTraj * 4 * 6;                       // per (group, lane): 6 doubles
+
+__global__ void __launch_bounds__(kBlock)
+ric_coop_two_link(const __grid_constant__ DevState st, const __grid_constant__ CostP cp, const double* __restrict__ AB) {
+  __shared__ __align__(128) double ring_all[kWarps][kCoopStages][kCoopStageDoubles];
+  __shared__ __align__(16) double xch_all[kWarps][2][kCoopXch];
+  __shared__ __align__(8) uint64_t bars_all[kWarps][kCoopStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = lane >> 2, j = lane & 3;
+  const int s0 = (blockIdx.x * kWarps + warp) * kCoopTraj, s = s0 + t;
+  if (s0 >= st.nslots) return;
+  const bool act = s < st.nslots && st.active[s];
+  const unsigned amask = __ballot_sync(0xffffffffu, act);
+  if (amask == 0) return;
+  const int64_t S = st.S;
+  const int H = st.H;
+  const int cur = warp_cur(st, s, act, amask);
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  double (*ring)[kCoopStageDoubles] = ring_all[warp];
+  double* xk_g = &xch_all[warp][0][t * 24];   // exchange A: K,G columns   [lane j][4]
+  double* xs_g = &xch_all[warp][1][t * 24];   // exchange B: S column + s  [lane j][6]
+  uint64_t* bars = bars_all[warp];
+  constexpr int oAB = 0, oX = kCoopTraj * kAB, oU = oX + kCoopTraj * NX;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kCoopStages; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](int k, int stage) {
+    mbar_arrive_expect_tx(&bars[stage], kCoopStageDoubles * 8);
+    tma_load_1d(&ring[stage][oAB], AB + ((int64_t)k * S + s0) * kAB, kCoopTraj * kAB * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oX], X + ((int64_t)k * S + s0) * NX, kCoopTraj * NX * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oU], U + ((int64_t)k * S + s0) * NU, kCoopTraj * NU * 8, &bars[stage]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kCoopStages; ++i)
+      if (H - 1 - i >= 0) issue(H - 1 - i, i);
+  }
+  double Qd[NX], Rd[NU], qt[NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) { Qd[c] = 2.0 * cp.w_x[c]; qt[c] = cp.x_target[c]; }
+#pragma unroll
+  for (int i = 0; i < NU; ++i) Rd[i] = 2.0 * cp.w_u[i];
+  const double Qdj = j == 0 ? Qd[0] : j == 1 ? Qd[1] : j == 2 ? Qd[2] : Qd[3];
+  const double qtj = j == 0 ? qt[0] : j == 1 ? qt[1] : j == 2 ? qt[2] : qt[3];
+  // terminal expansion (replicated in the four lanes)
+  double sv[NX], Sm[NX][NX];
+  {
+    double xN[NX];
+    ldv<NX>(X + ((int64_t)H * S + s) * NX, xN);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      sv[c] = -2.0 * cp.w_xf[c] * (qt[c] - xN[c]);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Sm[c][i] = (c == i) ? 2.0 * cp.w_xf[c] : 0.0;
+    }
+  }
+  bool bad = false;
+#pragma unroll 1
+  for (int k = H - 1, it = 0; k >= 0; --k, ++it) {
+    const int stage = it % kCoopStages;
+    mbar_wait(&bars[stage], (it / kCoopStages) & 1);
+    const double* rb = &ring[stage][0];
+    double ab[kAB], uk[NU];
+    ldv<kAB>(rb + oAB + t * kAB, ab);
+    ldv<NU>(rb + oU + t * NU, uk);
+    const double xkj = rb[oX + t * NX + j];
+    // column j of A (column 0 is e₀ exactly)
+    double Aj[NX];
+    const int jm = (j == 0) ? 0 : j - 1;   // clamped so the j = 0 lanes read a valid (unused) address
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+      const double v = rb[oAB + t * kAB + r * 3 + jm];
+      Aj[r] = (j == 0) ? ((r == 0) ? 1.0 : 0.0) : v;
+    }
+    __syncwarp();
+    if (lane == 0 && k - kCoopStages >= 0) issue(k - kCoopStages, stage);
+    double A[NX][NX], Bm[NX][NU];
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+      A[r][0] = (r == 0) ? 1.0 : 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) A[r][c + 1] = ab[r * 3 + c];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Bm[r][c] = ab[12 + r * NU + c];
+    }
+    // column j: SAj = S·A[:,j], Gj = Bᵀ·SAj
+    double SAj[NX], Gj[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double acc = Sm[i][0] * Aj[0];
+#pragma unroll
+      for (int c = 1; c < NX; ++c) acc = fma(Sm[i][c], Aj[c], acc);
+      SAj[i] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double acc = Bm[0][a] * SAj[0];
+#pragma unroll
+      for (int i = 1; i < NX; ++i) acc = fma(Bm[i][a], SAj[i], acc);
+      Gj[a] = acc;
+    }
+    // replicated m×m part: SB, H = R + BᵀSB, g = r + Bᵀ𝐬, H_reg⁻¹
+    double SB[NX][NU], Hm[NU][NU], g[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        double acc = Sm[i][0] * Bm[0][a];
+#pragma unroll
+        for (int c = 1; c < NX; ++c) acc = fma(Sm[i][c], Bm[c][a], acc);
+        SB[i][a] = acc;
+      }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double acc = Rd[a] * uk[a];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) acc = fma(Bm[i][a], sv[i], acc);
+      g[a] = acc;
+#pragma unroll
+      for (int b = 0; b < NU; ++b) {
+        double a3 = Bm[0][a] * SB[0][b];
+#pragma unroll
+        for (int i = 1; i < NX; ++i) a3 = fma(Bm[i][a], SB[i][b], a3);
+        Hm[a][b] = a3 + ((a == b) ? Rd[a] : 0.0);
+      }
+    }
+    const double h00 = Hm[0][0] + st.reg, h11 = Hm[1][1] + st.reg;
+    const double det = fma(h00, h11, -(Hm[0][1] * Hm[1][0]));
+    const double nid = -rcp_nr(det);
+    const double i00 = h11 * nid, i01 = -Hm[0][1] * nid, i10 = -Hm[1][0] * nid, i11 = h00 * nid;
+    double d[NU], Kj[NU];
+    d[0] = fma(i00, g[0], i01 * g[1]); d[1] = fma(i10, g[0], i11 * g[1]);
+    Kj[0] = fma(i00, Gj[0], i01 * Gj[1]); Kj[1] = fma(i10, Gj[0], i11 * Gj[1]);
+    // hg = H δu + g, Wj = H Kj + Gj   (unregularised H)
+    double hg[NU], Wj[NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      hg[a] = fma(Hm[a][1], d[1], fma(Hm[a][0], d[0], g[a]));
+      Wj[a] = fma(Hm[a][1], Kj[1], fma(Hm[a][0], Kj[0], Gj[a]));
+    }
+    bad |= isnan(d[0]) | isnan(d[1]) | isnan(Kj[0]) | isnan(Kj[1]);
+    // exchange 1: every lane needs all columns of K and G
+    {
+      const double kg[4] = {Kj[0], Kj[1], Gj[0], Gj[1]};
+      stv<4>(xk_g + j * 4, kg);
+    }
+    __syncwarp();
+    double Kc[NX][NU], Gc[NX][NU];   // [column][row a]
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      double v[4];
+      ldv<4>(xk_g + c * 4, v);
+      Kc[c][0] = v[0]; Kc[c][1] = v[1]; Gc[c][0] = v[2]; Gc[c][1] = v[3];
+    }
+    // 𝐒⁺[:,j] = 𝐐[:,j] + Aᵀ·SAj + Kᵀ·Wj + Gᵀ·Kj ;  𝐬⁺[j] = 𝐪[j] + A[:,j]·𝐬 + Kj·hg + Gj·δu
+    double Sn[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double acc = (i == j) ? Qdj : 0.0;
+      if (i == 0) acc += SAj[0];
+      else {
+#pragma unroll
+        for (int c = 0; c < NX; ++c) acc = fma(A[c][i], SAj[c], acc);
+      }
+      acc = fma(Kc[i][0], Wj[0], acc); acc = fma(Kc[i][1], Wj[1], acc);
+      acc = fma(Gc[i][0], Kj[0], acc); acc = fma(Gc[i][1], Kj[1], acc);
+      Sn[i] = acc;
+    }
+    double svj = -Qdj * (qtj - xkj);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) svj = fma(Aj[c], sv[c], svj);
+    svj = fma(Kj[0], hg[0], svj); svj = fma(Kj[1], hg[1], svj);
+    svj = fma(Gj[0], d[0], svj); svj = fma(Gj[1], d[1], svj);
+    // gains out: lane j owns K[:,j] (component i + 2j); lane 0 also writes δuff
+    if (act) {
+      stv<NU>(st.K + ((int64_t)k * S + s) * NK + NU * j, Kj);
+      if (j == 0) stv<NU>(st.duff + ((int64_t)k * S + s) * NU, d);
+    }
+    // exchange 2: re-replicate 𝐒 and 𝐬
+    {
+      const double sc[6] = {Sn[0], Sn[1], Sn[2], Sn[3], svj, 0.0};
+      stv<6>(xs_g + j * 6, sc);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      double v[6];
+      ldv<6>(xs_g + c * 6, v);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Sm[i][c] = v[i];
+      sv[c] = v[4];
+    }
+    // the exchange buffers are rewritten only after the next step's first __syncwarp pair
+  }
+  const unsigned badm = __ballot_sync(0xffffffffu, bad);
+  if (act && j == 0 && ((badm >> (t * 4)) & 0xf)) st.status[s] |= ST_NAN_GAINS;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -630,11 +860,13 @@ void launch_bwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP
   if (st.nslots <= 0) return;
   bwd_lpt_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, cp);
 }
-void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, double* AB, cudaStream_t s) {
+void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, double* AB, bool coop,
+                               cudaStream_t s) {
   if (st.nslots <= 0) return;
-  dim3 grid(grid_for(st.nslots, kBlock), st.H);
+  dim3 grid(grid_for(st.nslots, kBlock), grid_for(st.H, kLinSteps));
   lin_lpt_two_link<<<grid, kBlock, 0, s>>>(st, mp, AB);
-  ric_lpt_two_link<<<grid_for(st.nslots, kBlock), kBlock, kRicSmem, s>>>(st, cp, AB);
+  if (coop) ric_coop_two_link<<<grid_for(st.nslots, kWarps * kCoopTraj), kBlock, 0, s>>>(st, cp, AB);
+  else ric_lpt_two_link<<<grid_for(st.nslots, kBlock), kBlock, kRicSmem, s>>>(st, cp, AB);
 }
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
   if (st.nslots <= 0) return;

@@ -74,7 +74,12 @@ __device__ __forceinline__ void neg_solve(const double Hr[M][M], const double rh
 
 // One Riccati step.  In: A (n×n), Bm (n×m), cost expansion (qv, rv, Qd, Rd
 // diagonals), reg; in/out: sv (n), S (n×n).  Out: d (m), K (m×n).
-template <int N, int M>
+// A_COL0_E0: the caller guarantees A[:,0] = e₀ exactly (true for the 2-link plugin, whose
+// dynamics do not depend on θ₁), which removes the multiplications by those 0/1 entries.
+// The value update is evaluated as 𝐒 = 𝐐 + Aᵀ(SA) + Kᵀ(HK + G) + GᵀK and
+// 𝐬 = 𝐪 + Aᵀ𝐬 + Kᵀ(Hδu + g) + Gᵀδu — the reference's five terms (unregularised H, no
+// symmetrisation), two of them sharing a factor.
+template <int N, int M, bool A_COL0_E0 = false>
 __device__ __forceinline__ void riccati_step(const double A[N][N], const double Bm[N][M], const double qv[N],
                                              const double rv[M], const double Qd[N], const double Rd[M], double reg,
                                              double sv[N], double S[N][N], double d[M], double K[M][N]) {
@@ -84,6 +89,7 @@ __device__ __forceinline__ void riccati_step(const double A[N][N], const double 
   for (int i = 0; i < N; ++i) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
+      if (A_COL0_E0 && j == 0) { SA[i][0] = S[i][0]; continue; }
       double acc = S[i][0] * A[0][j];
 #pragma unroll
       for (int k = 1; k < N; ++k) acc = fma(S[i][k], A[k][j], acc);
@@ -131,49 +137,51 @@ __device__ __forceinline__ void riccati_step(const double A[N][N], const double 
   neg_solve<M, N>(Hr, G, K);
 #pragma unroll
   for (int i = 0; i < M; ++i) d[i] = dd[i][0];
-  // Hd = H δu, HK = H K   (unregularised H)
-  double Hd[M], HK[M][N];
+  // hg = H δu + g, W = H K + G   (unregularised H)
+  double hg[M], W[M][N];
 #pragma unroll
   for (int i = 0; i < M; ++i) {
-    double acc = Hm[i][0] * d[0];
+    double acc = g[i][0];
 #pragma unroll
-    for (int k = 1; k < M; ++k) acc = fma(Hm[i][k], d[k], acc);
-    Hd[i] = acc;
+    for (int k = 0; k < M; ++k) acc = fma(Hm[i][k], d[k], acc);
+    hg[i] = acc;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      double a2 = Hm[i][0] * K[0][j];
+      double a2 = G[i][j];
 #pragma unroll
-      for (int k = 1; k < M; ++k) a2 = fma(Hm[i][k], K[k][j], a2);
-      HK[i][j] = a2;
+      for (int k = 0; k < M; ++k) a2 = fma(Hm[i][k], K[k][j], a2);
+      W[i][j] = a2;
     }
   }
-  // 𝐬 = 𝐪 + Aᵀ𝐬 + Kᵀ(Hδu) + Kᵀg + Gᵀδu
+  // 𝐬 = 𝐪 + Aᵀ𝐬 + Kᵀ(Hδu + g) + Gᵀδu
   double svn[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     double acc = qv[i];
+    if (A_COL0_E0 && i == 0) acc += sv[0];
+    else {
 #pragma unroll
-    for (int k = 0; k < N; ++k) acc = fma(A[k][i], sv[k], acc);
+      for (int k = 0; k < N; ++k) acc = fma(A[k][i], sv[k], acc);
+    }
 #pragma unroll
-    for (int k = 0; k < M; ++k) acc = fma(K[k][i], Hd[k], acc);
-#pragma unroll
-    for (int k = 0; k < M; ++k) acc = fma(K[k][i], g[k][0], acc);
+    for (int k = 0; k < M; ++k) acc = fma(K[k][i], hg[k], acc);
 #pragma unroll
     for (int k = 0; k < M; ++k) acc = fma(G[k][i], d[k], acc);
     svn[i] = acc;
   }
-  // 𝐒 = 𝐐 + Aᵀ(SA) + Kᵀ(HK) + KᵀG + GᵀK
+  // 𝐒 = 𝐐 + Aᵀ(SA) + Kᵀ(HK + G) + GᵀK
 #pragma unroll
   for (int i = 0; i < N; ++i) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       double acc = (i == j) ? Qd[i] : 0.0;
+      if (A_COL0_E0 && i == 0) acc += SA[0][j];
+      else {
 #pragma unroll
-      for (int k = 0; k < N; ++k) acc = fma(A[k][i], SA[k][j], acc);
+        for (int k = 0; k < N; ++k) acc = fma(A[k][i], SA[k][j], acc);
+      }
 #pragma unroll
-      for (int k = 0; k < M; ++k) acc = fma(K[k][i], HK[k][j], acc);
-#pragma unroll
-      for (int k = 0; k < M; ++k) acc = fma(K[k][i], G[k][j], acc);
+      for (int k = 0; k < M; ++k) acc = fma(K[k][i], W[k][j], acc);
 #pragma unroll
       for (int k = 0; k < M; ++k) acc = fma(G[k][i], K[k][j], acc);
       S[i][j] = acc;  // SA already consumed S; in-place update is safe

@@ -13,6 +13,14 @@
 //   E₁=ΔtΨ₁, E₂=Δt(Φ₂E₁/2+Ψ₂), E₃=Δt(Φ₃E₂/2+Ψ₃), E₄=Δt(Φ₄E₃+Ψ₄), B = (E₁+2E₂+2E₃+E₄)/6
 // with Φ = ∂fc/∂state, Ψ = ∂fc/∂u of the continuous dynamics at each stage point.
 // ∂fc/∂θ₁ ≡ 0, so column 0 of every D is zero and A[:,0] = e₀ exactly.
+//
+// Latency structure.  A stage evaluation splits into a θ₂-only part (sincos, M, 1/det: ~25
+// dependent fp64 ops) and a short finish that needs the stage velocities (~8 ops).  The stage
+// angles only need the velocities of the PREVIOUS stage (θ₂⁽²⁾ = θ₂ + ½Δt·w₂ is known at once,
+// θ₂⁽⁴⁾ right after the second finish), so the θ₂-only parts are evaluated in pairs — stages
+// (1,2), then (3,4) — with the two chains interleaved statement by statement.  A lone warp
+// (the tail of a batched solve) then sees ~2 instead of 4 serial sincos+reciprocal chains per
+// time step; the arithmetic and its results are unchanged.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,54 +33,69 @@ struct TwoLinkP {
   double twobeta;  // 2β  (2_link_helper_functions.jl:30: α+2*β*cos(θ₂))
 };
 
-// One evaluation of the joint accelerations and what the Jacobians reuse.
+// θ₂-only part of one stage: M = [a b; b δ], 1/det(M), sin/cos θ₂
+struct TLPre {
+  double s2, c2, a, b, idet;
+};
+// after the finish: joint accelerations
 struct TLStage {
-  double acc0, acc1;      // θ̈
-  double a, b, idet;      // M = [a b; b δ], 1/det(M)
-  double s2, c2;          // sin θ₂, cos θ₂
+  double acc0, acc1;
 };
 
-__device__ __forceinline__ void tl_accel(const TwoLinkP& p, double th2, double w1, double w2, double u1, double u2,
-                                         TLStage& o) {
-  double s2, c2;
-  sincos_bf(th2, &s2, &c2);
-  const double a = fma(p.twobeta, c2, p.alpha);
-  const double b = fma(p.beta, c2, p.delta);
-  const double det = fma(a, p.delta, -(b * b));
-  const double idet = rcp_nr(det);
+template <int L>
+__device__ __forceinline__ void tl_pre(const TwoLinkP& p, const double th2[L], TLPre out[L]) {
+  double s[L], c[L], a[L], b[L], det[L], id[L];
+  sincos_bf_n<L>(th2, s, c);
+#pragma unroll
+  for (int l = 0; l < L; ++l) { a[l] = fma(p.twobeta, c[l], p.alpha); b[l] = fma(p.beta, c[l], p.delta); }
+#pragma unroll
+  for (int l = 0; l < L; ++l) det[l] = fma(a[l], p.delta, -(b[l] * b[l]));
+  rcp_nr_n<L>(det, id);
+#pragma unroll
+  for (int l = 0; l < L; ++l) { out[l].s2 = s[l]; out[l].c2 = c[l]; out[l].a = a[l]; out[l].b = b[l]; out[l].idet = id[l]; }
+}
+
+__device__ __forceinline__ void tl_fin(const TwoLinkP& p, const TLPre& pr, double w1, double w2, double u1, double u2,
+                                       TLStage& o) {
   // h = C θ̇ = −β s₂ w₂ (w₁ + ½w₂, ½w₁)
-  const double tw2 = (-p.beta * s2) * w2;
+  const double tw2 = (-p.beta * pr.s2) * w2;
   const double h1 = tw2 * fma(0.5, w2, w1);
   const double h2 = tw2 * (0.5 * w1);
   const double r1 = u1 - h1, r2 = u2 - h2;
-  o.acc0 = (p.delta * r1 - b * r2) * idet;
-  o.acc1 = (a * r2 - b * r1) * idet;
-  o.a = a; o.b = b; o.idet = idet; o.s2 = s2; o.c2 = c2;
+  o.acc0 = (p.delta * r1 - pr.b * r2) * pr.idet;
+  o.acc1 = (pr.a * r2 - pr.b * r1) * pr.idet;
 }
 
-// x⁺ = f(x,u): the reference's RK4 step, same stage order and the same
+// x⁺ = f(x,u): the reference's RK4 step, same stage values and the same
 // x + (1/6)(k1 + 2k2 + 2k3 + k4) combination (:72-78).
 __device__ __forceinline__ void tl_step(const TwoLinkP& p, const double x[4], const double u[2], double xn[4]) {
   const double dt = p.dt;
   TLStage st;
+  TLPre pr[2];
   double k1[4], k2[4], k3[4], k4[4];
-  tl_accel(p, x[1], x[2], x[3], u[0], u[1], st);
-  k1[0] = dt * x[2]; k1[1] = dt * x[3]; k1[2] = dt * st.acc0; k1[3] = dt * st.acc1;
+  // stages 1 and 2: both angles are known up front
+  k1[0] = dt * x[2]; k1[1] = dt * x[3];
   {
-    const double w1 = fma(0.5, k1[2], x[2]), w2 = fma(0.5, k1[3], x[3]);
-    tl_accel(p, fma(0.5, k1[1], x[1]), w1, w2, u[0], u[1], st);
-    k2[0] = dt * w1; k2[1] = dt * w2; k2[2] = dt * st.acc0; k2[3] = dt * st.acc1;
+    const double th[2] = {x[1], fma(0.5, k1[1], x[1])};
+    tl_pre<2>(p, th, pr);
   }
+  tl_fin(p, pr[0], x[2], x[3], u[0], u[1], st);
+  k1[2] = dt * st.acc0; k1[3] = dt * st.acc1;
+  const double w1b = fma(0.5, k1[2], x[2]), w2b = fma(0.5, k1[3], x[3]);
+  tl_fin(p, pr[1], w1b, w2b, u[0], u[1], st);
+  k2[0] = dt * w1b; k2[1] = dt * w2b; k2[2] = dt * st.acc0; k2[3] = dt * st.acc1;
+  // stages 3 and 4: θ₂⁽³⁾ needs w⁽²⁾ only, θ₂⁽⁴⁾ needs w⁽³⁾ = w + ½k2
+  const double w1c = fma(0.5, k2[2], x[2]), w2c = fma(0.5, k2[3], x[3]);
+  k3[0] = dt * w1c; k3[1] = dt * w2c;
   {
-    const double w1 = fma(0.5, k2[2], x[2]), w2 = fma(0.5, k2[3], x[3]);
-    tl_accel(p, fma(0.5, k2[1], x[1]), w1, w2, u[0], u[1], st);
-    k3[0] = dt * w1; k3[1] = dt * w2; k3[2] = dt * st.acc0; k3[3] = dt * st.acc1;
+    const double th[2] = {fma(0.5, k2[1], x[1]), x[1] + k3[1]};
+    tl_pre<2>(p, th, pr);
   }
-  {
-    const double w1 = x[2] + k3[2], w2 = x[3] + k3[3];
-    tl_accel(p, x[1] + k3[1], w1, w2, u[0], u[1], st);
-    k4[0] = dt * w1; k4[1] = dt * w2; k4[2] = dt * st.acc0; k4[3] = dt * st.acc1;
-  }
+  tl_fin(p, pr[0], w1c, w2c, u[0], u[1], st);
+  k3[2] = dt * st.acc0; k3[3] = dt * st.acc1;
+  const double w1d = x[2] + k3[2], w2d = x[3] + k3[3];
+  tl_fin(p, pr[1], w1d, w2d, u[0], u[1], st);
+  k4[0] = dt * w1d; k4[1] = dt * w2d; k4[2] = dt * st.acc0; k4[3] = dt * st.acc1;
   const double sixth = 1.0 / 6.0;
 #pragma unroll
   for (int c = 0; c < 4; ++c) xn[c] = fma(sixth, ((k1[c] + 2.0 * k2[c]) + 2.0 * k3[c]) + k4[c], x[c]);
@@ -80,12 +103,12 @@ __device__ __forceinline__ void tl_step(const TwoLinkP& p, const double x[4], co
 
 // Stage Jacobian rows of the accelerations: phi[r][j] = ∂acc_r/∂(θ₂,w₁,w₂)[j];
 // mi = M⁻¹ entries (i11, i12, i22) = ∂acc/∂u.
-__device__ __forceinline__ void tl_stage_jac(const TwoLinkP& p, const TLStage& st, double w1, double w2,
+__device__ __forceinline__ void tl_stage_jac(const TwoLinkP& p, const TLPre& pr, const TLStage& st, double w1, double w2,
                                              double phi[2][3], double mi[3]) {
-  const double i11 = p.delta * st.idet, i12 = -st.b * st.idet, i22 = st.a * st.idet;
+  const double i11 = p.delta * pr.idet, i12 = -pr.b * pr.idet, i22 = pr.a * pr.idet;
   mi[0] = i11; mi[1] = i12; mi[2] = i22;
-  const double t = -p.beta * st.s2;   // ∂M/∂θ₂ = t [2 1; 1 0]
-  const double tc = -p.beta * st.c2;  // ∂h/∂θ₂ = tc w₂ (w₁+½w₂, ½w₁)
+  const double t = -p.beta * pr.s2;   // ∂M/∂θ₂ = t [2 1; 1 0]
+  const double tc = -p.beta * pr.c2;  // ∂h/∂θ₂ = tc w₂ (w₁+½w₂, ½w₁)
   const double hw = fma(0.5, w2, w1);
   // v = ∂M/∂θ₂·acc + ∂h/∂θ₂ ;  ∂acc/∂θ₂ = −M⁻¹ v
   const double v1 = fma(t, fma(2.0, st.acc0, st.acc1), tc * w2 * hw);
@@ -131,13 +154,20 @@ __device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4
                                              double Bm[4][2]) {
   const double dt = p.dt;
   TLStage st;
+  TLPre pr[2];
   double phi[2][3], mi[3];
   double D[4][3], E[4][2], X[4][3], Y[4][2], SD[4][3], SE[4][2];
 
-  // ---- stage 1 at s₁ = x : D₁ = ΔtΦ₁, E₁ = ΔtΨ₁ (X₀ = I, Y₀ = 0 folded by hand)
-  tl_accel(p, x[1], x[2], x[3], u[0], u[1], st);
-  tl_stage_jac(p, st, x[2], x[3], phi, mi);
-  const double k1_1 = dt * x[3], k1_2 = dt * st.acc0, k1_3 = dt * st.acc1;
+  // ---- stages 1, 2: θ₂-only parts together
+  const double k1_1 = dt * x[3];
+  {
+    const double th[2] = {x[1], fma(0.5, k1_1, x[1])};
+    tl_pre<2>(p, th, pr);
+  }
+  // stage 1 at s₁ = x : D₁ = ΔtΦ₁, E₁ = ΔtΨ₁ (X₀ = I, Y₀ = 0 folded by hand)
+  tl_fin(p, pr[0], x[2], x[3], u[0], u[1], st);
+  tl_stage_jac(p, pr[0], st, x[2], x[3], phi, mi);
+  const double k1_2 = dt * st.acc0, k1_3 = dt * st.acc1;
   D[0][0] = 0.0; D[0][1] = dt;  D[0][2] = 0.0;
   D[1][0] = 0.0; D[1][1] = 0.0; D[1][2] = dt;
 #pragma unroll
@@ -154,9 +184,16 @@ __device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4
 
   // ---- stage 2 at s₂ = x + k₁/2
   double w1 = fma(0.5, k1_2, x[2]), w2 = fma(0.5, k1_3, x[3]);
-  tl_accel(p, fma(0.5, k1_1, x[1]), w1, w2, u[0], u[1], st);
-  tl_stage_jac(p, st, w1, w2, phi, mi);
+  tl_fin(p, pr[1], w1, w2, u[0], u[1], st);
+  tl_stage_jac(p, pr[1], st, w1, w2, phi, mi);
   const double k2_1 = dt * w2, k2_2 = dt * st.acc0, k2_3 = dt * st.acc1;
+  // stages 3, 4: θ₂-only parts together (θ₂⁽³⁾ = θ₂ + ½k2_1, θ₂⁽⁴⁾ = θ₂ + Δt·w₂⁽³⁾)
+  const double w1c = fma(0.5, k2_2, x[2]), w2c = fma(0.5, k2_3, x[3]);
+  const double k3_1 = dt * w2c;
+  {
+    const double th[2] = {fma(0.5, k2_1, x[1]), x[1] + k3_1};
+    tl_pre<2>(p, th, pr);
+  }
   tl_chain(dt, phi, mi, X, Y, D, E);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -167,10 +204,9 @@ __device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4
   }
 
   // ---- stage 3 at s₃ = x + k₂/2
-  w1 = fma(0.5, k2_2, x[2]); w2 = fma(0.5, k2_3, x[3]);
-  tl_accel(p, fma(0.5, k2_1, x[1]), w1, w2, u[0], u[1], st);
-  tl_stage_jac(p, st, w1, w2, phi, mi);
-  const double k3_1 = dt * w2, k3_2 = dt * st.acc0, k3_3 = dt * st.acc1;
+  tl_fin(p, pr[0], w1c, w2c, u[0], u[1], st);
+  tl_stage_jac(p, pr[0], st, w1c, w2c, phi, mi);
+  const double k3_2 = dt * st.acc0, k3_3 = dt * st.acc1;
   tl_chain(dt, phi, mi, X, Y, D, E);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -182,8 +218,8 @@ __device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4
 
   // ---- stage 4 at s₄ = x + k₃
   w1 = x[2] + k3_2; w2 = x[3] + k3_3;
-  tl_accel(p, x[1] + k3_1, w1, w2, u[0], u[1], st);
-  tl_stage_jac(p, st, w1, w2, phi, mi);
+  tl_fin(p, pr[1], w1, w2, u[0], u[1], st);
+  tl_stage_jac(p, pr[1], st, w1, w2, phi, mi);
   tl_chain(dt, phi, mi, X, Y, D, E);
 
   const double sixth = 1.0 / 6.0;
