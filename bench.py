@@ -3,11 +3,15 @@
 B = 65,536 trajectories per GPU, fp64), one process per GPU.
 
 A "step" = one batched `fit` (src/forward_pass.jl:148-179 semantics, tol 1e-6, max_iter 100)
-of the whole batch.  `value` times it with the inputs already resident in HBM (boundary
-layout → device layout → fit → boundary layout, all on device); `e2e` times the same
-solve through the host-facing C-ABI call ilqr_solve with pinned HOST buffers (H2D and D2H
-copies inside the timed region).  Shards are independent (no data-path collective); NCCL
-only gathers the per-trajectory costs / iteration counts after the timed region.
+of the whole batch.  The K timed steps go through the library's pool scheduler (ilqr_pool_*),
+which keeps up to 6 batches in flight per GPU so the latency-bound tail of one batch overlaps
+the full-width iterations of the next; each step still solves its whole batch to the same
+result.  `value` times this with the inputs resident in HBM (boundary layout → device layout →
+fit → boundary layout, all on device); `e2e` is the same with pinned HOST buffers (H2D and D2H
+inside the timed region, through ilqr_pool_submit = ilqr_solve per batch); `isolated` reports one
+batch at a time.  `roofline` comes from the isolated solves (per-kernel CUDA-event times).
+Shards are independent (no data-path collective); NCCL only gathers the per-trajectory costs /
+iteration counts after the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]
   python bench.py --impl reference ...   # CPU restatement of the reference (oracle) on all host cores
@@ -40,14 +44,14 @@ WORKLOAD = "configs[1]: batched 2-link arm, B=65536 x0~U[0,1)^4 per GPU, H=200, 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (debug only; default = config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-pipelined", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=None, help="batches in flight per GPU (pool handles)")
     return ap.parse_args()
 
 
@@ -162,12 +166,18 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- GPU arm
+IN_FLIGHT = 6   # batches kept in flight per GPU by the pool scheduler (ilqr_pool_*); --in-flight overrides
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import ilqr_b200
     from ilqr_b200 import _abi
 
+    global IN_FLIGHT
+    if args.in_flight:
+        IN_FLIGHT = args.in_flight
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -185,7 +195,7 @@ def run_b200(args):
 
     prob = ilqr_b200.two_link_problem(H, B, device=local)
     s = ilqr_b200.BatchSolver(prob)
-    stream = torch.cuda.ExternalStream(s.stream_ptr(), device=torch.device("cuda", local))
+    pool = ilqr_b200.SolverPool(prob, IN_FLIGHT)
 
     # inputs: generated once, kept resident in HBM in the boundary layout
     x0 = np.asfortranarray(make_x0(B, rank).T)
@@ -193,68 +203,90 @@ def run_b200(args):
     s.upload_x0(x0, u0)
     dx = torch.empty((B, N_, NKNOT), dtype=torch.float64, device="cuda")     # == Julia x[N,n,B]
     du = torch.zeros((B, M_, H), dtype=torch.float64, device="cuda")
-    ox, ou = torch.empty_like(dx), torch.empty_like(du)
     s.download_device(_abi.X, dx.data_ptr())
+    outs = [(torch.empty_like(dx), torch.empty_like(du)) for _ in range(IN_FLIGHT)]
     torch.cuda.synchronize()
-
-    def step_resident():
-        s.upload_device(dx.data_ptr(), du.data_ptr())
-        it = s.fit(MAX_ITER, TOL)
-        s.download_device(_abi.X, ox.data_ptr()); s.download_device(_abi.U, ou.data_ptr())
-        return it
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = s.launch_count()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, s.launch_count() - l0
+        return ms
 
-    for _ in range(args.warmup):
-        iters_run = step_resident()
+    def run_pipelined(steps, submit_one):
+        """`steps` batch solves through the pool, at most IN_FLIGHT in flight; CUDA events bracket the region."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = pool.launch_count()
+        e0.record()
+        tickets = []
+        for i in range(steps):
+            if i >= IN_FLIGHT:
+                pool.wait(tickets[i - IN_FLIGHT])     # its output buffers are about to be reused
+            tickets.append(submit_one(i))
+        for t in tickets[max(0, steps - IN_FLIGHT):]:
+            pool.wait(t)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), pool.launch_count() - l0
+
+    def submit_resident(i):
+        ox, ou = outs[i % IN_FLIGHT]
+        return pool.submit_ptrs(dx.data_ptr(), du.data_ptr(), None, MAX_ITER, TOL, ox.data_ptr(), ou.data_ptr(), device=True)
+
+    if args.warmup > 0:
+        run_pipelined(max(args.warmup, IN_FLIGHT), submit_resident)   # every handle warmed at least once
     clocks = ClockSampler(local); clocks.start()
-    prof_acc = dict(bwd_ms=0.0, fwd_ms=0.0, bwd_launches=0, fwd_launches=0, traj_iters=0.0, first_bwd_ms=0.0, first_fwd_ms=0.0)
-
-    def step_and_profile():
-        step_resident()
-        p = s.profile()
-        for k in prof_acc:
-            prof_acc[k] += p[k]
-
-    ms_total, launches = timed(step_and_profile, args.steps)
+    ms_total, launches = run_pipelined(args.steps, submit_resident)
     clk = clocks.stop()
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # roofline of the dominant kernel (device time measured live with CUDA events on the handle's stream)
+    # ---- one batch at a time on a single handle: per-kernel device times for the roofline, and the
+    # latency of an isolated solve
+    stream = torch.cuda.ExternalStream(s.stream_ptr(), device=torch.device("cuda", local))
+    prof_acc = dict(bwd_ms=0.0, fwd_ms=0.0, bwd_launches=0, fwd_launches=0, traj_iters=0.0, first_bwd_ms=0.0, first_fwd_ms=0.0)
+    iso_steps = 3
+    ox, ou = outs[0]
+    for rep in range(1 + iso_steps):
+        if rep == 1:
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        s.upload_device(dx.data_ptr(), du.data_ptr())
+        s.fit(MAX_ITER, TOL)
+        s.download_device(_abi.X, ox.data_ptr()); s.download_device(_abi.U, ou.data_ptr())
+        if rep >= 1:
+            p = s.profile()
+            for k in prof_acc:
+                prof_acc[k] += p[k]
+    e1.record(stream)
+    barrier()
+    iso_ms = max_over_ranks(e0.elapsed_time(e1)) / iso_steps
+
     dom = "bwd" if prof_acc["bwd_ms"] >= prof_acc["fwd_ms"] else "fwd"
     per_traj = BWD_BYTES if dom == "bwd" else FWD_BYTES
     dom_ms = prof_acc[dom + "_ms"]
     achieved = per_traj * prof_acc["traj_iters"] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    full_iter_ms = (prof_acc["first_bwd_ms"] + prof_acc["first_fwd_ms"]) / args.steps
-    roofline = {"bound": "hbm", "kernel": "bwd_lpt_two_link" if dom == "bwd" else "fwd_lpt_two_link",
+    full_iter_ms = (prof_acc["first_bwd_ms"] + prof_acc["first_fwd_ms"]) / iso_steps
+    first_dom_ms = prof_acc["first_" + dom + "_ms"] / iso_steps
+    roofline = {"bound": "hbm", "kernel": "bwd_lpt_two_link (+ lin/ric split kernels on small active sets)" if dom == "bwd" else "fwd_lpt_two_link",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": 1.632e9 if dom == "bwd" else 2.289e9, "peak_source": peak_src,
+                "traffic_note": "dram read+write per full-batch launch from profiles/ncu_full_r1_lpt_fullbatch.txt (algorithmic: %.3e)" % (per_traj * B_PER_GPU),
                 "algorithmic_bytes_per_trajectory": per_traj,
                 "avg_launch_ms": dom_ms / max(1, prof_acc[dom + "_launches"]),
-                "share_of_step": dom_ms / ms_total,
-                "both_kernels_GBps_first_iteration": (BWD_BYTES + FWD_BYTES) * B / (full_iter_ms * 1e-3) / 1e9 if full_iter_ms else None}
-
-    # FP64-pipe view of the same launches (the nominal bound of this path): DFMA-class
+                "measured_on": "isolated solves (one batch at a time), CUDA events on the handle's stream; averaged over all launches of a fit incl. the latency-bound tail",
+                "full_batch_launch": {"ms": first_dom_ms, "achieved": per_traj * B / (first_dom_ms * 1e-3) / 1e9 if first_dom_ms else None,
+                                      "frac": per_traj * B / (first_dom_ms * 1e-3) / 1e9 / hbm_peak if first_dom_ms else None},
+                "both_kernels_GBps_full_batch_iteration": (BWD_BYTES + FWD_BYTES) * B / (full_iter_ms * 1e-3) / 1e9 if full_iter_ms else None}
+    # FP64-pipe view of the same launches (the binding roofline of this path, SURVEY §8d): DFMA-class
     # instructions per trajectory-step counted from SASS (tools/sass_mix.py), 2 flops each
     fp64_peak_tf = None
     try:
@@ -263,67 +295,44 @@ def run_b200(args):
         pass
     FP64_INSTR = {"bwd": 928, "fwd": 273}
     flops = 2.0 * FP64_INSTR[dom] * H * prof_acc["traj_iters"]
-    roofline["fp64"] = {"achieved_tflops": flops / (dom_ms * 1e-3) / 1e12 if dom_ms else None,
-                        "peak_tflops": fp64_peak_tf, "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
+    roofline["fp64"] = {"achieved_tflops": flops / (dom_ms * 1e-3) / 1e12 if dom_ms else None, "peak_tflops": fp64_peak_tf,
+                        "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
                         "fp64_instr_per_trajectory_step": FP64_INSTR[dom],
-                        "note": "whole-fit average incl. the latency-bound tail; first-iteration (full batch) figures in profiles/"}
+                        "full_batch_launch_tflops": 2.0 * FP64_INSTR[dom] * H * B / (first_dom_ms * 1e-3) / 1e12 if first_dom_ms else None}
     if fp64_peak_tf and roofline["fp64"]["achieved_tflops"]:
         roofline["fp64"]["frac"] = roofline["fp64"]["achieved_tflops"] / fp64_peak_tf
+        if roofline["fp64"]["full_batch_launch_tflops"]:
+            roofline["fp64"]["full_batch_launch_frac"] = roofline["fp64"]["full_batch_launch_tflops"] / fp64_peak_tf
+    isolated = {"value": world * B / (iso_ms * 1e-3), "unit": UNIT, "ms_per_step": iso_ms,
+                "ms_per_iteration_full_batch": full_iter_ms, "batch_iterations_per_step": prof_acc["bwd_launches"] / iso_steps,
+                "note": "one batch at a time on one handle (no overlap between steps)"}
 
-    # pipelined throughput: the same K steps with up to 4 batches in flight on 4 handles (tails overlap bulks)
-    pipelined = None
-    if not args.no_pipelined:
-        import threading
-        nh = 4
-        extra = [ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, B, device=local)) for _ in range(nh - 1)]
-        pool = [s] + extra
-
-        def worker(sv, n):
-            for _ in range(n):
-                sv.upload_device(dx.data_ptr(), du.data_ptr())
-                sv.fit(MAX_ITER, TOL)
-
-        ksteps = max(nh, (args.steps + nh - 1) // nh * nh)
-        for rep in range(2):   # first repetition warms the extra handles up
-            barrier()
-            th = [threading.Thread(target=worker, args=(sv, ksteps // nh)) for sv in pool]
-            t0 = time.perf_counter()
-            [t.start() for t in th]
-            [t.join() for t in th]
-            barrier()
-            dtp = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dtp], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dtp = float(t.item())
-        pipelined = {"value": world * B * ksteps / dtp, "unit": UNIT, "batches_in_flight": nh, "steps": ksteps,
-                     "ms_per_step": 1e3 * dtp / ksteps, "timing": "host wall clock around barrier+synchronize"}
-        for sv in extra:
-            sv.close()
-
-    # end to end through the host-facing call with pinned host buffers
+    # ---- end to end through the host-facing C-ABI call with pinned host buffers (H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
         hx = torch.empty((B, N_, NKNOT), dtype=torch.float64).pin_memory(); hx.copy_(dx)
         hu = torch.zeros((B, M_, H), dtype=torch.float64).pin_memory()
-        hox = torch.empty_like(hx).pin_memory(); hou = torch.empty_like(hu).pin_memory()
-        hc = torch.empty(B, dtype=torch.float64).pin_memory()
-        hi = torch.empty(B, dtype=torch.int32).pin_memory(); hs = torch.empty(B, dtype=torch.int32).pin_memory()
-        lib = _abi.load_library()
+        houts = [(torch.empty_like(hx).pin_memory(), torch.empty_like(hu).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
+                  torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(IN_FLIGHT)]
 
-        def step_e2e():
-            rc = lib.ilqr_solve(s._h, hx.data_ptr(), hu.data_ptr(), None, MAX_ITER, TOL, hox.data_ptr(), hou.data_ptr(),
-                                hc.data_ptr(), hi.data_ptr(), hs.data_ptr())
-            if rc != 0:
-                raise RuntimeError(lib.ilqr_last_error(s._h).decode())
+        def submit_host(i):
+            hox, hou, hc, hi, hs = houts[i % IN_FLIGHT]
+            return pool.submit_ptrs(hx.data_ptr(), hu.data_ptr(), None, MAX_ITER, TOL, hox.data_ptr(), hou.data_ptr(),
+                                    hc.data_ptr(), hi.data_ptr(), hs.data_ptr(), device=False)
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_e2e()
-        ms_e2e, _ = timed(step_e2e, args.steps)
+        run_pipelined(IN_FLIGHT, submit_host)
+        ms_e2e, _ = run_pipelined(args.steps, submit_host)
         h2d = hx.numel() * 8 + hu.numel() * 8
-        d2h = hox.numel() * 8 + hou.numel() * 8 + B * 8 + B * 4 + B * 4
+        d2h = hx.numel() * 8 + hu.numel() * 8 + B * 8 + B * 4 + B * 4
+        # one isolated host-to-host solve for reference
+        barrier(); t0 = time.perf_counter()
+        pool.wait(submit_host(0)); torch.cuda.synchronize()
+        iso_e2e_ms = (time.perf_counter() - t0) * 1e3
         e2e = {"value": world * B / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps}
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "batches_in_flight": IN_FLIGHT,
+               "isolated_ms_per_step": iso_e2e_ms,
+               "api": "ilqr_pool_submit (= ilqr_solve per batch): pinned host x_init,u_init in, host x,u,cost,iters,status out"}
+        final_cost_sample = float(houts[0][2].mean().item())
 
     # the only collective: gather final costs / iteration counts (after the timed region)
     iters = torch.from_numpy(s.download(_abi.ITERS)).cuda()
@@ -343,16 +352,20 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD if B == B_PER_GPU else WORKLOAD + " [DEBUG batch=%d]" % B,
-                       "trajectories_per_gpu": B, "l2_policy": "inputs larger than L2 (%.2f GB working set per GPU vs 126 MB L2)" % (3.2 * B / 65536),
+                       "trajectories_per_gpu": B, "batches_in_flight": IN_FLIGHT,
+                       "step": "one batched fit of the whole batch; the K steps are submitted to the pool scheduler, which keeps up to %d "
+                               "batches in flight so that the latency-bound tail of one overlaps the bulk of the next (every step still "
+                               "solves its full batch to the same result); see `isolated` for one batch at a time" % IN_FLIGHT,
+                       "l2_policy": "inputs larger than L2 (%.2f GB working set per handle vs 126 MB L2)" % (3.2 * B / 65536),
                        "sharding": "independent batch slices per GPU, no data-path collective"},
-            "ms_per_iteration_full_batch": full_iter_ms,
-            "batch_iterations_per_step": prof_acc["bwd_launches"] / args.steps,
+            "isolated": isolated,
             "mean_iterations_per_trajectory": float(iters.double().mean().item()),
             "converged_fraction": float(((torch.from_numpy(status) & 16) != 0).double().mean().item()),
             "mean_final_cost": float(cost.mean().item()),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "pipelined": pipelined, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))
+    pool.close()
     s.close()
     if world > 1:
         dist.destroy_process_group()

@@ -56,6 +56,18 @@ SYMBOLS = {
     "ilqr_solve": (ctypes.c_int32, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                     ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_pool_create": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.POINTER(_H)]),
+    "ilqr_pool_destroy": (ctypes.c_int32, [_H]),
+    "ilqr_pool_last_error": (ctypes.c_char_p, [_H]),
+    "ilqr_pool_submit": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                          ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_pool_submit_device": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                                 ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_pool_wait": (ctypes.c_int32, [_H, ctypes.c_int64]),
+    "ilqr_pool_wait_all": (ctypes.c_int32, [_H]),
+    "ilqr_pool_launch_count": (ctypes.c_int64, [_H]),
     "ilqr_host_alloc": (ctypes.c_int32, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
     "ilqr_host_free": (ctypes.c_int32, [ctypes.c_void_p]),
     "ilqr_launch_count": (ctypes.c_int64, [_H]),

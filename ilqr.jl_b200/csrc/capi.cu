@@ -78,6 +78,7 @@ void free_all(ilqr_handle* h) {
   cudaFree(s.status); cudaFree(s.iters); cudaFree(s.active); cudaFree(s.cur); cudaFree(s.bar); cudaFree(s.n_active);
   cudaFree(s.traj); cudaFree(s.r_prev_cost); cudaFree(s.r_new_cost); cudaFree(s.r_alpha); cudaFree(s.r_du2);
   cudaFree(s.r_status); cudaFree(s.r_iters); cudaFree(s.r_active);
+  cudaFree(s.blocks_done);
   cudaFree(s.retire_list); cudaFree(s.move_src); cudaFree(s.move_dst); cudaFree(s.n_move);
   cudaFree(h->ab_scratch);
   cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
@@ -225,7 +226,11 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   CKC(dalloc(&h->stage_x, N * n * (size_t)p->B)); CKC(dalloc(&h->stage_u, H * m * (size_t)p->B));
   CKC(dalloc(&h->scratch_b, S));
   s.out_x = h->stage_x; s.out_u = h->stage_u;
-  CKC(cudaHostAlloc((void**)&h->pinned_i32, 64, cudaHostAllocDefault));
+  CKC(cudaHostAlloc((void**)&h->pinned_i32, 64, cudaHostAllocMapped));
+  CKC(cudaHostGetDevicePointer((void**)&s.n_active_host, h->pinned_i32, 0));
+  CKC(dalloc(&s.blocks_done, 1));
+  CKC(cudaMemsetAsync(s.blocks_done, 0, sizeof(uint32_t), h->stream));
+  CKC(cudaMemsetAsync(s.n_active, 0, sizeof(int32_t), h->stream));
   // padded slots must never hold NaN garbage that a kernel could trip on
   for (int i = 0; i < 2; ++i) { CKC(cudaMemsetAsync(s.x[i], 0, sizeof(double) * N * n * S, h->stream));
                                 CKC(cudaMemsetAsync(s.u[i], 0, sizeof(double) * H * m * S, h->stream)); }
@@ -357,10 +362,10 @@ static int32_t commit_async(ilqr_handle* h, double tol) {
 }
 
 static int32_t read_n_active(ilqr_handle* h, int32_t* n_active) {
-  CK(h, cudaMemcpyAsync(h->pinned_i32, h->st.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  // commit_kernel's last block stored the count into the mapped pinned int; nslots == 0 launches nothing
   CK(h, cudaStreamSynchronize(h->stream));
   accumulate_profile(h);
-  const int32_t na = h->pinned_i32[0];
+  const int32_t na = h->st.nslots > 0 ? ((volatile int32_t*)h->pinned_i32)[0] : 0;
   h->n_active_host = na;
   if (n_active) *n_active = na;
   // retire + re-pack once enough slots have finished to free whole warps

@@ -52,10 +52,13 @@ __device__ __forceinline__ int warp_cur(const DevState& st, int s, bool act, uns
 // Fused backward pass: linearisation + cost expansion + Riccati step per time step, k = H-1 … 0.
 // Ring: D stages of {x slab 1 KB, u slab 512 B} per warp.
 // ---------------------------------------------------------------------------------------------
+#ifndef ILQR_BWD_MIN_BLOCKS
+#define ILQR_BWD_MIN_BLOCKS 3   // ≤ 168 registers ⇒ 12 warps/SM (3 per sub-partition) feed the FP64 pipe
+#endif
 constexpr int kBwdStages = 4;
 constexpr int kBwdStageDoubles = 32 * (NX + NU);
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, ILQR_BWD_MIN_BLOCKS)
 bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
                  const __grid_constant__ CostP cp) {
   __shared__ __align__(128) double ring_all[kWarps][kBwdStages][kBwdStageDoubles];
@@ -695,6 +698,20 @@ __global__ void commit_kernel(const __grid_constant__ DevState st, double tol) {
   }
   const unsigned m = __ballot_sync(0xffffffffu, still);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(st.n_active, __popc(m));
+  // last block publishes the count straight into mapped host memory (no DMA-engine copy, which would
+  // queue behind other handles' bulk PCIe transfers) and re-arms the counters for the next iteration
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(st.blocks_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    const int32_t total = atomicAdd(st.n_active, 0);
+    *st.n_active_host = total;
+    *st.n_active = 0;
+    *st.blocks_done = 0u;
+    __threadfence_system();
+  }
 }
 
 __global__ void finalize_max_iter_kernel(const __grid_constant__ DevState st) {
@@ -877,7 +894,6 @@ void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const 
   rollout_init_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, d_x0);
 }
 void launch_commit(const DevState& st, double tol, cudaStream_t s) {
-  cudaMemsetAsync(st.n_active, 0, sizeof(int32_t), s);
   if (st.nslots > 0) commit_kernel<<<grid_for(st.nslots, 256), 256, 0, s>>>(st, tol);
 }
 void launch_finalize_max_iter(const DevState& st, cudaStream_t s) {

@@ -200,6 +200,65 @@ class BatchSolver:
         self._ck(self._lib.ilqr_sync(self._h), "ilqr_sync")
 
 
+class SolverPool:
+    """ilqr_pool: several batches in flight on one GPU (one handle + worker thread each).
+    submit*() return tickets without blocking; the caller keeps the buffers alive until wait()."""
+
+    def __init__(self, problem, n_handles=4):
+        self._lib = _abi.load_library()
+        self.problem = problem
+        self._p = ctypes.c_void_p()
+        rc = self._lib.ilqr_pool_create(ctypes.byref(problem), int(n_handles), ctypes.byref(self._p))
+        if rc != 0:
+            raise IlqrError("ilqr_pool_create: %s" % self._lib.ilqr_pool_last_error(None).decode())
+        self.n_handles = n_handles
+
+    def close(self):
+        if self._p:
+            self._lib.ilqr_pool_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit_ptrs(self, x, u, xt, max_iter, tol, xo, uo, cost=None, iters=None, status=None, device=False):
+        """Raw addresses (ints): host pointers, or device pointers with device=True."""
+        fn = self._lib.ilqr_pool_submit_device if device else self._lib.ilqr_pool_submit
+        t = fn(self._p, x, u, xt, int(max_iter), float(tol), xo, uo, cost, iters, status)
+        if t < 0:
+            raise IlqrError("ilqr_pool_submit failed (%d)" % t)
+        return t
+
+    def submit(self, x_init, u_init, out, x_traj=None, max_iter=100, tol=1e-6):
+        """NumPy (Fortran-ordered, boundary layout) in, preallocated `out` dict (x,u,cost,iters,status) filled on wait."""
+        xt = None if x_traj is None else x_traj.ctypes.data
+        return self.submit_ptrs(x_init.ctypes.data, u_init.ctypes.data, xt, max_iter, tol, out["x"].ctypes.data,
+                                out["u"].ctypes.data, out["cost"].ctypes.data, out["iters"].ctypes.data,
+                                out["status"].ctypes.data)
+
+    def wait(self, ticket):
+        rc = self._lib.ilqr_pool_wait(self._p, ticket)
+        if rc != 0:
+            raise IlqrError("pooled solve failed (%d): %s" % (rc, self._lib.ilqr_pool_last_error(self._p).decode()))
+
+    def wait_all(self):
+        rc = self._lib.ilqr_pool_wait_all(self._p)
+        if rc != 0:
+            raise IlqrError("pooled solve failed (%d): %s" % (rc, self._lib.ilqr_pool_last_error(self._p).decode()))
+
+    def launch_count(self):
+        return int(self._lib.ilqr_pool_launch_count(self._p))
+
+
 def _batch_of(x):
     x = _f64(x)
     return (x.shape[2] if x.ndim == 3 else 1), x.ndim == 2

@@ -191,6 +191,27 @@ int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, c
                    int32_t max_iter, double tol, double* x_out, double* u_out, double* cost_out,
                    int32_t* iters_out, int32_t* status_out);
 
+/* ---- batch scheduler: several batches in flight on one GPU --------------------------------
+ * Iteration counts are heavy tailed, so the last iterations of a batch run on few trajectories and
+ * leave the GPU mostly idle.  A pool owns n_handles handles (own stream + device buffers each) and
+ * one worker thread per handle; submitted batches are solved exactly as ilqr_solve would solve
+ * them, but the tail of one overlaps the full-width iterations and the PCIe copies of the others.
+ * submit returns a ticket (>= 0) without blocking; buffers must stay valid until the ticket is waited. */
+typedef struct ilqr_pool ilqr_pool;
+int32_t ilqr_pool_create(const ilqr_problem* p, int32_t n_handles, ilqr_pool** out);
+int32_t ilqr_pool_destroy(ilqr_pool* pool);
+const char* ilqr_pool_last_error(const ilqr_pool* pool);
+int64_t ilqr_pool_submit(ilqr_pool* pool, const double* x_init, const double* u_init, const double* x_traj,
+                         int32_t max_iter, double tol, double* x_out, double* u_out, double* cost_out,
+                         int32_t* iters_out, int32_t* status_out);
+/* same with device pointers (boundary layout); outputs are nullable */
+int64_t ilqr_pool_submit_device(ilqr_pool* pool, const double* d_x_init, const double* d_u_init,
+                                const double* d_x_traj, int32_t max_iter, double tol, double* d_x_out,
+                                double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out);
+int32_t ilqr_pool_wait(ilqr_pool* pool, int64_t ticket);
+int32_t ilqr_pool_wait_all(ilqr_pool* pool);
+int64_t ilqr_pool_launch_count(const ilqr_pool* pool);
+
 /* Page-locked host buffers for callers that want full-speed PCIe copies. */
 int32_t ilqr_host_alloc(void** out, uint64_t bytes);
 int32_t ilqr_host_free(void* p);

@@ -229,3 +229,22 @@ def test_full_size_properties():
         s2.fit(100, 1e-6)
         assert np.array_equal(s2.download(_abi.X), xs[:, :, :4096][:, :, perm])
         assert np.array_equal(s2.download(_abi.ITERS), it[:4096][perm])
+
+
+def test_pool_scheduler_equals_single_handle():
+    """Batches solved through ilqr_pool (several in flight) are bit-identical to ilqr_solve on one handle."""
+    B, H, NJ = 300, 60, 5
+    batches = [config2_batch(B, H, seed=100 + i)[1:] for i in range(NJ)]
+    prob = ilqr_b200.two_link_problem(H, B)
+    with _solver(H, B) as s:
+        ref = [s.solve(x, u, max_iter=50) for x, u in batches]
+    with ilqr_b200.SolverPool(prob, 3) as pool:
+        outs = [dict(x=np.empty_like(x), u=np.empty_like(u), cost=np.empty(B), iters=np.empty(B, dtype=np.int32),
+                     status=np.empty(B, dtype=np.int32)) for x, u in batches]
+        tickets = [pool.submit(x, u, o, max_iter=50) for (x, u), o in zip(batches, outs)]
+        for t in reversed(tickets):
+            pool.wait(t)
+        assert pool.launch_count() > 0
+    for r, o in zip(ref, outs):
+        for k in ("x", "u", "cost", "iters", "status"):
+            assert np.array_equal(r[k], o[k]), k
