@@ -39,6 +39,7 @@ struct ilqr_handle {
   double* ab_scratch = nullptr; // [H*20][S] linearisations for the split backward pass (lazy)
   int32_t split_below = 20000; // use the split backward pass when nslots <= this
   int32_t coop_below = 8192;   // ... and the warp-cooperative Riccati kernel when nslots <= this
+  int32_t fwd_split_above = 24000;  // two-kernel forward pass (α = 1, then dense retries) when nslots > this
   bool pend_bwd = false, pend_fwd = false;
   std::string err;
 };
@@ -78,7 +79,7 @@ void free_all(ilqr_handle* h) {
   cudaFree(s.status); cudaFree(s.iters); cudaFree(s.active); cudaFree(s.cur); cudaFree(s.bar); cudaFree(s.n_active);
   cudaFree(s.traj); cudaFree(s.r_prev_cost); cudaFree(s.r_new_cost); cudaFree(s.r_alpha); cudaFree(s.r_du2);
   cudaFree(s.r_status); cudaFree(s.r_iters); cudaFree(s.r_active);
-  cudaFree(s.blocks_done);
+  cudaFree(s.blocks_done); cudaFree(s.retry_list); cudaFree(s.n_retry);
   cudaFree(s.retire_list); cudaFree(s.move_src); cudaFree(s.move_dst); cudaFree(s.n_move);
   cudaFree(h->ab_scratch);
   cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
@@ -229,6 +230,8 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   CKC(cudaHostAlloc((void**)&h->pinned_i32, 64, cudaHostAllocMapped));
   CKC(cudaHostGetDevicePointer((void**)&s.n_active_host, h->pinned_i32, 0));
   CKC(dalloc(&s.blocks_done, 1));
+  CKC(dalloc(&s.retry_list, S)); CKC(dalloc(&s.n_retry, 1));
+  CKC(cudaMemsetAsync(s.n_retry, 0, sizeof(int32_t), h->stream));
   CKC(cudaMemsetAsync(s.blocks_done, 0, sizeof(uint32_t), h->stream));
   CKC(cudaMemsetAsync(s.n_active, 0, sizeof(int32_t), h->stream));
   // padded slots must never hold NaN garbage that a kernel could trip on
@@ -241,6 +244,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
 #undef CKC
   if (const char* e = getenv("ILQR_SPLIT_BELOW")) h->split_below = atoi(e);
   if (const char* e = getenv("ILQR_COOP_BELOW")) h->coop_below = atoi(e);
+  if (const char* e = getenv("ILQR_FWD_SPLIT_ABOVE")) h->fwd_split_above = atoi(e);
   if (const char* e = getenv("ILQR_COMPACTION")) h->compaction = atoi(e) != 0;
   h->mp.alpha = p->model_params[0]; h->mp.beta = p->model_params[1]; h->mp.delta = p->model_params[2];
   h->mp.dt = p->dt; h->mp.twobeta = 2 * p->model_params[1];
@@ -345,10 +349,12 @@ static int32_t backward_async(ilqr_handle* h) {
 
 static int32_t forward_async(ilqr_handle* h) {
   if (!h->have_gains) return fail(h, ILQR_ERR_STATE, "forward_pass before backward_pass");
+  const bool fsplit = h->st.nslots > h->fwd_split_above;
   cudaEventRecord(h->ev[2], h->stream);
-  launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
+  if (fsplit) launch_fwd_split_two_link(h->st, h->mp, h->cp, h->stream);
+  else launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[3], h->stream);
-  h->launches += 1;
+  h->launches += (fsplit && h->prob.n_alpha > 1) ? 2 : 1;
   h->have_candidate = true; h->ev_valid = true; h->pend_fwd = true;
   return check_launch(h, "forward kernel");
 }

@@ -46,6 +46,8 @@ struct DevState {
   int32_t* r_status; int32_t* r_iters; int32_t* r_active;
   double* out_x;     // [B][n*N] boundary layout: final iterate of retired trajectories
   double* out_u;     // [B][m*H]
+  // line-search retry list: slots whose α = 1 candidate was rejected (two-kernel forward pass)
+  int32_t* retry_list; int32_t* n_retry;
   // compaction work lists
   int32_t* retire_list; int32_t* move_src; int32_t* move_dst; int32_t* n_move;
   int64_t S;         // slot stride (B rounded up to 32)
@@ -62,6 +64,8 @@ void launch_bwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP
 // coop: warp-cooperative Riccati (4 lanes per trajectory) instead of the thread-local one
 void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, double* AB, bool coop,
                                cudaStream_t s);
+// two-kernel forward pass (α = 1 for all, then a dense retry kernel) for large active sets
+void launch_fwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0 /*[n][S] BF*/,
                                   cudaStream_t s);

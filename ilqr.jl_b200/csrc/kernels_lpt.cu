@@ -643,6 +643,199 @@ fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-kernel forward pass for LARGE active sets.  In fwd_lpt_two_link one rejected lane makes its
+// whole warp walk the horizon again; in the early iterations of config 2 a few per cent of the
+// trajectories need α = ½, which is enough to hit most warps and double the kernel's SM time.
+//  1. fwd1_lpt_two_link: the α = 1 candidate only (same TMA ring); rejected slots go to a list;
+//  2. fwd_retry_two_link: one lane per listed slot (dense warps, gathers instead of slabs), α = ½, ¼, …
+// The retry kernel is latency bound but occupies only a few SMs, which the other batches in flight
+// (pool scheduler) use meanwhile.  Results are identical to the one-kernel version.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fwd_step(const TwoLinkP& mp, const CostP& cp, double alpha, const double xk[NX],
+                                         const double uk[NU], const double dk[NU], const double Kk[NK],
+                                         const double xt[NX], double xb[NX], double ub[NU], double& cost, double& du2) {
+  double dx[NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) dx[c] = xb[c] - xk[c];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    double kdx = Kk[i] * dx[0];
+#pragma unroll
+    for (int c = 1; c < NX; ++c) kdx = fma(Kk[i + NU * c], dx[c], kdx);
+    ub[i] = fma(alpha, dk[i], uk[i]) + kdx;
+    const double e = ub[i] - uk[i];
+    du2 = fma(e, e, du2);
+  }
+  double lx = 0.0, lu = 0.0;
+#pragma unroll
+  for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - (xb[c] - xt[c]); lx = fma(cp.w_x[c] * e, e, lx); }
+#pragma unroll
+  for (int i = 0; i < NU; ++i) lu = fma(cp.w_u[i] * ub[i], ub[i], lu);
+  cost += lx + lu;
+  double xnext[NX];
+  tl_step(mp, xb, ub, xnext);
+#pragma unroll
+  for (int c = 0; c < NX; ++c) xb[c] = xnext[c];
+}
+
+template <bool HAS_XT>
+__global__ void __launch_bounds__(kBlock)
+fwd1_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
+                  const __grid_constant__ CostP cp) {
+  using Cfg = FwdCfg<HAS_XT>;
+  constexpr int D = Cfg::kStages, SD = Cfg::kStageDoubles;
+  constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU, oT = oK + 32 * NK;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double (*ring)[SD] = reinterpret_cast<double (*)[SD]>(smem_raw) + warp * D;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarps * D * SD) + warp * D;
+  const int s0 = (blockIdx.x * kWarps + warp) * 32, s = s0 + lane;
+  if (s0 >= st.nslots) return;
+  const bool act = s < st.nslots && st.active[s];
+  const unsigned amask = __ballot_sync(0xffffffffu, act);
+  if (amask == 0) return;
+  const int64_t S = st.S;
+  const int H = st.H;
+  const int cur = warp_cur(st, s, act, amask);
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  double* __restrict__ Xo = st.x[cur ^ 1];
+  double* __restrict__ Uo = st.u[cur ^ 1];
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](int k, int stage) {
+    mbar_arrive_expect_tx(&bars[stage], SD * 8);
+    tma_load_1d(&ring[stage][oX], X + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oU], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oD], st.duff + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+    tma_load_1d(&ring[stage][oK], st.K + ((int64_t)k * S + s0) * NK, 32 * NK * 8, &bars[stage]);
+    if constexpr (HAS_XT) tma_load_1d(&ring[stage][oT], st.xtraj + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+      if (i < H) issue(i, i);
+  }
+  const double prev = act ? st.prev_cost[s] : 0.0;
+  double xb[NX];
+  ldv<NX>(X + (int64_t)s * NX, xb);
+  if (act) stv<NX>(Xo + (int64_t)s * NX, xb);
+  double cost = 0.0, du2 = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < H; ++k) {
+    const int stage = k % D;
+    mbar_wait(&bars[stage], (k / D) & 1);
+    double xk[NX], uk[NU], dk[NU], Kk[NK], xt[NX];
+    ldv<NX>(&ring[stage][oX + lane * NX], xk);
+    ldv<NU>(&ring[stage][oU + lane * NU], uk);
+    ldv<NU>(&ring[stage][oD + lane * NU], dk);
+    ldv<NK>(&ring[stage][oK + lane * NK], Kk);
+    if constexpr (HAS_XT) ldv<NX>(&ring[stage][oT + lane * NX], xt);
+    else {
+#pragma unroll
+      for (int c = 0; c < NX; ++c) xt[c] = 0.0;
+    }
+    __syncwarp();
+    if (lane == 0 && k + D < H) issue(k + D, stage);
+    if (act) {
+      double ub[NU];
+      fwd_step(mp, cp, 1.0, xk, uk, dk, Kk, xt, xb, ub, cost, du2);
+      stv<NU>(Uo + ((int64_t)k * S + s) * NU, ub);
+      stv<NX>(Xo + ((int64_t)(k + 1) * S + s) * NX, xb);
+    }
+  }
+  if (act) {
+    double lf = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - xb[c]; lf = fma(cp.w_xf[c] * e, e, lf); }
+    cost += lf;
+    st.bar[s] = cur ^ 1;
+    if (prev - cost > 0.0) {   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < NX; ++c) bad |= isnan(xb[c]);
+      if (bad) st.status[s] |= ST_NAN_ROLLOUT;
+      st.new_cost[s] = cost; st.alpha[s] = 1.0; st.du2[s] = du2;
+    } else {
+      st.new_cost[s] = qnan(); st.alpha[s] = 0.0; st.du2[s] = qnan();   // = exhausted unless the retry accepts
+      if (st.n_alpha > 1) st.retry_list[atomicAdd(st.n_retry, 1)] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+fwd_retry_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
+                   const __grid_constant__ CostP cp) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= *st.n_retry) return;
+  const int s = st.retry_list[i];
+  const int64_t S = st.S;
+  const int H = st.H;
+  const int cur = st.cur[s];
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  double* __restrict__ Xo = st.x[cur ^ 1];
+  double* __restrict__ Uo = st.u[cur ^ 1];
+  const double* __restrict__ XT = st.xtraj;
+  const double prev = st.prev_cost[s];
+  double x0[NX];
+  ldv<NX>(X + (int64_t)s * NX, x0);
+  double alpha = 0.5;
+#pragma unroll 1
+  for (int j = 1; j < st.n_alpha; ++j, alpha *= 0.5) {
+    double xb[NX], cost = 0.0, du2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) xb[c] = x0[c];
+    double xk[NX], uk[NU], dk[NU], Kk[NK];   // operands of step k, prefetched one step ahead
+#pragma unroll
+    for (int c = 0; c < NX; ++c) xk[c] = x0[c];
+    ldv<NU>(U + (int64_t)s * NU, uk);
+    ldv<NU>(st.duff + (int64_t)s * NU, dk);
+    ldv<NK>(st.K + (int64_t)s * NK, Kk);
+#pragma unroll 1
+    for (int k = 0; k < H; ++k) {
+      double xk1[NX], uk1[NU], dk1[NU], Kk1[NK], xt[NX];
+      const int kn = (k + 1 < H) ? k + 1 : k;
+      ldv<NX>(X + ((int64_t)kn * S + s) * NX, xk1);
+      ldv<NU>(U + ((int64_t)kn * S + s) * NU, uk1);
+      ldv<NU>(st.duff + ((int64_t)kn * S + s) * NU, dk1);
+      ldv<NK>(st.K + ((int64_t)kn * S + s) * NK, Kk1);
+      if (XT) ldv<NX>(XT + ((int64_t)k * S + s) * NX, xt);
+      else {
+#pragma unroll
+        for (int c = 0; c < NX; ++c) xt[c] = 0.0;
+      }
+      double ub[NU];
+      fwd_step(mp, cp, alpha, xk, uk, dk, Kk, xt, xb, ub, cost, du2);
+      stv<NU>(Uo + ((int64_t)k * S + s) * NU, ub);
+      stv<NX>(Xo + ((int64_t)(k + 1) * S + s) * NX, xb);
+#pragma unroll
+      for (int c = 0; c < NX; ++c) xk[c] = xk1[c];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) { uk[c] = uk1[c]; dk[c] = dk1[c]; }
+#pragma unroll
+      for (int c = 0; c < NK; ++c) Kk[c] = Kk1[c];
+    }
+    double lf = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - xb[c]; lf = fma(cp.w_xf[c] * e, e, lf); }
+    cost += lf;
+    if (prev - cost > 0.0) {
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < NX; ++c) bad |= isnan(xb[c]);
+      if (bad) st.status[s] |= ST_NAN_ROLLOUT;
+      st.new_cost[s] = cost; st.alpha[s] = alpha; st.du2[s] = du2;
+      return;
+    }
+  }
+}
+
 // Open-loop rollout of u from x0 (animate_2_link.jl:14-16): x[cur] filled.  x0: [slot][4].
 __global__ void __launch_bounds__(kBlock)
 rollout_init_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
@@ -710,6 +903,7 @@ __global__ void commit_kernel(const __grid_constant__ DevState st, double tol) {
     *st.n_active_host = total;
     *st.n_active = 0;
     *st.blocks_done = 0u;
+    *st.n_retry = 0;
     __threadfence_system();
   }
 }
@@ -870,6 +1064,8 @@ constexpr size_t kRicSmem = sizeof(double) * kWarps * kRicStages * kRicStageDoub
 void init_kernel_attributes() {
   opt_in_smem(fwd_lpt_two_link<false>, FwdCfg<false>::kSmem);
   opt_in_smem(fwd_lpt_two_link<true>, FwdCfg<true>::kSmem);
+  opt_in_smem(fwd1_lpt_two_link<false>, FwdCfg<false>::kSmem);
+  opt_in_smem(fwd1_lpt_two_link<true>, FwdCfg<true>::kSmem);
   opt_in_smem(ric_lpt_two_link, kRicSmem);
 }
 
@@ -884,6 +1080,12 @@ void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const Cos
   lin_lpt_two_link<<<grid, kBlock, 0, s>>>(st, mp, AB);
   if (coop) ric_coop_two_link<<<grid_for(st.nslots, kWarps * kCoopTraj), kBlock, 0, s>>>(st, cp, AB);
   else ric_lpt_two_link<<<grid_for(st.nslots, kBlock), kBlock, kRicSmem, s>>>(st, cp, AB);
+}
+void launch_fwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
+  if (st.nslots <= 0) return;
+  if (st.xtraj) fwd1_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp);
+  else fwd1_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp);
+  if (st.n_alpha > 1) fwd_retry_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, cp);
 }
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
   if (st.nslots <= 0) return;
