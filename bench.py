@@ -293,7 +293,7 @@ def run_b200(args):
         fp64_peak_tf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_dfma_tflops"]
     except Exception:
         pass
-    FP64_INSTR = {"bwd": 928, "fwd": 273}
+    FP64_INSTR = {"bwd": 831, "fwd": 273}
     flops = 2.0 * FP64_INSTR[dom] * H * prof_acc["traj_iters"]
     roofline["fp64"] = {"achieved_tflops": flops / (dom_ms * 1e-3) / 1e12 if dom_ms else None, "peak_tflops": fp64_peak_tf,
                         "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",

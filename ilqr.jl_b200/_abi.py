@@ -48,6 +48,7 @@ SYMBOLS = {
     "ilqr_backward_pass": (ctypes.c_int32, [_H]),
     "ilqr_forward_pass": (ctypes.c_int32, [_H, ctypes.c_void_p]),
     "ilqr_commit": (ctypes.c_int32, [_H, ctypes.c_double, c_int32_p]),
+    "ilqr_set_reg": (ctypes.c_int32, [_H, ctypes.c_double]),
     "ilqr_set_active": (ctypes.c_int32, [_H, ctypes.c_void_p]),
     "ilqr_iterate": (ctypes.c_int32, [_H, ctypes.c_double, c_int32_p]),
     "ilqr_fit": (ctypes.c_int32, [_H, ctypes.c_int32, ctypes.c_double, c_int32_p]),

@@ -424,6 +424,14 @@ int32_t ilqr_set_active(ilqr_handle* h, const int32_t* active) {
   return check_launch(h, "set_active kernel");
 }
 
+int32_t ilqr_set_reg(ilqr_handle* h, double reg) {
+  if (!h) return ILQR_ERR_INVALID;
+  if (!(reg >= 0.0)) return fail(h, ILQR_ERR_INVALID, "reg must be >= 0");
+  h->prob.reg = reg;
+  h->st.reg = reg;
+  return ILQR_OK;
+}
+
 int32_t ilqr_iterate(ilqr_handle* h, double tol, int32_t* n_active) {
   if (!h) return ILQR_ERR_INVALID;
   CK(h, cudaSetDevice(h->device));

@@ -132,7 +132,7 @@ bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
 #pragma unroll
       for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
       double d[NU], Kk[NU][NX];
-      riccati_step<NX, NU, true>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
+      riccati_step<NX, NU, true, true>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
       double kv[NK];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
@@ -273,7 +273,7 @@ ric_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Co
 #pragma unroll
       for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
       double d[NU], Kk[NU][NX];
-      riccati_step<NX, NU, true>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
+      riccati_step<NX, NU, true, true>(A, Bm, qv, rv, Qd, Rd, st.reg, sv, Sm, d, Kk);
       double kv[NK];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
@@ -491,12 +491,14 @@ ric_coop_two_link(const __grid_constant__ DevState st, const __grid_constant__ C
       stv<6>(xs_g + j * 6, sc);
     }
     __syncwarp();
+    // upper triangle from the owning column, lower triangle mirrored (as riccati_step<…, SYM_S> does)
 #pragma unroll
     for (int c = 0; c < NX; ++c) {
       double v[6];
       ldv<6>(xs_g + c * 6, v);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) Sm[i][c] = v[i];
+      for (int i = 0; i < NX; ++i)
+        if (i <= c) { Sm[i][c] = v[i]; Sm[c][i] = v[i]; }
       sv[c] = v[4];
     }
     // the exchange buffers are rewritten only after the next step's first __syncwarp pair

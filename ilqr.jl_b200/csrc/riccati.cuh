@@ -79,7 +79,9 @@ __device__ __forceinline__ void neg_solve(const double Hr[M][M], const double rh
 // The value update is evaluated as 𝐒 = 𝐐 + Aᵀ(SA) + Kᵀ(HK + G) + GᵀK and
 // 𝐬 = 𝐪 + Aᵀ𝐬 + Kᵀ(Hδu + g) + Gᵀδu — the reference's five terms (unregularised H, no
 // symmetrisation), two of them sharing a factor.
-template <int N, int M, bool A_COL0_E0 = false>
+// SYM_S: 𝐒 is symmetric in exact arithmetic (the reference's 𝐒ᵢⱼ and 𝐒ⱼᵢ differ by rounding only, it
+// never symmetrises); with SYM_S the upper triangle is computed and mirrored.
+template <int N, int M, bool A_COL0_E0 = false, bool SYM_S = false>
 __device__ __forceinline__ void riccati_step(const double A[N][N], const double Bm[N][M], const double qv[N],
                                              const double rv[M], const double Qd[N], const double Rd[M], double reg,
                                              double sv[N], double S[N][N], double d[M], double K[M][N]) {
@@ -174,6 +176,7 @@ __device__ __forceinline__ void riccati_step(const double A[N][N], const double 
   for (int i = 0; i < N; ++i) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
+      if (SYM_S && j < i) { S[i][j] = S[j][i]; continue; }   // row j < i was finished in an earlier pass of the i loop
       double acc = (i == j) ? Qd[i] : 0.0;
       if (A_COL0_E0 && i == 0) acc += SA[0][j];
       else {

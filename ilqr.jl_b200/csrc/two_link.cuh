@@ -125,26 +125,46 @@ __device__ __forceinline__ void tl_stage_jac(const TwoLinkP& p, const TLPre& pr,
   phi[1][2] = -(i12 * b1 + i22 * b2);
 }
 
-// One link of the RK4 Jacobian chain.  X (4×3: state rows × columns θ₂,w₁,w₂)
-// and Y (4×2: state rows × u columns) are the previous stage's (I + c·D) and
-// c·E; outputs D = ΔtΦX, E = Δt(ΦY + Ψ).
-__device__ __forceinline__ void tl_chain(double dt, const double phi[2][3], const double mi[3], const double X[4][3],
+// One link of the RK4 Jacobian chain, UNSCALED: X (4×3: state rows × columns θ₂,w₁,w₂) and
+// Y (4×2: state rows × u columns) are the previous stage's (I + cΔt·D̃) and cΔt·Ẽ; outputs
+// D̃ = ΦX and Ẽ = ΦY + Ψ, i.e. D/Δt and E/Δt.  The Δt and RK4 weights are applied once, when the
+// next stage input and the final sums are formed, instead of on every entry of every stage.
+__device__ __forceinline__ void tl_chain(const double phi[2][3], const double mi[3], const double X[4][3],
                                          const double Y[4][2], double D[4][3], double E[4][2]) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    D[0][j] = dt * X[2][j];
-    D[1][j] = dt * X[3][j];
-    D[2][j] = dt * fma(phi[0][2], X[3][j], fma(phi[0][1], X[2][j], phi[0][0] * X[1][j]));
-    D[3][j] = dt * fma(phi[1][2], X[3][j], fma(phi[1][1], X[2][j], phi[1][0] * X[1][j]));
+    D[0][j] = X[2][j];
+    D[1][j] = X[3][j];
+    D[2][j] = fma(phi[0][2], X[3][j], fma(phi[0][1], X[2][j], phi[0][0] * X[1][j]));
+    D[3][j] = fma(phi[1][2], X[3][j], fma(phi[1][1], X[2][j], phi[1][0] * X[1][j]));
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const double m0 = (j == 0) ? mi[0] : mi[1];
     const double m1 = (j == 0) ? mi[1] : mi[2];
-    E[0][j] = dt * Y[2][j];
-    E[1][j] = dt * Y[3][j];
-    E[2][j] = dt * (fma(phi[0][2], Y[3][j], fma(phi[0][1], Y[2][j], phi[0][0] * Y[1][j])) + m0);
-    E[3][j] = dt * (fma(phi[1][2], Y[3][j], fma(phi[1][1], Y[2][j], phi[1][0] * Y[1][j])) + m1);
+    E[0][j] = Y[2][j];
+    E[1][j] = Y[3][j];
+    E[2][j] = fma(phi[0][2], Y[3][j], fma(phi[0][1], Y[2][j], fma(phi[0][0], Y[1][j], m0)));
+    E[3][j] = fma(phi[1][2], Y[3][j], fma(phi[1][1], Y[2][j], fma(phi[1][0], Y[1][j], m1)));
+  }
+}
+
+// next-stage inputs X = I + c·D̃, Y = c·Ẽ (c = ½Δt or Δt) and the weighted running sums
+template <bool FIRST>
+__device__ __forceinline__ void tl_advance(double c, double w, const double D[4][3], const double E[4][2],
+                                           double X[4][3], double Y[4][2], double SD[4][3], double SE[4][2]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      SD[r][j] = FIRST ? D[r][j] : fma(w, D[r][j], SD[r][j]);
+      X[r][j] = fma(c, D[r][j], (r == j + 1) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      SE[r][j] = FIRST ? E[r][j] : fma(w, E[r][j], SE[r][j]);
+      Y[r][j] = c * E[r][j];
+    }
   }
 }
 
@@ -152,7 +172,7 @@ __device__ __forceinline__ void tl_chain(double dt, const double phi[2][3], cons
 // (replaces linearize_dynamics, src/backward_pass.jl:25-40, for this plugin)
 __device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4], const double u[2], double A[4][4],
                                              double Bm[4][2]) {
-  const double dt = p.dt;
+  const double dt = p.dt, hdt = 0.5 * p.dt;
   TLStage st;
   TLPre pr[2];
   double phi[2][3], mi[3];
@@ -164,23 +184,17 @@ __device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4
     const double th[2] = {x[1], fma(0.5, k1_1, x[1])};
     tl_pre<2>(p, th, pr);
   }
-  // stage 1 at s₁ = x : D₁ = ΔtΦ₁, E₁ = ΔtΨ₁ (X₀ = I, Y₀ = 0 folded by hand)
+  // stage 1 at s₁ = x : D̃₁ = Φ₁, Ẽ₁ = Ψ₁ (X₀ = I, Y₀ = 0 folded by hand)
   tl_fin(p, pr[0], x[2], x[3], u[0], u[1], st);
   tl_stage_jac(p, pr[0], st, x[2], x[3], phi, mi);
   const double k1_2 = dt * st.acc0, k1_3 = dt * st.acc1;
-  D[0][0] = 0.0; D[0][1] = dt;  D[0][2] = 0.0;
-  D[1][0] = 0.0; D[1][1] = 0.0; D[1][2] = dt;
+  D[0][0] = 0.0; D[0][1] = 1.0; D[0][2] = 0.0;
+  D[1][0] = 0.0; D[1][1] = 0.0; D[1][2] = 1.0;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) { D[2][j] = dt * phi[0][j]; D[3][j] = dt * phi[1][j]; }
+  for (int j = 0; j < 3; ++j) { D[2][j] = phi[0][j]; D[3][j] = phi[1][j]; }
   E[0][0] = 0.0; E[0][1] = 0.0; E[1][0] = 0.0; E[1][1] = 0.0;
-  E[2][0] = dt * mi[0]; E[2][1] = dt * mi[1]; E[3][0] = dt * mi[1]; E[3][1] = dt * mi[2];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { SD[r][j] = D[r][j]; X[r][j] = 0.5 * D[r][j] + ((r == j + 1) ? 1.0 : 0.0); }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) { SE[r][j] = E[r][j]; Y[r][j] = 0.5 * E[r][j]; }
-  }
+  E[2][0] = mi[0]; E[2][1] = mi[1]; E[3][0] = mi[1]; E[3][1] = mi[2];
+  tl_advance<true>(hdt, 1.0, D, E, X, Y, SD, SE);
 
   // ---- stage 2 at s₂ = x + k₁/2
   double w1 = fma(0.5, k1_2, x[2]), w2 = fma(0.5, k1_3, x[3]);
@@ -194,42 +208,30 @@ __device__ __forceinline__ void tl_linearize(const TwoLinkP& p, const double x[4
     const double th[2] = {fma(0.5, k2_1, x[1]), x[1] + k3_1};
     tl_pre<2>(p, th, pr);
   }
-  tl_chain(dt, phi, mi, X, Y, D, E);
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { SD[r][j] = fma(2.0, D[r][j], SD[r][j]); X[r][j] = 0.5 * D[r][j] + ((r == j + 1) ? 1.0 : 0.0); }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) { SE[r][j] = fma(2.0, E[r][j], SE[r][j]); Y[r][j] = 0.5 * E[r][j]; }
-  }
+  tl_chain(phi, mi, X, Y, D, E);
+  tl_advance<false>(hdt, 2.0, D, E, X, Y, SD, SE);
 
   // ---- stage 3 at s₃ = x + k₂/2
   tl_fin(p, pr[0], w1c, w2c, u[0], u[1], st);
   tl_stage_jac(p, pr[0], st, w1c, w2c, phi, mi);
   const double k3_2 = dt * st.acc0, k3_3 = dt * st.acc1;
-  tl_chain(dt, phi, mi, X, Y, D, E);
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { SD[r][j] = fma(2.0, D[r][j], SD[r][j]); X[r][j] = D[r][j] + ((r == j + 1) ? 1.0 : 0.0); }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) { SE[r][j] = fma(2.0, E[r][j], SE[r][j]); Y[r][j] = E[r][j]; }
-  }
+  tl_chain(phi, mi, X, Y, D, E);
+  tl_advance<false>(dt, 2.0, D, E, X, Y, SD, SE);
 
   // ---- stage 4 at s₄ = x + k₃
   w1 = x[2] + k3_2; w2 = x[3] + k3_3;
   tl_fin(p, pr[1], w1, w2, u[0], u[1], st);
   tl_stage_jac(p, pr[1], st, w1, w2, phi, mi);
-  tl_chain(dt, phi, mi, X, Y, D, E);
+  tl_chain(phi, mi, X, Y, D, E);
 
-  const double sixth = 1.0 / 6.0;
+  const double dt6 = dt * (1.0 / 6.0);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     A[r][0] = (r == 0) ? 1.0 : 0.0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) A[r][j + 1] = fma(sixth, SD[r][j] + D[r][j], (r == j + 1) ? 1.0 : 0.0);
+    for (int j = 0; j < 3; ++j) A[r][j + 1] = fma(dt6, SD[r][j] + D[r][j], (r == j + 1) ? 1.0 : 0.0);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) Bm[r][j] = sixth * (SE[r][j] + E[r][j]);
+    for (int j = 0; j < 2; ++j) Bm[r][j] = dt6 * (SE[r][j] + E[r][j]);
   }
 }
 

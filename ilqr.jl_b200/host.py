@@ -145,6 +145,9 @@ class BatchSolver:
         self._ck(self._lib.ilqr_commit(self._h, float(tol), ctypes.byref(na)), "ilqr_commit")
         return na.value
 
+    def set_reg(self, reg):
+        self._ck(self._lib.ilqr_set_reg(self._h, float(reg)), "ilqr_set_reg")
+
     def set_active(self, mask):
         m = np.ascontiguousarray(np.asarray(mask).astype(np.int32))
         assert m.shape == (self.B,)

@@ -167,6 +167,10 @@ int32_t ilqr_forward_pass(ilqr_handle* h, const double* prev_cost);
  * n_active (nullable) receives how many trajectories are still iterating. */
 int32_t ilqr_commit(ilqr_handle* h, double tol, int32_t* n_active);
 
+/* Host-owned regularisation control: the constant added to diag(H) before the gain solve
+ * (src/backward_pass.jl:214 hard-codes 0.01).  Takes effect from the next backward pass. */
+int32_t ilqr_set_reg(ilqr_handle* h, double reg);
+
 /* Host-owned convergence control: trajectories whose mask entry (int32 [B]) is 0 stop iterating
  * (they keep their current iterate).  A stopped trajectory cannot be restarted; upload again. */
 int32_t ilqr_set_active(ilqr_handle* h, const int32_t* active);

@@ -248,3 +248,25 @@ def test_pool_scheduler_equals_single_handle():
     for r, o in zip(ref, outs):
         for k in ("x", "u", "cost", "iters", "status"):
             assert np.array_equal(r[k], o[k]), k
+
+
+def test_host_owned_regularisation_and_convergence_control():
+    """ilqr_set_reg changes the gains exactly as the oracle's `reg` does; ilqr_set_active stops trajectories."""
+    B, H = 6, 80
+    _, x, u = config2_batch(B, H, seed=77)
+    with _solver(H, B) as s:
+        s.upload(x, u)
+        for reg in (0.01, 1.0, 0.0):
+            s.set_reg(reg)
+            s.backward_pass()
+            d, K = s.download(_abi.DUFF), s.download(_abi.K)
+            for b in range(B):
+                d0, K0, _ = orc.backward_pass(x[:, :, b], u[:, :, b], reg)
+                assert rel_err(d[:, :, b], d0) < RTOL and rel_err(K[:, :, :, b], K0) < RTOL
+        s.set_reg(0.01)
+        mask = np.array([1, 0, 1, 1, 0, 1], dtype=np.int32)
+        s.set_active(mask)
+        s.fit(100, 1e-6)
+        it, xs = s.download(_abi.ITERS), s.download(_abi.X)
+        assert np.all(it[mask == 0] == 0) and np.all(it[mask == 1] > 0)
+        assert np.array_equal(xs[:, :, mask == 0], x[:, :, mask == 0])
