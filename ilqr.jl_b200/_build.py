@@ -32,7 +32,8 @@ def build(force=False, verbose=False):
     """Compile every CUDA source into ilqr.jl_b200/libilqr_b200.so.  Returns the path."""
     if not force and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("ILQR_NVCC_EXTRA", "").split()   # experiments: -DILQR_FWD1_STAGES=2 …
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -522,7 +522,7 @@ template <bool HAS_XT> struct FwdCfg {
 template <bool HAS_XT>
 __global__ void __launch_bounds__(kBlock)
 fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
-                 const __grid_constant__ CostP cp) {
+                 const __grid_constant__ CostP cp, const int max_pass) {
   using Cfg = FwdCfg<HAS_XT>;
   constexpr int D = Cfg::kStages, SD = Cfg::kStageDoubles;
   constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU, oT = oK + 32 * NK;
@@ -566,7 +566,7 @@ fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
   bool searching = act, bad = false;
   int fills = 0;   // ring uses so far (stage = fills % D, parity = (fills / D) & 1), warp-uniform
 #pragma unroll 1
-  for (int j = 0; j < st.n_alpha; ++j) {
+  for (int j = 0; j < max_pass; ++j) {
     if (!__any_sync(0xffffffffu, searching)) break;
     if (lane == 0) {
 #pragma unroll
@@ -642,6 +642,8 @@ fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
     st.bar[s] = cur ^ 1;
     if (bad) st.status[s] |= ST_NAN_ROLLOUT;
     st.new_cost[s] = acc_cost; st.alpha[s] = acc_alpha; st.du2[s] = acc_du2;
+    // two-kernel mode (max_pass = 1): still-rejected lanes continue in fwd_retry_two_link
+    if (searching && max_pass < st.n_alpha) st.retry_list[atomicAdd(st.n_retry, 1)] = s;
   }
 }
 
@@ -649,7 +651,7 @@ fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
 // Two-kernel forward pass for LARGE active sets.  In fwd_lpt_two_link one rejected lane makes its
 // whole warp walk the horizon again; in the early iterations of config 2 a few per cent of the
 // trajectories need α = ½, which is enough to hit most warps and double the kernel's SM time.
-//  1. fwd1_lpt_two_link: the α = 1 candidate only (same TMA ring); rejected slots go to a list;
+//  1. fwd_lpt_two_link with max_pass = 1: the α = 1 candidate only; rejected slots go to a list;
 //  2. fwd_retry_two_link: one lane per listed slot (dense warps, gathers instead of slabs), α = ½, ¼, …
 // The retry kernel is latency bound but occupies only a few SMs, which the other batches in flight
 // (pool scheduler) use meanwhile.  Results are identical to the one-kernel version.
@@ -679,95 +681,6 @@ __device__ __forceinline__ void fwd_step(const TwoLinkP& mp, const CostP& cp, do
   tl_step(mp, xb, ub, xnext);
 #pragma unroll
   for (int c = 0; c < NX; ++c) xb[c] = xnext[c];
-}
-
-template <bool HAS_XT>
-__global__ void __launch_bounds__(kBlock)
-fwd1_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
-                  const __grid_constant__ CostP cp) {
-  using Cfg = FwdCfg<HAS_XT>;
-  constexpr int D = Cfg::kStages, SD = Cfg::kStageDoubles;
-  constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU, oT = oK + 32 * NK;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double (*ring)[SD] = reinterpret_cast<double (*)[SD]>(smem_raw) + warp * D;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarps * D * SD) + warp * D;
-  const int s0 = (blockIdx.x * kWarps + warp) * 32, s = s0 + lane;
-  if (s0 >= st.nslots) return;
-  const bool act = s < st.nslots && st.active[s];
-  const unsigned amask = __ballot_sync(0xffffffffu, act);
-  if (amask == 0) return;
-  const int64_t S = st.S;
-  const int H = st.H;
-  const int cur = warp_cur(st, s, act, amask);
-  const double* __restrict__ X = st.x[cur];
-  const double* __restrict__ U = st.u[cur];
-  double* __restrict__ Xo = st.x[cur ^ 1];
-  double* __restrict__ Uo = st.u[cur ^ 1];
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) mbar_init(&bars[i], 1);
-    mbar_fence_init();
-  }
-  __syncwarp();
-  auto issue = [&](int k, int stage) {
-    mbar_arrive_expect_tx(&bars[stage], SD * 8);
-    tma_load_1d(&ring[stage][oX], X + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
-    tma_load_1d(&ring[stage][oU], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
-    tma_load_1d(&ring[stage][oD], st.duff + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
-    tma_load_1d(&ring[stage][oK], st.K + ((int64_t)k * S + s0) * NK, 32 * NK * 8, &bars[stage]);
-    if constexpr (HAS_XT) tma_load_1d(&ring[stage][oT], st.xtraj + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
-  };
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-      if (i < H) issue(i, i);
-  }
-  const double prev = act ? st.prev_cost[s] : 0.0;
-  double xb[NX];
-  ldv<NX>(X + (int64_t)s * NX, xb);
-  if (act) stv<NX>(Xo + (int64_t)s * NX, xb);
-  double cost = 0.0, du2 = 0.0;
-#pragma unroll 1
-  for (int k = 0; k < H; ++k) {
-    const int stage = k % D;
-    mbar_wait(&bars[stage], (k / D) & 1);
-    double xk[NX], uk[NU], dk[NU], Kk[NK], xt[NX];
-    ldv<NX>(&ring[stage][oX + lane * NX], xk);
-    ldv<NU>(&ring[stage][oU + lane * NU], uk);
-    ldv<NU>(&ring[stage][oD + lane * NU], dk);
-    ldv<NK>(&ring[stage][oK + lane * NK], Kk);
-    if constexpr (HAS_XT) ldv<NX>(&ring[stage][oT + lane * NX], xt);
-    else {
-#pragma unroll
-      for (int c = 0; c < NX; ++c) xt[c] = 0.0;
-    }
-    __syncwarp();
-    if (lane == 0 && k + D < H) issue(k + D, stage);
-    if (act) {
-      double ub[NU];
-      fwd_step(mp, cp, 1.0, xk, uk, dk, Kk, xt, xb, ub, cost, du2);
-      stv<NU>(Uo + ((int64_t)k * S + s) * NU, ub);
-      stv<NX>(Xo + ((int64_t)(k + 1) * S + s) * NX, xb);
-    }
-  }
-  if (act) {
-    double lf = 0.0;
-#pragma unroll
-    for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - xb[c]; lf = fma(cp.w_xf[c] * e, e, lf); }
-    cost += lf;
-    st.bar[s] = cur ^ 1;
-    if (prev - cost > 0.0) {   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
-      bool bad = false;
-#pragma unroll
-      for (int c = 0; c < NX; ++c) bad |= isnan(xb[c]);
-      if (bad) st.status[s] |= ST_NAN_ROLLOUT;
-      st.new_cost[s] = cost; st.alpha[s] = 1.0; st.du2[s] = du2;
-    } else {
-      st.new_cost[s] = qnan(); st.alpha[s] = 0.0; st.du2[s] = qnan();   // = exhausted unless the retry accepts
-      if (st.n_alpha > 1) st.retry_list[atomicAdd(st.n_retry, 1)] = s;
-    }
-  }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -1066,8 +979,6 @@ constexpr size_t kRicSmem = sizeof(double) * kWarps * kRicStages * kRicStageDoub
 void init_kernel_attributes() {
   opt_in_smem(fwd_lpt_two_link<false>, FwdCfg<false>::kSmem);
   opt_in_smem(fwd_lpt_two_link<true>, FwdCfg<true>::kSmem);
-  opt_in_smem(fwd1_lpt_two_link<false>, FwdCfg<false>::kSmem);
-  opt_in_smem(fwd1_lpt_two_link<true>, FwdCfg<true>::kSmem);
   opt_in_smem(ric_lpt_two_link, kRicSmem);
 }
 
@@ -1085,14 +996,14 @@ void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const Cos
 }
 void launch_fwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
   if (st.nslots <= 0) return;
-  if (st.xtraj) fwd1_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp);
-  else fwd1_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp);
+  if (st.xtraj) fwd_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp, 1);
+  else fwd_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp, 1);
   if (st.n_alpha > 1) fwd_retry_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, cp);
 }
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
   if (st.nslots <= 0) return;
-  if (st.xtraj) fwd_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp);
-  else fwd_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp);
+  if (st.xtraj) fwd_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp, st.n_alpha);
+  else fwd_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp, st.n_alpha);
 }
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0, cudaStream_t s) {
   rollout_init_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, d_x0);
