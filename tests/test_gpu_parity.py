@@ -270,3 +270,31 @@ def test_host_owned_regularisation_and_convergence_control():
         it, xs = s.download(_abi.ITERS), s.download(_abi.X)
         assert np.all(it[mask == 0] == 0) and np.all(it[mask == 1] > 0)
         assert np.array_equal(xs[:, :, mask == 0], x[:, :, mask == 0])
+
+
+def test_kernel_variants_are_bit_identical(monkeypatch):
+    """Fused vs split vs warp-cooperative backward pass, one- vs two-kernel forward pass, with and without
+    compaction: the library switches between them by active-set size, so they must agree bit for bit."""
+    B, H = 300, 60
+    _, x, u = stress_batch(B, H, seed=31)
+    variants = [
+        {},                                                                        # defaults at this size: split + coop, one-kernel fwd
+        {"ILQR_SPLIT_BELOW": "0", "ILQR_FWD_SPLIT_ABOVE": "0"},                   # fused backward, two-kernel forward
+        {"ILQR_SPLIT_BELOW": "100000", "ILQR_COOP_BELOW": "0"},                   # split backward, thread-local Riccati
+        {"ILQR_SPLIT_BELOW": "100000", "ILQR_COOP_BELOW": "100000", "ILQR_COMPACTION": "0"},   # cooperative Riccati, no re-packing
+    ]
+    results = []
+    for env in variants:
+        for k in ("ILQR_SPLIT_BELOW", "ILQR_COOP_BELOW", "ILQR_FWD_SPLIT_ABOVE", "ILQR_COMPACTION"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with _solver(H, B, trace_iters=40) as s:
+            s.upload(x, u)
+            s.fit(40, 1e-6)
+            results.append((s.download(_abi.X), s.download(_abi.U), s.download(_abi.ITERS), s.download(_abi.COST_TRACE),
+                            s.download(_abi.ALPHA_TRACE)))
+    assert np.nansum(results[0][4] < 1) > 0          # the line search fired
+    for r in results[1:]:
+        for a, b in zip(results[0], r):
+            assert np.array_equal(a, b, equal_nan=True)
