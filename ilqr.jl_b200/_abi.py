@@ -57,6 +57,8 @@ SYMBOLS = {
     "ilqr_solve": (ctypes.c_int32, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                     ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_mpc_start": (ctypes.c_int32, [_H, ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_mpc_step": (ctypes.c_int32, [_H, ctypes.c_int32, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "ilqr_pool_create": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.POINTER(_H)]),
     "ilqr_pool_destroy": (ctypes.c_int32, [_H]),
     "ilqr_pool_last_error": (ctypes.c_char_p, [_H]),

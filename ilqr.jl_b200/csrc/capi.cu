@@ -27,6 +27,8 @@ struct ilqr_handle {
   double* stage_u = nullptr;   // [B][m*H]
   double* stage_big = nullptr; // [B][m*n*H] (lazy; K downloads)
   double* scratch_b = nullptr; // [S] doubles
+  double* plant = nullptr;     // [B][n] MPC plant state (boundary layout, lazy)
+  double* u_applied = nullptr; // [B][m] controls applied by the last MPC step
   int32_t* pinned_i32 = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
@@ -81,7 +83,7 @@ void free_all(ilqr_handle* h) {
   cudaFree(s.r_status); cudaFree(s.r_iters); cudaFree(s.r_active);
   cudaFree(s.blocks_done); cudaFree(s.retry_list); cudaFree(s.n_retry);
   cudaFree(s.retire_list); cudaFree(s.move_src); cudaFree(s.move_dst); cudaFree(s.n_move);
-  cudaFree(h->ab_scratch);
+  cudaFree(h->ab_scratch); cudaFree(h->plant); cudaFree(h->u_applied);
   cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
   if (h->pinned_i32) cudaFreeHost(h->pinned_i32);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -330,6 +332,54 @@ int32_t ilqr_upload_gains(ilqr_handle* h, const double* duff, const double* K) {
   h->launches += 2;
   if (int32_t rc = check_launch(h, "upload_gains kernels")) return rc;
   h->have_gains = true;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+// x_init ← open-loop rollout of the (shifted) controls in out_u from the plant state; solver state reset.
+static int32_t mpc_reinit(ilqr_handle* h, int shift) {
+  const ilqr_problem& p = h->prob;
+  h->st.nslots = p.B;
+  launch_reset_state(h->st, h->stream);
+  launch_tf_to_bf(h->plant, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
+  launch_tf_to_bf(h->st.out_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream, shift);
+  launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
+  h->launches += 4;
+  if (int32_t rc = check_launch(h, "mpc re-initialisation kernels")) return rc;
+  h->loaded = true; h->have_gains = false; h->have_candidate = false;
+  for (auto& v : h->prof) v = 0.0;
+  h->n_active_host = p.B; h->pend_bwd = h->pend_fwd = false;
+  return ILQR_OK;
+}
+
+int32_t ilqr_mpc_start(ilqr_handle* h, const double* x0, const double* u_init) {
+  if (!h || !x0) return fail(h, ILQR_ERR_INVALID, "null argument");
+  const ilqr_problem& p = h->prob;
+  CK(h, cudaSetDevice(h->device));
+  if (!h->plant) { CK(h, dalloc(&h->plant, (size_t)p.B * p.n)); CK(h, dalloc(&h->u_applied, (size_t)p.B * p.m)); }
+  if (h->st.xtraj) { cudaFree(h->st.xtraj); h->st.xtraj = nullptr; }
+  CK(h, cudaMemcpyAsync(h->plant, x0, sizeof(double) * p.n * p.B, cudaMemcpyHostToDevice, h->stream));
+  if (u_init) CK(h, cudaMemcpyAsync(h->st.out_u, u_init, sizeof(double) * p.H * p.m * p.B, cudaMemcpyHostToDevice, h->stream));
+  else CK(h, cudaMemsetAsync(h->st.out_u, 0, sizeof(double) * p.H * p.m * p.B, h->stream));
+  if (int32_t rc = mpc_reinit(h, 0)) return rc;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return ILQR_OK;
+}
+
+static int32_t fit_loop(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_run);
+
+int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_applied, double* x_plant) {
+  if (!h) return ILQR_ERR_INVALID;
+  if (!h->plant || !h->loaded) return fail(h, ILQR_ERR_STATE, "mpc_step before mpc_start");
+  if (max_iter < 1) return fail(h, ILQR_ERR_INVALID, "max_iter < 1");
+  const ilqr_problem& p = h->prob;
+  CK(h, cudaSetDevice(h->device));
+  if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;        // solution → out_x / out_u (by trajectory)
+  launch_mpc_advance_two_link(h->mp, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
+  h->launches += 1;
+  if (u_applied) CK(h, cudaMemcpyAsync(u_applied, h->u_applied, sizeof(double) * p.m * p.B, cudaMemcpyDeviceToHost, h->stream));
+  if (x_plant) CK(h, cudaMemcpyAsync(x_plant, h->plant, sizeof(double) * p.n * p.B, cudaMemcpyDeviceToHost, h->stream));
+  if (int32_t rc = mpc_reinit(h, 1)) return rc;                            // warm start: shifted controls, fresh rollout
   CK(h, cudaStreamSynchronize(h->stream));
   return ILQR_OK;
 }

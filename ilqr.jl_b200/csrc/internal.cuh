@@ -84,8 +84,12 @@ void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaSt
 // layout.cu — boundary (Julia, time-fastest "TF") <-> BF transposes
 // TF: src[t*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + s]
 // slot_traj (nullable): t = slot_traj[s] (live slots only); otherwise t = s.  nslots = number of slots moved.
+// shift: read time index k + shift (zeros past the end) — the receding-horizon shift of a control sequence
 void launch_tf_to_bf(const double* tf, double* bf, const int32_t* slot_traj, int nslots, int T, int ncomp, int64_t S,
-                     cudaStream_t s);
+                     cudaStream_t s, int shift = 0);
+// MPC plant step: plant[t] ← f(plant[t], u_out[t][:,0]); u_applied[t] ← u_out[t][:,0]   (plant, u_applied: [B][n], [B][m])
+void launch_mpc_advance_two_link(const TwoLinkP& mp, const double* out_u, double* plant, double* u_applied, int B, int H,
+                                 cudaStream_t s);
 // sel (nullable): per-slot choice between bf0 and bf1
 void launch_bf_to_tf(const double* bf0, const double* bf1, const int32_t* sel, double* tf, const int32_t* slot_traj,
                      int nslots, int T, int ncomp, int64_t S, cudaStream_t s);

@@ -774,6 +774,24 @@ rollout_init_two_link(const __grid_constant__ DevState st, const __grid_constant
   }
 }
 
+// Receding-horizon plant step (config 5): apply the first control of every trajectory's solution to the plant
+// (the same dynamicsf, test/2_link_example/2_link_helper_functions.jl:49-79).  Boundary-layout inputs.
+__global__ void mpc_advance_two_link(const __grid_constant__ TwoLinkP mp, const double* __restrict__ out_u,
+                                     double* __restrict__ plant, double* __restrict__ u_applied, int B, int H) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B) return;
+  double x[NX], u[NU], xn[NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) x[c] = plant[(int64_t)t * NX + c];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) u[i] = out_u[(int64_t)t * NU * H + (int64_t)i * H];
+  tl_step(mp, x, u, xn);
+#pragma unroll
+  for (int c = 0; c < NX; ++c) plant[(int64_t)t * NX + c] = xn[c];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) u_applied[(int64_t)t * NU + i] = u[i];
+}
+
 __global__ void commit_kernel(const __grid_constant__ DevState st, double tol) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   bool still = false;
@@ -1007,6 +1025,10 @@ void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP
 }
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0, cudaStream_t s) {
   rollout_init_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, d_x0);
+}
+void launch_mpc_advance_two_link(const TwoLinkP& mp, const double* out_u, double* plant, double* u_applied, int B, int H,
+                                 cudaStream_t s) {
+  mpc_advance_two_link<<<grid_for(B, 128), 128, 0, s>>>(mp, out_u, plant, u_applied, B, H);
 }
 void launch_commit(const DevState& st, double tol, cudaStream_t s) {
   if (st.nslots > 0) commit_kernel<<<grid_for(st.nslots, 256), 256, 0, s>>>(st, tol);

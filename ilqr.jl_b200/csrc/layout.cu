@@ -21,7 +21,7 @@ constexpr int kThreads = 256;
 // dynamic smem: TK rows of (TS*ncomp + 1) doubles
 __global__ void __launch_bounds__(kThreads)
 tf_to_ksc_kernel(const double* __restrict__ tf, double* __restrict__ ksc, const int32_t* __restrict__ slot_traj,
-                 int nslots, int T, int ncomp, int64_t S) {
+                 int nslots, int T, int ncomp, int64_t S, int shift) {
   extern __shared__ double tile[];
   const int row = TS * ncomp + 1;
   const int k0 = blockIdx.x * TK, s0 = blockIdx.y * TS;
@@ -31,7 +31,8 @@ tf_to_ksc_kernel(const double* __restrict__ tf, double* __restrict__ ksc, const 
     const int k = k0 + kk, s = s0 + sl;
     if (k < T && s < nslots) {
       const int64_t t = slot_traj ? slot_traj[s] : s;
-      tile[kk * row + sl * ncomp + c] = tf[t * L + (int64_t)c * T + k];
+      // shift > 0: read time index k + shift, zero past the end (receding-horizon warm start)
+      tile[kk * row + sl * ncomp + c] = (k + shift < T) ? tf[t * L + (int64_t)c * T + k + shift] : 0.0;
     }
   }
   __syncthreads();
@@ -73,11 +74,11 @@ ksc_to_tf_kernel(const double* __restrict__ b0, const double* __restrict__ b1, c
 }  // namespace
 
 void launch_tf_to_bf(const double* tf, double* bf, const int32_t* slot_traj, int nslots, int T, int ncomp, int64_t S,
-                     cudaStream_t s) {
+                     cudaStream_t s, int shift) {
   if (nslots <= 0) return;
   dim3 grid((T + TK - 1) / TK, (nslots + TS - 1) / TS);
   const size_t smem = sizeof(double) * TK * (TS * ncomp + 1);
-  tf_to_ksc_kernel<<<grid, kThreads, smem, s>>>(tf, bf, slot_traj, nslots, T, ncomp, S);
+  tf_to_ksc_kernel<<<grid, kThreads, smem, s>>>(tf, bf, slot_traj, nslots, T, ncomp, S, shift);
 }
 
 void launch_bf_to_tf(const double* bf0, const double* bf1, const int32_t* sel, double* tf, const int32_t* slot_traj,

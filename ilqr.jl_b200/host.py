@@ -177,6 +177,19 @@ class BatchSolver:
                  "ilqr_solve")
         return out
 
+    # -- receding-horizon MPC ----------------------------------------------
+    def mpc_start(self, x0, u_init=None):
+        x0 = self._shape(x0, (self.n,))
+        u = None if u_init is None else self._shape(u_init, (self.H, self.m))
+        self._ck(self._lib.ilqr_mpc_start(self._h, x0.ctypes.data, None if u is None else u.ctypes.data), "ilqr_mpc_start")
+
+    def mpc_step(self, max_iter=5, tol=1e-6):
+        """One closed-loop step: solve (≤ max_iter iterations, warm-started), apply u[0] to the plant, shift.
+        Returns (u_applied[m,B], x_plant[n,B])."""
+        ua = np.empty((self.m, self.B), order="F"); xp = np.empty((self.n, self.B), order="F")
+        self._ck(self._lib.ilqr_mpc_step(self._h, int(max_iter), float(tol), ua.ctypes.data, xp.ctypes.data), "ilqr_mpc_step")
+        return ua, xp
+
     # -- introspection ----------------------------------------------------
     def launch_count(self):
         return int(self._lib.ilqr_launch_count(self._h))

@@ -195,6 +195,17 @@ int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, c
                    int32_t max_iter, double tol, double* x_out, double* u_out, double* cost_out,
                    int32_t* iters_out, int32_t* status_out);
 
+/* ---- receding-horizon MPC (BASELINE config 5), built on fit's warm-start property
+ * (src/forward_pass.jl:148-155 takes any x_init/u_init).  ilqr_mpc_start sets the plant states
+ * x0[n,B] and the initial control sequences (u_init[H,m,B] or NULL = zeros; x_init = open-loop
+ * rollout, animate_2_link.jl:14-16).  Each ilqr_mpc_step (1) runs fit for at most max_iter
+ * iterations from the current warm start, (2) applies every trajectory's first control to the plant
+ * (one dynamicsf step of the same model), (3) shifts the control sequences by one step (last = 0)
+ * and re-initialises x by an open-loop rollout from the new plant states.  u_applied[m,B] and
+ * x_plant[n,B] (host, nullable) receive the applied controls and the new plant states. */
+int32_t ilqr_mpc_start(ilqr_handle* h, const double* x0, const double* u_init);
+int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_applied, double* x_plant);
+
 /* ---- batch scheduler: several batches in flight on one GPU --------------------------------
  * Iteration counts are heavy tailed, so the last iterations of a batch run on few trajectories and
  * leave the GPU mostly idle.  A pool owns n_handles handles (own stream + device buffers each) and

@@ -298,3 +298,25 @@ def test_kernel_variants_are_bit_identical(monkeypatch):
     for r in results[1:]:
         for a, b in zip(results[0], r):
             assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_mpc_closed_loop_matches_oracle():
+    """Receding-horizon MPC (BASELINE config 5 pattern): solve (≤ K warm-started iterations), apply u[0] to the
+    plant, shift, re-initialise by rollout — against the same loop built from oracle calls."""
+    B, H, K, STEPS = 6, 40, 4, 5
+    rng = np.random.default_rng(8)
+    x0 = rng.random((B, 4))
+    with _solver(H, B) as s:
+        s.mpc_start(np.asfortranarray(x0.T))
+        got = [s.mpc_step(max_iter=K) for _ in range(STEPS)]
+    for b in range(B):
+        plant = x0[b].copy(); u = np.zeros((H, 2))
+        for t in range(STEPS):
+            x = orc.rollout(plant, u)
+            res = orc.fit(x, u, max_iter=K)
+            u0 = res["u"][0].copy()
+            plant = orc.dynamics(plant, u0)
+            u = np.vstack([res["u"][1:], np.zeros((1, 2))])
+            ua, xp = got[t]
+            assert np.max(np.abs(ua[:, b] - u0)) < RTOL * max(1.0, np.max(np.abs(u0))), (b, t)
+            assert np.max(np.abs(xp[:, b] - plant)) < RTOL * max(1.0, np.max(np.abs(plant))), (b, t)
