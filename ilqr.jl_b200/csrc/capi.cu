@@ -5,7 +5,9 @@
 // every numerical result comes from the CUDA kernels or the call fails.
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
+#include <functional>
 #include <cstring>
 #include <new>
 #include <string>
@@ -30,7 +32,10 @@ struct ilqr_handle {
   double* plant = nullptr;     // [B][n] MPC plant state (boundary layout, lazy)
   double* u_applied = nullptr; // [B][m] controls applied by the last MPC step
   int32_t* pinned_i32 = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kMaxBurst = 4;        // iterations launched back to back between host syncs (tail)
+  cudaEvent_t ev[kMaxBurst][4] = {};
+  int32_t burst_active[kMaxBurst] = {};      // live trajectories at the launch of each pending iteration
+  int32_t n_pending = 0;                     // iterations launched since the last sync
   bool ev_valid = false;
   int64_t launches = 0;
   bool loaded = false, have_gains = false, have_candidate = false;
@@ -40,6 +45,8 @@ struct ilqr_handle {
   bool compaction = true;      // retire + re-pack finished trajectories between iterations
   double* ab_scratch = nullptr; // [H*20][S] linearisations for the split backward pass (lazy)
   int32_t split_below = 20000; // use the split backward pass when nslots <= this
+  int32_t burst_max = 1;       // cap on iterations per host sync (1 = sync every iteration, the default: bursts of
+                               // 2-4 measured no faster on B200, bench9 vs bench9_b1; 0 = size-based policy; ILQR_BURST_MAX)
   int32_t coop_below = 8192;   // ... and the warp-cooperative Riccati kernel when nslots <= this
   int32_t fwd_split_above = 24000;  // two-kernel forward pass (α = 1, then dense retries) when nslots > this
   bool pend_bwd = false, pend_fwd = false;
@@ -86,7 +93,7 @@ void free_all(ilqr_handle* h) {
   cudaFree(h->ab_scratch); cudaFree(h->plant); cudaFree(h->u_applied);
   cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
   if (h->pinned_i32) cudaFreeHost(h->pinned_i32);
-  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& es : h->ev) for (auto& e : es) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -115,15 +122,23 @@ int32_t finish_upload(ilqr_handle* h) {
 
 // fold the event times of the passes launched since the last sync into the profile (stream must be idle)
 void accumulate_profile(ilqr_handle* h) {
-  float ms = 0.f;
-  if (h->pend_bwd && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) {
-    if (h->prof[2] == 0) h->prof[5] = ms;
-    h->prof[0] += ms; h->prof[2] += 1; h->prof[4] += h->n_active_host;
+  static const bool trace_timing = getenv("ILQR_TRACE_TIMING") != nullptr;
+  for (int i = 0; i < h->n_pending; ++i) {
+    if (h->burst_active[i] <= 0) continue;   // an iteration launched after everything had finished: no work
+    float bms = 0.f, fms = 0.f;
+    if (cudaEventElapsedTime(&bms, h->ev[i][0], h->ev[i][1]) == cudaSuccess) {
+      if (h->prof[2] == 0) h->prof[5] = bms;
+      h->prof[0] += bms; h->prof[2] += 1; h->prof[4] += h->burst_active[i];
+    }
+    if (cudaEventElapsedTime(&fms, h->ev[i][2], h->ev[i][3]) == cudaSuccess) {
+      if (h->prof[3] == 0) h->prof[6] = fms;
+      h->prof[1] += fms; h->prof[3] += 1;
+    }
+    if (trace_timing)
+      fprintf(stderr, "[ilqr] iter %3d active %6d slots %6d bwd %.3f ms fwd %.3f ms\n", (int)h->prof[2], h->burst_active[i],
+              h->st.nslots, bms, fms);
   }
-  if (h->pend_fwd && cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) {
-    if (h->prof[3] == 0) h->prof[6] = ms;
-    h->prof[1] += ms; h->prof[3] += 1;
-  }
+  h->n_pending = 0;
   h->pend_bwd = h->pend_fwd = false;
 }
 
@@ -207,7 +222,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   CKC(cudaSetDevice(p->device));
   init_kernel_attributes();
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  for (auto& e : h->ev) CKC(cudaEventCreate(&e));
+  for (auto& es : h->ev) for (auto& e : es) CKC(cudaEventCreate(&e));
   DevState& s = h->st;
   const size_t N = p->H + 1, H = p->H, n = p->n, m = p->m;
   s.S = ((int64_t)p->B + 31) / 32 * 32;
@@ -246,6 +261,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
 #undef CKC
   if (const char* e = getenv("ILQR_SPLIT_BELOW")) h->split_below = atoi(e);
   if (const char* e = getenv("ILQR_COOP_BELOW")) h->coop_below = atoi(e);
+  if (const char* e = getenv("ILQR_BURST_MAX")) h->burst_max = atoi(e);
   if (const char* e = getenv("ILQR_FWD_SPLIT_ABOVE")) h->fwd_split_above = atoi(e);
   if (const char* e = getenv("ILQR_COMPACTION")) h->compaction = atoi(e) != 0;
   h->mp.alpha = p->model_params[0]; h->mp.beta = p->model_params[1]; h->mp.delta = p->model_params[2];
@@ -388,10 +404,11 @@ static int32_t backward_async(ilqr_handle* h) {
   if (!h->loaded) return fail(h, ILQR_ERR_STATE, "backward_pass before upload");
   const bool split = h->st.nslots <= h->split_below;
   if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
-  cudaEventRecord(h->ev[0], h->stream);
+  const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
+  cudaEventRecord(h->ev[e][0], h->stream);
   if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->st.nslots <= h->coop_below, h->stream);
   else launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
-  cudaEventRecord(h->ev[1], h->stream);
+  cudaEventRecord(h->ev[e][1], h->stream);
   h->launches += split ? 2 : 1;
   h->have_gains = true; h->pend_bwd = true;
   return check_launch(h, "backward kernel");
@@ -400,10 +417,11 @@ static int32_t backward_async(ilqr_handle* h) {
 static int32_t forward_async(ilqr_handle* h) {
   if (!h->have_gains) return fail(h, ILQR_ERR_STATE, "forward_pass before backward_pass");
   const bool fsplit = h->st.nslots > h->fwd_split_above;
-  cudaEventRecord(h->ev[2], h->stream);
+  const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
+  cudaEventRecord(h->ev[e][2], h->stream);
   if (fsplit) launch_fwd_split_two_link(h->st, h->mp, h->cp, h->stream);
   else launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
-  cudaEventRecord(h->ev[3], h->stream);
+  cudaEventRecord(h->ev[e][3], h->stream);
   h->launches += (fsplit && h->prob.n_alpha > 1) ? 2 : 1;
   h->have_candidate = true; h->ev_valid = true; h->pend_fwd = true;
   return check_launch(h, "forward kernel");
@@ -411,7 +429,10 @@ static int32_t forward_async(ilqr_handle* h) {
 
 static int32_t commit_async(ilqr_handle* h, double tol) {
   if (!h->have_candidate) return fail(h, ILQR_ERR_STATE, "commit before forward_pass");
+  if (h->n_pending >= ilqr_handle::kMaxBurst) return fail(h, ILQR_ERR_STATE, "too many iterations in flight");
+  h->st.pub_slot = h->n_pending;
   launch_commit(h->st, tol, h->stream);
+  h->n_pending += 1;
   h->launches += 1;
   h->have_gains = false; h->have_candidate = false;
   return check_launch(h, "commit kernel");
@@ -420,8 +441,13 @@ static int32_t commit_async(ilqr_handle* h, double tol) {
 static int32_t read_n_active(ilqr_handle* h, int32_t* n_active) {
   // commit_kernel's last block stored the count into the mapped pinned int; nslots == 0 launches nothing
   CK(h, cudaStreamSynchronize(h->stream));
+  const volatile int32_t* pub = (volatile int32_t*)h->pinned_i32;
+  const int np = h->n_pending;
+  // live count at the launch of pending iteration i = what iteration i-1 published
+  h->burst_active[0] = h->n_active_host;
+  for (int i = 1; i < np; ++i) h->burst_active[i] = h->st.nslots > 0 ? pub[i - 1] : 0;
+  const int32_t na = (h->st.nslots > 0 && np > 0) ? pub[np - 1] : (np > 0 ? 0 : h->n_active_host);
   accumulate_profile(h);
-  const int32_t na = h->st.nslots > 0 ? ((volatile int32_t*)h->pinned_i32)[0] : 0;
   h->n_active_host = na;
   if (n_active) *n_active = na;
   // retire + re-pack once enough slots have finished to free whole warps
@@ -492,24 +518,27 @@ int32_t ilqr_iterate(ilqr_handle* h, double tol, int32_t* n_active) {
 }
 
 static int32_t fit_loop(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_run) {
-  int32_t it = 0, na = h->prob.B;
-  static const bool trace_timing = getenv("ILQR_TRACE_TIMING") != nullptr;
-  for (it = 1; it <= max_iter; ++it) {
-    const int32_t na_before = h->n_active_host, slots_before = h->st.nslots;
-    const double b0 = h->prof[0], f0 = h->prof[1];
-    if (int32_t rc = backward_async(h)) return rc;
-    if (int32_t rc = forward_async(h)) return rc;
-    if (int32_t rc = commit_async(h, tol)) return rc;
+  // Iterations are launched in bursts between host syncs once the active set is small: the kernels skip
+  // finished trajectories on their own, so the only cost of not looking every time is ≤ burst-1 empty
+  // iterations at the very end, while the GPU no longer idles for a host round trip per iteration.
+  int32_t it = 0, na = h->n_active_host;
+  while (it < max_iter && na > 0) {
+    int burst = h->st.nslots > h->split_below ? 1 : (h->st.nslots > 4096 ? 2 : ilqr_handle::kMaxBurst);
+    if (burst > max_iter - it) burst = max_iter - it;
+    if (h->burst_max > 0 && burst > h->burst_max) burst = h->burst_max;
+    for (int b = 0; b < burst; ++b) {
+      if (int32_t rc = backward_async(h)) return rc;
+      if (int32_t rc = forward_async(h)) return rc;
+      if (int32_t rc = commit_async(h, tol)) return rc;
+    }
+    const double done_before = h->prof[2];
     if (int32_t rc = read_n_active(h, &na)) return rc;
-    if (trace_timing)
-      fprintf(stderr, "[ilqr] iter %3d active %6d slots %6d bwd %.3f ms fwd %.3f ms\n", it, na_before, slots_before,
-              h->prof[0] - b0, h->prof[1] - f0);
-    if (na == 0) break;
+    it += (int32_t)(h->prof[2] - done_before);   // iterations that had live trajectories
+    if (na > 0 && (int32_t)(h->prof[2] - done_before) < burst) break;   // cannot happen; guards an endless loop
   }
   if (na > 0) {
     launch_finalize_max_iter(h->st, h->stream);
     h->launches += 1;
-    it = max_iter;
   }
   launch_flush_live(h->st, true, h->stream);   // every result now sits in the per-trajectory mirrors
   h->launches += 3;
@@ -613,12 +642,20 @@ int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, c
   if (!h || !x_init || !u_init || !x_out || !u_out) return fail(h, ILQR_ERR_INVALID, "null argument");
   const ilqr_problem& p = h->prob;
   CK(h, cudaSetDevice(h->device));
+  static const bool trace_phases = getenv("ILQR_TRACE_PHASES") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   if (int32_t rc = upload_xtraj(h, x_traj, cudaMemcpyHostToDevice)) return rc;
   const size_t N = p.H + 1, B = p.B;
   CK(h, cudaMemcpyAsync(h->stage_x, x_init, sizeof(double) * N * p.n * B, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * B, cudaMemcpyHostToDevice, h->stream));
+  if (trace_phases) cudaStreamSynchronize(h->stream);
+  const double t1 = now();
   if (int32_t rc = finish_upload(h)) return rc;
   if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;
+  if (trace_phases) cudaStreamSynchronize(h->stream);
+  const double t2 = now();
+  struct Tail { bool on; double t0, t1, t2; std::function<double()> now; ~Tail() { if (on) fprintf(stderr, "[ilqr] solve phases: h2d %.2f ms, fit %.2f ms, d2h %.2f ms\n", t1 - t0, t2 - t1, now() - t2); } } tail{trace_phases, t0, t1, t2, now};
   CK(h, cudaMemcpyAsync(x_out, h->st.out_x, sizeof(double) * N * p.n * B, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpyAsync(u_out, h->st.out_u, sizeof(double) * p.H * p.m * B, cudaMemcpyDeviceToHost, h->stream));
   if (cost_out) CK(h, cudaMemcpyAsync(cost_out, h->st.r_prev_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
@@ -641,8 +678,8 @@ int32_t ilqr_last_kernel_ms(ilqr_handle* h, float* bwd_ms, float* fwd_ms) {
   if (!h->ev_valid) return fail(h, ILQR_ERR_STATE, "no passes recorded");
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaStreamSynchronize(h->stream));
-  if (bwd_ms) CK(h, cudaEventElapsedTime(bwd_ms, h->ev[0], h->ev[1]));
-  if (fwd_ms) CK(h, cudaEventElapsedTime(fwd_ms, h->ev[2], h->ev[3]));
+  if (bwd_ms) CK(h, cudaEventElapsedTime(bwd_ms, h->ev[0][0], h->ev[0][1]));
+  if (fwd_ms) CK(h, cudaEventElapsedTime(fwd_ms, h->ev[0][2], h->ev[0][3]));
   return ILQR_OK;
 }
 

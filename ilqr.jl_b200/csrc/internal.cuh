@@ -40,7 +40,8 @@ struct DevState {
   int32_t* traj;     // [S] original trajectory index living in this slot
   int32_t* n_active; // device counter accumulated by commit (reset by its last block)
   uint32_t* blocks_done;     // commit's block ticket (last block publishes the count)
-  int32_t* n_active_host;    // device alias of a MAPPED pinned host int: the published count
+  int32_t* n_active_host;    // device alias of a MAPPED pinned host int array: the published counts
+  int32_t pub_slot;          // which entry of n_active_host this commit publishes to (iterations run in bursts)
   // per-TRAJECTORY result mirrors (index = original trajectory), written when a slot retires / is flushed
   double* r_prev_cost; double* r_new_cost; double* r_alpha; double* r_du2;
   int32_t* r_status; int32_t* r_iters; int32_t* r_active;

@@ -833,7 +833,7 @@ __global__ void commit_kernel(const __grid_constant__ DevState st, double tol) {
   __syncthreads();
   if (last && threadIdx.x == 0) {
     const int32_t total = atomicAdd(st.n_active, 0);
-    *st.n_active_host = total;
+    st.n_active_host[st.pub_slot] = total;
     *st.n_active = 0;
     *st.blocks_done = 0u;
     *st.n_retry = 0;
