@@ -23,7 +23,7 @@ _ip = ctypes.POINTER(ctypes.c_int32)
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ilqr_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ilqr_oracle.hpp", "serial_chain.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
     return so
@@ -183,3 +183,119 @@ def lq32_fit(A, B, Q, R, Qf, x, u, max_iter=10, tol=1e-6, reg=0.01):
 
 def hardware_threads():
     return int(lib().oracle_hardware_threads())
+
+
+# ---------------------------------------------------------------------------------------------
+# Serial-chain rigid-body plugin (oracle/serial_chain.hpp)
+# ---------------------------------------------------------------------------------------------
+CHAIN_STRIDE = 20   # xyz(3) rpy(3) axis(3) mass(1) com(3) ixx ixy ixz iyy iyz izz (6) pad(1)
+
+
+class ChainSpec(ctypes.Structure):
+    _fields_ = [("nq", ctypes.c_int32), ("pad", ctypes.c_int32), ("dt", ctypes.c_double),
+                ("gravity", ctypes.c_double * 3), ("joints", ctypes.c_double * (8 * CHAIN_STRIDE)),
+                ("x_target", ctypes.c_double * 16), ("w_x", ctypes.c_double * 16), ("w_u", ctypes.c_double * 8),
+                ("w_xf", ctypes.c_double * 16)]
+
+
+def chain_spec(joints, gravity=(0.0, 0.0, 0.0), dt=0.01, x_target=None, w_x=None, w_u=None, w_xf=None):
+    """joints: (nq, 20) array, one row per joint+child link (layout CHAIN_STRIDE above)."""
+    joints = np.asarray(joints, dtype=np.float64)
+    nq = joints.shape[0]
+    assert joints.shape == (nq, CHAIN_STRIDE) and nq in (2, 3, 6, 7), joints.shape
+    s = ChainSpec()
+    s.nq = nq; s.dt = dt
+    for k in range(3):
+        s.gravity[k] = float(gravity[k])
+    flat = joints.reshape(-1)
+    for i, v in enumerate(flat):
+        s.joints[i] = float(v)
+    for name, arr, cnt in (("x_target", x_target, 2 * nq), ("w_x", w_x, 2 * nq), ("w_u", w_u, nq), ("w_xf", w_xf, 2 * nq)):
+        if arr is not None:
+            arr = np.asarray(arr, dtype=np.float64)
+            assert arr.shape == (cnt,), (name, arr.shape)
+            for i in range(cnt):
+                getattr(s, name)[i] = float(arr[i])
+    return s
+
+
+def _chk(rc):
+    if rc < 0:
+        raise ValueError("oracle: unsupported chain size")
+    return rc
+
+
+def chain_mass_bias(spec, q, qd):
+    nq = spec.nq
+    M = np.zeros((nq, nq), order="F"); b = np.zeros(nq)
+    _chk(lib().oracle_chain_mass_bias(ctypes.byref(spec), _p(_f(q, (nq,))), _p(_f(qd, (nq,))), _p(M), _p(b)))
+    return M, b
+
+
+def chain_continuous_dynamics(spec, x, u):
+    nq = spec.nq; y = np.zeros(2 * nq)
+    _chk(lib().oracle_chain_continuous_dynamics(ctypes.byref(spec), _p(_f(x, (2 * nq,))), _p(_f(u, (nq,))), _p(y)))
+    return y
+
+
+def chain_dynamics(spec, x, u):
+    nq = spec.nq; y = np.zeros(2 * nq)
+    _chk(lib().oracle_chain_dynamics(ctypes.byref(spec), _p(_f(x, (2 * nq,))), _p(_f(u, (nq,))), _p(y)))
+    return y
+
+
+def chain_linearize(spec, x, u):
+    nq = spec.nq
+    A = np.zeros((2 * nq, 2 * nq), order="F"); B = np.zeros((2 * nq, nq), order="F")
+    _chk(lib().oracle_chain_linearize(ctypes.byref(spec), _p(_f(x, (2 * nq,))), _p(_f(u, (nq,))), _p(A), _p(B)))
+    return A, B
+
+
+def chain_rollout(spec, x0, u):
+    nq = spec.nq; u = _f(u); H = u.shape[0]
+    x = np.zeros((H + 1, 2 * nq), order="F")
+    _chk(lib().oracle_chain_rollout(ctypes.byref(spec), H, _p(_f(x0, (2 * nq,))), _p(u), _p(x)))
+    return x
+
+
+def chain_backward_pass(spec, x, u, reg=0.01):
+    nq = spec.nq; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 2 * nq))
+    d = np.zeros((H, nq), order="F"); K = np.zeros((H, nq, 2 * nq), order="F")
+    st = _chk(lib().oracle_chain_backward_pass(ctypes.byref(spec), H, _p(x), _p(u), ctypes.c_double(reg), _p(d), _p(K)))
+    return d, K, st
+
+
+def chain_total_cost(spec, x, u, x_traj=None):
+    nq = spec.nq; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 2 * nq))
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 2 * nq))
+    c = ctypes.c_double()
+    _chk(lib().oracle_chain_total_cost(ctypes.byref(spec), H, _p(x), _p(u), _p(xt), ctypes.byref(c)))
+    return c.value
+
+
+def chain_forward_pass(spec, x, u, d, K, prev_cost, jmax=32, x_traj=None):
+    nq = spec.nq; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 2 * nq)); d = _f(d, (H, nq)); K = _f(K, (H, nq, 2 * nq))
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 2 * nq))
+    xb = np.zeros((H + 1, 2 * nq), order="F"); ub = np.zeros((H, nq), order="F")
+    c = ctypes.c_double(); a = ctypes.c_double()
+    st = _chk(lib().oracle_chain_forward_pass(ctypes.byref(spec), H, _p(x), _p(u), _p(xt), _p(d), _p(K),
+                                              ctypes.c_double(prev_cost), jmax, _p(xb), _p(ub), ctypes.byref(c),
+                                              ctypes.byref(a)))
+    return xb, ub, c.value, a.value, st
+
+
+def chain_fit_batch(spec, x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, reg=0.01, jmax=32, nthreads=1, traces=True):
+    """x_init (N,n,B), u_init (H,m,B) Fortran-ordered.  Returns dict like fit_batch."""
+    nq = spec.nq
+    u = _f(u_init).copy(order="F"); H, _, B = u.shape
+    x = _f(x_init, (H + 1, 2 * nq, B)).copy(order="F")
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 2 * nq, B))
+    cost = alpha = du2 = None
+    if traces:
+        cost = np.full((max_iter, B), np.nan, order="F"); alpha = np.full((max_iter, B), np.nan, order="F")
+        du2 = np.full((max_iter, B), np.nan, order="F")
+    iters = np.zeros(B, dtype=np.int32); conv = np.zeros(B, dtype=np.int32); status = np.zeros(B, dtype=np.int32)
+    _chk(lib().oracle_chain_fit_batch(ctypes.byref(spec), B, H, _p(x), _p(u), _p(xt), max_iter, ctypes.c_double(tol),
+                                      ctypes.c_double(reg), jmax, nthreads, _p(cost), _p(alpha), _p(du2),
+                                      iters.ctypes.data_as(_ip), conv.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
+    return dict(x=x, u=u, cost=cost, alpha=alpha, du2=du2, iters=iters, converged=conv.astype(bool), status=status)

@@ -1,0 +1,136 @@
+"""Independent NumPy restatement of the serial-chain rigid-body plugin (test infrastructure).
+
+Deliberately NOT the algorithm of oracle/serial_chain.hpp (spatial-vector RNEA + CRBA) nor of the
+CUDA kernels (3-vector Newton–Euler in link frames): this one is the textbook Lagrangian form
+  M(q) = Σ_i m_i J_vᵢᵀ J_vᵢ + J_ωᵢᵀ (R_i I_i R_iᵀ) J_ωᵢ            (link COM Jacobians, world frame)
+  bias_k = Σ_ij Γ_kij q̇_i q̇_j + ∂V/∂q_k,  Γ_kij = ½(∂M_kj/∂q_i + ∂M_ki/∂q_j − ∂M_ij/∂q_k)
+with ∂M/∂q and ∂V/∂q from complex-step differentiation (exact to rounding).  Agreement of the three
+formulations pins the dynamics that RigidBodyDynamics.jl's mass_matrix / dynamics_bias compute
+(test/RBD_2_link_example/RBD_helper_functions.jl:57-66).
+"""
+import numpy as np
+
+STRIDE = 20
+
+
+def joint_row(xyz=(0, 0, 0), rpy=(0, 0, 0), axis=(0, 0, 1), mass=1.0, com=(0, 0, 0), inertia=(1, 0, 0, 1, 0, 1)):
+    """One row of the flat chain description: joint origin/axis + child link inertial."""
+    axis = np.asarray(axis, dtype=np.float64)
+    axis = axis / np.linalg.norm(axis)
+    return np.concatenate([xyz, rpy, axis, [mass], com, inertia, [0.0]]).astype(np.float64)
+
+
+def seven_dof_chain():
+    """BASELINE config 4: 7 revolute joints in the test/urdf/6Dof_arm.urdf pattern —
+    axes z,y,z,y,z,y,z, origin (1,0,0), mass 3, inertia 0.5·I, COM at the link frame, zero gravity."""
+    rows = []
+    for i in range(7):
+        rows.append(joint_row(xyz=(1, 0, 0), axis=(0, 0, 1) if i % 2 == 0 else (0, 1, 0), mass=3.0,
+                              inertia=(0.5, 0, 0, 0.5, 0, 0.5)))
+    return np.stack(rows)
+
+
+def random_chain(nq, rng, general=True):
+    """A chain that exercises every term: rpy offsets, skew axes, off-origin COMs, full inertia tensors."""
+    rows = []
+    for i in range(nq):
+        A = rng.normal(size=(3, 3))
+        I = A @ A.T + 0.5 * np.eye(3)            # SPD inertia about the COM
+        inertia = (I[0, 0], I[0, 1], I[0, 2], I[1, 1], I[1, 2], I[2, 2])
+        if general:
+            axis = rng.normal(size=3)
+            rpy = rng.uniform(-1, 1, 3)
+        else:
+            axis = np.eye(3)[rng.integers(0, 3)]
+            rpy = np.zeros(3)
+        rows.append(joint_row(xyz=rng.uniform(-1, 1, 3), rpy=rpy, axis=axis, mass=rng.uniform(0.5, 3.0),
+                              com=rng.uniform(-0.5, 0.5, 3), inertia=inertia))
+    return np.stack(rows)
+
+
+def _rot_rpy(rpy):
+    r, p, y = rpy
+    Rx = np.array([[1, 0, 0], [0, np.cos(r), -np.sin(r)], [0, np.sin(r), np.cos(r)]])
+    Ry = np.array([[np.cos(p), 0, np.sin(p)], [0, 1, 0], [-np.sin(p), 0, np.cos(p)]])
+    Rz = np.array([[np.cos(y), -np.sin(y), 0], [np.sin(y), np.cos(y), 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def _skew(a):
+    return np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+
+
+def _rot_axis(a, q):
+    K = _skew(a)
+    return np.eye(3) + np.sin(q) * K + (1 - np.cos(q)) * (K @ K)
+
+
+def _kinematics(joints, q):
+    """World pose of every link (complex-safe: no conj, no abs)."""
+    nq = joints.shape[0]
+    R = np.eye(3, dtype=q.dtype); o = np.zeros(3, dtype=q.dtype)
+    Rs, os_, zs = [], [], []
+    for i in range(nq):
+        xyz, rpy, axis = joints[i, 0:3], joints[i, 3:6], joints[i, 6:9]
+        o = o + R @ xyz
+        R = R @ _rot_rpy(rpy) @ _rot_axis(axis, q[i])
+        Rs.append(R); os_.append(o); zs.append(R @ axis)
+    return Rs, os_, zs
+
+
+def mass_matrix(joints, q):
+    q = np.asarray(q)
+    nq = joints.shape[0]
+    Rs, os_, zs = _kinematics(joints, q)
+    M = np.zeros((nq, nq), dtype=q.dtype)
+    for i in range(nq):
+        m, com, I6 = joints[i, 9], joints[i, 10:13], joints[i, 13:19]
+        Ic = np.array([[I6[0], I6[1], I6[2]], [I6[1], I6[3], I6[4]], [I6[2], I6[4], I6[5]]])
+        pc = os_[i] + Rs[i] @ com
+        Jv = np.zeros((3, nq), dtype=q.dtype); Jw = np.zeros((3, nq), dtype=q.dtype)
+        for j in range(i + 1):
+            Jv[:, j] = np.cross(zs[j], pc - os_[j]); Jw[:, j] = zs[j]
+        M = M + m * (Jv.T @ Jv) + Jw.T @ (Rs[i] @ Ic @ Rs[i].T) @ Jw
+    return M
+
+
+def potential(joints, q, gravity):
+    q = np.asarray(q)
+    Rs, os_, _ = _kinematics(joints, q)
+    V = 0.0
+    for i in range(joints.shape[0]):
+        pc = os_[i] + Rs[i] @ joints[i, 10:13]
+        V = V - joints[i, 9] * (np.asarray(gravity) @ pc)
+    return V
+
+
+def bias(joints, q, qd, gravity=(0, 0, 0)):
+    nq = joints.shape[0]
+    h = 1e-30
+    dM = np.zeros((nq, nq, nq)); dV = np.zeros(nq)       # dM[:,:,k] = ∂M/∂q_k
+    for k in range(nq):
+        qc = np.asarray(q, dtype=np.complex128).copy(); qc[k] += 1j * h
+        dM[:, :, k] = mass_matrix(joints, qc).imag / h
+        dV[k] = np.imag(potential(joints, qc, gravity)) / h
+    c = np.zeros(nq)
+    for k in range(nq):
+        acc = 0.0
+        for i in range(nq):
+            for j in range(nq):
+                acc += 0.5 * (dM[k, j, i] + dM[k, i, j] - dM[i, j, k]) * qd[i] * qd[j]
+        c[k] = acc + dV[k]
+    return c
+
+
+def continuous_dynamics(joints, x, u, gravity=(0, 0, 0)):
+    nq = joints.shape[0]
+    q, qd = x[:nq], x[nq:]
+    M = mass_matrix(joints, np.asarray(q, dtype=np.float64))
+    vdot = np.linalg.solve(M, u - bias(joints, q, qd, gravity))
+    return np.concatenate([qd, vdot])
+
+
+def dynamics(joints, x, u, gravity=(0, 0, 0), dt=0.01):
+    f = lambda xx: continuous_dynamics(joints, xx, u, gravity)
+    k1 = dt * f(x); k2 = dt * f(x + k1 / 2); k3 = dt * f(x + k2 / 2); k4 = dt * f(x + k3)
+    return x + (1.0 / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)

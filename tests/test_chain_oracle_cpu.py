@@ -1,0 +1,102 @@
+"""Pins the serial-chain oracle (oracle/serial_chain.hpp) against the independent NumPy restatement
+(tests/np_chain.py), finite differences and physical invariants.  CPU only."""
+import numpy as np
+import pytest
+
+import np_chain
+from oracle import oracle_py as orc
+
+
+@pytest.mark.parametrize("nq,general", [(2, True), (3, True), (7, True), (7, False), (6, False)])
+def test_mass_matrix_and_bias_match_lagrangian_form(nq, general):
+    rng = np.random.default_rng(10 + nq)
+    joints = np_chain.random_chain(nq, rng, general)
+    g = (0.3, -0.2, -9.81)
+    spec = orc.chain_spec(joints, gravity=g)
+    for _ in range(3):
+        q = rng.uniform(-2, 2, nq); qd = rng.uniform(-2, 2, nq)
+        M, b = orc.chain_mass_bias(spec, q, qd)
+        M0 = np_chain.mass_matrix(joints, q); b0 = np_chain.bias(joints, q, qd, g)
+        assert np.max(np.abs(M - M0)) <= 1e-11 * np.max(np.abs(M0))
+        assert np.max(np.abs(b - b0)) <= 1e-10 * max(1.0, np.max(np.abs(b0)))
+        assert np.max(np.abs(M - M.T)) <= 1e-12 * np.max(np.abs(M))
+        assert np.all(np.linalg.eigvalsh(0.5 * (M + M.T)) > 0)
+
+
+def test_config4_chain_dynamics_match():
+    joints = np_chain.seven_dof_chain()
+    spec = orc.chain_spec(joints)
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-1, 1, 7), rng.uniform(-1, 1, 7)]); u = rng.uniform(-5, 5, 7)
+    xd = orc.chain_continuous_dynamics(spec, x, u)
+    xd0 = np_chain.continuous_dynamics(joints, x, u)
+    assert np.max(np.abs(xd - xd0)) <= 1e-11 * np.max(np.abs(xd0))
+    xn = orc.chain_dynamics(spec, x, u)
+    xn0 = np_chain.dynamics(joints, x, u)
+    assert np.max(np.abs(xn - xn0)) <= 1e-12 * np.max(np.abs(xn0))
+
+
+def test_planar_two_link_chain_reproduces_the_two_link_plugin():
+    """The reference's hand-derived 2-link model (2_link_helper_functions.jl:29-33) as a URDF-style chain:
+    same inertia matrix, so the CRBA restatement is anchored to the reference's own closed form."""
+    c = orc.constants()
+    l = np.sqrt(2.) / 2.; r = 0.5 * l; m = 1.0; Iz = m * l * l / 12.0
+    joints = np.stack([
+        np_chain.joint_row(xyz=(0, 0, 0), axis=(0, 0, 1), mass=m, com=(r, 0, 0), inertia=(0, 0, 0, 0, 0, Iz)),
+        np_chain.joint_row(xyz=(l, 0, 0), axis=(0, 0, 1), mass=m, com=(r, 0, 0), inertia=(0, 0, 0, 0, 0, Iz))])
+    spec = orc.chain_spec(joints)
+    for th2 in (-1.3, 0.2, 2.5):
+        M, _ = orc.chain_mass_bias(spec, [0.4, th2], [0.0, 0.0])
+        M_ref = np.array([[c["alpha"] + 2 * c["beta"] * np.cos(th2), c["delta"] + c["beta"] * np.cos(th2)],
+                          [c["delta"] + c["beta"] * np.cos(th2), c["delta"]]])
+        assert np.max(np.abs(M - M_ref)) <= 1e-13
+
+
+@pytest.mark.parametrize("nq", [2, 7])
+def test_linearisation_matches_central_differences(nq):
+    rng = np.random.default_rng(nq)
+    joints = np_chain.random_chain(nq, rng, True)
+    spec = orc.chain_spec(joints, gravity=(0, 0, -9.81))
+    x = rng.uniform(-1, 1, 2 * nq); u = rng.uniform(-2, 2, nq)
+    A, B = orc.chain_linearize(spec, x, u)
+    h = 1e-6
+    for j in range(2 * nq):
+        e = np.zeros(2 * nq); e[j] = h
+        fd = (orc.chain_dynamics(spec, x + e, u) - orc.chain_dynamics(spec, x - e, u)) / (2 * h)
+        assert np.max(np.abs(A[:, j] - fd)) <= 1e-8 * max(1.0, np.max(np.abs(A)))
+    for j in range(nq):
+        e = np.zeros(nq); e[j] = h
+        fd = (orc.chain_dynamics(spec, x, u + e) - orc.chain_dynamics(spec, x, u - e)) / (2 * h)
+        assert np.max(np.abs(B[:, j] - fd)) <= 1e-8 * max(1.0, np.max(np.abs(B)))
+
+
+def test_energy_is_conserved_by_unforced_rollout():
+    """u = 0, no gravity: kinetic energy ½ q̇ᵀMq̇ is an invariant of the continuous dynamics (RK4 error only)."""
+    joints = np_chain.seven_dof_chain()
+    spec = orc.chain_spec(joints)
+    rng = np.random.default_rng(3)
+    x0 = np.concatenate([rng.uniform(-1, 1, 7), rng.uniform(-0.5, 0.5, 7)])
+    x = orc.chain_rollout(spec, x0, np.zeros((50, 7), order="F"))
+    E = []
+    for k in (0, 25, 50):
+        M, _ = orc.chain_mass_bias(spec, x[k, :7], x[k, 7:])
+        E.append(0.5 * x[k, 7:] @ M @ x[k, 7:])
+    assert abs(E[1] - E[0]) <= 1e-8 * E[0] and abs(E[2] - E[0]) <= 1e-8 * E[0]
+
+
+def test_chain_fit_decreases_cost_and_converges():
+    joints = np_chain.seven_dof_chain()
+    rng = np.random.default_rng(0)
+    target = np.concatenate([rng.uniform(-1, 1, 7), np.zeros(7)])
+    w = np.concatenate([np.ones(7), np.zeros(7)])
+    spec = orc.chain_spec(joints, x_target=target, w_x=w, w_u=np.ones(7), w_xf=w)
+    H, B = 20, 2
+    x = np.zeros((H + 1, 14, B), order="F"); u = np.zeros((H, 7, B), order="F")
+    for b in range(B):
+        x0 = np.concatenate([rng.uniform(-1, 1, 7), np.zeros(7)])
+        x[:, :, b] = orc.chain_rollout(spec, x0, u[:, :, b])
+    out = orc.chain_fit_batch(spec, x, u, max_iter=30, tol=1e-6, nthreads=2)
+    for b in range(B):
+        c = out["cost"][: out["iters"][b], b]
+        assert np.all(np.diff(c) < 0), c
+        assert out["status"][b] == 0
