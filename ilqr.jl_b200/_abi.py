@@ -7,9 +7,10 @@ from . import _build
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_N, MAX_M = 16, 8
-MODEL_TWO_LINK = 1
+MODEL_TWO_LINK, MODEL_SERIAL_CHAIN = 1, 2
+MAX_JOINTS, CHAIN_STRIDE = 8, 20
 VARIANT_AUTO, VARIANT_LANE_PER_TRAJ, VARIANT_WARP_PER_TRAJ = 0, 1, 2
 
 STATUS_NAN_GAINS, STATUS_NAN_ROLLOUT, STATUS_LS_EXHAUSTED = 1, 2, 4
@@ -30,6 +31,8 @@ class Problem(ctypes.Structure):
         ("model_params", ctypes.c_double * 32),
         ("x_target", ctypes.c_double * MAX_N), ("w_x", ctypes.c_double * MAX_N),
         ("w_u", ctypes.c_double * MAX_M), ("w_xf", ctypes.c_double * MAX_N),
+        ("nq", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("gravity", ctypes.c_double * 3),
+        ("chain", ctypes.c_double * (MAX_JOINTS * CHAIN_STRIDE)),
     ]
 
 
@@ -38,6 +41,8 @@ _H = ctypes.c_void_p
 SYMBOLS = {
     "ilqr_abi_version": (ctypes.c_int32, []),
     "ilqr_problem_two_link": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.c_int32]),
+    "ilqr_problem_serial_chain": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_int32, ctypes.c_int32]),
     "ilqr_create": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.POINTER(_H)]),
     "ilqr_destroy": (ctypes.c_int32, [_H]),
     "ilqr_last_error": (ctypes.c_char_p, [_H]),

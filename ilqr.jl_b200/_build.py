@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libilqr_b200.so")
-SOURCES = ["capi.cu", "kernels_lpt.cu", "layout.cu", "pool.cu"]
+SOURCES = ["capi.cu", "kernels_lpt.cu", "kernels_chain.cu", "layout.cu", "pool.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",
@@ -33,12 +33,27 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     extra = os.environ.get("ILQR_NVCC_EXTRA", "").split()   # experiments: -DILQR_FWD1_STAGES=2 …
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    # one nvcc per translation unit, in parallel, then one link step
+    objdir = os.path.join(HERE, "..", "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run([_nvcc()] + compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+        return src, obj, res
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, res in results:
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+        if verbose:
+            print(res.stderr)
+    res = subprocess.run([_nvcc(), "-shared", "-o", LIB] + [obj for _, obj, _ in results], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -23,6 +23,8 @@ struct ilqr_handle {
   cudaStream_t stream = nullptr;
   DevState st{};
   TwoLinkP mp{};
+  ChainP chain{};
+  bool is_chain = false;
   CostP cp{};
   // TF (boundary-layout) staging on device
   double* stage_x = nullptr;   // [B][n*N]
@@ -191,14 +193,40 @@ int32_t ilqr_problem_two_link(ilqr_problem* p, int32_t H, int32_t B) {
   return ILQR_OK;
 }
 
+int32_t ilqr_problem_serial_chain(ilqr_problem* p, int32_t nq, const double* joints, const double* gravity, int32_t H,
+                                  int32_t B) {
+  if (!p || !joints || nq < 1 || nq > ILQR_MAX_JOINTS) return ILQR_ERR_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->abi_version = ILQR_ABI_VERSION;
+  p->model_id = ILQR_MODEL_SERIAL_CHAIN;
+  p->nq = nq; p->n = 2 * nq; p->m = nq; p->H = H; p->B = B;
+  p->n_alpha = 32; p->variant = ILQR_VARIANT_AUTO;
+  p->dt = 0.01;    // animate_RBD_2_link.jl:8
+  p->reg = 0.01;   // src/backward_pass.jl:214
+  std::memcpy(p->chain, joints, sizeof(double) * nq * ILQR_CHAIN_STRIDE);
+  if (gravity) for (int k = 0; k < 3; ++k) p->gravity[k] = gravity[k];
+  return ILQR_OK;
+}
+
 const char* ilqr_last_error(const ilqr_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   if (!p || !out) return fail(nullptr, ILQR_ERR_INVALID, "null argument");
   *out = nullptr;
   if (p->abi_version != ILQR_ABI_VERSION) return fail(nullptr, ILQR_ERR_INVALID, "abi_version mismatch");
-  if (p->model_id != ILQR_MODEL_TWO_LINK || p->n != 4 || p->m != 2)
-    return fail(nullptr, ILQR_ERR_INVALID, "unsupported model (only ILQR_MODEL_TWO_LINK, n=4, m=2)");
+  const bool is_chain = p->model_id == ILQR_MODEL_SERIAL_CHAIN;
+  if (is_chain) {
+    if (!chain_supported(p->nq) || p->n != 2 * p->nq || p->m != p->nq)
+      return fail(nullptr, ILQR_ERR_INVALID, "ILQR_MODEL_SERIAL_CHAIN needs nq in {2,3,6,7}, n = 2 nq, m = nq");
+    for (int i = 0; i < p->nq; ++i) {
+      const double* a = p->chain + i * ILQR_CHAIN_STRIDE + 6;
+      if (std::fabs(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] - 1.0) > 1e-12)
+        return fail(nullptr, ILQR_ERR_INVALID, "joint axes must be unit vectors");
+      if (!(p->chain[i * ILQR_CHAIN_STRIDE + 9] > 0.0)) return fail(nullptr, ILQR_ERR_INVALID, "link masses must be > 0");
+    }
+  } else if (p->model_id != ILQR_MODEL_TWO_LINK || p->n != 4 || p->m != 2) {
+    return fail(nullptr, ILQR_ERR_INVALID, "unsupported model (ILQR_MODEL_TWO_LINK with n=4, m=2 or ILQR_MODEL_SERIAL_CHAIN)");
+  }
   if (p->H < 1 || p->B < 1 || p->n_alpha < 1 || p->n_alpha > 64 || p->trace_iters < 0)
     return fail(nullptr, ILQR_ERR_INVALID, "bad H/B/n_alpha/trace_iters");
   int ndev = 0;
@@ -210,7 +238,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
 
   ilqr_handle* h = new (std::nothrow) ilqr_handle();
   if (!h) return fail(nullptr, ILQR_ERR_INVALID, "out of host memory");
-  h->prob = *p; h->device = p->device;
+  h->prob = *p; h->device = p->device; h->is_chain = is_chain;
 #define CKC(call)                                                                               \
   do {                                                                                          \
     cudaError_t e__ = (call);                                                                   \
@@ -264,6 +292,28 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   if (const char* e = getenv("ILQR_BURST_MAX")) h->burst_max = atoi(e);
   if (const char* e = getenv("ILQR_FWD_SPLIT_ABOVE")) h->fwd_split_above = atoi(e);
   if (const char* e = getenv("ILQR_COMPACTION")) h->compaction = atoi(e) != 0;
+  if (is_chain) {
+    ChainP& c = h->chain;
+    c.nq = p->nq; c.dt = p->dt;
+    for (int k = 0; k < 3; ++k) c.g[k] = p->gravity[k];
+    for (int i = 0; i < p->nq; ++i) {
+      const double* r = p->chain + i * ILQR_CHAIN_STRIDE;
+      for (int k = 0; k < 3; ++k) { c.xyz[i][k] = r[k]; c.axis[i][k] = r[6 + k]; c.com[i][k] = r[10 + k]; }
+      c.mass[i] = r[9];
+      for (int k = 0; k < 6; ++k) c.I[i][k] = r[13 + k];
+      // URDF rpy: R = Rz(yaw)·Ry(pitch)·Rx(roll)
+      const double cr = std::cos(r[3]), sr = std::sin(r[3]), cpi = std::cos(r[4]), sp = std::sin(r[4]);
+      const double cy = std::cos(r[5]), sy = std::sin(r[5]);
+      const double R[9] = {cy * cpi, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                           sy * cpi, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                           -sp, cpi * sr, cpi * cr};
+      for (int k = 0; k < 9; ++k) c.R0[i][k] = R[k];
+      c.has_r0[i] = (r[3] != 0.0 || r[4] != 0.0 || r[5] != 0.0) ? 1 : 0;
+      c.axis_code[i] = 3;
+      for (int k = 0; k < 3; ++k)
+        if (r[6 + k] == 1.0 && r[6 + (k + 1) % 3] == 0.0 && r[6 + (k + 2) % 3] == 0.0) c.axis_code[i] = k;
+    }
+  }
   h->mp.alpha = p->model_params[0]; h->mp.beta = p->model_params[1]; h->mp.delta = p->model_params[2];
   h->mp.dt = p->dt; h->mp.twobeta = 2 * p->model_params[1];
   for (int i = 0; i < kMaxN; ++i) { h->cp.x_target[i] = p->x_target[i]; h->cp.w_x[i] = p->w_x[i]; h->cp.w_xf[i] = p->w_xf[i]; }
@@ -324,7 +374,8 @@ int32_t ilqr_upload_x0(ilqr_handle* h, const double* x0, const double* u_init, c
   launch_reset_state(h->st, h->stream);
   launch_tf_to_bf(h->stage_x, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
   launch_tf_to_bf(h->stage_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream);
-  launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
+  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->st.x[1], h->stream);
+  else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
   h->launches += 4;
   if (int32_t rc = check_launch(h, "upload_x0 kernels")) return rc;
   h->loaded = true; h->have_gains = false; h->have_candidate = false;
@@ -359,7 +410,8 @@ static int32_t mpc_reinit(ilqr_handle* h, int shift) {
   launch_reset_state(h->st, h->stream);
   launch_tf_to_bf(h->plant, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
   launch_tf_to_bf(h->st.out_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream, shift);
-  launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
+  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->st.x[1], h->stream);
+  else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
   h->launches += 4;
   if (int32_t rc = check_launch(h, "mpc re-initialisation kernels")) return rc;
   h->loaded = true; h->have_gains = false; h->have_candidate = false;
@@ -391,7 +443,8 @@ int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_ap
   const ilqr_problem& p = h->prob;
   CK(h, cudaSetDevice(h->device));
   if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;        // solution → out_x / out_u (by trajectory)
-  launch_mpc_advance_two_link(h->mp, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
+  if (h->is_chain) launch_mpc_advance_chain(h->chain, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
+  else launch_mpc_advance_two_link(h->mp, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
   h->launches += 1;
   if (u_applied) CK(h, cudaMemcpyAsync(u_applied, h->u_applied, sizeof(double) * p.m * p.B, cudaMemcpyDeviceToHost, h->stream));
   if (x_plant) CK(h, cudaMemcpyAsync(x_plant, h->plant, sizeof(double) * p.n * p.B, cudaMemcpyDeviceToHost, h->stream));
@@ -402,11 +455,12 @@ int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_ap
 
 static int32_t backward_async(ilqr_handle* h) {
   if (!h->loaded) return fail(h, ILQR_ERR_STATE, "backward_pass before upload");
-  const bool split = h->st.nslots <= h->split_below;
+  const bool split = !h->is_chain && h->st.nslots <= h->split_below;
   if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][0], h->stream);
-  if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->st.nslots <= h->coop_below, h->stream);
+  if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->cp, h->stream);
+  else if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->st.nslots <= h->coop_below, h->stream);
   else launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][1], h->stream);
   h->launches += split ? 2 : 1;
@@ -416,10 +470,11 @@ static int32_t backward_async(ilqr_handle* h) {
 
 static int32_t forward_async(ilqr_handle* h) {
   if (!h->have_gains) return fail(h, ILQR_ERR_STATE, "forward_pass before backward_pass");
-  const bool fsplit = h->st.nslots > h->fwd_split_above;
+  const bool fsplit = !h->is_chain && h->st.nslots > h->fwd_split_above;
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][2], h->stream);
-  if (fsplit) launch_fwd_split_two_link(h->st, h->mp, h->cp, h->stream);
+  if (h->is_chain) launch_fwd_chain(h->st, h->chain, h->cp, h->stream);
+  else if (fsplit) launch_fwd_split_two_link(h->st, h->mp, h->cp, h->stream);
   else launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][3], h->stream);
   h->launches += (fsplit && h->prob.n_alpha > 1) ? 2 : 1;

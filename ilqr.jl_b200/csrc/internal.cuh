@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "chain.cuh"
 #include "two_link.cuh"
 
 namespace ilqr {
@@ -81,6 +82,14 @@ void launch_compact(const DevState& st, int new_nslots, cudaStream_t s);
 // copy every live slot's scalars (and optionally its current iterate) to the per-trajectory mirrors
 void launch_flush_live(const DevState& st, bool with_iterates, cudaStream_t s);
 void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaStream_t s);
+
+// kernels_chain.cu — serial-chain rigid-body models (warp-per-trajectory backward pass, n = 2·nq, m = nq)
+bool chain_supported(int nq);
+void launch_bwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s);
+void launch_fwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s);
+void launch_rollout_init_chain(const DevState& st, const ChainP& cp, const double* d_x0 /*[slot][n]*/, cudaStream_t s);
+void launch_mpc_advance_chain(const ChainP& cp, const double* out_u, double* plant, double* u_applied, int B, int H,
+                              cudaStream_t s);
 
 // layout.cu — boundary (Julia, time-fastest "TF") <-> BF transposes
 // TF: src[t*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + s]

@@ -979,6 +979,48 @@ __global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ DevSt
   }
 }
 
+// runtime-(n, m) versions of the two kernels above for the serial-chain models (scalar accesses)
+__global__ void __launch_bounds__(128) retire_generic_kernel(const __grid_constant__ DevState st, int n_retire) {
+  const int w = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_retire) return;
+  const int s = st.retire_list[w], t = st.traj[s], c = st.cur[s];
+  const int64_t S = st.S;
+  const int N = st.H + 1, H = st.H, n = st.n, m = st.m;
+  const double* __restrict__ X = st.x[c];
+  const double* __restrict__ U = st.u[c];
+  double* __restrict__ ox = st.out_x + (int64_t)t * n * N;
+  double* __restrict__ ou = st.out_u + (int64_t)t * m * H;
+  for (int k = lane; k < N; k += 32)
+    for (int cc = 0; cc < n; ++cc) ox[cc * N + k] = X[((int64_t)k * S + s) * n + cc];
+  for (int k = lane; k < H; k += 32)
+    for (int cc = 0; cc < m; ++cc) ou[cc * H + k] = U[((int64_t)k * S + s) * m + cc];
+  if (lane == 0) copy_scalars_to_mirror(st, s, t, 0);
+}
+
+__global__ void __launch_bounds__(128) move_generic_kernel(const __grid_constant__ DevState st) {
+  const int w = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= *st.n_move) return;
+  const int src = st.move_src[w], dst = st.move_dst[w], c = st.cur[src];
+  const int64_t S = st.S;
+  const int N = st.H + 1, H = st.H, n = st.n, m = st.m;
+  double* __restrict__ X = st.x[c];
+  double* __restrict__ U = st.u[c];
+  for (int k = lane; k < N; k += 32)
+    for (int cc = 0; cc < n; ++cc) {
+      X[((int64_t)k * S + dst) * n + cc] = X[((int64_t)k * S + src) * n + cc];
+      if (st.xtraj) st.xtraj[((int64_t)k * S + dst) * n + cc] = st.xtraj[((int64_t)k * S + src) * n + cc];
+    }
+  for (int k = lane; k < H; k += 32)
+    for (int cc = 0; cc < m; ++cc) U[((int64_t)k * S + dst) * m + cc] = U[((int64_t)k * S + src) * m + cc];
+  if (lane == 0) {
+    st.prev_cost[dst] = st.prev_cost[src]; st.new_cost[dst] = st.new_cost[src];
+    st.alpha[dst] = st.alpha[src]; st.du2[dst] = st.du2[src];
+    st.status[dst] = st.status[src]; st.iters[dst] = st.iters[src];
+    st.cur[dst] = c; st.bar[dst] = st.bar[src]; st.traj[dst] = st.traj[src];
+    st.active[dst] = 1; st.active[src] = 0;
+  }
+}
+
 __global__ void flush_scalars_kernel(const __grid_constant__ DevState st) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < st.nslots) copy_scalars_to_mirror(st, s, st.traj[s], st.active[s]);
@@ -1050,8 +1092,13 @@ void launch_compact(const DevState& st, int new_nslots, cudaStream_t s) {
   const int n_retire = st.nslots - new_nslots;
   if (n_retire <= 0) return;
   compact_plan_kernel<<<1, 1024, 0, s>>>(st, new_nslots);
-  retire_kernel<<<grid_for(n_retire * 32, 128), 128, 0, s>>>(st, n_retire);
-  if (new_nslots > 0) move_kernel<<<grid_for(n_retire * 32, 128), 128, 0, s>>>(st);
+  const bool two_link = st.n == NX && st.m == NU;
+  if (two_link) retire_kernel<<<grid_for(n_retire * 32, 128), 128, 0, s>>>(st, n_retire);
+  else retire_generic_kernel<<<grid_for(n_retire * 32, 128), 128, 0, s>>>(st, n_retire);
+  if (new_nslots > 0) {
+    if (two_link) move_kernel<<<grid_for(n_retire * 32, 128), 128, 0, s>>>(st);
+    else move_generic_kernel<<<grid_for(n_retire * 32, 128), 128, 0, s>>>(st);
+  }
 }
 void launch_flush_live(const DevState& st, bool with_iterates, cudaStream_t s) {
   if (st.nslots <= 0) return;

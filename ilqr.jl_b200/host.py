@@ -39,6 +39,91 @@ def two_link_problem(H, B=1, n_alpha=32, trace_iters=0, device=0, reg=None, vari
     return p
 
 
+def serial_chain_problem(joints, H, B=1, gravity=(0.0, 0.0, 0.0), x_target=None, w_x=None, w_u=None, w_xf=None, dt=0.01,
+                         n_alpha=32, trace_iters=0, device=0, reg=None):
+    """The reference's rigid-body plugin (test/RBD_2_link_example/RBD_helper_functions.jl:48-116) for a fixed-base
+    serial chain: `joints` is an (nq, 20) array, one row per joint + child link — origin xyz(3), rpy(3), unit
+    axis(3), mass, COM(3), ixx ixy ixz iyy iyz izz, pad — e.g. from load_urdf().  Costs are the diagonal
+    quadratics l = Σ w_x (x* − x)² + Σ w_u u², lf = Σ w_xf (x* − x)²."""
+    lib = _abi.load_library()
+    joints = np.ascontiguousarray(np.asarray(joints, dtype=np.float64))
+    nq = joints.shape[0]
+    if joints.shape != (nq, _abi.CHAIN_STRIDE):
+        raise ValueError("joints must be (nq, %d)" % _abi.CHAIN_STRIDE)
+    g = np.ascontiguousarray(np.asarray(gravity, dtype=np.float64))
+    p = Problem()
+    rc = lib.ilqr_problem_serial_chain(ctypes.byref(p), nq, joints.ctypes.data, g.ctypes.data, int(H), int(B))
+    if rc != 0:
+        raise IlqrError("ilqr_problem_serial_chain failed")
+    p.dt = dt
+    p.n_alpha = n_alpha
+    p.trace_iters = trace_iters
+    p.device = device
+    if reg is not None:
+        p.reg = reg
+    for name, arr, cnt in (("x_target", x_target, 2 * nq), ("w_x", w_x, 2 * nq), ("w_u", w_u, nq), ("w_xf", w_xf, 2 * nq)):
+        if arr is not None:
+            arr = np.asarray(arr, dtype=np.float64)
+            if arr.shape != (cnt,):
+                raise ValueError("%s must have %d entries" % (name, cnt))
+            for i in range(cnt):
+                getattr(p, name)[i] = float(arr[i])
+    return p
+
+
+def load_urdf(path):
+    """Mini URDF loader for what the reference feeds parse_urdf (test/urdf/*.urdf, RBD_helper_functions.jl:6-7):
+    a serial chain of revolute/continuous joints.  Returns (joints[(nq, 20)], base_inertial) where base_inertial =
+    (mass, com[3], inertia[6]) of the root link (irrelevant for a fixed base)."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+
+    def vec(el, attr, default):
+        return [float(t) for t in el.get(attr).split()] if el is not None and el.get(attr) else list(default)
+
+    def inertial(link):
+        ine = link.find("inertial")
+        if ine is None:
+            return 0.0, [0.0] * 3, [0.0] * 6
+        mass = float(ine.find("mass").get("value"))
+        com = vec(ine.find("origin"), "xyz", (0, 0, 0))
+        if ine.find("origin") is not None and any(abs(v) > 0 for v in vec(ine.find("origin"), "rpy", (0, 0, 0))):
+            raise ValueError("rotated <inertial> frames are not supported")
+        I = ine.find("inertia")
+        return mass, com, [float(I.get(k)) for k in ("ixx", "ixy", "ixz", "iyy", "iyz", "izz")]
+
+    links = {l.get("name"): l for l in root.findall("link")}
+    joints = [j for j in root.findall("joint")]
+    children = {j.find("child").get("link") for j in joints}
+    roots = [n for n in links if n not in children]
+    if len(roots) != 1:
+        raise ValueError("expected exactly one root link")
+    rows, parent = [], roots[0]
+    by_parent = {}
+    for j in joints:
+        by_parent.setdefault(j.find("parent").get("link"), []).append(j)
+    while parent in by_parent:
+        js = by_parent[parent]
+        if len(js) != 1:
+            raise ValueError("not a serial chain: link %s has %d children" % (parent, len(js)))
+        j = js[0]
+        if j.get("type") == "fixed":
+            # massless frames welded to the chain (6Dof_arm.urdf's tool_frame) carry no dynamics
+            if inertial(links[j.find("child").get("link")])[0] != 0.0 or j.find("child").get("link") in by_parent:
+                raise ValueError("fixed joint %s: only massless leaf frames are supported" % j.get("name"))
+            break
+        if j.get("type") not in ("revolute", "continuous"):
+            raise ValueError("joint %s: only revolute/continuous joints are supported" % j.get("name"))
+        axis = np.array(vec(j.find("axis"), "xyz", (1, 0, 0)), dtype=np.float64)
+        axis = axis / np.linalg.norm(axis)
+        child = j.find("child").get("link")
+        mass, com, I = inertial(links[child])
+        rows.append(np.concatenate([vec(j.find("origin"), "xyz", (0, 0, 0)), vec(j.find("origin"), "rpy", (0, 0, 0)),
+                                    axis, [mass], com, I, [0.0]]))
+        parent = child
+    return np.stack(rows), inertial(links[roots[0]])
+
+
 def _f64(a):
     return np.asfortranarray(np.asarray(a, dtype=np.float64))
 

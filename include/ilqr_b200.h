@@ -41,15 +41,21 @@
 extern "C" {
 #endif
 
-#define ILQR_ABI_VERSION 1
+#define ILQR_ABI_VERSION 2
 #define ILQR_MAX_N 16
 #define ILQR_MAX_M 8
+#define ILQR_MAX_JOINTS 8
+#define ILQR_CHAIN_STRIDE 20 /* doubles per joint row of ilqr_problem.chain */
 
 /* model ids: which (dynamicsf, immediate_cost, final_cost) triple runs on device */
 enum ilqr_model {
   /* test/2_link_example/2_link_helper_functions.jl:4-108 — planar 2-link arm,
    * RK4, n=4, m=2.  model_params = {alpha, beta, delta} (lines :12-14). */
-  ILQR_MODEL_TWO_LINK = 1
+  ILQR_MODEL_TWO_LINK = 1,
+  /* test/RBD_2_link_example/RBD_helper_functions.jl:48-79 for fixed-base serial chains of revolute
+   * joints (the mechanisms of test/urdf/*.urdf): RK4 of v̇ = M(q) \ (u − bias(q,v)), q̇ = v;
+   * x = [q; q̇], n = 2·nq, m = nq.  Described by ilqr_problem.{nq, gravity, chain}. */
+  ILQR_MODEL_SERIAL_CHAIN = 2
 };
 
 /* per-trajectory status bits (int32) */
@@ -122,6 +128,15 @@ typedef struct ilqr_problem {
   double w_x[ILQR_MAX_N];
   double w_u[ILQR_MAX_M];
   double w_xf[ILQR_MAX_N];
+  /* ILQR_MODEL_SERIAL_CHAIN only (what parse_urdf reads, RBD_helper_functions.jl:6-7): joint i and its
+   * child link occupy chain[i*ILQR_CHAIN_STRIDE ..]: joint <origin xyz> (3), <origin rpy> (3),
+   * unit <axis xyz> (3), link <mass> (1), inertial <origin xyz> = COM (3),
+   * <inertia ixx ixy ixz iyy iyz izz> about the COM in link axes (6), pad (1).  Joint i's parent is
+   * link i-1 (link -1 = the fixed base).  nq in {2, 3, 6, 7}. */
+  int32_t nq;
+  int32_t reserved0;
+  double gravity[3];      /* gravity acceleration in the base frame (RBD_helper_functions.jl:7: zero) */
+  double chain[ILQR_MAX_JOINTS * ILQR_CHAIN_STRIDE];
 } ilqr_problem;
 
 typedef struct ilqr_handle ilqr_handle;
@@ -131,6 +146,11 @@ int32_t ilqr_abi_version(void);
 /* Fill `p` with the reference's 2-link problem (constants computed exactly as
  * 2_link_helper_functions.jl:4-26 does) for horizon H and batch B. */
 int32_t ilqr_problem_two_link(ilqr_problem* p, int32_t H, int32_t B);
+
+/* Fill `p` for a serial chain: joints = nq rows of ILQR_CHAIN_STRIDE doubles (layout above), gravity[3]
+ * (NULL = zero), dt = 0.01, reg = 0.01, n_alpha = 32, all cost weights zero (set x_target/w_x/w_u/w_xf after). */
+int32_t ilqr_problem_serial_chain(ilqr_problem* p, int32_t nq, const double* joints, const double* gravity, int32_t H,
+                                  int32_t B);
 
 int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out);
 int32_t ilqr_destroy(ilqr_handle* h);

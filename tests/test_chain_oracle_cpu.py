@@ -100,3 +100,20 @@ def test_chain_fit_decreases_cost_and_converges():
         c = out["cost"][: out["iters"][b], b]
         assert np.all(np.diff(c) < 0), c
         assert out["status"][b] == 0
+
+
+def test_urdf_loader_matches_committed_fixtures():
+    """The product's mini URDF loader on the reference's own mechanisms (only where /root/reference exists)."""
+    import os
+    import ilqr_b200
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    j6 = np.load(os.path.join(gold, "6dof_chain.npy")); j2 = np.load(os.path.join(gold, "2dof_chain.npy"))
+    assert j6.shape == (6, 20) and j2.shape == (2, 20)
+    # test/urdf/6Dof_arm.urdf: axes z,y,z,y,z,y; origins (.5,.5,0) then (1,0,0); mass 3; inertia 0.5·I
+    assert np.array_equal(j6[:, 6:9], np.array([[0, 0, 1], [0, 1, 0]] * 3, dtype=float))
+    assert np.array_equal(j6[0, 0:3], [0.5, 0.5, 0.0]) and np.all(j6[1:, 0:3] == [1.0, 0.0, 0.0])
+    assert np.all(j6[:, 9] == 3.0) and np.all(j6[:, 13:19] == [0.5, 0, 0, 0.5, 0, 0.5])
+    ref = "/root/reference/test/urdf"
+    if os.path.isdir(ref):
+        assert np.array_equal(ilqr_b200.load_urdf(os.path.join(ref, "6Dof_arm.urdf"))[0], j6)
+        assert np.array_equal(ilqr_b200.load_urdf(os.path.join(ref, "2Dof_arm.urdf"))[0], j2)

@@ -1,0 +1,147 @@
+"""GPU parity of the serial-chain model (ILQR_MODEL_SERIAL_CHAIN) against the CPU oracle, through the C ABI.
+
+Tolerances: north_star's 1e-9 relative on gains, candidates, per-iterate costs and final trajectories;
+1e-8 on the converged cost.  Sizes are what the oracle (dual numbers through 6×6 spatial algebra) finishes
+in seconds."""
+import numpy as np
+import pytest
+
+import ilqr_b200
+import np_chain
+from helpers import RTOL, RTOL_CONVERGED_COST, rel_err
+from ilqr_b200 import _abi
+from oracle import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(nq, general, B, H, seed, gravity=(0.0, 0.0, 0.0), config4=False, hard=None):
+    """hard = (w_final, dt): cheap controls, heavy terminal weight ⇒ 13…49 iterations with a spread of counts."""
+    rng = np.random.default_rng(seed)
+    joints = np_chain.seven_dof_chain() if config4 else np_chain.random_chain(nq, rng, general)
+    nq = joints.shape[0]
+    target = np.concatenate([rng.uniform(-1, 1, nq), np.zeros(nq)])
+    w_x = np.concatenate([np.ones(nq), 0.1 * np.ones(nq)])
+    w_u = rng.uniform(0.5, 2.0, nq)
+    w_xf = np.concatenate([10.0 * np.ones(nq), np.ones(nq)])
+    dt = 0.01
+    if hard is not None:
+        w_u = 0.01 * w_u
+        w_xf = np.concatenate([hard[0] * np.ones(nq), 0.1 * hard[0] * np.ones(nq)])
+        dt = hard[1]
+    spec = orc.chain_spec(joints, gravity=gravity, dt=dt, x_target=target, w_x=w_x, w_u=w_u, w_xf=w_xf)
+    prob = ilqr_b200.serial_chain_problem(joints, H, B, gravity=gravity, x_target=target, w_x=w_x, w_u=w_u, w_xf=w_xf,
+                                          dt=dt, trace_iters=60)
+    x0 = np.concatenate([rng.uniform(-1, 1, (B, nq)), rng.uniform(-0.5, 0.5, (B, nq))], axis=1)
+    u = np.asfortranarray(rng.uniform(-0.5, 0.5, (H, nq, B)))
+    x = np.zeros((H + 1, 2 * nq, B), order="F")
+    for b in range(B):
+        x[:, :, b] = orc.chain_rollout(spec, x0[b], u[:, :, b])
+    return spec, prob, x0, x, u
+
+
+CASES = [(3, True, (0.0, 0.0, -9.81)), (7, False, (0.0, 0.0, 0.0)), (7, True, (0.2, -0.1, -9.81)), (2, True, (0.0, 0.0, -9.81)),
+         (6, False, (0.0, 0.0, -9.81))]
+
+
+@pytest.mark.parametrize("nq,general,gravity", CASES)
+def test_rollout_init_matches_oracle(nq, general, gravity):
+    B, H = 5, 12
+    spec, prob, x0, x, u = _setup(nq, general, B, H, 100 + nq, gravity)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload_x0(np.asfortranarray(x0.T), u)
+        xg = s.download(_abi.X)
+    assert rel_err(xg, x) <= 1e-12
+
+
+@pytest.mark.parametrize("nq,general,gravity", CASES)
+def test_backward_pass_gains_match_oracle(nq, general, gravity):
+    B, H = 6, 15
+    spec, prob, x0, x, u = _setup(nq, general, B, H, 200 + nq, gravity)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        d, K, st = s.download(_abi.DUFF), s.download(_abi.K), s.download(_abi.STATUS)
+    assert not np.any(st)
+    for b in range(B):
+        d0, K0, st0 = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
+        assert st0 == 0
+        assert rel_err(d[:, :, b], d0) <= RTOL, (b, rel_err(d[:, :, b], d0))
+        assert rel_err(K[:, :, :, b], K0) <= RTOL, (b, rel_err(K[:, :, :, b], K0))
+
+
+@pytest.mark.parametrize("nq,general,gravity", CASES[:3])
+def test_forward_pass_candidate_matches_oracle(nq, general, gravity):
+    B, H = 6, 15
+    spec, prob, x0, x, u = _setup(nq, general, B, H, 300 + nq, gravity)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        d, K = s.download(_abi.DUFF), s.download(_abi.K)
+        s.forward_pass()
+        xb, ub, c, a = s.download(_abi.XBAR), s.download(_abi.UBAR), s.download(_abi.NEW_COST), s.download(_abi.ALPHA)
+    for b in range(B):
+        xb0, ub0, c0, a0, st0 = orc.chain_forward_pass(spec, x[:, :, b], u[:, :, b], d[:, :, b], K[:, :, :, b], np.inf)
+        assert a[b] == a0 == 1.0
+        assert rel_err(xb[:, :, b], xb0) <= RTOL and rel_err(ub[:, :, b], ub0) <= RTOL
+        assert abs(c[b] - c0) <= RTOL * abs(c0)
+
+
+def test_config4_chain_fit_matches_oracle():
+    """BASELINE config 4's mechanism (7-DoF, n = 14, m = 7) at oracle-sized B and H: iteration counts, per-iterate
+    cost / α / Σ(Δu)² traces, returned iterates."""
+    B, H = 12, 40
+    spec, prob, x0, x, u = _setup(7, False, B, H, 7, config4=True, hard=(1000.0, 0.05))
+    u[:] = 0.0
+    for b in range(B):
+        x[:, :, b] = orc.chain_rollout(spec, x0[b], u[:, :, b])
+    ref = orc.chain_fit_batch(spec, x, u, max_iter=60, tol=1e-9, nthreads=8)
+    assert ref["iters"].max() - ref["iters"].min() >= 10
+    with ilqr_b200.BatchSolver(prob) as s:
+        out = s.solve(x, u, max_iter=60, tol=1e-9)
+        ct, at, dt = s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE), s.download(_abi.DU2_TRACE)
+    assert np.array_equal(out["iters"], ref["iters"]), (out["iters"], ref["iters"])
+    for b in range(B):
+        it = ref["iters"][b]
+        assert rel_err(ct[:it, b], ref["cost"][:it, b]) <= RTOL
+        assert np.array_equal(at[:it, b], ref["alpha"][:it, b])
+        assert np.allclose(dt[:it, b], ref["du2"][:it, b], rtol=1e-6, atol=1e-12)
+        assert abs(out["cost"][b] - ref["cost"][it - 1, b]) <= RTOL_CONVERGED_COST * abs(ref["cost"][it - 1, b])
+    assert rel_err(out["x"], ref["x"]) <= RTOL and rel_err(out["u"], ref["u"]) <= 1e-7
+
+
+def test_general_chain_fit_with_gravity_and_compaction():
+    """Skew axes, rpy offsets, off-origin COMs, gravity; B = 70 spans three warps of slots so retiring converged
+    trajectories (compaction) is exercised with the runtime-(n, m) kernels."""
+    B, H = 70, 10
+    spec, prob, x0, x, u = _setup(3, True, B, H, 11, (0.0, 0.0, -9.81))
+    ref = orc.chain_fit_batch(spec, x, u, max_iter=40, tol=1e-5, nthreads=8)
+    with ilqr_b200.BatchSolver(prob) as s:
+        out = s.solve(x, u, max_iter=40, tol=1e-5)
+    assert np.array_equal(out["iters"], ref["iters"])
+    assert len(set(ref["iters"].tolist())) > 1
+    assert rel_err(out["x"], ref["x"]) <= RTOL
+    last = np.array([ref["cost"][ref["iters"][b] - 1, b] for b in range(B)])
+    assert np.max(np.abs(out["cost"] - last) / np.abs(last)) <= RTOL_CONVERGED_COST
+
+
+def test_urdf_loader_reads_the_reference_mechanisms():
+    """host-side mini URDF loader on the reference's own files is covered on CPU; here the loaded 6-DoF arm runs."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "6dof_chain.npy")
+    joints = np.load(path)
+    B, H = 4, 8
+    rng = np.random.default_rng(5)
+    target = np.concatenate([rng.uniform(-1, 1, 6), np.zeros(6)]); w = np.concatenate([np.ones(6), np.zeros(6)])
+    spec = orc.chain_spec(joints, x_target=target, w_x=w, w_u=np.ones(6), w_xf=w)
+    prob = ilqr_b200.serial_chain_problem(joints, H, B, x_target=target, w_x=w, w_u=np.ones(6), w_xf=w)
+    x0 = np.concatenate([rng.uniform(-1, 1, (B, 6)), np.zeros((B, 6))], axis=1)
+    u = np.zeros((H, 6, B), order="F"); x = np.zeros((H + 1, 12, B), order="F")
+    for b in range(B):
+        x[:, :, b] = orc.chain_rollout(spec, x0[b], u[:, :, b])
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload(x, u); s.backward_pass()
+        K = s.download(_abi.K)
+    for b in range(B):
+        _, K0, _ = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
+        assert rel_err(K[:, :, :, b], K0) <= RTOL
