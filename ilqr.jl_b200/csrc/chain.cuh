@@ -4,8 +4,8 @@
 //   test/RBD_2_link_example/RBD_helper_functions.jl:48-79   RK4 of  v̇ = M(q) \ (u − bias(q, v)),  q̇ = v
 // for the mechanisms of test/urdf/*.urdf (joint origin xyz/rpy + axis, child-link mass / COM / inertia).
 //
-// Formulation (own; the CPU oracle uses 6-D spatial vectors, this file 3-vector Newton–Euler in link
-// frames): inverse dynamics ID(q, q̇, q̈) by the recursive Newton–Euler algorithm, templated on the
+// Formulation (3-vector Newton–Euler in link frames, independent of the 6-D spatial-vector form the CPU
+// checker under tests/ uses): inverse dynamics ID(q, q̇, q̈) by the recursive Newton–Euler algorithm, templated on the
 // scalar type.  With T = double it yields the bias (q̈ = 0) and the columns of M (q̇ = 0, q̈ = e_j, no
 // gravity); with T = Dual (value + one tangent) it yields the directional derivative of ID along one
 // direction of (q, q̇), from which

@@ -27,6 +27,10 @@ struct Problem
     w_x::NTuple{16,Float64}
     w_u::NTuple{8,Float64}
     w_xf::NTuple{16,Float64}
+    nq::Int32
+    reserved0::Int32
+    gravity::NTuple{3,Float64}
+    chain::NTuple{160,Float64}     # ILQR_MAX_JOINTS × ILQR_CHAIN_STRIDE
 end
 
 const X, U, XBAR, UBAR, DUFF, K, NEW_COST, PREV_COST, ALPHA, DU2 = Int32.(0:9)
@@ -38,6 +42,18 @@ check(rc, h) = rc == 0 || error(unsafe_string(ccall((:ilqr_last_error, lib), Cst
 function two_link_problem(H::Integer, B::Integer)
     p = Ref{Problem}()
     ccall((:ilqr_problem_two_link, lib), Int32, (Ptr{Problem}, Int32, Int32), p, H, B) == 0 || error("problem")
+    return p[]
+end
+
+"""
+The rigid-body plugin of test/RBD_2_link_example/RBD_helper_functions.jl for a fixed-base serial chain.
+`joints` is 20 × nq (column per joint: origin xyz, rpy, unit axis, mass, COM, ixx ixy ixz iyy iyz izz, pad).
+Cost weights start at zero: rebuild the immutable struct with `Setfield`/`@set` or fill them before `Solver`.
+"""
+function serial_chain_problem(joints::Matrix{Float64}, gravity::Vector{Float64}, H::Integer, B::Integer)
+    p = Ref{Problem}()
+    ccall((:ilqr_problem_serial_chain, lib), Int32, (Ptr{Problem}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int32),
+          p, size(joints, 2), joints, gravity, H, B) == 0 || error("problem")
     return p[]
 end
 
