@@ -249,6 +249,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   } while (0)
   CKC(cudaSetDevice(p->device));
   init_kernel_attributes();
+  init_layout_attributes();
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& es : h->ev) for (auto& e : es) CKC(cudaEventCreate(&e));
   DevState& s = h->st;

@@ -95,6 +95,7 @@ void launch_mpc_advance_chain(const ChainP& cp, const double* out_u, double* pla
 // TF: src[t*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + s]
 // slot_traj (nullable): t = slot_traj[s] (live slots only); otherwise t = s.  nslots = number of slots moved.
 // shift: read time index k + shift (zeros past the end) — the receding-horizon shift of a control sequence
+void init_layout_attributes();   // opt-in dynamic shared memory; call once per process/device
 void launch_tf_to_bf(const double* tf, double* bf, const int32_t* slot_traj, int nslots, int T, int ncomp, int64_t S,
                      cudaStream_t s, int shift = 0);
 // MPC plant step: plant[t] ← f(plant[t], u_out[t][:,0]); u_applied[t] ← u_out[t][:,0]   (plant, u_applied: [B][n], [B][m])

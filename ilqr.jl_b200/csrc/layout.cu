@@ -14,17 +14,17 @@
 namespace ilqr {
 namespace {
 
-constexpr int TS = 32;   // slots per tile
+constexpr int kMaxTS = 32;   // slots per tile (fewer when ncomp is large, so that a tile stays ≤ 64 KB)
 constexpr int TK = 16;   // time steps per tile
 constexpr int kThreads = 256;
 
 // dynamic smem: TK rows of (TS*ncomp + 1) doubles
 __global__ void __launch_bounds__(kThreads)
 tf_to_ksc_kernel(const double* __restrict__ tf, double* __restrict__ ksc, const int32_t* __restrict__ slot_traj,
-                 int nslots, int T, int ncomp, int64_t S, int shift) {
+                 int nslots, int T, int ncomp, int64_t S, int shift, int TS) {
   extern __shared__ double tile[];
   const int row = TS * ncomp + 1;
-  const int k0 = blockIdx.x * TK, s0 = blockIdx.y * TS;
+  const int k0 = blockIdx.y * TK, s0 = blockIdx.x * TS;
   const int L = ncomp * T, E = TS * TK * ncomp;
   for (int idx = threadIdx.x; idx < E; idx += kThreads) {
     const int kk = idx % TK, rest = idx / TK, c = rest % ncomp, sl = rest / ncomp;
@@ -46,10 +46,11 @@ tf_to_ksc_kernel(const double* __restrict__ tf, double* __restrict__ ksc, const 
 
 __global__ void __launch_bounds__(kThreads)
 ksc_to_tf_kernel(const double* __restrict__ b0, const double* __restrict__ b1, const int32_t* __restrict__ sel,
-                 double* __restrict__ tf, const int32_t* __restrict__ slot_traj, int nslots, int T, int ncomp, int64_t S) {
+                 double* __restrict__ tf, const int32_t* __restrict__ slot_traj, int nslots, int T, int ncomp, int64_t S,
+                 int TS) {
   extern __shared__ double tile[];
   const int row = TS * ncomp + 1;
-  const int k0 = blockIdx.x * TK, s0 = blockIdx.y * TS;
+  const int k0 = blockIdx.y * TK, s0 = blockIdx.x * TS;
   const int L = ncomp * T, E = TS * TK * ncomp;
   for (int idx = threadIdx.x; idx < E; idx += kThreads) {
     const int within = idx % (TS * ncomp), kk = idx / (TS * ncomp);
@@ -71,22 +72,32 @@ ksc_to_tf_kernel(const double* __restrict__ b0, const double* __restrict__ b1, c
   }
 }
 
+// slots per tile: 32 for the small models; large component counts (K of a 7-DoF chain: 98) shrink the tile
+inline int tile_slots(int ncomp) { int ts = 512 / ncomp; return ts < 1 ? 1 : (ts > kMaxTS ? kMaxTS : ts); }
+
 }  // namespace
+
+void init_layout_attributes() {
+  cudaFuncSetAttribute(tf_to_ksc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(ksc_to_tf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
 
 void launch_tf_to_bf(const double* tf, double* bf, const int32_t* slot_traj, int nslots, int T, int ncomp, int64_t S,
                      cudaStream_t s, int shift) {
   if (nslots <= 0) return;
-  dim3 grid((T + TK - 1) / TK, (nslots + TS - 1) / TS);
+  const int TS = tile_slots(ncomp);
+  dim3 grid((nslots + TS - 1) / TS, (T + TK - 1) / TK);
   const size_t smem = sizeof(double) * TK * (TS * ncomp + 1);
-  tf_to_ksc_kernel<<<grid, kThreads, smem, s>>>(tf, bf, slot_traj, nslots, T, ncomp, S, shift);
+  tf_to_ksc_kernel<<<grid, kThreads, smem, s>>>(tf, bf, slot_traj, nslots, T, ncomp, S, shift, TS);
 }
 
 void launch_bf_to_tf(const double* bf0, const double* bf1, const int32_t* sel, double* tf, const int32_t* slot_traj,
                      int nslots, int T, int ncomp, int64_t S, cudaStream_t s) {
   if (nslots <= 0) return;
-  dim3 grid((T + TK - 1) / TK, (nslots + TS - 1) / TS);
+  const int TS = tile_slots(ncomp);
+  dim3 grid((nslots + TS - 1) / TS, (T + TK - 1) / TK);
   const size_t smem = sizeof(double) * TK * (TS * ncomp + 1);
-  ksc_to_tf_kernel<<<grid, kThreads, smem, s>>>(bf0, bf1, sel, tf, slot_traj, nslots, T, ncomp, S);
+  ksc_to_tf_kernel<<<grid, kThreads, smem, s>>>(bf0, bf1, sel, tf, slot_traj, nslots, T, ncomp, S, TS);
 }
 
 }  // namespace ilqr
