@@ -22,16 +22,18 @@ namespace ilqr {
 
 constexpr int kMaxQ = 8;
 
+// Canonical link frames (built on the host from the URDF description, capi.cu): every link frame is
+// re-oriented so that its joint axis is its own +z.  A joint is then "constant rotation Rf, then a turn
+// about z" for every mechanism, which keeps the device code free of per-joint branches (the first version
+// switched on the axis type per rotation and spent half its cycles on instruction-fetch stalls).
 struct ChainP {
   int32_t nq;
-  int32_t axis_code[kMaxQ];   // 0/1/2: joint axis is +x/+y/+z of the joint frame; 3: general unit axis
-  int32_t has_r0[kMaxQ];      // joint origin has a non-zero rpy
-  double xyz[kMaxQ][3];       // joint origin in the parent link frame
-  double R0[kMaxQ][9];        // fixed rotation of the joint frame (row-major, child → parent)
-  double axis[kMaxQ][3];
+  int32_t pad;
+  double xyz[kMaxQ][3];       // joint origin in the (canonical) parent link frame
+  double Rf[kMaxQ][9];        // row-major constant rotation: canonical child frame at q = 0 → canonical parent frame
   double mass[kMaxQ];
-  double com[kMaxQ][3];
-  double I[kMaxQ][6];         // ixx ixy ixz iyy iyz izz about the COM, link axes
+  double com[kMaxQ][3];       // in the canonical link frame
+  double I[kMaxQ][6];         // ixx ixy ixz iyy iyz izz about the COM, canonical link axes
   double g[3];                // gravity acceleration in the base frame
   double dt;
 };
@@ -68,35 +70,19 @@ template <class T> __device__ __forceinline__ V3<T> c_cross(const double p[3], V
   return {p[1] * a.z - p[2] * a.y, p[2] * a.x - p[0] * a.z, p[0] * a.y - p[1] * a.x};
 }
 
-// Rot(axis, ±q)·w from (sin q, cos q); sgn = +1: child → joint frame of the parent side, −1: the inverse
-template <class T> __device__ __forceinline__ V3<T> rot_axis(int code, const double a[3], T s, T c, V3<T> w, bool inverse) {
-  if (inverse) s = mk<T>(0.0) - s;
-  switch (code) {
-    case 0: return {w.x, c * w.y - s * w.z, s * w.y + c * w.z};
-    case 1: return {c * w.x + s * w.z, w.y, c * w.z - s * w.x};
-    case 2: return {c * w.x - s * w.y, s * w.x + c * w.y, w.z};
-    default: {
-      // Rodrigues: c·w + s·(a × w) + (1 − c)(a·w)·a
-      const V3<T> aw = c_cross<T>(a, w);
-      const T k = (1.0 - c) * (a[0] * w.x + a[1] * w.y + a[2] * w.z);
-      return {c * w.x + s * aw.x + a[0] * k, c * w.y + s * aw.y + a[1] * k, c * w.z + s * aw.z + a[2] * k};
-    }
-  }
-}
 template <class T> __device__ __forceinline__ V3<T> mat_c(const double R[9], V3<T> w, bool transpose) {
   if (!transpose)
     return {R[0] * w.x + R[1] * w.y + R[2] * w.z, R[3] * w.x + R[4] * w.y + R[5] * w.z, R[6] * w.x + R[7] * w.y + R[8] * w.z};
   return {R[0] * w.x + R[3] * w.y + R[6] * w.z, R[1] * w.x + R[4] * w.y + R[7] * w.z, R[2] * w.x + R[5] * w.y + R[8] * w.z};
 }
-// parent-frame vector → link-i frame, and back
+// parent-frame vector → link-i frame (Rot(z, −q)·Rfᵀ·w), and back (Rf·Rot(z, q)·w)
 template <class T> __device__ __forceinline__ V3<T> to_child(const ChainP& cp, int i, T s, T c, V3<T> w) {
-  if (cp.has_r0[i]) w = mat_c<T>(cp.R0[i], w, true);
-  return rot_axis<T>(cp.axis_code[i], cp.axis[i], s, c, w, true);
+  const V3<T> t = mat_c<T>(cp.Rf[i], w, true);
+  return {c * t.x + s * t.y, c * t.y - s * t.x, t.z};
 }
 template <class T> __device__ __forceinline__ V3<T> to_parent(const ChainP& cp, int i, T s, T c, V3<T> w) {
-  w = rot_axis<T>(cp.axis_code[i], cp.axis[i], s, c, w, false);
-  if (cp.has_r0[i]) w = mat_c<T>(cp.R0[i], w, false);
-  return w;
+  const V3<T> t = {c * w.x - s * w.y, s * w.x + c * w.y, w.z};
+  return mat_c<T>(cp.Rf[i], t, false);
 }
 
 // Inverse dynamics τ = ID(q, q̇, q̈) with gravity scaled by gscale (0 or 1); s, c = sin q, cos q.
@@ -113,10 +99,9 @@ __device__ __forceinline__ void chain_rnea(const ChainP& cp, const T (&s)[NQ], c
     const V3<T> wc = to_child<T>(cp, i, s[i], c[i], w);
     const V3<T> alc = to_child<T>(cp, i, s[i], c[i], al);
     acc = to_child<T>(cp, i, s[i], c[i], t);
-    const V3<T> av = {cp.axis[i][0] * qd[i], cp.axis[i][1] * qd[i], cp.axis[i][2] * qd[i]};
-    w = wc + av;
-    const V3<T> aa = {cp.axis[i][0] * qdd[i], cp.axis[i][1] * qdd[i], cp.axis[i][2] * qdd[i]};
-    al = alc + aa + cross<T>(w, av);
+    // joint axis = +z of the link frame: ω = ω_c + q̇ ẑ,  α = α_c + q̈ ẑ + ω × q̇ ẑ
+    w = {wc.x, wc.y, wc.z + qd[i]};
+    al = {alc.x + w.y * qd[i], alc.y - w.x * qd[i], alc.z + qdd[i]};
     const V3<T> ac = acc + cross_c<T>(al, cp.com[i]) + cross<T>(w, cross_c<T>(w, cp.com[i]));
     f[i] = {cp.mass[i] * ac.x, cp.mass[i] * ac.y, cp.mass[i] * ac.z};
     const double* I = cp.I[i];
@@ -130,7 +115,7 @@ __device__ __forceinline__ void chain_rnea(const ChainP& cp, const T (&s)[NQ], c
 #pragma unroll
   for (int i = NQ - 1; i >= 0; --i) {
     const V3<T> Fi = f[i] + F, Ni = n[i] + N;
-    tau[i] = cp.axis[i][0] * Ni.x + cp.axis[i][1] * Ni.y + cp.axis[i][2] * Ni.z;
+    tau[i] = Ni.z;
     if (i > 0) {
       F = to_parent<T>(cp, i, s[i], c[i], Fi);
       N = to_parent<T>(cp, i, s[i], c[i], Ni) + c_cross<T>(cp.xyz[i], F);
@@ -140,7 +125,7 @@ __device__ __forceinline__ void chain_rnea(const ChainP& cp, const T (&s)[NQ], c
 
 // ---- thread-local forward dynamics (rollouts: one thread per trajectory) -----------------------
 template <int NQ>
-__device__ __noinline__ void chain_forward_dynamics(const ChainP& cp, const double (&q)[NQ], const double (&v)[NQ],
+__device__ __forceinline__ void chain_forward_dynamics(const ChainP& cp, const double (&q)[NQ], const double (&v)[NQ],
                                                     const double (&u)[NQ], double (&vdot)[NQ]) {
   double s[NQ], c[NQ], zero[NQ];
 #pragma unroll

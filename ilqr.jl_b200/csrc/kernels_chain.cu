@@ -66,7 +66,7 @@ template <int NQ> __device__ __forceinline__ void m_solve(const double* Mf, cons
 // One RK4 stage at the primal point (q, v) with this lane's tangent (dq, dv, δu = e_udir):
 // vdot = M⁻¹(u − bias), dvdot = M⁻¹(δu − ∂ID(q, v, vdot)·(dq, dv)).
 template <int NQ>
-__device__ __noinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ>& sm, int lane, const double (&q)[NQ],
+__device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ>& sm, int lane, const double (&q)[NQ],
                                          const double (&v)[NQ], const double (&u)[NQ], const double (&dq)[NQ],
                                          const double (&dv)[NQ], int udir, double (&vdot)[NQ], double (&dvdot)[NQ]) {
   // sin/cos of the joint angles: lane i evaluates joint i, everybody receives all of them
