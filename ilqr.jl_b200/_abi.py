@@ -94,7 +94,7 @@ def load_library(rebuild=False):
     there is deliberately no fallback implementation."""
     global _lib
     if _lib is None or rebuild:
-        path = _build.build(force=rebuild)
+        path = os.environ.get("ILQR_LIB") or _build.build(force=rebuild)   # ILQR_LIB: a pre-built variant (experiments)
         lib = ctypes.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)   # AttributeError if the .so lacks a declared symbol

@@ -250,6 +250,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   CKC(cudaSetDevice(p->device));
   init_kernel_attributes();
   init_layout_attributes();
+  init_chain_attributes();
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& es : h->ev) for (auto& e : es) CKC(cudaEventCreate(&e));
   DevState& s = h->st;

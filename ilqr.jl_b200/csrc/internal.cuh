@@ -85,6 +85,7 @@ void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaSt
 
 // kernels_chain.cu — serial-chain rigid-body models (warp-per-trajectory backward pass, n = 2·nq, m = nq)
 bool chain_supported(int nq);
+void init_chain_attributes();    // opt-in dynamic shared memory; call once per process/device
 void launch_bwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s);
 void launch_fwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s);
 void launch_rollout_init_chain(const DevState& st, const ChainP& cp, const double* d_x0 /*[slot][n]*/, cudaStream_t s);

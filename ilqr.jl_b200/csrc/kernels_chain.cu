@@ -27,6 +27,9 @@ namespace ilqr {
 namespace {
 
 constexpr int kCW = 4;   // warps (= trajectories) per block in bwd_chain
+#ifndef ILQR_CHAIN_MIN_BLOCKS
+#define ILQR_CHAIN_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for
+#endif
 constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -43,7 +46,75 @@ template <int NQ> struct BwdSmem {
   double Mf[NQ * NQ];           // M(q) then its LU factors (unit lower below, upper on/above the diagonal)
   double bias[NQ];
   double invd[NQ];              // 1 / diagonal of the upper factor
+  // inverse-dynamics scratch.  The link loops are rolled (the unrolled version was 8.4 k instructions and
+  // instruction-fetch bound), so per-link state is indexed dynamically and lives here, [item][lane]:
+  double fn[NQ * 6 * 32];       // per lane: f_i, n_i (primal pass) or their tangents (dual pass)
+  double fnv[NQ * 6];           // dual pass: the values of f_i, n_i (the same on every lane)
+  double tng[2 * NQ * 32];      // per lane, per joint: (q̇, q̈) in the primal pass, (δq, δq̇) in the dual pass
+  double tau[NQ * 32];          // per lane: joint torques (primal pass) or their tangents (dual pass)
+  double qv[2 * NQ];            // stage point (q, q̇)
+  double sc[2 * NQ];            // sin q_i, cos q_i
+  double vd[NQ];                // v̇ at the stage point
 };
+
+// Per-pass views of the scratch: what joint i feeds the recursion and where link i's wrench is parked.
+template <int NQ> struct PrimalIO {
+  BwdSmem<NQ>& sm; int lane;
+  __device__ __forceinline__ double s(int i) const { return sm.sc[2 * i]; }
+  __device__ __forceinline__ double c(int i) const { return sm.sc[2 * i + 1]; }
+  __device__ __forceinline__ double qd(int i) const { return sm.tng[(2 * i) * 32 + lane]; }
+  __device__ __forceinline__ double qdd(int i) const { return sm.tng[(2 * i + 1) * 32 + lane]; }
+  __device__ __forceinline__ void put(int i, int k, double v) const { sm.fn[(i * 6 + k) * 32 + lane] = v; }
+  __device__ __forceinline__ double get(int i, int k) const { return sm.fn[(i * 6 + k) * 32 + lane]; }
+  __device__ __forceinline__ void out(int i, double v) const { sm.tau[i * 32 + lane] = v; }
+};
+template <int NQ> struct DualIO {
+  BwdSmem<NQ>& sm; int lane;
+  __device__ __forceinline__ Dual s(int i) const { return {sm.sc[2 * i], sm.sc[2 * i + 1] * sm.tng[(2 * i) * 32 + lane]}; }
+  __device__ __forceinline__ Dual c(int i) const { return {sm.sc[2 * i + 1], -sm.sc[2 * i] * sm.tng[(2 * i) * 32 + lane]}; }
+  __device__ __forceinline__ Dual qd(int i) const { return {sm.qv[NQ + i], sm.tng[(2 * i + 1) * 32 + lane]}; }
+  __device__ __forceinline__ Dual qdd(int i) const { return {sm.vd[i], 0.0}; }
+  __device__ __forceinline__ void put(int i, int k, Dual v) const { sm.fnv[i * 6 + k] = v.v; sm.fn[(i * 6 + k) * 32 + lane] = v.t; }
+  __device__ __forceinline__ Dual get(int i, int k) const { return {sm.fnv[i * 6 + k], sm.fn[(i * 6 + k) * 32 + lane]}; }
+  __device__ __forceinline__ void out(int i, Dual v) const { sm.tau[i * 32 + lane] = v.t; }
+};
+
+// chain_rnea (chain.cuh) with rolled link loops over shared-memory state; same arithmetic.
+template <class T, class IO, int NQ>
+__device__ __forceinline__ void warp_rnea(const ChainP& cp, const IO io, double gscale) {
+  V3<T> w = {mk<T>(0.0), mk<T>(0.0), mk<T>(0.0)}, al = w;
+  V3<T> acc = {mk<T>(-cp.g[0] * gscale), mk<T>(-cp.g[1] * gscale), mk<T>(-cp.g[2] * gscale)};
+#pragma unroll 1
+  for (int i = 0; i < NQ; ++i) {
+    const T s = io.s(i), c = io.c(i), qd = io.qd(i), qdd = io.qdd(i);
+    const V3<T> t = acc + cross_c<T>(al, cp.xyz[i]) + cross<T>(w, cross_c<T>(w, cp.xyz[i]));
+    const V3<T> wc = to_child<T>(cp, i, s, c, w);
+    const V3<T> alc = to_child<T>(cp, i, s, c, al);
+    acc = to_child<T>(cp, i, s, c, t);
+    w = {wc.x, wc.y, wc.z + qd};
+    al = {alc.x + w.y * qd, alc.y - w.x * qd, alc.z + qdd};
+    const V3<T> ac = acc + cross_c<T>(al, cp.com[i]) + cross<T>(w, cross_c<T>(w, cp.com[i]));
+    const V3<T> f = {cp.mass[i] * ac.x, cp.mass[i] * ac.y, cp.mass[i] * ac.z};
+    const double* I = cp.I[i];
+    const V3<T> Iw = {I[0] * w.x + I[1] * w.y + I[2] * w.z, I[1] * w.x + I[3] * w.y + I[4] * w.z,
+                      I[2] * w.x + I[4] * w.y + I[5] * w.z};
+    const V3<T> Ia = {I[0] * al.x + I[1] * al.y + I[2] * al.z, I[1] * al.x + I[3] * al.y + I[4] * al.z,
+                      I[2] * al.x + I[4] * al.y + I[5] * al.z};
+    const V3<T> n = Ia + cross<T>(w, Iw) + c_cross<T>(cp.com[i], f);
+    io.put(i, 0, f.x); io.put(i, 1, f.y); io.put(i, 2, f.z);
+    io.put(i, 3, n.x); io.put(i, 4, n.y); io.put(i, 5, n.z);
+  }
+  V3<T> F = {mk<T>(0.0), mk<T>(0.0), mk<T>(0.0)}, N = F;
+#pragma unroll 1
+  for (int i = NQ - 1; i >= 0; --i) {
+    const V3<T> f = {io.get(i, 0), io.get(i, 1), io.get(i, 2)}, n = {io.get(i, 3), io.get(i, 4), io.get(i, 5)};
+    const V3<T> Fi = f + F, Ni = n + N;
+    io.out(i, Ni.z);
+    const T s = io.s(i), c = io.c(i);
+    F = to_parent<T>(cp, i, s, c, Fi);
+    N = to_parent<T>(cp, i, s, c, Ni) + c_cross<T>(cp.xyz[i], F);
+  }
+}
 
 // y ← M⁻¹ y using the factors in shared memory (all lanes, each its own y)
 template <int NQ> __device__ __forceinline__ void m_solve(const double* Mf, const double* invd, double (&y)[NQ]) {
@@ -67,34 +138,34 @@ template <int NQ> __device__ __forceinline__ void m_solve(const double* Mf, cons
 // vdot = M⁻¹(u − bias), dvdot = M⁻¹(δu − ∂ID(q, v, vdot)·(dq, dv)).
 template <int NQ>
 __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ>& sm, int lane, const double (&q)[NQ],
-                                         const double (&v)[NQ], const double (&u)[NQ], const double (&dq)[NQ],
-                                         const double (&dv)[NQ], int udir, double (&vdot)[NQ], double (&dvdot)[NQ]) {
-  // sin/cos of the joint angles: lane i evaluates joint i, everybody receives all of them
+                                            const double (&v)[NQ], const double (&u)[NQ], const double (&dq)[NQ],
+                                            const double (&dv)[NQ], int udir, double (&vdot)[NQ], double (&dvdot)[NQ]) {
+  // sin/cos of the joint angles: lane i evaluates joint i
   double qi = q[0];
 #pragma unroll
   for (int i = 1; i < NQ; ++i) qi = (lane == i) ? q[i] : qi;
   double si, ci;
   sincos_bf(qi, &si, &ci);
-  double s[NQ], c[NQ];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) { s[i] = __shfl_sync(kFull, si, i); c[i] = __shfl_sync(kFull, ci, i); }
+  __syncwarp();   // the previous users of the scratch are done
+  if (lane < NQ) { sm.sc[2 * lane] = si; sm.sc[2 * lane + 1] = ci; }
   // lane j < NQ: column j of M = ID(q, 0, e_j) without gravity; the other lanes: bias = ID(q, v, 0)
-  {
-    const bool col = lane < NQ;
-    double qd_in[NQ], qdd_in[NQ], tau[NQ];
+  const bool col = lane < NQ;
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) { qd_in[i] = col ? 0.0 : v[i]; qdd_in[i] = (lane == i) ? 1.0 : 0.0; }
-    chain_rnea<double, NQ>(cp, s, c, qd_in, qdd_in, col ? 0.0 : 1.0, tau);
-    __syncwarp();
-    if (col) {
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) sm.Mf[i + NQ * lane] = tau[i];
-    } else if (lane == NQ) {
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) sm.bias[i] = tau[i];
-    }
-    __syncwarp();
+  for (int i = 0; i < NQ; ++i) {
+    sm.tng[(2 * i) * 32 + lane] = col ? 0.0 : v[i];
+    sm.tng[(2 * i + 1) * 32 + lane] = (lane == i) ? 1.0 : 0.0;
+    sm.qv[NQ + i] = v[i];   // every lane holds the same stage point
   }
+  __syncwarp();
+  warp_rnea<double, PrimalIO<NQ>, NQ>(cp, PrimalIO<NQ>{sm, lane}, col ? 0.0 : 1.0);
+  if (col) {
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) sm.Mf[i + NQ * lane] = sm.tau[i * 32 + lane];
+  } else if (lane == NQ) {
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) sm.bias[i] = sm.tau[i * 32 + lane];
+  }
+  __syncwarp();
   // factor M (symmetric positive definite ⇒ no pivoting): lane r eliminates row r
 #pragma unroll
   for (int k = 0; k < NQ - 1; ++k) {
@@ -112,17 +183,16 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ>& sm, i
   for (int i = 0; i < NQ; ++i) vdot[i] = u[i] - sm.bias[i];
   m_solve<NQ>(sm.Mf, sm.invd, vdot);
   // directional derivative of the inverse dynamics along this lane's tangent
-  {
-    Dual sD[NQ], cD[NQ], qdD[NQ], qddD[NQ], tauD[NQ];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      sD[i] = {s[i], c[i] * dq[i]}; cD[i] = {c[i], -s[i] * dq[i]};
-      qdD[i] = {v[i], dv[i]}; qddD[i] = {vdot[i], 0.0};
-    }
-    chain_rnea<Dual, NQ>(cp, sD, cD, qdD, qddD, 1.0, tauD);
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - tauD[i].t;
+  for (int i = 0; i < NQ; ++i) {
+    sm.tng[(2 * i) * 32 + lane] = dq[i];
+    sm.tng[(2 * i + 1) * 32 + lane] = dv[i];
+    sm.vd[i] = vdot[i];
   }
+  __syncwarp();
+  warp_rnea<Dual, DualIO<NQ>, NQ>(cp, DualIO<NQ>{sm, lane}, 1.0);
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - sm.tau[i * 32 + lane];
   m_solve<NQ>(sm.Mf, sm.invd, dvdot);
 }
 
@@ -157,11 +227,12 @@ __device__ __forceinline__ void chain_linearize(const ChainP& cp, BwdSmem<NQ>& s
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(kCW * 32)
+__global__ void __launch_bounds__(kCW * 32, ILQR_CHAIN_MIN_BLOCKS)
 bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, const __grid_constant__ CostP cost) {
   constexpr int n = 2 * NQ, m = NQ, NC = n + m + 1;   // NC column owners: x-directions, u-directions, affine
   static_assert(NC <= 32, "one warp must cover all column owners");
-  __shared__ BwdSmem<NQ> smem[kCW];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem<NQ>* smem = reinterpret_cast<BwdSmem<NQ>*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * kCW + warp;
   if (s >= st.nslots || !st.active[s]) return;   // warp-uniform
@@ -459,11 +530,18 @@ inline int grid_for(int n, int block) { return (n + block - 1) / block; }
     default: break;                                        \
   }
 
+void init_chain_attributes() {
+  cudaFuncSetAttribute(bwd_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<2>) * kCW));
+  cudaFuncSetAttribute(bwd_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<3>) * kCW));
+  cudaFuncSetAttribute(bwd_chain<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<6>) * kCW));
+  cudaFuncSetAttribute(bwd_chain<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<7>) * kCW));
+}
+
 bool chain_supported(int nq) { return nq == 2 || nq == 3 || nq == 6 || nq == 7; }
 
 void launch_bwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s) {
   if (st.nslots <= 0) return;
-  ILQR_CHAIN_DISPATCH(cp.nq, bwd_chain<NQ><<<grid_for(st.nslots, kCW), kCW * 32, 0, s>>>(st, cp, cost);)
+  ILQR_CHAIN_DISPATCH(cp.nq, bwd_chain<NQ><<<grid_for(st.nslots, kCW), kCW * 32, sizeof(BwdSmem<NQ>) * kCW, s>>>(st, cp, cost);)
 }
 void launch_fwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s) {
   if (st.nslots <= 0) return;
