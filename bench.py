@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--in-flight", type=int, default=None, help="batches in flight per GPU (pool handles)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the configs[3] (7-DoF chain) side measurement")
     return ap.parse_args()
 
 
@@ -123,6 +124,70 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# --------------------------------------------------------------------------- configs[3] side measurement
+def seven_dof_chain():
+    """7 revolute joints in the test/urdf/6Dof_arm.urdf pattern (axes z,y,z,y,z,y,z, origin
+    (1,0,0), mass 3, inertia 0.5·I, COM at the link frame, zero gravity).  Rows: include/ilqr_b200.h chain layout."""
+    rows = np.zeros((7, 20))
+    for i in range(7):
+        rows[i, 0:3] = (1.0, 0.0, 0.0)
+        rows[i, 6:9] = (0.0, 0.0, 1.0) if i % 2 == 0 else (0.0, 1.0, 0.0)
+        rows[i, 9] = 3.0
+        rows[i, 13:19] = (0.5, 0.0, 0.0, 0.5, 0.0, 0.5)
+    return rows
+
+
+def chain_config(batch, device=0):
+    import ilqr_b200
+    NQ, HC = 7, 100
+    rng = np.random.default_rng(0)
+    joints = seven_dof_chain()
+    target = np.concatenate([rng.uniform(-1, 1, NQ), np.zeros(NQ)])
+    w = np.concatenate([np.ones(NQ), np.zeros(NQ)])
+    prob = ilqr_b200.serial_chain_problem(joints, HC, batch, x_target=target, w_x=w, w_u=np.ones(NQ), w_xf=w, device=device)
+    x0 = np.zeros((2 * NQ, batch), order="F")
+    x0[:NQ, :] = rng.uniform(-1, 1, (NQ, batch))
+    return joints, target, w, prob, x0, np.zeros((HC, NQ, batch), order="F")
+
+
+def aux_chain(device, cpu_too):
+    """BASELINE configs[3] on one GPU: 7-DoF serial chain, n = 14, m = 7, H = 100, B = 262,144, fp64 —
+    one batched fit (tol 1e-6, max_iter 100) with the kernel times of its first (full-width) iteration."""
+    import ilqr_b200
+    from ilqr_b200 import _abi
+    Bc = 262144
+    joints, target, w, prob, x0, u = chain_config(Bc, device)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload_x0(x0, u)
+        t0 = time.perf_counter(); s.fit(MAX_ITER, TOL); dt = time.perf_counter() - t0
+        prof = s.profile()
+        it, st = s.download(_abi.ITERS), s.download(_abi.STATUS)
+    # FP64-pipe roofline of the dominant kernel: 18.3 k DFMA-class warp instructions per trajectory-step
+    # (profiles/ncu_full_r1_chain_B2368.txt: pipe-active share × cycles), one warp per trajectory ⇒ 32 lanes issue them
+    fp64_instr = 18300
+    tf = 2.0 * fp64_instr * 32 * 100 * Bc / (prof["first_bwd_ms"] * 1e-3) / 1e12
+    out = {"workload": "configs[3]: synthetic 7-DoF serial chain (n=14, m=7), B=262144, H=100, fp64, 1 GPU",
+           "value": Bc / dt, "unit": "solves/s", "fit_s": dt, "mean_iterations": float(it.mean()),
+           "converged_fraction": float(np.mean((st & 16) != 0)),
+           "bwd_chain_ms_full_batch": prof["first_bwd_ms"], "fwd_chain_ms_full_batch": prof["first_fwd_ms"],
+           "bwd_chain_issue_tflops_fp64": tf,
+           "note": "bwd_chain is FP64-pipe bound: 65 % pipe-active under ncu (profiles/ncu_full_r1_chain_B2368.txt); "
+                   "issue_tflops counts all 32 lanes of the warp-per-trajectory mapping (22 carry useful directions)"}
+    if cpu_too:
+        from oracle import oracle_py as orc
+        cores = os.cpu_count() or 1
+        nb = 2 * cores
+        spec = orc.chain_spec(joints, x_target=target, w_x=w, w_u=np.ones(7), w_xf=w)
+        xs = np.zeros((101, 14, nb), order="F"); us = np.zeros((100, 7, nb), order="F")
+        for b in range(nb):
+            xs[:, :, b] = orc.chain_rollout(spec, x0[:, b], us[:, :, b])
+        t0 = time.perf_counter()
+        orc.chain_fit_batch(spec, xs, us, max_iter=MAX_ITER, tol=TOL, nthreads=cores, traces=False)
+        out["cpu_baseline"] = {"value": nb / (time.perf_counter() - t0), "unit": "solves/s", "cores": cores, "kind": "port",
+                               "sample": "first %d trajectories of the batch" % nb}
+    return out
 
 
 # --------------------------------------------------------------------------- clocks
@@ -343,6 +408,14 @@ def run_b200(args):
         iters, cost = torch.cat(gi), torch.cat(gc)
     status = s.download(_abi.STATUS)
 
+    pool.close()
+    s.close()
+    other = None
+    if rank == 0 and world == 1 and not args.no_aux and B == B_PER_GPU:
+        try:
+            other = {"configs[3]": aux_chain(local, not args.no_cpu_baseline)}
+        except Exception as e:   # a side measurement must never take the headline line down
+            other = {"configs[3]": {"error": repr(e)}}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -363,10 +436,9 @@ def run_b200(args):
             "converged_fraction": float(((torch.from_numpy(status) & 16) != 0).double().mean().item()),
             "mean_final_cost": float(cost.mean().item()),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "other_configs": other,
         }
         print(json.dumps(line))
-    pool.close()
-    s.close()
     if world > 1:
         dist.destroy_process_group()
 
