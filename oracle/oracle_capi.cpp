@@ -205,77 +205,97 @@ int oracle_hardware_threads() { return (int)std::thread::hardware_concurrency();
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
-// Serial-chain rigid-body plugin (serial_chain.hpp): runtime nq dispatched to SerialChain<NQ>.
+// Rigid-body plugins (serial_chain.hpp): runtime (nq, floating) dispatched to SerialChain<NQ> /
+// FloatingChain<NQ>.
 // ---------------------------------------------------------------------------------------------
 #include "serial_chain.hpp"
 
 extern "C" {
 // POD mirror of the chain part of ilqr_problem (built by ctypes in oracle_py.py)
 struct oracle_chain_spec {
-  int32_t nq; int32_t pad;
+  int32_t nq; int32_t floating;       // floating: row nq of `joints` carries the base link's inertial
   double dt;
   double gravity[3];
-  double joints[8 * oracle::kChainStride];
+  double joints[9 * oracle::kChainStride];
   double x_target[16], w_x[16], w_u[8], w_xf[16];
 };
 }
 
 namespace {
-template <int NQ> SerialChain<NQ> make_chain(const oracle_chain_spec* s) {
-  SerialChain<NQ> p;
+template <int NQ> void fill(SerialChain<NQ>& p, const oracle_chain_spec* s) {
   for (int i = 0; i < NQ; ++i) p.joint[i].load(s->joints + i * kChainStride);
   for (int k = 0; k < 3; ++k) p.gravity[k] = s->gravity[k];
   p.dt = s->dt;
-  for (int i = 0; i < 2 * NQ; ++i) { p.x_target[i] = s->x_target[i]; p.w_x[i] = s->w_x[i]; p.w_xf[i] = s->w_xf[i]; }
-  for (int i = 0; i < NQ; ++i) p.w_u[i] = s->w_u[i];
+}
+template <class P> P make_plugin(const oracle_chain_spec* s) {
+  P p;
+  if constexpr (P::NX == 2 * P::NQ) {
+    fill(p, s);
+  } else {
+    fill(p.arm, s);
+    p.base.load(s->joints + P::NQ * kChainStride);
+    p.dt = s->dt;
+  }
+  for (int i = 0; i < P::NX; ++i) { p.x_target[i] = s->x_target[i]; p.w_x[i] = s->w_x[i]; p.w_xf[i] = s->w_xf[i]; }
+  for (int i = 0; i < P::NU; ++i) p.w_u[i] = s->w_u[i];
   return p;
 }
-#define CHAIN_DISPATCH(s, ...)                                                         \
-  switch ((s)->nq) {                                                                   \
-    case 2: { constexpr int NQ = 2; __VA_ARGS__ } break;                                      \
-    case 3: { constexpr int NQ = 3; __VA_ARGS__ } break;                                      \
-    case 6: { constexpr int NQ = 6; __VA_ARGS__ } break;                                      \
-    case 7: { constexpr int NQ = 7; __VA_ARGS__ } break;                                      \
-    default: return -1;                                                                \
+#define CHAIN_DISPATCH(s, ...)                                                              \
+  if ((s)->floating) {                                                                      \
+    switch ((s)->nq) {                                                                      \
+      case 1: { using P = FloatingChain<1>; __VA_ARGS__ } break;                           \
+      case 2: { using P = FloatingChain<2>; __VA_ARGS__ } break;                           \
+      default: return -1;                                                                   \
+    }                                                                                       \
+  } else {                                                                                  \
+    switch ((s)->nq) {                                                                      \
+      case 2: { using P = SerialChain<2>; __VA_ARGS__ } break;                             \
+      case 3: { using P = SerialChain<3>; __VA_ARGS__ } break;                             \
+      case 6: { using P = SerialChain<6>; __VA_ARGS__ } break;                             \
+      case 7: { using P = SerialChain<7>; __VA_ARGS__ } break;                             \
+      default: return -1;                                                                   \
+    }                                                                                       \
   }
 }  // namespace
 
 extern "C" {
 
-// M[nq×nq] column-major, bias[nq]
-int32_t oracle_chain_mass_bias(const oracle_chain_spec* s, const double* q, const double* qd, double* M, double* bias) {
+// fixed base: q[nq], vel[nq] → M[nq×nq], bias[nq];  floating: q = θ[nq], vel[6+nq] → M[(6+nq)²], bias[6+nq]
+int32_t oracle_chain_mass_bias(const oracle_chain_spec* s, const double* q, const double* vel, double* M, double* bias) {
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    Vec<double, NQ> qv, qdv;
-    for (int i = 0; i < NQ; ++i) { qv[i] = q[i]; qdv[i] = qd[i]; }
+    auto p = make_plugin<P>(s);
+    constexpr int NQ = P::NQ, NV = P::NU;
+    Vec<double, NQ> qv; Vec<double, NV> vv;
+    for (int i = 0; i < NQ; ++i) qv[i] = q[i];
+    for (int i = 0; i < NV; ++i) vv[i] = vel[i];
     auto Mm = p.template mass_matrix<double>(qv);
-    auto b = p.template dynamics_bias<double>(qv, qdv);
-    std::memcpy(M, Mm.a.data(), sizeof(double) * NQ * NQ);
-    std::memcpy(bias, b.a.data(), sizeof(double) * NQ);
+    auto b = p.template dynamics_bias<double>(qv, vv);
+    std::memcpy(M, Mm.a.data(), sizeof(double) * NV * NV);
+    std::memcpy(bias, b.a.data(), sizeof(double) * NV);
   })
   return 0;
 }
 
 int32_t oracle_chain_continuous_dynamics(const oracle_chain_spec* s, const double* x, const double* u, double* xdot) {
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    Vec<double, 2 * NQ> xv; Vec<double, NQ> uv;
-    for (int i = 0; i < 2 * NQ; ++i) xv[i] = x[i];
-    for (int i = 0; i < NQ; ++i) uv[i] = u[i];
+    auto p = make_plugin<P>(s);
+    Vec<double, P::NX> xv; Vec<double, P::NU> uv;
+    for (int i = 0; i < P::NX; ++i) xv[i] = x[i];
+    for (int i = 0; i < P::NU; ++i) uv[i] = u[i];
     auto y = p.template continuous_dynamics<double>(xv, uv);
-    std::memcpy(xdot, y.a.data(), sizeof(double) * 2 * NQ);
+    std::memcpy(xdot, y.a.data(), sizeof(double) * P::NX);
   })
   return 0;
 }
 
 int32_t oracle_chain_dynamics(const oracle_chain_spec* s, const double* x, const double* u, double* xn) {
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    Vec<double, 2 * NQ> xv; Vec<double, NQ> uv;
-    for (int i = 0; i < 2 * NQ; ++i) xv[i] = x[i];
-    for (int i = 0; i < NQ; ++i) uv[i] = u[i];
+    auto p = make_plugin<P>(s);
+    Vec<double, P::NX> xv; Vec<double, P::NU> uv;
+    for (int i = 0; i < P::NX; ++i) xv[i] = x[i];
+    for (int i = 0; i < P::NU; ++i) uv[i] = u[i];
     auto y = p.template dynamicsf<double>(xv, uv);
-    std::memcpy(xn, y.a.data(), sizeof(double) * 2 * NQ);
+    std::memcpy(xn, y.a.data(), sizeof(double) * P::NX);
   })
   return 0;
 }
@@ -283,16 +303,16 @@ int32_t oracle_chain_dynamics(const oracle_chain_spec* s, const double* x, const
 // A[n×n], B[n×m] column-major
 int32_t oracle_chain_linearize(const oracle_chain_spec* s, const double* x, const double* u, double* A, double* B) {
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    using SV = Solver<SerialChain<NQ>>;
+    auto p = make_plugin<P>(s);
+    using SV = Solver<P>;
     SV sv(p);
     typename SV::VX xv; typename SV::VU uv;
-    for (int i = 0; i < 2 * NQ; ++i) xv[i] = x[i];
-    for (int i = 0; i < NQ; ++i) uv[i] = u[i];
+    for (int i = 0; i < P::NX; ++i) xv[i] = x[i];
+    for (int i = 0; i < P::NU; ++i) uv[i] = u[i];
     typename SV::MXX Am; typename SV::MXU Bm;
     sv.linearize_dynamics(xv, uv, Am, Bm);
-    std::memcpy(A, Am.a.data(), sizeof(double) * 4 * NQ * NQ);
-    std::memcpy(B, Bm.a.data(), sizeof(double) * 2 * NQ * NQ);
+    std::memcpy(A, Am.a.data(), sizeof(double) * P::NX * P::NX);
+    std::memcpy(B, Bm.a.data(), sizeof(double) * P::NX * P::NU);
   })
   return 0;
 }
@@ -301,13 +321,13 @@ int32_t oracle_chain_linearize(const oracle_chain_spec* s, const double* x, cons
 int32_t oracle_chain_rollout(const oracle_chain_spec* s, int H, const double* x0, const double* u, double* x) {
   const int N = H + 1;
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    Vec<double, 2 * NQ> xv;
-    for (int c = 0; c < 2 * NQ; ++c) { xv[c] = x0[c]; x[0 + N * c] = x0[c]; }
+    auto p = make_plugin<P>(s);
+    Vec<double, P::NX> xv;
+    for (int c = 0; c < P::NX; ++c) { xv[c] = x0[c]; x[0 + N * c] = x0[c]; }
     for (int k = 0; k < H; ++k) {
-      Vec<double, NQ> uv; for (int i = 0; i < NQ; ++i) uv[i] = u[k + H * i];
+      Vec<double, P::NU> uv; for (int i = 0; i < P::NU; ++i) uv[i] = u[k + H * i];
       xv = p.template dynamicsf<double>(xv, uv);
-      for (int c = 0; c < 2 * NQ; ++c) x[(k + 1) + N * c] = xv[c];
+      for (int c = 0; c < P::NX; ++c) x[(k + 1) + N * c] = xv[c];
     }
   })
   return 0;
@@ -316,8 +336,8 @@ int32_t oracle_chain_rollout(const oracle_chain_spec* s, int H, const double* x0
 int32_t oracle_chain_backward_pass(const oracle_chain_spec* s, int H, const double* x, const double* u, double reg,
                                    double* duff, double* K) {
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    Solver<SerialChain<NQ>> sv(p); sv.reg = reg;
+    auto p = make_plugin<P>(s);
+    Solver<P> sv(p); sv.reg = reg;
     return sv.backward_pass(H, x, u, duff, K);
   })
   return 0;
@@ -326,8 +346,8 @@ int32_t oracle_chain_backward_pass(const oracle_chain_spec* s, int H, const doub
 int32_t oracle_chain_total_cost(const oracle_chain_spec* s, int H, const double* x, const double* u, const double* x_traj,
                                 double* cost) {
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    Solver<SerialChain<NQ>> sv(p);
+    auto p = make_plugin<P>(s);
+    Solver<P> sv(p);
     *cost = sv.total_cost(H, x, u, x_traj);
   })
   return 0;
@@ -337,8 +357,8 @@ int32_t oracle_chain_forward_pass(const oracle_chain_spec* s, int H, const doubl
                                   const double* duff, const double* K, double prev_cost, int jmax, double* xb, double* ub,
                                   double* new_cost, double* alpha) {
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    Solver<SerialChain<NQ>> sv(p); sv.jmax = jmax;
+    auto p = make_plugin<P>(s);
+    Solver<P> sv(p); sv.jmax = jmax;
     return sv.forward_pass(H, x, u, x_traj, duff, K, prev_cost, xb, ub, new_cost, alpha);
   })
   return 0;
@@ -350,11 +370,11 @@ int32_t oracle_chain_fit_batch(const oracle_chain_spec* s, int B, int H, double*
                                double* du2, int32_t* iters, int32_t* converged, int32_t* status) {
   const int N = H + 1;
   CHAIN_DISPATCH(s, {
-    auto p = make_chain<NQ>(s);
-    constexpr int n = 2 * NQ; constexpr int m = NQ;
+    auto p = make_plugin<P>(s);
+    constexpr int n = P::NX; constexpr int m = P::NU;
     std::atomic<int> next{0};
     auto work = [&]() {
-      Solver<SerialChain<NQ>> sv(p); sv.reg = reg; sv.jmax = jmax;
+      Solver<P> sv(p); sv.reg = reg; sv.jmax = jmax;
       for (;;) {
         int b = next.fetch_add(1);
         if (b >= B) break;

@@ -192,25 +192,40 @@ CHAIN_STRIDE = 20   # xyz(3) rpy(3) axis(3) mass(1) com(3) ixx ixy ixz iyy iyz i
 
 
 class ChainSpec(ctypes.Structure):
-    _fields_ = [("nq", ctypes.c_int32), ("pad", ctypes.c_int32), ("dt", ctypes.c_double),
-                ("gravity", ctypes.c_double * 3), ("joints", ctypes.c_double * (8 * CHAIN_STRIDE)),
+    _fields_ = [("nq", ctypes.c_int32), ("floating", ctypes.c_int32), ("dt", ctypes.c_double),
+                ("gravity", ctypes.c_double * 3), ("joints", ctypes.c_double * (9 * CHAIN_STRIDE)),
                 ("x_target", ctypes.c_double * 16), ("w_x", ctypes.c_double * 16), ("w_u", ctypes.c_double * 8),
                 ("w_xf", ctypes.c_double * 16)]
 
+    @property
+    def nv(self):      # velocity (= control) dimension
+        return self.nq + (6 if self.floating else 0)
 
-def chain_spec(joints, gravity=(0.0, 0.0, 0.0), dt=0.01, x_target=None, w_x=None, w_u=None, w_xf=None):
-    """joints: (nq, 20) array, one row per joint+child link (layout CHAIN_STRIDE above)."""
+    @property
+    def nx(self):
+        return 2 * self.nv
+
+
+def chain_spec(joints, gravity=(0.0, 0.0, 0.0), dt=0.01, x_target=None, w_x=None, w_u=None, w_xf=None, base=None):
+    """joints: (nq, 20) array, one row per joint+child link (layout CHAIN_STRIDE above).
+    base (optional, 20 doubles; only mass / com / inertia are used): makes the mechanism floating-base
+    (RBD_helper_functions.jl:7, floating = true): x = [p(3) MRP; r(3); θ; ω(3); v(3); θ̇]."""
     joints = np.asarray(joints, dtype=np.float64)
     nq = joints.shape[0]
-    assert joints.shape == (nq, CHAIN_STRIDE) and nq in (2, 3, 6, 7), joints.shape
+    assert joints.shape == (nq, CHAIN_STRIDE), joints.shape
     s = ChainSpec()
-    s.nq = nq; s.dt = dt
+    s.nq = nq; s.dt = dt; s.floating = 0 if base is None else 1
+    assert (nq in (1, 2)) if s.floating else (nq in (2, 3, 6, 7)), nq
     for k in range(3):
         s.gravity[k] = float(gravity[k])
+    if s.floating:
+        assert not any(gravity), "floating base: gravity must be zero (as in the reference)"
+        joints = np.concatenate([joints, np.asarray(base, dtype=np.float64).reshape(1, CHAIN_STRIDE)])
     flat = joints.reshape(-1)
     for i, v in enumerate(flat):
         s.joints[i] = float(v)
-    for name, arr, cnt in (("x_target", x_target, 2 * nq), ("w_x", w_x, 2 * nq), ("w_u", w_u, nq), ("w_xf", w_xf, 2 * nq)):
+    nv = s.nv
+    for name, arr, cnt in (("x_target", x_target, 2 * nv), ("w_x", w_x, 2 * nv), ("w_u", w_u, nv), ("w_xf", w_xf, 2 * nv)):
         if arr is not None:
             arr = np.asarray(arr, dtype=np.float64)
             assert arr.shape == (cnt,), (name, arr.shape)
@@ -225,58 +240,58 @@ def _chk(rc):
     return rc
 
 
-def chain_mass_bias(spec, q, qd):
-    nq = spec.nq
-    M = np.zeros((nq, nq), order="F"); b = np.zeros(nq)
-    _chk(lib().oracle_chain_mass_bias(ctypes.byref(spec), _p(_f(q, (nq,))), _p(_f(qd, (nq,))), _p(M), _p(b)))
+def chain_mass_bias(spec, q, vel):
+    nq, nv = spec.nq, spec.nv
+    M = np.zeros((nv, nv), order="F"); b = np.zeros(nv)
+    _chk(lib().oracle_chain_mass_bias(ctypes.byref(spec), _p(_f(q, (nq,))), _p(_f(vel, (nv,))), _p(M), _p(b)))
     return M, b
 
 
 def chain_continuous_dynamics(spec, x, u):
-    nq = spec.nq; y = np.zeros(2 * nq)
-    _chk(lib().oracle_chain_continuous_dynamics(ctypes.byref(spec), _p(_f(x, (2 * nq,))), _p(_f(u, (nq,))), _p(y)))
+    nx, nv = spec.nx, spec.nv; y = np.zeros(nx)
+    _chk(lib().oracle_chain_continuous_dynamics(ctypes.byref(spec), _p(_f(x, (nx,))), _p(_f(u, (nv,))), _p(y)))
     return y
 
 
 def chain_dynamics(spec, x, u):
-    nq = spec.nq; y = np.zeros(2 * nq)
-    _chk(lib().oracle_chain_dynamics(ctypes.byref(spec), _p(_f(x, (2 * nq,))), _p(_f(u, (nq,))), _p(y)))
+    nx, nv = spec.nx, spec.nv; y = np.zeros(nx)
+    _chk(lib().oracle_chain_dynamics(ctypes.byref(spec), _p(_f(x, (nx,))), _p(_f(u, (nv,))), _p(y)))
     return y
 
 
 def chain_linearize(spec, x, u):
-    nq = spec.nq
-    A = np.zeros((2 * nq, 2 * nq), order="F"); B = np.zeros((2 * nq, nq), order="F")
-    _chk(lib().oracle_chain_linearize(ctypes.byref(spec), _p(_f(x, (2 * nq,))), _p(_f(u, (nq,))), _p(A), _p(B)))
+    nx, nv = spec.nx, spec.nv
+    A = np.zeros((nx, nx), order="F"); B = np.zeros((nx, nv), order="F")
+    _chk(lib().oracle_chain_linearize(ctypes.byref(spec), _p(_f(x, (nx,))), _p(_f(u, (nv,))), _p(A), _p(B)))
     return A, B
 
 
 def chain_rollout(spec, x0, u):
-    nq = spec.nq; u = _f(u); H = u.shape[0]
-    x = np.zeros((H + 1, 2 * nq), order="F")
-    _chk(lib().oracle_chain_rollout(ctypes.byref(spec), H, _p(_f(x0, (2 * nq,))), _p(u), _p(x)))
+    nx, nv = spec.nx, spec.nv; u = _f(u); H = u.shape[0]
+    x = np.zeros((H + 1, nx), order="F")
+    _chk(lib().oracle_chain_rollout(ctypes.byref(spec), H, _p(_f(x0, (nx,))), _p(u), _p(x)))
     return x
 
 
 def chain_backward_pass(spec, x, u, reg=0.01):
-    nq = spec.nq; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 2 * nq))
-    d = np.zeros((H, nq), order="F"); K = np.zeros((H, nq, 2 * nq), order="F")
+    nx, nv = spec.nx, spec.nv; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, nx))
+    d = np.zeros((H, nv), order="F"); K = np.zeros((H, nv, nx), order="F")
     st = _chk(lib().oracle_chain_backward_pass(ctypes.byref(spec), H, _p(x), _p(u), ctypes.c_double(reg), _p(d), _p(K)))
     return d, K, st
 
 
 def chain_total_cost(spec, x, u, x_traj=None):
-    nq = spec.nq; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 2 * nq))
-    xt = None if x_traj is None else _f(x_traj, (H + 1, 2 * nq))
+    nx, nv = spec.nx, spec.nv; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, nx))
+    xt = None if x_traj is None else _f(x_traj, (H + 1, nx))
     c = ctypes.c_double()
     _chk(lib().oracle_chain_total_cost(ctypes.byref(spec), H, _p(x), _p(u), _p(xt), ctypes.byref(c)))
     return c.value
 
 
 def chain_forward_pass(spec, x, u, d, K, prev_cost, jmax=32, x_traj=None):
-    nq = spec.nq; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 2 * nq)); d = _f(d, (H, nq)); K = _f(K, (H, nq, 2 * nq))
-    xt = None if x_traj is None else _f(x_traj, (H + 1, 2 * nq))
-    xb = np.zeros((H + 1, 2 * nq), order="F"); ub = np.zeros((H, nq), order="F")
+    nx, nv = spec.nx, spec.nv; u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, nx)); d = _f(d, (H, nv)); K = _f(K, (H, nv, nx))
+    xt = None if x_traj is None else _f(x_traj, (H + 1, nx))
+    xb = np.zeros((H + 1, nx), order="F"); ub = np.zeros((H, nv), order="F")
     c = ctypes.c_double(); a = ctypes.c_double()
     st = _chk(lib().oracle_chain_forward_pass(ctypes.byref(spec), H, _p(x), _p(u), _p(xt), _p(d), _p(K),
                                               ctypes.c_double(prev_cost), jmax, _p(xb), _p(ub), ctypes.byref(c),
@@ -286,10 +301,10 @@ def chain_forward_pass(spec, x, u, d, K, prev_cost, jmax=32, x_traj=None):
 
 def chain_fit_batch(spec, x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, reg=0.01, jmax=32, nthreads=1, traces=True):
     """x_init (N,n,B), u_init (H,m,B) Fortran-ordered.  Returns dict like fit_batch."""
-    nq = spec.nq
+    nx = spec.nx
     u = _f(u_init).copy(order="F"); H, _, B = u.shape
-    x = _f(x_init, (H + 1, 2 * nq, B)).copy(order="F")
-    xt = None if x_traj is None else _f(x_traj, (H + 1, 2 * nq, B))
+    x = _f(x_init, (H + 1, nx, B)).copy(order="F")
+    xt = None if x_traj is None else _f(x_traj, (H + 1, nx, B))
     cost = alpha = du2 = None
     if traces:
         cost = np.full((max_iter, B), np.nan, order="F"); alpha = np.full((max_iter, B), np.nan, order="F")

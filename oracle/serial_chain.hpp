@@ -220,4 +220,131 @@ struct SerialChain {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Floating-base variant: the plugin exactly as the reference writes it
+//   test/RBD_2_link_example/RBD_helper_functions.jl:48-79, mechanism = parse_urdf(urdf, gravity = 0, floating = true)
+// State (:52-53)  x = [p(3) MRP; r(3); θ(NQ); ω(3); v(3); θ̇(NQ)],  control u ∈ R^{6+NQ} (wrench on the base
+// in base coordinates [torque; force], then joint torques).
+//   v̇ = M \ (−dynamics_bias + u)   with 𝑣 = [ω; v; θ̇]  (twist of the base in its own frame, then joint rates)
+//   q̇ = [pdot_from_w(p, ω); v; θ̇]   (:66 — the body-frame linear velocity is used as ṙ as is)
+// Third-party conventions restated (RigidBodyDynamics.jl / Attitude.jl, no version pinned, unverifiable here):
+// the base twist and the generalised base force are expressed in the base frame, angular part first;
+// pdot_from_w(p, ω) = ¼[(1 − pᵀp)I + 2[p]× + 2ppᵀ]ω (the standard MRP kinematics).  With zero gravity
+// (:7) neither M nor the bias depends on the base pose, so no quaternion convention enters.
+// ---------------------------------------------------------------------------------------------
+template <int NQv>
+struct FloatingChain {
+  static constexpr int NQ = NQv, NV = 6 + NQv, NX = 2 * NV, NU = NV;
+  SerialChain<NQv> arm;          // joints + child links (joint 0 hangs off the base link)
+  ChainJoint base;               // only mass / com / I are used
+  double dt = 0.01;
+  double x_target[NX] = {}, w_x[NX] = {}, w_u[NU] = {}, w_xf[NX] = {};
+
+  M6<double> base_inertia() const {
+    SerialChain<1> tmp; tmp.joint[0] = base;
+    return tmp.spatial_inertia(0);
+  }
+  template <class T> Vec<T, NV> dynamics_bias(const Vec<T, NQv>& q, const Vec<T, NV>& vel) const {
+    M6<T> X[NQv]; V6<T> v[NQv + 1], a[NQv + 1], f[NQv + 1];
+    for (int k = 0; k < 6; ++k) v[0][k] = vel[k];
+    a[0] = V6<T>::zeros();
+    {
+      M6<T> I0 = SerialChain<NQv>::template lift6<T>(base_inertia());
+      f[0] = I0 * a[0] + SerialChain<NQv>::template crf<T>(v[0], I0 * v[0]);
+    }
+    for (int i = 0; i < NQv; ++i) {
+      X[i] = arm.template joint_transform<T>(i, q[i]);
+      V6<T> S = arm.template motion_subspace<T>(i);
+      V6<T> vJ; for (int k = 0; k < 6; ++k) vJ[k] = S[k] * vel[6 + i];
+      v[i + 1] = X[i] * v[i] + vJ;
+      a[i + 1] = X[i] * a[i] + SerialChain<NQv>::template crm<T>(v[i + 1], vJ);
+      M6<T> I = SerialChain<NQv>::template lift6<T>(arm.spatial_inertia(i));
+      f[i + 1] = I * a[i + 1] + SerialChain<NQv>::template crf<T>(v[i + 1], I * v[i + 1]);
+    }
+    Vec<T, NV> tau;
+    for (int i = NQv - 1; i >= 0; --i) {
+      V6<T> S = arm.template motion_subspace<T>(i);
+      T acc = S[0] * f[i + 1][0];
+      for (int k = 1; k < 6; ++k) acc = acc + S[k] * f[i + 1][k];
+      tau[6 + i] = acc;
+      f[i] = f[i] + transpose(X[i]) * f[i + 1];
+    }
+    for (int k = 0; k < 6; ++k) tau[k] = f[0][k];
+    return tau;
+  }
+  template <class T> Mat<T, NV, NV> mass_matrix(const Vec<T, NQv>& q) const {
+    M6<T> X[NQv], Ic[NQv + 1];
+    Ic[0] = SerialChain<NQv>::template lift6<T>(base_inertia());
+    for (int i = 0; i < NQv; ++i) {
+      X[i] = arm.template joint_transform<T>(i, q[i]);
+      Ic[i + 1] = SerialChain<NQv>::template lift6<T>(arm.spatial_inertia(i));
+    }
+    for (int i = NQv - 1; i >= 0; --i) Ic[i] = Ic[i] + (transpose(X[i]) * Ic[i + 1]) * X[i];
+    Mat<T, NV, NV> M = Mat<T, NV, NV>::zeros();
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) M(a, b) = Ic[0](a, b);
+    for (int i = 0; i < NQv; ++i) {
+      V6<T> S = arm.template motion_subspace<T>(i);
+      V6<T> F = Ic[i + 1] * S;
+      T acc = S[0] * F[0];
+      for (int k = 1; k < 6; ++k) acc = acc + S[k] * F[k];
+      M(6 + i, 6 + i) = acc;
+      for (int j = i; j >= 0; --j) {
+        F = transpose(X[j]) * F;          // now in the frame of link j-1 (the base for j = 0)
+        if (j > 0) {
+          V6<T> Sj = arm.template motion_subspace<T>(j - 1);
+          T d = Sj[0] * F[0];
+          for (int k = 1; k < 6; ++k) d = d + Sj[k] * F[k];
+          M(6 + i, 6 + j - 1) = d; M(6 + j - 1, 6 + i) = d;
+        } else {
+          for (int k = 0; k < 6; ++k) { M(k, 6 + i) = F[k]; M(6 + i, k) = F[k]; }
+        }
+      }
+    }
+    return M;
+  }
+  // Attitude.jl pdot_from_w
+  template <class T> static void pdot_from_w(const T p[3], const T w[3], T out[3]) {
+    T pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    T pw = p[0] * w[0] + p[1] * w[1] + p[2] * w[2];
+    T cx[3] = {p[1] * w[2] - p[2] * w[1], p[2] * w[0] - p[0] * w[2], p[0] * w[1] - p[1] * w[0]};
+    for (int k = 0; k < 3; ++k) out[k] = 0.25 * ((1.0 - pp) * w[k] + 2.0 * cx[k] + (2.0 * pw) * p[k]);
+  }
+  // RBD_helper_functions.jl:50-71
+  template <class T> Vec<T, NX> continuous_dynamics(const Vec<T, NX>& x, const Vec<T, NU>& u) const {
+    T p[3] = {x[0], x[1], x[2]};
+    Vec<T, NQv> th; Vec<T, NV> vel;
+    for (int i = 0; i < NQv; ++i) th[i] = x[6 + i];
+    for (int i = 0; i < NV; ++i) vel[i] = x[NV + i];
+    Mat<T, NV, NV> M = mass_matrix<T>(th);
+    Vec<T, NV> rhs = u - dynamics_bias<T>(th, vel);
+    Vec<T, NV> vdot = lu_solve<T, NV, 1>(M, rhs);
+    T w[3] = {vel[0], vel[1], vel[2]}, pd[3];
+    pdot_from_w<T>(p, w, pd);
+    Vec<T, NX> xd;
+    for (int k = 0; k < 3; ++k) { xd[k] = pd[k]; xd[3 + k] = vel[3 + k]; }
+    for (int i = 0; i < NQv; ++i) xd[6 + i] = vel[6 + i];
+    for (int i = 0; i < NV; ++i) xd[NV + i] = vdot[i];
+    return xd;
+  }
+  template <class T> Vec<T, NX> dynamicsf(const Vec<T, NX>& x, const Vec<T, NU>& u) const {
+    Vec<T, NX> k1 = dt * continuous_dynamics<T>(x, u);
+    Vec<T, NX> k2 = dt * continuous_dynamics<T>(x + k1 / 2.0, u);
+    Vec<T, NX> k3 = dt * continuous_dynamics<T>(x + k2 / 2.0, u);
+    Vec<T, NX> k4 = dt * continuous_dynamics<T>(x + k3, u);
+    return x + (1.0 / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4);
+  }
+  // RBD_helper_functions.jl:85-116 with the scalar multipliers folded into the diagonal weights
+  template <class T> T immediate_cost(const Vec<T, NX>& x, const Vec<T, NU>& u) const {
+    T acc = T(0.0);
+    for (int i = 0; i < NX; ++i) { T e = x_target[i] - x[i]; acc = acc + w_x[i] * (e * e); }
+    for (int i = 0; i < NU; ++i) acc = acc + w_u[i] * (u[i] * u[i]);
+    return acc;
+  }
+  template <class T> T final_cost(const Vec<T, NX>& x) const {
+    T acc = T(0.0);
+    for (int i = 0; i < NX; ++i) { T e = x_target[i] - x[i]; acc = acc + w_xf[i] * (e * e); }
+    return acc;
+  }
+};
+
 }  // namespace oracle

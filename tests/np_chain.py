@@ -13,11 +13,13 @@ import numpy as np
 STRIDE = 20
 
 
-def joint_row(xyz=(0, 0, 0), rpy=(0, 0, 0), axis=(0, 0, 1), mass=1.0, com=(0, 0, 0), inertia=(1, 0, 0, 1, 0, 1)):
-    """One row of the flat chain description: joint origin/axis + child link inertial."""
+def joint_row(xyz=(0, 0, 0), rpy=(0, 0, 0), axis=(0, 0, 1), mass=1.0, com=(0, 0, 0), inertia=(1, 0, 0, 1, 0, 1), prismatic=False):
+    """One row of the flat chain description: joint origin/axis + child link inertial.  The last slot (a pad in
+    the product ABI) marks a prismatic joint — used only by this file, to model a floating base as a virtual
+    chain of three prismatic and three revolute joints."""
     axis = np.asarray(axis, dtype=np.float64)
     axis = axis / np.linalg.norm(axis)
-    return np.concatenate([xyz, rpy, axis, [mass], com, inertia, [0.0]]).astype(np.float64)
+    return np.concatenate([xyz, rpy, axis, [mass], com, inertia, [1.0 if prismatic else 0.0]]).astype(np.float64)
 
 
 def seven_dof_chain():
@@ -72,8 +74,12 @@ def _kinematics(joints, q):
     Rs, os_, zs = [], [], []
     for i in range(nq):
         xyz, rpy, axis = joints[i, 0:3], joints[i, 3:6], joints[i, 6:9]
-        o = o + R @ xyz
-        R = R @ _rot_rpy(rpy) @ _rot_axis(axis, q[i])
+        if joints[i, 19] == 1.0:      # prismatic: slide along the axis of the (fixed-rotation) joint frame
+            R = R @ _rot_rpy(rpy)
+            o = o + R @ (np.linalg.solve(_rot_rpy(rpy), xyz) + axis * q[i])
+        else:
+            o = o + R @ xyz
+            R = R @ _rot_rpy(rpy) @ _rot_axis(axis, q[i])
         Rs.append(R); os_.append(o); zs.append(R @ axis)
     return Rs, os_, zs
 
@@ -89,7 +95,10 @@ def mass_matrix(joints, q):
         pc = os_[i] + Rs[i] @ com
         Jv = np.zeros((3, nq), dtype=q.dtype); Jw = np.zeros((3, nq), dtype=q.dtype)
         for j in range(i + 1):
-            Jv[:, j] = np.cross(zs[j], pc - os_[j]); Jw[:, j] = zs[j]
+            if joints[j, 19] == 1.0:
+                Jv[:, j] = zs[j]
+            else:
+                Jv[:, j] = np.cross(zs[j], pc - os_[j]); Jw[:, j] = zs[j]
         M = M + m * (Jv.T @ Jv) + Jw.T @ (Rs[i] @ Ic @ Rs[i].T) @ Jw
     return M
 
@@ -134,3 +143,50 @@ def dynamics(joints, x, u, gravity=(0, 0, 0), dt=0.01):
     f = lambda xx: continuous_dynamics(joints, xx, u, gravity)
     k1 = dt * f(x); k2 = dt * f(x + k1 / 2); k3 = dt * f(x + k2 / 2); k4 = dt * f(x + k3)
     return x + (1.0 / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+
+
+# ---------------------------------------------------------------------------------------------
+# Floating base as a virtual chain: three prismatic joints (world x, y, z) then three revolute joints
+# (x, y, z; R = Rx·Ry·Rz), the last one carrying the base link; the arm follows.  At zero base angles the
+# body twist equals the virtual joint rates, so the body-frame equations the reference integrates
+# (RBD_helper_functions.jl:57-66: v̇ = M \ (u − bias) with 𝑣 = [ω; v; θ̇] in the base frame) follow from the
+# Lagrangian equations of the virtual chain by  v̇_body = tw(q, q̈) + ∂tw/∂q·q̇  (tw = body twist as a function of
+# the virtual coordinates and rates).  Zero gravity ⇒ the body-frame dynamics do not depend on the base pose,
+# so checking at zero base angles loses no generality.
+# ---------------------------------------------------------------------------------------------
+def virtual_floating_chain(base_row, joints):
+    rows = []
+    for k in range(3):
+        rows.append(joint_row(axis=np.eye(3)[k], mass=0.0, inertia=(0,) * 6, prismatic=True))
+    for k in range(2):
+        rows.append(joint_row(axis=np.eye(3)[k], mass=0.0, inertia=(0,) * 6))
+    last = np.array(base_row, dtype=np.float64).copy()
+    last[0:9] = joint_row(axis=(0, 0, 1))[0:9]; last[19] = 0.0
+    rows.append(last)
+    return np.concatenate([np.stack(rows), np.asarray(joints, dtype=np.float64)])
+
+
+def _body_twist(qv, rates):
+    """[ω_body; v_body] of the base from the six virtual coordinates' values (only the angles matter) and rates."""
+    a = qv[3:6]
+    Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
+    Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+    Rz = np.array([[np.cos(a[2]), -np.sin(a[2]), 0], [np.sin(a[2]), np.cos(a[2]), 0], [0, 0, 1]])
+    R = Rx @ Ry @ Rz
+    w_world = np.array([1, 0, 0]) * rates[3] + Rx @ np.array([0, 1, 0]) * rates[4] + Rx @ Ry @ np.array([0, 0, 1]) * rates[5]
+    return np.concatenate([R.T @ w_world, R.T @ rates[0:3]])
+
+
+def floating_body_acceleration(base_row, joints, theta, vel, u):
+    """v̇ = [ω̇; v̇; θ̈] (coordinate derivatives of the body-frame velocity vector) for 𝑣 = vel, generalised force u."""
+    nq = len(theta)
+    chain = virtual_floating_chain(base_row, joints)
+    q = np.concatenate([np.zeros(6), theta])
+    qd = np.concatenate([vel[3:6], vel[0:3], vel[6:]])        # zero base angles: ṙ = v_body, angle rates = ω_body
+    tau = np.concatenate([u[3:6], u[0:3], u[6:]])
+    M = mass_matrix(chain, q)
+    qdd = np.linalg.solve(M, tau - bias(chain, q, qd))
+    h = 1e-30
+    dtw = np.imag(_body_twist(q[:6].astype(np.complex128) + 1j * h * qd[:6], qd[:6])) / h      # ∂tw/∂q · q̇
+    acc6 = _body_twist(q[:6], qdd[:6]) + dtw
+    return np.concatenate([acc6, qdd[6:]]), M

@@ -117,3 +117,84 @@ def test_urdf_loader_matches_committed_fixtures():
     if os.path.isdir(ref):
         assert np.array_equal(ilqr_b200.load_urdf(os.path.join(ref, "6Dof_arm.urdf"))[0], j6)
         assert np.array_equal(ilqr_b200.load_urdf(os.path.join(ref, "2Dof_arm.urdf"))[0], j2)
+
+
+def _random_base(rng):
+    A = rng.normal(size=(3, 3)); I = A @ A.T + np.eye(3)
+    return np_chain.joint_row(mass=rng.uniform(5, 30), com=rng.uniform(-0.3, 0.3, 3),
+                              inertia=(I[0, 0], I[0, 1], I[0, 2], I[1, 1], I[1, 2], I[2, 2]))
+
+
+@pytest.mark.parametrize("nq", [1, 2])
+def test_floating_base_matches_virtual_chain_lagrangian(nq):
+    """Floating-base M and v̇ (body-frame twist coordinates, RBD_helper_functions.jl:57-66) against the Lagrangian
+    equations of a virtual 3-prismatic + 3-revolute chain carrying the base link."""
+    rng = np.random.default_rng(40 + nq)
+    joints = np_chain.random_chain(nq, rng, True)
+    base = _random_base(rng)
+    spec = orc.chain_spec(joints, base=base)
+    for _ in range(3):
+        theta = rng.uniform(-2, 2, nq); vel = rng.uniform(-1.5, 1.5, 6 + nq); u = rng.uniform(-5, 5, 6 + nq)
+        p = rng.uniform(-0.4, 0.4, 3); r = rng.uniform(-1, 1, 3)
+        x = np.concatenate([p, r, theta, vel])
+        xd = orc.chain_continuous_dynamics(spec, x, u)
+        acc0, Mv = np_chain.floating_body_acceleration(base, joints, theta, vel, u)
+        nv = 6 + nq
+        assert np.max(np.abs(xd[nv:] - acc0)) <= 1e-10 * max(1.0, np.max(np.abs(acc0)))
+        M, _ = orc.chain_mass_bias(spec, theta, vel)
+        perm = np.concatenate([[3, 4, 5, 0, 1, 2], np.arange(6, nv)])      # body order [ω; v] ↔ virtual order [r; angles]
+        assert np.max(np.abs(M - Mv[np.ix_(perm, perm)])) <= 1e-11 * np.max(np.abs(M))
+        # kinematics (:66): ṙ = v as is, θ̇, and the MRP rate ¼[(1−p²)I + 2[p]× + 2ppᵀ]ω
+        w = vel[:3]
+        pd = 0.25 * ((1 - p @ p) * w + 2 * np.cross(p, w) + 2 * (p @ w) * p)
+        assert np.allclose(xd[:3], pd, rtol=0, atol=1e-15) and np.array_equal(xd[3:6], vel[3:6])
+        assert np.array_equal(xd[6:nv], vel[6:])
+
+
+def test_floating_base_mrp_rate_is_the_rotation_kinematics():
+    """pdot_from_w must be the MRP kinematics of a body-frame ω: the rotation built from p(t+h) equals
+    R(p)·exp([ω]× h) to O(h²) (pins the sign conventions of the formula restated from Attitude.jl)."""
+    def R_of_p(p):
+        q0 = (1 - p @ p) / (1 + p @ p); qv = 2 * p / (1 + p @ p)
+        K = np.array([[0, -qv[2], qv[1]], [qv[2], 0, -qv[0]], [-qv[1], qv[0], 0]])
+        return np.eye(3) + 2 * q0 * K + 2 * K @ K
+    rng = np.random.default_rng(2)
+    spec = orc.chain_spec(np_chain.random_chain(1, rng, False), base=_random_base(rng))
+    p = rng.uniform(-0.5, 0.5, 3); w = rng.uniform(-1, 1, 3); h = 1e-6
+    x = np.concatenate([p, np.zeros(3), [0.3], w, np.zeros(3), [0.0]])
+    pd = orc.chain_continuous_dynamics(spec, x, np.zeros(7))[:3]
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    lhs = (R_of_p(p + h * pd) - R_of_p(p - h * pd)) / (2 * h)
+    assert np.max(np.abs(lhs - R_of_p(p) @ W)) <= 1e-8
+
+
+def test_floating_base_linearisation_and_fit():
+    rng = np.random.default_rng(8)
+    joints = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "2dof_chain.npy"))
+    base = np_chain.joint_row(mass=30.0, inertia=(50, 0, 0, 50, 0, 50))          # test/urdf/2Dof_arm.urdf base_link
+    # the reference's weights (RBD_helper_functions.jl:85-116) and target pose (animate_RBD_2_link.jl:10)
+    target = np.concatenate([[0, 0, 0, 5, 1, 2, 1, .3], np.zeros(8)])
+    w_x = np.concatenate([10.0 * np.array([100, 100, 100, 1, 1, 1, 10, 10.]), np.zeros(8)])
+    w_u = np.array([1, 1, 1, 100, 100, 100, 10, 10.])
+    w_xf = np.concatenate([1e5 * np.array([100, 100, 100, 1000, 1000, 1000, 10, 10.]), np.zeros(8)])
+    spec = orc.chain_spec(joints, base=base, x_target=target, w_x=w_x, w_u=w_u, w_xf=w_xf)
+    x = np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 2), rng.uniform(-1, 1, 8)])
+    u = rng.uniform(-2, 2, 8)
+    A, B = orc.chain_linearize(spec, x, u)
+    hh = 1e-6
+    for j in range(16):
+        e = np.zeros(16); e[j] = hh
+        fd = (orc.chain_dynamics(spec, x + e, u) - orc.chain_dynamics(spec, x - e, u)) / (2 * hh)
+        assert np.max(np.abs(A[:, j] - fd)) <= 1e-8
+    for j in range(8):
+        e = np.zeros(8); e[j] = hh
+        fd = (orc.chain_dynamics(spec, x, u + e) - orc.chain_dynamics(spec, x, u - e)) / (2 * hh)
+        assert np.max(np.abs(B[:, j] - fd)) <= 1e-8
+    # the reference's own start (RBD_helper_functions.jl:9: q = [0,0,0,1 | .5,.75,1 | 0,0] ⇒ MRP (0,0,1)), short horizon
+    H = 30
+    x0 = np.concatenate([[0, 0, 1.0], [.5, .75, 1.0], [0, 0], np.zeros(8)])
+    uu = np.zeros((H, 8, 1), order="F"); xx = np.zeros((H + 1, 16, 1), order="F")
+    xx[:, :, 0] = orc.chain_rollout(spec, x0, uu[:, :, 0])
+    out = orc.chain_fit_batch(spec, xx, uu, max_iter=15, tol=1e-6)
+    c = out["cost"][: out["iters"][0], 0]
+    assert out["status"][0] == 0 and np.all(np.diff(c) < 0), (out["status"], c)
