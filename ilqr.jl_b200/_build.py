@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libilqr_b200.so")
-SOURCES = ["capi.cu", "kernels_lpt.cu", "kernels_chain.cu", "layout.cu", "pool.cu"]
+SOURCES = ["capi.cu", "kernels_lpt.cu", "kernels_chain.cu", "kernels_chain_fl.cu", "layout.cu", "pool.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",

@@ -24,7 +24,7 @@ struct ilqr_handle {
   DevState st{};
   TwoLinkP mp{};
   ChainP chain{};
-  bool is_chain = false;
+  bool is_chain = false, floating = false;
   CostP cp{};
   // TF (boundary-layout) staging on device
   double* stage_x = nullptr;   // [B][n*N]
@@ -208,16 +208,33 @@ int32_t ilqr_problem_serial_chain(ilqr_problem* p, int32_t nq, const double* joi
   return ILQR_OK;
 }
 
+int32_t ilqr_problem_floating_chain(ilqr_problem* p, int32_t nq, const double* joints, const double* base_link, int32_t H,
+                                    int32_t B) {
+  if (!base_link || nq < 1 || nq + 1 > ILQR_MAX_JOINTS + 1) return ILQR_ERR_INVALID;
+  if (int32_t rc = ilqr_problem_serial_chain(p, nq, joints, nullptr, H, B)) return rc;
+  p->model_id = ILQR_MODEL_FLOATING_CHAIN;
+  p->n = 2 * (6 + nq); p->m = 6 + nq;
+  std::memcpy(p->chain + nq * ILQR_CHAIN_STRIDE, base_link, sizeof(double) * ILQR_CHAIN_STRIDE);
+  return ILQR_OK;
+}
+
 const char* ilqr_last_error(const ilqr_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   if (!p || !out) return fail(nullptr, ILQR_ERR_INVALID, "null argument");
   *out = nullptr;
   if (p->abi_version != ILQR_ABI_VERSION) return fail(nullptr, ILQR_ERR_INVALID, "abi_version mismatch");
-  const bool is_chain = p->model_id == ILQR_MODEL_SERIAL_CHAIN;
+  const bool floating = p->model_id == ILQR_MODEL_FLOATING_CHAIN;
+  const bool is_chain = p->model_id == ILQR_MODEL_SERIAL_CHAIN || floating;
   if (is_chain) {
-    if (!chain_supported(p->nq) || p->n != 2 * p->nq || p->m != p->nq)
-      return fail(nullptr, ILQR_ERR_INVALID, "ILQR_MODEL_SERIAL_CHAIN needs nq in {2,3,6,7}, n = 2 nq, m = nq");
+    const int nv = p->nq + (floating ? 6 : 0);
+    if (!chain_supported(p->nq, floating) || p->n != 2 * nv || p->m != nv)
+      return fail(nullptr, ILQR_ERR_INVALID, "serial chain: nq in {2,3,6,7} (fixed base) or {1,2} (floating base), n = 2 nv, m = nv");
+    if (floating) {
+      if (p->gravity[0] != 0.0 || p->gravity[1] != 0.0 || p->gravity[2] != 0.0)
+        return fail(nullptr, ILQR_ERR_INVALID, "floating base: gravity must be zero (RBD_helper_functions.jl:7)");
+      if (!(p->chain[p->nq * ILQR_CHAIN_STRIDE + 9] > 0.0)) return fail(nullptr, ILQR_ERR_INVALID, "base link mass must be > 0");
+    }
     for (int i = 0; i < p->nq; ++i) {
       const double* a = p->chain + i * ILQR_CHAIN_STRIDE + 6;
       if (std::fabs(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] - 1.0) > 1e-12)
@@ -238,7 +255,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
 
   ilqr_handle* h = new (std::nothrow) ilqr_handle();
   if (!h) return fail(nullptr, ILQR_ERR_INVALID, "out of host memory");
-  h->prob = *p; h->device = p->device; h->is_chain = is_chain;
+  h->prob = *p; h->device = p->device; h->is_chain = is_chain; h->floating = floating;
 #define CKC(call)                                                                               \
   do {                                                                                          \
     cudaError_t e__ = (call);                                                                   \
@@ -298,6 +315,12 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
     ChainP& c = h->chain;
     c.nq = p->nq; c.dt = p->dt;
     for (int k = 0; k < 3; ++k) c.g[k] = p->gravity[k];
+    if (floating) {   // root link inertial (row nq), in the base frame, which is left as it is
+      const double* r = p->chain + p->nq * ILQR_CHAIN_STRIDE;
+      c.base_mass = r[9];
+      for (int k = 0; k < 3; ++k) c.base_com[k] = r[10 + k];
+      for (int k = 0; k < 6; ++k) c.base_I[k] = r[13 + k];
+    }
     // Canonical link frames: L'_i = L_i·C_i with C_i ẑ = axis_i, so every joint turns about its own +z
     // (chain.cuh).  x_{L'_{i-1}} = C_{i-1}ᵀ xyz_i + (C_{i-1}ᵀ R0_i C_i)·Rot(z, q_i)·x_{L'_i}.
     double Cprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // row-major; the base frame is left alone
@@ -411,7 +434,7 @@ int32_t ilqr_upload_x0(ilqr_handle* h, const double* x0, const double* u_init, c
   launch_reset_state(h->st, h->stream);
   launch_tf_to_bf(h->stage_x, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
   launch_tf_to_bf(h->stage_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream);
-  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->st.x[1], h->stream);
+  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
   else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
   h->launches += 4;
   if (int32_t rc = check_launch(h, "upload_x0 kernels")) return rc;
@@ -447,7 +470,7 @@ static int32_t mpc_reinit(ilqr_handle* h, int shift) {
   launch_reset_state(h->st, h->stream);
   launch_tf_to_bf(h->plant, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
   launch_tf_to_bf(h->st.out_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream, shift);
-  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->st.x[1], h->stream);
+  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
   else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
   h->launches += 4;
   if (int32_t rc = check_launch(h, "mpc re-initialisation kernels")) return rc;
@@ -480,7 +503,7 @@ int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_ap
   const ilqr_problem& p = h->prob;
   CK(h, cudaSetDevice(h->device));
   if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;        // solution → out_x / out_u (by trajectory)
-  if (h->is_chain) launch_mpc_advance_chain(h->chain, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
+  if (h->is_chain) launch_mpc_advance_chain(h->chain, h->floating, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
   else launch_mpc_advance_two_link(h->mp, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
   h->launches += 1;
   if (u_applied) CK(h, cudaMemcpyAsync(u_applied, h->u_applied, sizeof(double) * p.m * p.B, cudaMemcpyDeviceToHost, h->stream));
@@ -496,7 +519,7 @@ static int32_t backward_async(ilqr_handle* h) {
   if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][0], h->stream);
-  if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->cp, h->stream);
+  if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
   else if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->st.nslots <= h->coop_below, h->stream);
   else launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][1], h->stream);
@@ -510,7 +533,7 @@ static int32_t forward_async(ilqr_handle* h) {
   const bool fsplit = !h->is_chain && h->st.nslots > h->fwd_split_above;
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][2], h->stream);
-  if (h->is_chain) launch_fwd_chain(h->st, h->chain, h->cp, h->stream);
+  if (h->is_chain) launch_fwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
   else if (fsplit) launch_fwd_split_two_link(h->st, h->mp, h->cp, h->stream);
   else launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][3], h->stream);

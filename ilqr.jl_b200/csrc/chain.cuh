@@ -34,8 +34,19 @@ struct ChainP {
   double mass[kMaxQ];
   double com[kMaxQ][3];       // in the canonical link frame
   double I[kMaxQ][6];         // ixx ixy ixz iyy iyz izz about the COM, canonical link axes
-  double g[3];                // gravity acceleration in the base frame
+  double g[3];                // gravity acceleration in the base frame (fixed base only)
   double dt;
+  // floating base (RBD_helper_functions.jl:7, floating = true): inertial of the root link, in its own frame
+  double base_mass, base_com[3], base_I[6];
+};
+
+// Dimensions of a mechanism: NQ revolute joints, optionally hanging off a free-floating base link.
+//   fixed base:    x = [q; q̇],                                  NV = NQ
+//   floating base: x = [p(3) MRP; r(3); θ; ω(3); v(3); θ̇],      NV = 6 + NQ   (RBD_helper_functions.jl:52-53)
+// n = 2·NV states, m = NV controls ([torque; force] on the base in base coordinates, then joint torques).
+template <int NQ, bool FL> struct ChainDims {
+  static constexpr int JO = FL ? 6 : 0;     // index of the first joint in the velocity vector
+  static constexpr int NV = NQ + JO, n = 2 * NV, m = NV;
 };
 
 // ---- value + one tangent ---------------------------------------------------------------------
@@ -50,6 +61,7 @@ __device__ __forceinline__ Dual operator*(double s, Dual a) { return {s * a.v, s
 __device__ __forceinline__ Dual operator*(Dual a, double s) { return {s * a.v, s * a.t}; }
 __device__ __forceinline__ Dual operator+(Dual a, double s) { return {a.v + s, a.t}; }
 __device__ __forceinline__ Dual operator-(double s, Dual a) { return {s - a.v, -a.t}; }
+__device__ __forceinline__ Dual operator+(double s, Dual a) { return {s + a.v, a.t}; }
 
 template <class T> __device__ __forceinline__ T mk(double x);
 template <> __device__ __forceinline__ double mk<double>(double x) { return x; }
@@ -85,111 +97,175 @@ template <class T> __device__ __forceinline__ V3<T> to_parent(const ChainP& cp, 
   return mat_c<T>(cp.Rf[i], t, false);
 }
 
-// Inverse dynamics τ = ID(q, q̇, q̈) with gravity scaled by gscale (0 or 1); s, c = sin q, cos q.
-template <class T, int NQ>
-__device__ __forceinline__ void chain_rnea(const ChainP& cp, const T (&s)[NQ], const T (&c)[NQ], const T (&qd)[NQ],
-                                           const T (&qdd)[NQ], double gscale, T (&tau)[NQ]) {
-  V3<T> f[NQ], n[NQ];
-  V3<T> w = {mk<T>(0.0), mk<T>(0.0), mk<T>(0.0)}, al = w;
-  V3<T> acc = {mk<T>(-cp.g[0] * gscale), mk<T>(-cp.g[1] * gscale), mk<T>(-cp.g[2] * gscale)};
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    // acceleration of the link-i origin, still in parent coordinates
-    const V3<T> t = acc + cross_c<T>(al, cp.xyz[i]) + cross<T>(w, cross_c<T>(w, cp.xyz[i]));
-    const V3<T> wc = to_child<T>(cp, i, s[i], c[i], w);
-    const V3<T> alc = to_child<T>(cp, i, s[i], c[i], al);
-    acc = to_child<T>(cp, i, s[i], c[i], t);
-    // joint axis = +z of the link frame: ω = ω_c + q̇ ẑ,  α = α_c + q̈ ẑ + ω × q̇ ẑ
-    w = {wc.x, wc.y, wc.z + qd[i]};
-    al = {alc.x + w.y * qd[i], alc.y - w.x * qd[i], alc.z + qdd[i]};
-    const V3<T> ac = acc + cross_c<T>(al, cp.com[i]) + cross<T>(w, cross_c<T>(w, cp.com[i]));
-    f[i] = {cp.mass[i] * ac.x, cp.mass[i] * ac.y, cp.mass[i] * ac.z};
-    const double* I = cp.I[i];
-    const V3<T> Iw = {I[0] * w.x + I[1] * w.y + I[2] * w.z, I[1] * w.x + I[3] * w.y + I[4] * w.z,
-                      I[2] * w.x + I[4] * w.y + I[5] * w.z};
-    const V3<T> Ia = {I[0] * al.x + I[1] * al.y + I[2] * al.z, I[1] * al.x + I[3] * al.y + I[4] * al.z,
-                      I[2] * al.x + I[4] * al.y + I[5] * al.z};
-    n[i] = Ia + cross<T>(w, Iw) + c_cross<T>(cp.com[i], f[i]);   // moment about the link origin
+template <class T> __device__ __forceinline__ V3<T> sym_mul(const double I[6], V3<T> w) {
+  return {I[0] * w.x + I[1] * w.y + I[2] * w.z, I[1] * w.x + I[3] * w.y + I[4] * w.z, I[2] * w.x + I[4] * w.y + I[5] * w.z};
+}
+
+// Newton–Euler forward step for joint i: parent-frame (ω, α, a) → link-i frame, then the link's wrench (f, n about
+// the link origin).  qd, qdd: the joint's rate and acceleration.
+template <class T>
+__device__ __forceinline__ void rnea_link(const ChainP& cp, int i, T s, T c, T qd, T qdd, V3<T>& w, V3<T>& al, V3<T>& acc,
+                                          V3<T>& f, V3<T>& n) {
+  // acceleration of the link-i origin, still in parent coordinates
+  const V3<T> t = acc + cross_c<T>(al, cp.xyz[i]) + cross<T>(w, cross_c<T>(w, cp.xyz[i]));
+  const V3<T> wc = to_child<T>(cp, i, s, c, w);
+  const V3<T> alc = to_child<T>(cp, i, s, c, al);
+  acc = to_child<T>(cp, i, s, c, t);
+  // joint axis = +z of the link frame: ω = ω_c + q̇ ẑ,  α = α_c + q̈ ẑ + ω × q̇ ẑ
+  w = {wc.x, wc.y, wc.z + qd};
+  al = {alc.x + w.y * qd, alc.y - w.x * qd, alc.z + qdd};
+  const V3<T> ac = acc + cross_c<T>(al, cp.com[i]) + cross<T>(w, cross_c<T>(w, cp.com[i]));
+  f = {cp.mass[i] * ac.x, cp.mass[i] * ac.y, cp.mass[i] * ac.z};
+  n = sym_mul<T>(cp.I[i], al) + cross<T>(w, sym_mul<T>(cp.I[i], w)) + c_cross<T>(cp.com[i], f);
+}
+// State of the root of the recursion and (floating base) the base link's own wrench.
+//   fixed base:    ω = α = 0, a = −g·gscale
+//   floating base: ω, ω̇ from the base twist and its rate; a = v̇ + ω × v (classical acceleration of the base origin;
+//                  the twist [ω; v] is expressed in the base frame), zero gravity
+template <class T, bool FL>
+__device__ __forceinline__ void rnea_root(const ChainP& cp, const T (&bv)[6], const T (&ba)[6], double gscale, V3<T>& w,
+                                          V3<T>& al, V3<T>& acc, V3<T>& fb, V3<T>& nb) {
+  if constexpr (FL) {
+    w = {bv[0], bv[1], bv[2]}; al = {ba[0], ba[1], ba[2]};
+    const V3<T> v = {bv[3], bv[4], bv[5]};
+    const V3<T> vd = {ba[3], ba[4], ba[5]};
+    acc = vd + cross<T>(w, v);
+    const V3<T> ac = acc + cross_c<T>(al, cp.base_com) + cross<T>(w, cross_c<T>(w, cp.base_com));
+    fb = {cp.base_mass * ac.x, cp.base_mass * ac.y, cp.base_mass * ac.z};
+    nb = sym_mul<T>(cp.base_I, al) + cross<T>(w, sym_mul<T>(cp.base_I, w)) + c_cross<T>(cp.base_com, fb);
+  } else {
+    w = {mk<T>(0.0), mk<T>(0.0), mk<T>(0.0)}; al = w; fb = w; nb = w;
+    acc = {mk<T>(-cp.g[0] * gscale), mk<T>(-cp.g[1] * gscale), mk<T>(-cp.g[2] * gscale)};
   }
+}
+
+// Inverse dynamics τ = ID(θ, 𝑣, 𝑣̇) (thread-local, unrolled): vel / acc are the NV-vectors [base twist (6);] joint
+// rates and their coordinate derivatives; s, c = sin θ, cos θ; gravity scaled by gscale (0 or 1).
+template <class T, int NQ, bool FL>
+__device__ __forceinline__ void chain_rnea(const ChainP& cp, const T (&s)[NQ], const T (&c)[NQ],
+                                           const T (&vel)[ChainDims<NQ, FL>::NV], const T (&accel)[ChainDims<NQ, FL>::NV],
+                                           double gscale, T (&tau)[ChainDims<NQ, FL>::NV]) {
+  constexpr int JO = ChainDims<NQ, FL>::JO;
+  V3<T> f[NQ], n[NQ], w, al, acc, fb, nb;
+  {
+    T bv[6], ba[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { bv[k] = FL ? vel[k] : mk<T>(0.0); ba[k] = FL ? accel[k] : mk<T>(0.0); }
+    rnea_root<T, FL>(cp, bv, ba, gscale, w, al, acc, fb, nb);
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) rnea_link<T>(cp, i, s[i], c[i], vel[JO + i], accel[JO + i], w, al, acc, f[i], n[i]);
   V3<T> F = {mk<T>(0.0), mk<T>(0.0), mk<T>(0.0)}, N = F;
 #pragma unroll
   for (int i = NQ - 1; i >= 0; --i) {
     const V3<T> Fi = f[i] + F, Ni = n[i] + N;
-    tau[i] = Ni.z;
-    if (i > 0) {
+    tau[JO + i] = Ni.z;
+    if (FL || i > 0) {
       F = to_parent<T>(cp, i, s[i], c[i], Fi);
       N = to_parent<T>(cp, i, s[i], c[i], Ni) + c_cross<T>(cp.xyz[i], F);
     }
   }
+  if constexpr (FL) {
+    const V3<T> Nt = nb + N, Ft = fb + F;
+    tau[0] = Nt.x; tau[1] = Nt.y; tau[2] = Nt.z; tau[3] = Ft.x; tau[4] = Ft.y; tau[5] = Ft.z;
+  }
+}
+
+// MRP kinematics ṗ = ¼[(1 − pᵀp)I + 2[p]× + 2ppᵀ]ω   (Attitude.jl pdot_from_w, RBD_helper_functions.jl:66)
+template <class T> __device__ __forceinline__ void mrp_rate(const T (&p)[3], const T (&w)[3], T (&pd)[3]) {
+  const T pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+  const T pw = p[0] * w[0] + p[1] * w[1] + p[2] * w[2];
+  const T omp = 1.0 - pp;
+  const T cx[3] = {p[1] * w[2] - p[2] * w[1], p[2] * w[0] - p[0] * w[2], p[0] * w[1] - p[1] * w[0]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pd[k] = 0.25 * (omp * w[k] + 2.0 * cx[k] + (2.0 * pw) * p[k]);
 }
 
 // ---- thread-local forward dynamics (rollouts: one thread per trajectory) -----------------------
-template <int NQ>
-__device__ __forceinline__ void chain_forward_dynamics(const ChainP& cp, const double (&q)[NQ], const double (&v)[NQ],
-                                                    const double (&u)[NQ], double (&vdot)[NQ]) {
-  double s[NQ], c[NQ], zero[NQ];
+// 𝑣̇ = M(θ)⁻¹ (u − bias(θ, 𝑣))
+template <int NQ, bool FL>
+__device__ __forceinline__ void chain_forward_dynamics(const ChainP& cp, const double (&th)[NQ],
+                                                       const double (&v)[ChainDims<NQ, FL>::NV],
+                                                       const double (&u)[ChainDims<NQ, FL>::NV],
+                                                       double (&vdot)[ChainDims<NQ, FL>::NV]) {
+  constexpr int NV = ChainDims<NQ, FL>::NV;
+  double s[NQ], c[NQ], zero[NV];
 #pragma unroll
-  for (int i = 0; i < NQ; ++i) { sincos_bf(q[i], &s[i], &c[i]); zero[i] = 0.0; }
-  double M[NQ][NQ], rhs[NQ];
+  for (int i = 0; i < NQ; ++i) sincos_bf(th[i], &s[i], &c[i]);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) zero[i] = 0.0;
+  double M[NV][NV], rhs[NV];
   {
-    double bias[NQ];
-    chain_rnea<double, NQ>(cp, s, c, v, zero, 1.0, bias);
+    double bias[NV];
+    chain_rnea<double, NQ, FL>(cp, s, c, v, zero, 1.0, bias);
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) rhs[i] = u[i] - bias[i];
+    for (int i = 0; i < NV; ++i) rhs[i] = u[i] - bias[i];
   }
 #pragma unroll 1
-  for (int j = 0; j < NQ; ++j) {   // column j of M = ID(q, 0, e_j) without gravity
-    double e[NQ], col[NQ];
+  for (int j = 0; j < NV; ++j) {   // column j of M = ID(θ, 0, e_j) without gravity
+    double e[NV], col[NV];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) e[i] = (i == j) ? 1.0 : 0.0;
-    chain_rnea<double, NQ>(cp, s, c, zero, e, 0.0, col);
+    for (int i = 0; i < NV; ++i) e[i] = (i == j) ? 1.0 : 0.0;
+    chain_rnea<double, NQ, FL>(cp, s, c, zero, e, 0.0, col);
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) M[i][j] = col[i];
+    for (int i = 0; i < NV; ++i) M[i][j] = col[i];
   }
   // M is symmetric positive definite: Gaussian elimination without pivoting
 #pragma unroll
-  for (int k = 0; k < NQ; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const double r = rcp_nr(M[k][k]);
 #pragma unroll
-    for (int i = k + 1; i < NQ; ++i) {
+    for (int i = k + 1; i < NV; ++i) {
       const double l = M[i][k] * r;
 #pragma unroll
-      for (int j = k + 1; j < NQ; ++j) M[i][j] = fma(-l, M[k][j], M[i][j]);
+      for (int j = k + 1; j < NV; ++j) M[i][j] = fma(-l, M[k][j], M[i][j]);
       rhs[i] = fma(-l, rhs[k], rhs[i]);
     }
     M[k][k] = r;
   }
 #pragma unroll
-  for (int i = NQ - 1; i >= 0; --i) {
+  for (int i = NV - 1; i >= 0; --i) {
     double a = rhs[i];
 #pragma unroll
-    for (int j = i + 1; j < NQ; ++j) a = fma(-M[i][j], vdot[j], a);
+    for (int j = i + 1; j < NV; ++j) a = fma(-M[i][j], vdot[j], a);
     vdot[i] = a * M[i][i];
   }
 }
 
-// x⁺ = RK4(x, u)   (RBD_helper_functions.jl:72-79), x = [q; q̇]
-template <int NQ>
-__device__ __forceinline__ void chain_step(const ChainP& cp, const double (&x)[2 * NQ], const double (&u)[NQ],
-                                           double (&xn)[2 * NQ]) {
-  double sum[2 * NQ], kprev[2 * NQ];
+// x⁺ = RK4(x, u)   (RBD_helper_functions.jl:72-79)
+template <int NQ, bool FL>
+__device__ __forceinline__ void chain_step(const ChainP& cp, const double (&x)[ChainDims<NQ, FL>::n],
+                                           const double (&u)[ChainDims<NQ, FL>::m], double (&xn)[ChainDims<NQ, FL>::n]) {
+  constexpr int NV = ChainDims<NQ, FL>::NV, JO = ChainDims<NQ, FL>::JO, n = 2 * NV;
+  double sum[n], kprev[n];
 #pragma unroll
-  for (int i = 0; i < 2 * NQ; ++i) { sum[i] = 0.0; kprev[i] = 0.0; }
+  for (int i = 0; i < n; ++i) { sum[i] = 0.0; kprev[i] = 0.0; }
 #pragma unroll 1
   for (int stg = 0; stg < 4; ++stg) {
     const double cin = (stg == 0) ? 0.0 : (stg == 3 ? 1.0 : 0.5), wgt = (stg == 1 || stg == 2) ? 2.0 : 1.0;
-    double q[NQ], v[NQ], vdot[NQ];
+    double cfg[NV], v[NV], th[NQ], vdot[NV], cdot[NV];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) { q[i] = fma(cin, kprev[i], x[i]); v[i] = fma(cin, kprev[NQ + i], x[NQ + i]); }
-    chain_forward_dynamics<NQ>(cp, q, v, u, vdot);
+    for (int i = 0; i < NV; ++i) { cfg[i] = fma(cin, kprev[i], x[i]); v[i] = fma(cin, kprev[NV + i], x[NV + i]); }
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      kprev[i] = cp.dt * v[i]; kprev[NQ + i] = cp.dt * vdot[i];
-      sum[i] = fma(wgt, kprev[i], sum[i]); sum[NQ + i] = fma(wgt, kprev[NQ + i], sum[NQ + i]);
+    for (int i = 0; i < NQ; ++i) th[i] = cfg[JO + i];
+    chain_forward_dynamics<NQ, FL>(cp, th, v, u, vdot);
+    // kinematics: q̇ = 𝑣, except the MRP rate of the floating base (RBD_helper_functions.jl:66)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cdot[i] = v[i];
+    if constexpr (FL) {
+      const double p[3] = {cfg[0], cfg[1], cfg[2]}, w[3] = {v[0], v[1], v[2]};
+      double pd[3];
+      mrp_rate<double>(p, w, pd);
+      cdot[0] = pd[0]; cdot[1] = pd[1]; cdot[2] = pd[2];
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      kprev[i] = cp.dt * cdot[i]; kprev[NV + i] = cp.dt * vdot[i];
+      sum[i] = fma(wgt, kprev[i], sum[i]); sum[NV + i] = fma(wgt, kprev[NV + i], sum[NV + i]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 2 * NQ; ++i) xn[i] = fma(1.0 / 6.0, sum[i], x[i]);
+  for (int i = 0; i < n; ++i) xn[i] = fma(1.0 / 6.0, sum[i], x[i]);
 }
 
 }  // namespace ilqr

@@ -83,14 +83,16 @@ void launch_compact(const DevState& st, int new_nslots, cudaStream_t s);
 void launch_flush_live(const DevState& st, bool with_iterates, cudaStream_t s);
 void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaStream_t s);
 
-// kernels_chain.cu — serial-chain rigid-body models (warp-per-trajectory backward pass, n = 2·nq, m = nq)
-bool chain_supported(int nq);
+// kernels_chain.cu / kernels_chain_fl.cu — serial-chain rigid-body models (warp-per-trajectory backward pass);
+// n = 2·NV, m = NV, NV = nq (+ 6 with a floating base)
+bool chain_supported(int nq, bool floating);
 void init_chain_attributes();    // opt-in dynamic shared memory; call once per process/device
-void launch_bwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s);
-void launch_fwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s);
-void launch_rollout_init_chain(const DevState& st, const ChainP& cp, const double* d_x0 /*[slot][n]*/, cudaStream_t s);
-void launch_mpc_advance_chain(const ChainP& cp, const double* out_u, double* plant, double* u_applied, int B, int H,
-                              cudaStream_t s);
+void launch_bwd_chain(const DevState& st, const ChainP& cp, bool floating, const CostP& cost, cudaStream_t s);
+void launch_fwd_chain(const DevState& st, const ChainP& cp, bool floating, const CostP& cost, cudaStream_t s);
+void launch_rollout_init_chain(const DevState& st, const ChainP& cp, bool floating, const double* d_x0 /*[slot][n]*/,
+                               cudaStream_t s);
+void launch_mpc_advance_chain(const ChainP& cp, bool floating, const double* out_u, double* plant, double* u_applied, int B,
+                              int H, cudaStream_t s);
 
 // layout.cu — boundary (Julia, time-fastest "TF") <-> BF transposes
 // TF: src[t*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + s]

@@ -1,525 +1,16 @@
-// kernels_chain.cu — generic (n = 2·nq, m = nq) kernels for serial-chain rigid-body models.
-//
-// Mapping.  The state no longer fits one thread (n = 14: S alone is 196 doubles), so the backward
-// pass runs ONE WARP PER TRAJECTORY:
-//   * linearisation: lane d carries tangent direction d of (x, u) — 2nq + nq ≤ 24 of the 32 lanes —
-//     through the four RK4 stages as a dual number (chain.cuh), so after the last stage lane d holds
-//     column d of [A | B] in registers.  The primal parts that every direction shares are built
-//     cooperatively per stage: lane j < nq computes column j of M(q) (one inverse-dynamics call with
-//     q̈ = e_j), lane nq the bias, the warp factors M in shared memory, every lane back-substitutes
-//     its own right-hand side;
-//   * Riccati step (src/backward_pass.jl:177-186, 207-218, 262-273): lane d owns column d of every
-//     n-column block (S·[A|B], [G|H|g], K|δu, the new S and s); the blocks other lanes need are
-//     published in shared memory (S, [A|B], [G|H|g], [K|δu] — ≈ 7 KB per warp at nq = 7) and read
-//     back as broadcast columns.  The m×m solve is an LU with partial pivoting on the column-owner
-//     layout (pivot column broadcast by shuffles, U published in shared memory).
-// The forward pass has no cross-trajectory coupling and 1/60 of the arithmetic, so it stays one
-// thread per trajectory (primal dynamics only), reading the [k][slot][component] layout directly.
-//
-// Reference functions restated: backward_pass (src/backward_pass.jl:324-357) → bwd_chain;
-// forward_pass + total_cost (src/forward_pass.jl:55-93, 182-196) → fwd_chain; the rigid-body plugin
-// (test/RBD_2_link_example/RBD_helper_functions.jl:48-116) → chain.cuh + CostP.
-#include "chain.cuh"
-#include "internal.cuh"
+// kernels_chain.cu — fixed-base instantiations of chain_kernels.cuh (nq = 2, 3, 6, 7) and the launchers that
+// dispatch on (floating, nq).  Floating-base instantiations live in kernels_chain_fl.cu (separate TU: build time).
+#include "chain_kernels.cuh"
 
 namespace ilqr {
+using namespace chain_detail;
 
-namespace {
-
-constexpr int kCW = 4;   // warps (= trajectories) per block in bwd_chain
-#ifndef ILQR_CHAIN_MIN_BLOCKS
-#define ILQR_CHAIN_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for
-#endif
-constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2;
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
-
-template <int NQ> struct BwdSmem {
-  static constexpr int n = 2 * NQ, m = NQ;
-  double S[n * n];              // value Hessian, column-major
-  double AB[n * (n + m)];       // [A | B], column-major
-  double GH[m * (n + m + 1)];   // [G | H | g], unregularised
-  double Kd[m * (n + 1)];       // [K | δu]
-  double U[m * m];              // upper factor of H_reg (row-permuted)
-  double sv[n];
-  double Mf[NQ * NQ];           // M(q) then its LU factors (unit lower below, upper on/above the diagonal)
-  double bias[NQ];
-  double invd[NQ];              // 1 / diagonal of the upper factor
-  // inverse-dynamics scratch.  The link loops are rolled (the unrolled version was 8.4 k instructions and
-  // instruction-fetch bound), so per-link state is indexed dynamically and lives here, [item][lane]:
-  double fn[NQ * 6 * 32];       // per lane: f_i, n_i (primal pass) or their tangents (dual pass)
-  double fnv[NQ * 6];           // dual pass: the values of f_i, n_i (the same on every lane)
-  double tng[2 * NQ * 32];      // per lane, per joint: (q̇, q̈) in the primal pass, (δq, δq̇) in the dual pass
-  double tau[NQ * 32];          // per lane: joint torques (primal pass) or their tangents (dual pass)
-  double qv[2 * NQ];            // stage point (q, q̇)
-  double sc[2 * NQ];            // sin q_i, cos q_i
-  double vd[NQ];                // v̇ at the stage point
-};
-
-// Per-pass views of the scratch: what joint i feeds the recursion and where link i's wrench is parked.
-template <int NQ> struct PrimalIO {
-  BwdSmem<NQ>& sm; int lane;
-  __device__ __forceinline__ double s(int i) const { return sm.sc[2 * i]; }
-  __device__ __forceinline__ double c(int i) const { return sm.sc[2 * i + 1]; }
-  __device__ __forceinline__ double qd(int i) const { return sm.tng[(2 * i) * 32 + lane]; }
-  __device__ __forceinline__ double qdd(int i) const { return sm.tng[(2 * i + 1) * 32 + lane]; }
-  __device__ __forceinline__ void put(int i, int k, double v) const { sm.fn[(i * 6 + k) * 32 + lane] = v; }
-  __device__ __forceinline__ double get(int i, int k) const { return sm.fn[(i * 6 + k) * 32 + lane]; }
-  __device__ __forceinline__ void out(int i, double v) const { sm.tau[i * 32 + lane] = v; }
-};
-template <int NQ> struct DualIO {
-  BwdSmem<NQ>& sm; int lane;
-  __device__ __forceinline__ Dual s(int i) const { return {sm.sc[2 * i], sm.sc[2 * i + 1] * sm.tng[(2 * i) * 32 + lane]}; }
-  __device__ __forceinline__ Dual c(int i) const { return {sm.sc[2 * i + 1], -sm.sc[2 * i] * sm.tng[(2 * i) * 32 + lane]}; }
-  __device__ __forceinline__ Dual qd(int i) const { return {sm.qv[NQ + i], sm.tng[(2 * i + 1) * 32 + lane]}; }
-  __device__ __forceinline__ Dual qdd(int i) const { return {sm.vd[i], 0.0}; }
-  __device__ __forceinline__ void put(int i, int k, Dual v) const { sm.fnv[i * 6 + k] = v.v; sm.fn[(i * 6 + k) * 32 + lane] = v.t; }
-  __device__ __forceinline__ Dual get(int i, int k) const { return {sm.fnv[i * 6 + k], sm.fn[(i * 6 + k) * 32 + lane]}; }
-  __device__ __forceinline__ void out(int i, Dual v) const { sm.tau[i * 32 + lane] = v.t; }
-};
-
-// chain_rnea (chain.cuh) with rolled link loops over shared-memory state; same arithmetic.
-template <class T, class IO, int NQ>
-__device__ __forceinline__ void warp_rnea(const ChainP& cp, const IO io, double gscale) {
-  V3<T> w = {mk<T>(0.0), mk<T>(0.0), mk<T>(0.0)}, al = w;
-  V3<T> acc = {mk<T>(-cp.g[0] * gscale), mk<T>(-cp.g[1] * gscale), mk<T>(-cp.g[2] * gscale)};
-#pragma unroll 1
-  for (int i = 0; i < NQ; ++i) {
-    const T s = io.s(i), c = io.c(i), qd = io.qd(i), qdd = io.qdd(i);
-    const V3<T> t = acc + cross_c<T>(al, cp.xyz[i]) + cross<T>(w, cross_c<T>(w, cp.xyz[i]));
-    const V3<T> wc = to_child<T>(cp, i, s, c, w);
-    const V3<T> alc = to_child<T>(cp, i, s, c, al);
-    acc = to_child<T>(cp, i, s, c, t);
-    w = {wc.x, wc.y, wc.z + qd};
-    al = {alc.x + w.y * qd, alc.y - w.x * qd, alc.z + qdd};
-    const V3<T> ac = acc + cross_c<T>(al, cp.com[i]) + cross<T>(w, cross_c<T>(w, cp.com[i]));
-    const V3<T> f = {cp.mass[i] * ac.x, cp.mass[i] * ac.y, cp.mass[i] * ac.z};
-    const double* I = cp.I[i];
-    const V3<T> Iw = {I[0] * w.x + I[1] * w.y + I[2] * w.z, I[1] * w.x + I[3] * w.y + I[4] * w.z,
-                      I[2] * w.x + I[4] * w.y + I[5] * w.z};
-    const V3<T> Ia = {I[0] * al.x + I[1] * al.y + I[2] * al.z, I[1] * al.x + I[3] * al.y + I[4] * al.z,
-                      I[2] * al.x + I[4] * al.y + I[5] * al.z};
-    const V3<T> n = Ia + cross<T>(w, Iw) + c_cross<T>(cp.com[i], f);
-    io.put(i, 0, f.x); io.put(i, 1, f.y); io.put(i, 2, f.z);
-    io.put(i, 3, n.x); io.put(i, 4, n.y); io.put(i, 5, n.z);
-  }
-  V3<T> F = {mk<T>(0.0), mk<T>(0.0), mk<T>(0.0)}, N = F;
-#pragma unroll 1
-  for (int i = NQ - 1; i >= 0; --i) {
-    const V3<T> f = {io.get(i, 0), io.get(i, 1), io.get(i, 2)}, n = {io.get(i, 3), io.get(i, 4), io.get(i, 5)};
-    const V3<T> Fi = f + F, Ni = n + N;
-    io.out(i, Ni.z);
-    const T s = io.s(i), c = io.c(i);
-    F = to_parent<T>(cp, i, s, c, Fi);
-    N = to_parent<T>(cp, i, s, c, Ni) + c_cross<T>(cp.xyz[i], F);
-  }
-}
-
-// y ← M⁻¹ y using the factors in shared memory (all lanes, each its own y)
-template <int NQ> __device__ __forceinline__ void m_solve(const double* Mf, const double* invd, double (&y)[NQ]) {
-#pragma unroll
-  for (int i = 1; i < NQ; ++i) {
-    double a = y[i];
-#pragma unroll
-    for (int j = 0; j < i; ++j) a = fma(-Mf[i + NQ * j], y[j], a);
-    y[i] = a;
-  }
-#pragma unroll
-  for (int i = NQ - 1; i >= 0; --i) {
-    double a = y[i];
-#pragma unroll
-    for (int j = i + 1; j < NQ; ++j) a = fma(-Mf[i + NQ * j], y[j], a);
-    y[i] = a * invd[i];
-  }
-}
-
-// One RK4 stage at the primal point (q, v) with this lane's tangent (dq, dv, δu = e_udir):
-// vdot = M⁻¹(u − bias), dvdot = M⁻¹(δu − ∂ID(q, v, vdot)·(dq, dv)).
-template <int NQ>
-__device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ>& sm, int lane, const double (&q)[NQ],
-                                            const double (&v)[NQ], const double (&u)[NQ], const double (&dq)[NQ],
-                                            const double (&dv)[NQ], int udir, double (&vdot)[NQ], double (&dvdot)[NQ]) {
-  // sin/cos of the joint angles: lane i evaluates joint i
-  double qi = q[0];
-#pragma unroll
-  for (int i = 1; i < NQ; ++i) qi = (lane == i) ? q[i] : qi;
-  double si, ci;
-  sincos_bf(qi, &si, &ci);
-  __syncwarp();   // the previous users of the scratch are done
-  if (lane < NQ) { sm.sc[2 * lane] = si; sm.sc[2 * lane + 1] = ci; }
-  // lane j < NQ: column j of M = ID(q, 0, e_j) without gravity; the other lanes: bias = ID(q, v, 0)
-  const bool col = lane < NQ;
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    sm.tng[(2 * i) * 32 + lane] = col ? 0.0 : v[i];
-    sm.tng[(2 * i + 1) * 32 + lane] = (lane == i) ? 1.0 : 0.0;
-    sm.qv[NQ + i] = v[i];   // every lane holds the same stage point
-  }
-  __syncwarp();
-  warp_rnea<double, PrimalIO<NQ>, NQ>(cp, PrimalIO<NQ>{sm, lane}, col ? 0.0 : 1.0);
-  if (col) {
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) sm.Mf[i + NQ * lane] = sm.tau[i * 32 + lane];
-  } else if (lane == NQ) {
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) sm.bias[i] = sm.tau[i * 32 + lane];
-  }
-  __syncwarp();
-  // factor M (symmetric positive definite ⇒ no pivoting): lane r eliminates row r
-#pragma unroll
-  for (int k = 0; k < NQ - 1; ++k) {
-    if (lane > k && lane < NQ) {
-      const double l = sm.Mf[lane + NQ * k] * rcp_nr(sm.Mf[k + NQ * k]);
-#pragma unroll
-      for (int j = k + 1; j < NQ; ++j) sm.Mf[lane + NQ * j] = fma(-l, sm.Mf[k + NQ * j], sm.Mf[lane + NQ * j]);
-      sm.Mf[lane + NQ * k] = l;
-    }
-    __syncwarp();
-  }
-  if (lane < NQ) sm.invd[lane] = rcp_nr(sm.Mf[lane + NQ * lane]);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) vdot[i] = u[i] - sm.bias[i];
-  m_solve<NQ>(sm.Mf, sm.invd, vdot);
-  // directional derivative of the inverse dynamics along this lane's tangent
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    sm.tng[(2 * i) * 32 + lane] = dq[i];
-    sm.tng[(2 * i + 1) * 32 + lane] = dv[i];
-    sm.vd[i] = vdot[i];
-  }
-  __syncwarp();
-  warp_rnea<Dual, DualIO<NQ>, NQ>(cp, DualIO<NQ>{sm, lane}, 1.0);
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - sm.tau[i * 32 + lane];
-  m_solve<NQ>(sm.Mf, sm.invd, dvdot);
-}
-
-// Column `lane` of [A | B] of the discrete RK4 map at (x, u)   (linearize_dynamics, src/backward_pass.jl:25-40)
-template <int NQ>
-__device__ __forceinline__ void chain_linearize(const ChainP& cp, BwdSmem<NQ>& sm, int lane, const double (&x)[2 * NQ],
-                                                const double (&u)[NQ], double (&ab)[2 * NQ]) {
-  constexpr int n = 2 * NQ;
-  const int udir = lane - n;   // ≥ 0 on the lanes that carry a control direction
-  double xi0[n], sum[n], kp[n], tp[n], tsum[n];
-#pragma unroll
-  for (int i = 0; i < n; ++i) { xi0[i] = (lane == i) ? 1.0 : 0.0; sum[i] = 0.0; kp[i] = 0.0; tp[i] = 0.0; tsum[i] = 0.0; }
-#pragma unroll 1
-  for (int stg = 0; stg < 4; ++stg) {
-    const double cin = (stg == 0) ? 0.0 : (stg == 3 ? 1.0 : 0.5), wgt = (stg == 1 || stg == 2) ? 2.0 : 1.0;
-    double q[NQ], v[NQ], dq[NQ], dv[NQ], vdot[NQ], dvdot[NQ];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      q[i] = fma(cin, kp[i], x[i]); v[i] = fma(cin, kp[NQ + i], x[NQ + i]);
-      dq[i] = fma(cin, tp[i], xi0[i]); dv[i] = fma(cin, tp[NQ + i], xi0[NQ + i]);
-    }
-    chain_stage<NQ>(cp, sm, lane, q, v, u, dq, dv, udir, vdot, dvdot);
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      kp[i] = cp.dt * v[i]; kp[NQ + i] = cp.dt * vdot[i];
-      tp[i] = cp.dt * dv[i]; tp[NQ + i] = cp.dt * dvdot[i];
-      tsum[i] = fma(wgt, tp[i], tsum[i]); tsum[NQ + i] = fma(wgt, tp[NQ + i], tsum[NQ + i]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < n; ++i) ab[i] = fma(1.0 / 6.0, tsum[i], xi0[i]);
-}
-
-template <int NQ>
-__global__ void __launch_bounds__(kCW * 32, ILQR_CHAIN_MIN_BLOCKS)
-bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, const __grid_constant__ CostP cost) {
-  constexpr int n = 2 * NQ, m = NQ, NC = n + m + 1;   // NC column owners: x-directions, u-directions, affine
-  static_assert(NC <= 32, "one warp must cover all column owners");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  BwdSmem<NQ>* smem = reinterpret_cast<BwdSmem<NQ>*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * kCW + warp;
-  if (s >= st.nslots || !st.active[s]) return;   // warp-uniform
-  BwdSmem<NQ>& sm = smem[warp];
-  const int64_t S = st.S;
-  const int H = st.H;
-  const int cur = st.cur[s];
-  const double* __restrict__ X = st.x[cur];
-  const double* __restrict__ U = st.u[cur];
-  const bool isX = lane < n, isU = lane >= n && lane < n + m, isAff = lane == n + m;
-  const int ucol = lane - n;
-
-  // terminal expansion: final_cost_quadratization (src/backward_pass.jl:134-153)
-  if (isX) {
-    const double xN = X[((int64_t)H * S + s) * n + lane];
-#pragma unroll
-    for (int i = 0; i < n; ++i) sm.S[i + n * lane] = (i == lane) ? 2.0 * cost.w_xf[lane] : 0.0;
-    sm.sv[lane] = -2.0 * cost.w_xf[lane] * (cost.x_target[lane] - xN);
-  }
-  __syncwarp();
-
-  bool bad = false;
-#pragma unroll 1
-  for (int k = H - 1; k >= 0; --k) {
-    double x[n], u[m];
-    {
-      const double* xp = X + ((int64_t)k * S + s) * n;
-      const double* up = U + ((int64_t)k * S + s) * m;
-#pragma unroll
-      for (int i = 0; i < n; ++i) x[i] = xp[i];
-#pragma unroll
-      for (int i = 0; i < m; ++i) u[i] = up[i];
-    }
-    double ab[n];
-    chain_linearize<NQ>(cp, sm, lane, x, u, ab);
-    if (lane >= n + m) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) ab[i] = 0.0;
-    }
-
-    // ---- optimal_controller_param (src/backward_pass.jl:177-186) in column-owner form
-    if (lane < n + m) {
-#pragma unroll
-      for (int r = 0; r < n; ++r) sm.AB[r + n * lane] = ab[r];
-    }
-    __syncwarp();
-    double w[n];   // S·(own column of [A|B]); the affine lane carries s itself
-#pragma unroll
-    for (int i = 0; i < n; ++i) w[i] = isAff ? sm.sv[i] : 0.0;
-#pragma unroll
-    for (int r = 0; r < n; ++r) {
-      const double a = ab[r];
-#pragma unroll
-      for (int i = 0; i < n; ++i) w[i] = fma(sm.S[i + n * r], a, w[i]);
-    }
-    double gh[m];   // own column of [G | H | g] = Bᵀ·w (+ cost terms)
-#pragma unroll
-    for (int i = 0; i < m; ++i) {
-      double a = 0.0;
-#pragma unroll
-      for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * (n + i)], w[r], a);
-      if (isU && ucol == i) a += 2.0 * cost.w_u[i];      // 𝐑 = 2·diag(w_u)
-      if (isAff) a = fma(2.0 * cost.w_u[i], u[i], a);    // 𝐫 = 2·w_u·u
-      gh[i] = a;
-    }
-    if (lane < NC) {
-#pragma unroll
-      for (int i = 0; i < m; ++i) sm.GH[i + m * lane] = gh[i];
-    }
-
-    // ---- feedback_parameters (src/backward_pass.jl:207-218): (H + reg·I) \ [G | g], partial-pivot LU.
-    // Every lane eliminates its own column; the pivot column (owned by lane n + kk) is broadcast.
-    double col[m];
-#pragma unroll
-    for (int i = 0; i < m; ++i) col[i] = gh[i] + ((isU && ucol == i) ? st.reg : 0.0);
-#pragma unroll
-    for (int kk = 0; kk < m; ++kk) {
-      double pc[m];
-#pragma unroll
-      for (int i = kk; i < m; ++i) pc[i] = __shfl_sync(kFull, col[i], n + kk);
-      int p = kk; double best = fabs(pc[kk]);
-#pragma unroll
-      for (int i = kk + 1; i < m; ++i) { const double a = fabs(pc[i]); if (a > best) { best = a; p = i; } }
-#pragma unroll
-      for (int i = kk + 1; i < m; ++i)
-        if (p == i) { double t = col[kk]; col[kk] = col[i]; col[i] = t; t = pc[kk]; pc[kk] = pc[i]; pc[i] = t; }
-      const double rp = rcp_nr(pc[kk]);
-#pragma unroll
-      for (int i = kk + 1; i < m; ++i) col[i] = fma(-(pc[i] * rp), col[kk], col[i]);
-    }
-    if (isU) {
-#pragma unroll
-      for (int i = 0; i < m; ++i) sm.U[i + m * ucol] = col[i];
-    }
-    __syncwarp();
-    double kc[m];   // own column of [K | δu] = −(H_reg)⁻¹·(own column of [G | g])
-#pragma unroll
-    for (int i = m - 1; i >= 0; --i) {
-      double a = col[i];
-#pragma unroll
-      for (int j = i + 1; j < m; ++j) a = fma(sm.U[i + m * j], kc[j], a);   // kc already carries the minus sign
-      kc[i] = -a * rcp_nr(sm.U[i + m * i]);
-    }
-    const int kcolidx = isAff ? n : lane;
-    if (isX || isAff) {
-#pragma unroll
-      for (int i = 0; i < m; ++i) { sm.Kd[i + m * kcolidx] = kc[i]; bad |= isnan(kc[i]); }
-    }
-    __syncwarp();
-
-    // ---- step_back (src/backward_pass.jl:262-273): own column of 𝐒 (x lanes) or 𝐬 (affine lane),
-    //      𝐐 + Aᵀ(S·A) + Kᵀ(H·K + G) + Gᵀ·K  with the UNREGULARISED H
-    double nw[n];
-    {
-      double t[m];
-#pragma unroll
-      for (int i = 0; i < m; ++i) {
-        double a = gh[i];
-#pragma unroll
-        for (int l = 0; l < m; ++l) a = fma(sm.GH[i + m * (n + l)], kc[l], a);
-        t[i] = a;
-      }
-#pragma unroll
-      for (int i = 0; i < n; ++i) {
-        double a = 0.0;
-#pragma unroll
-        for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * i], w[r], a);
-#pragma unroll
-        for (int l = 0; l < m; ++l) a = fma(sm.Kd[l + m * i], t[l], a);
-#pragma unroll
-        for (int l = 0; l < m; ++l) a = fma(sm.GH[l + m * i], kc[l], a);
-        // immediate_cost_quadratization (src/backward_pass.jl:81-109) of the diagonal quadratic cost
-        if (isAff) a += -2.0 * cost.w_x[i] * (cost.x_target[i] - x[i]);
-        else if (lane == i) a += 2.0 * cost.w_x[i];
-        nw[i] = a;
-      }
-    }
-    __syncwarp();   // every lane has finished reading S and sv
-    if (isX) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) sm.S[i + n * lane] = nw[i];
-    } else if (isAff) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) sm.sv[i] = nw[i];
-    }
-    // gains out: K[k][slot][i + m·j], δuff[k][slot][i]
-    if (isX) {
-      double* kp = st.K + ((int64_t)k * S + s) * (m * n) + m * lane;
-#pragma unroll
-      for (int i = 0; i < m; ++i) kp[i] = kc[i];
-    } else if (isAff) {
-      double* dp = st.duff + ((int64_t)k * S + s) * m;
-#pragma unroll
-      for (int i = 0; i < m; ++i) dp[i] = kc[i];
-    }
-    __syncwarp();
-  }
-  if (__any_sync(kFull, bad) && lane == 0) st.status[s] |= ST_NAN_GAINS;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Forward pass (src/forward_pass.jl:55-93), one thread per trajectory.  Candidates α = 1, ½, ¼ …
-// are rolled out in turn; a lane stops at the first one with prev − new > 0 (NaN ⇒ halve).
-// ---------------------------------------------------------------------------------------------
-template <int NQ>
-__global__ void __launch_bounds__(128)
-fwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, const __grid_constant__ CostP cost) {
-  constexpr int n = 2 * NQ, m = NQ;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= st.nslots || !st.active[s]) return;
-  const int64_t S = st.S;
-  const int H = st.H;
-  const int cur = st.cur[s];
-  const double* __restrict__ X = st.x[cur];
-  const double* __restrict__ U = st.u[cur];
-  double* __restrict__ Xo = st.x[cur ^ 1];
-  double* __restrict__ Uo = st.u[cur ^ 1];
-  const double* __restrict__ XT = st.xtraj;
-  const double prev = st.prev_cost[s];
-  double alpha = 1.0, acc_cost = qnan(), acc_du2 = qnan(), acc_alpha = 0.0;
-  bool bad = false;
-#pragma unroll 1
-  for (int j = 0; j < st.n_alpha; ++j, alpha *= 0.5) {
-    double xb[n], cst = 0.0, du2 = 0.0;
-#pragma unroll
-    for (int c = 0; c < n; ++c) { xb[c] = X[(int64_t)s * n + c]; Xo[(int64_t)s * n + c] = xb[c]; }
-#pragma unroll 1
-    for (int k = 0; k < H; ++k) {
-      const double* xk = X + ((int64_t)k * S + s) * n;
-      const double* uk = U + ((int64_t)k * S + s) * m;
-      const double* dk = st.duff + ((int64_t)k * S + s) * m;
-      const double* Kk = st.K + ((int64_t)k * S + s) * (m * n);
-      // ū = u + α δuff + K (x̄ − x)      (src/forward_pass.jl:72-73)
-      double dx[n], ub[m];
-#pragma unroll
-      for (int c = 0; c < n; ++c) dx[c] = xb[c] - xk[c];
-#pragma unroll
-      for (int i = 0; i < m; ++i) {
-        double kdx = Kk[i] * dx[0];
-#pragma unroll
-        for (int c = 1; c < n; ++c) kdx = fma(Kk[i + m * c], dx[c], kdx);
-        const double u0 = uk[i];
-        ub[i] = fma(alpha, dk[i], u0) + kdx;
-        const double e = ub[i] - u0;
-        du2 = fma(e, e, du2);
-        Uo[((int64_t)k * S + s) * m + i] = ub[i];
-      }
-      // running cost l(x̄ − x_traj, ū), summed left to right (src/forward_pass.jl:189-191)
-      double lx = 0.0, lu = 0.0;
-#pragma unroll
-      for (int c = 0; c < n; ++c) {
-        const double xt = XT ? XT[((int64_t)k * S + s) * n + c] : 0.0;
-        const double e = cost.x_target[c] - (xb[c] - xt);
-        lx = fma(cost.w_x[c] * e, e, lx);
-      }
-#pragma unroll
-      for (int i = 0; i < m; ++i) lu = fma(cost.w_u[i] * ub[i], ub[i], lu);
-      cst += lx + lu;
-      double xn[n];
-      chain_step<NQ>(cp, xb, ub, xn);   // x̄⁺ = f(x̄, ū)   (src/forward_pass.jl:74)
-#pragma unroll
-      for (int c = 0; c < n; ++c) { xb[c] = xn[c]; Xo[((int64_t)(k + 1) * S + s) * n + c] = xn[c]; }
-    }
-    double lf = 0.0;
-#pragma unroll
-    for (int c = 0; c < n; ++c) { const double e = cost.x_target[c] - xb[c]; lf = fma(cost.w_xf[c] * e, e, lf); }
-    cst += lf;
-    if (prev - cst > 0.0) {   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
-      acc_cost = cst; acc_du2 = du2; acc_alpha = alpha;
-#pragma unroll
-      for (int c = 0; c < n; ++c) bad |= isnan(xb[c]);
-      break;
-    }
-  }
-  st.bar[s] = cur ^ 1;
-  if (bad) st.status[s] |= ST_NAN_ROLLOUT;
-  st.new_cost[s] = acc_cost; st.alpha[s] = acc_alpha; st.du2[s] = acc_du2;
-}
-
-// Open-loop rollout of u from x0 (animate_RBD_2_link.jl:22-26).  x0: [slot][n].
-template <int NQ>
-__global__ void __launch_bounds__(128)
-rollout_init_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, const double* __restrict__ x0) {
-  constexpr int n = 2 * NQ, m = NQ;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= st.nslots) return;
-  const int64_t S = st.S;
-  const int cur = st.cur[s];
-  double* __restrict__ X = st.x[cur];
-  const double* __restrict__ U = st.u[cur];
-  double xb[n];
-#pragma unroll
-  for (int c = 0; c < n; ++c) { xb[c] = x0[(int64_t)s * n + c]; X[(int64_t)s * n + c] = xb[c]; }
-#pragma unroll 1
-  for (int k = 0; k < st.H; ++k) {
-    double ub[m], xn[n];
-#pragma unroll
-    for (int i = 0; i < m; ++i) ub[i] = U[((int64_t)k * S + s) * m + i];
-    chain_step<NQ>(cp, xb, ub, xn);
-#pragma unroll
-    for (int c = 0; c < n; ++c) { xb[c] = xn[c]; X[((int64_t)(k + 1) * S + s) * n + c] = xn[c]; }
-  }
-}
-
-// Receding-horizon plant step: plant[t] ← f(plant[t], first control of trajectory t's solution)
-template <int NQ>
-__global__ void __launch_bounds__(128)
-mpc_advance_chain(const __grid_constant__ ChainP cp, const double* __restrict__ out_u, double* __restrict__ plant,
-                  double* __restrict__ u_applied, int B, int H) {
-  constexpr int n = 2 * NQ, m = NQ;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B) return;
-  double x[n], u[m], xn[n];
-#pragma unroll
-  for (int c = 0; c < n; ++c) x[c] = plant[(int64_t)t * n + c];
-#pragma unroll
-  for (int i = 0; i < m; ++i) u[i] = out_u[(int64_t)t * m * H + (int64_t)i * H];
-  chain_step<NQ>(cp, x, u, xn);
-#pragma unroll
-  for (int c = 0; c < n; ++c) plant[(int64_t)t * n + c] = xn[c];
-#pragma unroll
-  for (int i = 0; i < m; ++i) u_applied[(int64_t)t * m + i] = u[i];
-}
-
-inline int grid_for(int n, int block) { return (n + block - 1) / block; }
-
-}  // namespace
+// kernels_chain_fl.cu
+void init_chain_fl_attributes();
+bool launch_bwd_chain_fl(const DevState&, const ChainP&, const CostP&, cudaStream_t);
+bool launch_fwd_chain_fl(const DevState&, const ChainP&, const CostP&, cudaStream_t);
+bool launch_rollout_init_chain_fl(const DevState&, const ChainP&, const double*, cudaStream_t);
+bool launch_mpc_advance_chain_fl(const ChainP&, const double*, double*, double*, int, int, cudaStream_t);
 
 #define ILQR_CHAIN_DISPATCH(nq, ...)                       \
   switch (nq) {                                            \
@@ -531,29 +22,31 @@ inline int grid_for(int n, int block) { return (n + block - 1) / block; }
   }
 
 void init_chain_attributes() {
-  cudaFuncSetAttribute(bwd_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<2>) * kCW));
-  cudaFuncSetAttribute(bwd_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<3>) * kCW));
-  cudaFuncSetAttribute(bwd_chain<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<6>) * kCW));
-  cudaFuncSetAttribute(bwd_chain<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<7>) * kCW));
+  set_attr<2, false>(); set_attr<3, false>(); set_attr<6, false>(); set_attr<7, false>();
+  init_chain_fl_attributes();
 }
 
-bool chain_supported(int nq) { return nq == 2 || nq == 3 || nq == 6 || nq == 7; }
+bool chain_supported(int nq, bool floating) { return floating ? (nq == 1 || nq == 2) : (nq == 2 || nq == 3 || nq == 6 || nq == 7); }
 
-void launch_bwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s) {
+void launch_bwd_chain(const DevState& st, const ChainP& cp, bool floating, const CostP& cost, cudaStream_t s) {
   if (st.nslots <= 0) return;
-  ILQR_CHAIN_DISPATCH(cp.nq, bwd_chain<NQ><<<grid_for(st.nslots, kCW), kCW * 32, sizeof(BwdSmem<NQ>) * kCW, s>>>(st, cp, cost);)
+  if (floating) { launch_bwd_chain_fl(st, cp, cost, s); return; }
+  ILQR_CHAIN_DISPATCH(cp.nq, run_bwd<NQ, false>(st, cp, cost, s);)
 }
-void launch_fwd_chain(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s) {
+void launch_fwd_chain(const DevState& st, const ChainP& cp, bool floating, const CostP& cost, cudaStream_t s) {
   if (st.nslots <= 0) return;
-  ILQR_CHAIN_DISPATCH(cp.nq, fwd_chain<NQ><<<grid_for(st.nslots, 128), 128, 0, s>>>(st, cp, cost);)
+  if (floating) { launch_fwd_chain_fl(st, cp, cost, s); return; }
+  ILQR_CHAIN_DISPATCH(cp.nq, run_fwd<NQ, false>(st, cp, cost, s);)
 }
-void launch_rollout_init_chain(const DevState& st, const ChainP& cp, const double* d_x0, cudaStream_t s) {
+void launch_rollout_init_chain(const DevState& st, const ChainP& cp, bool floating, const double* d_x0, cudaStream_t s) {
   if (st.nslots <= 0) return;
-  ILQR_CHAIN_DISPATCH(cp.nq, rollout_init_chain<NQ><<<grid_for(st.nslots, 128), 128, 0, s>>>(st, cp, d_x0);)
+  if (floating) { launch_rollout_init_chain_fl(st, cp, d_x0, s); return; }
+  ILQR_CHAIN_DISPATCH(cp.nq, run_rollout<NQ, false>(st, cp, d_x0, s);)
 }
-void launch_mpc_advance_chain(const ChainP& cp, const double* out_u, double* plant, double* u_applied, int B, int H,
-                              cudaStream_t s) {
-  ILQR_CHAIN_DISPATCH(cp.nq, mpc_advance_chain<NQ><<<grid_for(B, 128), 128, 0, s>>>(cp, out_u, plant, u_applied, B, H);)
+void launch_mpc_advance_chain(const ChainP& cp, bool floating, const double* out_u, double* plant, double* u_applied, int B,
+                              int H, cudaStream_t s) {
+  if (floating) { launch_mpc_advance_chain_fl(cp, out_u, plant, u_applied, B, H, s); return; }
+  ILQR_CHAIN_DISPATCH(cp.nq, run_advance<NQ, false>(cp, out_u, plant, u_applied, B, H, s);)
 }
 
 }  // namespace ilqr

@@ -40,11 +40,15 @@ def two_link_problem(H, B=1, n_alpha=32, trace_iters=0, device=0, reg=None, vari
 
 
 def serial_chain_problem(joints, H, B=1, gravity=(0.0, 0.0, 0.0), x_target=None, w_x=None, w_u=None, w_xf=None, dt=0.01,
-                         n_alpha=32, trace_iters=0, device=0, reg=None):
+                         n_alpha=32, trace_iters=0, device=0, reg=None, base=None):
     """The reference's rigid-body plugin (test/RBD_2_link_example/RBD_helper_functions.jl:48-116) for a fixed-base
     serial chain: `joints` is an (nq, 20) array, one row per joint + child link — origin xyz(3), rpy(3), unit
     axis(3), mass, COM(3), ixx ixy ixz iyy iyz izz, pad — e.g. from load_urdf().  Costs are the diagonal
-    quadratics l = Σ w_x (x* − x)² + Σ w_u u², lf = Σ w_xf (x* − x)²."""
+    quadratics l = Σ w_x (x* − x)² + Σ w_u u², lf = Σ w_xf (x* − x)².
+
+    base: (mass, com[3], inertia[6]) of the root link (load_urdf's second result) makes the mechanism floating-base
+    as in the reference (RBD_helper_functions.jl:7): x = [p(3) MRP; r(3); θ; ω(3); v(3); θ̇], u = base wrench
+    [torque; force] then joint torques; zero gravity only."""
     lib = _abi.load_library()
     joints = np.ascontiguousarray(np.asarray(joints, dtype=np.float64))
     nq = joints.shape[0]
@@ -52,7 +56,19 @@ def serial_chain_problem(joints, H, B=1, gravity=(0.0, 0.0, 0.0), x_target=None,
         raise ValueError("joints must be (nq, %d)" % _abi.CHAIN_STRIDE)
     g = np.ascontiguousarray(np.asarray(gravity, dtype=np.float64))
     p = Problem()
-    rc = lib.ilqr_problem_serial_chain(ctypes.byref(p), nq, joints.ctypes.data, g.ctypes.data, int(H), int(B))
+    if base is None:
+        rc = lib.ilqr_problem_serial_chain(ctypes.byref(p), nq, joints.ctypes.data, g.ctypes.data, int(H), int(B))
+        nv = nq
+    else:
+        if any(g):
+            raise ValueError("floating base: gravity must be zero")
+        row = np.zeros(_abi.CHAIN_STRIDE)
+        if len(base) == _abi.CHAIN_STRIDE:
+            row[:] = np.asarray(base, dtype=np.float64)
+        else:
+            row[9] = base[0]; row[10:13] = base[1]; row[13:19] = base[2]
+        rc = lib.ilqr_problem_floating_chain(ctypes.byref(p), nq, joints.ctypes.data, row.ctypes.data, int(H), int(B))
+        nv = 6 + nq
     if rc != 0:
         raise IlqrError("ilqr_problem_serial_chain failed")
     p.dt = dt
@@ -61,7 +77,7 @@ def serial_chain_problem(joints, H, B=1, gravity=(0.0, 0.0, 0.0), x_target=None,
     p.device = device
     if reg is not None:
         p.reg = reg
-    for name, arr, cnt in (("x_target", x_target, 2 * nq), ("w_x", w_x, 2 * nq), ("w_u", w_u, nq), ("w_xf", w_xf, 2 * nq)):
+    for name, arr, cnt in (("x_target", x_target, 2 * nv), ("w_x", w_x, 2 * nv), ("w_u", w_u, nv), ("w_xf", w_xf, 2 * nv)):
         if arr is not None:
             arr = np.asarray(arr, dtype=np.float64)
             if arr.shape != (cnt,):

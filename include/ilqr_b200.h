@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define ILQR_ABI_VERSION 2
+#define ILQR_ABI_VERSION 3
 #define ILQR_MAX_N 16
 #define ILQR_MAX_M 8
 #define ILQR_MAX_JOINTS 8
@@ -55,7 +55,13 @@ enum ilqr_model {
   /* test/RBD_2_link_example/RBD_helper_functions.jl:48-79 for fixed-base serial chains of revolute
    * joints (the mechanisms of test/urdf/*.urdf): RK4 of v̇ = M(q) \ (u − bias(q,v)), q̇ = v;
    * x = [q; q̇], n = 2·nq, m = nq.  Described by ilqr_problem.{nq, gravity, chain}. */
-  ILQR_MODEL_SERIAL_CHAIN = 2
+  ILQR_MODEL_SERIAL_CHAIN = 2,
+  /* The same plugin as the reference runs it (RBD_helper_functions.jl:7, floating = true): the chain hangs off a
+   * free-floating base link.  x = [p(3) MRP; r(3); θ(nq); ω(3); v(3); θ̇(nq)] (:52-53), n = 12 + 2·nq;
+   * u = [torque(3); force(3)] on the base in base coordinates, then joint torques, m = 6 + nq.
+   * v̇ = M \ (u − bias) for 𝑣 = [ω; v; θ̇] (base twist in the base frame), q̇ = [pdot_from_w(p, ω); v; θ̇] (:66).
+   * Zero gravity only (as the reference).  chain row nq carries the base link's mass / COM / inertia.  nq in {1, 2}. */
+  ILQR_MODEL_FLOATING_CHAIN = 3
 };
 
 /* per-trajectory status bits (int32) */
@@ -136,7 +142,7 @@ typedef struct ilqr_problem {
   int32_t nq;
   int32_t reserved0;
   double gravity[3];      /* gravity acceleration in the base frame (RBD_helper_functions.jl:7: zero) */
-  double chain[ILQR_MAX_JOINTS * ILQR_CHAIN_STRIDE];
+  double chain[(ILQR_MAX_JOINTS + 1) * ILQR_CHAIN_STRIDE];   /* + 1: the base link of a floating mechanism */
 } ilqr_problem;
 
 typedef struct ilqr_handle ilqr_handle;
@@ -151,6 +157,10 @@ int32_t ilqr_problem_two_link(ilqr_problem* p, int32_t H, int32_t B);
  * (NULL = zero), dt = 0.01, reg = 0.01, n_alpha = 32, all cost weights zero (set x_target/w_x/w_u/w_xf after). */
 int32_t ilqr_problem_serial_chain(ilqr_problem* p, int32_t nq, const double* joints, const double* gravity, int32_t H,
                                   int32_t B);
+
+/* Floating-base variant: base_link = one row of ILQR_CHAIN_STRIDE doubles (only mass, COM, inertia are read). */
+int32_t ilqr_problem_floating_chain(ilqr_problem* p, int32_t nq, const double* joints, const double* base_link, int32_t H,
+                                    int32_t B);
 
 int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out);
 int32_t ilqr_destroy(ilqr_handle* h);

@@ -30,7 +30,7 @@ struct Problem
     nq::Int32
     reserved0::Int32
     gravity::NTuple{3,Float64}
-    chain::NTuple{160,Float64}     # ILQR_MAX_JOINTS × ILQR_CHAIN_STRIDE
+    chain::NTuple{180,Float64}     # (ILQR_MAX_JOINTS + 1) × ILQR_CHAIN_STRIDE
 end
 
 const X, U, XBAR, UBAR, DUFF, K, NEW_COST, PREV_COST, ALPHA, DU2 = Int32.(0:9)

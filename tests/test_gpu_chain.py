@@ -155,3 +155,102 @@ def test_urdf_loader_reads_the_reference_mechanisms():
     for b in range(B):
         _, K0, _ = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
         assert rel_err(K[:, :, :, b], K0) <= RTOL
+
+
+# ---------------------------------------------------------------------------------------------
+# Floating base (ILQR_MODEL_FLOATING_CHAIN): the plugin as the reference runs it, test/RBD_2_link_example
+# ---------------------------------------------------------------------------------------------
+def _setup_floating(nq, B, H, seed, reference_config=False):
+    rng = np.random.default_rng(seed)
+    nv = 6 + nq
+    if reference_config:
+        joints = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "2dof_chain.npy"))
+        base = np_chain.joint_row(mass=30.0, inertia=(50, 0, 0, 50, 0, 50))               # 2Dof_arm.urdf base_link
+        target = np.concatenate([[0, 0, 0, 5, 1, 2, 1, .3], np.zeros(8)])                 # animate_RBD_2_link.jl:10
+        w_x = np.concatenate([10.0 * np.array([100, 100, 100, 1, 1, 1, 10, 10.]), np.zeros(8)])     # RBD_helper_functions.jl:88-99
+        w_u = np.array([1, 1, 1, 100, 100, 100, 10, 10.])
+        w_xf = np.concatenate([1e5 * np.array([100, 100, 100, 1000, 1000, 1000, 10, 10.]), np.zeros(8)])   # :109-115
+        # the reference pose (:9 ⇒ MRP (0,0,1), r = (.5,.75,1)) + U(−0.1, 0.1) on r and θ
+        x0 = np.tile(np.concatenate([[0, 0, 1.0], [.5, .75, 1.0], [0, 0], np.zeros(8)]), (B, 1))
+        x0[:, 3:8] += rng.uniform(-0.1, 0.1, (B, 5))
+        u = np.zeros((H, nv, B), order="F")
+    else:
+        joints = np_chain.random_chain(nq, rng, True)
+        A = rng.normal(size=(3, 3)); I = A @ A.T + np.eye(3)
+        base = np_chain.joint_row(mass=rng.uniform(5, 30), com=rng.uniform(-0.3, 0.3, 3),
+                                  inertia=(I[0, 0], I[0, 1], I[0, 2], I[1, 1], I[1, 2], I[2, 2]))
+        target = np.concatenate([rng.uniform(-0.5, 0.5, nv), np.zeros(nv)])
+        w_x = np.concatenate([np.ones(nv), 0.1 * np.ones(nv)])
+        w_u = rng.uniform(0.5, 2.0, nv)
+        w_xf = np.concatenate([10.0 * np.ones(nv), np.ones(nv)])
+        x0 = np.concatenate([rng.uniform(-0.4, 0.4, (B, 3)), rng.uniform(-1, 1, (B, 3 + nq)), rng.uniform(-0.5, 0.5, (B, nv))], axis=1)
+        u = np.asfortranarray(rng.uniform(-0.5, 0.5, (H, nv, B)))
+    spec = orc.chain_spec(joints, base=base, x_target=target, w_x=w_x, w_u=w_u, w_xf=w_xf)
+    prob = ilqr_b200.serial_chain_problem(joints, H, B, base=base, x_target=target, w_x=w_x, w_u=w_u, w_xf=w_xf, trace_iters=60)
+    x = np.zeros((H + 1, 2 * nv, B), order="F")
+    for b in range(B):
+        x[:, :, b] = orc.chain_rollout(spec, x0[b], u[:, :, b])
+    return spec, prob, x0, x, u
+
+
+@pytest.mark.parametrize("nq", [1, 2])
+def test_floating_base_passes_match_oracle(nq):
+    B, H = 6, 15
+    spec, prob, x0, x, u = _setup_floating(nq, B, H, 500 + nq)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload_x0(np.asfortranarray(x0.T), u)
+        assert rel_err(s.download(_abi.X), x) <= 1e-12
+        s.upload(x, u)
+        s.backward_pass()
+        d, K = s.download(_abi.DUFF), s.download(_abi.K)
+        s.forward_pass()
+        xb, ub, c, a = s.download(_abi.XBAR), s.download(_abi.UBAR), s.download(_abi.NEW_COST), s.download(_abi.ALPHA)
+    for b in range(B):
+        d0, K0, st0 = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
+        assert st0 == 0
+        assert rel_err(d[:, :, b], d0) <= RTOL and rel_err(K[:, :, :, b], K0) <= RTOL
+        xb0, ub0, c0, a0, _ = orc.chain_forward_pass(spec, x[:, :, b], u[:, :, b], d[:, :, b], K[:, :, :, b], np.inf)
+        assert a[b] == a0 == 1.0
+        assert rel_err(xb[:, :, b], xb0) <= RTOL and rel_err(ub[:, :, b], ub0) <= RTOL and abs(c[b] - c0) <= RTOL * abs(c0)
+
+
+def test_floating_base_fit_matches_oracle():
+    B, H = 10, 25
+    spec, prob, x0, x, u = _setup_floating(2, B, H, 77)
+    ref = orc.chain_fit_batch(spec, x, u, max_iter=40, tol=1e-8, nthreads=8)
+    with ilqr_b200.BatchSolver(prob) as s:
+        out = s.solve(x, u, max_iter=40, tol=1e-8)
+        ct = s.download(_abi.COST_TRACE)
+    assert np.array_equal(out["iters"], ref["iters"]), (out["iters"], ref["iters"])
+    for b in range(B):
+        it = ref["iters"][b]
+        assert rel_err(ct[:it, b], ref["cost"][:it, b]) <= RTOL
+    assert rel_err(out["x"], ref["x"]) <= RTOL
+
+
+def test_config3_reference_problem_matches_oracle():
+    """BASELINE configs[2] (test/RBD_2_link_example as written: 2Dof_arm.urdf on a floating base, the reference's
+    weights 1e3…1e8 and target pose) at oracle-sized B and H.  The terminal weights make H + reg·I ill-conditioned
+    (cond ≈ 1e7), so gains agree to ≈ cond·ε rather than 1e-9; costs and trajectories still meet 1e-9."""
+    B, H = 8, 40
+    spec, prob, x0, x, u = _setup_floating(2, B, H, 3, reference_config=True)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        d, K = s.download(_abi.DUFF), s.download(_abi.K)
+    for b in range(B):
+        d0, K0, _ = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
+        assert rel_err(d[:, :, b], d0) <= 1e-7 and rel_err(K[:, :, :, b], K0) <= 1e-7, (rel_err(d[:, :, b], d0), rel_err(K[:, :, :, b], K0))
+    ref = orc.chain_fit_batch(spec, x, u, max_iter=12, tol=1e-6, nthreads=8)
+    assert np.nanmin(ref["alpha"]) < 1.0          # the line search fires on this problem (α down to 1/8)
+    with ilqr_b200.BatchSolver(prob) as s:
+        out = s.solve(x, u, max_iter=12, tol=1e-6)
+        ct, at = s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE)
+    assert np.array_equal(out["iters"], ref["iters"]), (out["iters"], ref["iters"])
+    errs = []
+    for b in range(B):
+        it = ref["iters"][b]
+        assert np.array_equal(at[:it, b], ref["alpha"][:it, b]), (at[:it, b], ref["alpha"][:it, b])
+        errs.append(rel_err(ct[:it, b], ref["cost"][:it, b]))
+    print("config-3 cost-trace rel err", max(errs), "x rel err", rel_err(out["x"], ref["x"]))
+    assert max(errs) <= 1e-8 and rel_err(out["x"], ref["x"]) <= 1e-8
