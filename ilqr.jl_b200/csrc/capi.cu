@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <functional>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 
@@ -58,6 +59,11 @@ struct ilqr_handle {
 namespace {
 
 std::string g_create_err;
+
+// One bulk PCIe transfer per direction and device at a time: concurrent handles (pool scheduler) otherwise share
+// the link, every upload finishes late and no batch can start computing until all of them have arrived.
+constexpr int kMaxDevices = 64;
+std::mutex g_h2d_mu[kMaxDevices], g_d2h_mu[kMaxDevices];
 
 #define CK(h, call)                                                                             \
   do {                                                                                          \
@@ -760,17 +766,22 @@ int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, c
   static const bool trace_phases = getenv("ILQR_TRACE_PHASES") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  if (int32_t rc = upload_xtraj(h, x_traj, cudaMemcpyHostToDevice)) return rc;
   const size_t N = p.H + 1, B = p.B;
-  CK(h, cudaMemcpyAsync(h->stage_x, x_init, sizeof(double) * N * p.n * B, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * B, cudaMemcpyHostToDevice, h->stream));
-  if (trace_phases) cudaStreamSynchronize(h->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_h2d_mu[h->device % kMaxDevices]);
+    if (int32_t rc = upload_xtraj(h, x_traj, cudaMemcpyHostToDevice)) return rc;
+    CK(h, cudaMemcpyAsync(h->stage_x, x_init, sizeof(double) * N * p.n * B, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->stage_u, u_init, sizeof(double) * p.H * p.m * B, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+  }
   const double t1 = now();
   if (int32_t rc = finish_upload(h)) return rc;
   if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;
   if (trace_phases) cudaStreamSynchronize(h->stream);
   const double t2 = now();
   struct Tail { bool on; double t0, t1, t2; std::function<double()> now; ~Tail() { if (on) fprintf(stderr, "[ilqr] solve phases: h2d %.2f ms, fit %.2f ms, d2h %.2f ms\n", t1 - t0, t2 - t1, now() - t2); } } tail{trace_phases, t0, t1, t2, now};
+  CK(h, cudaStreamSynchronize(h->stream));   // results are in the mirrors; now queue for the link
+  std::lock_guard<std::mutex> lk(g_d2h_mu[h->device % kMaxDevices]);
   CK(h, cudaMemcpyAsync(x_out, h->st.out_x, sizeof(double) * N * p.n * B, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemcpyAsync(u_out, h->st.out_u, sizeof(double) * p.H * p.m * B, cudaMemcpyDeviceToHost, h->stream));
   if (cost_out) CK(h, cudaMemcpyAsync(cost_out, h->st.r_prev_cost, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
