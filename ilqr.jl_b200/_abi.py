@@ -64,6 +64,9 @@ SYMBOLS = {
     "ilqr_solve": (ctypes.c_int32, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                     ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_stream_solve_device": (ctypes.c_int32, [_H, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                                 ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "ilqr_mpc_start": (ctypes.c_int32, [_H, ctypes.c_void_p, ctypes.c_void_p]),
     "ilqr_mpc_step": (ctypes.c_int32, [_H, ctypes.c_int32, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "ilqr_pool_create": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.POINTER(_H)]),

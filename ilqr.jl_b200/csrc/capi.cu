@@ -3,6 +3,7 @@
 // boundary, kernel launches, and the batched mirror of fit's control loop
 // (src/forward_pass.jl:148-179 of the reference).  No CPU compute path exists:
 // every numerical result comes from the CUDA kernels or the call fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <chrono>
@@ -548,11 +549,11 @@ static int32_t forward_async(ilqr_handle* h) {
   return check_launch(h, "forward kernel");
 }
 
-static int32_t commit_async(ilqr_handle* h, double tol) {
+static int32_t commit_async(ilqr_handle* h, double tol, int32_t max_iter = 0x7fffffff) {
   if (!h->have_candidate) return fail(h, ILQR_ERR_STATE, "commit before forward_pass");
   if (h->n_pending >= ilqr_handle::kMaxBurst) return fail(h, ILQR_ERR_STATE, "too many iterations in flight");
   h->st.pub_slot = h->n_pending;
-  launch_commit(h->st, tol, h->stream);
+  launch_commit(h->st, tol, h->stream, max_iter);
   h->n_pending += 1;
   h->launches += 1;
   h->have_gains = false; h->have_candidate = false;
@@ -665,6 +666,92 @@ static int32_t fit_loop(ilqr_handle* h, int32_t max_iter, double tol, int32_t* i
   h->launches += 3;
   if (iters_run) *iters_run = it;
   return check_launch(h, "fit");
+}
+
+// Streaming admission.  The handle's B slots are kept full: as trajectories finish they are
+// retired straight into the caller's output arrays and their slots are refilled with the next pending
+// trajectories, so every launch runs at full width until the input is exhausted and the latency-bound tail
+// is paid once per stream instead of once per batch.  Each trajectory is iterated exactly as ilqr_fit would
+// iterate it (per-trajectory convergence and max_iter); results are bit-identical to batch-wise solves.
+int32_t ilqr_stream_solve_device(ilqr_handle* h, int64_t n_total, const double* d_x_init, const double* d_u_init,
+                                 int32_t max_iter, double tol, double* d_x_out, double* d_u_out, double* d_cost_out,
+                                 int32_t* d_iters_out, int32_t* d_status_out, int64_t* batch_iterations) {
+  if (!h || !d_x_init || !d_u_init || !d_x_out || !d_u_out) return fail(h, ILQR_ERR_INVALID, "null argument");
+  if (n_total < 1 || n_total > 0x7fffffff || max_iter < 1) return fail(h, ILQR_ERR_INVALID, "bad n_total / max_iter");
+  if (h->prob.trace_iters > 0) return fail(h, ILQR_ERR_INVALID, "streaming needs trace_iters == 0");
+  const ilqr_problem& p = h->prob;
+  DevState& st = h->st;
+  CK(h, cudaSetDevice(h->device));
+  if (st.xtraj) { cudaFree(st.xtraj); st.xtraj = nullptr; }
+  const size_t N = p.H + 1, n = p.n, m = p.m, H = p.H;
+  const int64_t S = st.S;
+  // per-TRAJECTORY mirrors over the whole stream; the caller's arrays where given
+  double *t_prev = nullptr, *t_new = nullptr, *t_alpha = nullptr, *t_du2 = nullptr;
+  int32_t *t_status = nullptr, *t_iters = nullptr, *t_active = nullptr;
+  auto cleanup = [&] { cudaFree(t_prev); cudaFree(t_new); cudaFree(t_alpha); cudaFree(t_du2); cudaFree(t_status); cudaFree(t_iters); cudaFree(t_active); };
+#define CKS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); h->err = std::string(#call) + ": " + cudaGetErrorString(e__); return ILQR_ERR_CUDA; } } while (0)
+  if (!d_cost_out) CKS(dalloc(&t_prev, (size_t)n_total));
+  if (!d_iters_out) CKS(dalloc(&t_iters, (size_t)n_total));
+  if (!d_status_out) CKS(dalloc(&t_status, (size_t)n_total));
+  CKS(dalloc(&t_new, (size_t)n_total)); CKS(dalloc(&t_alpha, (size_t)n_total)); CKS(dalloc(&t_du2, (size_t)n_total));
+  CKS(dalloc(&t_active, (size_t)n_total));
+  const DevState saved = st;
+  st.out_x = d_x_out; st.out_u = d_u_out;
+  st.r_prev_cost = d_cost_out ? d_cost_out : t_prev; st.r_iters = d_iters_out ? d_iters_out : t_iters;
+  st.r_status = d_status_out ? d_status_out : t_status;
+  st.r_new_cost = t_new; st.r_alpha = t_alpha; st.r_du2 = t_du2; st.r_active = t_active;
+  auto restore = [&] {
+    const int32_t ns = 0;
+    DevState r = saved; r.nslots = ns; st = r; cleanup();
+    h->loaded = false; h->have_gains = false; h->have_candidate = false; h->n_pending = 0;
+  };
+  for (auto& v : h->prof) v = 0.0;
+  int parity = 0;
+  int64_t next = 0, iters_run = 0;
+  auto admit = [&](int slot0) {
+    const int n_new = (int)std::min<int64_t>((int64_t)p.B - slot0, n_total - next);
+    if (n_new <= 0) return;
+    launch_tf_to_bf(d_x_init + (size_t)next * N * n, st.x[parity] + (size_t)slot0 * n, nullptr, n_new, (int)N, (int)n, S, h->stream);
+    launch_tf_to_bf(d_u_init + (size_t)next * H * m, st.u[parity] + (size_t)slot0 * m, nullptr, n_new, (int)H, (int)m, S, h->stream);
+    launch_admit(st, slot0, n_new, next, parity, h->stream);
+    h->launches += 3;
+    st.nslots = slot0 + n_new;
+    next += n_new;
+  };
+  st.nslots = 0;
+  admit(0);
+  h->loaded = true; h->have_gains = false; h->have_candidate = false; h->n_pending = 0;
+  h->n_active_host = st.nslots;
+  const int refill_min = std::max(32, p.B / 16);
+  while (st.nslots > 0) {
+    int32_t rc = backward_async(h);
+    if (rc == 0) rc = forward_async(h);
+    if (rc == 0) rc = commit_async(h, tol, max_iter);
+    if (rc != 0) { restore(); return rc; }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { restore(); return fail(h, ILQR_ERR_CUDA, "stream solve: kernel failure"); }
+    const int32_t na = ((volatile int32_t*)h->pinned_i32)[0];
+    h->burst_active[0] = h->n_active_host;
+    accumulate_profile(h);
+    ++iters_run;
+    parity ^= 1;
+    const int32_t finished = st.nslots - na;
+    const bool more = next < n_total;
+    if (finished > 0 && (na == 0 || (more ? finished >= refill_min : (finished >= 32 && finished * 16 >= st.nslots)))) {
+      launch_compact(st, na, h->stream);
+      h->launches += 3;
+      st.nslots = na;
+      if (more) admit(na);
+    }
+    h->n_active_host = na + (st.nslots - na);
+    if (st.nslots > na) h->n_active_host = st.nslots;   // freshly admitted slots are active
+    else h->n_active_host = na;
+  }
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) { restore(); return fail(h, ILQR_ERR_CUDA, "stream solve: retire failure"); }
+  if (batch_iterations) *batch_iterations = iters_run;
+  const int32_t rc = check_launch(h, "stream solve");
+  restore();
+#undef CKS
+  return rc;
 }
 
 int32_t ilqr_fit(ilqr_handle* h, int32_t max_iter, double tol, int32_t* iters_run) {

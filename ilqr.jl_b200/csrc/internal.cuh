@@ -71,7 +71,9 @@ void launch_fwd_split_two_link(const DevState& st, const TwoLinkP& mp, const Cos
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0 /*[n][S] BF*/,
                                   cudaStream_t s);
-void launch_commit(const DevState& st, double tol, cudaStream_t s);
+// max_iter: per-trajectory iteration cap applied on device (streaming mode); the batched fit loop counts on the host
+void launch_commit(const DevState& st, double tol, cudaStream_t s, int max_iter = 0x7fffffff);
+void launch_admit(const DevState& st, int slot0, int count, int64_t traj0, int parity, cudaStream_t s);
 void launch_finalize_max_iter(const DevState& st, cudaStream_t s);
 void launch_reset_state(const DevState& st, cudaStream_t s);
 void launch_set_prev_cost(const DevState& st, const double* d_prev, cudaStream_t s);

@@ -792,7 +792,7 @@ __global__ void mpc_advance_two_link(const __grid_constant__ TwoLinkP mp, const 
   for (int i = 0; i < NU; ++i) u_applied[(int64_t)t * NU + i] = u[i];
 }
 
-__global__ void commit_kernel(const __grid_constant__ DevState st, double tol) {
+__global__ void commit_kernel(const __grid_constant__ DevState st, double tol, int max_iter) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   bool still = false;
   if (s < st.nslots && st.active[s]) {
@@ -817,7 +817,12 @@ __global__ void commit_kernel(const __grid_constant__ DevState st, double tol) {
         st.active[s] = 0;
       } else {                     // :174-175
         st.cur[s] ^= 1;
-        still = true;
+        if (it >= max_iter) {      // streaming mode: max_iter is per trajectory; keep the newest iterate (:176-178)
+          stat |= ST_MAX_ITER;
+          st.active[s] = 0;
+        } else {
+          still = true;
+        }
       }
     }
     st.status[s] = stat;
@@ -839,6 +844,19 @@ __global__ void commit_kernel(const __grid_constant__ DevState st, double tol) {
     *st.n_retry = 0;
     __threadfence_system();
   }
+}
+
+// Streaming admission: slots [slot0, slot0 + count) receive fresh trajectories traj0 … (fit's start state,
+// src/forward_pass.jl:159-160); their iterate was loaded into buffer `parity`, the one every live slot reads next.
+__global__ void admit_kernel(const __grid_constant__ DevState st, int slot0, int count, int64_t traj0, int parity) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int s = slot0 + i;
+  const double nan = qnan();
+  st.prev_cost[s] = __longlong_as_double(0x7ff0000000000000LL);
+  st.new_cost[s] = nan; st.alpha[s] = nan; st.du2[s] = nan;
+  st.status[s] = 0; st.iters[s] = 0; st.cur[s] = parity; st.bar[s] = parity ^ 1; st.traj[s] = (int32_t)(traj0 + i);
+  st.active[s] = 1;
 }
 
 __global__ void finalize_max_iter_kernel(const __grid_constant__ DevState st) {
@@ -1072,8 +1090,11 @@ void launch_mpc_advance_two_link(const TwoLinkP& mp, const double* out_u, double
                                  cudaStream_t s) {
   mpc_advance_two_link<<<grid_for(B, 128), 128, 0, s>>>(mp, out_u, plant, u_applied, B, H);
 }
-void launch_commit(const DevState& st, double tol, cudaStream_t s) {
-  if (st.nslots > 0) commit_kernel<<<grid_for(st.nslots, 256), 256, 0, s>>>(st, tol);
+void launch_commit(const DevState& st, double tol, cudaStream_t s, int max_iter) {
+  if (st.nslots > 0) commit_kernel<<<grid_for(st.nslots, 256), 256, 0, s>>>(st, tol, max_iter);
+}
+void launch_admit(const DevState& st, int slot0, int count, int64_t traj0, int parity, cudaStream_t s) {
+  if (count > 0) admit_kernel<<<grid_for(count, 256), 256, 0, s>>>(st, slot0, count, traj0, parity);
 }
 void launch_finalize_max_iter(const DevState& st, cudaStream_t s) {
   if (st.nslots <= 0) return;

@@ -278,6 +278,14 @@ class BatchSolver:
                  "ilqr_solve")
         return out
 
+    def stream_solve_device(self, n_total, d_x, d_u, d_xo, d_uo, d_cost=None, d_iters=None, d_status=None, max_iter=100, tol=1e-6):
+        """ilqr_stream_solve_device: raw device addresses of boundary-layout arrays holding n_total trajectories; the
+        handle's B slots are kept full by admitting pending trajectories as others finish.  Returns batch iterations."""
+        it = ctypes.c_int64()
+        self._ck(self._lib.ilqr_stream_solve_device(self._h, int(n_total), d_x, d_u, int(max_iter), float(tol), d_xo, d_uo,
+                                                    d_cost, d_iters, d_status, ctypes.byref(it)), "ilqr_stream_solve_device")
+        return it.value
+
     # -- receding-horizon MPC ----------------------------------------------
     def mpc_start(self, x0, u_init=None):
         x0 = self._shape(x0, (self.n,))

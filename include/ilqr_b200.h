@@ -225,6 +225,16 @@ int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, c
                    int32_t max_iter, double tol, double* x_out, double* u_out, double* cost_out,
                    int32_t* iters_out, int32_t* status_out);
 
+/* Streaming admission over one handle (device pointers, boundary layout, n_total >= 1 trajectories — more than the
+ * handle's B slots is the point): the B slots are kept full, finished trajectories retire straight into the output
+ * arrays and their slots are refilled from the pending input, so every launch runs full width and the latency-bound
+ * tail is paid once per stream instead of once per batch.  Per-trajectory semantics are those of ilqr_fit (tol,
+ * max_iter apply to each trajectory); x_traj is not supported.  d_cost/d_iters/d_status nullable;
+ * batch_iterations (nullable) receives the number of backward+forward launches. */
+int32_t ilqr_stream_solve_device(ilqr_handle* h, int64_t n_total, const double* d_x_init, const double* d_u_init,
+                                 int32_t max_iter, double tol, double* d_x_out, double* d_u_out, double* d_cost_out,
+                                 int32_t* d_iters_out, int32_t* d_status_out, int64_t* batch_iterations);
+
 /* ---- receding-horizon MPC (BASELINE config 5), built on fit's warm-start property
  * (src/forward_pass.jl:148-155 takes any x_init/u_init).  ilqr_mpc_start sets the plant states
  * x0[n,B] and the initial control sequences (u_init[H,m,B] or NULL = zeros; x_init = open-loop

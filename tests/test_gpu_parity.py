@@ -320,3 +320,37 @@ def test_mpc_closed_loop_matches_oracle():
             ua, xp = got[t]
             assert np.max(np.abs(ua[:, b] - u0)) < RTOL * max(1.0, np.max(np.abs(u0))), (b, t)
             assert np.max(np.abs(xp[:, b] - plant)) < RTOL * max(1.0, np.max(np.abs(plant))), (b, t)
+
+
+def test_stream_admission_equals_batch_solves():
+    """ilqr_stream_solve_device: 96 slots kept full from 700 pending trajectories (config-2 and line-search-stress
+    inputs mixed, max_iter low enough that some trajectories hit it).  Every trajectory must come out exactly as a
+    plain batched solve leaves it: same iterate, cost, iteration count and status, bit for bit."""
+    import torch
+    H, n_total, slots, max_iter = 60, 700, 96, 25
+    _, xa, ua = config2_batch(400, H, seed=21)
+    _, xb, ub = stress_batch(300, H, seed=22)
+    x = np.asfortranarray(np.concatenate([xa, xb], axis=2)); u = np.asfortranarray(np.concatenate([ua, ub], axis=2))
+    perm = np.random.default_rng(0).permutation(n_total)
+    x = np.asfortranarray(x[:, :, perm]); u = np.asfortranarray(u[:, :, perm])
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, n_total)) as s:
+        ref = s.solve(x, u, max_iter=max_iter, tol=1e-6)
+    assert (ref["status"] & _abi.STATUS_MAX_ITER).any() and (ref["status"] & _abi.STATUS_CONVERGED).any()
+    # boundary layout [N,n,B] Fortran == C-contiguous [B,n,N]
+    dx = torch.from_numpy(np.ascontiguousarray(x.transpose(2, 1, 0))).cuda(); du = torch.from_numpy(np.ascontiguousarray(u.transpose(2, 1, 0))).cuda()
+    ox, ou = torch.zeros_like(dx), torch.zeros_like(du)
+    oc = torch.zeros(n_total, dtype=torch.float64, device="cuda")
+    oi = torch.zeros(n_total, dtype=torch.int32, device="cuda"); os_ = torch.zeros(n_total, dtype=torch.int32, device="cuda")
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, slots)) as s:
+        iters = s.stream_solve_device(n_total, dx.data_ptr(), du.data_ptr(), ox.data_ptr(), ou.data_ptr(), oc.data_ptr(),
+                                      oi.data_ptr(), os_.data_ptr(), max_iter=max_iter, tol=1e-6)
+        # the handle is reusable afterwards
+        out2 = s.solve(np.asfortranarray(x[:, :, :slots]), np.asfortranarray(u[:, :, :slots]), max_iter=max_iter, tol=1e-6)
+    torch.cuda.synchronize()
+    assert iters >= max_iter
+    assert np.array_equal(oi.cpu().numpy(), ref["iters"])
+    assert np.array_equal(os_.cpu().numpy(), ref["status"])
+    assert np.array_equal(oc.cpu().numpy(), ref["cost"])
+    assert np.array_equal(ox.cpu().numpy().transpose(2, 1, 0), ref["x"])
+    assert np.array_equal(ou.cpu().numpy().transpose(2, 1, 0), ref["u"])
+    assert np.array_equal(out2["x"], ref["x"][:, :, :slots]) and np.array_equal(out2["iters"], ref["iters"][:slots])
