@@ -26,7 +26,10 @@ struct ilqr_handle {
   DevState st{};
   TwoLinkP mp{};
   ChainP chain{};
-  bool is_chain = false, floating = false;
+  bool is_chain = false, floating = false, is_custom = false;
+  CustomModule cmod{};
+  CustomP cparams{};
+  std::string custom_src;
   CostP cp{};
   // TF (boundary-layout) staging on device
   double* stage_x = nullptr;   // [B][n*N]
@@ -215,6 +218,32 @@ int32_t ilqr_problem_serial_chain(ilqr_problem* p, int32_t nq, const double* joi
   return ILQR_OK;
 }
 
+int32_t ilqr_problem_custom(ilqr_problem* p, int32_t n, int32_t m, int32_t H, int32_t B, double dt, const char* dynamics_src,
+                            const double* params, int32_t n_params) {
+  if (!p || !dynamics_src || n < 1 || n > ILQR_MAX_N || m < 1 || m > ILQR_MAX_M || n_params < 0 || n_params > 32 ||
+      (n_params > 0 && !params))
+    return ILQR_ERR_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->abi_version = ILQR_ABI_VERSION;
+  p->model_id = ILQR_MODEL_CUSTOM;
+  p->n = n; p->m = m; p->H = H; p->B = B;
+  p->n_alpha = 32; p->variant = ILQR_VARIANT_AUTO;
+  p->dt = dt;
+  p->reg = 0.01;   // src/backward_pass.jl:214
+  for (int i = 0; i < n_params; ++i) p->model_params[i] = params[i];
+  p->custom_src = dynamics_src;
+  return ILQR_OK;
+}
+
+int32_t ilqr_custom_compile_check(const char* dynamics_src, int32_t n, int32_t m, char* log, int32_t log_len) {
+  if (!dynamics_src || n < 1 || n > ILQR_MAX_N || m < 1 || m > ILQR_MAX_M) return ILQR_ERR_INVALID;
+  std::vector<char> cubin;
+  std::string l;
+  const int32_t rc = custom_compile(dynamics_src, n, m, "sm_100a", cubin, l);
+  if (log && log_len > 0) { std::strncpy(log, l.c_str(), (size_t)log_len - 1); log[log_len - 1] = 0; }
+  return rc == 0 ? ILQR_OK : ILQR_ERR_INVALID;
+}
+
 int32_t ilqr_problem_floating_chain(ilqr_problem* p, int32_t nq, const double* joints, const double* base_link, int32_t H,
                                     int32_t B) {
   if (!base_link || nq < 1 || nq + 1 > ILQR_MAX_JOINTS + 1) return ILQR_ERR_INVALID;
@@ -248,9 +277,13 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
         return fail(nullptr, ILQR_ERR_INVALID, "joint axes must be unit vectors");
       if (!(p->chain[i * ILQR_CHAIN_STRIDE + 9] > 0.0)) return fail(nullptr, ILQR_ERR_INVALID, "link masses must be > 0");
     }
+  } else if (p->model_id == ILQR_MODEL_CUSTOM) {
+    if (!p->custom_src || p->n < 1 || p->n > ILQR_MAX_N || p->m < 1 || p->m > ILQR_MAX_M)
+      return fail(nullptr, ILQR_ERR_INVALID, "ILQR_MODEL_CUSTOM needs custom_src, 1 <= n <= 16, 1 <= m <= 8");
   } else if (p->model_id != ILQR_MODEL_TWO_LINK || p->n != 4 || p->m != 2) {
-    return fail(nullptr, ILQR_ERR_INVALID, "unsupported model (ILQR_MODEL_TWO_LINK with n=4, m=2 or ILQR_MODEL_SERIAL_CHAIN)");
+    return fail(nullptr, ILQR_ERR_INVALID, "unsupported model id / dimensions");
   }
+  const bool is_custom = p->model_id == ILQR_MODEL_CUSTOM;
   if (p->H < 1 || p->B < 1 || p->n_alpha < 1 || p->n_alpha > 64 || p->trace_iters < 0)
     return fail(nullptr, ILQR_ERR_INVALID, "bad H/B/n_alpha/trace_iters");
   int ndev = 0;
@@ -262,7 +295,8 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
 
   ilqr_handle* h = new (std::nothrow) ilqr_handle();
   if (!h) return fail(nullptr, ILQR_ERR_INVALID, "out of host memory");
-  h->prob = *p; h->device = p->device; h->is_chain = is_chain; h->floating = floating;
+  h->prob = *p; h->device = p->device; h->is_chain = is_chain; h->floating = floating; h->is_custom = is_custom;
+  if (is_custom) { h->custom_src = p->custom_src; h->prob.custom_src = h->custom_src.c_str(); }
 #define CKC(call)                                                                               \
   do {                                                                                          \
     cudaError_t e__ = (call);                                                                   \
@@ -381,6 +415,16 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
       std::memcpy(Cprev, C, sizeof C);
     }
   }
+  if (is_custom) {
+    h->cparams.dt = p->dt;
+    for (int i = 0; i < 32; ++i) h->cparams.p[i] = p->model_params[i];
+    std::string cerr;
+    if (custom_get(h->custom_src.c_str(), p->n, p->m, p->device, &h->cmod, cerr) != 0) {
+      g_create_err = "ILQR_MODEL_CUSTOM: " + cerr;
+      free_all(h); delete h;
+      return ILQR_ERR_INVALID;
+    }
+  }
   h->mp.alpha = p->model_params[0]; h->mp.beta = p->model_params[1]; h->mp.delta = p->model_params[2];
   h->mp.dt = p->dt; h->mp.twobeta = 2 * p->model_params[1];
   for (int i = 0; i < kMaxN; ++i) { h->cp.x_target[i] = p->x_target[i]; h->cp.w_x[i] = p->w_x[i]; h->cp.w_xf[i] = p->w_xf[i]; }
@@ -441,7 +485,8 @@ int32_t ilqr_upload_x0(ilqr_handle* h, const double* x0, const double* u_init, c
   launch_reset_state(h->st, h->stream);
   launch_tf_to_bf(h->stage_x, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
   launch_tf_to_bf(h->stage_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream);
-  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
+  if (h->is_custom) launch_rollout_init_custom(h->cmod, h->st, h->cparams, h->st.x[1], h->stream);
+  else if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
   else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
   h->launches += 4;
   if (int32_t rc = check_launch(h, "upload_x0 kernels")) return rc;
@@ -477,7 +522,8 @@ static int32_t mpc_reinit(ilqr_handle* h, int shift) {
   launch_reset_state(h->st, h->stream);
   launch_tf_to_bf(h->plant, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
   launch_tf_to_bf(h->st.out_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream, shift);
-  if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
+  if (h->is_custom) launch_rollout_init_custom(h->cmod, h->st, h->cparams, h->st.x[1], h->stream);
+  else if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
   else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
   h->launches += 4;
   if (int32_t rc = check_launch(h, "mpc re-initialisation kernels")) return rc;
@@ -510,7 +556,8 @@ int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_ap
   const ilqr_problem& p = h->prob;
   CK(h, cudaSetDevice(h->device));
   if (int32_t rc = fit_loop(h, max_iter, tol, nullptr)) return rc;        // solution → out_x / out_u (by trajectory)
-  if (h->is_chain) launch_mpc_advance_chain(h->chain, h->floating, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
+  if (h->is_custom) launch_mpc_advance_custom(h->cmod, h->cparams, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
+  else if (h->is_chain) launch_mpc_advance_chain(h->chain, h->floating, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
   else launch_mpc_advance_two_link(h->mp, h->st.out_u, h->plant, h->u_applied, p.B, p.H, h->stream);
   h->launches += 1;
   if (u_applied) CK(h, cudaMemcpyAsync(u_applied, h->u_applied, sizeof(double) * p.m * p.B, cudaMemcpyDeviceToHost, h->stream));
@@ -522,11 +569,12 @@ int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_ap
 
 static int32_t backward_async(ilqr_handle* h) {
   if (!h->loaded) return fail(h, ILQR_ERR_STATE, "backward_pass before upload");
-  const bool split = !h->is_chain && h->st.nslots <= h->split_below;
+  const bool split = !h->is_chain && !h->is_custom && h->st.nslots <= h->split_below;
   if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][0], h->stream);
-  if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
+  if (h->is_custom) launch_bwd_custom(h->cmod, h->st, h->cparams, h->cp, h->stream);
+  else if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
   else if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->st.nslots <= h->coop_below, h->stream);
   else launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][1], h->stream);
@@ -537,10 +585,11 @@ static int32_t backward_async(ilqr_handle* h) {
 
 static int32_t forward_async(ilqr_handle* h) {
   if (!h->have_gains) return fail(h, ILQR_ERR_STATE, "forward_pass before backward_pass");
-  const bool fsplit = !h->is_chain && h->st.nslots > h->fwd_split_above;
+  const bool fsplit = !h->is_chain && !h->is_custom && h->st.nslots > h->fwd_split_above;
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][2], h->stream);
-  if (h->is_chain) launch_fwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
+  if (h->is_custom) launch_fwd_custom(h->cmod, h->st, h->cparams, h->cp, h->stream);
+  else if (h->is_chain) launch_fwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
   else if (fsplit) launch_fwd_split_two_link(h->st, h->mp, h->cp, h->stream);
   else launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][3], h->stream);

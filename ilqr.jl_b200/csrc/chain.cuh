@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dual.cuh"
 #include "fastmath.cuh"
 
 namespace ilqr {
@@ -48,24 +49,6 @@ template <int NQ, bool FL> struct ChainDims {
   static constexpr int JO = FL ? 6 : 0;     // index of the first joint in the velocity vector
   static constexpr int NV = NQ + JO, n = 2 * NV, m = NV;
 };
-
-// ---- value + one tangent ---------------------------------------------------------------------
-struct Dual {
-  double v, t;
-};
-__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.t + b.t}; }
-__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.t - b.t}; }
-__device__ __forceinline__ Dual operator-(Dual a) { return {-a.v, -a.t}; }
-__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return {a.v * b.v, fma(a.t, b.v, a.v * b.t)}; }
-__device__ __forceinline__ Dual operator*(double s, Dual a) { return {s * a.v, s * a.t}; }
-__device__ __forceinline__ Dual operator*(Dual a, double s) { return {s * a.v, s * a.t}; }
-__device__ __forceinline__ Dual operator+(Dual a, double s) { return {a.v + s, a.t}; }
-__device__ __forceinline__ Dual operator-(double s, Dual a) { return {s - a.v, -a.t}; }
-__device__ __forceinline__ Dual operator+(double s, Dual a) { return {s + a.v, a.t}; }
-
-template <class T> __device__ __forceinline__ T mk(double x);
-template <> __device__ __forceinline__ double mk<double>(double x) { return x; }
-template <> __device__ __forceinline__ Dual mk<Dual>(double x) { return {x, 0.0}; }
 
 template <class T> struct V3 {
   T x, y, z;

@@ -24,6 +24,7 @@
 #pragma once
 #include "chain.cuh"
 #include "internal.cuh"
+#include "warp_riccati.cuh"
 
 namespace ilqr {
 namespace chain_detail {
@@ -37,15 +38,9 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-template <int NQ, bool FL> struct BwdSmem {
+template <int NQ, bool FL> struct BwdSmem : RiccatiSmem<ChainDims<NQ, FL>::n, ChainDims<NQ, FL>::m> {
   using D = ChainDims<NQ, FL>;
   static constexpr int n = D::n, m = D::m, NV = D::NV;
-  double S[n * n];              // value Hessian, column-major
-  double AB[n * (n + m)];       // [A | B], column-major
-  double GH[m * (n + m + 1)];   // [G | H | g], unregularised
-  double Kd[m * (n + 1)];       // [K | δu]
-  double U[m * m];              // upper factor of H_reg (row-permuted)
-  double sv[n];
   double Mf[NV * NV];           // M(θ) then its LU factors (unit lower below, upper on/above the diagonal)
   double bias[NV];
   double invd[NV];              // 1 / diagonal of the upper factor
@@ -260,17 +255,7 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   const int cur = st.cur[s];
   const double* __restrict__ X = st.x[cur];
   const double* __restrict__ U = st.u[cur];
-  const bool isX = lane < n, isU = lane >= n && lane < n + m, isAff = lane == n + m;
-  const int ucol = lane - n;
-
-  // terminal expansion: final_cost_quadratization (src/backward_pass.jl:134-153)
-  if (isX) {
-    const double xN = X[((int64_t)H * S + s) * n + lane];
-#pragma unroll
-    for (int i = 0; i < n; ++i) sm.S[i + n * lane] = (i == lane) ? 2.0 * cost.w_xf[lane] : 0.0;
-    sm.sv[lane] = -2.0 * cost.w_xf[lane] * (cost.x_target[lane] - xN);
-  }
-  __syncwarp();
+  riccati_terminal<n, m>(sm, lane, lane < n ? X[((int64_t)H * S + s) * n + lane] : 0.0, cost);
 
   bool bad = false;
 #pragma unroll 1
@@ -291,122 +276,8 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
       for (int i = 0; i < n; ++i) ab[i] = 0.0;
     }
 
-    // ---- optimal_controller_param (src/backward_pass.jl:177-186) in column-owner form
-    if (lane < n + m) {
-#pragma unroll
-      for (int r = 0; r < n; ++r) sm.AB[r + n * lane] = ab[r];
-    }
-    __syncwarp();
-    double w[n];   // S·(own column of [A|B]); the affine lane carries s itself
-#pragma unroll
-    for (int i = 0; i < n; ++i) w[i] = isAff ? sm.sv[i] : 0.0;
-#pragma unroll
-    for (int r = 0; r < n; ++r) {
-      const double a = ab[r];
-#pragma unroll
-      for (int i = 0; i < n; ++i) w[i] = fma(sm.S[i + n * r], a, w[i]);
-    }
-    double gh[m];   // own column of [G | H | g] = Bᵀ·w (+ cost terms)
-#pragma unroll
-    for (int i = 0; i < m; ++i) {
-      double a = 0.0;
-#pragma unroll
-      for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * (n + i)], w[r], a);
-      if (isU && ucol == i) a += 2.0 * cost.w_u[i];      // 𝐑 = 2·diag(w_u)
-      if (isAff) a = fma(2.0 * cost.w_u[i], u[i], a);    // 𝐫 = 2·w_u·u
-      gh[i] = a;
-    }
-    if (lane < NC) {
-#pragma unroll
-      for (int i = 0; i < m; ++i) sm.GH[i + m * lane] = gh[i];
-    }
-
-    // ---- feedback_parameters (src/backward_pass.jl:207-218): (H + reg·I) \ [G | g], partial-pivot LU.
-    // Every lane eliminates its own column; the pivot column (owned by lane n + kk) is broadcast.
-    double col[m];
-#pragma unroll
-    for (int i = 0; i < m; ++i) col[i] = gh[i] + ((isU && ucol == i) ? st.reg : 0.0);
-#pragma unroll
-    for (int kk = 0; kk < m; ++kk) {
-      double pc[m];
-#pragma unroll
-      for (int i = kk; i < m; ++i) pc[i] = __shfl_sync(kFull, col[i], n + kk);
-      int p = kk; double best = fabs(pc[kk]);
-#pragma unroll
-      for (int i = kk + 1; i < m; ++i) { const double a = fabs(pc[i]); if (a > best) { best = a; p = i; } }
-#pragma unroll
-      for (int i = kk + 1; i < m; ++i)
-        if (p == i) { double t = col[kk]; col[kk] = col[i]; col[i] = t; t = pc[kk]; pc[kk] = pc[i]; pc[i] = t; }
-      const double rp = rcp_nr(pc[kk]);
-#pragma unroll
-      for (int i = kk + 1; i < m; ++i) col[i] = fma(-(pc[i] * rp), col[kk], col[i]);
-    }
-    if (isU) {
-#pragma unroll
-      for (int i = 0; i < m; ++i) sm.U[i + m * ucol] = col[i];
-    }
-    __syncwarp();
-    double kc[m];   // own column of [K | δu] = −(H_reg)⁻¹·(own column of [G | g])
-#pragma unroll
-    for (int i = m - 1; i >= 0; --i) {
-      double a = col[i];
-#pragma unroll
-      for (int j = i + 1; j < m; ++j) a = fma(sm.U[i + m * j], kc[j], a);   // kc already carries the minus sign
-      kc[i] = -a * rcp_nr(sm.U[i + m * i]);
-    }
-    const int kcolidx = isAff ? n : lane;
-    if (isX || isAff) {
-#pragma unroll
-      for (int i = 0; i < m; ++i) { sm.Kd[i + m * kcolidx] = kc[i]; bad |= isnan(kc[i]); }
-    }
-    __syncwarp();
-
-    // ---- step_back (src/backward_pass.jl:262-273): own column of 𝐒 (x lanes) or 𝐬 (affine lane),
-    //      𝐐 + Aᵀ(S·A) + Kᵀ(H·K + G) + Gᵀ·K  with the UNREGULARISED H
-    double nw[n];
-    {
-      double t[m];
-#pragma unroll
-      for (int i = 0; i < m; ++i) {
-        double a = gh[i];
-#pragma unroll
-        for (int l = 0; l < m; ++l) a = fma(sm.GH[i + m * (n + l)], kc[l], a);
-        t[i] = a;
-      }
-#pragma unroll
-      for (int i = 0; i < n; ++i) {
-        double a = 0.0;
-#pragma unroll
-        for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * i], w[r], a);
-#pragma unroll
-        for (int l = 0; l < m; ++l) a = fma(sm.Kd[l + m * i], t[l], a);
-#pragma unroll
-        for (int l = 0; l < m; ++l) a = fma(sm.GH[l + m * i], kc[l], a);
-        // immediate_cost_quadratization (src/backward_pass.jl:81-109) of the diagonal quadratic cost
-        if (isAff) a += -2.0 * cost.w_x[i] * (cost.x_target[i] - x[i]);
-        else if (lane == i) a += 2.0 * cost.w_x[i];
-        nw[i] = a;
-      }
-    }
-    __syncwarp();   // every lane has finished reading S and sv
-    if (isX) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) sm.S[i + n * lane] = nw[i];
-    } else if (isAff) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) sm.sv[i] = nw[i];
-    }
-    // gains out: K[k][slot][i + m·j], δuff[k][slot][i]
-    if (isX) {
-      double* kp = st.K + ((int64_t)k * S + s) * (m * n) + m * lane;
-#pragma unroll
-      for (int i = 0; i < m; ++i) kp[i] = kc[i];
-    } else if (isAff) {
-      double* dp = st.duff + ((int64_t)k * S + s) * m;
-#pragma unroll
-      for (int i = 0; i < m; ++i) dp[i] = kc[i];
-    }
-    __syncwarp();
+    bad |= riccati_column_step<n, m>(sm, lane, ab, x, u, cost, st.reg, st.K + ((int64_t)k * S + s) * (m * n),
+                                     st.duff + ((int64_t)k * S + s) * m);
   }
   if (__any_sync(kFull, bad) && lane == 0) st.status[s] |= ST_NAN_GAINS;
 }

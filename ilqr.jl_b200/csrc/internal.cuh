@@ -4,60 +4,10 @@
 #include <stdint.h>
 
 #include "chain.cuh"
+#include "devstate.cuh"
 #include "two_link.cuh"
 
 namespace ilqr {
-
-constexpr int kMaxN = 16, kMaxM = 8;
-
-// Diagonal-weighted quadratic cost of ilqr_problem.
-struct CostP {
-  double x_target[kMaxN], w_x[kMaxN], w_u[kMaxM], w_xf[kMaxN];
-};
-
-// Device-resident solver state in the [k][slot][component] layout used by the
-// lane-per-trajectory kernels: element (k, c) of trajectory-slot s lives at
-// (k*S + s)*ncomp + c, so the slab a warp (32 consecutive slots) needs for one time
-// step is one contiguous run (a single TMA bulk copy) and a lane's own components
-// are one 128-bit-vectorisable group.
-struct DevState {
-  double* x[2];      // iterate ping-pong, [N][S][n]
-  double* u[2];      // [H][S][m]
-  double* xtraj;     // [N][S][n] or nullptr (= zeros)
-  double* duff;      // [H][S][m]
-  double* K;         // [H][S][m*n], component index i + m*j
-  double* prev_cost; // [S]
-  double* new_cost;
-  double* alpha;
-  double* du2;
-  double* cost_trace;   // [trace_iters][S] (nullable)
-  double* alpha_trace;
-  double* du2_trace;
-  int32_t* status;   // [S]
-  int32_t* iters;
-  int32_t* active;
-  int32_t* cur;      // which of x[2]/u[2] holds the slot's current iterate
-  int32_t* bar;      // which holds the last forward-pass candidate
-  int32_t* traj;     // [S] original trajectory index living in this slot
-  int32_t* n_active; // device counter accumulated by commit (reset by its last block)
-  uint32_t* blocks_done;     // commit's block ticket (last block publishes the count)
-  int32_t* n_active_host;    // device alias of a MAPPED pinned host int array: the published counts
-  int32_t pub_slot;          // which entry of n_active_host this commit publishes to (iterations run in bursts)
-  // per-TRAJECTORY result mirrors (index = original trajectory), written when a slot retires / is flushed
-  double* r_prev_cost; double* r_new_cost; double* r_alpha; double* r_du2;
-  int32_t* r_status; int32_t* r_iters; int32_t* r_active;
-  double* out_x;     // [B][n*N] boundary layout: final iterate of retired trajectories
-  double* out_u;     // [B][m*H]
-  // line-search retry list: slots whose α = 1 candidate was rejected (two-kernel forward pass)
-  int32_t* retry_list; int32_t* n_retry;
-  // compaction work lists
-  int32_t* retire_list; int32_t* move_src; int32_t* move_dst; int32_t* n_move;
-  int64_t S;         // slot stride (B rounded up to 32)
-  int32_t nslots;    // live slots: [0, nslots) (shrinks as finished trajectories are retired)
-  int32_t B;         // trajectories
-  int32_t H, n, m, n_alpha, trace_iters;
-  double reg;
-};
 
 // kernels_lpt.cu — lane-per-trajectory (throughput) mapping
 void init_kernel_attributes();   // opt-in dynamic shared memory sizes; call once per process/device
@@ -95,6 +45,23 @@ void launch_rollout_init_chain(const DevState& st, const ChainP& cp, bool floati
                                cudaStream_t s);
 void launch_mpc_advance_chain(const ChainP& cp, bool floating, const double* out_u, double* plant, double* u_applied, int B,
                               int H, cudaStream_t s);
+
+// custom.cu — user-defined dynamics compiled at run time with NVRTC (custom_kernels.cuh)
+struct CustomModule {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t bwd = nullptr, fwd = nullptr, rollout = nullptr, advance = nullptr;
+};
+}  // namespace ilqr
+#include <string>
+#include <vector>
+namespace ilqr {
+int32_t custom_compile(const char* user_src, int n, int m, const char* arch, std::vector<char>& cubin, std::string& log);
+int32_t custom_get(const char* user_src, int n, int m, int device, CustomModule* out, std::string& err);
+void launch_bwd_custom(const CustomModule& mod, const DevState& st, const CustomP& mp, const CostP& cost, cudaStream_t s);
+void launch_fwd_custom(const CustomModule& mod, const DevState& st, const CustomP& mp, const CostP& cost, cudaStream_t s);
+void launch_rollout_init_custom(const CustomModule& mod, const DevState& st, const CustomP& mp, const double* d_x0, cudaStream_t s);
+void launch_mpc_advance_custom(const CustomModule& mod, const CustomP& mp, const double* out_u, double* plant, double* u_applied,
+                               int B, int H, cudaStream_t s);
 
 // layout.cu — boundary (Julia, time-fastest "TF") <-> BF transposes
 // TF: src[t*(ncomp*T) + c*T + k]   BF: dst[(k*ncomp + c)*S + s]

@@ -1,0 +1,162 @@
+// warp_riccati.cuh — one Riccati step of backward_pass (src/backward_pass.jl:339-351) for ONE trajectory on ONE warp,
+// in column-owner form: lane d < n owns column d of every n-column block, lanes n … n+m-1 the control columns, lane
+// n+m the affine column (g, δu, s).  What other lanes need is published in shared memory and read back as broadcast
+// columns.  Shared by the rigid-body kernels (chain_kernels.cuh) and the NVRTC-compiled user models
+// (custom_kernels.cuh).  Costs are the diagonal quadratics of CostP.
+#pragma once
+#include "devstate.cuh"
+#include "fastmath.cuh"
+
+namespace ilqr {
+
+template <int n, int m> struct RiccatiSmem {
+  double S[n * n];              // value Hessian, column-major
+  double AB[n * (n + m)];       // [A | B], column-major
+  double GH[m * (n + m + 1)];   // [G | H | g], unregularised
+  double Kd[m * (n + 1)];       // [K | δu]
+  double U[m * m];              // upper factor of H_reg (row-permuted)
+  double sv[n];
+};
+
+// terminal expansion: final_cost_quadratization (src/backward_pass.jl:134-153); xN = component `lane` of x_N
+template <int n, int m>
+__device__ __forceinline__ void riccati_terminal(RiccatiSmem<n, m>& sm, int lane, double xN, const CostP& cost) {
+  if (lane < n) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) sm.S[i + n * lane] = (i == lane) ? 2.0 * cost.w_xf[lane] : 0.0;
+    sm.sv[lane] = -2.0 * cost.w_xf[lane] * (cost.x_target[lane] - xN);
+  }
+  __syncwarp();
+}
+
+// ab: this lane's column of [A | B] (zero on lanes ≥ n + m); x, u: the step's linearisation point (every lane).
+// Writes K[:, lane] / δu to Kout (m·n doubles, index i + m·j) / dout (m doubles).  Returns true if a gain is NaN.
+template <int n, int m>
+__device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int lane, const double (&ab)[n], const double (&x)[n],
+                                                    const double (&u)[m], const CostP& cost, double reg, double* Kout,
+                                                    double* dout) {
+  constexpr int NC = n + m + 1;
+  constexpr unsigned kFull = 0xffffffffu;
+  const bool isX = lane < n, isU = lane >= n && lane < n + m, isAff = lane == n + m;
+  const int ucol = lane - n;
+  bool bad = false;
+  // ---- optimal_controller_param (src/backward_pass.jl:177-186) in column-owner form
+  if (lane < n + m) {
+#pragma unroll
+    for (int r = 0; r < n; ++r) sm.AB[r + n * lane] = ab[r];
+  }
+  __syncwarp();
+  double w[n];   // S·(own column of [A|B]); the affine lane carries s itself
+#pragma unroll
+  for (int i = 0; i < n; ++i) w[i] = isAff ? sm.sv[i] : 0.0;
+#pragma unroll
+  for (int r = 0; r < n; ++r) {
+    const double a = ab[r];
+#pragma unroll
+    for (int i = 0; i < n; ++i) w[i] = fma(sm.S[i + n * r], a, w[i]);
+  }
+  double gh[m];   // own column of [G | H | g] = Bᵀ·w (+ cost terms)
+#pragma unroll
+  for (int i = 0; i < m; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * (n + i)], w[r], a);
+    if (isU && ucol == i) a += 2.0 * cost.w_u[i];      // 𝐑 = 2·diag(w_u)
+    if (isAff) a = fma(2.0 * cost.w_u[i], u[i], a);    // 𝐫 = 2·w_u·u
+    gh[i] = a;
+  }
+  if (lane < NC) {
+#pragma unroll
+    for (int i = 0; i < m; ++i) sm.GH[i + m * lane] = gh[i];
+  }
+
+  // ---- feedback_parameters (src/backward_pass.jl:207-218): (H + reg·I) \ [G | g], partial-pivot LU.
+  // Every lane eliminates its own column; the pivot column (owned by lane n + kk) is broadcast.
+  double col[m];
+#pragma unroll
+  for (int i = 0; i < m; ++i) col[i] = gh[i] + ((isU && ucol == i) ? reg : 0.0);
+#pragma unroll
+  for (int kk = 0; kk < m; ++kk) {
+    double pc[m];
+#pragma unroll
+    for (int i = kk; i < m; ++i) pc[i] = __shfl_sync(kFull, col[i], n + kk);
+    int p = kk; double best = fabs(pc[kk]);
+#pragma unroll
+    for (int i = kk + 1; i < m; ++i) { const double a = fabs(pc[i]); if (a > best) { best = a; p = i; } }
+#pragma unroll
+    for (int i = kk + 1; i < m; ++i)
+      if (p == i) { double t = col[kk]; col[kk] = col[i]; col[i] = t; t = pc[kk]; pc[kk] = pc[i]; pc[i] = t; }
+    const double rp = rcp_nr(pc[kk]);
+#pragma unroll
+    for (int i = kk + 1; i < m; ++i) col[i] = fma(-(pc[i] * rp), col[kk], col[i]);
+  }
+  if (isU) {
+#pragma unroll
+    for (int i = 0; i < m; ++i) sm.U[i + m * ucol] = col[i];
+  }
+  __syncwarp();
+  double kc[m];   // own column of [K | δu] = −(H_reg)⁻¹·(own column of [G | g])
+#pragma unroll
+  for (int i = m - 1; i >= 0; --i) {
+    double a = col[i];
+#pragma unroll
+    for (int j = i + 1; j < m; ++j) a = fma(sm.U[i + m * j], kc[j], a);   // kc already carries the minus sign
+    kc[i] = -a * rcp_nr(sm.U[i + m * i]);
+  }
+  const int kcolidx = isAff ? n : lane;
+  if (isX || isAff) {
+#pragma unroll
+    for (int i = 0; i < m; ++i) { sm.Kd[i + m * kcolidx] = kc[i]; bad |= isnan(kc[i]); }
+  }
+  __syncwarp();
+
+  // ---- step_back (src/backward_pass.jl:262-273): own column of 𝐒 (x lanes) or 𝐬 (affine lane),
+  //      𝐐 + Aᵀ(S·A) + Kᵀ(H·K + G) + Gᵀ·K  with the UNREGULARISED H
+  double nw[n];
+  {
+    double t[m];
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      double a = gh[i];
+#pragma unroll
+      for (int l = 0; l < m; ++l) a = fma(sm.GH[i + m * (n + l)], kc[l], a);
+      t[i] = a;
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      double a = 0.0;
+#pragma unroll
+      for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * i], w[r], a);
+#pragma unroll
+      for (int l = 0; l < m; ++l) a = fma(sm.Kd[l + m * i], t[l], a);
+#pragma unroll
+      for (int l = 0; l < m; ++l) a = fma(sm.GH[l + m * i], kc[l], a);
+      // immediate_cost_quadratization (src/backward_pass.jl:81-109) of the diagonal quadratic cost
+      if (isAff) a += -2.0 * cost.w_x[i] * (cost.x_target[i] - x[i]);
+      else if (lane == i) a += 2.0 * cost.w_x[i];
+      nw[i] = a;
+    }
+  }
+  __syncwarp();   // every lane has finished reading S and sv
+  if (isX) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) sm.S[i + n * lane] = nw[i];
+  } else if (isAff) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) sm.sv[i] = nw[i];
+  }
+  // gains out: K[k][slot][i + m·j], δuff[k][slot][i]
+  if (isX) {
+    double* kp = Kout + m * lane;
+#pragma unroll
+    for (int i = 0; i < m; ++i) kp[i] = kc[i];
+  } else if (isAff) {
+    double* dp = dout;
+#pragma unroll
+    for (int i = 0; i < m; ++i) dp[i] = kc[i];
+  }
+  __syncwarp();
+  return bad;
+}
+
+}  // namespace ilqr

@@ -87,6 +87,47 @@ def serial_chain_problem(joints, H, B=1, gravity=(0.0, 0.0, 0.0), x_target=None,
     return p
 
 
+_custom_sources = []   # keeps the source bytes of custom problems alive (ilqr_problem holds a raw pointer)
+
+
+def custom_problem(dynamics_src, n, m, H, B=1, dt=0.01, params=(), x_target=None, w_x=None, w_u=None, w_xf=None, n_alpha=32,
+                   trace_iters=0, device=0, reg=None):
+    """Any dynamics (the reference accepts any Julia function as `dynamicsf`, src/forward_pass.jl:148-153): CUDA C++ source
+    defining  template <class T> __device__ void ilqr_dynamics(const T* x, const T* u, const double* p, T* xdot);
+    compiled at run time (NVRTC) into the library's kernels, RK4-discretised with step dt and differentiated with dual
+    numbers.  Costs are the diagonal quadratics l = Σ w_x (x* − x)² + Σ w_u u², lf = Σ w_xf (x* − x)²."""
+    lib = _abi.load_library()
+    src = dynamics_src.encode() if isinstance(dynamics_src, str) else bytes(dynamics_src)
+    _custom_sources.append(src)
+    pr = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
+    p = Problem()
+    rc = lib.ilqr_problem_custom(ctypes.byref(p), int(n), int(m), int(H), int(B), float(dt), src,
+                                 pr.ctypes.data if pr.size else None, int(pr.size))
+    if rc != 0:
+        raise IlqrError("ilqr_problem_custom failed (n <= 16, m <= 8, <= 32 params)")
+    p.n_alpha = n_alpha
+    p.trace_iters = trace_iters
+    p.device = device
+    if reg is not None:
+        p.reg = reg
+    for name, arr, cnt in (("x_target", x_target, n), ("w_x", w_x, n), ("w_u", w_u, m), ("w_xf", w_xf, n)):
+        if arr is not None:
+            arr = np.asarray(arr, dtype=np.float64)
+            if arr.shape != (cnt,):
+                raise ValueError("%s must have %d entries" % (name, cnt))
+            for i in range(cnt):
+                getattr(p, name)[i] = float(arr[i])
+    return p
+
+
+def custom_compile_check(dynamics_src, n, m):
+    """(ok, compiler log) for a dynamics snippet; needs libnvrtc, no GPU."""
+    lib = _abi.load_library()
+    buf = ctypes.create_string_buffer(1 << 16)
+    rc = lib.ilqr_custom_compile_check(dynamics_src.encode(), int(n), int(m), buf, len(buf))
+    return rc == 0, buf.value.decode(errors="replace")
+
+
 def load_urdf(path):
     """Mini URDF loader for what the reference feeds parse_urdf (test/urdf/*.urdf, RBD_helper_functions.jl:6-7):
     a serial chain of revolute/continuous joints.  Returns (joints[(nq, 20)], base_inertial) where base_inertial =

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define ILQR_ABI_VERSION 3
+#define ILQR_ABI_VERSION 4
 #define ILQR_MAX_N 16
 #define ILQR_MAX_M 8
 #define ILQR_MAX_JOINTS 8
@@ -61,7 +61,15 @@ enum ilqr_model {
    * u = [torque(3); force(3)] on the base in base coordinates, then joint torques, m = 6 + nq.
    * v̇ = M \ (u − bias) for 𝑣 = [ω; v; θ̇] (base twist in the base frame), q̇ = [pdot_from_w(p, ω); v; θ̇] (:66).
    * Zero gravity only (as the reference).  chain row nq carries the base link's mass / COM / inertia.  nq in {1, 2}. */
-  ILQR_MODEL_FLOATING_CHAIN = 3
+  ILQR_MODEL_FLOATING_CHAIN = 3,
+  /* Any dynamics, as the reference accepts any Julia function for `dynamicsf` (src/forward_pass.jl:148-153): the caller
+   * supplies CUDA C++ source (ilqr_problem.custom_src) that defines
+   *     template <class T> __device__ void ilqr_dynamics(const T* x, const T* u, const double* p, T* xdot);
+   * (ẋ = f(x, u; p), p = model_params; T = double or ilqr::Dual — value + one tangent, with + − * / sin cos exp log
+   * sqrt overloaded).  The library compiles it at run time (NVRTC) into its warp-per-trajectory kernels, wraps it in
+   * the RK4 step of the reference's plugins and differentiates it with dual numbers (one tangent direction per lane),
+   * which is what ForwardDiff does to the Julia callback.  n <= 16, m <= 8; costs are the diagonal quadratics. */
+  ILQR_MODEL_CUSTOM = 4
 };
 
 /* per-trajectory status bits (int32) */
@@ -143,6 +151,8 @@ typedef struct ilqr_problem {
   int32_t reserved0;
   double gravity[3];      /* gravity acceleration in the base frame (RBD_helper_functions.jl:7: zero) */
   double chain[(ILQR_MAX_JOINTS + 1) * ILQR_CHAIN_STRIDE];   /* + 1: the base link of a floating mechanism */
+  /* ILQR_MODEL_CUSTOM only: NUL-terminated CUDA C++ source defining ilqr_dynamics (copied by ilqr_create) */
+  const char* custom_src;
 } ilqr_problem;
 
 typedef struct ilqr_handle ilqr_handle;
@@ -161,6 +171,15 @@ int32_t ilqr_problem_serial_chain(ilqr_problem* p, int32_t nq, const double* joi
 /* Floating-base variant: base_link = one row of ILQR_CHAIN_STRIDE doubles (only mass, COM, inertia are read). */
 int32_t ilqr_problem_floating_chain(ilqr_problem* p, int32_t nq, const double* joints, const double* base_link, int32_t H,
                                     int32_t B);
+
+/* User-defined dynamics: fills `p` for ILQR_MODEL_CUSTOM (dt, reg = 0.01, n_alpha = 32, zero cost weights);
+ * params (n_params <= 32 doubles, nullable) are handed to ilqr_dynamics as `p`.  dynamics_src must stay valid until
+ * ilqr_create returns. */
+int32_t ilqr_problem_custom(ilqr_problem* p, int32_t n, int32_t m, int32_t H, int32_t B, double dt, const char* dynamics_src,
+                            const double* params, int32_t n_params);
+/* Compile-only check of a dynamics snippet for sizes (n, m); needs libnvrtc but no GPU.  The compiler log (warnings
+ * and errors) is copied to log[0..log_len) when log != NULL.  Returns 0 if it compiles. */
+int32_t ilqr_custom_compile_check(const char* dynamics_src, int32_t n, int32_t m, char* log, int32_t log_len);
 
 int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out);
 int32_t ilqr_destroy(ilqr_handle* h);

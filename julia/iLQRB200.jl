@@ -31,6 +31,7 @@ struct Problem
     reserved0::Int32
     gravity::NTuple{3,Float64}
     chain::NTuple{180,Float64}     # (ILQR_MAX_JOINTS + 1) × ILQR_CHAIN_STRIDE
+    custom_src::Cstring            # ILQR_MODEL_CUSTOM: CUDA C++ source of ilqr_dynamics
 end
 
 const X, U, XBAR, UBAR, DUFF, K, NEW_COST, PREV_COST, ALPHA, DU2 = Int32.(0:9)

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_problem_struct_layout_and_two_link_constants():
     from oracle import oracle_py as orc
     p = ilqr_b200.two_link_problem(200, 7)
-    assert ctypes.sizeof(_abi.Problem) == 10 * 4 + 2 * 8 + (32 + 16 + 16 + 8 + 16) * 8 + 2 * 4 + (3 + 9 * 20) * 8
+    assert ctypes.sizeof(_abi.Problem) == 10 * 4 + 2 * 8 + (32 + 16 + 16 + 8 + 16) * 8 + 2 * 4 + (3 + 9 * 20) * 8 + 8
     assert (p.n, p.m, p.H, p.B, p.n_alpha) == (4, 2, 200, 7, 32)
     c = orc.constants()
     assert p.model_params[0] == c["alpha"] and p.model_params[1] == c["beta"] and p.model_params[2] == c["delta"]
