@@ -190,6 +190,34 @@ def aux_chain(device, cpu_too):
     return out
 
 
+def aux_floating(device):
+    """BASELINE configs[2] on one GPU: test/RBD_2_link_example as written (2Dof_arm.urdf on a floating base, n = 16, m = 8,
+    the reference's weights and target pose), B = 16,384, H = 300.  The reference's own script runs this problem with
+    max_iter = 1e6; here 10 batch iterations are timed (trajectory-iterations/s), parity is in tests/test_gpu_chain.py."""
+    import ilqr_b200
+    from ilqr_b200 import _abi
+    Bf, Hf, iters = 16384, 300, 10
+    joints = np.load(os.path.join(ROOT, "tests", "golden", "2dof_chain.npy"))
+    base = (30.0, [0.0, 0.0, 0.0], [50.0, 0.0, 0.0, 50.0, 0.0, 50.0])                 # 2Dof_arm.urdf base_link
+    target = np.concatenate([[0, 0, 0, 5, 1, 2, 1, .3], np.zeros(8)])                 # animate_RBD_2_link.jl:10
+    w_x = np.concatenate([10.0 * np.array([100, 100, 100, 1, 1, 1, 10, 10.]), np.zeros(8)])
+    w_u = np.array([1, 1, 1, 100, 100, 100, 10, 10.])
+    w_xf = np.concatenate([1e5 * np.array([100, 100, 100, 1000, 1000, 1000, 10, 10.]), np.zeros(8)])
+    prob = ilqr_b200.serial_chain_problem(joints, Hf, Bf, base=base, x_target=target, w_x=w_x, w_u=w_u, w_xf=w_xf, device=device)
+    rng = np.random.default_rng(0)
+    x0 = np.asfortranarray(np.tile(np.concatenate([[0, 0, 1.0], [.5, .75, 1.0], [0, 0], np.zeros(8)])[:, None], (1, Bf)))
+    x0[3:8, :] += rng.uniform(-0.1, 0.1, (5, Bf))
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload_x0(x0, np.zeros((Hf, 8, Bf), order="F"))
+        t0 = time.perf_counter(); s.fit(iters, TOL); dt = time.perf_counter() - t0
+        prof = s.profile()
+        cost = s.download(_abi.PREV_COST)
+    return {"workload": "configs[2]: floating-base 2Dof_arm.urdf (n=16, m=8), B=16384, H=300, fp64, 1 GPU, %d batch iterations" % iters,
+            "value": prof["traj_iters"] / dt, "unit": "trajectory-iterations/s", "ms_per_batch_iteration": 1e3 * dt / iters,
+            "bwd_chain_ms": prof["bwd_ms"] / max(1, prof["bwd_launches"]), "fwd_chain_ms": prof["fwd_ms"] / max(1, prof["fwd_launches"]),
+            "mean_cost_after": float(np.mean(cost))}
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -413,9 +441,9 @@ def run_b200(args):
     other = None
     if rank == 0 and world == 1 and not args.no_aux and B == B_PER_GPU:
         try:
-            other = {"configs[3]": aux_chain(local, not args.no_cpu_baseline)}
+            other = {"configs[3]": aux_chain(local, not args.no_cpu_baseline), "configs[2]": aux_floating(local)}
         except Exception as e:   # a side measurement must never take the headline line down
-            other = {"configs[3]": {"error": repr(e)}}
+            other = {"error": repr(e)}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:

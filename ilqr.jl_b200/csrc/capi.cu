@@ -757,15 +757,16 @@ int32_t ilqr_stream_solve_device(ilqr_handle* h, int64_t n_total, const double* 
   for (auto& v : h->prof) v = 0.0;
   int parity = 0;
   int64_t next = 0, iters_run = 0;
-  auto admit = [&](int slot0) {
+  auto admit = [&](int slot0) -> int {
     const int n_new = (int)std::min<int64_t>((int64_t)p.B - slot0, n_total - next);
-    if (n_new <= 0) return;
+    if (n_new <= 0) return 0;
     launch_tf_to_bf(d_x_init + (size_t)next * N * n, st.x[parity] + (size_t)slot0 * n, nullptr, n_new, (int)N, (int)n, S, h->stream);
     launch_tf_to_bf(d_u_init + (size_t)next * H * m, st.u[parity] + (size_t)slot0 * m, nullptr, n_new, (int)H, (int)m, S, h->stream);
     launch_admit(st, slot0, n_new, next, parity, h->stream);
     h->launches += 3;
     st.nslots = slot0 + n_new;
     next += n_new;
+    return n_new;
   };
   st.nslots = 0;
   admit(0);
@@ -785,15 +786,14 @@ int32_t ilqr_stream_solve_device(ilqr_handle* h, int64_t n_total, const double* 
     parity ^= 1;
     const int32_t finished = st.nslots - na;
     const bool more = next < n_total;
+    int admitted = 0;
     if (finished > 0 && (na == 0 || (more ? finished >= refill_min : (finished >= 32 && finished * 16 >= st.nslots)))) {
       launch_compact(st, na, h->stream);
       h->launches += 3;
       st.nslots = na;
-      if (more) admit(na);
+      if (more) admitted = admit(na);
     }
-    h->n_active_host = na + (st.nslots - na);
-    if (st.nslots > na) h->n_active_host = st.nslots;   // freshly admitted slots are active
-    else h->n_active_host = na;
+    h->n_active_host = na + admitted;   // live trajectories at the next launch
   }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { restore(); return fail(h, ILQR_ERR_CUDA, "stream solve: retire failure"); }
   if (batch_iterations) *batch_iterations = iters_run;

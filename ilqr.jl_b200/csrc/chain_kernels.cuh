@@ -31,7 +31,9 @@ namespace chain_detail {
 
 constexpr int kCW = 4;   // warps (= trajectories) per block in bwd_chain
 #ifndef ILQR_CHAIN_MIN_BLOCKS
-#define ILQR_CHAIN_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for
+#define ILQR_CHAIN_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for.  3 (168 registers, 12 warps/SM;
+                                  // the scratch fits: 17.5 KB per warp at nq = 7) measured 3 % faster on configs[3] and 4 %
+                                  // slower on configs[2]: the kernel is FP64-issue bound, not latency bound
 #endif
 constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2;
 constexpr unsigned kFull = 0xffffffffu;
@@ -45,38 +47,44 @@ template <int NQ, bool FL> struct BwdSmem : RiccatiSmem<ChainDims<NQ, FL>::n, Ch
   double bias[NV];
   double invd[NV];              // 1 / diagonal of the upper factor
   // inverse-dynamics scratch.  The link loops are rolled (the unrolled version was 8.4 k instructions and
-  // instruction-fetch bound), so per-link state is indexed dynamically and lives here, [item][lane]:
-  double fn[NQ * 6 * 32];       // per lane: f_i, n_i (primal pass) or their tangents (dual pass)
+  // instruction-fetch bound), so per-link state is indexed dynamically and lives here, [item][lane] with a lane
+  // stride of LS = n + m + 1 (only the column-owner lanes keep state; the others neither store nor matter):
+  static constexpr int LS = n + m + 1;
+  double fn[NQ * 6 * LS];       // per lane: f_i, n_i (primal pass) or their tangents (dual pass)
   double fnv[NQ * 6];           // dual pass: the values of f_i, n_i (the same on every lane)
-  double tng[2 * NV * 32];      // per lane, per velocity coordinate j: (𝑣_j, 𝑣̇_j) in the primal pass, (δq_j, δ𝑣_j) in the dual pass
-  double tau[NV * 32];          // per lane: generalised forces (primal pass) or their tangents (dual pass)
+  double tng[2 * NV * LS];      // per lane, per velocity coordinate j: (𝑣_j, 𝑣̇_j) in the primal pass, (δq_j, δ𝑣_j) in the dual
+                                // pass; a pass leaves its output — generalised force j (or its tangent) — in slot 2j+1, which
+                                // the recursion has finished reading by then
   double qv[2 * NV];            // stage point (configuration, velocity)
   double sc[2 * NQ];            // sin θ_i, cos θ_i
   double vd[NV];                // 𝑣̇ at the stage point
 };
 
 // Per-pass views of the scratch: what coordinate j feeds the recursion and where link i's wrench is parked.
+// l = min(lane, LS − 1); lanes ≥ LS read lane LS − 1's state and store nothing (on = false).
 template <int NQ, bool FL> struct PrimalIO {
-  BwdSmem<NQ, FL>& sm; int lane;
-  static constexpr int JO = ChainDims<NQ, FL>::JO;
+  BwdSmem<NQ, FL>& sm; int l; bool on;
+  static constexpr int JO = ChainDims<NQ, FL>::JO, LS = BwdSmem<NQ, FL>::LS;
   __device__ __forceinline__ double s(int i) const { return sm.sc[2 * i]; }
   __device__ __forceinline__ double c(int i) const { return sm.sc[2 * i + 1]; }
-  __device__ __forceinline__ double vel(int j) const { return sm.tng[(2 * j) * 32 + lane]; }
-  __device__ __forceinline__ double acc(int j) const { return sm.tng[(2 * j + 1) * 32 + lane]; }
-  __device__ __forceinline__ void put(int i, int k, double v) const { sm.fn[(i * 6 + k) * 32 + lane] = v; }
-  __device__ __forceinline__ double get(int i, int k) const { return sm.fn[(i * 6 + k) * 32 + lane]; }
-  __device__ __forceinline__ void out(int j, double v) const { sm.tau[j * 32 + lane] = v; }
+  __device__ __forceinline__ double vel(int j) const { return sm.tng[(2 * j) * LS + l]; }
+  __device__ __forceinline__ double acc(int j) const { return sm.tng[(2 * j + 1) * LS + l]; }
+  __device__ __forceinline__ void put(int i, int k, double v) const { if (on) sm.fn[(i * 6 + k) * LS + l] = v; }
+  __device__ __forceinline__ double get(int i, int k) const { return sm.fn[(i * 6 + k) * LS + l]; }
+  __device__ __forceinline__ void out(int j, double v) const { if (on) sm.tng[(2 * j + 1) * LS + l] = v; }
 };
 template <int NQ, bool FL> struct DualIO {
-  BwdSmem<NQ, FL>& sm; int lane;
-  static constexpr int JO = ChainDims<NQ, FL>::JO, NV = ChainDims<NQ, FL>::NV;
-  __device__ __forceinline__ Dual s(int i) const { return {sm.sc[2 * i], sm.sc[2 * i + 1] * sm.tng[(2 * (JO + i)) * 32 + lane]}; }
-  __device__ __forceinline__ Dual c(int i) const { return {sm.sc[2 * i + 1], -sm.sc[2 * i] * sm.tng[(2 * (JO + i)) * 32 + lane]}; }
-  __device__ __forceinline__ Dual vel(int j) const { return {sm.qv[NV + j], sm.tng[(2 * j + 1) * 32 + lane]}; }
+  BwdSmem<NQ, FL>& sm; int l; bool on;
+  static constexpr int JO = ChainDims<NQ, FL>::JO, NV = ChainDims<NQ, FL>::NV, LS = BwdSmem<NQ, FL>::LS;
+  __device__ __forceinline__ Dual s(int i) const { return {sm.sc[2 * i], sm.sc[2 * i + 1] * sm.tng[(2 * (JO + i)) * LS + l]}; }
+  __device__ __forceinline__ Dual c(int i) const { return {sm.sc[2 * i + 1], -sm.sc[2 * i] * sm.tng[(2 * (JO + i)) * LS + l]}; }
+  __device__ __forceinline__ Dual vel(int j) const { return {sm.qv[NV + j], sm.tng[(2 * j + 1) * LS + l]}; }
   __device__ __forceinline__ Dual acc(int j) const { return {sm.vd[j], 0.0}; }
-  __device__ __forceinline__ void put(int i, int k, Dual v) const { sm.fnv[i * 6 + k] = v.v; sm.fn[(i * 6 + k) * 32 + lane] = v.t; }
-  __device__ __forceinline__ Dual get(int i, int k) const { return {sm.fnv[i * 6 + k], sm.fn[(i * 6 + k) * 32 + lane]}; }
-  __device__ __forceinline__ void out(int j, Dual v) const { sm.tau[j * 32 + lane] = v.t; }
+  __device__ __forceinline__ void put(int i, int k, Dual v) const {
+    if (on) { sm.fnv[i * 6 + k] = v.v; sm.fn[(i * 6 + k) * LS + l] = v.t; }
+  }
+  __device__ __forceinline__ Dual get(int i, int k) const { return {sm.fnv[i * 6 + k], sm.fn[(i * 6 + k) * LS + l]}; }
+  __device__ __forceinline__ void out(int j, Dual v) const { if (on) sm.tng[(2 * j + 1) * LS + l] = v.t; }
 };
 
 // chain_rnea (chain.cuh) with rolled link loops over shared-memory state; same arithmetic.
@@ -140,7 +148,9 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
                                             const double (&dv)[ChainDims<NQ, FL>::NV], int udir,
                                             double (&cdot)[ChainDims<NQ, FL>::NV], double (&dcdot)[ChainDims<NQ, FL>::NV],
                                             double (&vdot)[ChainDims<NQ, FL>::NV], double (&dvdot)[ChainDims<NQ, FL>::NV]) {
-  constexpr int NV = ChainDims<NQ, FL>::NV, JO = ChainDims<NQ, FL>::JO;
+  constexpr int NV = ChainDims<NQ, FL>::NV, JO = ChainDims<NQ, FL>::JO, LS = BwdSmem<NQ, FL>::LS;
+  const bool on = lane < LS;
+  const int l = on ? lane : LS - 1;
   // sin/cos of the joint angles: lane i evaluates joint i
   double qi = cfg[JO];
 #pragma unroll
@@ -151,20 +161,22 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
   if (lane < NQ) { sm.sc[2 * lane] = si; sm.sc[2 * lane + 1] = ci; }
   // lane j < NV: column j of M = ID(θ, 0, e_j) without gravity; the other lanes: bias = ID(θ, 𝑣, 0)
   const bool col = lane < NV;
+  if (on) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    sm.tng[(2 * j) * 32 + lane] = col ? 0.0 : v[j];
-    sm.tng[(2 * j + 1) * 32 + lane] = (lane == j) ? 1.0 : 0.0;
-    sm.qv[NV + j] = v[j];   // every lane holds the same stage point
+    for (int j = 0; j < NV; ++j) {
+      sm.tng[(2 * j) * LS + l] = col ? 0.0 : v[j];
+      sm.tng[(2 * j + 1) * LS + l] = (lane == j) ? 1.0 : 0.0;
+      sm.qv[NV + j] = v[j];   // every lane holds the same stage point
+    }
   }
   __syncwarp();
-  warp_rnea<double, PrimalIO<NQ, FL>, NQ, FL>(cp, PrimalIO<NQ, FL>{sm, lane}, col ? 0.0 : 1.0);
+  warp_rnea<double, PrimalIO<NQ, FL>, NQ, FL>(cp, PrimalIO<NQ, FL>{sm, l, on}, col ? 0.0 : 1.0);
   if (col) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) sm.Mf[i + NV * lane] = sm.tau[i * 32 + lane];
+    for (int i = 0; i < NV; ++i) sm.Mf[i + NV * lane] = sm.tng[(2 * i + 1) * LS + l];
   } else if (lane == NV) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) sm.bias[i] = sm.tau[i * 32 + lane];
+    for (int i = 0; i < NV; ++i) sm.bias[i] = sm.tng[(2 * i + 1) * LS + l];
   }
   __syncwarp();
   // factor M (symmetric positive definite ⇒ no pivoting): lane r eliminates row r
@@ -184,16 +196,18 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
   for (int i = 0; i < NV; ++i) vdot[i] = u[i] - sm.bias[i];
   m_solve<NV>(sm.Mf, sm.invd, vdot);
   // directional derivative of the inverse dynamics along this lane's tangent
+  if (on) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    sm.tng[(2 * j) * 32 + lane] = dcfg[j];
-    sm.tng[(2 * j + 1) * 32 + lane] = dv[j];
-    sm.vd[j] = vdot[j];
+    for (int j = 0; j < NV; ++j) {
+      sm.tng[(2 * j) * LS + l] = dcfg[j];
+      sm.tng[(2 * j + 1) * LS + l] = dv[j];
+      sm.vd[j] = vdot[j];
+    }
   }
   __syncwarp();
-  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>{sm, lane}, 1.0);
+  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>{sm, l, on}, 1.0);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - sm.tau[i * 32 + lane];
+  for (int i = 0; i < NV; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - sm.tng[(2 * i + 1) * LS + l];
   m_solve<NV>(sm.Mf, sm.invd, dvdot);
   // kinematics q̇ = 𝑣, except the MRP rate of the floating base (RBD_helper_functions.jl:66)
 #pragma unroll
