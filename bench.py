@@ -258,6 +258,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pin_to_gpu_numa(index):
+    """Bind this rank (and the pool's worker threads, pinned buffers: first touch) to the CPUs `nvidia-smi topo -m`
+    lists as local to GPU `index`: with 8 ranks the bulk PCIe copies otherwise cross the socket interconnect."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=30).stdout
+        for line in out.splitlines():
+            tok = line.split()
+            if not tok or tok[0] != "GPU%d" % index:
+                continue
+            for t in tok[1:]:
+                if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", t):
+                    cpus = set()
+                    for part in t.split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+                    cpus &= os.sched_getaffinity(0)
+                    if cpus:
+                        os.sched_setaffinity(0, cpus)
+                        return "%s (%d cpus)" % (t, len(cpus))
+                    return None
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------- GPU arm
 IN_FLIGHT = 6   # batches kept in flight per GPU by the pool scheduler (ilqr_pool_*); --in-flight overrides
 
@@ -275,6 +301,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    affinity = pin_to_gpu_numa(local) if world > 1 and not os.environ.get("ILQR_NO_NUMA_PIN") else None
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -446,7 +473,7 @@ def run_b200(args):
             other = {"error": repr(e)}
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
             cpu = cpu_baseline(args.cpu_seconds)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -458,7 +485,8 @@ def run_b200(args):
                                "batches in flight so that the latency-bound tail of one overlaps the bulk of the next (every step still "
                                "solves its full batch to the same result); see `isolated` for one batch at a time" % IN_FLIGHT,
                        "l2_policy": "inputs larger than L2 (%.2f GB working set per handle vs 126 MB L2)" % (3.2 * B / 65536),
-                       "sharding": "independent batch slices per GPU, no data-path collective"},
+                       "sharding": "independent batch slices per GPU, no data-path collective",
+                       "cpu_affinity": affinity},
             "isolated": isolated,
             "mean_iterations_per_trajectory": float(iters.double().mean().item()),
             "converged_fraction": float(((torch.from_numpy(status) & 16) != 0).double().mean().item()),
