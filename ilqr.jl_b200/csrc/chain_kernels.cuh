@@ -58,6 +58,17 @@ template <int NQ, bool FL> struct BwdSmem : RiccatiSmem<ChainDims<NQ, FL>::n, Ch
   double qv[2 * NV];            // stage point (configuration, velocity)
   double sc[2 * NQ];            // sin θ_i, cos θ_i
   double vd[NV];                // 𝑣̇ at the stage point
+  // Software pipelining of the primal pass (fixed base, when NV + 1 lanes are free next to the LS column owners):
+  // lanes LS … LS+NV ride along in the dual pass of stage s and compute — in the VALUE half of the dual arithmetic,
+  // which every lane executes anyway — the columns of M and the bias at the point of stage s+1 (known once v̇ of stage
+  // s is known; for the last stage: the first stage of the next time step).  That removes the separate primal pass.
+  static constexpr bool PIPE = !FL && (LS + NV + 1 <= 32);
+  static constexpr int NSP = PIPE ? NV + 1 : 1;
+  double Mn[NV * NV];           // M at the next stage point (unfactored), bias there
+  double bn[NV];
+  double scn[2 * NQ];           // sin / cos of the next stage point's joint angles
+  double vn[NV];                // velocity of the next stage point
+  double fnv2[NQ * 6 * NSP];    // the riding lanes' own link wrenches
 };
 
 // Per-pass views of the scratch: what coordinate j feeds the recursion and where link i's wrench is parked.
@@ -74,17 +85,34 @@ template <int NQ, bool FL> struct PrimalIO {
   __device__ __forceinline__ void out(int j, double v) const { if (on) sm.tng[(2 * j + 1) * LS + l] = v; }
 };
 template <int NQ, bool FL> struct DualIO {
-  BwdSmem<NQ, FL>& sm; int l; bool on;
-  static constexpr int JO = ChainDims<NQ, FL>::JO, NV = ChainDims<NQ, FL>::NV, LS = BwdSmem<NQ, FL>::LS;
-  __device__ __forceinline__ Dual s(int i) const { return {sm.sc[2 * i], sm.sc[2 * i + 1] * sm.tng[(2 * (JO + i)) * LS + l]}; }
-  __device__ __forceinline__ Dual c(int i) const { return {sm.sc[2 * i + 1], -sm.sc[2 * i] * sm.tng[(2 * (JO + i)) * LS + l]}; }
-  __device__ __forceinline__ Dual vel(int j) const { return {sm.qv[NV + j], sm.tng[(2 * j + 1) * LS + l]}; }
-  __device__ __forceinline__ Dual acc(int j) const { return {sm.vd[j], 0.0}; }
-  __device__ __forceinline__ void put(int i, int k, Dual v) const {
-    if (on) { sm.fnv[i * 6 + k] = v.v; sm.fn[(i * 6 + k) * LS + l] = v.t; }
+  BwdSmem<NQ, FL>& sm; int l; bool on; int sp;   // sp ≥ 0: riding lane (sp < NV: column sp of the next M; sp = NV: next bias)
+  static constexpr int JO = ChainDims<NQ, FL>::JO, NV = ChainDims<NQ, FL>::NV, LS = BwdSmem<NQ, FL>::LS, NSP = BwdSmem<NQ, FL>::NSP;
+  static constexpr bool PIPE = BwdSmem<NQ, FL>::PIPE;
+  __device__ __forceinline__ bool ride() const { if constexpr (PIPE) return sp >= 0; else return false; }
+  __device__ __forceinline__ Dual s(int i) const {
+    const double sv = ride() ? sm.scn[2 * i] : sm.sc[2 * i], cv = ride() ? sm.scn[2 * i + 1] : sm.sc[2 * i + 1];
+    return {sv, cv * sm.tng[(2 * (JO + i)) * LS + l]};
   }
-  __device__ __forceinline__ Dual get(int i, int k) const { return {sm.fnv[i * 6 + k], sm.fn[(i * 6 + k) * LS + l]}; }
-  __device__ __forceinline__ void out(int j, Dual v) const { if (on) sm.tng[(2 * j + 1) * LS + l] = v.t; }
+  __device__ __forceinline__ Dual c(int i) const {
+    const double sv = ride() ? sm.scn[2 * i] : sm.sc[2 * i], cv = ride() ? sm.scn[2 * i + 1] : sm.sc[2 * i + 1];
+    return {cv, -sv * sm.tng[(2 * (JO + i)) * LS + l]};
+  }
+  __device__ __forceinline__ Dual vel(int j) const {
+    const double v = ride() ? (sp == NV ? sm.vn[j] : 0.0) : sm.qv[NV + j];
+    return {v, sm.tng[(2 * j + 1) * LS + l]};
+  }
+  __device__ __forceinline__ Dual acc(int j) const { return {ride() ? (sp == j ? 1.0 : 0.0) : sm.vd[j], 0.0}; }
+  __device__ __forceinline__ void put(int i, int k, Dual v) const {
+    if (ride()) sm.fnv2[(i * 6 + k) * NSP + sp] = v.v;
+    else if (on) { sm.fnv[i * 6 + k] = v.v; sm.fn[(i * 6 + k) * LS + l] = v.t; }
+  }
+  __device__ __forceinline__ Dual get(int i, int k) const {
+    return {ride() ? sm.fnv2[(i * 6 + k) * NSP + sp] : sm.fnv[i * 6 + k], sm.fn[(i * 6 + k) * LS + l]};
+  }
+  __device__ __forceinline__ void out(int j, Dual v) const {
+    if (ride()) { if (sp < NV) sm.Mn[j + NV * sp] = v.v; else sm.bn[j] = v.v; }
+    else if (on) sm.tng[(2 * j + 1) * LS + l] = v.t;
+  }
 };
 
 // chain_rnea (chain.cuh) with rolled link loops over shared-memory state; same arithmetic.
@@ -139,19 +167,15 @@ template <int NV> __device__ __forceinline__ void m_solve(const double* Mf, cons
   }
 }
 
-// One RK4 stage at the primal point (cfg, v) with this lane's tangent (dcfg, dv, δu = e_udir):
-//   vdot = M⁻¹(u − bias),  dvdot = M⁻¹(δu − ∂ID(θ, 𝑣, 𝑣̇)·(dcfg, dv)),  cdot / dcdot = kinematics and its tangent.
+// Stand-alone primal pass at the point (θ = cfg[JO…], v): M → Mdst (column-major), bias → bdst, sin/cos → scdst.
+// Lane j < NV computes column j of M = ID(θ, 0, e_j) without gravity; lane NV the bias = ID(θ, 𝑣, 0).
 template <int NQ, bool FL>
-__device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& sm, int lane,
-                                            const double (&cfg)[ChainDims<NQ, FL>::NV], const double (&v)[ChainDims<NQ, FL>::NV],
-                                            const double (&u)[ChainDims<NQ, FL>::NV], const double (&dcfg)[ChainDims<NQ, FL>::NV],
-                                            const double (&dv)[ChainDims<NQ, FL>::NV], int udir,
-                                            double (&cdot)[ChainDims<NQ, FL>::NV], double (&dcdot)[ChainDims<NQ, FL>::NV],
-                                            double (&vdot)[ChainDims<NQ, FL>::NV], double (&dvdot)[ChainDims<NQ, FL>::NV]) {
+__device__ __forceinline__ void chain_primal_pass(const ChainP& cp, BwdSmem<NQ, FL>& sm, int lane,
+                                                  const double (&cfg)[ChainDims<NQ, FL>::NV], const double (&v)[ChainDims<NQ, FL>::NV],
+                                                  double* Mdst, double* bdst, double* scdst) {
   constexpr int NV = ChainDims<NQ, FL>::NV, JO = ChainDims<NQ, FL>::JO, LS = BwdSmem<NQ, FL>::LS;
   const bool on = lane < LS;
   const int l = on ? lane : LS - 1;
-  // sin/cos of the joint angles: lane i evaluates joint i
   double qi = cfg[JO];
 #pragma unroll
   for (int i = 1; i < NQ; ++i) qi = (lane == i) ? cfg[JO + i] : qi;
@@ -159,34 +183,62 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
   sincos_bf(qi, &si, &ci);
   __syncwarp();   // the previous users of the scratch are done
   if (lane < NQ) { sm.sc[2 * lane] = si; sm.sc[2 * lane + 1] = ci; }
-  // lane j < NV: column j of M = ID(θ, 0, e_j) without gravity; the other lanes: bias = ID(θ, 𝑣, 0)
   const bool col = lane < NV;
   if (on) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       sm.tng[(2 * j) * LS + l] = col ? 0.0 : v[j];
       sm.tng[(2 * j + 1) * LS + l] = (lane == j) ? 1.0 : 0.0;
-      sm.qv[NV + j] = v[j];   // every lane holds the same stage point
     }
   }
   __syncwarp();
   warp_rnea<double, PrimalIO<NQ, FL>, NQ, FL>(cp, PrimalIO<NQ, FL>{sm, l, on}, col ? 0.0 : 1.0);
   if (col) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) sm.Mf[i + NV * lane] = sm.tng[(2 * i + 1) * LS + l];
+    for (int i = 0; i < NV; ++i) Mdst[i + NV * lane] = sm.tng[(2 * i + 1) * LS + l];
   } else if (lane == NV) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) sm.bias[i] = sm.tng[(2 * i + 1) * LS + l];
+    for (int i = 0; i < NV; ++i) bdst[i] = sm.tng[(2 * i + 1) * LS + l];
   }
+  if (scdst != sm.sc && lane < NQ) { scdst[2 * lane] = si; scdst[2 * lane + 1] = ci; }
   __syncwarp();
+}
+
+// One RK4 stage at the primal point (cfg, v) with this lane's tangent (dcfg, dv, δu = e_udir):
+//   vdot = M⁻¹(u − bias),  dvdot = M⁻¹(δu − ∂ID(θ, 𝑣, 𝑣̇)·(dcfg, dv)),  cdot / dcdot = kinematics and its tangent.
+// Pipelined variant (BwdSmem::PIPE): M, bias and sin/cos at this point were left in Mn / bn / scn by the previous
+// stage's dual pass; this stage's dual pass leaves them for the next point — x0 + cnext·Δt·(v, vdot) if nmode = 0,
+// xnext if nmode = 1 (first stage of the next time step), nothing useful if nmode = 2.
+template <int NQ, bool FL>
+__device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& sm, int lane,
+                                            const double (&cfg)[ChainDims<NQ, FL>::NV], const double (&v)[ChainDims<NQ, FL>::NV],
+                                            const double (&u)[ChainDims<NQ, FL>::NV], const double (&dcfg)[ChainDims<NQ, FL>::NV],
+                                            const double (&dv)[ChainDims<NQ, FL>::NV], int udir,
+                                            const double (&x0)[ChainDims<NQ, FL>::n], const double (&xnext)[ChainDims<NQ, FL>::n],
+                                            int nmode, double cnext,
+                                            double (&cdot)[ChainDims<NQ, FL>::NV], double (&dcdot)[ChainDims<NQ, FL>::NV],
+                                            double (&vdot)[ChainDims<NQ, FL>::NV], double (&dvdot)[ChainDims<NQ, FL>::NV]) {
+  constexpr int NV = ChainDims<NQ, FL>::NV, JO = ChainDims<NQ, FL>::JO, LS = BwdSmem<NQ, FL>::LS;
+  constexpr bool PIPE = BwdSmem<NQ, FL>::PIPE;
+  const bool on = lane < LS;
+  const int l = on ? lane : LS - 1;
+  if constexpr (PIPE) {
+    __syncwarp();   // the previous dual pass has delivered Mn / bn; nobody reads Mf / sc any more
+    for (int idx = lane; idx < NV * NV; idx += 32) sm.Mf[idx] = sm.Mn[idx];
+    if (lane < NV) sm.bias[lane] = sm.bn[lane];
+    if (lane < 2 * NQ) sm.sc[lane] = sm.scn[lane];
+    __syncwarp();
+  } else {
+    chain_primal_pass<NQ, FL>(cp, sm, lane, cfg, v, sm.Mf, sm.bias, sm.sc);
+  }
   // factor M (symmetric positive definite ⇒ no pivoting): lane r eliminates row r
 #pragma unroll
   for (int k = 0; k < NV - 1; ++k) {
     if (lane > k && lane < NV) {
-      const double l = sm.Mf[lane + NV * k] * rcp_nr(sm.Mf[k + NV * k]);
+      const double lk = sm.Mf[lane + NV * k] * rcp_nr(sm.Mf[k + NV * k]);
 #pragma unroll
-      for (int j = k + 1; j < NV; ++j) sm.Mf[lane + NV * j] = fma(-l, sm.Mf[k + NV * j], sm.Mf[lane + NV * j]);
-      sm.Mf[lane + NV * k] = l;
+      for (int j = k + 1; j < NV; ++j) sm.Mf[lane + NV * j] = fma(-lk, sm.Mf[k + NV * j], sm.Mf[lane + NV * j]);
+      sm.Mf[lane + NV * k] = lk;
     }
     __syncwarp();
   }
@@ -195,6 +247,22 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
 #pragma unroll
   for (int i = 0; i < NV; ++i) vdot[i] = u[i] - sm.bias[i];
   m_solve<NV>(sm.Mf, sm.invd, vdot);
+  int sp = -1;
+  if constexpr (PIPE) {
+    // the point the riding lanes work at: the next stage's (same arithmetic as chain_linearize uses to form it)
+    sp = (lane >= LS && lane < LS + NV + 1) ? lane - LS : -1;
+    double thn = 0.0;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const double t = (nmode == 0) ? fma(cnext, cp.dt * v[JO + i], x0[JO + i]) : xnext[JO + i];
+      thn = (lane == i) ? t : thn;
+    }
+    double sn, cn;
+    sincos_bf(thn, &sn, &cn);
+    if (lane < NQ) { sm.scn[2 * lane] = sn; sm.scn[2 * lane + 1] = cn; }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sm.vn[j] = (nmode == 0) ? fma(cnext, cp.dt * vdot[j], x0[NV + j]) : xnext[NV + j];
+  }
   // directional derivative of the inverse dynamics along this lane's tangent
   if (on) {
 #pragma unroll
@@ -202,10 +270,11 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
       sm.tng[(2 * j) * LS + l] = dcfg[j];
       sm.tng[(2 * j + 1) * LS + l] = dv[j];
       sm.vd[j] = vdot[j];
+      sm.qv[NV + j] = v[j];   // every lane holds the same stage point
     }
   }
   __syncwarp();
-  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>{sm, l, on}, 1.0);
+  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>{sm, l, on, sp}, (sp >= 0 && sp < NV) ? 0.0 : 1.0);
 #pragma unroll
   for (int i = 0; i < NV; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - sm.tng[(2 * i + 1) * LS + l];
   m_solve<NV>(sm.Mf, sm.invd, dvdot);
@@ -226,6 +295,7 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
 template <int NQ, bool FL>
 __device__ __forceinline__ void chain_linearize(const ChainP& cp, BwdSmem<NQ, FL>& sm, int lane,
                                                 const double (&x)[ChainDims<NQ, FL>::n], const double (&u)[ChainDims<NQ, FL>::m],
+                                                const double (&xprev)[ChainDims<NQ, FL>::n], bool has_prev,
                                                 double (&ab)[ChainDims<NQ, FL>::n]) {
   constexpr int NV = ChainDims<NQ, FL>::NV, n = 2 * NV;
   const int udir = lane - n;   // ≥ 0 on the lanes that carry a control direction
@@ -241,7 +311,10 @@ __device__ __forceinline__ void chain_linearize(const ChainP& cp, BwdSmem<NQ, FL
       cfg[i] = fma(cin, kp[i], x[i]); v[i] = fma(cin, kp[NV + i], x[NV + i]);
       dcfg[i] = fma(cin, tp[i], xi0[i]); dv[i] = fma(cin, tp[NV + i], xi0[NV + i]);
     }
-    chain_stage<NQ, FL>(cp, sm, lane, cfg, v, u, dcfg, dv, udir, cdot, dcdot, vdot, dvdot);
+    // what the riding lanes prepare: stage stg+1 of this step, or the first stage of time step k−1 (its point is x_{k−1})
+    const int nmode = (stg < 3) ? 0 : (has_prev ? 1 : 2);
+    const double cnext = (stg == 2) ? 1.0 : 0.5;
+    chain_stage<NQ, FL>(cp, sm, lane, cfg, v, u, dcfg, dv, udir, x, xprev, nmode, cnext, cdot, dcdot, vdot, dvdot);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       kp[i] = cp.dt * cdot[i]; kp[NV + i] = cp.dt * vdot[i];
@@ -272,19 +345,28 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   riccati_terminal<n, m>(sm, lane, lane < n ? X[((int64_t)H * S + s) * n + lane] : 0.0, cost);
 
   bool bad = false;
+  double x[n], xprev[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) x[i] = X[((int64_t)(H - 1) * S + s) * n + i];
+  if constexpr (BwdSmem<NQ, FL>::PIPE) {   // prologue of the software pipeline: M, bias, sin/cos at the first stage point
+    double cfg0[m], v0[m];
+#pragma unroll
+    for (int i = 0; i < m; ++i) { cfg0[i] = x[i]; v0[i] = x[m + i]; }
+    chain_primal_pass<NQ, FL>(cp, sm, lane, cfg0, v0, sm.Mn, sm.bn, sm.scn);
+  }
 #pragma unroll 1
   for (int k = H - 1; k >= 0; --k) {
-    double x[n], u[m];
+    double u[m];
     {
-      const double* xp = X + ((int64_t)k * S + s) * n;
+      const double* xp = X + ((int64_t)(k > 0 ? k - 1 : 0) * S + s) * n;
       const double* up = U + ((int64_t)k * S + s) * m;
 #pragma unroll
-      for (int i = 0; i < n; ++i) x[i] = xp[i];
+      for (int i = 0; i < n; ++i) xprev[i] = xp[i];
 #pragma unroll
       for (int i = 0; i < m; ++i) u[i] = up[i];
     }
     double ab[n];
-    chain_linearize<NQ, FL>(cp, sm, lane, x, u, ab);
+    chain_linearize<NQ, FL>(cp, sm, lane, x, u, xprev, k > 0, ab);
     if (lane >= n + m) {
 #pragma unroll
       for (int i = 0; i < n; ++i) ab[i] = 0.0;
@@ -292,6 +374,8 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
 
     bad |= riccati_column_step<n, m>(sm, lane, ab, x, u, cost, st.reg, st.K + ((int64_t)k * S + s) * (m * n),
                                      st.duff + ((int64_t)k * S + s) * m);
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xprev[i];
   }
   if (__any_sync(kFull, bad) && lane == 0) st.status[s] |= ST_NAN_GAINS;
 }
