@@ -29,7 +29,10 @@
 namespace ilqr {
 namespace chain_detail {
 
-constexpr int kCW = 4;   // warps (= trajectories) per block in bwd_chain
+#ifndef ILQR_CHAIN_WARPS
+#define ILQR_CHAIN_WARPS 4
+#endif
+constexpr int kCW = ILQR_CHAIN_WARPS;   // warps (= trajectories) per block in bwd_chain
 #ifndef ILQR_CHAIN_MIN_BLOCKS
 #define ILQR_CHAIN_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for.  3 (168 registers, 12 warps/SM;
                                   // the scratch fits: 17.5 KB per warp at nq = 7) measured 3 % faster on configs[3] and 4 %
@@ -85,34 +88,37 @@ template <int NQ, bool FL> struct PrimalIO {
   __device__ __forceinline__ void out(int j, double v) const { if (on) sm.tng[(2 * j + 1) * LS + l] = v; }
 };
 template <int NQ, bool FL> struct DualIO {
-  BwdSmem<NQ, FL>& sm; int l; bool on; int sp;   // sp ≥ 0: riding lane (sp < NV: column sp of the next M; sp = NV: next bias)
   static constexpr int JO = ChainDims<NQ, FL>::JO, NV = ChainDims<NQ, FL>::NV, LS = BwdSmem<NQ, FL>::LS, NSP = BwdSmem<NQ, FL>::NSP;
   static constexpr bool PIPE = BwdSmem<NQ, FL>::PIPE;
+  BwdSmem<NQ, FL>& sm; int l; bool on; int sp;   // sp ≥ 0: riding lane (sp < NV: column sp of the next M; sp = NV: next bias)
+  // where this lane's VALUE inputs live (selected once, so that the accessors below are straight-line code)
+  const double* scp; const double* velp; const double* fnvp; double vmask; int fs, fo;
+  __device__ __forceinline__ DualIO(BwdSmem<NQ, FL>& sm_, int l_, bool on_, int sp_) : sm(sm_), l(l_), on(on_), sp(sp_) {
+    const bool r = ride();
+    scp = r ? sm.scn : sm.sc;
+    velp = r ? sm.vn : sm.qv + NV;
+    fnvp = r ? sm.fnv2 : sm.fnv;
+    vmask = (r && sp < NV) ? 0.0 : 1.0;      // the M-column lanes run at zero velocity
+    fs = r ? NSP : 1; fo = r ? sp : 0;
+  }
   __device__ __forceinline__ bool ride() const { if constexpr (PIPE) return sp >= 0; else return false; }
-  __device__ __forceinline__ Dual s(int i) const {
-    const double sv = ride() ? sm.scn[2 * i] : sm.sc[2 * i], cv = ride() ? sm.scn[2 * i + 1] : sm.sc[2 * i + 1];
-    return {sv, cv * sm.tng[(2 * (JO + i)) * LS + l]};
+  __device__ __forceinline__ Dual s(int i) const { return {scp[2 * i], scp[2 * i + 1] * sm.tng[(2 * (JO + i)) * LS + l]}; }
+  __device__ __forceinline__ Dual c(int i) const { return {scp[2 * i + 1], -scp[2 * i] * sm.tng[(2 * (JO + i)) * LS + l]}; }
+  __device__ __forceinline__ Dual vel(int j) const { return {velp[j] * vmask, sm.tng[(2 * j + 1) * LS + l]}; }
+  __device__ __forceinline__ Dual acc(int j) const {
+    const double a = sm.vd[j];
+    return {ride() ? (sp == j ? 1.0 : 0.0) : a, 0.0};
   }
-  __device__ __forceinline__ Dual c(int i) const {
-    const double sv = ride() ? sm.scn[2 * i] : sm.sc[2 * i], cv = ride() ? sm.scn[2 * i + 1] : sm.sc[2 * i + 1];
-    return {cv, -sv * sm.tng[(2 * (JO + i)) * LS + l]};
-  }
-  __device__ __forceinline__ Dual vel(int j) const {
-    const double v = ride() ? (sp == NV ? sm.vn[j] : 0.0) : sm.qv[NV + j];
-    return {v, sm.tng[(2 * j + 1) * LS + l]};
-  }
-  __device__ __forceinline__ Dual acc(int j) const { return {ride() ? (sp == j ? 1.0 : 0.0) : sm.vd[j], 0.0}; }
   __device__ __forceinline__ void put(int i, int k, Dual v) const {
-    if (ride()) sm.fnv2[(i * 6 + k) * NSP + sp] = v.v;
-    else if (on) { sm.fnv[i * 6 + k] = v.v; sm.fn[(i * 6 + k) * LS + l] = v.t; }
+    if (ride() || on) fnvp_mut()[(i * 6 + k) * fs + fo] = v.v;
+    if (on) sm.fn[(i * 6 + k) * LS + l] = v.t;
   }
-  __device__ __forceinline__ Dual get(int i, int k) const {
-    return {ride() ? sm.fnv2[(i * 6 + k) * NSP + sp] : sm.fnv[i * 6 + k], sm.fn[(i * 6 + k) * LS + l]};
-  }
+  __device__ __forceinline__ Dual get(int i, int k) const { return {fnvp[(i * 6 + k) * fs + fo], sm.fn[(i * 6 + k) * LS + l]}; }
   __device__ __forceinline__ void out(int j, Dual v) const {
     if (ride()) { if (sp < NV) sm.Mn[j + NV * sp] = v.v; else sm.bn[j] = v.v; }
     else if (on) sm.tng[(2 * j + 1) * LS + l] = v.t;
   }
+  __device__ __forceinline__ double* fnvp_mut() const { return const_cast<double*>(fnvp); }
 };
 
 // chain_rnea (chain.cuh) with rolled link loops over shared-memory state; same arithmetic.
@@ -274,7 +280,7 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
     }
   }
   __syncwarp();
-  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>{sm, l, on, sp}, (sp >= 0 && sp < NV) ? 0.0 : 1.0);
+  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>(sm, l, on, sp), (sp >= 0 && sp < NV) ? 0.0 : 1.0);
 #pragma unroll
   for (int i = 0; i < NV; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - sm.tng[(2 * i + 1) * LS + l];
   m_solve<NV>(sm.Mf, sm.invd, dvdot);
