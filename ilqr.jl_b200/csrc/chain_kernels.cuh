@@ -71,7 +71,9 @@ template <int NQ, bool FL> struct BwdSmem : RiccatiSmem<ChainDims<NQ, FL>::n, Ch
   double bn[NV];
   double scn[2 * NQ];           // sin / cos of the next stage point's joint angles
   double vn[NV];                // velocity of the next stage point
-  double fnv2[NQ * 6 * NSP];    // the riding lanes' own link wrenches
+  // The riding lanes' own link wrenches (NQ·6·NSP doubles) live in [AB | GH], which only the Riccati step uses.
+  static_assert(NQ * 6 * NSP <= n * (n + m) + m * (n + m + 1), "riding-lane scratch must fit in [AB | GH]");
+  __device__ __forceinline__ double* fnv2() { return this->AB; }
 };
 
 // Per-pass views of the scratch: what coordinate j feeds the recursion and where link i's wrench is parked.
@@ -97,7 +99,7 @@ template <int NQ, bool FL> struct DualIO {
     const bool r = ride();
     scp = r ? sm.scn : sm.sc;
     velp = r ? sm.vn : sm.qv + NV;
-    fnvp = r ? sm.fnv2 : sm.fnv;
+    fnvp = r ? sm.fnv2() : sm.fnv;
     vmask = (r && sp < NV) ? 0.0 : 1.0;      // the M-column lanes run at zero velocity
     fs = r ? NSP : 1; fo = r ? sp : 0;
   }
