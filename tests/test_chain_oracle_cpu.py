@@ -198,3 +198,27 @@ def test_floating_base_linearisation_and_fit():
     out = orc.chain_fit_batch(spec, xx, uu, max_iter=15, tol=1e-6)
     c = out["cost"][: out["iters"][0], 0]
     assert out["status"][0] == 0 and np.all(np.diff(c) < 0), (out["status"], c)
+
+
+def _golden_specs():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain_golden.npz"))
+    fixed = orc.chain_spec(g["fixed_joints"], dt=float(g["fixed_dt"]), x_target=g["fixed_target"], w_x=g["fixed_w_x"],
+                           w_u=g["fixed_w_u"], w_xf=g["fixed_w_xf"])
+    floating = orc.chain_spec(g["floating_joints"], base=g["floating_base"], dt=float(g["floating_dt"]),
+                              x_target=g["floating_target"], w_x=g["floating_w_x"], w_u=g["floating_w_u"], w_xf=g["floating_w_xf"])
+    return g, dict(fixed=fixed, floating=floating)
+
+
+@pytest.mark.parametrize("name", ["fixed", "floating"])
+def test_chain_golden_fixture_matches_oracle(name):
+    """tests/golden/chain_golden.npz was written by tests/golden/make_chain_golden.py from this oracle."""
+    g, specs = _golden_specs()
+    spec = specs[name]
+    x, u = g[name + "_x_init"], g[name + "_u_init"]
+    for b in range(x.shape[2]):
+        d, K, _ = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
+        assert np.array_equal(d, g[name + "_duff0"][:, :, b]) and np.array_equal(K, g[name + "_K0"][:, :, :, b])
+    fit = orc.chain_fit_batch(spec, x, u, max_iter=int(g[name + "_max_iter"]), tol=float(g[name + "_tol"]), nthreads=4)
+    assert np.array_equal(fit["iters"], g[name + "_iters"]) and np.array_equal(fit["x"], g[name + "_x"])
+    assert np.array_equal(fit["cost"], g[name + "_cost"], equal_nan=True)

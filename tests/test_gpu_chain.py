@@ -254,3 +254,28 @@ def test_config3_reference_problem_matches_oracle():
         errs.append(rel_err(ct[:it, b], ref["cost"][:it, b]))
     print("config-3 cost-trace rel err", max(errs), "x rel err", rel_err(out["x"], ref["x"]))
     assert max(errs) <= 1e-8 and rel_err(out["x"], ref["x"]) <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["fixed", "floating"])
+def test_chain_matches_committed_golden_fixture(name):
+    """CUDA path against tests/golden/chain_golden.npz (frozen oracle output; make_chain_golden.py): first-iteration
+    gains, per-iterate costs / α, iteration counts and the returned iterates — without running the oracle here."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain_golden.npz"))
+    x, u = np.asfortranarray(g[name + "_x_init"]), np.asfortranarray(g[name + "_u_init"])
+    H, B = u.shape[0], u.shape[2]
+    base = g["floating_base"] if name == "floating" else None
+    prob = ilqr_b200.serial_chain_problem(g[name + "_joints"], H, B, base=base, dt=float(g[name + "_dt"]), x_target=g[name + "_target"],
+                                          w_x=g[name + "_w_x"], w_u=g[name + "_w_u"], w_xf=g[name + "_w_xf"], trace_iters=40)
+    max_iter, tol = int(g[name + "_max_iter"]), float(g[name + "_tol"])
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        assert rel_err(s.download(_abi.DUFF), g[name + "_duff0"]) <= RTOL and rel_err(s.download(_abi.K), g[name + "_K0"]) <= RTOL
+        out = s.solve(x, u, max_iter=max_iter, tol=tol)
+        ct, at = s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE)
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    for b in range(B):
+        it = g[name + "_iters"][b]
+        assert rel_err(ct[:it, b], g[name + "_cost"][:it, b]) <= RTOL and np.array_equal(at[:it, b], g[name + "_alpha"][:it, b])
+    assert rel_err(out["x"], g[name + "_x"]) <= RTOL
