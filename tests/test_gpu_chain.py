@@ -279,3 +279,40 @@ def test_chain_matches_committed_golden_fixture(name):
         it = g[name + "_iters"][b]
         assert rel_err(ct[:it, b], g[name + "_cost"][:it, b]) <= RTOL and np.array_equal(at[:it, b], g[name + "_alpha"][:it, b])
     assert rel_err(out["x"], g[name + "_x"]) <= RTOL
+
+
+def test_chain_mpc_closed_loop_matches_oracle():
+    """ilqr_mpc_* on a rigid-body model: solve (≤ K warm-started iterations), apply u[0] to the plant (the same
+    dynamicsf), shift — against the same loop built from oracle calls."""
+    B, H, K, STEPS, nq = 4, 15, 3, 3, 3
+    spec, prob, x0, x, u = _setup(nq, True, B, H, 900, (0.0, 0.0, -9.81))
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.mpc_start(np.asfortranarray(x0.T))
+        got = [s.mpc_step(max_iter=K) for _ in range(STEPS)]
+    for b in range(B):
+        plant = x0[b].copy(); uu = np.zeros((H, nq, 1), order="F")
+        for t in range(STEPS):
+            xx = np.zeros((H + 1, 2 * nq, 1), order="F"); xx[:, :, 0] = orc.chain_rollout(spec, plant, uu[:, :, 0])
+            res = orc.chain_fit_batch(spec, xx, uu, max_iter=K, tol=1e-6)
+            u0 = res["u"][0, :, 0].copy()
+            plant = orc.chain_dynamics(spec, plant, u0)
+            uu = np.asfortranarray(np.concatenate([res["u"][1:], np.zeros((1, nq, 1))], axis=0))
+            ua, xp = got[t]
+            assert np.max(np.abs(ua[:, b] - u0)) < RTOL * max(1.0, np.max(np.abs(u0))), (b, t)
+            assert np.max(np.abs(xp[:, b] - plant)) < RTOL * max(1.0, np.max(np.abs(plant))), (b, t)
+
+
+def test_custom_and_chain_models_through_the_pool():
+    """The pool scheduler is model-agnostic: rigid-body batches through ilqr_pool_* equal single-handle solves."""
+    B, H = 40, 12
+    spec, prob, x0, x, u = _setup(3, True, B, H, 901, (0.0, 0.0, -9.81), hard=(1000.0, 0.05))
+    with ilqr_b200.BatchSolver(prob) as s:
+        ref = s.solve(x, u, max_iter=20, tol=1e-8)
+    with ilqr_b200.SolverPool(prob, 2) as pool:
+        outs = [dict(x=np.empty_like(x), u=np.empty_like(u), cost=np.empty(B), iters=np.empty(B, dtype=np.int32),
+                     status=np.empty(B, dtype=np.int32)) for _ in range(3)]
+        tickets = [pool.submit(x, u, o, max_iter=20, tol=1e-8) for o in outs]
+        pool.wait_all()
+    for o in outs:
+        for k in ("x", "u", "cost", "iters", "status"):
+            assert np.array_equal(ref[k], o[k]), k
