@@ -164,17 +164,17 @@ def aux_chain(device, cpu_too):
         t0 = time.perf_counter(); s.fit(MAX_ITER, TOL); dt = time.perf_counter() - t0
         prof = s.profile()
         it, st = s.download(_abi.ITERS), s.download(_abi.STATUS)
-    # FP64-pipe roofline of the dominant kernel: 18.3 k DFMA-class warp instructions per trajectory-step
+    # FP64-pipe roofline of the dominant kernel: 13.6 k DFMA-class warp instructions per trajectory-step
     # (profiles/ncu_full_r1_chain_B2368.txt: pipe-active share × cycles), one warp per trajectory ⇒ 32 lanes issue them
-    fp64_instr = 18300
+    fp64_instr = 13600
     tf = 2.0 * fp64_instr * 32 * 100 * Bc / (prof["first_bwd_ms"] * 1e-3) / 1e12
     out = {"workload": "configs[3]: synthetic 7-DoF serial chain (n=14, m=7), B=262144, H=100, fp64, 1 GPU",
            "value": Bc / dt, "unit": "solves/s", "fit_s": dt, "mean_iterations": float(it.mean()),
            "converged_fraction": float(np.mean((st & 16) != 0)),
            "bwd_chain_ms_full_batch": prof["first_bwd_ms"], "fwd_chain_ms_full_batch": prof["first_fwd_ms"],
            "bwd_chain_issue_tflops_fp64": tf,
-           "note": "bwd_chain is FP64-pipe bound: 65 % pipe-active under ncu (profiles/ncu_full_r1_chain_B2368.txt); "
-                   "issue_tflops counts all 32 lanes of the warp-per-trajectory mapping (22 carry useful directions)"}
+           "note": "bwd_chain: FP64 pipe ~55 % active under ncu at 8 warps/SM (profiles/ncu_full_r1_chain_B2368.txt); "
+                   "issue_tflops counts all 32 lanes of the warp-per-trajectory mapping (30 carry work: 22 column owners + 8 riding lanes)"}
     if cpu_too:
         from oracle import oracle_py as orc
         cores = os.cpu_count() or 1
