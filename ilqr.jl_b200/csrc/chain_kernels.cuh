@@ -34,9 +34,10 @@ namespace chain_detail {
 #endif
 constexpr int kCW = ILQR_CHAIN_WARPS;   // warps (= trajectories) per block in bwd_chain
 #ifndef ILQR_CHAIN_MIN_BLOCKS
-#define ILQR_CHAIN_MIN_BLOCKS 2   // resident blocks per SM the register allocation is sized for.  3 (168 registers, 12 warps/SM;
-                                  // the scratch fits: 17.5 KB per warp at nq = 7) measured 3 % faster on configs[3] and 4 %
-                                  // slower on configs[2]: the kernel is FP64-issue bound, not latency bound
+#define ILQR_CHAIN_MIN_BLOCKS 3   // resident blocks per SM the register allocation is sized for: 3 × 4 warps = 12 warps/SM
+                                  // (160 registers without spills once the per-step uniform state lives in shared
+                                  // memory; 18.4 KB of shared memory per warp at nq = 7).  Measured against 2 blocks:
+                                  // 65.5 → 57.7 ms (configs[3], B = 16,384), 150 → 148 ms (configs[2])
 #endif
 constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2;
 constexpr unsigned kFull = 0xffffffffu;
@@ -71,6 +72,9 @@ template <int NQ, bool FL> struct BwdSmem : RiccatiSmem<ChainDims<NQ, FL>::n, Ch
   double bn[NV];
   double scn[2 * NQ];           // sin / cos of the next stage point's joint angles
   double vn[NV];                // velocity of the next stage point
+  // the time step's linearisation point and its predecessor's state: the same on every lane, so they live here once
+  // instead of 35 doubles of registers per thread
+  double xs[n], xps[n], us[m];
   // The riding lanes' own link wrenches (NQ·6·NSP doubles) live in [AB | GH], which only the Riccati step uses.
   static_assert(NQ * 6 * NSP <= n * (n + m) + m * (n + m + 1), "riding-lane scratch must fit in [AB | GH]");
   __device__ __forceinline__ double* fnv2() { return this->AB; }
@@ -353,28 +357,28 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   riccati_terminal<n, m>(sm, lane, lane < n ? X[((int64_t)H * S + s) * n + lane] : 0.0, cost);
 
   bool bad = false;
-  double x[n], xprev[n];
-#pragma unroll
-  for (int i = 0; i < n; ++i) x[i] = X[((int64_t)(H - 1) * S + s) * n + i];
+  if (lane < n) sm.xps[lane] = X[((int64_t)(H - 1) * S + s) * n + lane];
+  __syncwarp();
   if constexpr (BwdSmem<NQ, FL>::PIPE) {   // prologue of the software pipeline: M, bias, sin/cos at the first stage point
     double cfg0[m], v0[m];
 #pragma unroll
-    for (int i = 0; i < m; ++i) { cfg0[i] = x[i]; v0[i] = x[m + i]; }
+    for (int i = 0; i < m; ++i) { cfg0[i] = sm.xps[i]; v0[i] = sm.xps[m + i]; }
     chain_primal_pass<NQ, FL>(cp, sm, lane, cfg0, v0, sm.Mn, sm.bn, sm.scn);
   }
 #pragma unroll 1
   for (int k = H - 1; k >= 0; --k) {
-    double u[m];
-    {
-      const double* xp = X + ((int64_t)(k > 0 ? k - 1 : 0) * S + s) * n;
-      const double* up = U + ((int64_t)k * S + s) * m;
-#pragma unroll
-      for (int i = 0; i < n; ++i) xprev[i] = xp[i];
-#pragma unroll
-      for (int i = 0; i < m; ++i) u[i] = up[i];
-    }
+    // x_k (loaded as x_{k−1} one step ago), x_{k−1}, u_k → shared memory
+    const double xk = (lane < n) ? sm.xps[lane] : 0.0;
+    const double xkm1 = (lane < n) ? X[((int64_t)(k > 0 ? k - 1 : 0) * S + s) * n + lane] : 0.0;
+    const double uk = (lane < m) ? U[((int64_t)k * S + s) * m + lane] : 0.0;
+    __syncwarp();
+    if (lane < n) { sm.xs[lane] = xk; sm.xps[lane] = xkm1; }
+    if (lane < m) sm.us[lane] = uk;
+    __syncwarp();
+    const double (&x)[n] = sm.xs;
+    const double (&u)[m] = sm.us;
     double ab[n];
-    chain_linearize<NQ, FL>(cp, sm, lane, x, u, xprev, k > 0, ab);
+    chain_linearize<NQ, FL>(cp, sm, lane, x, u, sm.xps, k > 0, ab);
     if (lane >= n + m) {
 #pragma unroll
       for (int i = 0; i < n; ++i) ab[i] = 0.0;
@@ -382,8 +386,6 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
 
     bad |= riccati_column_step<n, m>(sm, lane, ab, x, u, cost, st.reg, st.K + ((int64_t)k * S + s) * (m * n),
                                      st.duff + ((int64_t)k * S + s) * m);
-#pragma unroll
-    for (int i = 0; i < n; ++i) x[i] = xprev[i];
   }
   if (__any_sync(kFull, bad) && lane == 0) st.status[s] |= ST_NAN_GAINS;
 }
