@@ -316,3 +316,26 @@ def test_custom_and_chain_models_through_the_pool():
     for o in outs:
         for k in ("x", "u", "cost", "iters", "status"):
             assert np.array_equal(ref[k], o[k]), k
+
+
+def test_stream_admission_on_a_rigid_body_model():
+    """ilqr_stream_solve_device with the runtime-(n, m) retire / move / admit kernels: 40 slots kept full from 150 pending
+    trajectories of a 3-joint chain; bit-identical to one plain batched solve."""
+    import torch
+    n_total, slots, H = 150, 40, 12
+    spec, prob_all, x0, x, u = _setup(3, True, n_total, H, 902, (0.0, 0.0, -9.81), hard=(1000.0, 0.05))
+    with ilqr_b200.BatchSolver(prob_all) as s:
+        ref = s.solve(x, u, max_iter=25, tol=1e-8)
+    assert len(set(ref["iters"].tolist())) > 3
+    prob = ilqr_b200.Problem.from_buffer_copy(prob_all); prob.B = slots; prob.trace_iters = 0
+    dx = torch.from_numpy(np.ascontiguousarray(x.transpose(2, 1, 0))).cuda(); du = torch.from_numpy(np.ascontiguousarray(u.transpose(2, 1, 0))).cuda()
+    ox, ou = torch.zeros_like(dx), torch.zeros_like(du)
+    oc = torch.zeros(n_total, dtype=torch.float64, device="cuda")
+    oi = torch.zeros(n_total, dtype=torch.int32, device="cuda"); os_ = torch.zeros(n_total, dtype=torch.int32, device="cuda")
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.stream_solve_device(n_total, dx.data_ptr(), du.data_ptr(), ox.data_ptr(), ou.data_ptr(), oc.data_ptr(), oi.data_ptr(),
+                              os_.data_ptr(), max_iter=25, tol=1e-8)
+    torch.cuda.synchronize()
+    assert np.array_equal(oi.cpu().numpy(), ref["iters"]) and np.array_equal(os_.cpu().numpy(), ref["status"])
+    assert np.array_equal(oc.cpu().numpy(), ref["cost"])
+    assert np.array_equal(ox.cpu().numpy().transpose(2, 1, 0), ref["x"]) and np.array_equal(ou.cpu().numpy().transpose(2, 1, 0), ref["u"])
