@@ -164,8 +164,95 @@ template <class T> __device__ __forceinline__ void mrp_rate(const T (&p)[3], con
   for (int k = 0; k < 3; ++k) pd[k] = 0.25 * (omp * w[k] + 2.0 * cx[k] + (2.0 * pw) * p[k]);
 }
 
+// ---- joint-space inertia matrix by the composite-rigid-body algorithm (what RigidBodyDynamics.jl's mass_matrix
+// computes, RBD_helper_functions.jl:57), thread-local.  Composite inertias are kept per link as (mass, first moment
+// h = m·r_com, inertia tensor J about the LINK-FRAME ORIGIN), all in link coordinates.
+struct Composite {
+  double m;
+  V3<double> h;
+  double J[6];   // xx xy xz yy yz zz
+};
+__device__ __forceinline__ Composite link_composite(double mass, const double com[3], const double I[6]) {
+  const double cc = com[0] * com[0] + com[1] * com[1] + com[2] * com[2];
+  Composite r;
+  r.m = mass;
+  r.h = {mass * com[0], mass * com[1], mass * com[2]};
+  r.J[0] = I[0] + mass * (cc - com[0] * com[0]); r.J[1] = I[1] - mass * com[0] * com[1]; r.J[2] = I[2] - mass * com[0] * com[2];
+  r.J[3] = I[3] + mass * (cc - com[1] * com[1]); r.J[4] = I[4] - mass * com[1] * com[2];
+  r.J[5] = I[5] + mass * (cc - com[2] * com[2]);
+  return r;
+}
+// parent += child (composite of link i, in frame i about origin i) seen from the parent frame / origin
+__device__ __forceinline__ void add_child(const ChainP& cp, int i, double s, double c, const Composite& ch, Composite& par) {
+  const double* p = cp.xyz[i];
+  // E·J·Eᵀ: rotate the columns, then the rows
+  const V3<double> a0 = to_parent<double>(cp, i, s, c, {ch.J[0], ch.J[1], ch.J[2]});
+  const V3<double> a1 = to_parent<double>(cp, i, s, c, {ch.J[1], ch.J[3], ch.J[4]});
+  const V3<double> a2 = to_parent<double>(cp, i, s, c, {ch.J[2], ch.J[4], ch.J[5]});
+  const V3<double> r0 = to_parent<double>(cp, i, s, c, {a0.x, a1.x, a2.x});
+  const V3<double> r1 = to_parent<double>(cp, i, s, c, {a0.y, a1.y, a2.y});
+  const V3<double> r2 = to_parent<double>(cp, i, s, c, {a0.z, a1.z, a2.z});
+  const V3<double> hE = to_parent<double>(cp, i, s, c, ch.h);
+  const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2], ph = p[0] * hE.x + p[1] * hE.y + p[2] * hE.z;
+  const double d = ch.m * pp + 2.0 * ph;   // shift of the reference point from the child origin to the parent origin
+  par.m += ch.m;
+  par.h = {par.h.x + hE.x + ch.m * p[0], par.h.y + hE.y + ch.m * p[1], par.h.z + hE.z + ch.m * p[2]};
+  par.J[0] += r0.x + d - ch.m * p[0] * p[0] - 2.0 * p[0] * hE.x;
+  par.J[1] += r1.x - ch.m * p[0] * p[1] - p[0] * hE.y - hE.x * p[1];
+  par.J[2] += r2.x - ch.m * p[0] * p[2] - p[0] * hE.z - hE.x * p[2];
+  par.J[3] += r1.y + d - ch.m * p[1] * p[1] - 2.0 * p[1] * hE.y;
+  par.J[4] += r2.y - ch.m * p[1] * p[2] - p[1] * hE.z - hE.y * p[2];
+  par.J[5] += r2.z + d - ch.m * p[2] * p[2] - 2.0 * p[2] * hE.z;
+}
+
+template <int NQ, bool FL>
+__device__ __forceinline__ void chain_crba(const ChainP& cp, const double (&s)[NQ], const double (&c)[NQ],
+                                           double (&M)[ChainDims<NQ, FL>::NV][ChainDims<NQ, FL>::NV]) {
+  constexpr int JO = ChainDims<NQ, FL>::JO;
+  Composite comp[NQ];
+#pragma unroll
+  for (int i = NQ - 1; i >= 0; --i) {
+    comp[i] = link_composite(cp.mass[i], cp.com[i], cp.I[i]);
+    if (i < NQ - 1) add_child(cp, i + 1, s[i + 1], c[i + 1], comp[i + 1], comp[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    // unit acceleration about joint i's axis (ẑ of frame i): wrench on the composite, about the frame-i origin
+    V3<double> n = {comp[i].J[2], comp[i].J[4], comp[i].J[5]};
+    V3<double> f = {-comp[i].h.y, comp[i].h.x, 0.0};
+    M[JO + i][JO + i] = n.z;
+#pragma unroll
+    for (int j = i; j >= 1; --j) {   // carry the wrench down to frame j−1; its ẑ moment is the coupling with joint j−1
+      f = to_parent<double>(cp, j, s[j], c[j], f);
+      n = to_parent<double>(cp, j, s[j], c[j], n) + c_cross<double>(cp.xyz[j], f);
+      M[JO + j - 1][JO + i] = n.z; M[JO + i][JO + j - 1] = n.z;
+    }
+    if constexpr (FL) {              // … and into the base frame: coupling with the base twist [ω; v]
+      f = to_parent<double>(cp, 0, s[0], c[0], f);
+      n = to_parent<double>(cp, 0, s[0], c[0], n) + c_cross<double>(cp.xyz[0], f);
+      M[0][6 + i] = n.x; M[1][6 + i] = n.y; M[2][6 + i] = n.z; M[3][6 + i] = f.x; M[4][6 + i] = f.y; M[5][6 + i] = f.z;
+      M[6 + i][0] = n.x; M[6 + i][1] = n.y; M[6 + i][2] = n.z; M[6 + i][3] = f.x; M[6 + i][4] = f.y; M[6 + i][5] = f.z;
+    }
+  }
+  if constexpr (FL) {   // base block: spatial inertia of the whole mechanism about the base origin, for 𝑣 = [ω; v]
+    Composite B = link_composite(cp.base_mass, cp.base_com, cp.base_I);
+    add_child(cp, 0, s[0], c[0], comp[0], B);
+    const double J[3][3] = {{B.J[0], B.J[1], B.J[2]}, {B.J[1], B.J[3], B.J[4]}, {B.J[2], B.J[4], B.J[5]}};
+    const double hx[3][3] = {{0.0, -B.h.z, B.h.y}, {B.h.z, 0.0, -B.h.x}, {-B.h.y, B.h.x, 0.0}};   // [h]×
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        M[a][b] = J[a][b];
+        M[a][3 + b] = hx[a][b];        // n = h × v̇
+        M[3 + a][b] = hx[b][a];        // f = ω̇ × h
+        M[3 + a][3 + b] = (a == b) ? B.m : 0.0;
+      }
+  }
+}
+
 // ---- thread-local forward dynamics (rollouts: one thread per trajectory) -----------------------
-// 𝑣̇ = M(θ)⁻¹ (u − bias(θ, 𝑣))
+// 𝑣̇ = M(θ)⁻¹ (u − bias(θ, 𝑣)): M by the composite-rigid-body algorithm, bias by one inverse-dynamics pass
 template <int NQ, bool FL>
 __device__ __forceinline__ void chain_forward_dynamics(const ChainP& cp, const double (&th)[NQ],
                                                        const double (&v)[ChainDims<NQ, FL>::NV],
@@ -184,15 +271,7 @@ __device__ __forceinline__ void chain_forward_dynamics(const ChainP& cp, const d
 #pragma unroll
     for (int i = 0; i < NV; ++i) rhs[i] = u[i] - bias[i];
   }
-#pragma unroll 1
-  for (int j = 0; j < NV; ++j) {   // column j of M = ID(θ, 0, e_j) without gravity
-    double e[NV], col[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) e[i] = (i == j) ? 1.0 : 0.0;
-    chain_rnea<double, NQ, FL>(cp, s, c, zero, e, 0.0, col);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) M[i][j] = col[i];
-  }
+  chain_crba<NQ, FL>(cp, s, c, M);
   // M is symmetric positive definite: Gaussian elimination without pivoting
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
