@@ -390,39 +390,51 @@ def run_b200(args):
     barrier()
     iso_ms = max_over_ranks(e0.elapsed_time(e1)) / iso_steps
 
-    dom = "bwd" if prof_acc["bwd_ms"] >= prof_acc["fwd_ms"] else "fwd"
-    per_traj = BWD_BYTES if dom == "bwd" else FWD_BYTES
-    dom_ms = prof_acc[dom + "_ms"]
-    achieved = per_traj * prof_acc["traj_iters"] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     full_iter_ms = (prof_acc["first_bwd_ms"] + prof_acc["first_fwd_ms"]) / iso_steps
-    first_dom_ms = prof_acc["first_" + dom + "_ms"] / iso_steps
-    roofline = {"bound": "hbm", "kernel": "bwd_lpt_two_link (+ lin/ric split kernels on small active sets)" if dom == "bwd" else "fwd_lpt_two_link",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": 1.632e9 if dom == "bwd" else 2.289e9, "peak_source": peak_src,
-                "traffic_note": "dram read+write per full-batch launch from profiles/ncu_full_r1_lpt_fullbatch.txt (algorithmic: %.3e)" % (per_traj * B_PER_GPU),
-                "algorithmic_bytes_per_trajectory": per_traj,
-                "avg_launch_ms": dom_ms / max(1, prof_acc[dom + "_launches"]),
-                "measured_on": "isolated solves (one batch at a time), CUDA events on the handle's stream; averaged over all launches of a fit incl. the latency-bound tail",
-                "full_batch_launch": {"ms": first_dom_ms, "achieved": per_traj * B / (first_dom_ms * 1e-3) / 1e9 if first_dom_ms else None,
-                                      "frac": per_traj * B / (first_dom_ms * 1e-3) / 1e9 / hbm_peak if first_dom_ms else None},
-                "both_kernels_GBps_full_batch_iteration": (BWD_BYTES + FWD_BYTES) * B / (full_iter_ms * 1e-3) / 1e9 if full_iter_ms else None}
-    # FP64-pipe view of the same launches (the binding roofline of this path): DFMA-class
-    # instructions per trajectory-step counted from SASS (tools/sass_mix.py), 2 flops each
     fp64_peak_tf = None
     try:
         fp64_peak_tf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_dfma_tflops"]
     except Exception:
         pass
+    # DFMA-class instructions per trajectory-step counted from SASS (tools/sass_mix.py), 2 flops each
     FP64_INSTR = {"bwd": 831, "fwd": 273}
-    flops = 2.0 * FP64_INSTR[dom] * H * prof_acc["traj_iters"]
-    roofline["fp64"] = {"achieved_tflops": flops / (dom_ms * 1e-3) / 1e12 if dom_ms else None, "peak_tflops": fp64_peak_tf,
-                        "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
-                        "fp64_instr_per_trajectory_step": FP64_INSTR[dom],
-                        "full_batch_launch_tflops": 2.0 * FP64_INSTR[dom] * H * B / (first_dom_ms * 1e-3) / 1e12 if first_dom_ms else None}
-    if fp64_peak_tf and roofline["fp64"]["achieved_tflops"]:
-        roofline["fp64"]["frac"] = roofline["fp64"]["achieved_tflops"] / fp64_peak_tf
-        if roofline["fp64"]["full_batch_launch_tflops"]:
-            roofline["fp64"]["full_batch_launch_frac"] = roofline["fp64"]["full_batch_launch_tflops"] / fp64_peak_tf
+    NCU_TRAFFIC = {"bwd": 1.632e9, "fwd": 2.289e9}      # dram read+write per full-batch launch (profiles/ncu_full_r1_fullbatch.txt)
+    NAMES = {"bwd": "backward pass: bwd_lpt_two_link (nslots > 20,000), lin_lpt + ric_lpt / ric_coop_two_link below",
+             "fwd": "fwd_lpt_two_link (+ fwd_retry_two_link for rejected step sizes)"}
+    pass_ms = prof_acc["bwd_ms"] + prof_acc["fwd_ms"]
+
+    def kernel_roofline(which):
+        per_traj = BWD_BYTES if which == "bwd" else FWD_BYTES
+        ms = prof_acc[which + "_ms"]
+        first_ms = prof_acc["first_" + which + "_ms"] / iso_steps
+        ach = per_traj * prof_acc["traj_iters"] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        flops = 2.0 * FP64_INSTR[which] * H * prof_acc["traj_iters"]
+        r = {"bound": "hbm", "kernel": NAMES[which], "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+             "traffic": NCU_TRAFFIC[which], "peak_source": peak_src,
+             "traffic_note": "dram read+write per full-batch launch from profiles/ncu_full_r1_fullbatch.txt (algorithmic: %.3e)" % (per_traj * B_PER_GPU),
+             "algorithmic_bytes_per_trajectory": per_traj, "avg_launch_ms": ms / max(1, prof_acc[which + "_launches"]),
+             "share_of_kernel_time": ms / pass_ms if pass_ms else None,
+             "measured_on": "isolated solves (one batch at a time), CUDA events on the handle's stream; averaged over all "
+                            "launches of a fit incl. the latency-bound tail (≈ 80 of 100 launches run on < 15 % of the batch)",
+             "full_batch_launch": {"ms": first_ms, "achieved": per_traj * B / (first_ms * 1e-3) / 1e9 if first_ms else None,
+                                   "frac": per_traj * B / (first_ms * 1e-3) / 1e9 / hbm_peak if first_ms else None},
+             "fp64": {"achieved_tflops": flops / (ms * 1e-3) / 1e12 if ms else None, "peak_tflops": fp64_peak_tf,
+                      "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
+                      "fp64_instr_per_trajectory_step": FP64_INSTR[which],
+                      "full_batch_launch_tflops": 2.0 * FP64_INSTR[which] * H * B / (first_ms * 1e-3) / 1e12 if first_ms else None}}
+        if fp64_peak_tf and r["fp64"]["achieved_tflops"]:
+            r["fp64"]["frac"] = r["fp64"]["achieved_tflops"] / fp64_peak_tf
+            if r["fp64"]["full_batch_launch_tflops"]:
+                r["fp64"]["full_batch_launch_frac"] = r["fp64"]["full_batch_launch_tflops"] / fp64_peak_tf
+        return r
+
+    # The single kernel with the largest share of the step is fwd_lpt_two_link (32 % of the serialised launch list,
+    # profiles/launches_r1_summary.csv; HBM-bound).  The backward PASS is larger in total (55 %) but split over four
+    # kernels (bwd_lpt 22 %, ric_coop 16 %, lin_lpt 12 %, ric_lpt 4 %) and FP64-bound: its view is in `backward_pass`.
+    roofline = kernel_roofline("fwd")
+    roofline["backward_pass"] = kernel_roofline("bwd")
+    roofline["backward_pass"]["bound_note"] = "FP64-pipe bound (see fp64.*); the hbm figures are given for completeness"
+    roofline["both_kernels_GBps_full_batch_iteration"] = (BWD_BYTES + FWD_BYTES) * B / (full_iter_ms * 1e-3) / 1e9 if full_iter_ms else None
     isolated = {"value": world * B / (iso_ms * 1e-3), "unit": UNIT, "ms_per_step": iso_ms,
                 "ms_per_iteration_full_batch": full_iter_ms, "batch_iterations_per_step": prof_acc["bwd_launches"] / iso_steps,
                 "note": "one batch at a time on one handle (no overlap between steps)"}
