@@ -58,6 +58,19 @@ function serial_chain_problem(joints::Matrix{Float64}, gravity::Vector{Float64},
     return p[]
 end
 
+"""
+Any `dynamicsf` (what passing a Julia function does in the reference, src/forward_pass.jl:148-153): `src` is CUDA C++
+defining `template <class T> __device__ void ilqr_dynamics(const T* x, const T* u, const double* p, T* xdot)`; it is
+compiled by NVRTC inside `Solver(p)`.  Keep `src` alive until the Solver exists (the struct holds a raw pointer).
+"""
+function custom_problem(src::String, n::Integer, m::Integer, H::Integer, B::Integer, dt::Float64, params::Vector{Float64})
+    p = Ref{Problem}()
+    ccall((:ilqr_problem_custom, lib), Int32,
+          (Ptr{Problem}, Int32, Int32, Int32, Int32, Float64, Cstring, Ptr{Float64}, Int32),
+          p, n, m, H, B, dt, src, params, length(params)) == 0 || error("problem")
+    return p[]
+end
+
 mutable struct Solver
     h::Ptr{Cvoid}
     p::Problem
@@ -123,6 +136,30 @@ function fit(x_init::Array{Float64,3}, u_init::Array{Float64,3}, p::Problem;
     st = download(s, STATUS, B; T = Int32)
     @assert !any(st .& 8 .!= 0)          # src/forward_pass.jl:168  prev_cost > new_cost
     return (download(s, X, N, n, B), download(s, U, M, m, B))
+end
+
+"""
+One call, host in → host out (upload, batched fit with per-trajectory convergence, download): `ilqr_solve`.
+Returns (x̄, ū, cost[B], iters[B], status[B]).
+"""
+function solve(s::Solver, x_init::Array{Float64,3}, u_init::Array{Float64,3}; max_iter::Int64 = 100, tol::Float64 = 1e-6)
+    B = s.p.B
+    x = similar(x_init); u = similar(u_init)
+    cost = Vector{Float64}(undef, B); iters = Vector{Int32}(undef, B); status = Vector{Int32}(undef, B)
+    check(ccall((:ilqr_solve, lib), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                s.h, x_init, u_init, C_NULL, max_iter, tol, x, u, cost, iters, status), s.h)
+    return (x, u, cost, iters, status)
+end
+
+"Receding-horizon MPC (BASELINE config 5): `mpc_start!` once, then `mpc_step!` per plant step → (u_applied[m,B], x_plant[n,B])."
+mpc_start!(s::Solver, x0::Matrix{Float64}) =
+    check(ccall((:ilqr_mpc_start, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), s.h, x0, C_NULL), s.h)
+function mpc_step!(s::Solver; max_iter::Int64 = 3, tol::Float64 = 1e-6)
+    ua = Matrix{Float64}(undef, s.p.m, s.p.B); xp = Matrix{Float64}(undef, s.p.n, s.p.B)
+    check(ccall((:ilqr_mpc_step, lib), Int32, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}, Ptr{Float64}), s.h, max_iter, tol, ua, xp), s.h)
+    return (ua, xp)
 end
 
 # single-problem convenience with the reference's exact shapes x[N×n], u[H×m]
