@@ -413,6 +413,8 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
       c.I[i][0] = Ic[0]; c.I[i][1] = 0.5 * (Ic[1] + Ic[3]); c.I[i][2] = 0.5 * (Ic[2] + Ic[6]);
       c.I[i][3] = Ic[4]; c.I[i][4] = 0.5 * (Ic[5] + Ic[7]); c.I[i][5] = Ic[8];
       std::memcpy(Cprev, C, sizeof C);
+      if (i == p->nq - 1)   // Izz + m (cx² + cy²) in the canonical frame
+        c.last_diag = c.I[i][5] + c.mass[i] * (c.com[i][0] * c.com[i][0] + c.com[i][1] * c.com[i][1]);
     }
   }
   if (is_custom) {

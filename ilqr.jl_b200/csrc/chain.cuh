@@ -39,6 +39,8 @@ struct ChainP {
   double dt;
   // floating base (RBD_helper_functions.jl:7, floating = true): inertial of the root link, in its own frame
   double base_mass, base_com[3], base_I[6];
+  // M[last][last]: inertia of the last link about its own joint axis (+z of its canonical frame) — independent of q
+  double last_diag;
 };
 
 // Dimensions of a mechanism: NQ revolute joints, optionally hanging off a free-floating base link.

@@ -52,8 +52,8 @@ template <int NQ, bool FL> struct BwdSmem : RiccatiSmem<ChainDims<NQ, FL>::n, Ch
   double invd[NV];              // 1 / diagonal of the upper factor
   // inverse-dynamics scratch.  The link loops are rolled (the unrolled version was 8.4 k instructions and
   // instruction-fetch bound), so per-link state is indexed dynamically and lives here, [item][lane] with a lane
-  // stride of LS = n + m + 1 (only the column-owner lanes keep state; the others neither store nor matter):
-  static constexpr int LS = n + m + 1;
+  // stride of LS = n + m (only the lanes that carry a tangent direction keep state; the others neither store nor matter):
+  static constexpr int LS = n + m;
   double fn[NQ * 6 * LS];       // per lane: f_i, n_i (primal pass) or their tangents (dual pass)
   double fnv[NQ * 6];           // dual pass: the values of f_i, n_i (the same on every lane)
   double tng[2 * NV * LS];      // per lane, per velocity coordinate j: (𝑣_j, 𝑣̇_j) in the primal pass, (δq_j, δ𝑣_j) in the dual
@@ -62,12 +62,14 @@ template <int NQ, bool FL> struct BwdSmem : RiccatiSmem<ChainDims<NQ, FL>::n, Ch
   double qv[2 * NV];            // stage point (configuration, velocity)
   double sc[2 * NQ];            // sin θ_i, cos θ_i
   double vd[NV];                // 𝑣̇ at the stage point
-  // Software pipelining of the primal pass (fixed base, when NV + 1 lanes are free next to the LS column owners):
-  // lanes LS … LS+NV ride along in the dual pass of stage s and compute — in the VALUE half of the dual arithmetic,
-  // which every lane executes anyway — the columns of M and the bias at the point of stage s+1 (known once v̇ of stage
-  // s is known; for the last stage: the first stage of the next time step).  That removes the separate primal pass.
-  static constexpr bool PIPE = !FL && (LS + NV + 1 <= 32);
-  static constexpr int NSP = PIPE ? NV + 1 : 1;
+  // Software pipelining of the primal pass (when NV lanes are free next to the LS tangent lanes): lanes LS … LS+NV−1
+  // ride along in the dual pass of stage s and compute — in the VALUE half of the dual arithmetic, which every lane
+  // executes anyway — the bias and the first NV−1 columns of M at the point of stage s+1 (known once v̇ of stage s is
+  // known; for the last stage: the first stage of the next time step).  The last column of M follows from symmetry
+  // and a constant (the last link's inertia about its own joint axis, ChainP::last_diag).  That removes the separate
+  // primal pass.  Riding lane sp = lane − LS: sp < NV−1 → column sp of M, sp = NV−1 → bias.
+  static constexpr bool PIPE = LS + NV <= 32;
+  static constexpr int NSP = PIPE ? NV : 1;
   double Mn[NV * NV];           // M at the next stage point (unfactored), bias there
   double bn[NV];
   double scn[2 * NQ];           // sin / cos of the next stage point's joint angles
@@ -96,7 +98,7 @@ template <int NQ, bool FL> struct PrimalIO {
 template <int NQ, bool FL> struct DualIO {
   static constexpr int JO = ChainDims<NQ, FL>::JO, NV = ChainDims<NQ, FL>::NV, LS = BwdSmem<NQ, FL>::LS, NSP = BwdSmem<NQ, FL>::NSP;
   static constexpr bool PIPE = BwdSmem<NQ, FL>::PIPE;
-  BwdSmem<NQ, FL>& sm; int l; bool on; int sp;   // sp ≥ 0: riding lane (sp < NV: column sp of the next M; sp = NV: next bias)
+  BwdSmem<NQ, FL>& sm; int l; bool on; int sp;   // sp ≥ 0: riding lane (sp < NV−1: column sp of the next M; sp = NV−1: next bias)
   // where this lane's VALUE inputs live (selected once, so that the accessors below are straight-line code)
   const double* scp; const double* velp; const double* fnvp; double vmask; int fs, fo;
   __device__ __forceinline__ DualIO(BwdSmem<NQ, FL>& sm_, int l_, bool on_, int sp_) : sm(sm_), l(l_), on(on_), sp(sp_) {
@@ -104,7 +106,7 @@ template <int NQ, bool FL> struct DualIO {
     scp = r ? sm.scn : sm.sc;
     velp = r ? sm.vn : sm.qv + NV;
     fnvp = r ? sm.fnv2() : sm.fnv;
-    vmask = (r && sp < NV) ? 0.0 : 1.0;      // the M-column lanes run at zero velocity
+    vmask = (r && sp < NV - 1) ? 0.0 : 1.0;  // the M-column lanes run at zero velocity
     fs = r ? NSP : 1; fo = r ? sp : 0;
   }
   __device__ __forceinline__ bool ride() const { if constexpr (PIPE) return sp >= 0; else return false; }
@@ -113,7 +115,7 @@ template <int NQ, bool FL> struct DualIO {
   __device__ __forceinline__ Dual vel(int j) const { return {velp[j] * vmask, sm.tng[(2 * j + 1) * LS + l]}; }
   __device__ __forceinline__ Dual acc(int j) const {
     const double a = sm.vd[j];
-    return {ride() ? (sp == j ? 1.0 : 0.0) : a, 0.0};
+    return {ride() ? ((sp == j && sp < NV - 1) ? 1.0 : 0.0) : a, 0.0};
   }
   __device__ __forceinline__ void put(int i, int k, Dual v) const {
     if (ride() || on) fnvp_mut()[(i * 6 + k) * fs + fo] = v.v;
@@ -121,7 +123,7 @@ template <int NQ, bool FL> struct DualIO {
   }
   __device__ __forceinline__ Dual get(int i, int k) const { return {fnvp[(i * 6 + k) * fs + fo], sm.fn[(i * 6 + k) * LS + l]}; }
   __device__ __forceinline__ void out(int j, Dual v) const {
-    if (ride()) { if (sp < NV) sm.Mn[j + NV * sp] = v.v; else sm.bn[j] = v.v; }
+    if (ride()) { if (sp < NV - 1) sm.Mn[j + NV * sp] = v.v; else sm.bn[j] = v.v; }
     else if (on) sm.tng[(2 * j + 1) * LS + l] = v.t;
   }
   __device__ __forceinline__ double* fnvp_mut() const { return const_cast<double*>(fnvp); }
@@ -236,8 +238,12 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
   const int l = on ? lane : LS - 1;
   if constexpr (PIPE) {
     __syncwarp();   // the previous dual pass has delivered Mn / bn; nobody reads Mf / sc any more
-    for (int idx = lane; idx < NV * NV; idx += 32) sm.Mf[idx] = sm.Mn[idx];
-    if (lane < NV) sm.bias[lane] = sm.bn[lane];
+    for (int idx = lane; idx < NV * (NV - 1); idx += 32) sm.Mf[idx] = sm.Mn[idx];
+    if (lane < NV) {
+      sm.bias[lane] = sm.bn[lane];
+      // last column: by symmetry from the last row of the other columns; its diagonal entry is configuration-independent
+      sm.Mf[lane + NV * (NV - 1)] = (lane < NV - 1) ? sm.Mn[(NV - 1) + NV * lane] : cp.last_diag;
+    }
     if (lane < 2 * NQ) sm.sc[lane] = sm.scn[lane];
     __syncwarp();
   } else {
@@ -262,7 +268,7 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
   int sp = -1;
   if constexpr (PIPE) {
     // the point the riding lanes work at: the next stage's (same arithmetic as chain_linearize uses to form it)
-    sp = (lane >= LS && lane < LS + NV + 1) ? lane - LS : -1;
+    sp = (lane >= LS && lane < LS + NV) ? lane - LS : -1;
     double thn = 0.0;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
@@ -286,7 +292,7 @@ __device__ __forceinline__ void chain_stage(const ChainP& cp, BwdSmem<NQ, FL>& s
     }
   }
   __syncwarp();
-  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>(sm, l, on, sp), (sp >= 0 && sp < NV) ? 0.0 : 1.0);
+  warp_rnea<Dual, DualIO<NQ, FL>, NQ, FL>(cp, DualIO<NQ, FL>(sm, l, on, sp), (sp >= 0 && sp < NV - 1) ? 0.0 : 1.0);
 #pragma unroll
   for (int i = 0; i < NV; ++i) dvdot[i] = ((udir == i) ? 1.0 : 0.0) - sm.tng[(2 * i + 1) * LS + l];
   m_solve<NV>(sm.Mf, sm.invd, dvdot);
