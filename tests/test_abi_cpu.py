@@ -69,3 +69,53 @@ def test_product_package_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_problem_validation_happens_before_any_device_work():
+    """Unsupported problems are refused with a message by ilqr_create (ILQR_ERR_INVALID), on any machine."""
+    import np_chain
+    joints = np_chain.seven_dof_chain()
+
+    def create_error(p):
+        with pytest.raises(ilqr_b200.IlqrError) as e:
+            ilqr_b200.BatchSolver(p)
+        return str(e.value)
+
+    p = ilqr_b200.two_link_problem(10, 2); p.abi_version = 1
+    assert "abi_version" in create_error(p)
+    p = ilqr_b200.two_link_problem(10, 2); p.n = 5
+    assert "unsupported model" in create_error(p)
+    p = ilqr_b200.two_link_problem(10, 2); p.n_alpha = 0
+    assert "bad H/B/n_alpha" in create_error(p)
+    p = ilqr_b200.serial_chain_problem(joints[:5], 10, 2)                       # 5 joints: not an instantiated size
+    assert "nq in" in create_error(p)
+    bad = joints.copy(); bad[2, 6:9] = (0.0, 0.5, 0.5)                          # not a unit axis
+    assert "unit vectors" in create_error(ilqr_b200.serial_chain_problem(bad, 10, 2))
+    bad = joints.copy(); bad[3, 9] = 0.0
+    assert "masses" in create_error(ilqr_b200.serial_chain_problem(bad, 10, 2))
+    p = ilqr_b200.serial_chain_problem(joints[:2], 10, 2, base=(30.0, [0, 0, 0], [50, 0, 0, 50, 0, 50]))
+    assert (p.model_id, p.n, p.m) == (_abi.MODEL_FLOATING_CHAIN, 16, 8)
+    p.gravity[2] = -9.81
+    assert "gravity must be zero" in create_error(p)
+    with pytest.raises(ValueError):
+        ilqr_b200.serial_chain_problem(joints[:2], 10, 2, gravity=(0, 0, -9.81), base=(30.0, [0, 0, 0], [50, 0, 0, 50, 0, 50]))
+
+
+def test_urdf_loader_rejects_what_it_cannot_model(tmp_path):
+    urdf = tmp_path / "tree.urdf"
+    urdf.write_text("""<robot name="t"><link name="a"/><link name="b"/><link name="c"/>
+      <joint name="j1" type="revolute"><parent link="a"/><child link="b"/><axis xyz="0 0 1"/></joint>
+      <joint name="j2" type="revolute"><parent link="a"/><child link="c"/><axis xyz="0 0 1"/></joint></robot>""")
+    with pytest.raises(ValueError, match="not a serial chain"):
+        ilqr_b200.load_urdf(str(urdf))
+    urdf.write_text("""<robot name="t"><link name="a"/><link name="b"><inertial><mass value="1"/>
+      <inertia ixx="1" ixy="0" ixz="0" iyy="1" iyz="0" izz="1"/></inertial></link>
+      <joint name="j1" type="prismatic"><parent link="a"/><child link="b"/><axis xyz="0 0 1"/></joint></robot>""")
+    with pytest.raises(ValueError, match="only revolute"):
+        ilqr_b200.load_urdf(str(urdf))
+    urdf.write_text("""<robot name="t"><link name="a"/><link name="b"><inertial><mass value="2"/><origin xyz="0.1 0 0"/>
+      <inertia ixx="1" ixy="0" ixz="0" iyy="2" iyz="0" izz="3"/></inertial></link>
+      <joint name="j1" type="continuous"><parent link="a"/><child link="b"/><origin xyz="0 0 1" rpy="0 0 0.5"/><axis xyz="0 2 0"/></joint></robot>""")
+    joints, base = ilqr_b200.load_urdf(str(urdf))
+    assert joints.shape == (1, 20) and base[0] == 0.0
+    assert list(joints[0, :13]) == [0, 0, 1, 0, 0, 0.5, 0, 1, 0, 2, 0.1, 0, 0] and list(joints[0, 13:19]) == [1, 0, 0, 2, 0, 3]
