@@ -4,7 +4,7 @@ B = 65,536 trajectories per GPU, fp64), one process per GPU.
 
 A "step" = one batched `fit` (src/forward_pass.jl:148-179 semantics, tol 1e-6, max_iter 100)
 of the whole batch.  The K timed steps go through the library's pool scheduler (ilqr_pool_*),
-which keeps up to 6 batches in flight per GPU so the latency-bound tail of one batch overlaps
+which keeps up to 8 batches in flight per GPU so the latency-bound tail of one batch overlaps
 the full-width iterations of the next; each step still solves its whole batch to the same
 result.  `value` times this with the inputs resident in HBM (boundary layout → device layout →
 fit → boundary layout, all on device); `e2e` is the same with pinned HOST buffers (H2D and D2H
@@ -44,8 +44,8 @@ WORKLOAD = "configs[1]: batched 2-link arm, B=65536 x0~U[0,1)^4 per GPU, H=200, 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=36, help="timed steps (batched fits); 36 = six rounds of the six pool handles, so the pipeline fill and the un-overlapped tail of the last batches are amortised")
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=40, help="timed steps (batched fits); 40 = five rounds of the eight pool handles, so the pipeline fill and the un-overlapped tail of the last batches are amortised")
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (debug only; default = config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample duration")
@@ -285,7 +285,8 @@ def pin_to_gpu_numa(index):
 
 
 # --------------------------------------------------------------------------- GPU arm
-IN_FLIGHT = 6   # batches kept in flight per GPU by the pool scheduler (ilqr_pool_*); --in-flight overrides
+IN_FLIGHT = 8   # batches kept in flight per GPU by the pool scheduler (ilqr_pool_*); --in-flight overrides
+                # (measured at K = 36: 6 → 2.22 M / 1.98 M, 8 → 2.28 M / 2.01 M, 10 → 2.28 M / 2.03 M solves/s resident / e2e)
 
 
 def run_b200(args):
