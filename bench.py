@@ -2,14 +2,18 @@
 """bench.py — iLQR solves/sec on BASELINE.json config 2 (batched 2-link arm, H=200,
 B = 65,536 trajectories per GPU, fp64), one process per GPU.
 
-A "step" = one batched `fit` (src/forward_pass.jl:148-179 semantics, tol 1e-6, max_iter 100)
-of the whole batch.  The K timed steps go through the library's pool scheduler (ilqr_pool_*),
-which keeps up to 8 batches in flight per GPU so the latency-bound tail of one batch overlaps
-the full-width iterations of the next; each step still solves its whole batch to the same
-result.  `value` times this with the inputs resident in HBM (boundary layout → device layout →
-fit → boundary layout, all on device); `e2e` is the same with pinned HOST buffers (H2D and D2H
-inside the timed region, through ilqr_pool_submit = ilqr_solve per batch); `isolated` reports one
-batch at a time.  `roofline` comes from the isolated solves (per-kernel CUDA-event times).
+A "step" = one batch of 65,536 trajectories solved with `fit` semantics (src/forward_pass.jl:148-179,
+tol 1e-6, max_iter 100 per trajectory).  The K timed steps are submitted to the library's streamer
+(ilqr_streamer_*, csrc/kernels_round.cu): one launch per iLQR iteration runs backward sweep, forward
+sweep, accept / converge test, retirement and admission for 56,832 slots (148 SMs x 12 warps x 32
+lanes); a slot whose trajectory finishes takes the next pending one, of the same or the next batch,
+so every launch runs full width although iteration counts range from 5 to 100.  Every trajectory
+still comes out bit-identical to a plain batched solve of its batch (tests/test_gpu_parity.py).
+`value` times this with the batches resident in HBM (the kernels read and write the caller's
+boundary-layout arrays directly); `e2e` is the same with pinned HOST buffers (upload and copy-back
+inside the timed region, ilqr_streamer_submit); `batch_pool` is the batch-synchronous scheduler
+(ilqr_pool_*, what round 1 first shipped) and `isolated` one batch at a time on one handle.
+`roofline` is for the round kernel, from CUDA events on the launching stream over the timed region.
 Shards are independent (no data-path collective); NCCL only gathers the per-trajectory costs /
 iteration counts after the timed region.
 
@@ -44,7 +48,7 @@ WORKLOAD = "configs[1]: batched 2-link arm, B=65536 x0~U[0,1)^4 per GPU, H=200, 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40, help="timed steps (batched fits); 40 = five rounds of the eight pool handles, so the pipeline fill and the un-overlapped tail of the last batches are amortised")
+    ap.add_argument("--steps", type=int, default=40, help="timed steps (batches of 65,536 trajectories); the stream's final drain (the stragglers of the last batches) is inside the timed region, 40 steps amortise it to ~10 %%")
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (debug only; default = config 2)")
@@ -52,6 +56,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--in-flight", type=int, default=None, help="batches in flight per GPU (pool handles)")
+    ap.add_argument("--ring", type=int, default=12, help="batches in flight in the streamer")
+    ap.add_argument("--pool-steps", type=int, default=16, help="timed steps of the batch-synchronous pool comparison (0 = skip)")
     ap.add_argument("--no-aux", action="store_true", help="skip the configs[3] (7-DoF chain) side measurement")
     return ap.parse_args()
 
@@ -316,7 +322,10 @@ def run_b200(args):
 
     prob = ilqr_b200.two_link_problem(H, B, device=local)
     s = ilqr_b200.BatchSolver(prob)
-    pool = ilqr_b200.SolverPool(prob, IN_FLIGHT)
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    SLOTS = n_sm * 12 * 32            # one block of 12 warps per SM (csrc/kernels_round.cu)
+    RING = args.ring
+    streamer = ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, SLOTS, device=local), B, ring=RING, max_iter=MAX_ITER, tol=TOL)
 
     # inputs: generated once, kept resident in HBM in the boundary layout
     x0 = np.asfortranarray(make_x0(B, rank).T)
@@ -325,7 +334,6 @@ def run_b200(args):
     dx = torch.empty((B, N_, NKNOT), dtype=torch.float64, device="cuda")     # == Julia x[N,n,B]
     du = torch.zeros((B, M_, H), dtype=torch.float64, device="cuda")
     s.download_device(_abi.X, dx.data_ptr())
-    outs = [(torch.empty_like(dx), torch.empty_like(du)) for _ in range(IN_FLIGHT)]
     torch.cuda.synchronize()
 
     def barrier():
@@ -340,41 +348,75 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
-    def run_pipelined(steps, submit_one):
-        """`steps` batch solves through the pool, at most IN_FLIGHT in flight; CUDA events bracket the region."""
+    def run_windowed(steps, submit_one, wait_one, window):
+        """`steps` batches, at most `window` in flight; CUDA events on the current stream bracket the region (every
+        submitted batch is complete, results delivered, before the closing event is recorded)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = pool.launch_count()
         e0.record()
         tickets = []
         for i in range(steps):
-            if i >= IN_FLIGHT:
-                pool.wait(tickets[i - IN_FLIGHT])     # its output buffers are about to be reused
+            if i >= window:
+                wait_one(tickets[i - window])     # its output buffers are about to be reused
             tickets.append(submit_one(i))
-        for t in tickets[max(0, steps - IN_FLIGHT):]:
-            pool.wait(t)
+        for t in tickets[max(0, steps - window):]:
+            wait_one(t)
         e1.record()
         barrier()
-        return max_over_ranks(e0.elapsed_time(e1)), pool.launch_count() - l0
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def out_set(dev):
+        mk = (lambda t: t.cuda()) if dev else (lambda t: t.pin_memory())
+        return [mk(torch.empty((B, N_, NKNOT), dtype=torch.float64)), mk(torch.empty((B, M_, H), dtype=torch.float64)),
+                mk(torch.empty(B, dtype=torch.float64)), mk(torch.empty(B, dtype=torch.int32)), mk(torch.empty(B, dtype=torch.int32))]
+
+    # ---- headline: K batches through the streamer, resident in HBM
+    douts = [out_set(True) for _ in range(RING)]
 
     def submit_resident(i):
-        ox, ou = outs[i % IN_FLIGHT]
-        return pool.submit_ptrs(dx.data_ptr(), du.data_ptr(), None, MAX_ITER, TOL, ox.data_ptr(), ou.data_ptr(), device=True)
+        return streamer.submit_ptrs(dx.data_ptr(), du.data_ptr(), *[t.data_ptr() for t in douts[i % RING]], device=True)
 
     if args.warmup > 0:
-        run_pipelined(max(args.warmup, IN_FLIGHT), submit_resident)   # every handle warmed at least once
+        run_windowed(args.warmup, submit_resident, streamer.wait, RING)
     clocks = ClockSampler(local); clocks.start()
-    ms_total, launches = run_pipelined(args.steps, submit_resident)
+    p0, l0 = streamer.profile(), streamer.launch_count()
+    ms_total = run_windowed(args.steps, submit_resident, streamer.wait, RING)
+    p1, launches = streamer.profile(), streamer.launch_count() - l0
     clk = clocks.stop()
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
+    round_ms, rounds_timed = p1["round_ms"] - p0["round_ms"], p1["rounds_timed"] - p0["rounds_timed"]
+    rounds_total = p1["rounds_launched"] - p0["rounds_launched"]
+    iters_dev = douts[0][3].clone(); cost_dev = douts[0][2].clone(); status_dev = douts[0][4].clone()
+    mean_iters = float(iters_dev.double().mean().item())
+
+    # ---- comparison: the batch-synchronous pool scheduler (several handles, one batch each)
+    batch_pool = None
+    if args.pool_steps > 0:
+        pool = ilqr_b200.SolverPool(prob, IN_FLIGHT)
+        pouts = [(torch.empty_like(dx), torch.empty_like(du)) for _ in range(IN_FLIGHT)]
+
+        def submit_pool(i):
+            ox, ou = pouts[i % IN_FLIGHT]
+            return pool.submit_ptrs(dx.data_ptr(), du.data_ptr(), None, MAX_ITER, TOL, ox.data_ptr(), ou.data_ptr(), device=True)
+
+        run_windowed(IN_FLIGHT, submit_pool, pool.wait, IN_FLIGHT)
+        ms_pool = run_windowed(args.pool_steps, submit_pool, pool.wait, IN_FLIGHT)
+        batch_pool = {"value": world * B / (ms_pool / args.pool_steps * 1e-3), "unit": UNIT, "ms_per_step": ms_pool / args.pool_steps,
+                      "steps": args.pool_steps, "batches_in_flight": IN_FLIGHT,
+                      "note": "ilqr_pool_*: %d handles, each solving one whole batch at a time (backward / forward / commit / "
+                              "compaction launches per iteration); inputs resident in HBM" % IN_FLIGHT}
+        same = bool(torch.equal(pouts[0][0], douts[0][0]) and torch.equal(pouts[0][1], douts[0][1]))
+        batch_pool["results_identical_to_streamer"] = same
+        pool.close()
+        del pouts
 
     # ---- one batch at a time on a single handle: per-kernel device times for the roofline, and the
     # latency of an isolated solve
     stream = torch.cuda.ExternalStream(s.stream_ptr(), device=torch.device("cuda", local))
     prof_acc = dict(bwd_ms=0.0, fwd_ms=0.0, bwd_launches=0, fwd_launches=0, traj_iters=0.0, first_bwd_ms=0.0, first_fwd_ms=0.0)
     iso_steps = 3
-    ox, ou = outs[0]
+    ox, ou = douts[1 % RING][0], douts[1 % RING][1]
     for rep in range(1 + iso_steps):
         if rep == 1:
             barrier()
@@ -429,54 +471,75 @@ def run_b200(args):
                 r["fp64"]["full_batch_launch_frac"] = r["fp64"]["full_batch_launch_tflops"] / fp64_peak_tf
         return r
 
-    # The single kernel with the largest share of the step is fwd_lpt_two_link (32 % of the serialised launch list,
-    # profiles/launches_r1_summary.csv; HBM-bound).  The backward PASS is larger in total (55 %) but split over four
-    # kernels (bwd_lpt 22 %, ric_coop 16 %, lin_lpt 12 %, ric_lpt 4 %) and FP64-bound: its view is in `backward_pass`.
-    roofline = kernel_roofline("fwd")
-    roofline["backward_pass"] = kernel_roofline("bwd")
-    roofline["backward_pass"]["bound_note"] = "FP64-pipe bound (see fp64.*); the hbm figures are given for completeness"
-    roofline["both_kernels_GBps_full_batch_iteration"] = (BWD_BYTES + FWD_BYTES) * B / (full_iter_ms * 1e-3) / 1e9 if full_iter_ms else None
+    # ---- roofline of the round kernel (every launch of the timed region): CUDA events on the launching stream, fence to
+    # fence over groups of 8 back-to-back launches (csrc/capi.cu round_group); algorithmic bytes and FP64 instructions of
+    # the trajectory-iterations those launches performed
+    ITER_BYTES = BWD_BYTES + FWD_BYTES                        # 60,904 B per trajectory-iteration
+    FP64_ROUND = FP64_INSTR["bwd"] + FP64_INSTR["fwd"]        # 1,104 DFMA-class instructions per trajectory-step (SASS)
+    traj_iters_total = mean_iters * B * args.steps            # every step solves the same batch
+    share = rounds_timed / rounds_total if rounds_total else 0.0
+    avg_launch_ms = round_ms / rounds_timed if rounds_timed else None
+    ach = ITER_BYTES * traj_iters_total * share / (round_ms * 1e-3) / 1e9 if round_ms else 0.0
+    tfl = 2.0 * FP64_ROUND * H * traj_iters_total * share / (round_ms * 1e-3) / 1e12 if round_ms else None
+    roofline = {
+        "bound": "hbm", "kernel": "round_lpt_two_link<12, 4> (backward sweep + forward sweep + accept / converge test + retirement + admission; "
+                                  "the only kernel launched in the timed region)",
+        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 2.81e9, "peak_source": peak_src,
+        "traffic_note": "dram read+write of one full-width launch under ncu (profiles/ncu_full_r1_round.txt): 2.20 GB read + 0.61 GB "
+                        "written; algorithmic %.3e B for %d slots — part of the gains written by the backward sweep is still in L2 "
+                        "when the forward sweep reads it" % (ITER_BYTES * SLOTS, SLOTS),
+        "algorithmic_bytes_per_trajectory_iteration": ITER_BYTES, "avg_launch_ms": avg_launch_ms, "launches_timed": rounds_timed,
+        "launches_in_timed_region": rounds_total, "slots": SLOTS,
+        "trajectory_iterations_per_launch": traj_iters_total / rounds_total if rounds_total else None,
+        "measured_on": "the K timed steps (resident arm): CUDA events on the streamer's stream around every group of 8 launches; includes the "
+                       "final drain, whose launches run on the stragglers only",
+        "fp64": {"achieved_tflops": tfl, "peak_tflops": fp64_peak_tf, "frac": tfl / fp64_peak_tf if (tfl and fp64_peak_tf) else None,
+                 "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
+                 "fp64_instr_per_trajectory_step": FP64_ROUND,
+                 "note": "the binding roofline: the FP64 pipe is 75 % active in a full-width launch (ncu), HBM traffic 3.0 TB/s"},
+        "batch_path_kernels": {"fwd_lpt_two_link": kernel_roofline("fwd"), "backward_pass": kernel_roofline("bwd")},
+    }
     isolated = {"value": world * B / (iso_ms * 1e-3), "unit": UNIT, "ms_per_step": iso_ms,
                 "ms_per_iteration_full_batch": full_iter_ms, "batch_iterations_per_step": prof_acc["bwd_launches"] / iso_steps,
-                "note": "one batch at a time on one handle (no overlap between steps)"}
+                "note": "one batch at a time on one handle through the batch path (ilqr_fit: no overlap between steps)"}
 
     # ---- end to end through the host-facing C-ABI call with pinned host buffers (H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
         hx = torch.empty((B, N_, NKNOT), dtype=torch.float64).pin_memory(); hx.copy_(dx)
         hu = torch.zeros((B, M_, H), dtype=torch.float64).pin_memory()
-        houts = [(torch.empty_like(hx).pin_memory(), torch.empty_like(hu).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
-                  torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(IN_FLIGHT)]
+        houts = [out_set(False) for _ in range(RING)]
 
         def submit_host(i):
-            hox, hou, hc, hi, hs = houts[i % IN_FLIGHT]
-            return pool.submit_ptrs(hx.data_ptr(), hu.data_ptr(), None, MAX_ITER, TOL, hox.data_ptr(), hou.data_ptr(),
-                                    hc.data_ptr(), hi.data_ptr(), hs.data_ptr(), device=False)
+            return streamer.submit_ptrs(hx.data_ptr(), hu.data_ptr(), *[t.data_ptr() for t in houts[i % RING]], device=False)
 
-        run_pipelined(IN_FLIGHT, submit_host)
-        ms_e2e, _ = run_pipelined(args.steps, submit_host)
+        run_windowed(max(3, min(args.warmup, RING)), submit_host, streamer.wait, RING)
+        r0 = streamer.rounds()
+        ms_e2e = run_windowed(args.steps, submit_host, streamer.wait, RING)
+        e2e_rounds = streamer.rounds() - r0
         h2d = hx.numel() * 8 + hu.numel() * 8
         d2h = hx.numel() * 8 + hu.numel() * 8 + B * 8 + B * 4 + B * 4
-        # one isolated host-to-host solve for reference
+        # one isolated host-to-host solve of a single batch for reference (batch path: ilqr_solve)
+        hs1 = houts[1 % RING]
         barrier(); t0 = time.perf_counter()
-        pool.wait(submit_host(0)); torch.cuda.synchronize()
+        s.solve_ptrs(hx.data_ptr(), hu.data_ptr(), MAX_ITER, TOL, *[t.data_ptr() for t in hs1])
+        torch.cuda.synchronize()
         iso_e2e_ms = (time.perf_counter() - t0) * 1e3
         e2e = {"value": world * B / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "batches_in_flight": IN_FLIGHT,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "batches_in_flight": RING, "launches": e2e_rounds,
                "isolated_ms_per_step": iso_e2e_ms,
-               "api": "ilqr_pool_submit (= ilqr_solve per batch): pinned host x_init,u_init in, host x,u,cost,iters,status out"}
-        final_cost_sample = float(houts[0][2].mean().item())
+               "results_identical_to_resident_arm": bool(torch.equal(houts[0][0], douts[0][0].cpu()) and torch.equal(houts[0][3], douts[0][3].cpu())),
+               "api": "ilqr_streamer_submit: pinned host x_init,u_init in, host x,u,cost,iters,status out; uploads and copy-backs run on "
+                      "copy streams beside the rounds"}
+    streamer.close()
 
-    # the only collective: gather final costs / iteration counts (after the timed region)
-    iters = torch.from_numpy(s.download(_abi.ITERS)).cuda()
-    cost = torch.from_numpy(s.download(_abi.PREV_COST)).cuda()
+    # the only collective: gather final costs / iteration counts / status of the timed steps' batch (after the timed region)
+    iters, cost, status = iters_dev, cost_dev, status_dev
     if world > 1:
         gi = [torch.empty_like(iters) for _ in range(world)]; gc = [torch.empty_like(cost) for _ in range(world)]
-        dist.all_gather(gi, iters); dist.all_gather(gc, cost)
-        iters, cost = torch.cat(gi), torch.cat(gc)
-    status = s.download(_abi.STATUS)
-
-    pool.close()
+        gs = [torch.empty_like(status) for _ in range(world)]
+        dist.all_gather(gi, iters); dist.all_gather(gc, cost); dist.all_gather(gs, status)
+        iters, cost, status = torch.cat(gi), torch.cat(gc), torch.cat(gs)
     s.close()
     other = None
     if rank == 0 and world == 1 and not args.no_aux and B == B_PER_GPU:
@@ -493,16 +556,18 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD if B == B_PER_GPU else WORKLOAD + " [DEBUG batch=%d]" % B,
-                       "trajectories_per_gpu": B, "batches_in_flight": IN_FLIGHT,
-                       "step": "one batched fit of the whole batch; the K steps are submitted to the pool scheduler, which keeps up to %d "
-                               "batches in flight so that the latency-bound tail of one overlaps the bulk of the next (every step still "
-                               "solves its full batch to the same result); see `isolated` for one batch at a time" % IN_FLIGHT,
-                       "l2_policy": "inputs larger than L2 (%.2f GB working set per handle vs 126 MB L2)" % (3.2 * B / 65536),
+                       "trajectories_per_gpu": B, "batches_in_flight": RING, "slots": SLOTS,
+                       "step": "one batch of %d trajectories solved to fit's per-trajectory convergence (tol 1e-6, max_iter 100); the K steps "
+                               "are submitted to the streamer, which solves them as one stream through %d slots — a slot that finishes a "
+                               "trajectory takes the next pending one in the same launch (up to %d batches in flight); every trajectory "
+                               "comes out bit-identical to a batched solve of its batch; `batch_pool` = the batch-synchronous "
+                               "scheduler, `isolated` = one batch at a time" % (B, SLOTS, RING),
+                       "l2_policy": "inputs larger than L2 (%.2f GB slot working set + %d x 0.63 GB batches in flight vs 126 MB L2)" % (3.2 * SLOTS / 65536, RING),
                        "sharding": "independent batch slices per GPU, no data-path collective",
                        "cpu_affinity": affinity},
-            "isolated": isolated,
+            "isolated": isolated, "batch_pool": batch_pool,
             "mean_iterations_per_trajectory": float(iters.double().mean().item()),
-            "converged_fraction": float(((torch.from_numpy(status) & 16) != 0).double().mean().item()),
+            "converged_fraction": float(((status & 16) != 0).double().mean().item()),
             "mean_final_cost": float(cost.mean().item()),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "other_configs": other,

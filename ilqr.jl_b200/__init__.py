@@ -9,8 +9,8 @@ library and a B200.
 from . import _abi, _build
 from ._abi import Problem, load_library
 from ._build import build
-from .host import BatchSolver, IlqrError, SolverPool, backward_pass, custom_compile_check, custom_problem, fit, forward_pass, load_urdf, serial_chain_problem, two_link_problem
+from .host import BatchSolver, IlqrError, SolverPool, Streamer, backward_pass, custom_compile_check, custom_problem, fit, forward_pass, load_urdf, serial_chain_problem, two_link_problem
 from .sharding import fit_sharded, shard_range
 
-__all__ = ["BatchSolver", "IlqrError", "Problem", "SolverPool", "backward_pass", "build", "custom_compile_check", "custom_problem", "fit", "fit_sharded", "forward_pass", "load_library", "load_urdf", "serial_chain_problem", "shard_range",
+__all__ = ["BatchSolver", "IlqrError", "Problem", "SolverPool", "Streamer", "backward_pass", "build", "custom_compile_check", "custom_problem", "fit", "fit_sharded", "forward_pass", "load_library", "load_urdf", "serial_chain_problem", "shard_range",
            "two_link_problem"]

@@ -85,12 +85,27 @@ SYMBOLS = {
     "ilqr_pool_wait": (ctypes.c_int32, [_H, ctypes.c_int64]),
     "ilqr_pool_wait_all": (ctypes.c_int32, [_H]),
     "ilqr_pool_launch_count": (ctypes.c_int64, [_H]),
+    "ilqr_streamer_create": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_double, ctypes.POINTER(_H)]),
+    "ilqr_streamer_destroy": (ctypes.c_int32, [_H]),
+    "ilqr_streamer_last_error": (ctypes.c_char_p, [_H]),
+    "ilqr_streamer_submit": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_streamer_submit_device": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_streamer_wait": (ctypes.c_int32, [_H, ctypes.c_int64]),
+    "ilqr_streamer_wait_all": (ctypes.c_int32, [_H]),
+    "ilqr_streamer_launch_count": (ctypes.c_int64, [_H]),
+    "ilqr_streamer_rounds": (ctypes.c_int64, [_H]),
+    "ilqr_streamer_profile": (ctypes.c_int32, [_H, c_double_p]),
     "ilqr_host_alloc": (ctypes.c_int32, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
     "ilqr_host_free": (ctypes.c_int32, [ctypes.c_void_p]),
     "ilqr_launch_count": (ctypes.c_int64, [_H]),
     "ilqr_last_kernel_ms": (ctypes.c_int32, [_H, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "ilqr_profile": (ctypes.c_int32, [_H, c_double_p]),
+    "ilqr_stream_profile": (ctypes.c_int32, [_H, c_double_p]),
     "ilqr_set_variant": (ctypes.c_int32, [_H, ctypes.c_int32]),
+    "ilqr_set_tuning": (ctypes.c_int32, [_H, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "ilqr_sync": (ctypes.c_int32, [_H]),
     "ilqr_stream": (ctypes.c_void_p, [_H]),
 }

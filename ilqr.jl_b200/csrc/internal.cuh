@@ -35,6 +35,43 @@ void launch_compact(const DevState& st, int new_nslots, cudaStream_t s);
 void launch_flush_live(const DevState& st, bool with_iterates, cudaStream_t s);
 void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaStream_t s);
 
+// kernels_round.cu — streaming solve of the 2-link model, one launch per iteration ("round") incl. retirement and
+// admission.  Everything lives in the [k][slot][component] layout of DevState; per-slot scalars are indexed by slot.
+// Trajectories are numbered over the whole stream; trajectory t belongs to batch t / Bb, whose boundary-layout
+// arrays are found in entry (t / Bb) % R of a small device table (a ring of R batches in flight).
+struct BatchTab {
+  const double* in_x; const double* in_u;                                          // [Bb][n·N], [Bb][m·H]
+  double* out_x; double* out_u; double* out_cost; int32_t* out_iters; int32_t* out_status;   // last three nullable
+  int64_t reserved;
+};
+struct RoundP {
+  double* x[2]; double* u[2];   // iterate ping-pong (every warp reads buffer `parity`, writes the other)
+  double* duff; double* K;
+  double* prev_cost; int32_t* iters; int32_t* status;
+  long long* traj;              // ≥ 0 live (trajectory index), −1 idle, ≤ −2 holds queue ticket −2 − value
+  int32_t* ls_j;                // line-search attempt of the next forward sweep (α = 2^-ls_j)
+  const BatchTab* tab;          // [R]
+  int32_t* done;                // [R] trajectories of the batch in each ring entry that have retired …
+  int32_t* done_host;           // … mirrored into mapped host memory by every launch's last block
+  unsigned long long* next;     // queue head (tickets handed out)
+  unsigned long long* retired;  // trajectories finished
+  uint32_t* blocks_done;
+  long long* pub;               // device alias of mapped host memory: pub[2·slot] = retired, pub[2·slot+1] = next
+  long long Bb;                 // trajectories per batch
+  int32_t R;                    // ring entries
+  int32_t nslots, H, n_alpha;
+  int64_t S;                    // slot stride
+  double reg;
+};
+struct RoundArgs {
+  long long n_avail;            // trajectories [0, n_avail) of the stream are resident
+  double tol;
+  int32_t parity, shifted, max_iter, pub_slot;
+};
+void init_round_attributes();
+void launch_round_two_link(const RoundP& rp, const TwoLinkP& mp, const CostP& cp, const RoundArgs& ra, int warps_per_sm,
+                           cudaStream_t s);
+
 // kernels_chain.cu / kernels_chain_fl.cu — serial-chain rigid-body models (warp-per-trajectory backward pass);
 // n = 2·NV, m = NV, NV = nq (+ 6 with a floating base)
 bool chain_supported(int nq, bool floating);

@@ -1,0 +1,413 @@
+// kernels_round.cu — streaming solve of the 2-link model: ONE launch = one whole iLQR iteration ("round") for every
+// slot of the handle — backward sweep, forward sweep, the fit loop's accept / converge test, retirement of finished
+// trajectories into the caller's output arrays and admission of pending ones into the freed slots.
+//
+// Why: iteration counts are heavy tailed (5…100 on config 2, mean 19).  Batch-synchronous solving leaves most of
+// the machine idle while a batch's stragglers finish; here a slot that finishes takes the next pending trajectory
+// in the same launch, so every round runs at full width, no host round trip / commit / compaction launch sits
+// between iterations and the slot count can be sized to the machine (a whole number of warps per SM sub-partition)
+// instead of to the batch.
+//
+// Mapping: as kernels_lpt.cu — lane per trajectory, 32 consecutive slots per warp, [k][slot][component] layout,
+// per-time-step slabs streamed into a shared-memory ring by TMA bulk copies.  Per-trajectory arithmetic is the
+// same code (tl_linearize, riccati_step, tl_step), so results are bit-identical to the batch path.
+//
+// Line search without divergence: every live lane rolls out ONE step size per round.  A lane whose candidate is
+// rejected (prev − new ≤ 0 or NaN, src/forward_pass.jl:77-82) keeps its gains, halves α and sits out the next
+// backward sweep; its current iterate is copied into the other buffer so that the whole warp keeps one buffer
+// parity (the slab copies need that).  The accepted α is exactly the largest 2⁻ʲ the reference would accept.
+//
+// One block per SM (12 or 16 warps).  Phase shift: the second group of four warps (one per SM sub-partition; with 16
+// warps also the fourth group) runs forward sweep → bookkeeping → backward sweep inside a launch (its gains are then
+// one launch old), the others backward → forward, so that on every sub-partition the FP64-bound backward sweeps of
+// some warps overlap the HBM-bound forward sweeps of the others.
+//
+// Reference functions restated (paths relative to /root/reference): backward_pass src/backward_pass.jl:324-357,
+// forward_pass src/forward_pass.jl:55-93, total_cost :182-196, fit's loop tail :168-178.
+#include "internal.cuh"
+#include "riccati.cuh"
+#include "tma.cuh"
+
+namespace ilqr {
+
+namespace {
+
+constexpr int NX = 4, NU = 2, NK = NU * NX;
+constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2, ST_LS_EXHAUSTED = 4, ST_CONVERGED = 16, ST_MAX_ITER = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kStageDoubles = 32 * (NX + NU + NU + NK);   // forward stage: x, u, δuff, K slabs = 4 KB (backward uses 1.5 KB of it)
+
+__device__ __forceinline__ double qinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+template <int C> __device__ __forceinline__ void ldv(const double* __restrict__ p, double* v) {
+#pragma unroll
+  for (int i = 0; i < C; i += 2) { const double2 t = *reinterpret_cast<const double2*>(p + i); v[i] = t.x; v[i + 1] = t.y; }
+}
+// L2 loads: data another lane of this warp wrote earlier in the same launch
+template <int C> __device__ __forceinline__ void ldv_cg(const double* p, double* v) {
+#pragma unroll
+  for (int i = 0; i < C; i += 2) { const double2 t = __ldcg(reinterpret_cast<const double2*>(p + i)); v[i] = t.x; v[i + 1] = t.y; }
+}
+template <int C> __device__ __forceinline__ void stv(double* __restrict__ p, const double* v) {
+#pragma unroll
+  for (int i = 0; i < C; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(v[i], v[i + 1]);
+}
+
+// generic-proxy global writes of this thread → visible to later async-proxy (TMA) reads; pair with __syncwarp()
+__device__ __forceinline__ void publish_to_tma() {
+  __threadfence();
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  __syncwarp();
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // issuer side as well: the copies are issued by lane 0
+}
+
+// ---- warp-cooperative slot copies (lane = time index mod 32) -------------------------------------------------
+__device__ __forceinline__ void copy_slot(const double* Xs, const double* Us, double* Xd, double* Ud, int64_t S, int sj,
+                                          int H, int lane) {
+  for (int k = lane; k <= H; k += 32) {
+    double v[NX];
+    ldv_cg<NX>(Xs + ((int64_t)k * S + sj) * NX, v);
+    stv<NX>(Xd + ((int64_t)k * S + sj) * NX, v);
+  }
+  for (int k = lane; k < H; k += 32) {
+    double v[NU];
+    ldv_cg<NU>(Us + ((int64_t)k * S + sj) * NU, v);
+    stv<NU>(Ud + ((int64_t)k * S + sj) * NU, v);
+  }
+}
+// slot → boundary layout (trajectory-major, component rows of N / H doubles; layout.cu)
+__device__ __forceinline__ void retire_slot(const double* Xs, const double* Us, double* __restrict__ ox,
+                                            double* __restrict__ ou, int64_t S, int sj, int H, int lane) {
+  const int N = H + 1;
+  for (int k = lane; k < N; k += 32) {
+    double v[NX];
+    ldv_cg<NX>(Xs + ((int64_t)k * S + sj) * NX, v);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) ox[c * N + k] = v[c];
+  }
+  for (int k = lane; k < H; k += 32) {
+    double v[NU];
+    ldv_cg<NU>(Us + ((int64_t)k * S + sj) * NU, v);
+#pragma unroll
+    for (int c = 0; c < NU; ++c) ou[c * H + k] = v[c];
+  }
+}
+__device__ __forceinline__ void admit_slot(const double* __restrict__ ix, const double* __restrict__ iu, double* Xd,
+                                           double* Ud, int64_t S, int sj, int H, int lane) {
+  const int N = H + 1;
+  for (int k = lane; k < N; k += 32) {
+    double v[NX];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) v[c] = ix[c * N + k];
+    stv<NX>(Xd + ((int64_t)k * S + sj) * NX, v);
+  }
+  for (int k = lane; k < H; k += 32) {
+    double v[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) v[c] = iu[c * H + k];
+    stv<NU>(Ud + ((int64_t)k * S + sj) * NU, v);
+  }
+}
+
+// Slot state in rp.traj[s]:  t ≥ 0 — live, solving trajectory t;  −1 — idle;  ≤ −2 — holds queue ticket −2 − t and
+// waits for that trajectory to become available (t < n_avail).
+template <int kWarps, int D>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ TwoLinkP mp,
+                   const __grid_constant__ CostP cp, const __grid_constant__ RoundArgs ra) {
+  constexpr int SD = kStageDoubles;
+  constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ bool last_block;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double (*ring)[SD] = reinterpret_cast<double (*)[SD]>(smem_raw) + warp * D;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarps * D * SD) + warp * D;
+  const int s0 = (blockIdx.x * kWarps + warp) * 32, s = s0 + lane;
+
+  if (s0 < rp.nslots) {
+    const int64_t S = rp.S;
+    const int H = rp.H;
+    const bool usable = s < rp.nslots;
+    long long t = usable ? rp.traj[s] : -1;
+    bool live = t >= 0;
+    int lsj = live ? rp.ls_j[s] : 0;
+    double prev = live ? rp.prev_cost[s] : 0.0;
+    // warps w, w+4, w+8 … of a block share an SM sub-partition: shift every second group of four
+    const bool odd = ra.shifted && ((warp >> 2) & 1);
+    int fills = 0;   // ring uses so far (stage = fills % D, phase parity = (fills / D) & 1), warp-uniform
+
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) mbar_init(&bars[i], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+      const bool is_bwd = (ph == 0) != odd;
+      if (is_bwd) {
+        // ------------------------------------------------------------------------------------------------
+        // backward sweep over the current iterate (src/backward_pass.jl:324-357); lanes in a line-search
+        // retry keep the gains they have
+        // ------------------------------------------------------------------------------------------------
+        const int pb = odd ? (ra.parity ^ 1) : ra.parity;   // odd warps: after this launch's bookkeeping
+        const double* X = rp.x[pb];
+        const double* U = rp.u[pb];
+        const bool act = live && lsj == 0;
+        if (__any_sync(kFull, act)) {
+          auto issue = [&](int k, int stage) {   // lane 0 only
+            mbar_arrive_expect_tx(&bars[stage], 32 * (NX + NU) * 8);
+            tma_load_1d(&ring[stage][oX], X + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+            tma_load_1d(&ring[stage][oU], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+          };
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+              if (H - 1 - i >= 0) issue(H - 1 - i, (fills + i) % D);
+          }
+          double Qd[NX], Rd[NU], qt[NX];
+#pragma unroll
+          for (int c = 0; c < NX; ++c) { Qd[c] = 2.0 * cp.w_x[c]; qt[c] = cp.x_target[c]; }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) Rd[i] = 2.0 * cp.w_u[i];
+          // terminal expansion: final_cost_quadratization (src/backward_pass.jl:134-153)
+          double sv[NX], Sm[NX][NX];
+          {
+            double xN[NX];
+            ldv_cg<NX>(X + ((int64_t)H * S + s) * NX, xN);
+#pragma unroll
+            for (int c = 0; c < NX; ++c) {
+              sv[c] = -2.0 * cp.w_xf[c] * (qt[c] - xN[c]);
+#pragma unroll
+              for (int j = 0; j < NX; ++j) Sm[c][j] = (c == j) ? 2.0 * cp.w_xf[c] : 0.0;
+            }
+          }
+          bool bad = false;
+#pragma unroll 1
+          for (int k = H - 1; k >= 0; --k, ++fills) {
+            const int stage = fills % D;
+            mbar_wait(&bars[stage], (fills / D) & 1);
+            double xk[NX], uk[NU];
+            ldv<NX>(&ring[stage][oX + lane * NX], xk);
+            ldv<NU>(&ring[stage][oU + lane * NU], uk);
+            __syncwarp();
+            if (lane == 0 && k - D >= 0) issue(k - D, stage);
+            if (act) {
+              double A[NX][NX], Bm[NX][NU];
+              tl_linearize(mp, xk, uk, A, Bm);
+              double qv[NX], rv[NU];
+#pragma unroll
+              for (int c = 0; c < NX; ++c) qv[c] = -Qd[c] * (qt[c] - xk[c]);
+#pragma unroll
+              for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
+              double d[NU], Kk[NU][NX];
+              riccati_step<NX, NU, true, true>(A, Bm, qv, rv, Qd, Rd, rp.reg, sv, Sm, d, Kk);
+              double kv[NK];
+#pragma unroll
+              for (int i = 0; i < NU; ++i) {
+                bad |= isnan(d[i]);
+#pragma unroll
+                for (int j = 0; j < NX; ++j) { kv[i + NU * j] = Kk[i][j]; bad |= isnan(Kk[i][j]); }
+              }
+              stv<NU>(rp.duff + ((int64_t)k * S + s) * NU, d);
+              stv<NK>(rp.K + ((int64_t)k * S + s) * NK, kv);
+            }
+          }
+          if (act && bad) rp.status[s] |= ST_NAN_GAINS;
+        }
+      } else {
+        // ------------------------------------------------------------------------------------------------
+        // forward sweep: one step size per lane (src/forward_pass.jl:55-93), candidate → the other buffer
+        // ------------------------------------------------------------------------------------------------
+        const double* X = rp.x[ra.parity];
+        const double* U = rp.u[ra.parity];
+        double* Xo = rp.x[ra.parity ^ 1];
+        double* Uo = rp.u[ra.parity ^ 1];
+        double cost = 0.0, du2 = 0.0;
+        bool accepted = false, bad_r = false;
+        if (__any_sync(kFull, live)) {
+          auto issue = [&](int k, int stage) {   // lane 0 only
+            mbar_arrive_expect_tx(&bars[stage], SD * 8);
+            tma_load_1d(&ring[stage][oX], X + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
+            tma_load_1d(&ring[stage][oU], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+            tma_load_1d(&ring[stage][oD], rp.duff + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
+            tma_load_1d(&ring[stage][oK], rp.K + ((int64_t)k * S + s0) * NK, 32 * NK * 8, &bars[stage]);
+          };
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+              if (i < H) issue(i, (fills + i) % D);
+          }
+          const double alpha = __longlong_as_double((long long)(1023 - lsj) << 52);   // 2^-lsj
+          double xb[NX];
+          ldv_cg<NX>(X + (int64_t)s * NX, xb);
+          if (live) stv<NX>(Xo + (int64_t)s * NX, xb);
+#pragma unroll 1
+          for (int k = 0; k < H; ++k, ++fills) {
+            const int stage = fills % D;
+            mbar_wait(&bars[stage], (fills / D) & 1);
+            double xk[NX], uk[NU], dk[NU], Kk[NK];
+            ldv<NX>(&ring[stage][oX + lane * NX], xk);
+            ldv<NU>(&ring[stage][oU + lane * NU], uk);
+            ldv<NU>(&ring[stage][oD + lane * NU], dk);
+            ldv<NK>(&ring[stage][oK + lane * NK], Kk);
+            __syncwarp();
+            if (lane == 0 && k + D < H) issue(k + D, stage);
+            if (live) {
+              // ū = u + α δuff + K (x̄ − x)      (src/forward_pass.jl:72-73)
+              double dx[NX], ub[NU];
+#pragma unroll
+              for (int c = 0; c < NX; ++c) dx[c] = xb[c] - xk[c];
+#pragma unroll
+              for (int i = 0; i < NU; ++i) {
+                double kdx = Kk[i] * dx[0];
+#pragma unroll
+                for (int c = 1; c < NX; ++c) kdx = fma(Kk[i + NU * c], dx[c], kdx);
+                ub[i] = fma(alpha, dk[i], uk[i]) + kdx;
+                const double e = ub[i] - uk[i];
+                du2 = fma(e, e, du2);
+              }
+              stv<NU>(Uo + ((int64_t)k * S + s) * NU, ub);
+              // running cost l(x̄, ū), summed left to right (src/forward_pass.jl:189-191; x_traj = 0)
+              double lx = 0.0, lu = 0.0;
+#pragma unroll
+              for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - (xb[c] - 0.0); lx = fma(cp.w_x[c] * e, e, lx); }
+#pragma unroll
+              for (int i = 0; i < NU; ++i) lu = fma(cp.w_u[i] * ub[i], ub[i], lu);
+              cost += lx + lu;
+              // x̄⁺ = f(x̄, ū)                    (src/forward_pass.jl:74)
+              double xnext[NX];
+              tl_step(mp, xb, ub, xnext);
+#pragma unroll
+              for (int c = 0; c < NX; ++c) xb[c] = xnext[c];
+              stv<NX>(Xo + ((int64_t)(k + 1) * S + s) * NX, xb);
+            }
+          }
+          if (live) {
+            double lf = 0.0;
+#pragma unroll
+            for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - xb[c]; lf = fma(cp.w_xf[c] * e, e, lf); }
+            cost += lf;
+            if (prev - cost > 0.0) {   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
+              accepted = true;
+#pragma unroll
+              for (int c = 0; c < NX; ++c) bad_r |= isnan(xb[c]);
+            }
+          }
+        }
+        // ------------------------------------------------------------------------------------------------
+        // fit's loop tail per lane (src/forward_pass.jl:168-178; commit_kernel in kernels_lpt.cu)
+        // action: 1 = retire the current iterate, 2 = retire the candidate, 3 = line-search retry
+        // ------------------------------------------------------------------------------------------------
+        int action = 0, it_out = 0;
+        int32_t stat = 0;
+        if (live) {
+          stat = rp.status[s];
+          if (accepted) {
+            it_out = rp.iters[s] + 1;
+            rp.iters[s] = it_out;
+            if (bad_r) stat |= ST_NAN_ROLLOUT;
+            prev = cost;
+            rp.prev_cost[s] = cost;
+            lsj = 0;
+            if (du2 <= ra.tol) { stat |= ST_CONVERGED; action = 1; }        // :171 — break BEFORE the update
+            else if (it_out >= ra.max_iter) { stat |= ST_MAX_ITER; action = 2; }  // :176-178 — keep the newest
+          } else if (lsj + 1 >= rp.n_alpha) {
+            it_out = rp.iters[s] + 1;
+            rp.iters[s] = it_out;
+            stat |= ST_LS_EXHAUSTED;
+            action = 1;
+          } else {
+            lsj += 1;
+            action = 3;
+          }
+          rp.status[s] = stat;
+          rp.ls_j[s] = lsj;
+        }
+        __syncwarp();   // the candidate stores above are ordered before the cooperative reads below
+        // (a) retrying lanes: carry the current iterate over to the buffer every lane of the warp reads next
+        for (unsigned m3 = __ballot_sync(kFull, action == 3); m3; m3 &= m3 - 1)
+          copy_slot(X, U, Xo, Uo, S, s0 + __ffs(m3) - 1, H, lane);
+        // (b) finished lanes: iterate → the batch's output arrays (boundary layout), scalars, counters
+        const unsigned mret = __ballot_sync(kFull, action == 1 || action == 2);
+        for (unsigned m = mret; m; m &= m - 1) {
+          const int j = __ffs(m) - 1;
+          const int aj = __shfl_sync(kFull, action, j);
+          const long long tj = __shfl_sync(kFull, t, j);
+          const long long bj = tj / rp.Bb, loc = tj - bj * rp.Bb;
+          const BatchTab& e = rp.tab[bj % rp.R];
+          retire_slot(aj == 1 ? X : Xo, aj == 1 ? U : Uo, e.out_x + loc * (NX * (long long)(H + 1)),
+                      e.out_u + loc * (NU * (long long)H), S, s0 + j, H, lane);
+        }
+        if (action == 1 || action == 2) {
+          const long long bj = t / rp.Bb, loc = t - bj * rp.Bb;
+          const int slot = (int)(bj % rp.R);
+          const BatchTab& e = rp.tab[slot];
+          if (e.out_cost) e.out_cost[loc] = prev;
+          if (e.out_iters) e.out_iters[loc] = it_out;
+          if (e.out_status) e.out_status[loc] = stat;
+          atomicAdd(rp.done + slot, 1);
+          t = -1; live = false;
+        }
+        if (mret && lane == 0) atomicAdd(rp.retired, (unsigned long long)__popc(mret));
+        // (c) idle lanes take a queue ticket; ticket holders whose trajectory has arrived are admitted
+        const unsigned mtick = __ballot_sync(kFull, usable && t == -1);
+        if (mtick) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(rp.next, (unsigned long long)__popc(mtick));
+          base = __shfl_sync(kFull, base, 0);
+          if (usable && t == -1) t = -2 - (long long)(base + __popc(mtick & ((1u << lane) - 1)));
+        }
+        const bool adm = usable && t <= -2 && (-2 - t) < ra.n_avail;
+        if (adm) t = -2 - t;
+        for (unsigned m = __ballot_sync(kFull, adm); m; m &= m - 1) {
+          const int j = __ffs(m) - 1;
+          const long long tj = __shfl_sync(kFull, t, j);
+          const long long bj = tj / rp.Bb, loc = tj - bj * rp.Bb;
+          const BatchTab& e = rp.tab[bj % rp.R];
+          admit_slot(e.in_x + loc * (NX * (long long)(H + 1)), e.in_u + loc * (NU * (long long)H), Xo, Uo, S, s0 + j, H, lane);
+        }
+        if (adm) {   // fit's start state (src/forward_pass.jl:159-160)
+          rp.prev_cost[s] = qinf(); rp.iters[s] = 0; rp.status[s] = 0; rp.ls_j[s] = 0;
+          live = true; lsj = 0; prev = qinf();
+        }
+        if (usable) rp.traj[s] = t;
+      }
+      // this phase's global writes (gains / candidate / admitted iterates) → the next phase's slab copies
+      publish_to_tma();
+    }
+  }
+
+  // last block publishes the counters into mapped host memory (no DMA copy that could queue behind bulk transfers)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_block = (atomicAdd(rp.blocks_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last_block) {
+    for (int i = threadIdx.x; i < rp.R; i += kWarps * 32) rp.done_host[i] = atomicAdd(rp.done + i, 0);
+    if (threadIdx.x == 0) {
+      rp.pub[2 * ra.pub_slot] = (long long)atomicAdd(rp.retired, 0ull);
+      rp.pub[2 * ra.pub_slot + 1] = (long long)atomicAdd(rp.next, 0ull);
+      *rp.blocks_done = 0u;
+    }
+    __threadfence_system();
+  }
+}
+
+template <int kWarps, int D> constexpr size_t round_smem() { return sizeof(double) * kWarps * D * kStageDoubles + sizeof(uint64_t) * kWarps * D; }
+
+}  // namespace
+
+void init_round_attributes() {
+  cudaFuncSetAttribute(round_lpt_two_link<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<12, 4>());
+  cudaFuncSetAttribute(round_lpt_two_link<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<16, 3>());
+}
+
+void launch_round_two_link(const RoundP& rp, const TwoLinkP& mp, const CostP& cp, const RoundArgs& ra, int warps_per_sm,
+                           cudaStream_t s) {
+  if (warps_per_sm >= 16) round_lpt_two_link<16, 3><<<(int)((rp.S + 511) / 512), 512, round_smem<16, 3>(), s>>>(rp, mp, cp, ra);
+  else round_lpt_two_link<12, 4><<<(int)((rp.S + 383) / 384), 384, round_smem<12, 4>(), s>>>(rp, mp, cp, ra);
+}
+
+}  // namespace ilqr

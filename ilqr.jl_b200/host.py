@@ -305,6 +305,10 @@ class BatchSolver:
         self._ck(self._lib.ilqr_fit(self._h, int(max_iter), float(tol), ctypes.byref(it)), "ilqr_fit")
         return it.value
 
+    def solve_ptrs(self, x, u, max_iter, tol, xo, uo, cost=None, iters=None, status=None, x_traj=None):
+        """ilqr_solve on raw HOST addresses (ints) of boundary-layout arrays (pinned for full-speed copies)."""
+        self._ck(self._lib.ilqr_solve(self._h, x, u, x_traj, int(max_iter), float(tol), xo, uo, cost, iters, status), "ilqr_solve")
+
     def solve(self, x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, out=None):
         """Host in → host out (ilqr_solve).  Returns dict(x,u,cost,iters,status)."""
         x = self._shape(x_init, (self.N, self.n))
@@ -356,8 +360,19 @@ class BatchSolver:
         return dict(bwd_ms=out[0], fwd_ms=out[1], bwd_launches=int(out[2]), fwd_launches=int(out[3]),
                     traj_iters=out[4], first_bwd_ms=out[5], first_fwd_ms=out[6])
 
+    def stream_profile(self):
+        """Last streaming solve (ilqr_stream_profile): device ms, rounds launched, rounds at completion, trajectories."""
+        out = (ctypes.c_double * 4)()
+        self._ck(self._lib.ilqr_stream_profile(self._h, out), "ilqr_stream_profile")
+        return dict(ms=out[0], rounds_launched=int(out[1]), rounds=int(out[2]), trajectories=int(out[3]))
+
     def stream_ptr(self):
         return int(self._lib.ilqr_stream(self._h) or 0)
+
+    def set_tuning(self, split_below=-1, coop_below=-1, fwd_split_above=-1, compaction=-1):
+        """ilqr_set_tuning: kernel-selection thresholds of the batch path (negative = unchanged)."""
+        self._ck(self._lib.ilqr_set_tuning(self._h, int(split_below), int(coop_below), int(fwd_split_above), int(compaction)),
+                 "ilqr_set_tuning")
 
     def set_variant(self, v):
         self._ck(self._lib.ilqr_set_variant(self._h, v), "ilqr_set_variant")
@@ -423,6 +438,74 @@ class SolverPool:
 
     def launch_count(self):
         return int(self._lib.ilqr_pool_launch_count(self._p))
+
+
+class Streamer:
+    """ilqr_streamer: continuous batching over the fused rounds (2-link model).  `problem.B` is the number of SLOTS
+    (size it to the machine: 148 SMs x 12 warps x 32 = 56,832 on B200), `batch_size` the number of trajectories in
+    every submitted batch; up to `ring` batches are in flight (submit blocks while the ring is full)."""
+
+    def __init__(self, problem, batch_size, ring=8, max_iter=100, tol=1e-6):
+        self._lib = _abi.load_library()
+        self.problem, self.batch_size, self.ring = problem, int(batch_size), int(ring)
+        self._p = ctypes.c_void_p()
+        rc = self._lib.ilqr_streamer_create(ctypes.byref(problem), int(batch_size), int(ring), int(max_iter), float(tol),
+                                            ctypes.byref(self._p))
+        if rc != 0:
+            raise IlqrError("ilqr_streamer_create (%d): %s" % (rc, self._lib.ilqr_streamer_last_error(None).decode()))
+
+    def close(self):
+        if self._p:
+            self._lib.ilqr_streamer_destroy(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit_ptrs(self, x, u, xo, uo, cost=None, iters=None, status=None, device=False):
+        """Raw addresses (ints) of boundary-layout arrays of batch_size trajectories: host pointers, or device pointers
+        with device=True.  Returns a ticket."""
+        fn = self._lib.ilqr_streamer_submit_device if device else self._lib.ilqr_streamer_submit
+        t = fn(self._p, x, u, xo, uo, cost, iters, status)
+        if t < 0:
+            raise IlqrError("ilqr_streamer_submit failed (%d): %s" % (t, self._lib.ilqr_streamer_last_error(self._p).decode()))
+        return t
+
+    def submit(self, x_init, u_init, out):
+        """NumPy (Fortran-ordered, boundary layout) in, preallocated `out` dict (x, u, cost, iters, status) filled on wait."""
+        return self.submit_ptrs(x_init.ctypes.data, u_init.ctypes.data, out["x"].ctypes.data, out["u"].ctypes.data,
+                                out["cost"].ctypes.data, out["iters"].ctypes.data, out["status"].ctypes.data)
+
+    def wait(self, ticket):
+        rc = self._lib.ilqr_streamer_wait(self._p, ticket)
+        if rc != 0:
+            raise IlqrError("streamed solve failed (%d): %s" % (rc, self._lib.ilqr_streamer_last_error(self._p).decode()))
+
+    def wait_all(self):
+        rc = self._lib.ilqr_streamer_wait_all(self._p)
+        if rc != 0:
+            raise IlqrError("streamed solve failed (%d): %s" % (rc, self._lib.ilqr_streamer_last_error(self._p).decode()))
+
+    def launch_count(self):
+        return int(self._lib.ilqr_streamer_launch_count(self._p))
+
+    def rounds(self):
+        return int(self._lib.ilqr_streamer_rounds(self._p))
+
+    def profile(self):
+        """Cumulative: device ms over the timed rounds, rounds covered, batches completed, rounds launched."""
+        out = (ctypes.c_double * 4)()
+        self._lib.ilqr_streamer_profile(self._p, out)
+        return dict(round_ms=out[0], rounds_timed=int(out[1]), batches_completed=int(out[2]), rounds_launched=int(out[3]))
 
 
 def _batch_of(x):

@@ -286,6 +286,35 @@ int32_t ilqr_pool_wait(ilqr_pool* pool, int64_t ticket);
 int32_t ilqr_pool_wait_all(ilqr_pool* pool);
 int64_t ilqr_pool_launch_count(const ilqr_pool* pool);
 
+/* ---- streamer: continuous batching over the fused rounds (csrc/kernels_round.cu; ILQR_MODEL_TWO_LINK) -----------
+ * Batches of batch_size trajectories are solved as ONE stream through the p->B slots of a single handle: a slot whose
+ * trajectory finishes takes the next pending one — of the same or of the next batch — inside the same launch, so every
+ * launch runs full width, however heavy-tailed the iteration counts are.  One launch per iLQR iteration does the
+ * backward sweep, the forward sweep, fit's accept / converge test (src/forward_pass.jl:168-178, per trajectory:
+ * tol, max_iter), retirement into the batch's output arrays and admission.  Up to `ring` batches are in flight;
+ * submit blocks while the ring is full.  Host submissions are uploaded on a copy stream while the rounds run and
+ * copied back as soon as the batch's last trajectory has retired.  Every trajectory comes out bit-identical to
+ * ilqr_solve / ilqr_fit on its batch.  Size p->B to the machine (148 SMs x 12 warps x 32 lanes = 56,832 on B200),
+ * not to the batch.  Buffers must stay valid until the ticket has been waited for. */
+typedef struct ilqr_streamer ilqr_streamer;
+int32_t ilqr_streamer_create(const ilqr_problem* p, int32_t batch_size, int32_t ring, int32_t max_iter, double tol,
+                             ilqr_streamer** out);
+int32_t ilqr_streamer_destroy(ilqr_streamer* s);
+const char* ilqr_streamer_last_error(const ilqr_streamer* s);
+/* host pointers (pinned for full-speed copies), boundary layout; cost/iters/status nullable; returns a ticket >= 0 */
+int64_t ilqr_streamer_submit(ilqr_streamer* s, const double* x_init, const double* u_init, double* x_out, double* u_out,
+                             double* cost_out, int32_t* iters_out, int32_t* status_out);
+/* device pointers: read and written by the kernels directly, no staging copy */
+int64_t ilqr_streamer_submit_device(ilqr_streamer* s, const double* d_x_init, const double* d_u_init, double* d_x_out,
+                                    double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out);
+int32_t ilqr_streamer_wait(ilqr_streamer* s, int64_t ticket);
+int32_t ilqr_streamer_wait_all(ilqr_streamer* s);
+int64_t ilqr_streamer_launch_count(const ilqr_streamer* s);   /* kernels launched so far */
+int64_t ilqr_streamer_rounds(const ilqr_streamer* s);         /* of which rounds (iterations over all slots) */
+/* out4 = {sum of device ms over the timed rounds (CUDA events on the handle's stream, fence to fence over groups of
+ * back-to-back launches), number of rounds that sum covers, batches completed, rounds launched}; cumulative. */
+int32_t ilqr_streamer_profile(ilqr_streamer* s, double* out4);
+
 /* Page-locked host buffers for callers that want full-speed PCIe copies. */
 int32_t ilqr_host_alloc(void** out, uint64_t bytes);
 int32_t ilqr_host_free(void* p);
@@ -298,7 +327,17 @@ int32_t ilqr_last_kernel_ms(ilqr_handle* h, float* bwd_ms, float* fwd_ms); /* CU
  * out[3] forward launches, out[4] Σ over launches of active trajectories (trajectory-iterations),
  * out[5] first-iteration backward ms, out[6] first-iteration forward ms, out[7] reserved. */
 int32_t ilqr_profile(ilqr_handle* h, double* out8);
+/* Last streaming solve of this handle (fused rounds, csrc/kernels_round.cu): out4 = {device ms from the first to the
+ * last launch (CUDA events on the handle's stream), rounds launched, rounds launched when completion was seen,
+ * trajectories solved}. */
+int32_t ilqr_stream_profile(ilqr_handle* h, double* out4);
 int32_t ilqr_set_variant(ilqr_handle* h, int32_t variant);
+/* Kernel-selection thresholds of the batch path (2-link model): the split backward pass (time-parallel linearisation +
+ * Riccati kernel) is used when live slots <= split_below, its 4-lane cooperative Riccati kernel when <= coop_below, the
+ * two-kernel forward pass (alpha = 1 for all, dense retry kernel) when > fwd_split_above; compaction != 0 retires and
+ * re-packs finished slots between iterations.  Negative values leave a setting unchanged.  ilqr_pool_create with more
+ * than one handle selects (0, 0, INT32_MAX, 0): see DESIGN.md section 5, "handles running concurrently on one GPU". */
+int32_t ilqr_set_tuning(ilqr_handle* h, int32_t split_below, int32_t coop_below, int32_t fwd_split_above, int32_t compaction);
 int32_t ilqr_sync(ilqr_handle* h);
 void* ilqr_stream(ilqr_handle* h);                    /* the cudaStream_t of this handle */
 

@@ -354,3 +354,53 @@ def test_stream_admission_equals_batch_solves():
     assert np.array_equal(ox.cpu().numpy().transpose(2, 1, 0), ref["x"])
     assert np.array_equal(ou.cpu().numpy().transpose(2, 1, 0), ref["u"])
     assert np.array_equal(out2["x"], ref["x"][:, :, :slots]) and np.array_equal(out2["iters"], ref["iters"][:slots])
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_streamer_equals_batch_solves(device):
+    """ilqr_streamer: five batches of 64 trajectories (config-2 and line-search-stress inputs mixed, max_iter low enough
+    that some hit it) through 96 slots with a ring of two batches — slots are refilled across batch boundaries and the
+    ring entries are reused.  Host buffers (upload / copy-back on the copy streams) and device buffers.  Every batch
+    must come out exactly as a plain batched solve of that batch leaves it, bit for bit."""
+    import torch
+    H, Bb, nb, slots, max_iter = 60, 64, 5, 96, 25
+    _, xa, ua = config2_batch(200, H, seed=31)
+    _, xb, ub = stress_batch(120, H, seed=32)
+    x = np.concatenate([xa, xb], axis=2); u = np.concatenate([ua, ub], axis=2)
+    perm = np.random.default_rng(1).permutation(nb * Bb)
+    x = np.asfortranarray(x[:, :, perm]); u = np.asfortranarray(u[:, :, perm])
+    refs = []
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, Bb)) as s:
+        for b in range(nb):
+            sl = slice(b * Bb, (b + 1) * Bb)
+            refs.append(s.solve(np.asfortranarray(x[:, :, sl]), np.asfortranarray(u[:, :, sl]), max_iter=max_iter, tol=1e-6))
+    allst = np.concatenate([r["status"] for r in refs])
+    assert (allst & _abi.STATUS_MAX_ITER).any() and (allst & _abi.STATUS_CONVERGED).any()
+    ins, outs = [], []
+    for b in range(nb):
+        sl = slice(b * Bb, (b + 1) * Bb)
+        bx = torch.from_numpy(np.ascontiguousarray(x[:, :, sl].transpose(2, 1, 0))); bu = torch.from_numpy(np.ascontiguousarray(u[:, :, sl].transpose(2, 1, 0)))
+        o = [torch.zeros_like(bx), torch.zeros_like(bu), torch.zeros(Bb, dtype=torch.float64), torch.zeros(Bb, dtype=torch.int32),
+             torch.zeros(Bb, dtype=torch.int32)]
+        if device:
+            bx, bu, o = bx.cuda(), bu.cuda(), [t.cuda() for t in o]
+        else:
+            bx, bu, o = bx.pin_memory(), bu.pin_memory(), [t.pin_memory() for t in o]
+        ins.append((bx, bu)); outs.append(o)
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, slots), Bb, ring=2, max_iter=max_iter, tol=1e-6) as st:
+        tickets = [st.submit_ptrs(ins[b][0].data_ptr(), ins[b][1].data_ptr(), *[t.data_ptr() for t in outs[b]], device=device)
+                   for b in range(nb)]
+        for t in tickets:
+            st.wait(t)
+        assert st.rounds() >= max_iter
+        # the streamer idles and picks up again
+        t2 = st.submit_ptrs(ins[0][0].data_ptr(), ins[0][1].data_ptr(), *[t.data_ptr() for t in outs[0]], device=device)
+        st.wait(t2)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        ox, ou, oc, oi, os_ = [t.cpu().numpy() for t in outs[b]]
+        assert np.array_equal(oi, refs[b]["iters"]), b
+        assert np.array_equal(os_, refs[b]["status"]), b
+        assert np.array_equal(oc, refs[b]["cost"]), b
+        assert np.array_equal(ox.transpose(2, 1, 0), refs[b]["x"]), b
+        assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b

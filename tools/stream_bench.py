@@ -45,5 +45,8 @@ for rep in range(2):
     th = [threading.Thread(target=run, args=(i,)) for i in range(NS)]
     [t.start() for t in th]; [t.join() for t in th]
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
+same = bool(torch.equal(ox[:B], ox[(K - 1) * B:]) and torch.equal(ou[:B], ou[(K - 1) * B:]) and torch.equal(oi[:B], oi[(K - 1) * B:]))
 print(json.dumps({"K": K, "streams": NS, "slots": SLOTS, "solves_per_s": n_total / dt, "ms_per_batch": 1e3 * dt / K,
-                  "batch_iterations": its, "mean_iters": float(oi.double().mean().item())}))
+                  "batch_iterations": its, "mean_iters": float(oi.double().mean().item()),
+                  "first_and_last_batch_identical": same, "stream_profile": [s_.stream_profile() for s_ in solvers],
+                  "env": {k: v for k, v in os.environ.items() if k.startswith("ILQR_")}}))
