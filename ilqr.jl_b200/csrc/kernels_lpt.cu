@@ -39,9 +39,6 @@ template <int C> __device__ __forceinline__ void ldv(const double* __restrict__ 
 template <int C> __device__ __forceinline__ void stv(double* __restrict__ p, const double* v) {
 #pragma unroll
   for (int i = 0; i < C; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(v[i], v[i + 1]);
-#ifdef ILQR_FENCE_STV
-  asm volatile("fence.proxy.async.global;" ::: "memory");
-#endif
 }
 
 // Which of the two iterate buffers the ACTIVE lanes of this warp read: all active trajectories flip

@@ -162,6 +162,38 @@ function mpc_step!(s::Solver; max_iter::Int64 = 3, tol::Float64 = 1e-6)
     return (ua, xp)
 end
 
+"""
+Continuous batching (`ilqr_streamer_*`, 2-link model): batches of `batch_size` trajectories are solved as ONE stream through the
+`p.B` slots of a handle — a slot that finishes a trajectory takes the next pending one in the same launch — with per-trajectory
+`fit` semantics (src/forward_pass.jl:148-179).  `submit!` returns a ticket at once; the arrays must stay alive (and pinned, for
+full-speed copies) until `wait(streamer, ticket)` returns.  Size `p.B` to the machine (56,832 on a B200), not to the batch.
+"""
+mutable struct Streamer
+    h::Ptr{Cvoid}
+    batch_size::Int
+    function Streamer(p::Problem, batch_size::Integer; ring::Integer = 12, max_iter::Integer = 100, tol::Float64 = 1e-6)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:ilqr_streamer_create, lib), Int32, (Ref{Problem}, Int32, Int32, Int32, Float64, Ptr{Ptr{Cvoid}}),
+                   p, batch_size, ring, max_iter, tol, h)
+        rc == 0 || error("ilqr_streamer_create: " * unsafe_string(ccall((:ilqr_streamer_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+        s = new(h[], batch_size)
+        finalizer(x -> ccall((:ilqr_streamer_destroy, lib), Int32, (Ptr{Cvoid},), x.h), s)
+        s
+    end
+end
+function submit!(s::Streamer, x_init::Array{Float64,3}, u_init::Array{Float64,3}, x_out::Array{Float64,3}, u_out::Array{Float64,3},
+                 cost::Vector{Float64}, iters::Vector{Int32}, status::Vector{Int32})
+    @assert size(x_init, 3) == s.batch_size == size(u_init, 3) "every submitted batch has batch_size trajectories"
+    t = ccall((:ilqr_streamer_submit, lib), Int64,
+              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+              s.h, x_init, u_init, x_out, u_out, cost, iters, status)
+    t >= 0 || error("ilqr_streamer_submit failed ($t)")
+    t
+end
+Base.wait(s::Streamer, ticket::Int64) =
+    ccall((:ilqr_streamer_wait, lib), Int32, (Ptr{Cvoid}, Int64), s.h, ticket) == 0 ||
+    error(unsafe_string(ccall((:ilqr_streamer_last_error, lib), Cstring, (Ptr{Cvoid},), s.h)))
+
 # single-problem convenience with the reference's exact shapes x[N×n], u[H×m]
 fit(x_init::Matrix{Float64}, u_init::Matrix{Float64}, p::Problem; kw...) = begin
     (x, u) = fit(reshape(x_init, size(x_init)..., 1), reshape(u_init, size(u_init)..., 1), p; kw...)
