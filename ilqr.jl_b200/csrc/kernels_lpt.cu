@@ -63,6 +63,7 @@ bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
                  const __grid_constant__ CostP cp) {
   __shared__ __align__(128) double ring_all[kWarps][kBwdStages][kBwdStageDoubles];
   __shared__ __align__(8) uint64_t bars_all[kWarps][kBwdStages];
+  __shared__ uint32_t ring_fence[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s0 = (blockIdx.x * kWarps + warp) * 32, s = s0 + lane;
   if (s0 >= st.nslots) return;
@@ -122,7 +123,10 @@ bwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
     ldv<NX>(&ring[stage][lane * NX], xk);
     ldv<NU>(&ring[stage][32 * NX + lane * NU], uk);
     __syncwarp();
-    if (lane == 0 && k - kBwdStages >= 0) issue(k - kBwdStages, stage);
+    if (lane == 0 && k - kBwdStages >= 0) {
+      ring_reads_done(&ring_fence[warp], ring_token<NX>(xk) | ring_token<NU>(uk));
+      issue(k - kBwdStages, stage);
+    }
     if (act) {
       double A[NX][NX], Bm[NX][NU];
       tl_linearize(mp, xk, uk, A, Bm);
@@ -198,6 +202,7 @@ constexpr int kRicStageDoubles = 32 * (kAB + NX + NU);
 __global__ void __launch_bounds__(kBlock)
 ric_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ CostP cp, const double* __restrict__ AB) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t ring_fence[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double (*ring)[kRicStageDoubles] =
       reinterpret_cast<double (*)[kRicStageDoubles]>(smem_raw) + warp * kRicStages;
@@ -257,7 +262,10 @@ ric_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Co
     ldv<NX>(&ring[stage][32 * kAB + lane * NX], xk);
     ldv<NU>(&ring[stage][32 * (kAB + NX) + lane * NU], uk);
     __syncwarp();
-    if (lane == 0 && k - kRicStages >= 0) issue(k - kRicStages, stage);
+    if (lane == 0 && k - kRicStages >= 0) {
+      ring_reads_done(&ring_fence[warp], ring_token<kAB>(ab) | ring_token<NX>(xk) | ring_token<NU>(uk));
+      issue(k - kRicStages, stage);
+    }
     if (act) {
       double A[NX][NX], Bm[NX][NU], qv[NX], rv[NU];
 #pragma unroll
@@ -309,6 +317,7 @@ ric_coop_two_link(const __grid_constant__ DevState st, const __grid_constant__ C
   __shared__ __align__(128) double ring_all[kWarps][kCoopStages][kCoopStageDoubles];
   __shared__ __align__(16) double xch_all[kWarps][2][kCoopXch];
   __shared__ __align__(8) uint64_t bars_all[kWarps][kCoopStages];
+  __shared__ uint32_t ring_fence[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = lane >> 2, j = lane & 3;
   const int s0 = (blockIdx.x * kWarps + warp) * kCoopTraj, s = s0 + t;
@@ -382,7 +391,10 @@ ric_coop_two_link(const __grid_constant__ DevState st, const __grid_constant__ C
       Aj[r] = (j == 0) ? ((r == 0) ? 1.0 : 0.0) : v;
     }
     __syncwarp();
-    if (lane == 0 && k - kCoopStages >= 0) issue(k - kCoopStages, stage);
+    if (lane == 0 && k - kCoopStages >= 0) {
+      ring_reads_done(&ring_fence[warp], ring_token<kAB>(ab) | ring_token<NU>(uk) | ring_token<NX>(Aj) | ring_token<1>(&xkj));
+      issue(k - kCoopStages, stage);
+    }
     double A[NX][NX], Bm[NX][NU];
 #pragma unroll
     for (int r = 0; r < NX; ++r) {
@@ -527,6 +539,7 @@ fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
   constexpr int D = Cfg::kStages, SD = Cfg::kStageDoubles;
   constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU, oT = oK + 32 * NK;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint32_t ring_fence[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double (*ring)[SD] = reinterpret_cast<double (*)[SD]>(smem_raw) + warp * D;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarps * D * SD) + warp * D;
@@ -593,7 +606,11 @@ fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
         for (int c = 0; c < NX; ++c) xt[c] = 0.0;
       }
       __syncwarp();
-      if (lane == 0 && k + D < H) issue(k + D, stage);
+      if (lane == 0 && k + D < H) {
+        ring_reads_done(&ring_fence[warp], ring_token<NX>(xk) | ring_token<NU>(uk) | ring_token<NU>(dk) | ring_token<NK>(Kk) |
+                                               (HAS_XT ? ring_token<NX>(xt) : 0u));
+        issue(k + D, stage);
+      }
       if (searching) {
         // ū = u + α δuff + K (x̄ − x)      (src/forward_pass.jl:72-73)
         double dx[NX], ub[NU];

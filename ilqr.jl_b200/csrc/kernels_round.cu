@@ -119,6 +119,7 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
   constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ bool last_block;
+  __shared__ uint32_t ring_fence[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double (*ring)[SD] = reinterpret_cast<double (*)[SD]>(smem_raw) + warp * D;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double) * kWarps * D * SD) + warp * D;
@@ -192,7 +193,10 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
             ldv<NX>(&ring[stage][oX + lane * NX], xk);
             ldv<NU>(&ring[stage][oU + lane * NU], uk);
             __syncwarp();
-            if (lane == 0 && k - D >= 0) issue(k - D, stage);
+            if (lane == 0 && k - D >= 0) {
+              ring_reads_done(&ring_fence[warp], ring_token<NX>(xk) | ring_token<NU>(uk));   // tma.cuh: reads returned, then refill
+              issue(k - D, stage);
+            }
             if (act) {
               double A[NX][NX], Bm[NX][NU];
               tl_linearize(mp, xk, uk, A, Bm);
@@ -253,7 +257,10 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
             ldv<NU>(&ring[stage][oD + lane * NU], dk);
             ldv<NK>(&ring[stage][oK + lane * NK], Kk);
             __syncwarp();
-            if (lane == 0 && k + D < H) issue(k + D, stage);
+            if (lane == 0 && k + D < H) {
+              ring_reads_done(&ring_fence[warp], ring_token<NX>(xk) | ring_token<NU>(uk) | ring_token<NU>(dk) | ring_token<NK>(Kk));
+              issue(k + D, stage);
+            }
             if (live) {
               // ū = u + α δuff + K (x̄ − x)      (src/forward_pass.jl:72-73)
               double dx[NX], ub[NU];

@@ -109,10 +109,6 @@ int32_t ilqr_pool_create(const ilqr_problem* prob, int32_t n_handles, ilqr_pool*
       delete p;
       return rc;
     }
-    // Handles whose kernels overlap on the device: only the fused backward kernel and the one-kernel forward pass,
-    // no compaction.  With the split / retry / compaction kernels in the mix, concurrent handles were measured to
-    // deviate from a solo solve (tools/compare_paths.py); this set is exact.
-    if (n_handles > 1 && !getenv("ILQR_POOL_ALL_KERNELS")) ilqr_set_tuning(h, 0, 0, 0x7fffffff, 0);
     p->handles.push_back(h);
   }
   for (int i = 0; i < n_handles; ++i) p->workers.emplace_back(worker_main, p, i);

@@ -40,4 +40,20 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
+// Ring-stage reuse.  The bulk copy that refills a stage (async proxy) must not be issued before the shared-memory reads of
+// that stage have RETURNED.  __syncwarp() only orders the instruction streams: an LDS is complete when its wavefronts
+// have come back through the load/store pipe, and when other warps on the SM keep that pipe busy with uncoalesced
+// global accesses (the gather kernels of the batch path running in another stream; the slot copies of the round kernel)
+// a few 4-lane wavefronts can return after a refill that hit in L2 has landed — those lanes then see time step k + D
+// instead of k.  Found with tools/trace_divergence.py (concurrent handles deviated from a solo solve in groups of four
+// adjacent slots, from some time step to the end of the horizon).  Fix: the elected lane consumes one register of every
+// LDS of the stage (a warp instruction retires for all lanes at once) in a store the compiler cannot drop, then issues.
+template <int C> __device__ __forceinline__ uint32_t ring_token(const double* v) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < C; i += 2) t |= (uint32_t)__double2hiint(v[i]);   // one element per 16-byte LDS
+  return t;
+}
+__device__ __forceinline__ void ring_reads_done(volatile uint32_t* scratch, uint32_t token) { *scratch = token; }
+
 }  // namespace ilqr

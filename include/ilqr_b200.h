@@ -335,8 +335,8 @@ int32_t ilqr_set_variant(ilqr_handle* h, int32_t variant);
 /* Kernel-selection thresholds of the batch path (2-link model): the split backward pass (time-parallel linearisation +
  * Riccati kernel) is used when live slots <= split_below, its 4-lane cooperative Riccati kernel when <= coop_below, the
  * two-kernel forward pass (alpha = 1 for all, dense retry kernel) when > fwd_split_above; compaction != 0 retires and
- * re-packs finished slots between iterations.  Negative values leave a setting unchanged.  ilqr_pool_create with more
- * than one handle selects (0, 0, INT32_MAX, 0): see DESIGN.md section 5, "handles running concurrently on one GPU". */
+ * re-packs finished slots between iterations.  Negative values leave a setting unchanged.  All variants give
+ * bit-identical results; the thresholds only trade launch count against latency (tools/compare_paths.py bisects with them). */
 int32_t ilqr_set_tuning(ilqr_handle* h, int32_t split_below, int32_t coop_below, int32_t fwd_split_above, int32_t compaction);
 int32_t ilqr_sync(ilqr_handle* h);
 void* ilqr_stream(ilqr_handle* h);                    /* the cudaStream_t of this handle */

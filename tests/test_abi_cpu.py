@@ -52,6 +52,10 @@ def test_no_cpu_fallback():
         ilqr_b200.BatchSolver(p)
     with pytest.raises(ilqr_b200.IlqrError):
         ilqr_b200.fit(np.zeros((11, 4)), np.zeros((10, 2)), p)
+    with pytest.raises(ilqr_b200.IlqrError, match="no CUDA device"):
+        ilqr_b200.Streamer(p, 2)
+    with pytest.raises(ilqr_b200.IlqrError):
+        ilqr_b200.SolverPool(p, 2)
 
 
 def test_shape_assert_mirrors_reference():

@@ -404,3 +404,48 @@ def test_streamer_equals_batch_solves(device):
         assert np.array_equal(oc, refs[b]["cost"]), b
         assert np.array_equal(ox.transpose(2, 1, 0), refs[b]["x"]), b
         assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b
+
+
+def test_full_size_solve_paths_agree_bit_for_bit():
+    """BASELINE config-2 size (B = 65,536, H = 200).  The same batch through (i) one handle of the batch path that has
+    the GPU to itself, (ii) the streamer (56,832 slots, two batches in flight so that slots are refilled across the
+    batch boundary), (iii) the pool scheduler with four handles whose kernels overlap on the device: every trajectory's
+    final iterate and iteration count must be identical.  (Small batches do not exercise (iii): their kernels barely
+    overlap — DESIGN.md section 5b.)"""
+    import torch
+    B, H = 65536, 200
+    x0 = np.asfortranarray(np.random.default_rng(1000).random((B, 4)).T)
+    with _solver(H, B) as s:
+        s.upload_x0(x0, np.zeros((H, 2, B), order="F"))
+        dx = torch.empty((B, 4, H + 1), dtype=torch.float64, device="cuda")
+        s.download_device(_abi.X, dx.data_ptr())
+        du = torch.zeros((B, 2, H), dtype=torch.float64, device="cuda")
+        s.upload_device(dx.data_ptr(), du.data_ptr())
+        s.fit(100, 1e-6)
+        rx, ru = torch.empty_like(dx), torch.empty_like(du)
+        s.download_device(_abi.X, rx.data_ptr()); s.download_device(_abi.U, ru.data_ptr())
+        ri = torch.from_numpy(s.download(_abi.ITERS)).cuda()
+
+    def fresh():
+        return [torch.zeros_like(dx), torch.zeros_like(du), torch.zeros(B, dtype=torch.float64, device="cuda"),
+                torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")]
+
+    outs = [fresh() for _ in range(2)]
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, 56832), B, ring=2) as st:
+        tk = [st.submit_ptrs(dx.data_ptr(), du.data_ptr(), *[t.data_ptr() for t in o], device=True) for o in outs]
+        for t in tk:
+            st.wait(t)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o[0], rx) and torch.equal(o[1], ru) and torch.equal(o[3], ri)
+    NH = 4
+    pouts = [fresh() for _ in range(NH)]
+    with ilqr_b200.SolverPool(ilqr_b200.two_link_problem(H, B), NH) as pool:
+        tk = [pool.submit_ptrs(dx.data_ptr(), du.data_ptr(), None, 100, 1e-6, o[0].data_ptr(), o[1].data_ptr(), None, o[3].data_ptr(), None,
+                               device=True) for o in pouts]
+        for t in tk:
+            pool.wait(t)
+    torch.cuda.synchronize()
+    for o in pouts:
+        assert torch.equal(o[3], ri), int((o[3] != ri).sum())
+        assert torch.equal(o[0], rx) and torch.equal(o[1], ru)
