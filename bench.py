@@ -484,10 +484,9 @@ def run_b200(args):
     roofline = {
         "bound": "hbm", "kernel": "round_lpt_two_link<12, 4> (backward sweep + forward sweep + accept / converge test + retirement + admission; "
                                   "the only kernel launched in the timed region)",
-        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 2.81e9, "peak_source": peak_src,
-        "traffic_note": "dram read+write of one full-width launch under ncu (profiles/ncu_full_r1_round.txt): 2.20 GB read + 0.61 GB "
-                        "written; algorithmic %.3e B for %d slots — part of the gains written by the backward sweep is still in L2 "
-                        "when the forward sweep reads it" % (ITER_BYTES * SLOTS, SLOTS),
+        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 3.708e9, "peak_source": peak_src,
+        "traffic_note": "dram read+write of one full-width launch under ncu (profiles/ncu_full_r1_round.txt): 2.20 GB read + 1.51 GB "
+                        "written; algorithmic %.3e B for %d slots" % (ITER_BYTES * SLOTS, SLOTS),
         "algorithmic_bytes_per_trajectory_iteration": ITER_BYTES, "avg_launch_ms": avg_launch_ms, "launches_timed": rounds_timed,
         "launches_in_timed_region": rounds_total, "slots": SLOTS,
         "trajectory_iterations_per_launch": traj_iters_total / rounds_total if rounds_total else None,
@@ -496,7 +495,7 @@ def run_b200(args):
         "fp64": {"achieved_tflops": tfl, "peak_tflops": fp64_peak_tf, "frac": tfl / fp64_peak_tf if (tfl and fp64_peak_tf) else None,
                  "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
                  "fp64_instr_per_trajectory_step": FP64_ROUND,
-                 "note": "the binding roofline: the FP64 pipe is 75 % active in a full-width launch (ncu), HBM traffic 3.0 TB/s"},
+                 "note": "the binding roofline: the FP64 pipe is 71 % active in a full-width launch (ncu, 1.03 ms), DRAM traffic 3.6 TB/s"},
         "batch_path_kernels": {"fwd_lpt_two_link": kernel_roofline("fwd"), "backward_pass": kernel_roofline("bwd")},
     }
     isolated = {"value": world * B / (iso_ms * 1e-3), "unit": UNIT, "ms_per_step": iso_ms,

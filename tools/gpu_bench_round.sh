@@ -8,5 +8,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-aux --no-e2e --pool-steps 0 > gpurun_out/ncu_launches_round.log 2>&1
 tail -2 gpurun_out/ncu_launches_round.log | head -c 300; echo
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:round_lpt --launch-skip 40 --launch-count 1 \
-  -o gpurun_out/prof_round_r1 -f python tools/stream_bench.py 2 1 56832 > gpurun_out/ncu_round.log 2>&1
+  -o gpurun_out/prof_round_r1 -f python tools/stream_bench.py 6 1 56832 > gpurun_out/ncu_round.log 2>&1
 tail -2 gpurun_out/ncu_round.log
