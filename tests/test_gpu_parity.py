@@ -406,6 +406,38 @@ def test_streamer_equals_batch_solves(device):
         assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b
 
 
+@pytest.mark.parametrize("H,slots,Bb,nb,max_iter,n_alpha", [(1, 40, 37, 3, 4, 32), (5, 33, 50, 4, 3, 32), (60, 64, 64, 3, 12, 1), (37, 96, 1, 9, 8, 32)])
+def test_streamer_ragged_sizes_and_exhausted_line_search(H, slots, Bb, nb, max_iter, n_alpha):
+    """Streamer edge cases: horizon shorter than the slab ring (H = 1), slot counts that do not fill the last warp, batches
+    smaller and larger than the slot count (single-trajectory batches included), max_iter reached after very few
+    iterations, and a line search that runs out of step sizes (n_alpha = 1 on the stress inputs ⇒ LS_EXHAUSTED) — each
+    batch against a plain batched solve of the same problem, bit for bit."""
+    n = nb * Bb
+    _, xa, ua = config2_batch(n - n // 2, H, seed=41)
+    _, xb, ub = stress_batch(n // 2, H, seed=42)
+    x = np.asfortranarray(np.concatenate([xa, xb], axis=2)); u = np.asfortranarray(np.concatenate([ua, ub], axis=2))
+    perm = np.random.default_rng(2).permutation(n)
+    x = np.asfortranarray(x[:, :, perm]); u = np.asfortranarray(u[:, :, perm])
+    refs = []
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, Bb, n_alpha=n_alpha)) as s:
+        for b in range(nb):
+            sl = slice(b * Bb, (b + 1) * Bb)
+            refs.append(s.solve(np.asfortranarray(x[:, :, sl]), np.asfortranarray(u[:, :, sl]), max_iter=max_iter, tol=1e-6))
+    if n_alpha == 1:
+        assert (np.concatenate([r["status"] for r in refs]) & _abi.STATUS_LS_EXHAUSTED).any()
+    outs = [dict(x=np.zeros((H + 1, 4, Bb), order="F"), u=np.zeros((H, 2, Bb), order="F"), cost=np.zeros(Bb),
+                 iters=np.zeros(Bb, dtype=np.int32), status=np.zeros(Bb, dtype=np.int32)) for _ in range(nb)]
+    ins = [(np.asfortranarray(x[:, :, b * Bb:(b + 1) * Bb]), np.asfortranarray(u[:, :, b * Bb:(b + 1) * Bb])) for b in range(nb)]
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, slots, n_alpha=n_alpha), Bb, ring=2, max_iter=max_iter, tol=1e-6) as st:
+        tickets = [st.submit(ins[b][0], ins[b][1], outs[b]) for b in range(nb)]
+        st.wait_all()
+        for t in tickets:
+            st.wait(t)
+    for b in range(nb):
+        for k in ("iters", "status", "cost", "x", "u"):
+            assert np.array_equal(outs[b][k], refs[b][k], equal_nan=True), (b, k)
+
+
 def test_full_size_solve_paths_agree_bit_for_bit():
     """BASELINE config-2 size (B = 65,536, H = 200).  The same batch through (i) one handle of the batch path that has
     the GPU to itself, (ii) the streamer (56,832 slots, two batches in flight so that slots are refilled across the
