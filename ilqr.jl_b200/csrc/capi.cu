@@ -82,6 +82,7 @@ struct ilqr_handle {
   int32_t round_shift = 1;                   // phase-shift a third / half of the warps (ILQR_ROUND_SHIFT)
   int32_t round_group = 8;                   // rounds between completion checks (ILQR_ROUND_GROUP)
   bool stream_fused = true;                  // ILQR_STREAM_FUSED=0: the launch-per-pass streaming loop
+  bool round_drain = true;                   // gather the remaining trajectories once the queue is empty (ILQR_ROUND_DRAIN=0: off)
   double stream_prof[4] = {0, 0, 0, 0};      // last stream: device ms, rounds launched, rounds until done, n_total
   std::string err;
 };
@@ -389,6 +390,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   if (const char* e = getenv("ILQR_ROUND_SHIFT")) h->round_shift = atoi(e);
   if (const char* e = getenv("ILQR_ROUND_GROUP")) h->round_group = std::max(1, atoi(e));
   if (const char* e = getenv("ILQR_STREAM_FUSED")) h->stream_fused = atoi(e) != 0;
+  if (const char* e = getenv("ILQR_ROUND_DRAIN")) h->round_drain = atoi(e) != 0;
   if (is_chain) {
     ChainP& c = h->chain;
     c.nq = p->nq; c.dt = p->dt;
@@ -808,13 +810,14 @@ static int32_t round_set_batch(ilqr_handle* h, int slot, const BatchTab& e) {
   return ILQR_OK;
 }
 
-static int32_t round_group(ilqr_handle* h, long long n_avail, int32_t max_iter, double tol) {
+static int32_t round_group(ilqr_handle* h, long long n_avail, int32_t max_iter, double tol, bool drain) {
   const int G = h->round_group;
   const int64_t g = h->round_groups;
   for (int r = 0; r < G; ++r) {
     RoundArgs ra{};
     ra.n_avail = n_avail; ra.tol = tol; ra.parity = h->round_parity; ra.shifted = h->round_shift; ra.max_iter = max_iter;
     ra.pub_slot = (int32_t)(g & 1);
+    ra.drain = (drain && h->round_drain) ? 1 : 0;
     launch_round_two_link(h->rp, h->mp, h->cp, ra, h->round_warps, h->stream);
     h->round_parity ^= 1;
   }
@@ -875,7 +878,7 @@ int32_t ilqr_stream_solve_device(ilqr_handle* h, int64_t n_total, const double* 
     const int64_t guard = ((n_total + p.B - 1) / p.B + 1) * (int64_t)max_iter * p.n_alpha + 4 * h->round_group;
     int64_t done_at = -1;
     while (h->pub_retired < n_total) {
-      if (int32_t rc = round_group(h, n_total, max_iter, tol)) return rc;
+      if (int32_t rc = round_group(h, n_total, max_iter, tol, h->pub_next >= n_total)) return rc;
       if (h->pub_retired >= n_total) done_at = (h->round_groups - 1) * h->round_group;
       else if (h->rounds_launched > guard) return fail(h, ILQR_ERR_STATE, "stream solve: no progress (internal error)");
     }
@@ -1239,7 +1242,9 @@ int32_t streamer_step(ilqr_streamer* s, int64_t sub, int64_t& uploaded, int64_t&
     ++published;
   }
   // 3. one more group of rounds; afterwards the counters of the group before it are known
-  if (int32_t rc = round_group(h, published * s->Bb, s->max_iter, s->tol)) return rc;
+  // drain: nothing left to admit and nothing on its way (the counters lag two groups: that only delays the switch)
+  const bool drain = published == sub && h->pub_next >= published * s->Bb;
+  if (int32_t rc = round_group(h, published * s->Bb, s->max_iter, s->tol, drain)) return rc;
   const int64_t seen_group = h->round_groups - 2;   // newest group whose counters were read
   // 4. batches whose last trajectory has retired: copy back (host) / complete (device)
   std::vector<int64_t> finished;

@@ -67,6 +67,7 @@ struct RoundArgs {
   long long n_avail;            // trajectories [0, n_avail) of the stream are resident
   double tol;
   int32_t parity, shifted, max_iter, pub_slot;
+  int32_t drain;                // the pending queue is empty: gather the remaining trajectories (kernels_round.cu)
 };
 void init_round_attributes();
 void launch_round_two_link(const RoundP& rp, const TwoLinkP& mp, const CostP& cp, const RoundArgs& ra, int warps_per_sm,

@@ -75,6 +75,19 @@ __device__ __forceinline__ void copy_slot(const double* Xs, const double* Us, do
     stv<NU>(Ud + ((int64_t)k * S + sj) * NU, v);
   }
 }
+// slot src → slot dst of the same buffer
+__device__ __forceinline__ void move_slot(double* X, double* U, int64_t S, int src, int dst, int H, int lane) {
+  for (int k = lane; k <= H; k += 32) {
+    double v[NX];
+    ldv_cg<NX>(X + ((int64_t)k * S + src) * NX, v);
+    stv<NX>(X + ((int64_t)k * S + dst) * NX, v);
+  }
+  for (int k = lane; k < H; k += 32) {
+    double v[NU];
+    ldv_cg<NU>(U + ((int64_t)k * S + src) * NU, v);
+    stv<NU>(U + ((int64_t)k * S + dst) * NU, v);
+  }
+}
 // slot → boundary layout (trajectory-major, component rows of N / H doubles; layout.cu)
 __device__ __forceinline__ void retire_slot(const double* Xs, const double* Us, double* __restrict__ ox,
                                             double* __restrict__ ou, int64_t S, int sj, int H, int lane) {
@@ -386,9 +399,46 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
     }
   }
 
-  // last block publishes the counters into mapped host memory (no DMA copy that could queue behind bulk transfers)
   __threadfence();
   __syncthreads();
+  // Drain (the pending queue is empty, ra.drain): gather what is left of the block's trajectories in its first four
+  // warps — one per SM sub-partition, all of the backward → forward kind.  Warp w adopts from warps w+4, w+8, … (the
+  // ones it shares a scheduler with) into its idle lanes: the iterate every slot reads in the next launch (buffer
+  // parity^1) and the slot's scalars move, the source slot inherits the adopting lane's queue ticket.  A trajectory
+  // that came from a forward → backward warp has its gains recomputed from the same iterate: identical.  Lanes in a
+  // line-search retry (they still need their slot's old gains) stay where they are until the retry is over.  The
+  // 2.7 % of trajectories that run to max_iter would otherwise keep most warps alive for the last ~90 launches of a
+  // stream; gathered, each scheduler runs one warp and a launch costs its latency instead of the full-width time.
+  if (ra.drain && warp < 4) {
+    const int b0 = blockIdx.x * kWarps * 32, sd = b0 + warp * 32 + lane;
+    const bool mine = sd < rp.nslots;
+    const long long myt = mine ? __ldcg(rp.traj + sd) : 0;
+    bool myidle = mine && myt < 0;
+    double* Xn = rp.x[ra.parity ^ 1];
+    double* Un = rp.u[ra.parity ^ 1];
+#pragma unroll 1
+    for (int sw = warp + 4; sw < kWarps; sw += 4) {
+      const int ss = b0 + sw * 32 + lane;
+      const bool in = ss < rp.nslots;
+      const bool cand = in && __ldcg(rp.traj + ss) >= 0 && __ldcg(rp.ls_j + ss) == 0;
+      unsigned cm = __ballot_sync(kFull, cand), im = __ballot_sync(kFull, myidle);
+      while (cm && im) {
+        const int jc = __ffs(cm) - 1, ji = __ffs(im) - 1;
+        cm &= cm - 1; im &= im - 1;
+        const int src = b0 + sw * 32 + jc, dst = b0 + warp * 32 + ji;
+        move_slot(Xn, Un, rp.S, src, dst, rp.H, lane);
+        if (lane == ji) {
+          rp.prev_cost[dst] = __ldcg(rp.prev_cost + src); rp.iters[dst] = __ldcg(rp.iters + src);
+          rp.status[dst] = __ldcg(rp.status + src); rp.ls_j[dst] = 0;
+          rp.traj[dst] = __ldcg(rp.traj + src);
+          rp.traj[src] = myt;
+          myidle = false;
+        }
+      }
+    }
+  }
+  // last block publishes the counters into mapped host memory (no DMA copy that could queue behind bulk transfers)
+  __threadfence();
   if (threadIdx.x == 0) last_block = (atomicAdd(rp.blocks_done, 1u) == gridDim.x - 1);
   __syncthreads();
   if (last_block) {

@@ -406,12 +406,14 @@ def test_streamer_equals_batch_solves(device):
         assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b
 
 
-@pytest.mark.parametrize("H,slots,Bb,nb,max_iter,n_alpha", [(1, 40, 37, 3, 4, 32), (5, 33, 50, 4, 3, 32), (60, 64, 64, 3, 12, 1), (37, 96, 1, 9, 8, 32)])
+@pytest.mark.parametrize("H,slots,Bb,nb,max_iter,n_alpha", [(1, 40, 37, 3, 4, 32), (5, 33, 50, 4, 3, 32), (60, 64, 64, 3, 12, 1), (37, 96, 1, 9, 8, 32),
+                                                              (40, 384, 150, 4, 25, 32), (25, 800, 333, 3, 30, 32)])
 def test_streamer_ragged_sizes_and_exhausted_line_search(H, slots, Bb, nb, max_iter, n_alpha):
     """Streamer edge cases: horizon shorter than the slab ring (H = 1), slot counts that do not fill the last warp, batches
     smaller and larger than the slot count (single-trajectory batches included), max_iter reached after very few
     iterations, and a line search that runs out of step sizes (n_alpha = 1 on the stress inputs ⇒ LS_EXHAUSTED) — each
-    batch against a plain batched solve of the same problem, bit for bit."""
+    batch against a plain batched solve of the same problem, bit for bit.  The last two cases have enough warps per block
+    for the drain to gather trajectories across warps (kernels_round.cu)."""
     n = nb * Bb
     _, xa, ua = config2_batch(n - n // 2, H, seed=41)
     _, xb, ub = stress_batch(n // 2, H, seed=42)
