@@ -472,7 +472,7 @@ def run_b200(args):
         return r
 
     # ---- roofline of the round kernel (every launch of the timed region): CUDA events on the launching stream, fence to
-    # fence over groups of 8 back-to-back launches (csrc/capi.cu round_group); algorithmic bytes and FP64 instructions of
+    # fence over groups of 8 back-to-back launches (csrc/streamer.cu round_group); algorithmic bytes and FP64 instructions of
     # the trajectory-iterations those launches performed
     ITER_BYTES = BWD_BYTES + FWD_BYTES                        # 60,904 B per trajectory-iteration
     FP64_ROUND = FP64_INSTR["bwd"] + FP64_INSTR["fwd"]        # 1,104 DFMA-class instructions per trajectory-step (SASS)
