@@ -495,6 +495,7 @@ def run_b200(args):
         "fp64": {"achieved_tflops": tfl, "peak_tflops": fp64_peak_tf, "frac": tfl / fp64_peak_tf if (tfl and fp64_peak_tf) else None,
                  "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
                  "fp64_instr_per_trajectory_step": FP64_ROUND,
+                 "reference_formulation_flops_per_trajectory_step": 9619,   # oracle/count_ops.cpp (+ 180 sin/cos): dual-number Jacobians / Hessians
                  "note": "the binding roofline: the FP64 pipe is 71 % active in a full-width launch (ncu, 1.03 ms), DRAM traffic 3.6 TB/s"},
         "batch_path_kernels": {"fwd_lpt_two_link": kernel_roofline("fwd"), "backward_pass": kernel_roofline("bwd")},
     }

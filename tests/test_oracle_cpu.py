@@ -182,3 +182,17 @@ def test_batch_threads_equal_single():
     assert np.array_equal(r1["x"], r4["x"]) and np.array_equal(r1["iters"], r4["iters"])
     one = orc.fit(x[:, :, 2], u[:, :, 2], max_iter=30)
     assert np.array_equal(one["x"], r1["x"][:, :, 2]) and one["iters"] == r1["iters"][2]
+
+
+def test_instrumented_op_count_of_the_reference_formulation():
+    """exact fp64 operation counts of one time step of the reference's formulation (dual-number Jacobians
+    and Hessians as ForwardDiff evaluates them), from the oracle's own templates run on a counting scalar
+    (oracle/count_ops.cpp).  Pins the constants quoted in DESIGN.md §4 and in bench.py's roofline block."""
+    import json
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    subprocess.check_call(["make", "-s", "-C", here, "count_ops"])
+    out = subprocess.run([os.path.join(here, "count_ops")], capture_output=True, text=True, check=True).stdout
+    line = [l for l in out.splitlines() if l.startswith("JSON ")][0]
+    c = json.loads(line[5:])
+    assert c == {"backward_flops_per_step": 9063, "forward_flops_per_step": 556, "trig_per_step": 180, "neg_per_step": 448}
