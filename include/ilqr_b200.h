@@ -249,7 +249,10 @@ int32_t ilqr_solve(ilqr_handle* h, const double* x_init, const double* u_init, c
  * arrays and their slots are refilled from the pending input, so every launch runs full width and the latency-bound
  * tail is paid once per stream instead of once per batch.  Per-trajectory semantics are those of ilqr_fit (tol,
  * max_iter apply to each trajectory); x_traj is not supported.  d_cost/d_iters/d_status nullable;
- * batch_iterations (nullable) receives the number of backward+forward launches. */
+ * batch_iterations (nullable) receives the number of backward+forward launches.  For ILQR_MODEL_TWO_LINK this runs the
+ * fused rounds (csrc/kernels_round.cu: one launch per iteration does both sweeps, the accept / converge test, retirement
+ * and admission); the other models go through separate backward / forward / commit / compaction launches.  Results are
+ * bit-identical to ilqr_fit on the same trajectories either way.  See ilqr_streamer_* for batches that arrive over time. */
 int32_t ilqr_stream_solve_device(ilqr_handle* h, int64_t n_total, const double* d_x_init, const double* d_u_init,
                                  int32_t max_iter, double tol, double* d_x_out, double* d_u_out, double* d_cost_out,
                                  int32_t* d_iters_out, int32_t* d_status_out, int64_t* batch_iterations);
