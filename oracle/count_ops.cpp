@@ -15,6 +15,7 @@
 #include <cstdio>
 
 #include "ilqr_oracle.hpp"
+#include "serial_chain.hpp"
 
 namespace oracle {
 
@@ -53,6 +54,92 @@ static OpCount operator+(OpCount a, const OpCount& b) {
 }
 
 }  // namespace oracle
+
+// The same for BASELINE configs[3]: the synthetic 7-revolute chain (axes z,y,z,y,z,y,z, origin (1,0,0), mass 3, inertia
+// 0.5·I, zero gravity; bench.py seven_dof_chain), n = 14, m = 7, through the rigid-body plugin as restated in
+// serial_chain.hpp (RNEA bias + CRBA mass matrix with explicit 6×6 Plücker transforms, `M \ (u − bias)`, RK4) and the
+// same ForwardDiff-style calls.  RigidBodyDynamics.jl's own spatial algebra is leaner than dense 6×6 products, so this
+// is an upper estimate of what the reference executes, not a pinned figure.
+static void chain7() {
+  using namespace oracle;
+  constexpr int NQ = 7, cn = 14, cm = 7;
+  using P = SerialChain<NQ>;
+  using CX = Vec<R, cn>; using CU = Vec<R, cm>;
+  using CXX = Mat<R, cn, cn>; using CXU = Mat<R, cn, cm>; using CUX = Mat<R, cm, cn>; using CUU = Mat<R, cm, cm>;
+  P p;
+  for (int i = 0; i < NQ; ++i) {
+    double row[kChainStride] = {0};
+    row[0] = 1.0;
+    row[6 + ((i % 2 == 0) ? 2 : 1)] = 1.0;
+    row[9] = 3.0;
+    row[13] = 0.5; row[16] = 0.5; row[18] = 0.5;
+    p.joint[i].load(row);
+  }
+  for (int i = 0; i < NQ; ++i) { p.x_target[i] = 0.1 * (i + 1); p.w_x[i] = 1.0; p.w_xf[i] = 1.0; p.w_u[i] = 1.0; }
+  CX x; CU u;
+  for (int i = 0; i < NQ; ++i) { x[i] = 0.2 * (i + 1) - 0.7; x[NQ + i] = 0.05 * (i + 1); u[i] = 0.1 * (i - 3); }
+  take();
+  CXX A = jacobian<cn>([&](const auto& xd) { return p.dynamicsf(xd, lift<R, cm, cn>(u)); }, x);
+  OpCount cA = take();
+  CXU B = jacobian<cn>([&](const auto& ud) { return p.dynamicsf(lift<R, cn, cm>(x), ud); }, u);
+  OpCount cB = take();
+  R q = p.immediate_cost(x, u);
+  CX qv = gradient<R, cn>([&](const auto& xd) {
+    using S = std::decay_t<decltype(xd[0])>;
+    Vec<S, cm> uu; for (int i = 0; i < cm; ++i) uu[i] = S(u[i]);
+    return p.immediate_cost(xd, uu); }, x);
+  CU rv = gradient<R, cm>([&](const auto& ud) {
+    using S = std::decay_t<decltype(ud[0])>;
+    Vec<S, cn> xx; for (int i = 0; i < cn; ++i) xx[i] = S(x[i]);
+    return p.immediate_cost(xx, ud); }, u);
+  CXX Q = hessian<R, cn>([&](const auto& xd) {
+    using S = std::decay_t<decltype(xd[0])>;
+    Vec<S, cm> uu; for (int i = 0; i < cm; ++i) uu[i] = S(u[i]);
+    return p.immediate_cost(xd, uu); }, x);
+  CUX Pm = jacobian<cm>([&](const auto& xd) {
+    using SX = std::decay_t<decltype(xd[0])>;
+    Vec<SX, cm> u0; for (int i = 0; i < cm; ++i) u0[i] = SX(u[i]);
+    return gradient<SX, cm>([&](const auto& ud) {
+      using SU = std::decay_t<decltype(ud[0])>;
+      Vec<SU, cn> xx; for (int i = 0; i < cn; ++i) xx[i] = SU(xd[i]);
+      return p.immediate_cost(xx, ud); }, u0);
+  }, x);
+  CUU Rm = hessian<R, cm>([&](const auto& ud) {
+    using S = std::decay_t<decltype(ud[0])>;
+    Vec<S, cn> xx; for (int i = 0; i < cn; ++i) xx[i] = S(x[i]);
+    return p.immediate_cost(xx, ud); }, u);
+  OpCount cQ = take();
+  CX sv; CXX S = CXX::zeros();
+  for (int i = 0; i < cn; ++i) { sv[i] = 0.1 * (i + 1); for (int j = 0; j < cn; ++j) S(i, j) = (i == j) ? 2.0 : 0.01; }
+  take();
+  auto Bt = transpose(B);
+  CU g = rv + Bt * sv;
+  CUX G = Pm + (Bt * S) * A;
+  CUU Hm = Rm + (Bt * S) * B;
+  CUU Hreg = Hm;
+  for (int i = 0; i < cm; ++i) Hreg(i, i) = Hm(i, i) + R(0.01) * 1.0;
+  CU du = lu_solve<R, cm, 1>(-Hreg, g);
+  CUX K = lu_solve<R, cm, cn>(-Hreg, G);
+  auto Kt = transpose(K); auto At = transpose(A); auto Gt = transpose(G); auto dut = transpose(du);
+  R s_new = q + ((0.5 * dut) * Hm * du)[0] + (dut * g)[0];
+  CX sv_new = qv + At * sv + (Kt * Hm) * du + Kt * g + Gt * du;
+  CXX S_new = Q + (At * S) * A + (Kt * Hm) * K + Kt * G + Gt * K;
+  OpCount cR = take();
+  (void)s_new; (void)sv_new; (void)S_new;
+  CX xn = p.dynamicsf(x, u);
+  OpCount cD = take();
+  (void)xn;
+  std::printf("\n7-DoF serial chain (configs[3]: n = 14, m = 7), reference formulation as restated in serial_chain.hpp, one time step:\n");
+  show("linearize_dynamics: A (jacobian over 14 directions)", cA);
+  show("linearize_dynamics: B (jacobian over 7 directions)", cB);
+  show("immediate_cost_quadratization", cQ);
+  show("Riccati step (g, G, H, two LU solves, step_back)", cR);
+  show("forward: dynamicsf (RK4)", cD);
+  OpCount t = cA + cB + cQ + cR + cD;
+  std::printf("per trajectory-step: %lld flops (+ %lld sin/cos) = %.2f MFLOP; per trajectory-iteration at H = 100: %.1f MFLOP\n", t.flops(), t.trig,
+              t.flops() / 1e6, 100.0 * t.flops() / 1e6);
+  std::printf("JSON7 {\"flops_per_step\": %lld, \"riccati_flops_per_step\": %lld, \"trig_per_step\": %lld}\n", t.flops(), cR.flops(), t.trig);
+}
 
 int main() {
   using namespace oracle;
@@ -160,5 +247,6 @@ int main() {
   std::printf("per trajectory-iteration at H = 200: %.3f MFLOP\n", 200.0 * tot.flops() / 1e6);
   std::printf("JSON {\"backward_flops_per_step\": %lld, \"forward_flops_per_step\": %lld, \"trig_per_step\": %lld, \"neg_per_step\": %lld}\n",
               bwd.flops(), fwd.flops(), tot.trig, tot.neg);
+  chain7();
   return 0;
 }

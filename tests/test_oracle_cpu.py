@@ -196,3 +196,7 @@ def test_instrumented_op_count_of_the_reference_formulation():
     line = [l for l in out.splitlines() if l.startswith("JSON ")][0]
     c = json.loads(line[5:])
     assert c == {"backward_flops_per_step": 9063, "forward_flops_per_step": 556, "trig_per_step": 180, "neg_per_step": 448}
+    c7 = json.loads([l for l in out.splitlines() if l.startswith("JSON7 ")][0][6:])      # 7-DoF chain, configs[3]
+    assert c7 == {"flops_per_step": 2231012, "riccati_flops_per_step": 34055, "trig_per_step": 560}
+    # SURVEY §8(d) estimated the dense Riccati step at F_ric(14, 7) = 30.4 kFLOP "+ ~8 % matrix additions"
+    assert abs(c7["riccati_flops_per_step"] / 30.4e3 - 1.08) < 0.06
