@@ -41,7 +41,7 @@ void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaSt
 // arrays are found in entry (t / Bb) % R of a small device table (a ring of R batches in flight).
 struct BatchTab {
   const double* in_x; const double* in_u;                                          // [Bb][n·N], [Bb][m·H]
-  double* out_x; double* out_u; double* out_cost; int32_t* out_iters; int32_t* out_status;   // last three nullable
+  double* out_x; double* out_u; double* out_cost; int32_t* out_iters; int32_t* out_status;   // all nullable
   int64_t reserved;
 };
 struct RoundP {
@@ -70,6 +70,9 @@ struct RoundArgs {
   int32_t drain;                // the pending queue is empty: gather the remaining trajectories (kernels_round.cu)
 };
 void init_round_attributes();
+// x_init[Bb][n][N] (boundary layout) = open-loop rollout of u (boundary layout, nullptr = zeros) from x0[Bb][n]
+void launch_rollout_tf_two_link(const TwoLinkP& mp, const double* d_x0, const double* d_u, double* d_x, long long Bb, int H,
+                                cudaStream_t s);
 void launch_round_two_link(const RoundP& rp, const TwoLinkP& mp, const CostP& cp, const RoundArgs& ra, int warps_per_sm,
                            cudaStream_t s);
 

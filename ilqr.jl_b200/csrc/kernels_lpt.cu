@@ -660,7 +660,10 @@ fwd_lpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ Tw
     if (bad) st.status[s] |= ST_NAN_ROLLOUT;
     st.new_cost[s] = acc_cost; st.alpha[s] = acc_alpha; st.du2[s] = acc_du2;
     // two-kernel mode (max_pass = 1): still-rejected lanes continue in fwd_retry_two_link
-    if (searching && max_pass < st.n_alpha) st.retry_list[atomicAdd(st.n_retry, 1)] = s;
+    if (searching && max_pass < st.n_alpha) {
+      const int idx = atomicAdd(st.n_retry, 1);
+      if (idx < st.S) st.retry_list[idx] = s;   // the list has S entries; the counter is zeroed before every α = 1 launch
+    }
   }
 }
 
@@ -704,7 +707,7 @@ __global__ void __launch_bounds__(kBlock)
 fwd_retry_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
                    const __grid_constant__ CostP cp) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= *st.n_retry) return;
+  if (i >= *st.n_retry || i >= st.S) return;
   const int s = st.retry_list[i];
   const int64_t S = st.S;
   const int H = st.H;
@@ -1091,6 +1094,9 @@ void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const Cos
 }
 void launch_fwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
   if (st.nslots <= 0) return;
+  // a forward pass may follow another one without a commit in between (ilqr_forward_pass twice, or an upload after a
+  // forward pass): the retry list always starts empty, in stream order
+  cudaMemsetAsync(st.n_retry, 0, sizeof(int32_t), s);
   if (st.xtraj) fwd_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp, 1);
   else fwd_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp, 1);
   if (st.n_alpha > 1) fwd_retry_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, cp);

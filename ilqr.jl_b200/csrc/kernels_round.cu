@@ -92,18 +92,20 @@ __device__ __forceinline__ void move_slot(double* X, double* U, int64_t S, int s
 __device__ __forceinline__ void retire_slot(const double* Xs, const double* Us, double* __restrict__ ox,
                                             double* __restrict__ ou, int64_t S, int sj, int H, int lane) {
   const int N = H + 1;
-  for (int k = lane; k < N; k += 32) {
-    double v[NX];
-    ldv_cg<NX>(Xs + ((int64_t)k * S + sj) * NX, v);
+  if (ox)   // nullable: a caller that wants ū (or the scalars) only
+    for (int k = lane; k < N; k += 32) {
+      double v[NX];
+      ldv_cg<NX>(Xs + ((int64_t)k * S + sj) * NX, v);
 #pragma unroll
-    for (int c = 0; c < NX; ++c) ox[c * N + k] = v[c];
-  }
-  for (int k = lane; k < H; k += 32) {
-    double v[NU];
-    ldv_cg<NU>(Us + ((int64_t)k * S + sj) * NU, v);
+      for (int c = 0; c < NX; ++c) ox[c * N + k] = v[c];
+    }
+  if (ou)
+    for (int k = lane; k < H; k += 32) {
+      double v[NU];
+      ldv_cg<NU>(Us + ((int64_t)k * S + sj) * NU, v);
 #pragma unroll
-    for (int c = 0; c < NU; ++c) ou[c * H + k] = v[c];
-  }
+      for (int c = 0; c < NU; ++c) ou[c * H + k] = v[c];
+    }
 }
 __device__ __forceinline__ void admit_slot(const double* __restrict__ ix, const double* __restrict__ iu, double* Xd,
                                            double* Ud, int64_t S, int sj, int H, int lane) {
@@ -357,8 +359,8 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
           const long long tj = __shfl_sync(kFull, t, j);
           const long long bj = tj / rp.Bb, loc = tj - bj * rp.Bb;
           const BatchTab& e = rp.tab[bj % rp.R];
-          retire_slot(aj == 1 ? X : Xo, aj == 1 ? U : Uo, e.out_x + loc * (NX * (long long)(H + 1)),
-                      e.out_u + loc * (NU * (long long)H), S, s0 + j, H, lane);
+          retire_slot(aj == 1 ? X : Xo, aj == 1 ? U : Uo, e.out_x ? e.out_x + loc * (NX * (long long)(H + 1)) : nullptr,
+                      e.out_u ? e.out_u + loc * (NU * (long long)H) : nullptr, S, s0 + j, H, lane);
         }
         if (action == 1 || action == 2) {
           const long long bj = t / rp.Bb, loc = t - bj * rp.Bb;
@@ -442,6 +444,9 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
   if (threadIdx.x == 0) last_block = (atomicAdd(rp.blocks_done, 1u) == gridDim.x - 1);
   __syncthreads();
   if (last_block) {
+    // every block's result stores are ordered before its blocks_done ticket (device scope); this fence extends that
+    // order to the host / copy engines that act on the counters published below
+    __threadfence_system();
     for (int i = threadIdx.x; i < rp.R; i += kWarps * 32) rp.done_host[i] = atomicAdd(rp.done + i, 0);
     if (threadIdx.x == 0) {
       rp.pub[2 * ra.pub_slot] = (long long)atomicAdd(rp.retired, 0ull);
@@ -452,6 +457,28 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
   }
 }
 
+// Problem setup on device (animate_2_link.jl:11-16): x_init = open-loop rollout of u_init from x0, written in the
+// boundary layout the rounds admit from.  x0: [Bb][4]; u: boundary layout [Bb][2][H] or nullptr (= zeros, the
+// reference's own initial guess); x: [Bb][4][N].  Lane per trajectory, the same tl_step as every other path.
+__global__ void __launch_bounds__(128)
+rollout_tf_two_link(const __grid_constant__ TwoLinkP mp, const double* __restrict__ x0, const double* __restrict__ u,
+                    double* __restrict__ x, long long Bb, int H) {
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (t >= Bb) return;
+  const int N = H + 1;
+  double xb[NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) { xb[c] = x0[t * NX + c]; x[(t * NX + c) * N] = xb[c]; }
+  for (int k = 0; k < H; ++k) {
+    double ub[NU], xn[NX];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) ub[i] = u ? u[(t * NU + i) * H + k] : 0.0;
+    tl_step(mp, xb, ub, xn);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) { xb[c] = xn[c]; x[(t * NX + c) * N + k + 1] = xb[c]; }
+  }
+}
+
 template <int kWarps, int D> constexpr size_t round_smem() { return sizeof(double) * kWarps * D * kStageDoubles + sizeof(uint64_t) * kWarps * D; }
 
 }  // namespace
@@ -459,6 +486,11 @@ template <int kWarps, int D> constexpr size_t round_smem() { return sizeof(doubl
 void init_round_attributes() {
   cudaFuncSetAttribute(round_lpt_two_link<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<12, 4>());
   cudaFuncSetAttribute(round_lpt_two_link<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<16, 3>());
+}
+
+void launch_rollout_tf_two_link(const TwoLinkP& mp, const double* d_x0, const double* d_u, double* d_x, long long Bb, int H,
+                                cudaStream_t s) {
+  if (Bb > 0) rollout_tf_two_link<<<(unsigned)((Bb + 127) / 128), 128, 0, s>>>(mp, d_x0, d_u, d_x, Bb, H);
 }
 
 void launch_round_two_link(const RoundP& rp, const TwoLinkP& mp, const CostP& cp, const RoundArgs& ra, int warps_per_sm,

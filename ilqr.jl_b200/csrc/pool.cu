@@ -12,7 +12,6 @@
 #include <mutex>
 #include <string>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/ilqr_b200.h"
@@ -37,8 +36,10 @@ struct ilqr_pool {
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   std::deque<Job> queue;
-  std::unordered_map<int64_t, int32_t> finished;   // ticket → rc
-  int64_t next_ticket = 0, in_flight = 0;
+  // per ticket, kept for the life of the pool: a ticket may be waited for more than once, or after wait_all
+  std::vector<char> done;
+  std::vector<int32_t> rcs;
+  int64_t next_ticket = 0, in_flight = 0, reported = 0;   // reported: tickets below it were covered by a wait_all
   bool stop = false;
   std::string err;
 };
@@ -73,7 +74,7 @@ void worker_main(ilqr_pool* p, int idx) {
     {
       std::lock_guard<std::mutex> lk(p->mu);
       if (rc != 0) p->err = ilqr_last_error(h);
-      p->finished[job.ticket] = rc;
+      p->rcs[(size_t)job.ticket] = rc; p->done[(size_t)job.ticket] = 1;
       --p->in_flight;
     }
     p->cv_done.notify_all();
@@ -85,6 +86,7 @@ int64_t submit(ilqr_pool* p, Job job) {
   {
     std::lock_guard<std::mutex> lk(p->mu);
     job.ticket = p->next_ticket++;
+    p->done.push_back(0); p->rcs.push_back(0);
     p->queue.push_back(job);
     ++p->in_flight;
   }
@@ -155,10 +157,8 @@ int32_t ilqr_pool_wait(ilqr_pool* p, int64_t ticket) {
   if (!p || ticket < 0) return ILQR_ERR_INVALID;
   std::unique_lock<std::mutex> lk(p->mu);
   if (ticket >= p->next_ticket) return ILQR_ERR_INVALID;
-  p->cv_done.wait(lk, [&] { return p->finished.count(ticket) > 0; });
-  const int32_t rc = p->finished[ticket];
-  p->finished.erase(ticket);
-  return rc;
+  p->cv_done.wait(lk, [&] { return p->done[(size_t)ticket] != 0; });
+  return p->rcs[(size_t)ticket];
 }
 
 int32_t ilqr_pool_wait_all(ilqr_pool* p) {
@@ -166,9 +166,9 @@ int32_t ilqr_pool_wait_all(ilqr_pool* p) {
   std::unique_lock<std::mutex> lk(p->mu);
   p->cv_done.wait(lk, [&] { return p->in_flight == 0; });
   int32_t rc = ILQR_OK;
-  for (auto& kv : p->finished)
-    if (kv.second != 0) rc = kv.second;
-  p->finished.clear();
+  for (int64_t t = p->reported; t < p->next_ticket; ++t)
+    if (p->rcs[(size_t)t] != 0) rc = p->rcs[(size_t)t];
+  p->reported = p->next_ticket;
   return rc;
 }
 

@@ -155,7 +155,7 @@ struct ilqr_streamer {
   int32_t max_iter = 100;
   double tol = 1e-6;
   // device staging ring for host-pointer submissions (lazy)
-  double *sx = nullptr, *su = nullptr, *sox = nullptr, *sou = nullptr, *scost = nullptr;
+  double *sx = nullptr, *su = nullptr, *sx0 = nullptr, *sox = nullptr, *sou = nullptr, *scost = nullptr;
   int32_t *siters = nullptr, *sstatus = nullptr;
   cudaStream_t cs_in = nullptr, cs_out = nullptr;
   struct Entry {
@@ -163,6 +163,7 @@ struct ilqr_streamer {
     double *xo = nullptr, *uo = nullptr, *cost = nullptr;
     int32_t *iters = nullptr, *status = nullptr;
     bool host = false, busy = false;
+    bool x0mode = false;         // x points at x0[n,Bb]: x_init is rolled out on device (u may be NULL = zeros)
     int stage = 0;               // 0 submitted, 1 upload enqueued, 2 published to the kernels, 3 copy-back enqueued
     int64_t seq = -1, avail_group = 0;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -184,13 +185,17 @@ namespace {
 
 std::string g_streamer_err;
 
-int32_t streamer_alloc_staging(ilqr_streamer* s) {
-  if (s->sx) return ILQR_OK;
+// device staging, allocated on first need: inputs (host submissions and x0 submissions), outputs (host submissions)
+int32_t streamer_alloc_staging(ilqr_streamer* s, bool in, bool out) {
   ilqr_handle* h = s->h;
   const size_t N = h->prob.H + 1, H = h->prob.H, n = h->prob.n, m = h->prob.m, tot = (size_t)s->Bb * s->R;
-  CK(h, dalloc(&s->sx, N * n * tot)); CK(h, dalloc(&s->su, H * m * tot));
-  CK(h, dalloc(&s->sox, N * n * tot)); CK(h, dalloc(&s->sou, H * m * tot));
-  CK(h, dalloc(&s->scost, tot)); CK(h, dalloc(&s->siters, tot)); CK(h, dalloc(&s->sstatus, tot));
+  if (in && !s->sx) {
+    CK(h, dalloc(&s->sx, N * n * tot)); CK(h, dalloc(&s->su, H * m * tot)); CK(h, dalloc(&s->sx0, n * tot));
+  }
+  if (out && !s->sox) {
+    CK(h, dalloc(&s->sox, N * n * tot)); CK(h, dalloc(&s->sou, H * m * tot));
+    CK(h, dalloc(&s->scost, tot)); CK(h, dalloc(&s->siters, tot)); CK(h, dalloc(&s->sstatus, tot));
+  }
   return ILQR_OK;
 }
 
@@ -204,11 +209,27 @@ int32_t streamer_step(ilqr_streamer* s, int64_t sub, int64_t& uploaded, int64_t&
       std::lock_guard<std::mutex> lk(s->mu);
       e = s->ring[uploaded % s->R];
     }
-    if (e.host) {
-      if (int32_t rc = streamer_alloc_staging(s)) return rc;
+    if (e.host || e.x0mode) {
+      if (int32_t rc = streamer_alloc_staging(s, true, e.host)) return rc;
       const size_t slot = (size_t)(uploaded % s->R);
-      CK(h, cudaMemcpyAsync(s->sx + slot * Bb * N * n, e.x, sizeof(double) * Bb * N * n, cudaMemcpyHostToDevice, s->cs_in));
-      CK(h, cudaMemcpyAsync(s->su + slot * Bb * H * m, e.u, sizeof(double) * Bb * H * m, cudaMemcpyHostToDevice, s->cs_in));
+      double* sx = s->sx + slot * Bb * N * n;
+      double* su = s->su + slot * Bb * H * m;
+      if (e.x0mode) {
+        // problem setup on device (animate_2_link.jl:11-16): only x0 (and u_init, if any) crosses the bus
+        const double* x0 = e.x;
+        if (e.host) {
+          double* sx0 = s->sx0 + slot * Bb * n;
+          CK(h, cudaMemcpyAsync(sx0, e.x, sizeof(double) * Bb * n, cudaMemcpyHostToDevice, s->cs_in));
+          x0 = sx0;
+          if (e.u) CK(h, cudaMemcpyAsync(su, e.u, sizeof(double) * Bb * H * m, cudaMemcpyHostToDevice, s->cs_in));
+        }
+        if (!e.u) CK(h, cudaMemsetAsync(su, 0, sizeof(double) * Bb * H * m, s->cs_in));
+        launch_rollout_tf_two_link(h->mp, x0, e.u ? (e.host ? su : e.u) : nullptr, sx, (long long)Bb, (int)H, s->cs_in);
+        ++h->launches;
+      } else {
+        CK(h, cudaMemcpyAsync(sx, e.x, sizeof(double) * Bb * N * n, cudaMemcpyHostToDevice, s->cs_in));
+        CK(h, cudaMemcpyAsync(su, e.u, sizeof(double) * Bb * H * m, cudaMemcpyHostToDevice, s->cs_in));
+      }
       CK(h, cudaEventRecord(e.ev_in, s->cs_in));
     }
     e.stage = 1;
@@ -217,18 +238,20 @@ int32_t streamer_step(ilqr_streamer* s, int64_t sub, int64_t& uploaded, int64_t&
   while (published < uploaded) {
     ilqr_streamer::Entry& e = s->work[published % s->R];
     const size_t slot = (size_t)(published % s->R);
-    if (e.host) {
+    if (e.host || e.x0mode) {
       const bool starving = h->pub_next + 2LL * h->prob.B >= published * s->Bb;
       if (!starving && cudaEventQuery(e.ev_in) != cudaSuccess) break;
       CK(h, cudaStreamWaitEvent(h->stream, e.ev_in, 0));
     }
     BatchTab t{};
-    if (e.host) {
-      t.in_x = s->sx + slot * Bb * N * n; t.in_u = s->su + slot * Bb * H * m;
-      t.out_x = s->sox + slot * Bb * N * n; t.out_u = s->sou + slot * Bb * H * m;
-      t.out_cost = s->scost + slot * Bb; t.out_iters = s->siters + slot * Bb; t.out_status = s->sstatus + slot * Bb;
+    t.in_x = (e.host || e.x0mode) ? s->sx + slot * Bb * N * n : e.x;
+    t.in_u = (e.host || (e.x0mode && !e.u)) ? s->su + slot * Bb * H * m : e.u;
+    if (e.host) {   // outputs the caller did not ask for are not produced at all (nullable, kernels_round.cu)
+      t.out_x = e.xo ? s->sox + slot * Bb * N * n : nullptr; t.out_u = e.uo ? s->sou + slot * Bb * H * m : nullptr;
+      t.out_cost = e.cost ? s->scost + slot * Bb : nullptr; t.out_iters = e.iters ? s->siters + slot * Bb : nullptr;
+      t.out_status = e.status ? s->sstatus + slot * Bb : nullptr;
     } else {
-      t.in_x = e.x; t.in_u = e.u; t.out_x = e.xo; t.out_u = e.uo; t.out_cost = e.cost; t.out_iters = e.iters; t.out_status = e.status;
+      t.out_x = e.xo; t.out_u = e.uo; t.out_cost = e.cost; t.out_iters = e.iters; t.out_status = e.status;
     }
     if (int32_t rc = round_set_batch(h, (int)slot, t)) return rc;
     e.avail_group = h->round_groups;
@@ -349,7 +372,7 @@ int32_t ilqr_streamer_destroy(ilqr_streamer* s) {
   s->cv_work.notify_all();
   if (s->worker.joinable()) s->worker.join();
   cudaSetDevice(s->h->device);
-  cudaFree(s->sx); cudaFree(s->su); cudaFree(s->sox); cudaFree(s->sou); cudaFree(s->scost); cudaFree(s->siters); cudaFree(s->sstatus);
+  cudaFree(s->sx); cudaFree(s->su); cudaFree(s->sx0); cudaFree(s->sox); cudaFree(s->sou); cudaFree(s->scost); cudaFree(s->siters); cudaFree(s->sstatus);
   for (auto& e : s->ring) { if (e.ev_in) cudaEventDestroy(e.ev_in); if (e.ev_out) cudaEventDestroy(e.ev_out); }
   if (s->cs_in) cudaStreamDestroy(s->cs_in);
   if (s->cs_out) cudaStreamDestroy(s->cs_out);
@@ -360,9 +383,9 @@ int32_t ilqr_streamer_destroy(ilqr_streamer* s) {
 
 const char* ilqr_streamer_last_error(const ilqr_streamer* s) { return s ? s->err.c_str() : g_streamer_err.c_str(); }
 
-static int64_t streamer_submit(ilqr_streamer* s, bool host, const double* x, const double* u, double* xo, double* uo,
+static int64_t streamer_submit(ilqr_streamer* s, bool host, bool x0mode, const double* x, const double* u, double* xo, double* uo,
                                double* cost, int32_t* iters, int32_t* status) {
-  if (!s || !x || !u || !xo || !uo) return ILQR_ERR_INVALID;
+  if (!s || !x || (!u && !x0mode)) return ILQR_ERR_INVALID;   // every output is nullable
   int64_t seq;
   {
     std::unique_lock<std::mutex> lk(s->mu);
@@ -373,7 +396,7 @@ static int64_t streamer_submit(ilqr_streamer* s, bool host, const double* x, con
     seq = s->submitted;
     ilqr_streamer::Entry& e = s->ring[slot];
     e.x = x; e.u = u; e.xo = xo; e.uo = uo; e.cost = cost; e.iters = iters; e.status = status;
-    e.host = host; e.busy = true; e.stage = 0; e.seq = seq;
+    e.host = host; e.x0mode = x0mode; e.busy = true; e.stage = 0; e.seq = seq;
     s->done_flags.push_back(0);
     ++s->submitted;
   }
@@ -383,12 +406,22 @@ static int64_t streamer_submit(ilqr_streamer* s, bool host, const double* x, con
 
 int64_t ilqr_streamer_submit(ilqr_streamer* s, const double* x_init, const double* u_init, double* x_out, double* u_out,
                              double* cost_out, int32_t* iters_out, int32_t* status_out) {
-  return streamer_submit(s, true, x_init, u_init, x_out, u_out, cost_out, iters_out, status_out);
+  return streamer_submit(s, true, false, x_init, u_init, x_out, u_out, cost_out, iters_out, status_out);
 }
 
 int64_t ilqr_streamer_submit_device(ilqr_streamer* s, const double* d_x_init, const double* d_u_init, double* d_x_out,
                                     double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out) {
-  return streamer_submit(s, false, d_x_init, d_u_init, d_x_out, d_u_out, d_cost_out, d_iters_out, d_status_out);
+  return streamer_submit(s, false, false, d_x_init, d_u_init, d_x_out, d_u_out, d_cost_out, d_iters_out, d_status_out);
+}
+
+int64_t ilqr_streamer_submit_x0(ilqr_streamer* s, const double* x0, const double* u_init, double* x_out, double* u_out,
+                                double* cost_out, int32_t* iters_out, int32_t* status_out) {
+  return streamer_submit(s, true, true, x0, u_init, x_out, u_out, cost_out, iters_out, status_out);
+}
+
+int64_t ilqr_streamer_submit_x0_device(ilqr_streamer* s, const double* d_x0, const double* d_u_init, double* d_x_out,
+                                       double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out) {
+  return streamer_submit(s, false, true, d_x0, d_u_init, d_x_out, d_u_out, d_cost_out, d_iters_out, d_status_out);
 }
 
 int32_t ilqr_streamer_wait(ilqr_streamer* s, int64_t ticket) {

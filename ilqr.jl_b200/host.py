@@ -471,19 +471,48 @@ class Streamer:
         except Exception:
             pass
 
-    def submit_ptrs(self, x, u, xo, uo, cost=None, iters=None, status=None, device=False):
+    def submit_ptrs(self, x, u, xo=None, uo=None, cost=None, iters=None, status=None, device=False, x0=False):
         """Raw addresses (ints) of boundary-layout arrays of batch_size trajectories: host pointers, or device pointers
-        with device=True.  Returns a ticket."""
-        fn = self._lib.ilqr_streamer_submit_device if device else self._lib.ilqr_streamer_submit
+        with device=True.  x0=True: `x` is x0[n,Bb] and x_init is rolled out on the device (`u` may be None = zeros).
+        Every output is optional (None = not produced, not copied back).  Returns a ticket."""
+        fn = {(False, False): self._lib.ilqr_streamer_submit, (True, False): self._lib.ilqr_streamer_submit_device,
+              (False, True): self._lib.ilqr_streamer_submit_x0, (True, True): self._lib.ilqr_streamer_submit_x0_device}[(bool(device), bool(x0))]
         t = fn(self._p, x, u, xo, uo, cost, iters, status)
         if t < 0:
             raise IlqrError("ilqr_streamer_submit failed (%d): %s" % (t, self._lib.ilqr_streamer_last_error(self._p).decode()))
         return t
 
+    def _check(self, a, lead, dtype, name):
+        """The C ABI takes raw pointers: a wrong dtype, a C-ordered slice or a wrong shape would be misread silently."""
+        if a is None:
+            return None
+        if not isinstance(a, np.ndarray) or a.dtype != dtype:
+            raise TypeError("%s: expected a NumPy array of %s" % (name, np.dtype(dtype)))
+        shape = tuple(lead) + (self.batch_size,)
+        if a.shape != shape:
+            raise ValueError("%s: expected shape %s, got %s" % (name, shape, a.shape))
+        if not a.flags.f_contiguous:
+            raise ValueError("%s: expected a Fortran-ordered (Julia column-major) contiguous array; use np.asfortranarray" % name)
+        return a.ctypes.data
+
+    def _outs(self, out):
+        p = self.problem
+        return (self._check(out.get("x"), (p.H + 1, p.n), np.float64, "out['x']"), self._check(out.get("u"), (p.H, p.m), np.float64, "out['u']"),
+                self._check(out.get("cost"), (), np.float64, "out['cost']"), self._check(out.get("iters"), (), np.int32, "out['iters']"),
+                self._check(out.get("status"), (), np.int32, "out['status']"))
+
     def submit(self, x_init, u_init, out):
-        """NumPy (Fortran-ordered, boundary layout) in, preallocated `out` dict (x, u, cost, iters, status) filled on wait."""
-        return self.submit_ptrs(x_init.ctypes.data, u_init.ctypes.data, out["x"].ctypes.data, out["u"].ctypes.data,
-                                out["cost"].ctypes.data, out["iters"].ctypes.data, out["status"].ctypes.data)
+        """NumPy (Fortran-ordered, boundary layout) in, preallocated `out` dict (any of x, u, cost, iters, status) filled on wait."""
+        p = self.problem
+        return self.submit_ptrs(self._check(x_init, (p.H + 1, p.n), np.float64, "x_init"), self._check(u_init, (p.H, p.m), np.float64, "u_init"),
+                                *self._outs(out))
+
+    def submit_x0(self, x0, u_init, out):
+        """x0[n,Bb] (+ u_init[H,m,Bb] or None = zeros): x_init is the open-loop rollout, computed on the device
+        (animate_2_link.jl:11-16).  `out` as in submit()."""
+        p = self.problem
+        return self.submit_ptrs(self._check(x0, (p.n,), np.float64, "x0"), self._check(u_init, (p.H, p.m), np.float64, "u_init"),
+                                *self._outs(out), x0=True)
 
     def wait(self, ticket):
         rc = self._lib.ilqr_streamer_wait(self._p, ticket)
@@ -563,7 +592,13 @@ def fit(x_init, u_init, problem, x_traj=None, max_iter=100, tol=1e-6, info=None)
     B, single = _batch_of(x)
     with BatchSolver(_problem_for(problem, M, B)) as s:
         out = s.solve(x, u, x_traj, max_iter=max_iter, tol=tol)
-    assert not np.any(out["status"] & _abi.STATUS_NOT_DECREASED)   # src/forward_pass.jl:168
+    st = out["status"]
+    assert not np.any(st & _abi.STATUS_NOT_DECREASED)   # src/forward_pass.jl:168
+    assert not np.any(st & _abi.STATUS_NAN_GAINS)       # src/backward_pass.jl:353-354
+    assert not np.any(st & _abi.STATUS_NAN_ROLLOUT)     # src/forward_pass.jl:89-90
+    if np.any(st & _abi.STATUS_LS_EXHAUSTED):
+        raise IlqrError("line search exhausted n_alpha candidates on %d trajectories (reference: infinite loop, "
+                        "src/forward_pass.jl:70)" % int(np.count_nonzero(st & _abi.STATUS_LS_EXHAUSTED)))
     if info is not None:
         info.update(cost=out["cost"], iters=out["iters"], status=out["status"])
     return (out["x"][..., 0], out["u"][..., 0]) if single else (out["x"], out["u"])

@@ -304,12 +304,23 @@ int32_t ilqr_streamer_create(const ilqr_problem* p, int32_t batch_size, int32_t 
                              ilqr_streamer** out);
 int32_t ilqr_streamer_destroy(ilqr_streamer* s);
 const char* ilqr_streamer_last_error(const ilqr_streamer* s);
-/* host pointers (pinned for full-speed copies), boundary layout; cost/iters/status nullable; returns a ticket >= 0 */
+/* host pointers (pinned for full-speed copies), boundary layout; returns a ticket >= 0.  EVERY output pointer is
+ * nullable: an output the caller does not ask for is neither produced by the kernels nor copied back (a caller that
+ * needs only ū halves the device-to-host traffic by passing x_out = NULL). */
 int64_t ilqr_streamer_submit(ilqr_streamer* s, const double* x_init, const double* u_init, double* x_out, double* u_out,
                              double* cost_out, int32_t* iters_out, int32_t* status_out);
 /* device pointers: read and written by the kernels directly, no staging copy */
 int64_t ilqr_streamer_submit_device(ilqr_streamer* s, const double* d_x_init, const double* d_u_init, double* d_x_out,
                                     double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out);
+/* Problem setup on device, as the reference's own scripts build their inputs (test/2_link_example/animate_2_link.jl:11-16:
+ * x_init = open-loop rollout of u_init from x0): x0[n,Bb] and u_init[H,m,Bb] (NULL = zeros, the reference's initial
+ * guess) are all that crosses the bus — 2 MB instead of 631 MB per 65,536-trajectory batch at config 2 with u_init = NULL.
+ * The rollout runs on the copy stream with the same dynamics step as every other path, so the results are bit-identical
+ * to ilqr_streamer_submit on ilqr_upload_x0's x_init.  Outputs as above (all nullable). */
+int64_t ilqr_streamer_submit_x0(ilqr_streamer* s, const double* x0, const double* u_init, double* x_out, double* u_out,
+                                double* cost_out, int32_t* iters_out, int32_t* status_out);
+int64_t ilqr_streamer_submit_x0_device(ilqr_streamer* s, const double* d_x0, const double* d_u_init, double* d_x_out,
+                                       double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out);
 int32_t ilqr_streamer_wait(ilqr_streamer* s, int64_t ticket);
 int32_t ilqr_streamer_wait_all(ilqr_streamer* s);
 int64_t ilqr_streamer_launch_count(const ilqr_streamer* s);   /* kernels launched so far */

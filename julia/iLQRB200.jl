@@ -88,6 +88,48 @@ upload!(s::Solver, x::Array{Float64,3}, u::Array{Float64,3}, x_traj = nothing) =
     check(ccall((:ilqr_upload, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 s.h, x, u, x_traj === nothing ? C_NULL : x_traj), s.h)
 
+"""
+Problem-setup helper (animate_2_link.jl:11-16): `x_init` = open-loop rollout of `u_init` from `x0[n,B]`, on the device.
+"""
+upload_x0!(s::Solver, x0::Matrix{Float64}, u::Array{Float64,3}, x_traj = nothing) =
+    check(ccall((:ilqr_upload_x0, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                s.h, x0, u, x_traj === nothing ? C_NULL : x_traj), s.h)
+
+"Gains computed elsewhere (δuff[H,m,B], K[H,m,n,B]) for `forward_pass` with the reference's own argument list."
+upload_gains!(s::Solver, duff::Array{Float64,3}, K::Array{Float64,4}) =
+    check(ccall((:ilqr_upload_gains, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), s.h, duff, K), s.h)
+
+# ---- host-owned regularisation and convergence control (north_star: Julia owns both) ----------------------------
+"The constant added to diag(H) before the gain solve (src/backward_pass.jl:214 hard-codes 0.01); from the next backward pass on."
+set_reg!(s::Solver, reg::Float64) = check(ccall((:ilqr_set_reg, lib), Int32, (Ptr{Cvoid}, Float64), s.h, reg), s.h)
+
+"Trajectories whose mask entry is 0 stop iterating (they keep their current iterate): the host's own convergence test."
+set_active!(s::Solver, active::Vector{Int32}) =
+    check(ccall((:ilqr_set_active, lib), Int32, (Ptr{Cvoid}, Ptr{Int32}), s.h, active), s.h)
+
+"The tail of fit's loop body on the device (src/forward_pass.jl:168-175) → number of trajectories still iterating."
+function commit!(s::Solver, tol::Float64)
+    n_active = Ref{Int32}(0)
+    check(ccall((:ilqr_commit, lib), Int32, (Ptr{Cvoid}, Float64, Ptr{Int32}), s.h, tol, n_active), s.h)
+    return n_active[]
+end
+
+"backward + forward + commit in one call → number of trajectories still iterating."
+function iterate!(s::Solver, tol::Float64)
+    n_active = Ref{Int32}(0)
+    check(ccall((:ilqr_iterate, lib), Int32, (Ptr{Cvoid}, Float64, Ptr{Int32}), s.h, tol, n_active), s.h)
+    return n_active[]
+end
+
+"`ilqr_fit`: the whole loop on the library's side (per-trajectory convergence) → batch iterations executed."
+function fit!(s::Solver; max_iter::Integer = 100, tol::Float64 = 1e-6)
+    iters = Ref{Int32}(0)
+    check(ccall((:ilqr_fit, lib), Int32, (Ptr{Cvoid}, Int32, Float64, Ptr{Int32}), s.h, max_iter, tol, iters), s.h)
+    return iters[]
+end
+
+sync(s::Solver) = check(ccall((:ilqr_sync, lib), Int32, (Ptr{Cvoid},), s.h), s.h)
+
 function download(s::Solver, which::Int32, dims...; T = Float64)
     out = Array{T}(undef, dims...)
     check(ccall((:ilqr_download, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), s.h, which, out), s.h)
@@ -190,6 +232,93 @@ function submit!(s::Streamer, x_init::Array{Float64,3}, u_init::Array{Float64,3}
     t >= 0 || error("ilqr_streamer_submit failed ($t)")
     t
 end
+"""
+`x0[n,batch_size]` (+ `u_init` or `nothing` = zeros): `x_init` is rolled out on the device (animate_2_link.jl:11-16), so only
+x0 crosses the bus.  Any output may be `nothing` (not produced, not copied back).
+"""
+function submit_x0!(s::Streamer, x0::Matrix{Float64}, u_init, x_out, u_out, cost, iters, status)
+    @assert size(x0, 2) == s.batch_size "every submitted batch has batch_size trajectories"
+    nul(a) = a === nothing ? C_NULL : pointer(a)
+    t = GC.@preserve x0 u_init x_out u_out cost iters status ccall((:ilqr_streamer_submit_x0, lib), Int64,
+              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+              s.h, x0, nul(u_init), nul(x_out), nul(u_out), nul(cost), nul(iters), nul(status))
+    t >= 0 || error("ilqr_streamer_submit_x0 failed ($t)")
+    t
+end
+"Device-pointer forms (CUDA.jl `CuPtr`s converted to `Ptr{Float64}` by the caller): read and written by the kernels directly."
+submit_device!(s::Streamer, d_x::Ptr{Float64}, d_u::Ptr{Float64}, d_xo::Ptr{Float64}, d_uo::Ptr{Float64},
+               d_cost::Ptr{Float64}, d_iters::Ptr{Int32}, d_status::Ptr{Int32}) =
+    ccall((:ilqr_streamer_submit_device, lib), Int64,
+          (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+          s.h, d_x, d_u, d_xo, d_uo, d_cost, d_iters, d_status)
+submit_x0_device!(s::Streamer, d_x0::Ptr{Float64}, d_u::Ptr{Float64}, d_xo::Ptr{Float64}, d_uo::Ptr{Float64},
+                  d_cost::Ptr{Float64}, d_iters::Ptr{Int32}, d_status::Ptr{Int32}) =
+    ccall((:ilqr_streamer_submit_x0_device, lib), Int64,
+          (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+          s.h, d_x0, d_u, d_xo, d_uo, d_cost, d_iters, d_status)
+wait_all(s::Streamer) = ccall((:ilqr_streamer_wait_all, lib), Int32, (Ptr{Cvoid},), s.h) == 0 ||
+    error(unsafe_string(ccall((:ilqr_streamer_last_error, lib), Cstring, (Ptr{Cvoid},), s.h)))
+rounds(s::Streamer) = ccall((:ilqr_streamer_rounds, lib), Int64, (Ptr{Cvoid},), s.h)
+
+"""
+`ilqr_stream_solve_device`: `n_total` trajectories resident in HBM (device pointers, boundary layout) streamed through the
+solver's `p.B` slots; per-trajectory `fit` semantics.  Returns the number of batch iterations (launches of a whole iteration).
+"""
+function stream_solve_device(s::Solver, n_total::Integer, d_x::Ptr{Float64}, d_u::Ptr{Float64}, d_xo::Ptr{Float64}, d_uo::Ptr{Float64},
+                             d_cost::Ptr{Float64}, d_iters::Ptr{Int32}, d_status::Ptr{Int32}; max_iter::Integer = 100, tol::Float64 = 1e-6)
+    its = Ref{Int64}(0)
+    check(ccall((:ilqr_stream_solve_device, lib), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32},
+                 Ptr{Int32}, Ptr{Int64}),
+                s.h, n_total, d_x, d_u, max_iter, tol, d_xo, d_uo, d_cost, d_iters, d_status, its), s.h)
+    return its[]
+end
+
+"""
+Batch scheduler (`ilqr_pool_*`): `n_handles` batches in flight on one GPU, each solved exactly as `solve` would.
+`submit!` returns a ticket; keep the arrays alive until `wait(pool, ticket)`.
+"""
+mutable struct Pool
+    h::Ptr{Cvoid}
+    function Pool(p::Problem, n_handles::Integer)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:ilqr_pool_create, lib), Int32, (Ref{Problem}, Int32, Ptr{Ptr{Cvoid}}), p, n_handles, h)
+        rc == 0 || error("ilqr_pool_create: " * unsafe_string(ccall((:ilqr_pool_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+        s = new(h[])
+        finalizer(x -> ccall((:ilqr_pool_destroy, lib), Int32, (Ptr{Cvoid},), x.h), s)
+        s
+    end
+end
+function submit!(pool::Pool, x_init::Array{Float64,3}, u_init::Array{Float64,3}, x_out::Array{Float64,3}, u_out::Array{Float64,3},
+                 cost::Vector{Float64}, iters::Vector{Int32}, status::Vector{Int32}; x_traj = nothing, max_iter::Integer = 100,
+                 tol::Float64 = 1e-6)
+    t = ccall((:ilqr_pool_submit, lib), Int64,
+              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+               Ptr{Int32}, Ptr{Int32}),
+              pool.h, x_init, u_init, x_traj === nothing ? C_NULL : x_traj, max_iter, tol, x_out, u_out, cost, iters, status)
+    t >= 0 || error("ilqr_pool_submit failed ($t)")
+    t
+end
+submit_device!(pool::Pool, d_x::Ptr{Float64}, d_u::Ptr{Float64}, d_xt::Ptr{Float64}, d_xo::Ptr{Float64}, d_uo::Ptr{Float64},
+               d_cost::Ptr{Float64}, d_iters::Ptr{Int32}, d_status::Ptr{Int32}; max_iter::Integer = 100, tol::Float64 = 1e-6) =
+    ccall((:ilqr_pool_submit_device, lib), Int64,
+          (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+           Ptr{Int32}, Ptr{Int32}),
+          pool.h, d_x, d_u, d_xt, max_iter, tol, d_xo, d_uo, d_cost, d_iters, d_status)
+Base.wait(pool::Pool, ticket::Int64) =
+    ccall((:ilqr_pool_wait, lib), Int32, (Ptr{Cvoid}, Int64), pool.h, ticket) == 0 ||
+    error(unsafe_string(ccall((:ilqr_pool_last_error, lib), Cstring, (Ptr{Cvoid},), pool.h)))
+wait_all(pool::Pool) = ccall((:ilqr_pool_wait_all, lib), Int32, (Ptr{Cvoid},), pool.h) == 0 ||
+    error(unsafe_string(ccall((:ilqr_pool_last_error, lib), Cstring, (Ptr{Cvoid},), pool.h)))
+
+"Page-locked host arrays for full-speed PCIe copies (`ilqr_host_alloc`); release with `host_free`."
+function host_alloc(::Type{T}, dims...) where {T}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    ccall((:ilqr_host_alloc, lib), Int32, (Ptr{Ptr{Cvoid}}, UInt64), p, sizeof(T) * prod(dims)) == 0 || error("ilqr_host_alloc")
+    return unsafe_wrap(Array, Ptr{T}(p[]), dims)
+end
+host_free(a::Array) = ccall((:ilqr_host_free, lib), Int32, (Ptr{Cvoid},), a)
+
 Base.wait(s::Streamer, ticket::Int64) =
     ccall((:ilqr_streamer_wait, lib), Int32, (Ptr{Cvoid}, Int64), s.h, ticket) == 0 ||
     error(unsafe_string(ccall((:ilqr_streamer_last_error, lib), Cstring, (Ptr{Cvoid},), s.h)))

@@ -244,6 +244,8 @@ def test_pool_scheduler_equals_single_handle():
         tickets = [pool.submit(x, u, o, max_iter=50) for (x, u), o in zip(batches, outs)]
         for t in reversed(tickets):
             pool.wait(t)
+        pool.wait_all()
+        pool.wait(tickets[0]); pool.wait(tickets[-1])       # waiting again (also after wait_all) returns at once
         assert pool.launch_count() > 0
     for r, o in zip(ref, outs):
         for k in ("x", "u", "cost", "iters", "status"):
@@ -483,3 +485,89 @@ def test_full_size_solve_paths_agree_bit_for_bit():
     for o in pouts:
         assert torch.equal(o[3], ri), int((o[3] != ri).sum())
         assert torch.equal(o[0], rx) and torch.equal(o[1], ru)
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_streamer_submit_x0_and_optional_outputs(device):
+    """ilqr_streamer_submit_x0[_device]: only x0 (and optionally u_init) crosses the bus, x_init is rolled out on the
+    device (animate_2_link.jl:11-16).  Results must be bit-identical to ilqr_streamer_submit on the x_init that
+    ilqr_upload_x0 produces; outputs that are not asked for (NULL) are left untouched."""
+    import torch
+    H, Bb, nb, slots, max_iter = 60, 80, 4, 96, 30
+    rng = np.random.default_rng(5)
+    x0 = np.asfortranarray(rng.random((4, nb * Bb)))
+    uz = np.zeros((H, 2, nb * Bb), order="F")
+    ur = np.asfortranarray(0.2 * rng.normal(size=(H, 2, nb * Bb)))
+    refs = []
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, Bb)) as s:
+        for b in range(nb):
+            sl = slice(b * Bb, (b + 1) * Bb)
+            u = ur if b % 2 else uz
+            s.upload_x0(np.asfortranarray(x0[:, sl]), np.asfortranarray(u[:, :, sl]))
+            xin = s.download(_abi.X)
+            refs.append(s.solve(xin, np.asfortranarray(u[:, :, sl]), max_iter=max_iter, tol=1e-6))
+
+    def mk(t):
+        return t.cuda() if device else t.pin_memory()
+
+    def ptr(t):
+        return None if t is None else t.data_ptr()
+
+    ins, outs = [], []
+    for b in range(nb):
+        sl = slice(b * Bb, (b + 1) * Bb)
+        bx0 = mk(torch.from_numpy(np.ascontiguousarray(x0[:, sl].T)))                       # [Bb][n] == Fortran [n,Bb]
+        bu = mk(torch.from_numpy(np.ascontiguousarray(ur[:, :, sl].transpose(2, 1, 0)))) if b % 2 else None
+        o = [mk(torch.full((Bb, 4, H + 1), -7.0, dtype=torch.float64)), mk(torch.zeros((Bb, 2, H), dtype=torch.float64)),
+             mk(torch.zeros(Bb, dtype=torch.float64)), mk(torch.zeros(Bb, dtype=torch.int32)), mk(torch.zeros(Bb, dtype=torch.int32))]
+        ins.append((bx0, bu)); outs.append(o)
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, slots), Bb, ring=2, max_iter=max_iter, tol=1e-6) as st:
+        tickets = []
+        for b in range(nb):
+            o = outs[b]
+            # batch 2: x_out = NULL (ū only), batch 3: only the scalars
+            xo = None if b >= 2 else o[0]
+            uo = None if b == 3 else o[1]
+            tickets.append(st.submit_ptrs(ins[b][0].data_ptr(), ptr(ins[b][1]), ptr(xo), ptr(uo), o[2].data_ptr(), o[3].data_ptr(),
+                                          o[4].data_ptr(), device=device, x0=True))
+        for t in tickets:
+            st.wait(t)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        ox, ou, oc, oi, os_ = [t.cpu().numpy() for t in outs[b]]
+        assert np.array_equal(oi, refs[b]["iters"]), b
+        assert np.array_equal(os_, refs[b]["status"]), b
+        assert np.array_equal(oc, refs[b]["cost"]), b
+        if b < 2:
+            assert np.array_equal(ox.transpose(2, 1, 0), refs[b]["x"]), b
+        else:
+            assert np.all(ox == -7.0)
+        if b < 3:
+            assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b
+        else:
+            assert not ou.any()
+
+
+def test_forward_pass_twice_without_commit_large_batch():
+    """Two forward passes in a row on a batch large enough for the two-kernel forward pass (α = 1 for all, dense retry
+    kernel for the rejected slots; nslots > fwd_split_above): the retry list of the first pass must not leak into the
+    second one.  Compared with the one-kernel forward pass on the same gains, bit for bit."""
+    B, H = 24576, 30
+    x0 = np.random.default_rng(3).uniform(-3.1, 3.1, (4, B)); x0[2:] *= 2.5
+    x0 = np.asfortranarray(x0)
+    u = np.zeros((H, 2, B), order="F")
+    res = []
+    for split_above in (0, 1 << 30):
+        with _solver(H, B) as s:
+            s.set_tuning(fwd_split_above=split_above)
+            s.upload_x0(x0, u)
+            s.backward_pass(); s.forward_pass()
+            prev = s.download(_abi.NEW_COST) * (1 - 1e-7)      # a hair below the accepted candidate's cost: that step size is
+            s.forward_pass(prev)                                 # now rejected and the trajectory must halve α further
+            first = (s.download(_abi.ALPHA), s.download(_abi.NEW_COST))
+            s.forward_pass(prev)                                 # again, no commit in between
+            res.append(first + (s.download(_abi.ALPHA), s.download(_abi.NEW_COST), s.download(_abi.XBAR), s.download(_abi.UBAR)))
+    assert np.sum(res[0][0] < 1.0) > 100
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(res[0][0], res[0][2]) and np.array_equal(res[0][1], res[0][3], equal_nan=True)
