@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "iLQR solves/sec (batched 2-link arm, H=200)"
+NCU_ROUND_FILE = "ncu_full_r1_round.txt"     # tools/ncu_summary.py of one full-width launch of the round kernel (profiles/)
 UNIT = "solves/s"
 H, B_PER_GPU, MAX_ITER, TOL = 200, 65536, 100, 1e-6
 N_, M_ = 4, 2
@@ -77,29 +78,73 @@ def cpu_inputs(x0):
     return x, u
 
 
-def cpu_solves_per_sec(x0, threads):
+def cpu_solves_per_sec(x0, threads, xu=None, traces=False):
     from oracle import oracle_py as orc
-    x, u = cpu_inputs(x0)
+    x, u = xu if xu is not None else cpu_inputs(x0)
     t0 = time.perf_counter()
-    res = orc.fit_batch(x, u, max_iter=MAX_ITER, tol=TOL, nthreads=threads, traces=False)
+    res = orc.fit_batch(x, u, max_iter=MAX_ITER, tol=TOL, nthreads=threads, traces=traces)
     dt = time.perf_counter() - t0
-    return x0.shape[0] / dt, dt, res
+    return x.shape[2] / dt, dt, res
 
 
-def cpu_baseline(target_seconds):
+def cpu_baseline(target_seconds, x_init=None):
     """The oracle (CPU restatement of the reference; Julia itself is not installable here) on all host cores,
-    on a bounded sample of the same workload."""
+    on a bounded sample of the same workload.  x_init (optional, [N,n,B] Fortran): the very arrays the GPU arm solved,
+    so that the oracle's results for the sample can be compared with the GPU's (parity_report)."""
     cores = os.cpu_count() or 1
     x0 = make_x0(B_PER_GPU, 0)
+
+    def xu(lo, hi):
+        if x_init is None:
+            return None
+        return np.asfortranarray(x_init[:, :, lo:hi]), np.zeros((H, M_, hi - lo), order="F")
+
     probe = max(cores * 4, 32)
-    rate, dt, _ = cpu_solves_per_sec(x0[:probe], cores)
+    rate, dt, _ = cpu_solves_per_sec(x0[:probe], cores, xu(0, probe))
     sample = int(min(B_PER_GPU, max(probe, rate * target_seconds)))
-    rate, dt, res = cpu_solves_per_sec(x0[:sample], cores)
-    rate1, dt1, _ = cpu_solves_per_sec(x0[: max(8, min(sample, int(rate / cores * 4) + 8))], 1)
+    rate, dt, res = cpu_solves_per_sec(x0[:sample], cores, xu(0, sample), traces=True)
+    n1 = max(8, min(sample, int(rate / cores * 4) + 8))
+    rate1, dt1, _ = cpu_solves_per_sec(x0[:n1], 1, xu(0, n1))
     return dict(value=rate, unit=UNIT, cores=cores, kind="port",
                 sample="first %d of the 65,536 config-2 trajectories (rank-0 seed), %.1f s wall, mean %.1f iterations"
                        % (sample, dt, float(res["iters"].mean())),
-                single_thread_value=rate1)
+                single_thread_value=rate1), res, sample
+
+
+def parity_report(ref, n, gpu, traced):
+    """Oracle results for the first n trajectories of the timed batch against what the measured path (the streamer)
+    returned for the same trajectories.  Branch decisions (iteration counts, convergence flags, accepted step sizes)
+    are counted separately from value errors: a flipped decision is a different trajectory, not a rounding
+    error.  `traced` = the same trajectories through the batch path with per-iteration traces (the streamer keeps none);
+    the batch path must equal the streamer bit for bit."""
+    it_g, it_r = gpu["iters"][:n], ref["iters"][:n]
+    conv_g = (gpu["status"][:n] & 16) != 0
+    same = it_g == it_r
+
+    def rel(a, b):   # per trajectory, max-norm relative
+        ax = tuple(range(a.ndim - 1))
+        return np.max(np.abs(a - b), axis=ax) / np.maximum(np.max(np.abs(b), axis=ax), 1e-300)
+
+    ex, eu = rel(gpu["x"][..., :n], ref["x"][..., :n]), rel(gpu["u"][..., :n], ref["u"][..., :n])
+    last = ref["cost"][np.maximum(it_r, 1) - 1, np.arange(n)]
+    ec = np.abs(gpu["cost"][:n] - last) / np.abs(last)
+    out = {"n": int(n), "against": "oracle (CPU restatement of iLQR.jl; the reference ships no golden vectors and Julia is absent: parity unpinned)",
+           "iters_mismatch": int(np.sum(~same)), "converged_flag_mismatch": int(np.sum(conv_g != ref["converged"][:n])),
+           "max_rel_x": float(ex[same].max()), "max_rel_u": float(eu[same].max()), "max_rel_cost": float(ec[same].max()),
+           "tolerance": {"x_u_per_iterate_cost": 1e-9, "converged_cost": 1e-8},
+           "within_tolerance": bool(np.all(same) and ex.max() < 1e-9 and eu.max() < 1e-9 and ec.max() < 1e-8)}
+    if traced is not None:
+        at, ct = traced["alpha_trace"], traced["cost_trace"]
+        am = 0; worst = 0.0; du2_flips = 0
+        for b in range(n):
+            k = min(int(it_g[b]), int(it_r[b]))
+            am += int(np.sum(at[:k, b] != ref["alpha"][:k, b]))
+            if k:
+                worst = max(worst, float(np.max(np.abs(ct[:k, b] - ref["cost"][:k, b]) / np.abs(ref["cost"][:k, b]))))
+        out.update(alpha_mismatch=am, alpha_decisions=int(np.sum(np.minimum(it_g, it_r))), max_rel_cost_per_iterate=worst,
+                   line_search_halvings_in_sample=int(np.nansum(ref["alpha"][:, :n] < 1.0)),
+                   batch_path_equals_streamer_bitwise=bool(traced["bitwise"]))
+    return out
 
 
 def run_reference(args):
@@ -158,29 +203,41 @@ def chain_config(batch, device=0):
     return joints, target, w, prob, x0, np.zeros((HC, NQ, batch), order="F")
 
 
-def aux_chain(device, cpu_too):
-    """BASELINE configs[3] on one GPU: 7-DoF serial chain, n = 14, m = 7, H = 100, B = 262,144, fp64 —
-    one batched fit (tol 1e-6, max_iter 100) with the kernel times of its first (full-width) iteration."""
+def aux_chain(device, cpu_too, rank=0, world=1, dist=None):
+    """BASELINE configs[3]: 7-DoF serial chain, n = 14, m = 7, H = 100, B = 262,144 trajectories IN TOTAL, fp64 — "sharded
+    across 2/4/8 B200" (north_star): every rank solves a contiguous slice of the same batch (strong scaling), one batched
+    fit (tol 1e-6, max_iter 100); time = max over ranks.  Kernel times are those of the first (full-width) iteration."""
     import ilqr_b200
     from ilqr_b200 import _abi
+    from ilqr_b200.sharding import shard_range
     Bc = 262144
+    lo, hi = shard_range(Bc, rank, world)
     joints, target, w, prob, x0, u = chain_config(Bc, device)
+    prob.B = hi - lo
+    x0 = np.asfortranarray(x0[:, lo:hi]); u = np.asfortranarray(u[:, :, lo:hi])
     with ilqr_b200.BatchSolver(prob) as s:
         s.upload_x0(x0, u)
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter(); s.fit(MAX_ITER, TOL); dt = time.perf_counter() - t0
         prof = s.profile()
         it, st = s.download(_abi.ITERS), s.download(_abi.STATUS)
-    # FP64-pipe roofline of the dominant kernel: 13.6 k DFMA-class warp instructions per trajectory-step
-    # (profiles/ncu_full_r1_chain_B2368.txt: pipe-active share × cycles), one warp per trajectory ⇒ 32 lanes issue them
-    fp64_instr = 13600
-    tf = 2.0 * fp64_instr * 32 * 100 * Bc / (prof["first_bwd_ms"] * 1e-3) / 1e12
-    out = {"workload": "configs[3]: synthetic 7-DoF serial chain (n=14, m=7), B=262144, H=100, fp64, 1 GPU",
-           "value": Bc / dt, "unit": "solves/s", "fit_s": dt, "mean_iterations": float(it.mean()),
-           "converged_fraction": float(np.mean((st & 16) != 0)),
-           "bwd_chain_ms_full_batch": prof["first_bwd_ms"], "fwd_chain_ms_full_batch": prof["first_fwd_ms"],
-           "bwd_chain_issue_tflops_fp64": tf,
-           "note": "bwd_chain: FP64 pipe ~55 % active under ncu at 8 warps/SM (profiles/ncu_full_r1_chain_B2368.txt); "
-                   "issue_tflops counts all 32 lanes of the warp-per-trajectory mapping (30 carry work: 22 column owners + 8 riding lanes)"}
+    stats = np.array([dt, prof["first_bwd_ms"], prof["first_fwd_ms"]])
+    sums = np.array([float(it.sum()), float(np.sum((st & 16) != 0))])
+    if dist is not None:
+        import torch
+        t = torch.tensor(stats, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); stats = t.cpu().numpy()
+        t = torch.tensor(sums, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); sums = t.cpu().numpy()
+    dt, bwd_ms, fwd_ms = (float(v) for v in stats)
+    sass = (sass_counts() or {}).get("bwd_chain7")
+    out = {"workload": "configs[3]: synthetic 7-DoF serial chain (n=14, m=7), B=262144 in total, H=100, fp64, sharded over %d GPU(s) "
+                       "(%d trajectories per GPU)" % (world, hi - lo),
+           "value": Bc / dt, "unit": "solves/s", "n_gpus": world, "scaling": "strong", "fit_s": dt, "mean_iterations": sums[0] / Bc,
+           "converged_fraction": sums[1] / Bc,
+           "bwd_chain_ms_first_iteration": bwd_ms, "fwd_chain_ms_first_iteration": fwd_ms,
+           "bwd_chain_ms_full_batch": bwd_ms * (Bc / (hi - lo)),
+           "bwd_chain_static_fp64_instructions": sass["fp64"] if sass else None,
+           "note": "bwd_chain_ms_full_batch = first-iteration backward time scaled to 262,144 trajectories (= the measured time at 1 GPU)"}
     if cpu_too:
         from oracle import oracle_py as orc
         cores = os.cpu_count() or 1
@@ -193,6 +250,49 @@ def aux_chain(device, cpu_too):
         orc.chain_fit_batch(spec, xs, us, max_iter=MAX_ITER, tol=TOL, nthreads=cores, traces=False)
         out["cpu_baseline"] = {"value": nb / (time.perf_counter() - t0), "unit": "solves/s", "cores": cores, "kind": "port",
                                "sample": "first %d trajectories of the batch" % nb}
+    return out
+
+
+def aux_mpc(device, rank=0, world=1, dist=None, B_total=4096, steps=500, max_iter=3):
+    """BASELINE configs[4]: receding-horizon MPC — 4,096 closed-loop 2-link rollouts IN TOTAL sharded over the ranks, every
+    plant step: <= max_iter warm-started iLQR iterations, apply u[0] to the plant, shift (ilqr_mpc_step); 500 steps.
+    control-steps/s = B_total * steps / max-over-ranks wall time (each step returns its controls to the host)."""
+    import ilqr_b200
+    from ilqr_b200.sharding import shard_range
+    lo, hi = shard_range(B_total, rank, world)
+    x0 = np.asfortranarray(np.random.default_rng(5).random((B_total, 4))[lo:hi].T)
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, hi - lo, device=device)) as s:
+        s.mpc_start(x0)
+        for _ in range(5):
+            s.mpc_step(max_iter)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ua, xp = s.mpc_step(max_iter)
+        dt = time.perf_counter() - t0
+        theta_star = np.array(list(s.problem.x_target)[:2])
+        err = float(np.abs(xp[:2].T - theta_star).max())
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt, err], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, err = float(t[0]), float(t[1])
+    return {"workload": "configs[4]: MPC, %d closed-loop 2-link rollouts in total on %d GPU(s) (%d per GPU), H=200, <= %d warm-started "
+                        "iLQR iterations per plant step, %d plant steps" % (B_total, world, hi - lo, max_iter, steps),
+            "value": B_total * steps / dt, "unit": "control-steps/s", "ms_per_plant_step": 1e3 * dt / steps, "n_gpus": world,
+            "scaling": "strong", "max_joint_error_after_run": err}
+
+
+def aux_configs(rank, world, local, dist, cpu_too):
+    """Side measurements of the other BASELINE configs, behind the headline; every rank takes part (sharded configs)."""
+    out = {}
+    c3 = aux_chain(local, cpu_too, rank, world, dist)
+    c5 = aux_mpc(local, rank, world, dist)
+    if rank == 0:
+        out["configs[3]"] = c3
+        out["configs[4]"] = c5
+        if world == 1:
+            out["configs[2]"] = aux_floating(local)
     return out
 
 
@@ -222,6 +322,79 @@ def aux_floating(device):
             "value": prof["traj_iters"] / dt, "unit": "trajectory-iterations/s", "ms_per_batch_iteration": 1e3 * dt / iters,
             "bwd_chain_ms": prof["bwd_ms"] / max(1, prof["bwd_launches"]), "fwd_chain_ms": prof["fwd_ms"] / max(1, prof["fwd_launches"]),
             "mean_cost_after": float(np.mean(cost))}
+
+
+# --------------------------------------------------------------------------- roofline inputs (nothing hand-typed)
+def sass_counts():
+    """Static FP64 instruction mix of the hot kernels, counted from the SASS of the library that is loaded
+    (ilqr.jl_b200/_build.py::sass_mix, written at build time to build/sass_mix.json; counted on the fly if absent)."""
+    mix = None
+    try:
+        mix = json.load(open(os.path.join(ROOT, "build", "sass_mix.json")))
+    except Exception:
+        try:
+            from ilqr_b200 import _build
+            mix = _build.sass_mix()
+        except Exception:
+            return None
+
+    def pick(tag):
+        for k, v in mix.items():
+            if tag in k:
+                return v
+        return None
+    return {"round": pick("round_lpt_two_linkILi12ELi4"), "round16": pick("round_lpt_two_linkILi16"),
+            "bwd": pick("bwd_lpt_two_link"), "fwd": pick("fwd_lpt_two_linkILb0"), "bwd_chain7": pick("bwd_chainILi7ELb0")}
+
+
+def ncu_file_metrics(name, kernel_tag):
+    """dram bytes (read + write), duration and FP64-pipe share of one launch from a committed tools/ncu_summary.py
+    file under profiles/ (ncu --set full, one launch): {traffic, ms, fp64_pipe_pct, file} or None."""
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        blocks = open(path).read().split("-----")
+    except Exception:
+        return None
+    for b in blocks:
+        if kernel_tag not in b:
+            continue
+        val = {}
+        for line in b.splitlines():
+            t = line.split()
+            if len(t) >= 2:
+                val[t[0]] = t[1:]
+        try:
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            rd = float(val["dram__bytes_read.sum"][0]) * unit[val["dram__bytes_read.sum"][1]]
+            wr = float(val["dram__bytes_write.sum"][0]) * unit[val["dram__bytes_write.sum"][1]]
+            tu = {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}
+            ms = float(val["gpu__time_duration.sum"][0]) * tu[val["gpu__time_duration.sum"][1]]
+            pipe = float(val["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"][0])
+            return {"traffic": rd + wr, "ms": ms, "fp64_pipe_pct": pipe, "file": "profiles/" + name}
+        except Exception:
+            return None
+    return None
+
+
+def fp64_peak_inrun(device):
+    """tools/fp64_peak (DFMA micro-benchmark, built by __graft_entry__.build()) run on this GPU right before the timed
+    region: the FP64 roofline denominator MEASURED_PEAKS.json does not carry.  Falls back to the committed
+    profiles/fp64_peak.json (and says so)."""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    try:
+        env = dict(os.environ); env["CUDA_VISIBLE_DEVICES"] = str(device)
+        q = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=clocks.sm", "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=20).stdout.strip()
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env).stdout.strip().splitlines()[-1]
+        d = json.loads(out)
+        return {"tflops": d["fp64_dfma_tflops"], "source": "tools/fp64_peak.cu DFMA micro-benchmark run inside this bench on this GPU",
+                "lat_dfma_cycles": d.get("lat_dfma_cycles"), "sm_mhz_before": float(q) if q else None}
+    except Exception as e:
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+            return {"tflops": d["fp64_dfma_tflops"], "source": "profiles/fp64_peak.json (committed; in-run measurement failed: %r)" % (e,)}
+        except Exception:
+            return {"tflops": None, "source": "unavailable"}
 
 
 # --------------------------------------------------------------------------- clocks
@@ -320,10 +493,13 @@ def run_b200(args):
         pass
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
 
+    fp64_peak = fp64_peak_inrun(local) if rank == 0 else {"tflops": None, "source": "rank 0 only"}
     prob = ilqr_b200.two_link_problem(H, B, device=local)
     s = ilqr_b200.BatchSolver(prob)
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    SLOTS = n_sm * 12 * 32            # one block of 12 warps per SM (csrc/kernels_round.cu)
+    round_warps = int(os.environ.get("ILQR_ROUND_WARPS", "12"))
+    rounds_per_launch = int(os.environ.get("ILQR_ROUND_MULTI", "1"))
+    SLOTS = n_sm * round_warps * 32   # one block of 12 (or 16) warps per SM (csrc/kernels_round.cu)
     RING = args.ring
     streamer = ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, SLOTS, device=local), B, ring=RING, max_iter=MAX_ITER, tol=TOL)
 
@@ -434,14 +610,20 @@ def run_b200(args):
     iso_ms = max_over_ranks(e0.elapsed_time(e1)) / iso_steps
 
     full_iter_ms = (prof_acc["first_bwd_ms"] + prof_acc["first_fwd_ms"]) / iso_steps
-    fp64_peak_tf = None
-    try:
-        fp64_peak_tf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_dfma_tflops"]
-    except Exception:
-        pass
-    # DFMA-class instructions per trajectory-step counted from SASS (tools/sass_mix.py), 2 flops each
-    FP64_INSTR = {"bwd": 831, "fwd": 273}
-    NCU_TRAFFIC = {"bwd": 1.632e9, "fwd": 2.289e9}      # dram read+write per full-batch launch (profiles/ncu_full_r1_fullbatch.txt)
+    fp64_peak_tf = fp64_peak["tflops"]
+    # FP64 instructions per trajectory-step: static SASS counts of the library that is loaded (build/sass_mix.json);
+    # "slot" flops count every DFMA / DMUL / DADD as one 2-flop pipe slot (what the pipe can issue), "true" flops count
+    # DFMA = 2, DMUL = DADD = 1
+    sass = sass_counts() or {}
+    round_tag = "round16" if round_warps >= 16 else "round"
+
+    def instr(tag):
+        v = sass.get(tag)
+        return (v["fp64"], 2 * v["DFMA"] + v["DMUL"] + v["DADD"]) if v else (None, None)
+
+    FP64_INSTR = {"bwd": instr("bwd")[0], "fwd": instr("fwd")[0]}
+    ncu_batch = {"bwd": ncu_file_metrics("ncu_full_r1_fullbatch.txt", "bwd_lpt_two_link"),
+                 "fwd": ncu_file_metrics("ncu_full_r1_fullbatch.txt", "fwd_lpt_two_link")}
     NAMES = {"bwd": "backward pass: bwd_lpt_two_link (nslots > 20,000), lin_lpt + ric_lpt / ric_coop_two_link below",
              "fwd": "fwd_lpt_two_link (+ fwd_retry_two_link for rejected step sizes)"}
     pass_ms = prof_acc["bwd_ms"] + prof_acc["fwd_ms"]
@@ -451,52 +633,60 @@ def run_b200(args):
         ms = prof_acc[which + "_ms"]
         first_ms = prof_acc["first_" + which + "_ms"] / iso_steps
         ach = per_traj * prof_acc["traj_iters"] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        flops = 2.0 * FP64_INSTR[which] * H * prof_acc["traj_iters"]
-        r = {"bound": "hbm", "kernel": NAMES[which], "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-             "traffic": NCU_TRAFFIC[which], "peak_source": peak_src,
-             "traffic_note": "dram read+write per full-batch launch from profiles/ncu_full_r1_fullbatch.txt (algorithmic: %.3e)" % (per_traj * B_PER_GPU),
+        ni = FP64_INSTR[which]
+        flops = 2.0 * ni * H * prof_acc["traj_iters"] if ni else None
+        nc = ncu_batch[which]
+        r = {"kernel": NAMES[which], "hbm_achieved_gbs": ach, "hbm_frac": ach / hbm_peak,
+             "traffic": nc["traffic"] if nc else None, "traffic_source": nc["file"] if nc else None,
              "algorithmic_bytes_per_trajectory": per_traj, "avg_launch_ms": ms / max(1, prof_acc[which + "_launches"]),
              "share_of_kernel_time": ms / pass_ms if pass_ms else None,
              "measured_on": "isolated solves (one batch at a time), CUDA events on the handle's stream; averaged over all "
                             "launches of a fit incl. the latency-bound tail (≈ 80 of 100 launches run on < 15 % of the batch)",
-             "full_batch_launch": {"ms": first_ms, "achieved": per_traj * B / (first_ms * 1e-3) / 1e9 if first_ms else None,
-                                   "frac": per_traj * B / (first_ms * 1e-3) / 1e9 / hbm_peak if first_ms else None},
-             "fp64": {"achieved_tflops": flops / (ms * 1e-3) / 1e12 if ms else None, "peak_tflops": fp64_peak_tf,
-                      "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
-                      "fp64_instr_per_trajectory_step": FP64_INSTR[which],
-                      "full_batch_launch_tflops": 2.0 * FP64_INSTR[which] * H * B / (first_ms * 1e-3) / 1e12 if first_ms else None}}
-        if fp64_peak_tf and r["fp64"]["achieved_tflops"]:
-            r["fp64"]["frac"] = r["fp64"]["achieved_tflops"] / fp64_peak_tf
-            if r["fp64"]["full_batch_launch_tflops"]:
-                r["fp64"]["full_batch_launch_frac"] = r["fp64"]["full_batch_launch_tflops"] / fp64_peak_tf
+             "full_batch_launch": {"ms": first_ms, "hbm_gbs": per_traj * B / (first_ms * 1e-3) / 1e9 if first_ms else None,
+                                   "hbm_frac": per_traj * B / (first_ms * 1e-3) / 1e9 / hbm_peak if first_ms else None,
+                                   "fp64_slot_tflops": 2.0 * ni * H * B / (first_ms * 1e-3) / 1e12 if (first_ms and ni) else None},
+             "fp64_instr_per_trajectory_step": ni,
+             "fp64_slot_tflops": flops / (ms * 1e-3) / 1e12 if (ms and flops) else None}
+        if fp64_peak_tf and r["full_batch_launch"]["fp64_slot_tflops"]:
+            r["full_batch_launch"]["fp64_slot_frac"] = r["full_batch_launch"]["fp64_slot_tflops"] / fp64_peak_tf
         return r
 
     # ---- roofline of the round kernel (every launch of the timed region): CUDA events on the launching stream, fence to
-    # fence over groups of 8 back-to-back launches (csrc/streamer.cu round_group); algorithmic bytes and FP64 instructions of
+    # fence over groups of back-to-back launches (csrc/streamer.cu round_group); algorithmic bytes and FP64 instructions of
     # the trajectory-iterations those launches performed
     ITER_BYTES = BWD_BYTES + FWD_BYTES                        # 60,904 B per trajectory-iteration
-    FP64_ROUND = FP64_INSTR["bwd"] + FP64_INSTR["fwd"]        # 1,104 DFMA-class instructions per trajectory-step (SASS)
+    FP64_ROUND, FP64_ROUND_TRUE = instr(round_tag)
     traj_iters_total = mean_iters * B * args.steps            # every step solves the same batch
     share = rounds_timed / rounds_total if rounds_total else 0.0
     avg_launch_ms = round_ms / rounds_timed if rounds_timed else None
     ach = ITER_BYTES * traj_iters_total * share / (round_ms * 1e-3) / 1e9 if round_ms else 0.0
-    tfl = 2.0 * FP64_ROUND * H * traj_iters_total * share / (round_ms * 1e-3) / 1e12 if round_ms else None
+    per_s = traj_iters_total * share * H / (round_ms * 1e-3) if round_ms else None      # trajectory-steps per second
+    slot_tf = 2.0 * FP64_ROUND * per_s / 1e12 if (per_s and FP64_ROUND) else None
+    true_tf = FP64_ROUND_TRUE * per_s / 1e12 if (per_s and FP64_ROUND_TRUE) else None
+    ncu_round = ncu_file_metrics(NCU_ROUND_FILE, "round_lpt_two_link")
+    kname = "round_lpt_two_link<%s> (backward sweep + forward sweep + accept / converge test + retirement + admission; the only " \
+            "kernel launched in the timed region)" % ("16, 3" if round_warps >= 16 else "12, 4")
     roofline = {
-        "bound": "hbm", "kernel": "round_lpt_two_link<12, 4> (backward sweep + forward sweep + accept / converge test + retirement + admission; "
-                                  "the only kernel launched in the timed region)",
-        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 3.708e9, "peak_source": peak_src,
-        "traffic_note": "dram read+write of one full-width launch under ncu (profiles/ncu_full_r1_round.txt): 2.20 GB read + 1.51 GB "
-                        "written; algorithmic %.3e B for %d slots" % (ITER_BYTES * SLOTS, SLOTS),
-        "algorithmic_bytes_per_trajectory_iteration": ITER_BYTES, "avg_launch_ms": avg_launch_ms, "launches_timed": rounds_timed,
-        "launches_in_timed_region": rounds_total, "slots": SLOTS,
+        "bound": "fp64", "kernel": kname,
+        "achieved": slot_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s", "frac": slot_tf / fp64_peak_tf if (slot_tf and fp64_peak_tf) else None,
+        "achieved_is": "FP64 pipe-slot rate: every DFMA / DMUL / DADD the kernel issues counted as one 2-flop slot (%s FP64 instructions per "
+                       "trajectory-step, static SASS count) — the occupancy of the pipe that bounds the kernel, not a flop count" % FP64_ROUND,
+        "true_flops_tflops": true_tf, "true_flops_frac": true_tf / fp64_peak_tf if (true_tf and fp64_peak_tf) else None,
+        "true_flops_per_trajectory_step": FP64_ROUND_TRUE,
+        "peak_source": fp64_peak["source"] + " (FP64 is not in MEASURED_PEAKS.json; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
+        "fp64_peak_detail": fp64_peak,
+        "hbm": {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_trajectory_iteration": ITER_BYTES},
+        "traffic": ncu_round["traffic"] if ncu_round else None,
+        "traffic_note": ("dram read + write of one full-width launch under ncu --set full (%s: %.3f ms, FP64 pipe %.1f %% active); algorithmic "
+                         "%.3e B for %d slots" % (ncu_round["file"], ncu_round["ms"], ncu_round["fp64_pipe_pct"], ITER_BYTES * SLOTS, SLOTS))
+                        if ncu_round else "no ncu capture committed for this kernel",
+        "avg_launch_ms": avg_launch_ms, "launches_timed": rounds_timed,
+        "launches_in_timed_region": rounds_total, "slots": SLOTS, "rounds_per_launch": rounds_per_launch,
         "trajectory_iterations_per_launch": traj_iters_total / rounds_total if rounds_total else None,
-        "measured_on": "the K timed steps (resident arm): CUDA events on the streamer's stream around every group of 8 launches; includes the "
-                       "final drain, whose launches run on the stragglers only",
-        "fp64": {"achieved_tflops": tfl, "peak_tflops": fp64_peak_tf, "frac": tfl / fp64_peak_tf if (tfl and fp64_peak_tf) else None,
-                 "peak_source": "tools/fp64_peak.cu DFMA micro-benchmark on B200 (profiles/fp64_peak.json)",
-                 "fp64_instr_per_trajectory_step": FP64_ROUND,
-                 "reference_formulation_flops_per_trajectory_step": 9619,   # oracle/count_ops.cpp (+ 180 sin/cos): dual-number Jacobians / Hessians
-                 "note": "the binding roofline: the FP64 pipe is 71 % active in a full-width launch (ncu, 1.03 ms), DRAM traffic 3.6 TB/s"},
+        "measured_on": "the K timed steps (resident arm): CUDA events on the streamer's stream around every group of back-to-back launches; "
+                       "includes the final drain, whose launches run on the stragglers only",
+        "reference_formulation_flops_per_trajectory_step": 9619,   # oracle/count_ops.cpp (+ 180 sin/cos): dual-number Jacobians / Hessians
         "batch_path_kernels": {"fwd_lpt_two_link": kernel_roofline("fwd"), "backward_pass": kernel_roofline("bwd")},
     }
     isolated = {"value": world * B / (iso_ms * 1e-3), "unit": UNIT, "ms_per_step": iso_ms,
@@ -505,32 +695,58 @@ def run_b200(args):
 
     # ---- end to end through the host-facing C-ABI call with pinned host buffers (H2D + D2H inside the timed region)
     e2e = None
+    e2e_variants = None
     if not args.no_e2e:
         hx = torch.empty((B, N_, NKNOT), dtype=torch.float64).pin_memory(); hx.copy_(dx)
         hu = torch.zeros((B, M_, H), dtype=torch.float64).pin_memory()
+        hx0 = torch.from_numpy(np.ascontiguousarray(x0.T)).pin_memory()        # [B][n] == Julia x0[n,B]
         houts = [out_set(False) for _ in range(RING)]
 
-        def submit_host(i):
-            return streamer.submit_ptrs(hx.data_ptr(), hu.data_ptr(), *[t.data_ptr() for t in houts[i % RING]], device=False)
+        def e2e_run(submit_one, h2d, d2h, api):
+            run_windowed(max(3, min(args.warmup, RING)), submit_one, streamer.wait, RING)
+            r0 = streamer.rounds()
+            ms = run_windowed(args.steps, submit_one, streamer.wait, RING) / args.steps
+            return {"value": world * B / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms, "h2d_gbs_per_rank": h2d / ms / 1e6, "d2h_gbs_per_rank": d2h / ms / 1e6,
+                    "host_link_gbs_all_ranks": world * (h2d + d2h) / ms / 1e6,
+                    "batches_in_flight": RING, "launches": streamer.rounds() - r0, "api": api}
 
-        run_windowed(max(3, min(args.warmup, RING)), submit_host, streamer.wait, RING)
-        r0 = streamer.rounds()
-        ms_e2e = run_windowed(args.steps, submit_host, streamer.wait, RING)
-        e2e_rounds = streamer.rounds() - r0
-        h2d = hx.numel() * 8 + hu.numel() * 8
-        d2h = hx.numel() * 8 + hu.numel() * 8 + B * 8 + B * 4 + B * 4
+        def same_as_resident(ho, which=(0, 1, 2, 3, 4)):
+            return bool(all(torch.equal(ho[j], douts[0][j].cpu()) for j in which))
+
+        scal = B * 8 + B * 4 + B * 4
+        # (1) headline: the reference's own fit signature — x_init and u_init in, x̄ and ū (+ cost, iterations, status) out
+        e2e = e2e_run(lambda i: streamer.submit_ptrs(hx.data_ptr(), hu.data_ptr(), *[t.data_ptr() for t in houts[i % RING]], device=False),
+                      hx.numel() * 8 + hu.numel() * 8, hx.numel() * 8 + hu.numel() * 8 + scal,
+                      "ilqr_streamer_submit: pinned host x_init,u_init in, host x,u,cost,iters,status out; uploads and copy-backs run on "
+                      "copy streams beside the rounds")
+        e2e["results_identical_to_resident_arm"] = same_as_resident(houts[0])
         # one isolated host-to-host solve of a single batch for reference (batch path: ilqr_solve)
         hs1 = houts[1 % RING]
         barrier(); t0 = time.perf_counter()
         s.solve_ptrs(hx.data_ptr(), hu.data_ptr(), MAX_ITER, TOL, *[t.data_ptr() for t in hs1])
         torch.cuda.synchronize()
-        iso_e2e_ms = (time.perf_counter() - t0) * 1e3
-        e2e = {"value": world * B / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "batches_in_flight": RING, "launches": e2e_rounds,
-               "isolated_ms_per_step": iso_e2e_ms,
-               "results_identical_to_resident_arm": bool(torch.equal(houts[0][0], douts[0][0].cpu()) and torch.equal(houts[0][3], douts[0][3].cpu())),
-               "api": "ilqr_streamer_submit: pinned host x_init,u_init in, host x,u,cost,iters,status out; uploads and copy-backs run on "
-                      "copy streams beside the rounds"}
+        e2e["isolated_ms_per_step"] = (time.perf_counter() - t0) * 1e3
+        # (2) problem setup on device (animate_2_link.jl:11-16): only x0 crosses the bus, x_init is rolled out by the library
+        for o in houts:
+            for t in o:
+                t.zero_()
+        v2 = e2e_run(lambda i: streamer.submit_ptrs(hx0.data_ptr(), None, *[t.data_ptr() for t in houts[i % RING]], device=False, x0=True),
+                     hx0.numel() * 8, hx.numel() * 8 + hu.numel() * 8 + scal,
+                     "ilqr_streamer_submit_x0: pinned host x0[n,B] in (u_init = NULL = zeros, x_init rolled out on the device), host "
+                     "x,u,cost,iters,status out")
+        v2["results_identical_to_resident_arm"] = same_as_resident(houts[0])
+        # (3) same, the caller asks for ū and the scalars only (x_out = NULL)
+        for o in houts:
+            for t in o:
+                t.zero_()
+        v3 = e2e_run(lambda i: streamer.submit_ptrs(hx0.data_ptr(), None, None, *[t.data_ptr() for t in houts[i % RING][1:]], device=False, x0=True),
+                     hx0.numel() * 8, hu.numel() * 8 + scal,
+                     "ilqr_streamer_submit_x0 with x_out = NULL: host x0 in, host u,cost,iters,status out")
+        v3["results_identical_to_resident_arm"] = same_as_resident(houts[0], (1, 2, 3, 4))
+        e2e_variants = {"x0_in__x_u_out": v2, "x0_in__u_out": v3,
+                        "note": "the headline `e2e` moves what the reference's fit signature moves (x_init, u_init in; x̄, ū out); these two move "
+                                "less across the host link, which all ranks of a node share"}
     streamer.close()
 
     # the only collective: gather final costs / iteration counts / status of the timed steps' batch (after the timed region)
@@ -540,17 +756,34 @@ def run_b200(args):
         gs = [torch.empty_like(status) for _ in range(world)]
         dist.all_gather(gi, iters); dist.all_gather(gc, cost); dist.all_gather(gs, status)
         iters, cost, status = torch.cat(gi), torch.cat(gc), torch.cat(gs)
-    s.close()
-    other = None
-    if rank == 0 and world == 1 and not args.no_aux and B == B_PER_GPU:
+
+    # ---- parity of the measured path on this very batch: the oracle on the cpu_baseline sample vs the streamer's outputs
+    cpu = parity = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
+        x_init_host = np.asfortranarray(dx.cpu().numpy().transpose(2, 1, 0))        # [N,n,B]
+        cpu, ref, n_s = cpu_baseline(args.cpu_seconds, x_init_host)
+        gpu = {"x": douts[0][0][:n_s].cpu().numpy().transpose(2, 1, 0), "u": douts[0][1][:n_s].cpu().numpy().transpose(2, 1, 0),
+               "cost": douts[0][2][:n_s].cpu().numpy(), "iters": douts[0][3][:n_s].cpu().numpy(), "status": douts[0][4][:n_s].cpu().numpy()}
+        traced = None
         try:
-            other = {"configs[3]": aux_chain(local, not args.no_cpu_baseline), "configs[2]": aux_floating(local)}
-        except Exception as e:   # a side measurement must never take the headline line down
+            with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, n_s, trace_iters=MAX_ITER, device=local)) as st_:
+                st_.upload(np.asfortranarray(x_init_host[:, :, :n_s]), np.zeros((H, M_, n_s), order="F"))
+                st_.fit(MAX_ITER, TOL)
+                bx, bi = st_.download(_abi.X), st_.download(_abi.ITERS)
+                traced = {"alpha_trace": st_.download(_abi.ALPHA_TRACE), "cost_trace": st_.download(_abi.COST_TRACE),
+                          "bitwise": np.array_equal(bx, gpu["x"]) and np.array_equal(bi, gpu["iters"])}
+        except Exception as e:
+            traced = None
+        parity = parity_report(ref, n_s, gpu, traced)
+    s.close()
+    del douts
+    other = None
+    if not args.no_aux and B == B_PER_GPU:
+        try:   # a side measurement must never take the headline line down
+            other = aux_configs(rank, world, local, dist if world > 1 else None, cpu_too=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+        except Exception as e:
             other = {"error": repr(e)}
     if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
-            cpu = cpu_baseline(args.cpu_seconds)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -569,7 +802,8 @@ def run_b200(args):
             "mean_iterations_per_trajectory": float(iters.double().mean().item()),
             "converged_fraction": float(((status & 16) != 0).double().mean().item()),
             "mean_final_cost": float(cost.mean().item()),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "e2e_variants": e2e_variants,
+            "gpu_launches": int(launches), "clocks": clk,
             "other_configs": other,
         }
         print(json.dumps(line))
