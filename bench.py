@@ -404,11 +404,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.window = None          # (t0, t1) of the timed region: only samples taken inside it count
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -416,13 +417,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        rows = self.rows
+        if self.window:
+            inside = [r for r in rows if self.window[0] <= r[0] <= self.window[1] + 0.05]
+            rows = inside or rows
+        for _, r in rows:
             f = [t.strip() for t in r.split(",")]
             if len(f) < 6:
                 continue
@@ -499,7 +504,7 @@ def run_b200(args):
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     round_warps = int(os.environ.get("ILQR_ROUND_WARPS", "12"))
     rounds_per_launch = int(os.environ.get("ILQR_ROUND_MULTI", "1"))
-    SLOTS = n_sm * round_warps * 32   # one block of 12 (or 16) warps per SM (csrc/kernels_round.cu)
+    SLOTS = n_sm * (16 if round_warps >= 16 else 12) * 32   # one block of 12 (or 16) warps per SM (csrc/kernels_round.cu)
     RING = args.ring
     streamer = ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, SLOTS, device=local), B, ring=RING, max_iter=MAX_ITER, tol=TOL)
 
@@ -552,13 +557,16 @@ def run_b200(args):
     def submit_resident(i):
         return streamer.submit_ptrs(dx.data_ptr(), du.data_ptr(), *[t.data_ptr() for t in douts[i % RING]], device=True)
 
+    clocks = ClockSampler(local); clocks.start()     # started early: nvidia-smi takes a while to deliver its first sample
     if args.warmup > 0:
         run_windowed(args.warmup, submit_resident, streamer.wait, RING)
-    clocks = ClockSampler(local); clocks.start()
     p0, l0 = streamer.profile(), streamer.launch_count()
+    t_w0 = time.perf_counter()
     ms_total = run_windowed(args.steps, submit_resident, streamer.wait, RING)
+    clocks.window = (t_w0, time.perf_counter())
     p1, launches = streamer.profile(), streamer.launch_count() - l0
     clk = clocks.stop()
+    clk["sampled"] = "nvidia-smi -lms 50 during the timed region (%d samples inside it)" % clk.get("samples", 0)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
     round_ms, rounds_timed = p1["round_ms"] - p0["round_ms"], p1["rounds_timed"] - p0["rounds_timed"]

@@ -300,6 +300,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   if (const char* e = getenv("ILQR_ROUND_WARPS")) h->round_warps = atoi(e);
   if (const char* e = getenv("ILQR_ROUND_SHIFT")) h->round_shift = atoi(e);
   if (const char* e = getenv("ILQR_ROUND_GROUP")) h->round_group = std::max(1, atoi(e));
+  if (const char* e = getenv("ILQR_ROUND_MULTI")) h->round_multi = std::max(1, atoi(e));
   if (const char* e = getenv("ILQR_STREAM_FUSED")) h->stream_fused = atoi(e) != 0;
   if (const char* e = getenv("ILQR_ROUND_DRAIN")) h->round_drain = atoi(e) != 0;
   if (is_chain) {

@@ -68,6 +68,7 @@ struct RoundArgs {
   double tol;
   int32_t parity, shifted, max_iter, pub_slot;
   int32_t drain;                // the pending queue is empty: gather the remaining trajectories (kernels_round.cu)
+  int32_t rounds;               // whole iterations per launch (>= 1; 1 when draining)
 };
 void init_round_attributes();
 // x_init[Bb][n][N] (boundary layout) = open-loop rollout of u (boundary layout, nullptr = zeros) from x0[Bb][n]

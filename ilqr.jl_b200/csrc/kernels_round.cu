@@ -126,7 +126,10 @@ __device__ __forceinline__ void admit_slot(const double* __restrict__ ix, const 
 
 // Slot state in rp.traj[s]:  t ≥ 0 — live, solving trajectory t;  −1 — idle;  ≤ −2 — holds queue ticket −2 − t and
 // waits for that trajectory to become available (t < n_avail).
-template <int kWarps, int D>
+// PARK (the 16-warp build, 128 registers): the value function (𝐬, 𝐒: 20 doubles) is parked in shared memory while the
+// time step is linearised — in the δuff / K part of the first two ring stages, which the backward sweep does not use —
+// so that the RK4 Jacobian chain (60 doubles) does not have to share the register file with it.
+template <int kWarps, int D, bool PARK>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ TwoLinkP mp,
                    const __grid_constant__ CostP cp, const __grid_constant__ RoundArgs ra) {
@@ -160,14 +163,17 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
     __syncwarp();
 
 #pragma unroll 1
-    for (int ph = 0; ph < 2; ++ph) {
+    for (int rr = 0; rr < 2 * ra.rounds; ++rr) {
+      // ra.rounds whole iterations per launch: the slots of a warp depend on nothing another warp does, so a warp goes
+      // from one round to the next without waiting for the grid (buffer parity flips per round)
+      const int ph = rr & 1, par = ra.parity ^ ((rr >> 1) & 1);
       const bool is_bwd = (ph == 0) != odd;
       if (is_bwd) {
         // ------------------------------------------------------------------------------------------------
         // backward sweep over the current iterate (src/backward_pass.jl:324-357); lanes in a line-search
         // retry keep the gains they have
         // ------------------------------------------------------------------------------------------------
-        const int pb = odd ? (ra.parity ^ 1) : ra.parity;   // odd warps: after this launch's bookkeeping
+        const int pb = odd ? (par ^ 1) : par;   // odd warps: after this launch's bookkeeping
         const double* X = rp.x[pb];
         const double* U = rp.u[pb];
         const bool act = live && lsj == 0;
@@ -200,6 +206,21 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
             }
           }
           bool bad = false;
+          // parked value function: 𝐒 element e = 4c + j of lane l at ring[e / 10][oD + (e % 10) * 32 + l], 𝐬 behind it —
+          // the first two stages as laid out in memory (the stage rotation does not move it); lane-strided: no conflicts
+          volatile double* park0 = &ring[0][oD + lane];
+          volatile double* park1 = &ring[1][oD + lane];
+          if constexpr (PARK) {
+#pragma unroll
+            for (int c = 0; c < NX; ++c) {
+              park1[(6 + c) * 32] = sv[c];
+#pragma unroll
+              for (int j = 0; j < NX; ++j) {
+                const int e = c * NX + j;
+                if (e < 10) park0[e * 32] = Sm[c][j]; else park1[(e - 10) * 32] = Sm[c][j];
+              }
+            }
+          }
 #pragma unroll 1
           for (int k = H - 1; k >= 0; --k, ++fills) {
             const int stage = fills % D;
@@ -221,7 +242,29 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
 #pragma unroll
               for (int i = 0; i < NU; ++i) rv[i] = Rd[i] * uk[i];
               double d[NU], Kk[NU][NX];
+              if constexpr (PARK) {
+#pragma unroll
+                for (int c = 0; c < NX; ++c) {
+                  sv[c] = park1[(6 + c) * 32];
+#pragma unroll
+                  for (int j = 0; j < NX; ++j) {
+                    const int e = c * NX + j;
+                    Sm[c][j] = (e < 10) ? park0[e * 32] : park1[(e - 10) * 32];
+                  }
+                }
+              }
               riccati_step<NX, NU, true, true>(A, Bm, qv, rv, Qd, Rd, rp.reg, sv, Sm, d, Kk);
+              if constexpr (PARK) {
+#pragma unroll
+                for (int c = 0; c < NX; ++c) {
+                  park1[(6 + c) * 32] = sv[c];
+#pragma unroll
+                  for (int j = 0; j < NX; ++j) {
+                    const int e = c * NX + j;
+                    if (e < 10) park0[e * 32] = Sm[c][j]; else park1[(e - 10) * 32] = Sm[c][j];
+                  }
+                }
+              }
               double kv[NK];
 #pragma unroll
               for (int i = 0; i < NU; ++i) {
@@ -239,10 +282,10 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
         // ------------------------------------------------------------------------------------------------
         // forward sweep: one step size per lane (src/forward_pass.jl:55-93), candidate → the other buffer
         // ------------------------------------------------------------------------------------------------
-        const double* X = rp.x[ra.parity];
-        const double* U = rp.u[ra.parity];
-        double* Xo = rp.x[ra.parity ^ 1];
-        double* Uo = rp.u[ra.parity ^ 1];
+        const double* X = rp.x[par];
+        const double* U = rp.u[par];
+        double* Xo = rp.x[par ^ 1];
+        double* Uo = rp.u[par ^ 1];
         double cost = 0.0, du2 = 0.0;
         bool accepted = false, bad_r = false;
         if (__any_sync(kFull, live)) {
@@ -416,8 +459,8 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
     const bool mine = sd < rp.nslots;
     const long long myt = mine ? __ldcg(rp.traj + sd) : 0;
     bool myidle = mine && myt < 0;
-    double* Xn = rp.x[ra.parity ^ 1];
-    double* Un = rp.u[ra.parity ^ 1];
+    double* Xn = rp.x[ra.parity ^ (ra.rounds & 1)];   // the buffer every slot reads in the next launch
+    double* Un = rp.u[ra.parity ^ (ra.rounds & 1)];
 #pragma unroll 1
     for (int sw = warp + 4; sw < kWarps; sw += 4) {
       const int ss = b0 + sw * 32 + lane;
@@ -484,8 +527,9 @@ template <int kWarps, int D> constexpr size_t round_smem() { return sizeof(doubl
 }  // namespace
 
 void init_round_attributes() {
-  cudaFuncSetAttribute(round_lpt_two_link<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<12, 4>());
-  cudaFuncSetAttribute(round_lpt_two_link<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<16, 3>());
+  cudaFuncSetAttribute(round_lpt_two_link<12, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<12, 4>());
+  cudaFuncSetAttribute(round_lpt_two_link<16, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<16, 3>());
+  cudaFuncSetAttribute(round_lpt_two_link<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<16, 3>());
 }
 
 void launch_rollout_tf_two_link(const TwoLinkP& mp, const double* d_x0, const double* d_u, double* d_x, long long Bb, int H,
@@ -495,8 +539,10 @@ void launch_rollout_tf_two_link(const TwoLinkP& mp, const double* d_x0, const do
 
 void launch_round_two_link(const RoundP& rp, const TwoLinkP& mp, const CostP& cp, const RoundArgs& ra, int warps_per_sm,
                            cudaStream_t s) {
-  if (warps_per_sm >= 16) round_lpt_two_link<16, 3><<<(int)((rp.S + 511) / 512), 512, round_smem<16, 3>(), s>>>(rp, mp, cp, ra);
-  else round_lpt_two_link<12, 4><<<(int)((rp.S + 383) / 384), 384, round_smem<12, 4>(), s>>>(rp, mp, cp, ra);
+  // warps_per_sm: 12 (168 registers), 16 (128 registers, the compiler spills), 17 = 16 warps with the parked value function
+  if (warps_per_sm == 17) round_lpt_two_link<16, 3, true><<<(int)((rp.S + 511) / 512), 512, round_smem<16, 3>(), s>>>(rp, mp, cp, ra);
+  else if (warps_per_sm >= 16) round_lpt_two_link<16, 3, false><<<(int)((rp.S + 511) / 512), 512, round_smem<16, 3>(), s>>>(rp, mp, cp, ra);
+  else round_lpt_two_link<12, 4, false><<<(int)((rp.S + 383) / 384), 384, round_smem<12, 4>(), s>>>(rp, mp, cp, ra);
 }
 
 }  // namespace ilqr

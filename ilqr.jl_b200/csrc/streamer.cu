@@ -66,29 +66,35 @@ static int32_t round_set_batch(ilqr_handle* h, int slot, const BatchTab& e) {
 }
 
 static int32_t round_group(ilqr_handle* h, long long n_avail, int32_t max_iter, double tol, bool drain) {
-  const int G = h->round_group;
   const int64_t g = h->round_groups;
-  for (int r = 0; r < G; ++r) {
+  const bool draining = drain && h->round_drain;
+  // a group is round_group iterations: launches of round_multi iterations each (one iteration per launch while
+  // draining — the gathering at the end of a launch needs the block barrier)
+  const int R = draining ? 1 : std::max(1, std::min(h->round_multi, h->round_group));
+  const int L = std::max(1, h->round_group / R);
+  for (int r = 0; r < L; ++r) {
     RoundArgs ra{};
     ra.n_avail = n_avail; ra.tol = tol; ra.parity = h->round_parity; ra.shifted = h->round_shift; ra.max_iter = max_iter;
     ra.pub_slot = (int32_t)(g & 1);
-    ra.drain = (drain && h->round_drain) ? 1 : 0;
+    ra.drain = draining ? 1 : 0;
+    ra.rounds = R;
     launch_round_two_link(h->rp, h->mp, h->cp, ra, h->round_warps, h->stream);
-    h->round_parity ^= 1;
+    h->round_parity ^= (R & 1);
   }
-  h->rounds_launched += G; h->launches += G;
+  h->rounds_launched += (int64_t)L * R; h->launches += L;
   if (int32_t rc = check_launch(h, "round kernel")) return rc;
   CK(h, cudaEventRecord(h->round_ev[g & 3], h->stream));
+  h->round_group_rounds[g & 3] = L * R;
   h->round_groups = g + 1;
   if (g >= 1) {
     CK(h, cudaEventSynchronize(h->round_ev[(g - 1) & 3]));
     const volatile long long* pub = (const volatile long long*)h->round_pub;
     h->pub_retired = pub[2 * ((g - 1) & 1)];
     h->pub_next = pub[2 * ((g - 1) & 1) + 1];
-    float ms = 0.f;   // group g-1 ran right behind group g-2 on the stream: fence to fence = its G launches
+    float ms = 0.f;   // group g-1 ran right behind group g-2 on the stream: fence to fence = its launches
     if (h->round_skip_timing > 0) --h->round_skip_timing;
     else if (g >= 2 && cudaEventElapsedTime(&ms, h->round_ev[(g - 2) & 3], h->round_ev[(g - 1) & 3]) == cudaSuccess) {
-      h->round_ms += ms; h->round_ms_rounds += G;
+      h->round_ms += ms; h->round_ms_rounds += h->round_group_rounds[(g - 1) & 3];
     }
   }
   return ILQR_OK;
@@ -125,7 +131,7 @@ int32_t stream_solve_rounds(ilqr_handle* h, int64_t n_total, const double* d_x_i
   int64_t done_at = -1;
   while (h->pub_retired < n_total) {
     if (int32_t rc = round_group(h, n_total, max_iter, tol, h->pub_next >= n_total)) return rc;
-    if (h->pub_retired >= n_total) done_at = (h->round_groups - 1) * h->round_group;
+    if (h->pub_retired >= n_total) done_at = h->rounds_launched - h->round_group_rounds[(h->round_groups - 1) & 3];
     else if (h->rounds_launched > guard) return fail(h, ILQR_ERR_STATE, "stream solve: no progress (internal error)");
   }
   CK(h, cudaEventRecord(h->span_ev[1], h->stream));

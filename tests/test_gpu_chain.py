@@ -230,8 +230,9 @@ def test_floating_base_fit_matches_oracle():
 
 def test_config3_reference_problem_matches_oracle():
     """BASELINE configs[2] (test/RBD_2_link_example as written: 2Dof_arm.urdf on a floating base, the reference's
-    weights 1e3…1e8 and target pose) at oracle-sized B and H.  The terminal weights make H + reg·I ill-conditioned
-    (cond ≈ 1e7), so gains agree to ≈ cond·ε rather than 1e-9; costs and trajectories still meet 1e-9."""
+    weights 1e3…1e8 and target pose) at oracle-sized B and H: gains, per-iterate costs and trajectories at north_star's
+    1e-9 (observed on B200: gains 3e-15, tools/config3_gain_error.py — the terminal weights of 1e8 make H + reg·I
+    ill-conditioned, but both sides factor the same matrix with partial pivoting and the errors stay at rounding level)."""
     B, H = 8, 40
     spec, prob, x0, x, u = _setup_floating(2, B, H, 3, reference_config=True)
     with ilqr_b200.BatchSolver(prob) as s:
@@ -240,7 +241,7 @@ def test_config3_reference_problem_matches_oracle():
         d, K = s.download(_abi.DUFF), s.download(_abi.K)
     for b in range(B):
         d0, K0, _ = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
-        assert rel_err(d[:, :, b], d0) <= 1e-7 and rel_err(K[:, :, :, b], K0) <= 1e-7, (rel_err(d[:, :, b], d0), rel_err(K[:, :, :, b], K0))
+        assert rel_err(d[:, :, b], d0) <= RTOL and rel_err(K[:, :, :, b], K0) <= RTOL, (rel_err(d[:, :, b], d0), rel_err(K[:, :, :, b], K0))
     ref = orc.chain_fit_batch(spec, x, u, max_iter=12, tol=1e-6, nthreads=8)
     assert np.nanmin(ref["alpha"]) < 1.0          # the line search fires on this problem (α down to 1/8)
     with ilqr_b200.BatchSolver(prob) as s:
@@ -253,7 +254,7 @@ def test_config3_reference_problem_matches_oracle():
         assert np.array_equal(at[:it, b], ref["alpha"][:it, b]), (at[:it, b], ref["alpha"][:it, b])
         errs.append(rel_err(ct[:it, b], ref["cost"][:it, b]))
     print("config-3 cost-trace rel err", max(errs), "x rel err", rel_err(out["x"], ref["x"]))
-    assert max(errs) <= 1e-8 and rel_err(out["x"], ref["x"]) <= 1e-8
+    assert max(errs) <= RTOL and rel_err(out["x"], ref["x"]) <= RTOL
 
 
 @pytest.mark.parametrize("name", ["fixed", "floating"])

@@ -571,3 +571,67 @@ def test_forward_pass_twice_without_commit_large_batch():
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a, b, equal_nan=True)
     assert np.array_equal(res[0][0], res[0][2]) and np.array_equal(res[0][1], res[0][3], equal_nan=True)
+
+
+def test_streamer_directly_against_oracle_2048_trajectories():
+    """The measured path (ilqr_streamer_submit: host buffers, fused rounds, continuous batching) DIRECTLY against the
+    oracle — not via the batch path — on 2,048 config-2 trajectories, four batches of 512 through 1,024
+    slots so that slots are refilled across batch boundaries.  Branch decisions (iteration counts, convergence flags) are
+    counted separately from value errors; tolerances are north_star's: iterates 1e-9, converged cost 1e-8."""
+    H, Bb, nb, slots = 200, 512, 4, 1024
+    n = Bb * nb
+    _, x, u = config2_batch(n, H, seed=2024)
+    ref = orc.fit_batch(x, u, max_iter=100, tol=1e-6, nthreads=os.cpu_count() or 1, traces=True)
+    outs = [dict(x=np.zeros((H + 1, 4, Bb), order="F"), u=np.zeros((H, 2, Bb), order="F"), cost=np.zeros(Bb),
+                 iters=np.zeros(Bb, dtype=np.int32), status=np.zeros(Bb, dtype=np.int32)) for _ in range(nb)]
+    ins = [(np.asfortranarray(x[:, :, b * Bb:(b + 1) * Bb]), np.asfortranarray(u[:, :, b * Bb:(b + 1) * Bb])) for b in range(nb)]
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, slots), Bb, ring=2, max_iter=100, tol=1e-6) as st:
+        for b in range(nb):
+            st.submit(ins[b][0], ins[b][1], outs[b])
+        st.wait_all()
+    it = np.concatenate([o["iters"] for o in outs]); stt = np.concatenate([o["status"] for o in outs])
+    xs = np.concatenate([o["x"] for o in outs], axis=2); us = np.concatenate([o["u"] for o in outs], axis=2)
+    cost = np.concatenate([o["cost"] for o in outs])
+    assert int(np.sum(it != ref["iters"])) == 0, "iteration-count (branch decision) mismatches"
+    assert np.array_equal((stt & _abi.STATUS_CONVERGED) != 0, ref["converged"])
+    assert not np.any(stt & (1 | 2 | 4 | 8))
+    assert rel_err_per_traj(xs, ref["x"]).max() < RTOL and rel_err_per_traj(us, ref["u"]).max() < RTOL
+    last = ref["cost"][ref["iters"] - 1, np.arange(n)]
+    assert np.max(np.abs(cost - last) / np.abs(last)) < RTOL_CONVERGED_COST
+    assert len(np.unique(it)) > 10          # the heavy-tailed iteration counts of config 2 are in the sample
+
+
+def test_config1_single_trajectory_H900_against_anchor_and_oracle():
+    """BASELINE configs[0] (test/2_link_example/animate_2_link.jl:7-25): ONE trajectory, x0 = [.1, −.1, 0, 0], H = 900,
+    u_init = 0, x_init = zero-input rollout, tol 1e-6 — on the GPU through ilqr_fit (per-iteration traces), ilqr_solve
+    and the streamer, against the oracle and the SURVEY §6 anchor (7 iterations, final cost 340.0501055786)."""
+    import json
+    with open(os.path.join(GOLD, "survey_anchors.json")) as f:
+        anchor = [c for c in json.load(f)["cases"] if c["H"] == 900][0]
+    H = 900
+    x0 = np.array(anchor["x0"])
+    u = np.zeros((H, 2))
+    x = orc.rollout(x0, u)
+    ref = orc.fit(x, u, max_iter=100, tol=1e-6)
+    p = ilqr_b200.two_link_problem(H, 1, trace_iters=100)
+    with ilqr_b200.BatchSolver(p) as s:
+        s.upload_x0(x0.reshape(4, 1), u.reshape(H, 2, 1))
+        assert rel_err(s.download(_abi.X)[:, :, 0], x) < 1e-12
+        s.upload(x, u)
+        s.fit(100, 1e-6)
+        it, ct, at = int(s.download(_abi.ITERS)[0]), s.download(_abi.COST_TRACE)[:, 0], s.download(_abi.ALPHA_TRACE)[:, 0]
+        xs, us = s.download(_abi.X)[:, :, 0], s.download(_abi.U)[:, :, 0]
+    assert it == anchor["iters"] == ref["iters"]
+    assert np.allclose(ct[:it], anchor["trace"], rtol=1e-9, atol=0) and np.all(at[:it] == 1.0)
+    assert abs(ct[it - 1] - anchor["last_cost"]) < RTOL_CONVERGED_COST * anchor["last_cost"]
+    assert rel_err(xs, ref["x"]) < RTOL and rel_err(us, ref["u"]) < RTOL
+    # the reference's fit signature, single problem
+    x2, u2 = ilqr_b200.fit(x, u, ilqr_b200.two_link_problem(H), max_iter=100, tol=1e-6)
+    assert np.array_equal(x2, xs) and np.array_equal(u2, us)
+    # the streamer with a batch of one trajectory in 32 slots
+    out = dict(x=np.zeros((H + 1, 4, 1), order="F"), u=np.zeros((H, 2, 1), order="F"), cost=np.zeros(1),
+               iters=np.zeros(1, dtype=np.int32), status=np.zeros(1, dtype=np.int32))
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, 32), 1, ring=2, max_iter=100, tol=1e-6) as st:
+        st.wait(st.submit(np.asfortranarray(x.reshape(H + 1, 4, 1)), np.asfortranarray(u.reshape(H, 2, 1)), out))
+    assert out["iters"][0] == it and np.array_equal(out["x"][:, :, 0], xs) and np.array_equal(out["u"][:, :, 0], us)
+    assert abs(out["cost"][0] - anchor["last_cost"]) < RTOL_CONVERGED_COST * anchor["last_cost"]

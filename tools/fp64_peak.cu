@@ -20,6 +20,24 @@ __global__ void dfma_throughput(double* out, int iters, double a, double b, int 
   if (s == 12345.678) out[0] = s;
 }
 
+// The same with three distinct VECTOR register operands per DFMA (what real code issues: the loop above multiplies by two
+// uniform values, i.e. one register operand per instruction) — the register-file side of the FP64 pipe's peak.
+template <int ILP>
+__global__ void dfma3_throughput(double* out, int iters, double a, double b) {
+  double acc[ILP], x[ILP], y[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) { acc[i] = threadIdx.x * 1e-3 + i; x[i] = a + 1e-12 * (threadIdx.x + i); y[i] = b + 1e-13 * (threadIdx.x * 3 + i); }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], x[(i + 3) % ILP], y[(i + 5) % ILP]);
+    if (it == iters - 7) { x[0] += 1e-15; y[1] += 1e-15; }   // keeps x, y in registers as live, non-constant values
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += acc[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 __global__ void latency_kernel(double* out, long long* cycles, int iters, double a, double b, int mode) {
   double x = a;
   long long t0 = clock64();
@@ -63,6 +81,19 @@ int main() {
       if (ms < b2) b2 = ms;
     }
     printf(", \"ms_lanes%d\": %.4f", lanes, b2);
+  }
+  // three register operands; full occupancy and the round kernel's residency (one block of 12 warps per SM)
+  for (int cfg = 0; cfg < 2; ++cfg) {
+    const int bl = cfg == 0 ? blocks : p.multiProcessorCount, th = cfg == 0 ? threads : 384;
+    float b3 = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(e0);
+      dfma3_throughput<8><<<bl, th>>>(out, iters, 1.0000001, 1e-9);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < b3) b3 = ms;
+    }
+    printf(", \"%s\": %.3f", cfg == 0 ? "fp64_dfma_3reg_tflops" : "fp64_dfma_3reg_12warps_tflops", 2.0 * 8 * iters * (double)bl * th / (b3 * 1e-3) / 1e12);
   }
   const char* names[5] = {"dfma", "sincos", "div", "dadd", "dmul"};
   for (int mode = 0; mode < 5; ++mode) {
