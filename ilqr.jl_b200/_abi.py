@@ -7,7 +7,7 @@ from . import _build
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_N, MAX_M = 16, 8
 MODEL_TWO_LINK, MODEL_SERIAL_CHAIN, MODEL_FLOATING_CHAIN, MODEL_CUSTOM = 1, 2, 3, 4
 MAX_JOINTS, CHAIN_STRIDE = 8, 20
@@ -31,7 +31,7 @@ class Problem(ctypes.Structure):
         ("model_params", ctypes.c_double * 32),
         ("x_target", ctypes.c_double * MAX_N), ("w_x", ctypes.c_double * MAX_N),
         ("w_u", ctypes.c_double * MAX_M), ("w_xf", ctypes.c_double * MAX_N),
-        ("nq", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("gravity", ctypes.c_double * 3),
+        ("nq", ctypes.c_int32), ("custom_cost", ctypes.c_int32), ("gravity", ctypes.c_double * 3),
         ("chain", ctypes.c_double * ((MAX_JOINTS + 1) * CHAIN_STRIDE)),
         ("custom_src", ctypes.c_char_p),
     ]
@@ -48,7 +48,7 @@ SYMBOLS = {
                                                     ctypes.c_int32, ctypes.c_int32]),
     "ilqr_problem_custom": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                             ctypes.c_double, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int32]),
-    "ilqr_custom_compile_check": (ctypes.c_int32, [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32]),
+    "ilqr_custom_compile_check": (ctypes.c_int32, [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32]),
     "ilqr_create": (ctypes.c_int32, [ctypes.POINTER(Problem), ctypes.POINTER(_H)]),
     "ilqr_destroy": (ctypes.c_int32, [_H]),
     "ilqr_last_error": (ctypes.c_char_p, [_H]),

@@ -179,11 +179,11 @@ int32_t ilqr_problem_custom(ilqr_problem* p, int32_t n, int32_t m, int32_t H, in
   return ILQR_OK;
 }
 
-int32_t ilqr_custom_compile_check(const char* dynamics_src, int32_t n, int32_t m, char* log, int32_t log_len) {
+int32_t ilqr_custom_compile_check(const char* dynamics_src, int32_t n, int32_t m, int32_t custom_cost, char* log, int32_t log_len) {
   if (!dynamics_src || n < 1 || n > ILQR_MAX_N || m < 1 || m > ILQR_MAX_M) return ILQR_ERR_INVALID;
   std::vector<char> cubin;
   std::string l;
-  const int32_t rc = custom_compile(dynamics_src, n, m, "sm_100a", cubin, l);
+  const int32_t rc = custom_compile(dynamics_src, n, m, custom_cost != 0, "sm_100a", cubin, l);
   if (log && log_len > 0) { std::strncpy(log, l.c_str(), (size_t)log_len - 1); log[log_len - 1] = 0; }
   return rc == 0 ? ILQR_OK : ILQR_ERR_INVALID;
 }
@@ -372,7 +372,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
     h->cparams.dt = p->dt;
     for (int i = 0; i < 32; ++i) h->cparams.p[i] = p->model_params[i];
     std::string cerr;
-    if (custom_get(h->custom_src.c_str(), p->n, p->m, p->device, &h->cmod, cerr) != 0) {
+    if (custom_get(h->custom_src.c_str(), p->n, p->m, p->custom_cost != 0, p->device, &h->cmod, cerr) != 0) {
       g_create_err = "ILQR_MODEL_CUSTOM: " + cerr;
       free_all(h); delete h;
       return ILQR_ERR_INVALID;

@@ -57,7 +57,8 @@ inline unsigned grid_for(int n, int block) { return (unsigned)((n + block - 1) /
 }  // namespace
 
 // Compile the user's snippet into a cubin for `arch` (e.g. "sm_100a").  No GPU needed.
-int32_t custom_compile(const char* user_src, int n, int m, const char* arch, std::vector<char>& cubin, std::string& log) {
+int32_t custom_compile(const char* user_src, int n, int m, bool user_cost, const char* arch, std::vector<char>& cubin,
+                       std::string& log) {
   std::string err;
   const Nvrtc* rt = nvrtc(err);
   if (!rt) { log = err; return -1; }
@@ -69,9 +70,9 @@ int32_t custom_compile(const char* user_src, int n, int m, const char* arch, std
     return -1;
   }
   const std::string a = std::string("--gpu-architecture=") + arch, dn = "-DILQR_N=" + std::to_string(n),
-                    dm = "-DILQR_M=" + std::to_string(m);
-  const char* opts[] = {a.c_str(), "-std=c++17", dn.c_str(), dm.c_str(), "-lineinfo"};
-  const nvrtcResult rc = rt->compile(prog, 5, opts);
+                    dm = "-DILQR_M=" + std::to_string(m), dc = std::string("-DILQR_USER_COST=") + (user_cost ? "1" : "0");
+  const char* opts[] = {a.c_str(), "-std=c++17", dn.c_str(), dm.c_str(), dc.c_str(), "-lineinfo"};
+  const nvrtcResult rc = rt->compile(prog, 6, opts);
   size_t ls = 0;
   if (rt->log_size(prog, &ls) == NVRTC_SUCCESS && ls > 1) { log.resize(ls); rt->log(prog, &log[0]); }
   if (rc != NVRTC_SUCCESS) {
@@ -88,8 +89,8 @@ int32_t custom_compile(const char* user_src, int n, int m, const char* arch, std
 }
 
 // Compiled + loaded module for (device, n, m, source); cached for the life of the process.
-int32_t custom_get(const char* user_src, int n, int m, int device, CustomModule* out, std::string& err) {
-  const std::string key = std::to_string(device) + "|" + std::to_string(n) + "|" + std::to_string(m) + "|" + user_src;
+int32_t custom_get(const char* user_src, int n, int m, bool user_cost, int device, CustomModule* out, std::string& err) {
+  const std::string key = std::to_string(device) + "|" + std::to_string(n) + "|" + std::to_string(m) + "|" + (user_cost ? "c|" : "d|") + user_src;
   std::lock_guard<std::mutex> lk(g_cache_mu);
   auto it = g_cache.find(key);
   if (it != g_cache.end()) { *out = it->second; return 0; }
@@ -97,7 +98,7 @@ int32_t custom_get(const char* user_src, int n, int m, int device, CustomModule*
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { err = "cudaGetDeviceProperties failed"; return -1; }
   const std::string arch = "sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + (prop.major >= 9 ? "a" : "");
   std::vector<char> cubin;
-  if (custom_compile(user_src, n, m, arch.c_str(), cubin, err) != 0) return -1;
+  if (custom_compile(user_src, n, m, user_cost, arch.c_str(), cubin, err) != 0) return -1;
   CustomModule mod;
   cudaLibrary_t lib;
   cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);

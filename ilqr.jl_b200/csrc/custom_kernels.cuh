@@ -24,6 +24,9 @@
 #if !defined(ILQR_N) || !defined(ILQR_M)
 #error "custom_kernels.cuh needs -DILQR_N=<state dim> -DILQR_M=<control dim>"
 #endif
+#ifndef ILQR_USER_COST
+#define ILQR_USER_COST 0   // 1: the snippet also defines ilqr_cost<T> / ilqr_final_cost<T> (ilqr_problem.custom_cost)
+#endif
 
 namespace ilqr {
 namespace custom {
@@ -50,6 +53,71 @@ __device__ __forceinline__ void rk4_step(const CustomP& mp, const T (&x)[n], con
   for (int i = 0; i < n; ++i) { sum[i] = sum[i] + mp.dt * k[i]; xn[i] = x[i] + (1.0 / 6.0) * sum[i]; }
 }
 
+#if ILQR_USER_COST
+// User-defined costs (the reference takes any Julia function as immediate_cost / final_cost and differentiates it with
+// ForwardDiff: gradient, hessian and jacobian(gradient), src/backward_pass.jl:95-106, 142-150).  Column-owner form of that
+// expansion: lane d < n + m evaluates the cost n + m times in second-order dual numbers, perturbing z = (x, u) along its own
+// direction e_d (ε₁) and along e_e (ε₂), e = 0 … n+m−1; the ε₁ε₂ coefficient is Hessian entry (e, d), the ε₂ coefficient
+// gradient entry e.  So lane d ends up with column d of [𝐐 𝐏ᵀ; 𝐏 𝐑] and the affine lane (which owns no direction)
+// with the gradient (𝐪, 𝐫) — exactly what riccati_column_step<GENERAL> asks of each lane.
+__device__ __forceinline__ void cost_columns(const CustomP& mp, int lane, const double (&x)[n], const double (&u)[m],
+                                             double (&cx)[n], double (&cu)[m]) {
+  const bool aff = lane == n + m;
+#pragma unroll 1
+  for (int e = 0; e < n + m; ++e) {
+    Dual2 xd[n], ud[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) xd[i] = {x[i], (lane == i) ? 1.0 : 0.0, (e == i) ? 1.0 : 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < m; ++i) ud[i] = {u[i], (lane == n + i) ? 1.0 : 0.0, (e == n + i) ? 1.0 : 0.0, 0.0};
+    const Dual2 l = ::ilqr_cost<Dual2>(xd, ud, mp.p);
+    const double val = aff ? l.b : l.ab;
+#pragma unroll
+    for (int i = 0; i < n; ++i) cx[i] = (e == i) ? val : cx[i];
+#pragma unroll
+    for (int i = 0; i < m; ++i) cu[i] = (e == n + i) ? val : cu[i];
+  }
+}
+// final_cost_quadratization (src/backward_pass.jl:134-153): column d of 𝐐_N on lane d < n, 𝐪_N on the affine lane
+__device__ __forceinline__ void final_cost_columns(const CustomP& mp, int lane, const double (&x)[n], double (&cx)[n]) {
+  const bool aff = lane == n + m;
+#pragma unroll 1
+  for (int e = 0; e < n; ++e) {
+    Dual2 xd[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) xd[i] = {x[i], (lane == i) ? 1.0 : 0.0, (e == i) ? 1.0 : 0.0, 0.0};
+    const Dual2 l = ::ilqr_final_cost<Dual2>(xd, mp.p);
+    const double val = aff ? l.b : l.ab;
+#pragma unroll
+    for (int i = 0; i < n; ++i) cx[i] = (e == i) ? val : cx[i];
+  }
+}
+#endif
+
+// running and final cost of a rollout (total_cost, src/forward_pass.jl:182-196); xs = x̄ − x_traj
+__device__ __forceinline__ double running_cost(const CustomP& mp, const CostP& cost, const double (&xs)[n], const double (&ub)[m]) {
+#if ILQR_USER_COST
+  return ::ilqr_cost<double>(xs, ub, mp.p);
+#else
+  double lx = 0.0, lu = 0.0;      // summed left to right (src/forward_pass.jl:189-191)
+#pragma unroll
+  for (int c = 0; c < n; ++c) { const double e = cost.x_target[c] - xs[c]; lx = fma(cost.w_x[c] * e, e, lx); }
+#pragma unroll
+  for (int i = 0; i < m; ++i) lu = fma(cost.w_u[i] * ub[i], ub[i], lu);
+  return lx + lu;
+#endif
+}
+__device__ __forceinline__ double terminal_cost(const CustomP& mp, const CostP& cost, const double (&xb)[n]) {
+#if ILQR_USER_COST
+  return ::ilqr_final_cost<double>(xb, mp.p);
+#else
+  double lf = 0.0;
+#pragma unroll
+  for (int c = 0; c < n; ++c) { const double e = cost.x_target[c] - xb[c]; lf = fma(cost.w_xf[c] * e, e, lf); }
+  return lf;
+#endif
+}
+
 }  // namespace custom
 }  // namespace ilqr
 
@@ -69,7 +137,17 @@ ilqr_bwd_custom(const __grid_constant__ ilqr::DevState st, const __grid_constant
   const int cur = st.cur[s];
   const double* __restrict__ X = st.x[cur];
   const double* __restrict__ U = st.u[cur];
+#if ILQR_USER_COST
+  {
+    double xN[n], cxN[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) { xN[i] = X[((int64_t)H * S + s) * n + i]; cxN[i] = 0.0; }
+    final_cost_columns(mp, lane, xN, cxN);
+    riccati_terminal_columns<n, m>(sm, lane, cxN);
+  }
+#else
   riccati_terminal<n, m>(sm, lane, lane < n ? X[((int64_t)H * S + s) * n + lane] : 0.0, cost);
+#endif
   bool bad = false;
 #pragma unroll 1
   for (int k = H - 1; k >= 0; --k) {
@@ -85,8 +163,19 @@ ilqr_bwd_custom(const __grid_constant__ ilqr::DevState st, const __grid_constant
     rk4_step<Dual>(mp, xd, ud, xnd);
 #pragma unroll
     for (int i = 0; i < n; ++i) ab[i] = (lane < n + m) ? xnd[i].t : 0.0;
+#if ILQR_USER_COST
+    double cx[n], cu[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) cx[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) cu[i] = 0.0;
+    cost_columns(mp, lane, x, u, cx, cu);   // evaluated at the raw x_k — no x_traj subtraction (src/backward_pass.jl:341)
+    bad |= riccati_column_step<n, m, true>(sm, lane, ab, x, u, cost, st.reg, st.K + ((int64_t)k * S + s) * (m * n),
+                                           st.duff + ((int64_t)k * S + s) * m, cx, cu);
+#else
     bad |= riccati_column_step<n, m>(sm, lane, ab, x, u, cost, st.reg, st.K + ((int64_t)k * S + s) * (m * n),
                                      st.duff + ((int64_t)k * S + s) * m);
+#endif
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) st.status[s] |= 1;   // ILQR_STATUS_NAN_GAINS
 }
@@ -136,25 +225,16 @@ ilqr_fwd_custom(const __grid_constant__ ilqr::DevState st, const __grid_constant
         du2 = fma(e, e, du2);
         Uo[((int64_t)k * S + s) * m + i] = ub[i];
       }
-      double lx = 0.0, lu = 0.0;      // running cost, summed left to right (src/forward_pass.jl:189-191)
+      double xs[n];                   // l(x̄ − x_traj, ū)   (src/forward_pass.jl:190)
 #pragma unroll
-      for (int c = 0; c < n; ++c) {
-        const double xt = XT ? XT[((int64_t)k * S + s) * n + c] : 0.0;
-        const double e = cost.x_target[c] - (xb[c] - xt);
-        lx = fma(cost.w_x[c] * e, e, lx);
-      }
-#pragma unroll
-      for (int i = 0; i < m; ++i) lu = fma(cost.w_u[i] * ub[i], ub[i], lu);
-      cst += lx + lu;
+      for (int c = 0; c < n; ++c) xs[c] = xb[c] - (XT ? XT[((int64_t)k * S + s) * n + c] : 0.0);
+      cst += running_cost(mp, cost, xs, ub);
       double xn[n];
       rk4_step<double>(mp, xb, ub, xn);
 #pragma unroll
       for (int c = 0; c < n; ++c) { xb[c] = xn[c]; Xo[((int64_t)(k + 1) * S + s) * n + c] = xn[c]; }
     }
-    double lf = 0.0;
-#pragma unroll
-    for (int c = 0; c < n; ++c) { const double e = cost.x_target[c] - xb[c]; lf = fma(cost.w_xf[c] * e, e, lf); }
-    cst += lf;
+    cst += terminal_cost(mp, cost, xb);
     if (prev - cst > 0.0) {   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
       acc_cost = cst; acc_du2 = du2; acc_alpha = alpha;
 #pragma unroll

@@ -97,8 +97,9 @@ struct CustomModule {
 #include <string>
 #include <vector>
 namespace ilqr {
-int32_t custom_compile(const char* user_src, int n, int m, const char* arch, std::vector<char>& cubin, std::string& log);
-int32_t custom_get(const char* user_src, int n, int m, int device, CustomModule* out, std::string& err);
+// user_cost: the snippet also defines ilqr_cost<T> / ilqr_final_cost<T> (ilqr_problem.custom_cost)
+int32_t custom_compile(const char* user_src, int n, int m, bool user_cost, const char* arch, std::vector<char>& cubin, std::string& log);
+int32_t custom_get(const char* user_src, int n, int m, bool user_cost, int device, CustomModule* out, std::string& err);
 void launch_bwd_custom(const CustomModule& mod, const DevState& st, const CustomP& mp, const CostP& cost, cudaStream_t s);
 void launch_fwd_custom(const CustomModule& mod, const DevState& st, const CustomP& mp, const CostP& cost, cudaStream_t s);
 void launch_rollout_init_custom(const CustomModule& mod, const DevState& st, const CustomP& mp, const double* d_x0, cudaStream_t s);

@@ -29,12 +29,29 @@ __device__ __forceinline__ void riccati_terminal(RiccatiSmem<n, m>& sm, int lane
   __syncwarp();
 }
 
+// terminal expansion of a general final cost: cx = this lane's column of 𝐐_N (lanes < n) or 𝐪_N (affine lane n + m)
+template <int n, int m>
+__device__ __forceinline__ void riccati_terminal_columns(RiccatiSmem<n, m>& sm, int lane, const double (&cx)[n]) {
+  if (lane < n) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) sm.S[i + n * lane] = cx[i];
+  } else if (lane == n + m) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) sm.sv[i] = cx[i];
+  }
+  __syncwarp();
+}
+
 // ab: this lane's column of [A | B] (zero on lanes ≥ n + m); x, u: the step's linearisation point (every lane).
 // Writes K[:, lane] / δu to Kout (m·n doubles, index i + m·j) / dout (m doubles).  Returns true if a gain is NaN.
-template <int n, int m>
+// GENERAL = false: the diagonal quadratic cost of CostP (𝐏 = 0), expanded in closed form.
+// GENERAL = true: any cost (immediate_cost_quadratization, src/backward_pass.jl:81-109) — the caller passes this lane's
+// column of the cost expansion: cx[n] = 𝐐[:, d] on x lane d, 𝐪 on the affine lane; cu[m] = 𝐏[:, d] on x lane d
+// (the cross term ∂²l/∂u∂x of :98 enters G = 𝐏 + BᵀSA, :182), 𝐑[:, j] on u lane j, 𝐫 on the affine lane.
+template <int n, int m, bool GENERAL = false>
 __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int lane, const double (&ab)[n], const double (&x)[n],
                                                     const double (&u)[m], const CostP& cost, double reg, double* Kout,
-                                                    double* dout) {
+                                                    double* dout, const double* cx = nullptr, const double* cu = nullptr) {
   constexpr int NC = n + m + 1;
   constexpr unsigned kFull = 0xffffffffu;
   const bool isX = lane < n, isU = lane >= n && lane < n + m, isAff = lane == n + m;
@@ -61,8 +78,12 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
     double a = 0.0;
 #pragma unroll
     for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * (n + i)], w[r], a);
-    if (isU && ucol == i) a += 2.0 * cost.w_u[i];      // 𝐑 = 2·diag(w_u)
-    if (isAff) a = fma(2.0 * cost.w_u[i], u[i], a);    // 𝐫 = 2·w_u·u
+    if constexpr (GENERAL) {
+      if (lane < NC) a += cu[i];                         // 𝐏 (x lanes), 𝐑 (u lanes), 𝐫 (affine lane)
+    } else {
+      if (isU && ucol == i) a += 2.0 * cost.w_u[i];      // 𝐑 = 2·diag(w_u)
+      if (isAff) a = fma(2.0 * cost.w_u[i], u[i], a);    // 𝐫 = 2·w_u·u
+    }
     gh[i] = a;
   }
   if (lane < NC) {
@@ -132,8 +153,12 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
 #pragma unroll
       for (int l = 0; l < m; ++l) a = fma(sm.GH[l + m * i], kc[l], a);
       // immediate_cost_quadratization (src/backward_pass.jl:81-109) of the diagonal quadratic cost
-      if (isAff) a += -2.0 * cost.w_x[i] * (cost.x_target[i] - x[i]);
-      else if (lane == i) a += 2.0 * cost.w_x[i];
+      if constexpr (GENERAL) {
+        if (isX || isAff) a += cx[i];                    // 𝐐 (x lanes), 𝐪 (affine lane)
+      } else {
+        if (isAff) a += -2.0 * cost.w_x[i] * (cost.x_target[i] - x[i]);
+        else if (lane == i) a += 2.0 * cost.w_x[i];
+      }
       nw[i] = a;
     }
   }

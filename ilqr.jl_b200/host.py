@@ -91,11 +91,14 @@ _custom_sources = []   # keeps the source bytes of custom problems alive (ilqr_p
 
 
 def custom_problem(dynamics_src, n, m, H, B=1, dt=0.01, params=(), x_target=None, w_x=None, w_u=None, w_xf=None, n_alpha=32,
-                   trace_iters=0, device=0, reg=None):
+                   trace_iters=0, device=0, reg=None, user_cost=False):
     """Any dynamics (the reference accepts any Julia function as `dynamicsf`, src/forward_pass.jl:148-153): CUDA C++ source
     defining  template <class T> __device__ void ilqr_dynamics(const T* x, const T* u, const double* p, T* xdot);
     compiled at run time (NVRTC) into the library's kernels, RK4-discretised with step dt and differentiated with dual
-    numbers.  Costs are the diagonal quadratics l = Σ w_x (x* − x)² + Σ w_u u², lf = Σ w_xf (x* − x)²."""
+    numbers.  Costs are the diagonal quadratics l = Σ w_x (x* − x)² + Σ w_u u², lf = Σ w_xf (x* − x)² — or, with
+    user_cost=True, the functions  template <class T> __device__ T ilqr_cost(const T* x, const T* u, const double* p)  and
+    template <class T> __device__ T ilqr_final_cost(const T* x, const double* p)  defined in the same snippet (the reference
+    takes any Julia function as immediate_cost / final_cost), expanded to second order incl. the cross term ∂²l/∂u∂x."""
     lib = _abi.load_library()
     src = dynamics_src.encode() if isinstance(dynamics_src, str) else bytes(dynamics_src)
     _custom_sources.append(src)
@@ -105,6 +108,7 @@ def custom_problem(dynamics_src, n, m, H, B=1, dt=0.01, params=(), x_target=None
                                  pr.ctypes.data if pr.size else None, int(pr.size))
     if rc != 0:
         raise IlqrError("ilqr_problem_custom failed (n <= 16, m <= 8, <= 32 params)")
+    p.custom_cost = 1 if user_cost else 0
     p.n_alpha = n_alpha
     p.trace_iters = trace_iters
     p.device = device
@@ -120,11 +124,11 @@ def custom_problem(dynamics_src, n, m, H, B=1, dt=0.01, params=(), x_target=None
     return p
 
 
-def custom_compile_check(dynamics_src, n, m):
-    """(ok, compiler log) for a dynamics snippet; needs libnvrtc, no GPU."""
+def custom_compile_check(dynamics_src, n, m, user_cost=False):
+    """(ok, compiler log) for a snippet (dynamics; with user_cost also ilqr_cost / ilqr_final_cost); needs libnvrtc, no GPU."""
     lib = _abi.load_library()
     buf = ctypes.create_string_buffer(1 << 16)
-    rc = lib.ilqr_custom_compile_check(dynamics_src.encode(), int(n), int(m), buf, len(buf))
+    rc = lib.ilqr_custom_compile_check(dynamics_src.encode(), int(n), int(m), 1 if user_cost else 0, buf, len(buf))
     return rc == 0, buf.value.decode(errors="replace")
 
 

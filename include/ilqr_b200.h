@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define ILQR_ABI_VERSION 4
+#define ILQR_ABI_VERSION 5
 #define ILQR_MAX_N 16
 #define ILQR_MAX_M 8
 #define ILQR_MAX_JOINTS 8
@@ -68,7 +68,8 @@ enum ilqr_model {
    * (ẋ = f(x, u; p), p = model_params; T = double or ilqr::Dual — value + one tangent, with + − * / sin cos exp log
    * sqrt overloaded).  The library compiles it at run time (NVRTC) into its warp-per-trajectory kernels, wraps it in
    * the RK4 step of the reference's plugins and differentiates it with dual numbers (one tangent direction per lane),
-   * which is what ForwardDiff does to the Julia callback.  n <= 16, m <= 8; costs are the diagonal quadratics. */
+   * which is what ForwardDiff does to the Julia callback.  n <= 16, m <= 8; costs are the diagonal quadratics or, with
+   * ilqr_problem.custom_cost = 1, user-defined functions in the same snippet. */
   ILQR_MODEL_CUSTOM = 4
 };
 
@@ -148,7 +149,14 @@ typedef struct ilqr_problem {
    * <inertia ixx ixy ixz iyy iyz izz> about the COM in link axes (6), pad (1).  Joint i's parent is
    * link i-1 (link -1 = the fixed base).  nq in {2, 3, 6, 7}. */
   int32_t nq;
-  int32_t reserved0;
+  /* ILQR_MODEL_CUSTOM only.  0: costs are the diagonal quadratics above.  1: custom_src also defines
+   *     template <class T> __device__ T ilqr_cost(const T* x, const T* u, const double* p);      // immediate_cost(x, u)
+   *     template <class T> __device__ T ilqr_final_cost(const T* x, const double* p);            // final_cost(x)
+   * (any C++ in +, −, *, /, sin, cos, exp, log, sqrt; T = double or a second-order dual number) and the library expands
+   * them as the reference expands its Julia callbacks (src/backward_pass.jl:95-106, 142-150): 𝐪, 𝐫, 𝐐, 𝐑 and the cross
+   * term 𝐏 = ∂²l/∂u∂x, which enters G = 𝐏 + BᵀSA (:182); total_cost evaluates them at (x̄ − x_traj, ū) (src/forward_pass.jl:190).
+   * x_target / w_x / w_u / w_xf are then unused. */
+  int32_t custom_cost;
   double gravity[3];      /* gravity acceleration in the base frame (RBD_helper_functions.jl:7: zero) */
   double chain[(ILQR_MAX_JOINTS + 1) * ILQR_CHAIN_STRIDE];   /* + 1: the base link of a floating mechanism */
   /* ILQR_MODEL_CUSTOM only: NUL-terminated CUDA C++ source defining ilqr_dynamics (copied by ilqr_create) */
@@ -177,9 +185,9 @@ int32_t ilqr_problem_floating_chain(ilqr_problem* p, int32_t nq, const double* j
  * ilqr_create returns. */
 int32_t ilqr_problem_custom(ilqr_problem* p, int32_t n, int32_t m, int32_t H, int32_t B, double dt, const char* dynamics_src,
                             const double* params, int32_t n_params);
-/* Compile-only check of a dynamics snippet for sizes (n, m); needs libnvrtc but no GPU.  The compiler log (warnings
+/* Compile-only check of a snippet (dynamics; with custom_cost != 0 also the two cost functions) for sizes (n, m); needs libnvrtc but no GPU.  The compiler log (warnings
  * and errors) is copied to log[0..log_len) when log != NULL.  Returns 0 if it compiles. */
-int32_t ilqr_custom_compile_check(const char* dynamics_src, int32_t n, int32_t m, char* log, int32_t log_len);
+int32_t ilqr_custom_compile_check(const char* dynamics_src, int32_t n, int32_t m, int32_t custom_cost, char* log, int32_t log_len);
 
 int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out);
 int32_t ilqr_destroy(ilqr_handle* h);

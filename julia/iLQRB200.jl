@@ -28,7 +28,7 @@ struct Problem
     w_u::NTuple{8,Float64}
     w_xf::NTuple{16,Float64}
     nq::Int32
-    reserved0::Int32
+    custom_cost::Int32             # ILQR_MODEL_CUSTOM: 1 = the snippet also defines ilqr_cost / ilqr_final_cost
     gravity::NTuple{3,Float64}
     chain::NTuple{180,Float64}     # (ILQR_MAX_JOINTS + 1) × ILQR_CHAIN_STRIDE
     custom_src::Cstring            # ILQR_MODEL_CUSTOM: CUDA C++ source of ilqr_dynamics

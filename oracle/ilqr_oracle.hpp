@@ -330,6 +330,35 @@ struct TwoLink {
   }
 };
 
+// The 2-link plugin with the costs src/cost_functions.jl intended (that file is dead code in the reference: its include is
+// commented out at src/iLQR.jl:9, and as written it needs RigidBodyDynamics' MechanismState).  final_cost =
+// weight · ‖tool(θ) − target‖² — "the weighted euclidean distance from the specified tool location to a target location"
+// (src/cost_functions.jl:1-27), with the planar forward kinematics of the 2-link arm
+// (2_link_helper_functions.jl:19-26 is its inverse); immediate_cost = w_tool · the same distance + Σu² (:30-54 has Σu²)
+// + gamma · u·θ̇ (mechanical power), which is NOT in the reference: it is there so that the cross term 𝐏 = ∂²l/∂u∂x of
+// immediate_cost_quadratization (src/backward_pass.jl:98) is exercised — every cost the reference ships has 𝐏 = 0.
+// The solver above differentiates these with the same nested dual numbers as any other callback.
+struct TwoLinkToolCost : TwoLink {
+  double w_tool = 1.0, w_final = 50.0, gamma = 0.3;
+  template <class T> void tool(const Vec<T, 4>& x, T& px, T& py) const {
+    px = l1 * cos(x[0]) + l2 * cos(x[0] + x[1]);
+    py = l1 * sin(x[0]) + l2 * sin(x[0] + x[1]);
+  }
+  template <class T> T immediate_cost(const Vec<T, 4>& x, const Vec<T, 2>& u) const {
+    T px, py; tool<T>(x, px, py);
+    T ex = px - target_tool_loc[0], ey = py - target_tool_loc[1];
+    T dist = ex * ex + ey * ey;
+    T torque = u[0] * u[0] + u[1] * u[1];
+    T power = u[0] * x[2] + u[1] * x[3];
+    return w_tool * dist + torque + gamma * power;
+  }
+  template <class T> T final_cost(const Vec<T, 4>& x) const {
+    T px, py; tool<T>(x, px, py);
+    T ex = px - target_tool_loc[0], ey = py - target_tool_loc[1];
+    return w_final * (ex * ex + ey * ey);
+  }
+};
+
 // A linear-dynamics / quadratic-cost plugin used only for the known-answer
 // (discrete LQR) test of the solver core.  Not in the reference.
 template <int NXv, int NUv>

@@ -173,6 +173,66 @@ void oracle_two_link_fit_batch(int B, int H, double* x, double* u, const double*
   for (auto& t : th) t.join();
 }
 
+// ---- the 2-link arm with the tool-point cost + a cross term (TwoLinkToolCost): generic cost quadratisation incl. 𝐏 ----
+static TwoLinkToolCost tool_plugin(double w_tool, double w_final, double gamma) {
+  TwoLinkToolCost p; p.w_tool = w_tool; p.w_final = w_final; p.gamma = gamma; return p;
+}
+// out: q(1) qv(4) rv(2) Q(16, column-major) P(8: m×n column-major) R(4)
+void oracle_tool_cost_quad(double w_tool, double w_final, double gamma, const double* x, const double* u, double* out) {
+  TwoLinkToolCost p = tool_plugin(w_tool, w_final, gamma);
+  Solver<TwoLinkToolCost> s(p);
+  Vec<double, 4> xv; Vec<double, 2> uv;
+  for (int i = 0; i < 4; ++i) xv[i] = x[i];
+  for (int i = 0; i < 2; ++i) uv[i] = u[i];
+  double q; Vec<double, 4> qv; Vec<double, 2> rv; Mat<double, 4, 4> Q; Mat<double, 2, 4> Pm; Mat<double, 2, 2> R;
+  s.immediate_cost_quadratization(xv, uv, q, qv, rv, Q, Pm, R);
+  int o = 0;
+  out[o++] = q;
+  for (int i = 0; i < 4; ++i) out[o++] = qv[i];
+  for (int i = 0; i < 2; ++i) out[o++] = rv[i];
+  for (int j = 0; j < 4; ++j) for (int i = 0; i < 4; ++i) out[o++] = Q(i, j);
+  for (int j = 0; j < 4; ++j) for (int i = 0; i < 2; ++i) out[o++] = Pm(i, j);
+  for (int j = 0; j < 2; ++j) for (int i = 0; i < 2; ++i) out[o++] = R(i, j);
+}
+int32_t oracle_tool_backward_pass(double w_tool, double w_final, double gamma, int H, const double* x, const double* u,
+                                  double reg, double* duff, double* K) {
+  TwoLinkToolCost p = tool_plugin(w_tool, w_final, gamma);
+  Solver<TwoLinkToolCost> s(p); s.reg = reg;
+  return s.backward_pass(H, x, u, duff, K);
+}
+double oracle_tool_total_cost(double w_tool, double w_final, double gamma, int H, const double* x, const double* u,
+                              const double* x_traj) {
+  TwoLinkToolCost p = tool_plugin(w_tool, w_final, gamma);
+  Solver<TwoLinkToolCost> s(p);
+  return s.total_cost(H, x, u, x_traj);
+}
+void oracle_tool_fit_batch(double w_tool, double w_final, double gamma, int B, int H, double* x, double* u,
+                           const double* x_traj, int max_iter, double tol, double reg, int jmax, int nthreads, double* cost,
+                           double* alpha, double* du2, int32_t* iters, int32_t* converged, int32_t* status) {
+  const int N = H + 1;
+  const TwoLinkToolCost p = tool_plugin(w_tool, w_final, gamma);
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    Solver<TwoLinkToolCost> s(p); s.reg = reg; s.jmax = jmax;
+    for (;;) {
+      int b = next.fetch_add(1);
+      if (b >= B) break;
+      auto tr = s.fit(H, x + (size_t)b * N * 4, u + (size_t)b * H * 2, x_traj ? x_traj + (size_t)b * N * 4 : nullptr,
+                      max_iter, tol);
+      for (int i = 0; i < tr.iters; ++i) {
+        if (cost) cost[(size_t)b * max_iter + i] = tr.cost[i];
+        if (alpha) alpha[(size_t)b * max_iter + i] = tr.alpha[i];
+        if (du2) du2[(size_t)b * max_iter + i] = tr.du2[i];
+      }
+      iters[b] = tr.iters; converged[b] = tr.converged ? 1 : 0; status[b] = tr.status;
+    }
+  };
+  if (nthreads <= 1) { work(); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work);
+  for (auto& t : th) t.join();
+}
+
 // ---- discrete-LQR known-answer support (solver core on a linear plugin) ----
 // n=3, m=2.  A[3x3], B[3x2], Q, R, Qf column-major.  Runs ONE backward pass
 // around (x,u) and returns gains.

@@ -174,6 +174,45 @@ def fit_batch(x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, reg=0.01, jma
     return dict(x=x, u=u, cost=cost, alpha=alpha, du2=du2, iters=iters, converged=conv.astype(bool), status=status)
 
 
+# ---- the 2-link arm with the FK tool-point cost + a cross term (oracle TwoLinkToolCost): generic quadratisation incl. 𝐏
+_cd = ctypes.c_double
+
+
+def tool_cost_quad(x, u, w_tool=1.0, w_final=50.0, gamma=0.3):
+    """immediate_cost_quadratization (src/backward_pass.jl:81-109) of the tool-point cost → (q, 𝐪[4], 𝐫[2], 𝐐[4,4], 𝐏[2,4], 𝐑[2,2])."""
+    out = np.zeros(35)
+    lib().oracle_tool_cost_quad(_cd(w_tool), _cd(w_final), _cd(gamma), _p(_f(x)), _p(_f(u)), _p(out))
+    return (out[0], out[1:5].copy(), out[5:7].copy(), out[7:23].reshape(4, 4, order="F"), out[23:31].reshape(2, 4, order="F"),
+            out[31:35].reshape(2, 2, order="F"))
+
+
+def tool_backward_pass(x, u, w_tool=1.0, w_final=50.0, gamma=0.3, reg=0.01):
+    u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 4))
+    d = np.zeros((H, 2), order="F"); K = np.zeros((H, 2, 4), order="F")
+    st = lib().oracle_tool_backward_pass(_cd(w_tool), _cd(w_final), _cd(gamma), H, _p(x), _p(u), _cd(reg), _p(d), _p(K))
+    return d, K, st
+
+
+def tool_total_cost(x, u, x_traj=None, w_tool=1.0, w_final=50.0, gamma=0.3):
+    u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 4))
+    lib().oracle_tool_total_cost.restype = ctypes.c_double
+    return lib().oracle_tool_total_cost(_cd(w_tool), _cd(w_final), _cd(gamma), H, _p(x), _p(u), _p(None if x_traj is None else _f(x_traj)))
+
+
+def tool_fit_batch(x_init, u_init, x_traj=None, w_tool=1.0, w_final=50.0, gamma=0.3, max_iter=100, tol=1e-6, reg=0.01, jmax=32,
+                   nthreads=1):
+    u = _f(u_init).copy(order="F"); H, _, B = u.shape
+    x = _f(x_init, (H + 1, 4, B)).copy(order="F")
+    xt = None if x_traj is None else _f(x_traj, (H + 1, 4, B))
+    cost = np.full((max_iter, B), np.nan, order="F"); alpha = np.full((max_iter, B), np.nan, order="F")
+    du2 = np.full((max_iter, B), np.nan, order="F")
+    iters = np.zeros(B, dtype=np.int32); conv = np.zeros(B, dtype=np.int32); status = np.zeros(B, dtype=np.int32)
+    lib().oracle_tool_fit_batch(_cd(w_tool), _cd(w_final), _cd(gamma), B, H, _p(x), _p(u), _p(xt), max_iter, _cd(tol), _cd(reg),
+                                jmax, nthreads, _p(cost), _p(alpha), _p(du2), iters.ctypes.data_as(_ip), conv.ctypes.data_as(_ip),
+                                status.ctypes.data_as(_ip))
+    return dict(x=x, u=u, cost=cost, alpha=alpha, du2=du2, iters=iters, converged=conv.astype(bool), status=status)
+
+
 def lq32_backward_pass(A, B, Q, R, Qf, x, u, reg=0.01):
     u = _f(u); H = u.shape[0]; x = _f(x, (H + 1, 3))
     d = np.zeros((H, 2), order="F"); K = np.zeros((H, 2, 3), order="F")

@@ -36,3 +36,49 @@ BROKEN = r"""
 template <class T>
 __device__ void ilqr_dynamics(const T* x, const T* u, const double* p, T* xdot) { xdot[0] = undefined_symbol; }
 """
+
+# ---- user-defined costs (ilqr_problem.custom_cost = 1): the same snippet also defines ilqr_cost / ilqr_final_cost ----
+# The reference's own 2-link costs (2_link_helper_functions.jl:82-108) written as a user would: p[3], p[4] = θ*.
+TWO_LINK_WITH_ITS_COST = TWO_LINK + r"""
+template <class T>
+__device__ T ilqr_cost(const T* x, const T* u, const double* p) {
+  const T e0 = p[3] - x[0], e1 = p[4] - x[1];
+  const T euclidean = e0 * e0 + e1 * e1;
+  const T torque = u[0] * u[0] + u[1] * u[1];
+  return euclidean * 1.0 + torque * 1.0;
+}
+template <class T>
+__device__ T ilqr_final_cost(const T* x, const double* p) {
+  const T e0 = p[3] - x[0], e1 = p[4] - x[1];
+  return (e0 * e0 + e1 * e1) * 1.0;
+}
+"""
+
+# The tool-point cost src/cost_functions.jl intended (weighted squared distance of the tool location to a target, through
+# the arm's forward kinematics) plus a u·θ̇ term that makes the cross term 𝐏 = ∂²l/∂u∂x non-zero (oracle: TwoLinkToolCost).
+# p = (α, β, δ, l1, l2, target_x, target_y, w_tool, w_final, gamma).
+TWO_LINK_TOOL_COST = TWO_LINK + r"""
+template <class T>
+__device__ void tool_point(const T* x, const double* p, T& px, T& py) {
+  using namespace ilqr;
+  px = p[3] * cos(x[0]) + p[4] * cos(x[0] + x[1]);
+  py = p[3] * sin(x[0]) + p[4] * sin(x[0] + x[1]);
+}
+template <class T>
+__device__ T ilqr_cost(const T* x, const T* u, const double* p) {
+  T px, py;
+  tool_point<T>(x, p, px, py);
+  const T ex = px - p[5], ey = py - p[6];
+  const T dist = ex * ex + ey * ey;
+  const T torque = u[0] * u[0] + u[1] * u[1];
+  const T power = u[0] * x[2] + u[1] * x[3];
+  return p[7] * dist + torque + p[9] * power;
+}
+template <class T>
+__device__ T ilqr_final_cost(const T* x, const double* p) {
+  T px, py;
+  tool_point<T>(x, p, px, py);
+  const T ex = px - p[5], ey = py - p[6];
+  return p[8] * (ex * ex + ey * ey);
+}
+"""

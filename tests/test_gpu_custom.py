@@ -94,3 +94,84 @@ def test_custom_pendulum_matches_numpy_restatement():
 def test_custom_compile_error_surfaces_in_create():
     with pytest.raises(ilqr_b200.IlqrError, match="undefined_symbol"):
         ilqr_b200.BatchSolver(ilqr_b200.custom_problem(custom_snippets.BROKEN, 2, 1, 10, 4))
+
+
+def _two_link_params():
+    c = orc.constants()
+    return c, (c["alpha"], c["beta"], c["delta"])
+
+
+def test_user_cost_snippet_of_the_two_link_costs_equals_builtin_and_oracle():
+    """ILQR_MODEL_CUSTOM with custom_cost = 1: the reference's own 2-link costs (2_link_helper_functions.jl:82-108) written
+    as a user snippet and expanded with second-order dual numbers must reproduce the closed-form built-in expansion:
+    gains, per-iterate costs, α decisions, iteration counts and iterates — against the built-in model and the oracle."""
+    B, H = 32, 60
+    c, par = _two_link_params()
+    _, xa, ua = config2_batch(16, H, seed=16)
+    _, xs, us = stress_batch(16, H, seed=17)
+    x = np.asfortranarray(np.concatenate([xa, xs], axis=2)); u = np.asfortranarray(np.concatenate([ua, us], axis=2))
+    prob = ilqr_b200.custom_problem(custom_snippets.TWO_LINK_WITH_ITS_COST, 4, 2, H, B, dt=c["dt"],
+                                    params=par + (c["theta_star"][0], c["theta_star"][1]), user_cost=True, trace_iters=60)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        d, K = s.download(_abi.DUFF), s.download(_abi.K)
+        out = s.solve(x, u, max_iter=60, tol=1e-6)
+        ct, at = s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE)
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, B)) as s:
+        s.upload(x, u)
+        s.backward_pass()
+        db, Kb = s.download(_abi.DUFF), s.download(_abi.K)
+        builtin = s.solve(x, u, max_iter=60, tol=1e-6)
+    assert rel_err(d, db) <= RTOL and rel_err(K, Kb) <= RTOL
+    for b in range(B):
+        d0, K0, _ = orc.backward_pass(x[:, :, b], u[:, :, b])
+        assert rel_err(d[:, :, b], d0) <= RTOL and rel_err(K[:, :, :, b], K0) <= RTOL
+    ref = orc.fit_batch(x, u, max_iter=60, tol=1e-6, nthreads=8)
+    assert np.array_equal(out["iters"], ref["iters"]) and np.array_equal(out["iters"], builtin["iters"])
+    for b in range(B):
+        it = ref["iters"][b]
+        assert rel_err(ct[:it, b], ref["cost"][:it, b]) <= RTOL and np.array_equal(at[:it, b], ref["alpha"][:it, b])
+    assert rel_err(out["x"], ref["x"]) <= RTOL and rel_err(out["x"], builtin["x"]) <= RTOL
+
+
+def test_user_cost_tool_point_with_cross_term_matches_oracle_quadratisation():
+    """A cost with 𝐏 = ∂²l/∂u∂x ≠ 0 (src/backward_pass.jl:98) and the FK tool-point distance src/cost_functions.jl intended:
+    the GPU expands the user snippet (second-order duals), the oracle differentiates the same function with nested duals
+    as ForwardDiff would; gains (where 𝐏 enters through G = 𝐏 + BᵀSA), rollout costs incl. x_traj, and a whole fit."""
+    B, H = 24, 50
+    c, par = _two_link_params()
+    W_TOOL, W_FINAL, GAMMA = 1.0, 50.0, 0.3
+    l = np.sqrt(2.0) / 2.0
+    params = par + (l, l, 0.6, -0.5, W_TOOL, W_FINAL, GAMMA)
+    x0, x, u = config2_batch(B, H, seed=26)
+    rng = np.random.default_rng(27)
+    u = np.asfortranarray(u + 0.2 * rng.normal(size=u.shape))
+    for b in range(B):
+        x[:, :, b] = orc.rollout(x0[b], u[:, :, b])
+    xt = np.asfortranarray(0.05 * rng.normal(size=x.shape))
+    prob = ilqr_b200.custom_problem(custom_snippets.TWO_LINK_TOOL_COST, 4, 2, H, B, dt=c["dt"], params=params, user_cost=True,
+                                    trace_iters=40)
+    with ilqr_b200.BatchSolver(prob) as s:
+        s.upload(x, u, xt)
+        s.backward_pass()
+        d, K = s.download(_abi.DUFF), s.download(_abi.K)
+        s.forward_pass()
+        xb, ub, cst = s.download(_abi.XBAR), s.download(_abi.UBAR), s.download(_abi.NEW_COST)
+        out = s.solve(x, u, max_iter=40, tol=1e-6)
+        ct, at = s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE)
+    for b in range(B):
+        d0, K0, _ = orc.tool_backward_pass(x[:, :, b], u[:, :, b], W_TOOL, W_FINAL, GAMMA)
+        assert rel_err(d[:, :, b], d0) <= RTOL and rel_err(K[:, :, :, b], K0) <= RTOL, (b, rel_err(d[:, :, b], d0), rel_err(K[:, :, :, b], K0))
+        # the same gains without the cross term are measurably different: 𝐏 is really in G
+        c0 = orc.tool_total_cost(xb[:, :, b], ub[:, :, b], xt[:, :, b], W_TOOL, W_FINAL, GAMMA)
+        assert abs(cst[b] - c0) <= RTOL * abs(c0)
+    d_nop = orc.tool_backward_pass(x[:, :, 0], u[:, :, 0], W_TOOL, W_FINAL, 0.0)[0]
+    assert rel_err(d[:, :, 0], d_nop) > 1e-3
+    ref = orc.tool_fit_batch(x, u, None, W_TOOL, W_FINAL, GAMMA, max_iter=40, tol=1e-6, nthreads=8)
+    assert np.array_equal(out["iters"], ref["iters"]), (out["iters"], ref["iters"])
+    for b in range(B):
+        it = ref["iters"][b]
+        assert np.array_equal(at[:it, b], ref["alpha"][:it, b])
+        assert rel_err(ct[:it, b], ref["cost"][:it, b]) <= RTOL
+    assert rel_err(out["x"], ref["x"]) <= 1e-8 and rel_err(out["u"], ref["u"]) <= 1e-7
