@@ -22,8 +22,12 @@
 // forward_pass + total_cost (src/forward_pass.jl:55-93, 182-196) → fwd_chain; the rigid-body plugin
 // (test/RBD_2_link_example/RBD_helper_functions.jl:48-116) → chain.cuh + CostP.
 #pragma once
+#include <algorithm>
+
 #include "chain.cuh"
+#include "chain_lin.cuh"
 #include "internal.cuh"
+#include "tma.cuh"
 #include "warp_riccati.cuh"
 
 namespace ilqr {
@@ -40,6 +44,7 @@ constexpr int kCW = ILQR_CHAIN_WARPS;   // warps (= trajectories) per block in b
                                   // 65.5 → 57.7 ms (configs[3], B = 16,384), 150 → 148 ms (configs[2])
 #endif
 constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2;
+inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -397,6 +402,159 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
 }
 
 // ---------------------------------------------------------------------------------------------
+// Split backward pass for fixed-base chains (the default; ILQR_CHAIN_ANALYTIC=0 keeps bwd_chain above):
+//   lin_chain — ONE THREAD per (trajectory, time step): the RK4 stage points and, per stage, the closed-form ∂ID/∂q,
+//               ∂ID/∂q̇ and the LDLᵀ factors of M (chain_lin.cuh) → scratch in HBM.  26 M independent work items at
+//               configs[3]; no lane repeats another's arithmetic.
+//   ric_chain — ONE WARP per trajectory, backwards in time: lane d applies M⁻¹ to its column of the stage Jacobians,
+//               chains the four stages into column d of [A | B] and owns column d in the Riccati step (warp_riccati.cuh).
+// Scratch layout: per (trajectory, block of 4 time steps) one contiguous block [stage·items + item][step mod 4] — four
+// neighbouring lin_chain lanes (consecutive time steps) fill a 32-byte sector together, and ric_chain fetches the block
+// with one TMA bulk copy per 4 steps.  The batch is processed in chunks so that the scratch stays below ~28 GB.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLinThreads = 64;
+
+template <int NQ> struct LinStore {   // per-link state in shared memory, [item][thread]
+  double* base;
+  __device__ __forceinline__ double get(int i, int o) const { return base[(i * chain_lin::kLinkDoubles + o) * kLinThreads]; }
+  __device__ __forceinline__ void put(int i, int o, double v) { base[(i * chain_lin::kLinkDoubles + o) * kLinThreads] = v; }
+};
+template <int NQ> struct LinOut {
+  double* blk; double* cur;   // blk: this (trajectory, 4-step block)'s scratch + (step mod 4)
+  __device__ __forceinline__ void stage(int s) { cur = blk + (size_t)s * chain_lin::StageItems<NQ>::kCount * 4; }
+  __device__ __forceinline__ void put(int item, double v) { cur[item * 4] = v; }
+};
+template <int NQ> constexpr int kLinBlockDoubles = 4 * chain_lin::StageItems<NQ>::kCount * 4;   // 4 stages × items × 4 time steps
+
+template <int NQ>
+__global__ void __launch_bounds__(kLinThreads)
+lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, double* __restrict__ scratch, int slot0,
+          int nchunk, int Hb) {
+  extern __shared__ __align__(16) double lin_smem[];
+  constexpr int n = 2 * NQ, m = NQ;
+  const long long t = (long long)blockIdx.x * kLinThreads + threadIdx.x;
+  const int Hp = Hb * 4;
+  const int sl = (int)(t / Hp), k = (int)(t - (long long)sl * Hp);
+  if (sl >= nchunk || k >= st.H) return;
+  const int s = slot0 + sl;
+  if (!st.active[s]) return;
+  const int cur = st.cur[s];
+  const double* xp = st.x[cur] + ((int64_t)k * st.S + s) * n;
+  const double* up = st.u[cur] + ((int64_t)k * st.S + s) * m;
+  double x[n], u[m];
+#pragma unroll
+  for (int i = 0; i < n; ++i) x[i] = xp[i];
+#pragma unroll
+  for (int i = 0; i < m; ++i) u[i] = up[i];
+  LinStore<NQ> store{lin_smem + threadIdx.x};
+  LinOut<NQ> out;
+  out.blk = scratch + ((size_t)sl * Hb + (k >> 2)) * kLinBlockDoubles<NQ> + (k & 3);
+  out.cur = out.blk;
+  chain_lin::step_derivatives<NQ>(cp, x, u, store, out);
+}
+
+template <int NQ> struct RicSmem : RiccatiSmem<2 * NQ, NQ> {
+  alignas(16) double blk[kLinBlockDoubles<NQ>];
+  double xs[2 * NQ], us[NQ];
+  alignas(8) uint64_t bar;
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(kCW * 32)
+ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, const __grid_constant__ CostP cost,
+          const double* __restrict__ scratch, int slot0, int nchunk, int Hb) {
+  using IT = chain_lin::StageItems<NQ>;
+  constexpr int n = 2 * NQ, m = NQ;
+  static_assert(n + m + 1 <= 32, "one warp must cover all column owners");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RicSmem<NQ>* smem = reinterpret_cast<RicSmem<NQ>*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sl = blockIdx.x * kCW + warp;
+  if (sl >= nchunk) return;
+  const int s = slot0 + sl;
+  if (!st.active[s]) return;   // warp-uniform
+  RicSmem<NQ>& sm = smem[warp];
+  const int64_t S = st.S;
+  const int H = st.H;
+  const int cur = st.cur[s];
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  if (lane == 0) { mbar_init(&sm.bar, 1); mbar_fence_init(); }
+  riccati_terminal<n, m>(sm, lane, lane < n ? X[((int64_t)H * S + s) * n + lane] : 0.0, cost);
+  uint32_t phase = 0;
+  bool bad = false;
+  const int udir = lane - n;
+#pragma unroll 1
+  for (int k = H - 1; k >= 0; --k) {
+    const int kk = k & 3;
+    const double xk = (lane < n) ? X[((int64_t)k * S + s) * n + lane] : 0.0;
+    const double uk = (lane < m) ? U[((int64_t)k * S + s) * m + lane] : 0.0;
+    __syncwarp();   // the previous step is done with xs / us / blk
+    if (lane < n) sm.xs[lane] = xk;
+    if (lane < m) sm.us[lane] = uk;
+    if (k == H - 1 || kk == 3) {   // a new block of four time steps
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's reads of the old block precede the copy
+        mbar_arrive_expect_tx(&sm.bar, (uint32_t)(kLinBlockDoubles<NQ> * sizeof(double)));
+        tma_load_1d(sm.blk, scratch + ((size_t)sl * Hb + (k >> 2)) * kLinBlockDoubles<NQ>,
+                    (uint32_t)(kLinBlockDoubles<NQ> * sizeof(double)), &sm.bar);
+      }
+      mbar_wait(&sm.bar, phase);
+      phase ^= 1u;
+    }
+    __syncwarp();
+    // column `lane` of [A | B]: tangent of the RK4 step along direction `lane` (linearize_dynamics, src/backward_pass.jl:25-40)
+    double ab[n];
+    {
+      double tp[n], tsum[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) { tp[i] = 0.0; tsum[i] = 0.0; }
+#pragma unroll 1
+      for (int stg = 0; stg < 4; ++stg) {
+        const double* it = sm.blk + (size_t)stg * IT::kCount * 4 + kk;
+        const double cin = (stg == 0) ? 0.0 : (stg == 3 ? 1.0 : 0.5), wgt = (stg == 1 || stg == 2) ? 2.0 : 1.0;
+        double dq[NQ], dv[NQ], y[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          dq[i] = fma(cin, tp[i], (lane == i) ? 1.0 : 0.0);
+          dv[i] = fma(cin, tp[NQ + i], (lane == NQ + i) ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {   // δu − ∂ID·(δq, δq̇)
+          double a = (udir == i) ? 1.0 : 0.0;
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) a = fma(-it[(IT::kJq + i * NQ + j) * 4], dq[j], fma(-it[(IT::kJv + i * NQ + j) * 4], dv[j], a));
+          y[i] = a;
+        }
+#pragma unroll
+        for (int i = 1; i < NQ; ++i)     // M⁻¹ = L⁻ᵀ D⁻¹ L⁻¹
+#pragma unroll
+          for (int j = 0; j < i; ++j) y[i] = fma(-it[IT::L(i, j) * 4], y[j], y[i]);
+#pragma unroll
+        for (int i = NQ - 1; i >= 0; --i) {
+          double a = y[i] * it[(IT::kDinv + i) * 4];
+#pragma unroll
+          for (int j = i + 1; j < NQ; ++j) a = fma(-it[IT::L(j, i) * 4], y[j], a);
+          y[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          tp[i] = cp.dt * dv[i]; tp[NQ + i] = cp.dt * y[i];
+          tsum[i] = fma(wgt, tp[i], tsum[i]); tsum[NQ + i] = fma(wgt, tp[NQ + i], tsum[NQ + i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < n; ++i) ab[i] = (lane < n + m) ? fma(1.0 / 6.0, tsum[i], (lane == i) ? 1.0 : 0.0) : 0.0;
+    }
+    const double (&x)[n] = sm.xs;
+    const double (&u)[m] = sm.us;
+    bad |= riccati_column_step<n, m>(sm, lane, ab, x, u, cost, st.reg, st.K + ((int64_t)k * S + s) * (m * n),
+                                     st.duff + ((int64_t)k * S + s) * m);
+  }
+  if (__any_sync(kFull, bad) && lane == 0) st.status[s] |= ST_NAN_GAINS;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Forward pass (src/forward_pass.jl:55-93), one thread per trajectory.  Candidates α = 1, ½, ¼ …
 // are rolled out in turn; a lane stops at the first one with prev − new > 0 (NaN ⇒ halve).
 // ---------------------------------------------------------------------------------------------
@@ -520,13 +678,30 @@ mpc_advance_chain(const __grid_constant__ ChainP cp, const double* __restrict__ 
   for (int i = 0; i < m; ++i) u_applied[(int64_t)t * m + i] = u[i];
 }
 
-inline int grid_for(int n, int block) { return (n + block - 1) / block; }
 
 template <int NQ, bool FL> void set_attr() {
   cudaFuncSetAttribute(bwd_chain<NQ, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(BwdSmem<NQ, FL>) * kCW));
 }
 template <int NQ, bool FL> void run_bwd(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s) {
   bwd_chain<NQ, FL><<<grid_for(st.nslots, kCW), kCW * 32, sizeof(BwdSmem<NQ, FL>) * kCW, s>>>(st, cp, cost);
+}
+template <int NQ> void set_attr_split() {
+  cudaFuncSetAttribute(lin_chain<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(sizeof(double) * kLinThreads * NQ * chain_lin::kLinkDoubles));
+  cudaFuncSetAttribute(ric_chain<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RicSmem<NQ>) * kCW));
+}
+// bytes of linearisation scratch per trajectory
+template <int NQ> size_t split_scratch_bytes(int H) { return (size_t)((H + 3) / 4) * kLinBlockDoubles<NQ> * sizeof(double); }
+template <int NQ>
+void run_bwd_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, int chunk, cudaStream_t s) {
+  const int Hb = (st.H + 3) / 4;
+  for (int slot0 = 0; slot0 < st.nslots; slot0 += chunk) {
+    const int cnt = std::min(chunk, st.nslots - slot0);
+    const long long items = (long long)cnt * Hb * 4;
+    lin_chain<NQ><<<(unsigned)((items + kLinThreads - 1) / kLinThreads), kLinThreads,
+                    sizeof(double) * kLinThreads * NQ * chain_lin::kLinkDoubles, s>>>(st, cp, scratch, slot0, cnt, Hb);
+    ric_chain<NQ><<<grid_for(cnt, kCW), kCW * 32, sizeof(RicSmem<NQ>) * kCW, s>>>(st, cp, cost, scratch, slot0, cnt, Hb);
+  }
 }
 template <int NQ, bool FL> void run_fwd(const DevState& st, const ChainP& cp, const CostP& cost, cudaStream_t s) {
   fwd_chain<NQ, FL><<<grid_for(st.nslots, 128), 128, 0, s>>>(st, cp, cost);

@@ -45,6 +45,10 @@ struct ilqr_handle {
   int32_t coop_below = 8192;   // ... and the warp-cooperative Riccati kernel when nslots <= this
   int32_t fwd_split_above = 24000;  // two-kernel forward pass (α = 1, then dense retries) when nslots > this
   bool pend_bwd = false, pend_fwd = false;
+  // split backward pass of the fixed-base rigid-body models (chain_lin.cuh): linearisation scratch for `lin_chunk` trajectories
+  double* lin_scratch = nullptr;
+  int32_t lin_chunk = 0;
+  bool chain_analytic = true;  // ILQR_CHAIN_ANALYTIC=0: the dual-number kernel bwd_chain
   // fused streaming rounds (kernels_round.cu)
   static constexpr int kMaxRing = 64;        // batches in flight in one stream
   unsigned long long* round_ctr = nullptr;   // device: [0] queue head, [1] retired, [2] block ticket

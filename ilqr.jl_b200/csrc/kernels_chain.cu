@@ -23,7 +23,19 @@ bool launch_mpc_advance_chain_fl(const ChainP&, const double*, double*, double*,
 
 void init_chain_attributes() {
   set_attr<2, false>(); set_attr<3, false>(); set_attr<6, false>(); set_attr<7, false>();
+  set_attr_split<2>(); set_attr_split<3>(); set_attr_split<6>(); set_attr_split<7>();
   init_chain_fl_attributes();
+}
+
+// split backward pass (fixed base): bytes of linearisation scratch one trajectory needs, and the pass itself over
+// [0, nslots) in chunks of `chunk` trajectories (scratch holds `chunk` trajectories)
+size_t chain_split_scratch_bytes(int nq, int H) {
+  ILQR_CHAIN_DISPATCH(nq, return split_scratch_bytes<NQ>(H);)
+  return 0;
+}
+void launch_bwd_chain_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, int chunk, cudaStream_t s) {
+  if (st.nslots <= 0) return;
+  ILQR_CHAIN_DISPATCH(cp.nq, run_bwd_split<NQ>(st, cp, cost, scratch, chunk, s);)
 }
 
 bool chain_supported(int nq, bool floating) { return floating ? (nq == 1 || nq == 2) : (nq == 2 || nq == 3 || nq == 6 || nq == 7); }

@@ -340,3 +340,30 @@ def test_stream_admission_on_a_rigid_body_model():
     assert np.array_equal(oi.cpu().numpy(), ref["iters"]) and np.array_equal(os_.cpu().numpy(), ref["status"])
     assert np.array_equal(oc.cpu().numpy(), ref["cost"])
     assert np.array_equal(ox.cpu().numpy().transpose(2, 1, 0), ref["x"]) and np.array_equal(ou.cpu().numpy().transpose(2, 1, 0), ref["u"])
+
+
+@pytest.mark.parametrize("nq,general,gravity,H", [(7, True, (0.2, -0.1, -9.81), 15), (3, True, (0.0, 0.0, -9.81), 13), (2, True, (0, 0, 0), 1),
+                                                 (6, False, (0.0, 0.0, -9.81), 6)])
+def test_split_backward_pass_chunked_and_against_the_dual_number_kernel(monkeypatch, nq, general, gravity, H):
+    """The fixed-base backward pass is lin_chain (closed-form inverse-dynamics derivatives, one thread per (trajectory,
+    time step)) + ric_chain (one warp per trajectory).  It must agree with the first version's dual-number kernel
+    (ILQR_CHAIN_ANALYTIC=0) and with the oracle to 1e-9, also when the batch is processed in several chunks (scratch
+    budget smaller than the batch) and for horizons that are not a multiple of the 4-step scratch blocks."""
+    B = 70
+    spec, prob, x0, x, u = _setup(nq, general, B, H, 900 + nq, gravity)
+    gains = {}
+    for name, env in (("dual", {"ILQR_CHAIN_ANALYTIC": "0"}), ("split", {}), ("split_chunked", {"ILQR_CHAIN_SCRATCH_GB": "1e-4"})):
+        for k in ("ILQR_CHAIN_ANALYTIC", "ILQR_CHAIN_SCRATCH_GB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with ilqr_b200.BatchSolver(prob) as s:
+            s.upload(x, u)
+            s.backward_pass()
+            gains[name] = (s.download(_abi.DUFF), s.download(_abi.K))
+            assert not np.any(s.download(_abi.STATUS))
+    assert np.array_equal(gains["split"][0], gains["split_chunked"][0]) and np.array_equal(gains["split"][1], gains["split_chunked"][1])
+    assert rel_err(gains["split"][0], gains["dual"][0]) <= RTOL and rel_err(gains["split"][1], gains["dual"][1]) <= RTOL
+    for b in range(0, B, 9):
+        d0, K0, _ = orc.chain_backward_pass(spec, x[:, :, b], u[:, :, b])
+        assert rel_err(gains["split"][0][:, :, b], d0) <= RTOL and rel_err(gains["split"][1][:, :, :, b], K0) <= RTOL

@@ -38,6 +38,29 @@ __global__ void dfma3_throughput(double* out, int iters, double a, double b) {
   if (s == 12345.678) out[0] = s;
 }
 
+// Operand mix of a DFMA stream, MODE: 0 = fma(acc, x_vec, b_uniform) (two vector register operands),
+// 1 = fma(x_i, y_j, acc) with x_i shared by two consecutive instructions (what a small matrix product issues: the
+// compiler can mark it .reuse), 2 = DMUL + DADD pairs on vector registers.
+template <int MODE>
+__global__ void dfma_mix_throughput(double* out, int iters, double a, double b) {
+  double acc[8], x[8], y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i] = threadIdx.x * 1e-3 + i; x[i] = a + 1e-12 * (threadIdx.x + i); y[i] = b + 1e-13 * (threadIdx.x * 3 + i); }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE == 0) acc[i] = fma(acc[i], x[(i + 3) % 8], b);
+      if (MODE == 1) acc[i] = fma(x[i / 2], y[(i + 5) % 8], acc[i]);
+      if (MODE == 2) acc[i] = (i & 1) ? acc[i] * x[(i + 3) % 8] : acc[i] + y[(i + 5) % 8];
+    }
+    if (it == iters - 7) { x[0] += 1e-15; y[1] += 1e-15; }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 __global__ void latency_kernel(double* out, long long* cycles, int iters, double a, double b, int mode) {
   double x = a;
   long long t0 = clock64();
@@ -94,6 +117,22 @@ int main() {
       if (rep > 0 && ms < b3) b3 = ms;
     }
     printf(", \"%s\": %.3f", cfg == 0 ? "fp64_dfma_3reg_tflops" : "fp64_dfma_3reg_12warps_tflops", 2.0 * 8 * iters * (double)bl * th / (b3 * 1e-3) / 1e12);
+  }
+  {
+    const char* mix[3] = {"fp64_dfma_2reg_tflops", "fp64_dfma_3reg_shared_operand_tflops", "fp64_dmul_dadd_2reg_slot_tflops"};
+    for (int mode = 0; mode < 3; ++mode) {
+      float bm = 1e30f;
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        if (mode == 0) dfma_mix_throughput<0><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        if (mode == 1) dfma_mix_throughput<1><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        if (mode == 2) dfma_mix_throughput<2><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < bm) bm = ms;
+      }
+      printf(", \"%s\": %.3f", mix[mode], 2.0 * 8 * iters * (double)blocks * threads / (bm * 1e-3) / 1e12);
+    }
   }
   const char* names[5] = {"dfma", "sincos", "div", "dadd", "dmul"};
   for (int mode = 0; mode < 5; ++mode) {
