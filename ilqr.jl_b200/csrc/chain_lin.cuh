@@ -16,7 +16,7 @@
 // the apparent change of velocity Ψ̇_j and acceleration c_j + Ψ̇_j × v_k seen from the rotated frame — the identities
 // behind the analytical inverse-dynamics derivatives of the spatial-algebra literature).  In block form D_k has only
 // two non-zero 3×3 blocks: D11 = −[n]× + [ω]×J − J[ω]× − [v]×[h]× − [h]×[v]×, D21 = −2[f]× with (n, f) = I_k v_k, so the
-// composite needs 9 + 3 numbers.  Validated against the oracle's dual-number linearisation on the host
+// composite needs 9 + 3 numbers.  Validated against the CPU checker's dual-number linearisation on the host
 // (tests/test_chain_lin_cpu.py compiles this header with g++) and on the GPU (tests/test_gpu_chain.py).
 //
 // Output per (trajectory, time step): for each RK4 stage the 126 numbers [∂ID/∂q (7×7) | ∂ID/∂q̇ (7×7) | L, 1/d of
