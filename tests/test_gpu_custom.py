@@ -183,5 +183,7 @@ def test_user_cost_tool_point_with_cross_term_matches_oracle_quadratisation():
     for b in np.flatnonzero(stable):
         it = ref["iters"][b]
         assert np.array_equal(at[:it, b], ref["alpha"][:it, b])
-        assert rel_err(ct[:it, b], ref["cost"][:it, b]) <= RTOL
+        nan = np.isnan(ref["cost"][:it, b])          # an exhausted line search records NaN on both sides (α = 0)
+        assert np.array_equal(np.isnan(ct[:it, b]), nan)
+        assert rel_err(ct[:it, b][~nan], ref["cost"][:it, b][~nan]) <= RTOL
     assert rel_err(out["x"][:, :, stable], ref["x"][:, :, stable]) <= 1e-8 and rel_err(out["u"][:, :, stable], ref["u"][:, :, stable]) <= 1e-7
