@@ -388,7 +388,10 @@ def fp64_peak_inrun(device):
         out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env).stdout.strip().splitlines()[-1]
         d = json.loads(out)
         return {"tflops": d["fp64_dfma_tflops"], "source": "tools/fp64_peak.cu DFMA micro-benchmark run inside this bench on this GPU",
-                "lat_dfma_cycles": d.get("lat_dfma_cycles"), "sm_mhz_before": float(q) if q else None}
+                "lat_dfma_cycles": d.get("lat_dfma_cycles"), "sm_mhz_before": float(q) if q else None,
+                # the DFMA rate depends on how many of the three sources are vector registers (register-file bandwidth)
+                "tflops_by_vector_register_sources": {"1": d["fp64_dfma_tflops"], "2": d.get("fp64_dfma_2reg_tflops"),
+                                                      "3": d.get("fp64_dfma_3reg_tflops")}}
     except Exception as e:
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
@@ -672,6 +675,22 @@ def run_b200(args):
     slot_tf = 2.0 * FP64_ROUND * per_s / 1e12 if (per_s and FP64_ROUND) else None
     true_tf = FP64_ROUND_TRUE * per_s / 1e12 if (per_s and FP64_ROUND_TRUE) else None
     ncu_round = ncu_file_metrics(NCU_ROUND_FILE, "round_lpt_two_link")
+    # Operand-limited ceiling: the FP64 pipe issues a warp instruction every 2.0 / 2.6 / 3.75 cycles with 1 / 2 / 3 vector-
+    # register sources (measured in-run); weighting the kernel's own instruction mix (SASS) gives the rate the pipe can
+    # sustain on THIS instruction stream — the ceiling that extra warps cannot lift.
+    operand = None
+    mixv = (sass.get(round_tag) or {}).get("fp64_by_vector_register_sources")
+    rates = fp64_peak.get("tflops_by_vector_register_sources") or {}
+    if mixv and all(rates.get(k) for k in ("1", "2", "3")) and slot_tf:
+        cyc = {k: 2.0 * rates["1"] / rates[k] for k in ("1", "2", "3")}
+        tot = sum(mixv.values())
+        mean_cyc = sum(mixv.get(k, 0) * cyc[k] for k in cyc) / tot
+        ceil_tf = rates["1"] * 2.0 / mean_cyc
+        operand = {"fp64_instructions_by_vector_register_sources": mixv, "pipe_cycles_per_instruction": cyc,
+                   "mean_pipe_cycles_per_fp64_instruction": mean_cyc, "operand_limited_peak_tflops": ceil_tf,
+                   "frac_of_operand_limited_peak": slot_tf / ceil_tf,
+                   "note": "tools/sass_operands.py + tools/fp64_peak.cu: a full-width launch needs slots/128 warps per scheduler x H steps x "
+                           "sum(count x cycles) pipe cycles; profiles/ncu_full_r1_round.txt shows 1.94 M elapsed cycles against 1.97 M predicted"}
     kname = "round_lpt_two_link<%s> (backward sweep + forward sweep + accept / converge test + retirement + admission; the only " \
             "kernel launched in the timed region)" % ("16, 3" if round_warps >= 16 else "12, 4")
     roofline = {
@@ -682,7 +701,7 @@ def run_b200(args):
         "true_flops_tflops": true_tf, "true_flops_frac": true_tf / fp64_peak_tf if (true_tf and fp64_peak_tf) else None,
         "true_flops_per_trajectory_step": FP64_ROUND_TRUE,
         "peak_source": fp64_peak["source"] + " (FP64 is not in MEASURED_PEAKS.json; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
-        "fp64_peak_detail": fp64_peak,
+        "fp64_peak_detail": fp64_peak, "operand_mix": operand,
         "hbm": {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_trajectory_iteration": ITER_BYTES},
         "traffic": ncu_round["traffic"] if ncu_round else None,

@@ -297,6 +297,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   if (const char* e = getenv("ILQR_COOP_BELOW")) h->coop_below = atoi(e);
   if (const char* e = getenv("ILQR_BURST_MAX")) h->burst_max = atoi(e);
   if (const char* e = getenv("ILQR_FWD_SPLIT_ABOVE")) h->fwd_split_above = atoi(e);
+  if (const char* e = getenv("ILQR_FWD_WPT_BELOW")) h->fwd_wpt_below = atoi(e);
   if (const char* e = getenv("ILQR_COMPACTION")) h->compaction = atoi(e) != 0;
   if (const char* e = getenv("ILQR_ROUND_WARPS")) h->round_warps = atoi(e);
   if (const char* e = getenv("ILQR_ROUND_SHIFT")) h->round_shift = atoi(e);
@@ -460,7 +461,13 @@ int32_t ilqr_mpc_step(ilqr_handle* h, int32_t max_iter, double tol, double* u_ap
 
 static int32_t backward_async(ilqr_handle* h) {
   if (!h->loaded) return fail(h, ILQR_ERR_STATE, "backward_pass before upload");
-  const bool split = !h->is_chain && !h->is_custom && h->st.nslots <= h->split_below;
+  // ilqr_variant: LANE_PER_TRAJ = the fused lane-per-trajectory kernel whatever the size; WARP_PER_TRAJ = time-parallel
+  // linearisation + the 4-lanes-per-trajectory cooperative Riccati kernel whatever the size; AUTO = by live-trajectory count
+  const int32_t variant = h->prob.variant;
+  const bool two_link_b = !h->is_chain && !h->is_custom;
+  const bool split = two_link_b && variant != ILQR_VARIANT_LANE_PER_TRAJ &&
+                     (variant == ILQR_VARIANT_WARP_PER_TRAJ || h->st.nslots <= h->split_below);
+  const bool coop = variant == ILQR_VARIANT_WARP_PER_TRAJ || h->st.nslots <= h->coop_below;
   if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][0], h->stream);
@@ -478,7 +485,7 @@ static int32_t backward_async(ilqr_handle* h) {
     launch_bwd_chain_split(h->st, h->chain, h->cp, h->lin_scratch, h->lin_chunk, h->stream);
   }
   else if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
-  else if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, h->st.nslots <= h->coop_below, h->stream);
+  else if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, coop, h->stream);
   else launch_bwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][1], h->stream);
   h->launches += split ? 2 : 1;
@@ -488,11 +495,15 @@ static int32_t backward_async(ilqr_handle* h) {
 
 static int32_t forward_async(ilqr_handle* h) {
   if (!h->have_gains) return fail(h, ILQR_ERR_STATE, "forward_pass before backward_pass");
-  const bool fsplit = !h->is_chain && !h->is_custom && h->st.nslots > h->fwd_split_above;
+  const bool two_link = !h->is_chain && !h->is_custom;
+  const bool wpt = two_link && h->prob.variant != ILQR_VARIANT_LANE_PER_TRAJ &&
+                   (h->prob.variant == ILQR_VARIANT_WARP_PER_TRAJ || h->st.nslots <= h->fwd_wpt_below);
+  const bool fsplit = two_link && !wpt && h->st.nslots > h->fwd_split_above;
   const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
   cudaEventRecord(h->ev[e][2], h->stream);
   if (h->is_custom) launch_fwd_custom(h->cmod, h->st, h->cparams, h->cp, h->stream);
   else if (h->is_chain) launch_fwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
+  else if (wpt) launch_fwd_wpt_two_link(h->st, h->mp, h->cp, h->stream);
   else if (fsplit) launch_fwd_split_two_link(h->st, h->mp, h->cp, h->stream);
   else launch_fwd_lpt_two_link(h->st, h->mp, h->cp, h->stream);
   cudaEventRecord(h->ev[e][3], h->stream);

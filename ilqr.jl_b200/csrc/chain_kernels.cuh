@@ -408,9 +408,9 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
 //               configs[3]; no lane repeats another's arithmetic.
 //   ric_chain — ONE WARP per trajectory, backwards in time: lane d applies M⁻¹ to its column of the stage Jacobians,
 //               chains the four stages into column d of [A | B] and owns column d in the Riccati step (warp_riccati.cuh).
-// Scratch layout: per (trajectory, block of 4 time steps) one contiguous block [stage·items + item][step mod 4] — four
-// neighbouring lin_chain lanes (consecutive time steps) fill a 32-byte sector together, and ric_chain fetches the block
-// with one TMA bulk copy per 4 steps.  The batch is processed in chunks so that the scratch stays below ~28 GB.
+// Scratch layout: per (trajectory, block of 4 time steps) one contiguous block [stage][pair][step mod 4][2] — four
+// neighbouring lin_chain lanes (consecutive time steps) fill two 32-byte sectors together with one 16-byte store each,
+// ric_chain fetches the block with one TMA bulk copy per 4 steps and reads it back in 16-byte broadcast loads.  The batch is processed in chunks so that the scratch stays below ~28 GB.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLinThreads = 64;
 
@@ -420,11 +420,13 @@ template <int NQ> struct LinStore {   // per-link state in shared memory, [item]
   __device__ __forceinline__ void put(int i, int o, double v) { base[(i * chain_lin::kLinkDoubles + o) * kLinThreads] = v; }
 };
 template <int NQ> struct LinOut {
-  double* blk; double* cur;   // blk: this (trajectory, 4-step block)'s scratch + (step mod 4)
-  __device__ __forceinline__ void stage(int s) { cur = blk + (size_t)s * chain_lin::StageItems<NQ>::kCount * 4; }
-  __device__ __forceinline__ void put(int item, double v) { cur[item * 4] = v; }
+  double* blk; double* cur;   // blk: this (trajectory, 4-step block)'s scratch + 2·(step mod 4)
+  __device__ __forceinline__ void stage(int s) { cur = blk + (size_t)s * chain_lin::StageItems<NQ>::kPairs * 8; }
+  __device__ __forceinline__ void put_pair(int pair, double v0, double v1) {
+    *reinterpret_cast<double2*>(cur + pair * 8) = make_double2(v0, v1);
+  }
 };
-template <int NQ> constexpr int kLinBlockDoubles = 4 * chain_lin::StageItems<NQ>::kCount * 4;   // 4 stages × items × 4 time steps
+template <int NQ> constexpr int kLinBlockDoubles = 4 * chain_lin::StageItems<NQ>::kPairs * 8;   // 4 stages × pairs × 4 time steps × 2
 
 template <int NQ>
 __global__ void __launch_bounds__(kLinThreads)
@@ -448,7 +450,7 @@ lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   for (int i = 0; i < m; ++i) u[i] = up[i];
   LinStore<NQ> store{lin_smem + threadIdx.x};
   LinOut<NQ> out;
-  out.blk = scratch + ((size_t)sl * Hb + (k >> 2)) * kLinBlockDoubles<NQ> + (k & 3);
+  out.blk = scratch + ((size_t)sl * Hb + (k >> 2)) * kLinBlockDoubles<NQ> + 2 * (k & 3);
   out.cur = out.blk;
   chain_lin::step_derivatives<NQ>(cp, x, u, store, out);
 }
@@ -511,7 +513,7 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
       for (int i = 0; i < n; ++i) { tp[i] = 0.0; tsum[i] = 0.0; }
 #pragma unroll 1
       for (int stg = 0; stg < 4; ++stg) {
-        const double* it = sm.blk + (size_t)stg * IT::kCount * 4 + kk;
+        const double2* it = reinterpret_cast<const double2*>(sm.blk) + (size_t)stg * IT::kPairs * 4 + kk;   // pair p at it[4p]
         const double cin = (stg == 0) ? 0.0 : (stg == 3 ? 1.0 : 0.5), wgt = (stg == 1 || stg == 2) ? 2.0 : 1.0;
         double dq[NQ], dv[NQ], y[NQ];
 #pragma unroll
@@ -523,18 +525,24 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
         for (int i = 0; i < NQ; ++i) {   // δu − ∂ID·(δq, δq̇)
           double a = (udir == i) ? 1.0 : 0.0;
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) a = fma(-it[(IT::kJq + i * NQ + j) * 4], dq[j], fma(-it[(IT::kJv + i * NQ + j) * 4], dv[j], a));
+          for (int j = 0; j < NQ; ++j) {
+            const double2 J = it[4 * (i * NQ + j)];
+            a = fma(-J.x, dq[j], fma(-J.y, dv[j], a));
+          }
           y[i] = a;
         }
+        double ld[2 * IT::kLDPairs];     // L and 1/d, read once for both substitutions
+#pragma unroll
+        for (int p = 0; p < IT::kLDPairs; ++p) { const double2 t = it[4 * (NQ * NQ + p)]; ld[2 * p] = t.x; ld[2 * p + 1] = t.y; }
 #pragma unroll
         for (int i = 1; i < NQ; ++i)     // M⁻¹ = L⁻ᵀ D⁻¹ L⁻¹
 #pragma unroll
-          for (int j = 0; j < i; ++j) y[i] = fma(-it[IT::L(i, j) * 4], y[j], y[i]);
+          for (int j = 0; j < i; ++j) y[i] = fma(-ld[IT::L(i, j)], y[j], y[i]);
 #pragma unroll
         for (int i = NQ - 1; i >= 0; --i) {
-          double a = y[i] * it[(IT::kDinv + i) * 4];
+          double a = y[i] * ld[IT::Dinv(i)];
 #pragma unroll
-          for (int j = i + 1; j < NQ; ++j) a = fma(-it[IT::L(j, i) * 4], y[j], a);
+          for (int j = i + 1; j < NQ; ++j) a = fma(-ld[IT::L(j, i)], y[j], a);
           y[i] = a;
         }
 #pragma unroll

@@ -19,7 +19,7 @@
 // composite needs 9 + 3 numbers.  Validated against the CPU checker's dual-number linearisation on the host
 // (tests/test_chain_lin_cpu.py compiles this header with g++) and on the GPU (tests/test_gpu_chain.py).
 //
-// Output per (trajectory, time step): for each RK4 stage the 126 numbers [∂ID/∂q (7×7) | ∂ID/∂q̇ (7×7) | L, 1/d of
+// Output per (trajectory, time step): for each RK4 stage the 126 numbers [(∂ID/∂q, ∂ID/∂q̇) pairs (7×7) | L, 1/d of
 // M = L·diag(d)·Lᵀ], consumed by ric_chain (chain_kernels.cuh), which applies M⁻¹, chains the four stages and runs the
 // Riccati step, one warp per trajectory.  Per-link state (S, Ψ̇, c, I: 28 doubles per link) lives in shared memory,
 // [item][thread]; link velocities and accelerations are re-derived on the way back (v_{i−1} = v_i − S_i q̇_i).
@@ -92,11 +92,13 @@ template <class St> ILQR_CL si ldI(const St& st, int i) {
   return I;
 }
 
-// items of one stage's output
+// One stage's output, as PAIRS of doubles (the consumer fetches 16 bytes at a time): pair i·NQ + j = (∂ID_i/∂q_j,
+// ∂ID_i/∂q̇_j); behind them the strictly lower triangle of L (row-major packed: (i, j < i) at i(i−1)/2 + j) and 1/d,
+// NQ(NQ+1)/2 doubles, two per pair.
 template <int NQ> struct StageItems {
-  static constexpr int kJq = 0, kJv = NQ * NQ, kL = 2 * NQ * NQ, kDinv = kL + NQ * (NQ - 1) / 2, kCount = kDinv + NQ;
-  // strictly lower triangle of L, row-major packed: (i, j < i) at kL + i(i−1)/2 + j
-  static ILQR_CLC int L(int i, int j) { return kL + i * (i - 1) / 2 + j; }
+  static constexpr int kLD = NQ * (NQ + 1) / 2, kLDPairs = (kLD + 1) / 2, kPairs = NQ * NQ + kLDPairs, kCount = 2 * kPairs;
+  static ILQR_CLC int L(int i, int j) { return i * (i - 1) / 2 + j; }         // index into the L / 1/d block
+  static ILQR_CLC int Dinv(int i) { return NQ * (NQ - 1) / 2 + i; }
 };
 
 // One RK4 stage at (q, qd) with control u: v̇ → vdot, the stage's items → out.put(item, value).
@@ -200,11 +202,17 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
       }
     }
   }
+  {
+    double ld[2 * IT::kLDPairs];
+    ld[2 * IT::kLDPairs - 1] = 0.0;
 #pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    out.put(IT::kDinv + i, dinv[i]);
+    for (int i = 0; i < NQ; ++i) {
+      ld[IT::Dinv(i)] = dinv[i];
 #pragma unroll
-    for (int j = 0; j < i; ++j) out.put(IT::L(i, j), M[i][j]);
+      for (int j = 0; j < i; ++j) ld[IT::L(i, j)] = M[i][j];
+    }
+#pragma unroll
+    for (int p = 0; p < IT::kLDPairs; ++p) out.put_pair(NQ * NQ + p, ld[2 * p], ld[2 * p + 1]);
   }
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {   // L y = rhs
@@ -279,12 +287,8 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
 #pragma unroll 1
       for (int j = 0; j <= i; ++j) {
         const sv Sj = ld6(st, j, 0), Pj = ld6(st, j, 6), Cj = ld6(st, j, 12);
-        out.put(IT::kJq + i * NQ + j, dot6(U, Cj) + dot(T.a, Pj.a));
-        out.put(IT::kJv + i * NQ + j, 2.0 * dot6(U, Pj) + dot(T.a, Sj.a));
-        if (j < i) {
-          out.put(IT::kJq + j * NQ + i, dot6(Sj, gv));
-          out.put(IT::kJv + j * NQ + i, dot6(Sj, hq));
-        }
+        out.put_pair(i * NQ + j, dot6(U, Cj) + dot(T.a, Pj.a), 2.0 * dot6(U, Pj) + dot(T.a, Sj.a));
+        if (j < i) out.put_pair(j * NQ + i, dot6(Sj, gv), dot6(Sj, hq));
       }
       v = fma6(-qd[i], S, v);
       a = fma6(-vdot[i], S, fma6(-qd[i], Pd, a));

@@ -44,6 +44,8 @@ struct ilqr_handle {
                                // 2-4 measured no faster on B200, bench9 vs bench9_b1; 0 = size-based policy; ILQR_BURST_MAX)
   int32_t coop_below = 8192;   // ... and the warp-cooperative Riccati kernel when nslots <= this
   int32_t fwd_split_above = 24000;  // two-kernel forward pass (α = 1, then dense retries) when nslots > this
+  int32_t fwd_wpt_below = 0;        // warp-per-trajectory forward pass (all step sizes at once) when nslots <= this under
+                                    // ILQR_VARIANT_AUTO (ILQR_FWD_WPT_BELOW); always under ILQR_VARIANT_WARP_PER_TRAJ
   bool pend_bwd = false, pend_fwd = false;
   // split backward pass of the fixed-base rigid-body models (chain_lin.cuh): linearisation scratch for `lin_chunk` trajectories
   double* lin_scratch = nullptr;

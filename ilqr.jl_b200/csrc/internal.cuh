@@ -19,6 +19,8 @@ void launch_bwd_split_two_link(const DevState& st, const TwoLinkP& mp, const Cos
 // two-kernel forward pass (α = 1 for all, then a dense retry kernel) for large active sets
 void launch_fwd_split_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
+// warp per trajectory, all step sizes α = 2⁻ʲ at once (one per lane) — the north_star mapping; bit-identical results
+void launch_fwd_wpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s);
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0 /*[n][S] BF*/,
                                   cudaStream_t s);
 // max_iter: per-trajectory iteration cap applied on device (streaming mode); the batched fit loop counts on the host

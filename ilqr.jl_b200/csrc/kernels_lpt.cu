@@ -771,6 +771,113 @@ fwd_retry_two_link(const __grid_constant__ DevState st, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward pass in the mapping BASELINE.json's north_star sketches: ONE WARP per trajectory, the parallel line search
+// "evaluating all step sizes at once".  The reference tries α = 1, ½, ¼ … one after the other
+// (src/forward_pass.jl:70-86); here lane j rolls out α = 2⁻ʲ, all 32 candidates in the time of one, and a ballot picks
+// the largest accepted α — the same answer the sequential loop gives, and the same arithmetic per candidate (fwd_step), so
+// the result is bit-identical to fwd_lpt_two_link.  Lane 0 writes its (α = 1) candidate while it rolls; if another
+// lane wins (≈ 1 % of the iterations on config 2), the winner's step size is rolled out once more on every lane and
+// lane 0 writes that one.  Operands of a step are the same on all lanes: one broadcast load each, prefetched a step ahead.
+// Pays where the batch no longer fills the machine and the line search is active (ILQR_VARIANT_WARP_PER_TRAJ, or
+// automatically below ILQR_FWD_WPT_BELOW live trajectories): a lane-per-trajectory warp walks the horizon once more for
+// every halving any of its 32 trajectories needs.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_XT>
+__global__ void __launch_bounds__(kBlock)
+fwd_wpt_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp, const __grid_constant__ CostP cp) {
+  constexpr unsigned kFullMask = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * kWarps + warp;
+  if (s >= st.nslots || !st.active[s]) return;   // warp-uniform
+  const int64_t S = st.S;
+  const int H = st.H;
+  const int cur = st.cur[s];
+  const double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  double* __restrict__ Xo = st.x[cur ^ 1];
+  double* __restrict__ Uo = st.u[cur ^ 1];
+  const double* __restrict__ XT = st.xtraj;
+  const double prev = st.prev_cost[s];
+  double x0[NX];
+  ldv<NX>(X + (int64_t)s * NX, x0);
+
+  // one candidate per lane; `store`: this lane writes x̄, ū
+  auto rollout = [&](double alpha, bool store, double& cost, double& du2, bool& nan_x) {
+    double xb[NX], xk[NX], uk[NU], dk[NU], Kk[NK];
+    cost = 0.0; du2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) { xb[c] = x0[c]; xk[c] = x0[c]; }
+    if (store) stv<NX>(Xo + (int64_t)s * NX, xb);
+    ldv<NU>(U + (int64_t)s * NU, uk);
+    ldv<NU>(st.duff + (int64_t)s * NU, dk);
+    ldv<NK>(st.K + (int64_t)s * NK, Kk);
+#pragma unroll 1
+    for (int k = 0; k < H; ++k) {
+      double xk1[NX], uk1[NU], dk1[NU], Kk1[NK], xt[NX];
+      const int kn = (k + 1 < H) ? k + 1 : k;
+      ldv<NX>(X + ((int64_t)kn * S + s) * NX, xk1);
+      ldv<NU>(U + ((int64_t)kn * S + s) * NU, uk1);
+      ldv<NU>(st.duff + ((int64_t)kn * S + s) * NU, dk1);
+      ldv<NK>(st.K + ((int64_t)kn * S + s) * NK, Kk1);
+      if (HAS_XT) ldv<NX>(XT + ((int64_t)k * S + s) * NX, xt);
+      else {
+#pragma unroll
+        for (int c = 0; c < NX; ++c) xt[c] = 0.0;
+      }
+      double ub[NU];
+      fwd_step(mp, cp, alpha, xk, uk, dk, Kk, xt, xb, ub, cost, du2);
+      if (store) {
+        stv<NU>(Uo + ((int64_t)k * S + s) * NU, ub);
+        stv<NX>(Xo + ((int64_t)(k + 1) * S + s) * NX, xb);
+      }
+#pragma unroll
+      for (int c = 0; c < NX; ++c) xk[c] = xk1[c];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) { uk[c] = uk1[c]; dk[c] = dk1[c]; }
+#pragma unroll
+      for (int c = 0; c < NK; ++c) Kk[c] = Kk1[c];
+    }
+    double lf = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - xb[c]; lf = fma(cp.w_xf[c] * e, e, lf); }
+    cost += lf;
+    nan_x = false;
+#pragma unroll
+    for (int c = 0; c < NX; ++c) nan_x |= isnan(xb[c]);
+  };
+
+  double acc_cost = qnan(), acc_du2 = qnan(), acc_alpha = 0.0;
+  bool bad = false;
+#pragma unroll 1
+  for (int base = 0; base < st.n_alpha; base += 32) {
+    const int j = base + lane;
+    const double alpha = __longlong_as_double((long long)(1023 - (j < 1000 ? j : 1000)) << 52);   // 2⁻ʲ
+    double cost, du2;
+    bool nan_x;
+    rollout(alpha, lane == 0 && base == 0, cost, du2, nan_x);
+    const bool accept = j < st.n_alpha && (prev - cost > 0.0);   // NaN compares false ⇒ halve (src/forward_pass.jl:79-82)
+    const unsigned m = __ballot_sync(kFullMask, accept);
+    if (m) {
+      const int w = __ffs(m) - 1;   // the largest accepted step size
+      acc_cost = __shfl_sync(kFullMask, cost, w); acc_du2 = __shfl_sync(kFullMask, du2, w);
+      acc_alpha = __shfl_sync(kFullMask, alpha, w);
+      bad = __shfl_sync(kFullMask, (int)nan_x, w) != 0;
+      if (w != 0 || base != 0) {    // lane 0 did not hold the winner: roll it out once more, lane 0 writes
+        double c2, d2;
+        bool n2;
+        rollout(acc_alpha, lane == 0, c2, d2, n2);
+      }
+      break;
+    }
+  }
+  if (lane == 0) {
+    st.bar[s] = cur ^ 1;
+    if (bad) st.status[s] |= ST_NAN_ROLLOUT;
+    st.new_cost[s] = acc_cost; st.alpha[s] = acc_alpha; st.du2[s] = acc_du2;
+  }
+}
+
 // Open-loop rollout of u from x0 (animate_2_link.jl:14-16): x[cur] filled.  x0: [slot][4].
 __global__ void __launch_bounds__(kBlock)
 rollout_init_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp,
@@ -1105,6 +1212,11 @@ void launch_fwd_lpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP
   if (st.nslots <= 0) return;
   if (st.xtraj) fwd_lpt_two_link<true><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<true>::kSmem, s>>>(st, mp, cp, st.n_alpha);
   else fwd_lpt_two_link<false><<<grid_for(st.nslots, kBlock), kBlock, FwdCfg<false>::kSmem, s>>>(st, mp, cp, st.n_alpha);
+}
+void launch_fwd_wpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP& cp, cudaStream_t s) {
+  if (st.nslots <= 0) return;
+  if (st.xtraj) fwd_wpt_two_link<true><<<grid_for(st.nslots, kWarps), kBlock, 0, s>>>(st, mp, cp);
+  else fwd_wpt_two_link<false><<<grid_for(st.nslots, kWarps), kBlock, 0, s>>>(st, mp, cp);
 }
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0, cudaStream_t s) {
   rollout_init_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, d_x0);

@@ -10,12 +10,13 @@
 namespace ilqr {
 
 template <int n, int m> struct RiccatiSmem {
-  double S[n * n];              // value Hessian, column-major
-  double AB[n * (n + m)];       // [A | B], column-major
-  double GH[m * (n + m + 1)];   // [G | H | g], unregularised
-  double Kd[m * (n + 1)];       // [K | δu]
-  double U[m * m];              // upper factor of H_reg (row-permuted)
-  double sv[n];
+  // 16-byte aligned so that the broadcast reads of a column (even n: pairs of rows) can be 128-bit loads
+  alignas(16) double S[n * n];              // value Hessian, column-major
+  alignas(16) double AB[n * (n + m)];       // [A | B], column-major
+  alignas(16) double GH[m * (n + m + 1)];   // [G | H | g], unregularised
+  alignas(16) double Kd[m * (n + 1)];       // [K | δu]
+  alignas(16) double U[m * m];              // upper factor of H_reg (row-permuted)
+  alignas(16) double sv[n];
 };
 
 // terminal expansion: final_cost_quadratization (src/backward_pass.jl:134-153); xN = component `lane` of x_N

@@ -92,11 +92,15 @@ enum ilqr_error {
   ILQR_ERR_STATE = -4       /* call out of order (e.g. forward before backward) */
 };
 
-/* kernel mapping */
+/* kernel mapping of the batch path for ILQR_MODEL_TWO_LINK (ilqr_problem.variant, ilqr_set_variant); every mapping
+ * returns bit-identical results (tests/test_gpu_parity.py) */
 enum ilqr_variant {
-  ILQR_VARIANT_AUTO = 0,           /* choose by active-trajectory count */
-  ILQR_VARIANT_LANE_PER_TRAJ = 1,  /* one thread per trajectory, batch-fastest layout (throughput) */
-  ILQR_VARIANT_WARP_PER_TRAJ = 2   /* one warp per trajectory, time-fastest layout (latency) */
+  ILQR_VARIANT_AUTO = 0,           /* choose by live-trajectory count (ilqr_set_tuning thresholds) */
+  ILQR_VARIANT_LANE_PER_TRAJ = 1,  /* one thread per trajectory end to end: fused backward kernel, sequential step-size
+                                    * halving inside the forward kernel (throughput mapping) */
+  ILQR_VARIANT_WARP_PER_TRAJ = 2   /* the mapping BASELINE.json sketches — lanes cooperate on one trajectory: time-parallel
+                                    * linearisation, 4-lane cooperative Riccati recursion, and a forward pass with one WARP per
+                                    * trajectory whose 32 lanes roll out all step sizes α = 2^-j at once (latency mapping) */
 };
 
 /* which array ilqr_download / ilqr_device_ptr refers to */
@@ -213,8 +217,10 @@ int32_t ilqr_upload_gains(ilqr_handle* h, const double* duff, const double* K);
 int32_t ilqr_backward_pass(ilqr_handle* h);
 
 /* forward_pass (src/forward_pass.jl:55-93) on every active trajectory: closed-
- * loop rollout, all step sizes α = 2^-j evaluated, largest α with
- * prev_cost - new_cost > 0 kept → x̄, ū, new_cost, alpha, du2 on device.
+ * loop rollout with α = 1, then α/2, α/4 … for the trajectories whose candidate
+ * was rejected (sequentially per trajectory, or all 2^-j at once on the lanes of a
+ * warp under ILQR_VARIANT_WARP_PER_TRAJ); the largest α = 2^-j, j < n_alpha, with
+ * prev_cost - new_cost > 0 is kept → x̄, ū, new_cost, alpha, du2 on device.
  * prev_cost: host [B] or NULL to use the device-resident value (Inf after upload). */
 int32_t ilqr_forward_pass(ilqr_handle* h, const double* prev_cost);
 

@@ -19,7 +19,7 @@ template <int NQ> struct HostStore {
 template <int NQ> struct HostOut {
   double* base; double* cur;
   void stage(int s) { cur = base + s * chain_lin::StageItems<NQ>::kCount; }
-  void put(int item, double v) { cur[item] = v; }
+  void put_pair(int pair, double v0, double v1) { cur[2 * pair] = v0; cur[2 * pair + 1] = v1; }
 };
 
 // [A | B] (n × (n+m), column-major) of the RK4 step from the four stages' items — the arithmetic of ric_chain's lanes
@@ -36,13 +36,14 @@ template <int NQ> void assemble(const ChainP& cp, const double* items, double* A
       for (int i = 0; i < NQ; ++i) { dq[i] = cin * tp[i] + xi0[i]; dv[i] = cin * tp[NQ + i] + xi0[NQ + i]; }
       for (int i = 0; i < NQ; ++i) {
         double a = (col - n == i) ? 1.0 : 0.0;
-        for (int j = 0; j < NQ; ++j) a -= it[IT::kJq + i * NQ + j] * dq[j] + it[IT::kJv + i * NQ + j] * dv[j];
+        for (int j = 0; j < NQ; ++j) a -= it[2 * (i * NQ + j)] * dq[j] + it[2 * (i * NQ + j) + 1] * dv[j];
         y[i] = a;
       }
-      for (int i = 0; i < NQ; ++i) for (int j = 0; j < i; ++j) y[i] -= it[IT::L(i, j)] * y[j];
+      const double* ld = it + 2 * NQ * NQ;
+      for (int i = 0; i < NQ; ++i) for (int j = 0; j < i; ++j) y[i] -= ld[IT::L(i, j)] * y[j];
       for (int i = NQ - 1; i >= 0; --i) {
-        double a = y[i] * it[IT::kDinv + i];
-        for (int j = i + 1; j < NQ; ++j) a -= it[IT::L(j, i)] * y[j];
+        double a = y[i] * ld[IT::Dinv(i)];
+        for (int j = i + 1; j < NQ; ++j) a -= ld[IT::L(j, i)] * y[j];
         y[i] = a;
       }
       for (int i = 0; i < NQ; ++i) {

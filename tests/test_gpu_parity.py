@@ -635,3 +635,37 @@ def test_config1_single_trajectory_H900_against_anchor_and_oracle():
         st.wait(st.submit(np.asfortranarray(x.reshape(H + 1, 4, 1)), np.asfortranarray(u.reshape(H, 2, 1)), out))
     assert out["iters"][0] == it and np.array_equal(out["x"][:, :, 0], xs) and np.array_equal(out["u"][:, :, 0], us)
     assert abs(out["cost"][0] - anchor["last_cost"]) < RTOL_CONVERGED_COST * anchor["last_cost"]
+
+
+@pytest.mark.parametrize("with_xtraj", [False, True])
+def test_mapping_variants_are_bit_identical(with_xtraj):
+    """ilqr_variant: AUTO, LANE_PER_TRAJ (one thread per trajectory) and WARP_PER_TRAJ (BASELINE's sketch: lanes cooperate
+    on a trajectory — time-parallel linearisation, 4-lane Riccati, and a forward pass whose 32 lanes roll out all step
+    sizes α = 2⁻ʲ at once instead of halving sequentially, src/forward_pass.jl:70-86) must return the same bits: gains,
+    accepted step sizes, costs, candidates, whole fits.  Stress inputs, so that step sizes down to 2⁻⁵ are selected;
+    n_alpha = 40 > 32 exercises the second block of candidates of the warp-wide search."""
+    B, H = 160, 60
+    _, xa, ua = config2_batch(B // 2, H, seed=51)
+    _, xb_, ub_ = stress_batch(B // 2, H, seed=52)
+    x = np.asfortranarray(np.concatenate([xa, xb_], axis=2)); u = np.asfortranarray(np.concatenate([ua, ub_], axis=2))
+    xt = np.asfortranarray(0.05 * np.random.default_rng(53).normal(size=x.shape)) if with_xtraj else None
+    res = {}
+    for v in (_abi.VARIANT_AUTO, _abi.VARIANT_LANE_PER_TRAJ, _abi.VARIANT_WARP_PER_TRAJ):
+        with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, B, n_alpha=40, trace_iters=40, variant=v)) as s:
+            s.upload(x, u, xt)
+            s.backward_pass(); s.forward_pass()
+            first = (s.download(_abi.DUFF), s.download(_abi.K), s.download(_abi.XBAR), s.download(_abi.UBAR), s.download(_abi.NEW_COST),
+                     s.download(_abi.ALPHA), s.download(_abi.DU2))
+            # a forward pass whose α = 1 candidate is rejected everywhere: the search must find the same smaller step
+            prev = first[4] * (1 - 1e-7)
+            s.forward_pass(prev)
+            second = (s.download(_abi.XBAR), s.download(_abi.ALPHA), s.download(_abi.NEW_COST))
+            s.upload(x, u, xt)
+            s.fit(40, 1e-6)
+            res[v] = first + second + (s.download(_abi.X), s.download(_abi.U), s.download(_abi.ITERS), s.download(_abi.STATUS),
+                                       s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE))
+    ref = res[_abi.VARIANT_AUTO]
+    assert np.sum(ref[8] < 1.0) > B // 2 and np.nanmin(ref[-1]) <= 2.0 ** -3
+    for v in (_abi.VARIANT_LANE_PER_TRAJ, _abi.VARIANT_WARP_PER_TRAJ):
+        for a, b in zip(ref, res[v]):
+            assert np.array_equal(a, b, equal_nan=True), v
