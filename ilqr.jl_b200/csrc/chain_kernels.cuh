@@ -408,25 +408,31 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
 //               configs[3]; no lane repeats another's arithmetic.
 //   ric_chain — ONE WARP per trajectory, backwards in time: lane d applies M⁻¹ to its column of the stage Jacobians,
 //               chains the four stages into column d of [A | B] and owns column d in the Riccati step (warp_riccati.cuh).
-// Scratch layout: per (trajectory, block of 4 time steps) one contiguous block [stage][pair][step mod 4][2] — four
-// neighbouring lin_chain lanes (consecutive time steps) fill two 32-byte sectors together with one 16-byte store each,
-// ric_chain fetches the block with one TMA bulk copy per 4 steps and reads it back in 16-byte broadcast loads.  The batch is processed in chunks so that the scratch stays below ~28 GB.
+// Scratch layout: per (trajectory, block of kLinSteps time steps) one contiguous block [stage][pair][step in block][2] —
+// neighbouring lin_chain lanes (consecutive time steps) fill a 32-byte sector together with one 16-byte store each,
+// ric_chain fetches the block with one TMA bulk copy and reads it back in 16-byte broadcast loads.  The batch is processed in chunks so that the scratch stays below ~28 GB.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLinThreads = 64;
+constexpr int kLinSteps = 2;    // time steps per scratch block (two neighbouring lin_chain lanes fill one 32-byte sector)
 
-template <int NQ> struct LinStore {   // per-link state in shared memory, [item][thread]
-  double* base;
-  __device__ __forceinline__ double get(int i, int o) const { return base[(i * chain_lin::kLinkDoubles + o) * kLinThreads]; }
-  __device__ __forceinline__ void put(int i, int o, double v) { base[(i * chain_lin::kLinkDoubles + o) * kLinThreads] = v; }
+template <int NQ> struct LinStore {   // per-link state in shared memory, [pair of items][thread][2]: 128-bit accesses
+  double2* base;                      // = smem + threadIdx.x
+  __device__ __forceinline__ void get2(int i, int o, double& v0, double& v1) const {
+    const double2 t = base[((i * chain_lin::kLinkDoubles + o) >> 1) * kLinThreads];
+    v0 = t.x; v1 = t.y;
+  }
+  __device__ __forceinline__ void put2(int i, int o, double v0, double v1) {
+    base[((i * chain_lin::kLinkDoubles + o) >> 1) * kLinThreads] = make_double2(v0, v1);
+  }
 };
 template <int NQ> struct LinOut {
   double* blk; double* cur;   // blk: this (trajectory, 4-step block)'s scratch + 2·(step mod 4)
-  __device__ __forceinline__ void stage(int s) { cur = blk + (size_t)s * chain_lin::StageItems<NQ>::kPairs * 8; }
+  __device__ __forceinline__ void stage(int s) { cur = blk + (size_t)s * chain_lin::StageItems<NQ>::kPairs * (2 * kLinSteps); }
   __device__ __forceinline__ void put_pair(int pair, double v0, double v1) {
-    *reinterpret_cast<double2*>(cur + pair * 8) = make_double2(v0, v1);
+    *reinterpret_cast<double2*>(cur + pair * (2 * kLinSteps)) = make_double2(v0, v1);
   }
 };
-template <int NQ> constexpr int kLinBlockDoubles = 4 * chain_lin::StageItems<NQ>::kPairs * 8;   // 4 stages × pairs × 4 time steps × 2
+template <int NQ> constexpr int kLinBlockDoubles = 4 * chain_lin::StageItems<NQ>::kPairs * kLinSteps * 2;   // 4 stages × pairs × steps × 2
 
 template <int NQ>
 __global__ void __launch_bounds__(kLinThreads)
@@ -435,7 +441,7 @@ lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   extern __shared__ __align__(16) double lin_smem[];
   constexpr int n = 2 * NQ, m = NQ;
   const long long t = (long long)blockIdx.x * kLinThreads + threadIdx.x;
-  const int Hp = Hb * 4;
+  const int Hp = Hb * kLinSteps;
   const int sl = (int)(t / Hp), k = (int)(t - (long long)sl * Hp);
   if (sl >= nchunk || k >= st.H) return;
   const int s = slot0 + sl;
@@ -448,9 +454,9 @@ lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   for (int i = 0; i < n; ++i) x[i] = xp[i];
 #pragma unroll
   for (int i = 0; i < m; ++i) u[i] = up[i];
-  LinStore<NQ> store{lin_smem + threadIdx.x};
+  LinStore<NQ> store{reinterpret_cast<double2*>(lin_smem) + threadIdx.x};
   LinOut<NQ> out;
-  out.blk = scratch + ((size_t)sl * Hb + (k >> 2)) * kLinBlockDoubles<NQ> + 2 * (k & 3);
+  out.blk = scratch + ((size_t)sl * Hb + (k / kLinSteps)) * kLinBlockDoubles<NQ> + 2 * (k % kLinSteps);
   out.cur = out.blk;
   chain_lin::step_derivatives<NQ>(cp, x, u, store, out);
 }
@@ -488,17 +494,17 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   const int udir = lane - n;
 #pragma unroll 1
   for (int k = H - 1; k >= 0; --k) {
-    const int kk = k & 3;
+    const int kk = k % kLinSteps;
     const double xk = (lane < n) ? X[((int64_t)k * S + s) * n + lane] : 0.0;
     const double uk = (lane < m) ? U[((int64_t)k * S + s) * m + lane] : 0.0;
     __syncwarp();   // the previous step is done with xs / us / blk
     if (lane < n) sm.xs[lane] = xk;
     if (lane < m) sm.us[lane] = uk;
-    if (k == H - 1 || kk == 3) {   // a new block of four time steps
+    if (k == H - 1 || kk == kLinSteps - 1) {   // a new block of time steps
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's reads of the old block precede the copy
         mbar_arrive_expect_tx(&sm.bar, (uint32_t)(kLinBlockDoubles<NQ> * sizeof(double)));
-        tma_load_1d(sm.blk, scratch + ((size_t)sl * Hb + (k >> 2)) * kLinBlockDoubles<NQ>,
+        tma_load_1d(sm.blk, scratch + ((size_t)sl * Hb + (k / kLinSteps)) * kLinBlockDoubles<NQ>,
                     (uint32_t)(kLinBlockDoubles<NQ> * sizeof(double)), &sm.bar);
       }
       mbar_wait(&sm.bar, phase);
@@ -513,7 +519,7 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
       for (int i = 0; i < n; ++i) { tp[i] = 0.0; tsum[i] = 0.0; }
 #pragma unroll 1
       for (int stg = 0; stg < 4; ++stg) {
-        const double2* it = reinterpret_cast<const double2*>(sm.blk) + (size_t)stg * IT::kPairs * 4 + kk;   // pair p at it[4p]
+        const double2* it = reinterpret_cast<const double2*>(sm.blk) + (size_t)stg * IT::kPairs * kLinSteps + kk;   // pair p at it[kLinSteps·p]
         const double cin = (stg == 0) ? 0.0 : (stg == 3 ? 1.0 : 0.5), wgt = (stg == 1 || stg == 2) ? 2.0 : 1.0;
         double dq[NQ], dv[NQ], y[NQ];
 #pragma unroll
@@ -526,14 +532,14 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
           double a = (udir == i) ? 1.0 : 0.0;
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {
-            const double2 J = it[4 * (i * NQ + j)];
+            const double2 J = it[kLinSteps * (i * NQ + j)];
             a = fma(-J.x, dq[j], fma(-J.y, dv[j], a));
           }
           y[i] = a;
         }
         double ld[2 * IT::kLDPairs];     // L and 1/d, read once for both substitutions
 #pragma unroll
-        for (int p = 0; p < IT::kLDPairs; ++p) { const double2 t = it[4 * (NQ * NQ + p)]; ld[2 * p] = t.x; ld[2 * p + 1] = t.y; }
+        for (int p = 0; p < IT::kLDPairs; ++p) { const double2 t = it[kLinSteps * (NQ * NQ + p)]; ld[2 * p] = t.x; ld[2 * p + 1] = t.y; }
 #pragma unroll
         for (int i = 1; i < NQ; ++i)     // M⁻¹ = L⁻ᵀ D⁻¹ L⁻¹
 #pragma unroll
@@ -699,13 +705,13 @@ template <int NQ> void set_attr_split() {
   cudaFuncSetAttribute(ric_chain<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RicSmem<NQ>) * kCW));
 }
 // bytes of linearisation scratch per trajectory
-template <int NQ> size_t split_scratch_bytes(int H) { return (size_t)((H + 3) / 4) * kLinBlockDoubles<NQ> * sizeof(double); }
+template <int NQ> size_t split_scratch_bytes(int H) { return (size_t)((H + kLinSteps - 1) / kLinSteps) * kLinBlockDoubles<NQ> * sizeof(double); }
 template <int NQ>
 void run_bwd_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, int chunk, cudaStream_t s) {
-  const int Hb = (st.H + 3) / 4;
+  const int Hb = (st.H + kLinSteps - 1) / kLinSteps;
   for (int slot0 = 0; slot0 < st.nslots; slot0 += chunk) {
     const int cnt = std::min(chunk, st.nslots - slot0);
-    const long long items = (long long)cnt * Hb * 4;
+    const long long items = (long long)cnt * Hb * kLinSteps;
     lin_chain<NQ><<<(unsigned)((items + kLinThreads - 1) / kLinThreads), kLinThreads,
                     sizeof(double) * kLinThreads * NQ * chain_lin::kLinkDoubles, s>>>(st, cp, scratch, slot0, cnt, Hb);
     ric_chain<NQ><<<grid_for(cnt, kCW), kCW * 32, sizeof(RicSmem<NQ>) * kCW, s>>>(st, cp, cost, scratch, slot0, cnt, Hb);

@@ -75,21 +75,26 @@ ILQR_CL void iadd(si& A, const si& B) {
   for (int k = 0; k < 6; ++k) A.J[k] += B.J[k];
 }
 
-// per-link storage: S (0..5), Ψ̇ (6..11), c (12..17), inertia (18..27); St::at(link, item) is an lvalue
+// per-link storage: S (0..5), Ψ̇ (6..11), c (12..17), inertia (18..27)
 constexpr int kLinkDoubles = 28;
+// (St::get2 / put2 move an aligned pair (o even) — one 128-bit shared-memory access on the device)
 template <class St> ILQR_CL sv ld6(const St& st, int i, int o) {
-  return {{st.get(i, o), st.get(i, o + 1), st.get(i, o + 2)}, {st.get(i, o + 3), st.get(i, o + 4), st.get(i, o + 5)}};
+  double a0, a1, a2, a3, a4, a5;
+  st.get2(i, o, a0, a1); st.get2(i, o + 2, a2, a3); st.get2(i, o + 4, a4, a5);
+  return {{a0, a1, a2}, {a3, a4, a5}};
 }
 template <class St> ILQR_CL void st6(St& st, int i, int o, sv x) {
-  st.put(i, o, x.a.x); st.put(i, o + 1, x.a.y); st.put(i, o + 2, x.a.z);
-  st.put(i, o + 3, x.b.x); st.put(i, o + 4, x.b.y); st.put(i, o + 5, x.b.z);
+  st.put2(i, o, x.a.x, x.a.y); st.put2(i, o + 2, x.a.z, x.b.x); st.put2(i, o + 4, x.b.y, x.b.z);
 }
 template <class St> ILQR_CL si ldI(const St& st, int i) {
   si I;
-  I.m = st.get(i, 18); I.h = {st.get(i, 19), st.get(i, 20), st.get(i, 21)};
-#pragma unroll
-  for (int k = 0; k < 6; ++k) I.J[k] = st.get(i, 22 + k);
+  st.get2(i, 18, I.m, I.h.x); st.get2(i, 20, I.h.y, I.h.z);
+  st.get2(i, 22, I.J[0], I.J[1]); st.get2(i, 24, I.J[2], I.J[3]); st.get2(i, 26, I.J[4], I.J[5]);
   return I;
+}
+template <class St> ILQR_CL void stI(St& st, int i, const si& I) {
+  st.put2(i, 18, I.m, I.h.x); st.put2(i, 20, I.h.y, I.h.z);
+  st.put2(i, 22, I.J[0], I.J[1]); st.put2(i, 24, I.J[2], I.J[3]); st.put2(i, 26, I.J[4], I.J[5]);
 }
 
 // One stage's output, as PAIRS of doubles (the consumer fetches 16 bytes at a time): pair i·NQ + j = (∂ID_i/∂q_j,
@@ -155,9 +160,7 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
       v = fma6(qd[i], S, v);
       a0 = fma6(qd[i], Pd, a0);
       st6(st, i, 0, S); st6(st, i, 6, Pd);
-      st.put(i, 18, I.m); st.put(i, 19, I.h.x); st.put(i, 20, I.h.y); st.put(i, 21, I.h.z);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) st.put(i, 22 + k, I.J[k]);
+      stI(st, i, I);
     }
   }
   const sv v_tip = v, a0_tip = a0;

@@ -13,8 +13,8 @@ using namespace ilqr;
 namespace {
 template <int NQ> struct HostStore {
   double a[NQ * chain_lin::kLinkDoubles];
-  double get(int i, int o) const { return a[i * chain_lin::kLinkDoubles + o]; }
-  void put(int i, int o, double v) { a[i * chain_lin::kLinkDoubles + o] = v; }
+  void get2(int i, int o, double& v0, double& v1) const { v0 = a[i * chain_lin::kLinkDoubles + o]; v1 = a[i * chain_lin::kLinkDoubles + o + 1]; }
+  void put2(int i, int o, double v0, double v1) { a[i * chain_lin::kLinkDoubles + o] = v0; a[i * chain_lin::kLinkDoubles + o + 1] = v1; }
 };
 template <int NQ> struct HostOut {
   double* base; double* cur;
