@@ -729,6 +729,33 @@ def run_b200(args):
         hx0 = torch.from_numpy(np.ascontiguousarray(x0.T)).pin_memory()        # [B][n] == Julia x0[n,B]
         houts = [out_set(False) for _ in range(RING)]
 
+        def host_link_probe(reps=4):
+            """What the host link gives THIS rank while every rank of the node moves data at the same time: the e2e
+            buffers copied host→device and device→host concurrently on two streams, no compute (the ceiling the e2e arm is
+            measured against — with 8 ranks the link, not the GPU, bounds the full-x_init variant)."""
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            dst = torch.empty_like(dx); src = douts[0][0]
+            res = {}
+            for name, do_in, do_out in (("h2d_only", True, False), ("d2h_only", False, True), ("both", True, True)):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                s_in.wait_stream(torch.cuda.current_stream()); s_out.wait_stream(torch.cuda.current_stream())
+                for _ in range(reps):
+                    if do_in:
+                        with torch.cuda.stream(s_in):
+                            dst.copy_(hx, non_blocking=True)
+                    if do_out:
+                        with torch.cuda.stream(s_out):
+                            houts[0][0].copy_(src, non_blocking=True)
+                torch.cuda.current_stream().wait_stream(s_in); torch.cuda.current_stream().wait_stream(s_out)
+                e1.record()
+                barrier()
+                ms = max_over_ranks(e0.elapsed_time(e1))
+                nbytes = hx.numel() * 8 * reps
+                res[name] = {"gbs_per_rank_per_direction": nbytes / ms / 1e6, "gbs_all_ranks": world * nbytes * ((1 if do_in else 0) + (1 if do_out else 0)) / ms / 1e6}
+            return res
+
         def e2e_run(submit_one, h2d, d2h, api):
             run_windowed(max(3, min(args.warmup, RING)), submit_one, streamer.wait, RING)
             r0 = streamer.rounds()
@@ -771,7 +798,9 @@ def run_b200(args):
                      hx0.numel() * 8, hu.numel() * 8 + scal,
                      "ilqr_streamer_submit_x0 with x_out = NULL: host x0 in, host u,cost,iters,status out")
         v3["results_identical_to_resident_arm"] = same_as_resident(houts[0], (1, 2, 3, 4))
-        e2e_variants = {"x0_in__x_u_out": v2, "x0_in__u_out": v3,
+        link = host_link_probe()
+        e2e["host_link_ceiling"] = link
+        e2e_variants = {"x0_in__x_u_out": v2, "x0_in__u_out": v3, "host_link_ceiling": link,
                         "note": "the headline `e2e` moves what the reference's fit signature moves (x_init, u_init in; x̄, ū out); these two move "
                                 "less across the host link, which all ranks of a node share"}
     streamer.close()

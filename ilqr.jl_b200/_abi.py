@@ -93,6 +93,10 @@ SYMBOLS = {
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "ilqr_streamer_submit_device": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_streamer_submit_traj": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ilqr_streamer_submit_traj_device": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "ilqr_streamer_submit_x0": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "ilqr_streamer_submit_x0_device": (ctypes.c_int64, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -41,7 +41,7 @@ void free_all(ilqr_handle* h) {
   cudaFree(s.r_status); cudaFree(s.r_iters); cudaFree(s.r_active);
   cudaFree(s.blocks_done); cudaFree(s.retry_list); cudaFree(s.n_retry);
   cudaFree(s.retire_list); cudaFree(s.move_src); cudaFree(s.move_dst); cudaFree(s.n_move);
-  cudaFree(h->ab_scratch); cudaFree(h->lin_scratch); cudaFree(h->plant); cudaFree(h->u_applied);
+  cudaFree(h->ab_scratch); cudaFree(h->lin_scratch); cudaFree(h->round_xt); cudaFree(h->plant); cudaFree(h->u_applied);
   cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
   if (h->pinned_i32) cudaFreeHost(h->pinned_i32);
   cudaFree(h->round_ctr); cudaFree(h->round_traj); cudaFree(h->round_tab); cudaFree(h->round_done);

@@ -44,8 +44,11 @@ struct ilqr_handle {
                                // 2-4 measured no faster on B200, bench9 vs bench9_b1; 0 = size-based policy; ILQR_BURST_MAX)
   int32_t coop_below = 8192;   // ... and the warp-cooperative Riccati kernel when nslots <= this
   int32_t fwd_split_above = 24000;  // two-kernel forward pass (α = 1, then dense retries) when nslots > this
-  int32_t fwd_wpt_below = 0;        // warp-per-trajectory forward pass (all step sizes at once) when nslots <= this under
-                                    // ILQR_VARIANT_AUTO (ILQR_FWD_WPT_BELOW); always under ILQR_VARIANT_WARP_PER_TRAJ
+  int32_t fwd_wpt_below = 1184;     // warp-per-trajectory forward pass (all step sizes at once) when nslots <= this under
+                                    // ILQR_VARIANT_AUTO (ILQR_FWD_WPT_BELOW); always under ILQR_VARIANT_WARP_PER_TRAJ.
+                                    // Measured (tools/variant_bench.py, forward pass, ms lane- vs warp-per-trajectory):
+                                    // 512 live: 0.315 → 0.238 (α = 1 everywhere), 0.70 → 0.24 (line search active);
+                                    // 2,048: 0.317 → 0.39 / 0.78 → 0.57; 8,192: 0.32 → 1.1 / 0.78 → 1.6
   bool pend_bwd = false, pend_fwd = false;
   // split backward pass of the fixed-base rigid-body models (chain_lin.cuh): linearisation scratch for `lin_chunk` trajectories
   double* lin_scratch = nullptr;
@@ -56,6 +59,7 @@ struct ilqr_handle {
   unsigned long long* round_ctr = nullptr;   // device: [0] queue head, [1] retired, [2] block ticket
   long long* round_pub = nullptr;            // mapped host: 2 publication slots × {retired, next}
   long long* round_traj = nullptr;           // device [S]: slot state (RoundP::traj)
+  double* round_xt = nullptr;                // device [N][S][n]: x_traj per slot (lazy: first batch submitted with an x_traj)
   ilqr::BatchTab* round_tab = nullptr;             // device [kMaxRing]
   ilqr::BatchTab* round_tab_host = nullptr;        // pinned staging for table updates
   int32_t* round_done = nullptr;             // device [kMaxRing]

@@ -44,11 +44,12 @@ void launch_set_active_by_traj(const DevState& st, const int32_t* d_mask, cudaSt
 struct BatchTab {
   const double* in_x; const double* in_u;                                          // [Bb][n·N], [Bb][m·H]
   double* out_x; double* out_u; double* out_cost; int32_t* out_iters; int32_t* out_status;   // all nullable
-  int64_t reserved;
+  const double* in_xt;                                                                       // [Bb][n·N] x_traj, nullable (= zeros)
 };
 struct RoundP {
   double* x[2]; double* u[2];   // iterate ping-pong (every warp reads buffer `parity`, writes the other)
   double* duff; double* K;
+  double* xt;                   // [N][S][n] x_traj of the slot's trajectory; nullptr until a batch with x_traj is submitted
   double* prev_cost; int32_t* iters; int32_t* status;
   long long* traj;              // ≥ 0 live (trajectory index), −1 idle, ≤ −2 holds queue ticket −2 − value
   int32_t* ls_j;                // line-search attempt of the next forward sweep (α = 2^-ls_j)

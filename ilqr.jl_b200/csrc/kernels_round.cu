@@ -36,6 +36,7 @@ constexpr int NX = 4, NU = 2, NK = NU * NX;
 constexpr int32_t ST_NAN_GAINS = 1, ST_NAN_ROLLOUT = 2, ST_LS_EXHAUSTED = 4, ST_CONVERGED = 16, ST_MAX_ITER = 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kStageDoubles = 32 * (NX + NU + NU + NK);   // forward stage: x, u, δuff, K slabs = 4 KB (backward uses 1.5 KB of it)
+constexpr int kStageDoublesXT = kStageDoubles + 32 * NX;  // + the x_traj slab (fit's keyword argument, src/forward_pass.jl:151,190)
 
 __device__ __forceinline__ double qinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
@@ -124,16 +125,29 @@ __device__ __forceinline__ void admit_slot(const double* __restrict__ ix, const 
   }
 }
 
+// x_traj of an admitted trajectory → the slot's [k][slot][component] copy (zeros if the batch has none)
+__device__ __forceinline__ void admit_xt(const double* __restrict__ ixt, double* XT, int64_t S, int sj, int H, int lane) {
+  const int N = H + 1;
+  for (int k = lane; k < N; k += 32) {
+    double v[NX];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) v[c] = ixt ? ixt[c * N + k] : 0.0;
+    stv<NX>(XT + ((int64_t)k * S + sj) * NX, v);
+  }
+}
+
 // Slot state in rp.traj[s]:  t ≥ 0 — live, solving trajectory t;  −1 — idle;  ≤ −2 — holds queue ticket −2 − t and
 // waits for that trajectory to become available (t < n_avail).
 // PARK (the 16-warp build, 128 registers): the value function (𝐬, 𝐒: 20 doubles) is parked in shared memory while the
 // time step is linearised — in the δuff / K part of the first two ring stages, which the backward sweep does not use —
 // so that the RK4 Jacobian chain (60 doubles) does not have to share the register file with it.
-template <int kWarps, int D, bool PARK>
+// XT: the running cost is l(x̄ − x_traj, ū) (total_cost, src/forward_pass.jl:190): one more slab per time step in the forward sweep.
+template <int kWarps, int D, bool PARK, bool XT = false>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ TwoLinkP mp,
                    const __grid_constant__ CostP cp, const __grid_constant__ RoundArgs ra) {
-  constexpr int SD = kStageDoubles;
+  constexpr int SD = XT ? kStageDoublesXT : kStageDoubles;
+  constexpr int oT = kStageDoubles;   // x_traj slab behind the K slab
   constexpr int oX = 0, oU = 32 * NX, oD = oU + 32 * NU, oK = oD + 32 * NU;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ bool last_block;
@@ -295,6 +309,7 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
             tma_load_1d(&ring[stage][oU], U + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
             tma_load_1d(&ring[stage][oD], rp.duff + ((int64_t)k * S + s0) * NU, 32 * NU * 8, &bars[stage]);
             tma_load_1d(&ring[stage][oK], rp.K + ((int64_t)k * S + s0) * NK, 32 * NK * 8, &bars[stage]);
+            if constexpr (XT) tma_load_1d(&ring[stage][oT], rp.xt + ((int64_t)k * S + s0) * NX, 32 * NX * 8, &bars[stage]);
           };
           if (lane == 0) {
 #pragma unroll
@@ -309,14 +324,21 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
           for (int k = 0; k < H; ++k, ++fills) {
             const int stage = fills % D;
             mbar_wait(&bars[stage], (fills / D) & 1);
-            double xk[NX], uk[NU], dk[NU], Kk[NK];
+            double xk[NX], uk[NU], dk[NU], Kk[NK], xtk[NX];
             ldv<NX>(&ring[stage][oX + lane * NX], xk);
             ldv<NU>(&ring[stage][oU + lane * NU], uk);
             ldv<NU>(&ring[stage][oD + lane * NU], dk);
             ldv<NK>(&ring[stage][oK + lane * NK], Kk);
+            if constexpr (XT) ldv<NX>(&ring[stage][oT + lane * NX], xtk);
+            else {
+#pragma unroll
+              for (int c = 0; c < NX; ++c) xtk[c] = 0.0;
+            }
             __syncwarp();
             if (lane == 0 && k + D < H) {
-              ring_reads_done(&ring_fence[warp], ring_token<NX>(xk) | ring_token<NU>(uk) | ring_token<NU>(dk) | ring_token<NK>(Kk));
+              uint32_t tok = ring_token<NX>(xk) | ring_token<NU>(uk) | ring_token<NU>(dk) | ring_token<NK>(Kk);
+              if constexpr (XT) tok |= ring_token<NX>(xtk);
+              ring_reads_done(&ring_fence[warp], tok);
               issue(k + D, stage);
             }
             if (live) {
@@ -334,10 +356,10 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
                 du2 = fma(e, e, du2);
               }
               stv<NU>(Uo + ((int64_t)k * S + s) * NU, ub);
-              // running cost l(x̄, ū), summed left to right (src/forward_pass.jl:189-191; x_traj = 0)
+              // running cost l(x̄ − x_traj, ū), summed left to right (src/forward_pass.jl:189-191)
               double lx = 0.0, lu = 0.0;
 #pragma unroll
-              for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - (xb[c] - 0.0); lx = fma(cp.w_x[c] * e, e, lx); }
+              for (int c = 0; c < NX; ++c) { const double e = cp.x_target[c] - (xb[c] - xtk[c]); lx = fma(cp.w_x[c] * e, e, lx); }
 #pragma unroll
               for (int i = 0; i < NU; ++i) lu = fma(cp.w_u[i] * ub[i], ub[i], lu);
               cost += lx + lu;
@@ -432,6 +454,7 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
           const long long bj = tj / rp.Bb, loc = tj - bj * rp.Bb;
           const BatchTab& e = rp.tab[bj % rp.R];
           admit_slot(e.in_x + loc * (NX * (long long)(H + 1)), e.in_u + loc * (NU * (long long)H), Xo, Uo, S, s0 + j, H, lane);
+          if constexpr (XT) admit_xt(e.in_xt ? e.in_xt + loc * (NX * (long long)(H + 1)) : nullptr, rp.xt, S, s0 + j, H, lane);
         }
         if (adm) {   // fit's start state (src/forward_pass.jl:159-160)
           rp.prev_cost[s] = qinf(); rp.iters[s] = 0; rp.status[s] = 0; rp.ls_j[s] = 0;
@@ -472,6 +495,12 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
         cm &= cm - 1; im &= im - 1;
         const int src = b0 + sw * 32 + jc, dst = b0 + warp * 32 + ji;
         move_slot(Xn, Un, rp.S, src, dst, rp.H, lane);
+        if constexpr (XT)
+          for (int k = lane; k <= rp.H; k += 32) {
+            double v[NX];
+            ldv_cg<NX>(rp.xt + ((int64_t)k * rp.S + src) * NX, v);
+            stv<NX>(rp.xt + ((int64_t)k * rp.S + dst) * NX, v);
+          }
         if (lane == ji) {
           rp.prev_cost[dst] = __ldcg(rp.prev_cost + src); rp.iters[dst] = __ldcg(rp.iters + src);
           rp.status[dst] = __ldcg(rp.status + src); rp.ls_j[dst] = 0;
@@ -522,7 +551,9 @@ rollout_tf_two_link(const __grid_constant__ TwoLinkP mp, const double* __restric
   }
 }
 
-template <int kWarps, int D> constexpr size_t round_smem() { return sizeof(double) * kWarps * D * kStageDoubles + sizeof(uint64_t) * kWarps * D; }
+template <int kWarps, int D, bool XT = false> constexpr size_t round_smem() {
+  return sizeof(double) * kWarps * D * (XT ? kStageDoublesXT : kStageDoubles) + sizeof(uint64_t) * kWarps * D;
+}
 
 }  // namespace
 
@@ -530,6 +561,7 @@ void init_round_attributes() {
   cudaFuncSetAttribute(round_lpt_two_link<12, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<12, 4>());
   cudaFuncSetAttribute(round_lpt_two_link<16, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<16, 3>());
   cudaFuncSetAttribute(round_lpt_two_link<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<16, 3>());
+  cudaFuncSetAttribute(round_lpt_two_link<12, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<12, 3, true>());
 }
 
 void launch_rollout_tf_two_link(const TwoLinkP& mp, const double* d_x0, const double* d_u, double* d_x, long long Bb, int H,
@@ -539,8 +571,10 @@ void launch_rollout_tf_two_link(const TwoLinkP& mp, const double* d_x0, const do
 
 void launch_round_two_link(const RoundP& rp, const TwoLinkP& mp, const CostP& cp, const RoundArgs& ra, int warps_per_sm,
                            cudaStream_t s) {
-  // warps_per_sm: 12 (168 registers), 16 (128 registers, the compiler spills), 17 = 16 warps with the parked value function
-  if (warps_per_sm == 17) round_lpt_two_link<16, 3, true><<<(int)((rp.S + 511) / 512), 512, round_smem<16, 3>(), s>>>(rp, mp, cp, ra);
+  // warps_per_sm: 12 (168 registers), 16 (128 registers, the compiler spills), 17 = 16 warps with the parked value function;
+  // rp.xt != nullptr: the x_traj variant (12 warps, three-stage ring of 5 KB stages)
+  if (rp.xt) round_lpt_two_link<12, 3, false, true><<<(int)((rp.S + 383) / 384), 384, round_smem<12, 3, true>(), s>>>(rp, mp, cp, ra);
+  else if (warps_per_sm == 17) round_lpt_two_link<16, 3, true><<<(int)((rp.S + 511) / 512), 512, round_smem<16, 3>(), s>>>(rp, mp, cp, ra);
   else if (warps_per_sm >= 16) round_lpt_two_link<16, 3, false><<<(int)((rp.S + 511) / 512), 512, round_smem<16, 3>(), s>>>(rp, mp, cp, ra);
   else round_lpt_two_link<12, 4, false><<<(int)((rp.S + 383) / 384), 384, round_smem<12, 4>(), s>>>(rp, mp, cp, ra);
 }

@@ -161,11 +161,11 @@ struct ilqr_streamer {
   int32_t max_iter = 100;
   double tol = 1e-6;
   // device staging ring for host-pointer submissions (lazy)
-  double *sx = nullptr, *su = nullptr, *sx0 = nullptr, *sox = nullptr, *sou = nullptr, *scost = nullptr;
+  double *sx = nullptr, *su = nullptr, *sx0 = nullptr, *sxt = nullptr, *sox = nullptr, *sou = nullptr, *scost = nullptr;
   int32_t *siters = nullptr, *sstatus = nullptr;
   cudaStream_t cs_in = nullptr, cs_out = nullptr;
   struct Entry {
-    const double *x = nullptr, *u = nullptr;
+    const double *x = nullptr, *u = nullptr, *xt = nullptr;   // xt: x_traj (fit's keyword argument), nullable
     double *xo = nullptr, *uo = nullptr, *cost = nullptr;
     int32_t *iters = nullptr, *status = nullptr;
     bool host = false, busy = false;
@@ -236,7 +236,18 @@ int32_t streamer_step(ilqr_streamer* s, int64_t sub, int64_t& uploaded, int64_t&
         CK(h, cudaMemcpyAsync(sx, e.x, sizeof(double) * Bb * N * n, cudaMemcpyHostToDevice, s->cs_in));
         CK(h, cudaMemcpyAsync(su, e.u, sizeof(double) * Bb * H * m, cudaMemcpyHostToDevice, s->cs_in));
       }
+      if (e.host && e.xt) {
+        if (!s->sxt) CK(h, dalloc(&s->sxt, N * n * (size_t)s->Bb * s->R));
+        CK(h, cudaMemcpyAsync(s->sxt + slot * Bb * N * n, e.xt, sizeof(double) * Bb * N * n, cudaMemcpyHostToDevice, s->cs_in));
+      }
       CK(h, cudaEventRecord(e.ev_in, s->cs_in));
+    }
+    if (e.xt && !h->rp.xt) {
+      // first batch with an x_traj: from the next launch on the rounds run the x_traj variant of the kernel; the slots
+      // that are live now (and every later batch without an x_traj) have x_traj = 0, the reference's default
+      if (!h->round_xt) CK(h, dalloc(&h->round_xt, (size_t)(H + 1) * n * (size_t)h->st.S));
+      CK(h, cudaMemsetAsync(h->round_xt, 0, sizeof(double) * (H + 1) * n * (size_t)h->st.S, h->stream));
+      h->rp.xt = h->round_xt;
     }
     e.stage = 1;
   }
@@ -252,6 +263,7 @@ int32_t streamer_step(ilqr_streamer* s, int64_t sub, int64_t& uploaded, int64_t&
     BatchTab t{};
     t.in_x = (e.host || e.x0mode) ? s->sx + slot * Bb * N * n : e.x;
     t.in_u = (e.host || (e.x0mode && !e.u)) ? s->su + slot * Bb * H * m : e.u;
+    t.in_xt = !e.xt ? nullptr : (e.host ? s->sxt + slot * Bb * N * n : e.xt);
     if (e.host) {   // outputs the caller did not ask for are not produced at all (nullable, kernels_round.cu)
       t.out_x = e.xo ? s->sox + slot * Bb * N * n : nullptr; t.out_u = e.uo ? s->sou + slot * Bb * H * m : nullptr;
       t.out_cost = e.cost ? s->scost + slot * Bb : nullptr; t.out_iters = e.iters ? s->siters + slot * Bb : nullptr;
@@ -378,7 +390,7 @@ int32_t ilqr_streamer_destroy(ilqr_streamer* s) {
   s->cv_work.notify_all();
   if (s->worker.joinable()) s->worker.join();
   cudaSetDevice(s->h->device);
-  cudaFree(s->sx); cudaFree(s->su); cudaFree(s->sx0); cudaFree(s->sox); cudaFree(s->sou); cudaFree(s->scost); cudaFree(s->siters); cudaFree(s->sstatus);
+  cudaFree(s->sx); cudaFree(s->su); cudaFree(s->sx0); cudaFree(s->sxt); cudaFree(s->sox); cudaFree(s->sou); cudaFree(s->scost); cudaFree(s->siters); cudaFree(s->sstatus);
   for (auto& e : s->ring) { if (e.ev_in) cudaEventDestroy(e.ev_in); if (e.ev_out) cudaEventDestroy(e.ev_out); }
   if (s->cs_in) cudaStreamDestroy(s->cs_in);
   if (s->cs_out) cudaStreamDestroy(s->cs_out);
@@ -390,7 +402,7 @@ int32_t ilqr_streamer_destroy(ilqr_streamer* s) {
 const char* ilqr_streamer_last_error(const ilqr_streamer* s) { return s ? s->err.c_str() : g_streamer_err.c_str(); }
 
 static int64_t streamer_submit(ilqr_streamer* s, bool host, bool x0mode, const double* x, const double* u, double* xo, double* uo,
-                               double* cost, int32_t* iters, int32_t* status) {
+                               double* cost, int32_t* iters, int32_t* status, const double* xt = nullptr) {
   if (!s || !x || (!u && !x0mode)) return ILQR_ERR_INVALID;   // every output is nullable
   int64_t seq;
   {
@@ -401,7 +413,7 @@ static int64_t streamer_submit(ilqr_streamer* s, bool host, bool x0mode, const d
     if (s->rc != 0) return s->rc;
     seq = s->submitted;
     ilqr_streamer::Entry& e = s->ring[slot];
-    e.x = x; e.u = u; e.xo = xo; e.uo = uo; e.cost = cost; e.iters = iters; e.status = status;
+    e.x = x; e.u = u; e.xt = xt; e.xo = xo; e.uo = uo; e.cost = cost; e.iters = iters; e.status = status;
     e.host = host; e.x0mode = x0mode; e.busy = true; e.stage = 0; e.seq = seq;
     s->done_flags.push_back(0);
     ++s->submitted;
@@ -418,6 +430,17 @@ int64_t ilqr_streamer_submit(ilqr_streamer* s, const double* x_init, const doubl
 int64_t ilqr_streamer_submit_device(ilqr_streamer* s, const double* d_x_init, const double* d_u_init, double* d_x_out,
                                     double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out) {
   return streamer_submit(s, false, false, d_x_init, d_u_init, d_x_out, d_u_out, d_cost_out, d_iters_out, d_status_out);
+}
+
+int64_t ilqr_streamer_submit_traj(ilqr_streamer* s, const double* x_init, const double* u_init, const double* x_traj, double* x_out,
+                                  double* u_out, double* cost_out, int32_t* iters_out, int32_t* status_out) {
+  return streamer_submit(s, true, false, x_init, u_init, x_out, u_out, cost_out, iters_out, status_out, x_traj);
+}
+
+int64_t ilqr_streamer_submit_traj_device(ilqr_streamer* s, const double* d_x_init, const double* d_u_init, const double* d_x_traj,
+                                         double* d_x_out, double* d_u_out, double* d_cost_out, int32_t* d_iters_out,
+                                         int32_t* d_status_out) {
+  return streamer_submit(s, false, false, d_x_init, d_u_init, d_x_out, d_u_out, d_cost_out, d_iters_out, d_status_out, d_x_traj);
 }
 
 int64_t ilqr_streamer_submit_x0(ilqr_streamer* s, const double* x0, const double* u_init, double* x_out, double* u_out,

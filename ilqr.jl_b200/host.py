@@ -475,13 +475,19 @@ class Streamer:
         except Exception:
             pass
 
-    def submit_ptrs(self, x, u, xo=None, uo=None, cost=None, iters=None, status=None, device=False, x0=False):
+    def submit_ptrs(self, x, u, xo=None, uo=None, cost=None, iters=None, status=None, device=False, x0=False, x_traj=None):
         """Raw addresses (ints) of boundary-layout arrays of batch_size trajectories: host pointers, or device pointers
         with device=True.  x0=True: `x` is x0[n,Bb] and x_init is rolled out on the device (`u` may be None = zeros).
         Every output is optional (None = not produced, not copied back).  Returns a ticket."""
-        fn = {(False, False): self._lib.ilqr_streamer_submit, (True, False): self._lib.ilqr_streamer_submit_device,
-              (False, True): self._lib.ilqr_streamer_submit_x0, (True, True): self._lib.ilqr_streamer_submit_x0_device}[(bool(device), bool(x0))]
-        t = fn(self._p, x, u, xo, uo, cost, iters, status)
+        if x_traj is not None:     # fit's keyword argument (src/forward_pass.jl:151)
+            if x0:
+                raise ValueError("x_traj goes with x_init submissions")
+            fn = self._lib.ilqr_streamer_submit_traj_device if device else self._lib.ilqr_streamer_submit_traj
+            t = fn(self._p, x, u, x_traj, xo, uo, cost, iters, status)
+        else:
+            fn = {(False, False): self._lib.ilqr_streamer_submit, (True, False): self._lib.ilqr_streamer_submit_device,
+                  (False, True): self._lib.ilqr_streamer_submit_x0, (True, True): self._lib.ilqr_streamer_submit_x0_device}[(bool(device), bool(x0))]
+            t = fn(self._p, x, u, xo, uo, cost, iters, status)
         if t < 0:
             raise IlqrError("ilqr_streamer_submit failed (%d): %s" % (t, self._lib.ilqr_streamer_last_error(self._p).decode()))
         return t
@@ -505,11 +511,12 @@ class Streamer:
                 self._check(out.get("cost"), (), np.float64, "out['cost']"), self._check(out.get("iters"), (), np.int32, "out['iters']"),
                 self._check(out.get("status"), (), np.int32, "out['status']"))
 
-    def submit(self, x_init, u_init, out):
-        """NumPy (Fortran-ordered, boundary layout) in, preallocated `out` dict (any of x, u, cost, iters, status) filled on wait."""
+    def submit(self, x_init, u_init, out, x_traj=None):
+        """NumPy (Fortran-ordered, boundary layout) in, preallocated `out` dict (any of x, u, cost, iters, status) filled on wait.
+        x_traj: fit's keyword argument (src/forward_pass.jl:151), same shape as x_init."""
         p = self.problem
         return self.submit_ptrs(self._check(x_init, (p.H + 1, p.n), np.float64, "x_init"), self._check(u_init, (p.H, p.m), np.float64, "u_init"),
-                                *self._outs(out))
+                                *self._outs(out), x_traj=self._check(x_traj, (p.H + 1, p.n), np.float64, "x_traj"))
 
     def submit_x0(self, x0, u_init, out):
         """x0[n,Bb] (+ u_init[H,m,Bb] or None = zeros): x_init is the open-loop rollout, computed on the device

@@ -326,6 +326,14 @@ int64_t ilqr_streamer_submit(ilqr_streamer* s, const double* x_init, const doubl
 /* device pointers: read and written by the kernels directly, no staging copy */
 int64_t ilqr_streamer_submit_device(ilqr_streamer* s, const double* d_x_init, const double* d_u_init, double* d_x_out,
                                     double* d_u_out, double* d_cost_out, int32_t* d_iters_out, int32_t* d_status_out);
+/* With fit's keyword argument x_traj (src/forward_pass.jl:151: the running cost is l(x̄ − x_traj, ū), :190): x_traj[N,n,Bb],
+ * same layout and residency as x_init; NULL = zeros.  From the first such batch on the rounds run the x_traj variant of
+ * the kernel (one more slab per time step); results stay bit-identical to ilqr_solve with the same x_traj. */
+int64_t ilqr_streamer_submit_traj(ilqr_streamer* s, const double* x_init, const double* u_init, const double* x_traj, double* x_out,
+                                  double* u_out, double* cost_out, int32_t* iters_out, int32_t* status_out);
+int64_t ilqr_streamer_submit_traj_device(ilqr_streamer* s, const double* d_x_init, const double* d_u_init, const double* d_x_traj,
+                                         double* d_x_out, double* d_u_out, double* d_cost_out, int32_t* d_iters_out,
+                                         int32_t* d_status_out);
 /* Problem setup on device, as the reference's own scripts build their inputs (test/2_link_example/animate_2_link.jl:11-16:
  * x_init = open-loop rollout of u_init from x0): x0[n,Bb] and u_init[H,m,Bb] (NULL = zeros, the reference's initial
  * guess) are all that crosses the bus — 2 MB instead of 631 MB per 65,536-trajectory batch at config 2 with u_init = NULL.

@@ -319,6 +319,15 @@ function host_alloc(::Type{T}, dims...) where {T}
 end
 host_free(a::Array) = ccall((:ilqr_host_free, lib), Int32, (Ptr{Cvoid},), a)
 
+"With fit's keyword argument `x_traj` (src/forward_pass.jl:151); same shape as `x_init`."
+function submit_traj!(s::Streamer, x_init::Array{Float64,3}, u_init::Array{Float64,3}, x_traj::Array{Float64,3}, x_out::Array{Float64,3},
+                      u_out::Array{Float64,3}, cost::Vector{Float64}, iters::Vector{Int32}, status::Vector{Int32})
+    t = ccall((:ilqr_streamer_submit_traj, lib), Int64,
+              (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+              s.h, x_init, u_init, x_traj, x_out, u_out, cost, iters, status)
+    t >= 0 || error("ilqr_streamer_submit_traj failed ($t)")
+    t
+end
 Base.wait(s::Streamer, ticket::Int64) =
     ccall((:ilqr_streamer_wait, lib), Int32, (Ptr{Cvoid}, Int64), s.h, ticket) == 0 ||
     error(unsafe_string(ccall((:ilqr_streamer_last_error, lib), Cstring, (Ptr{Cvoid},), s.h)))

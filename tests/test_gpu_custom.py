@@ -176,8 +176,14 @@ def test_user_cost_tool_point_with_cross_term_matches_oracle_quadratisation():
     stable = np.ones(B, dtype=bool)
     for trial in range(3):
         xp = x * (1 + 1e-15 * rng.standard_normal(x.shape)); up = u * (1 + 1e-15 * rng.standard_normal(u.shape))
-        stable &= orc.tool_fit_batch(xp, up, None, W_TOOL, W_FINAL, GAMMA, max_iter=40, tol=1e-6, nthreads=8)["iters"] == ref["iters"]
-    assert stable.sum() >= int(0.8 * B)
+        pert = orc.tool_fit_batch(xp, up, None, W_TOOL, W_FINAL, GAMMA, max_iter=40, tol=1e-6, nthreads=8)
+        stable &= pert["iters"] == ref["iters"]
+        for b in range(B):      # ... and whose cost traces do not amplify a 1e-15 perturbation beyond 1e-11
+            it = min(ref["iters"][b], pert["iters"][b])
+            a, c = ref["cost"][:it, b], pert["cost"][:it, b]
+            ok = ~np.isnan(a) & ~np.isnan(c)
+            stable[b] &= bool(np.array_equal(np.isnan(a), np.isnan(c)) and (not ok.any() or np.max(np.abs(a[ok] - c[ok]) / np.abs(a[ok])) < 1e-11))
+    assert stable.sum() >= int(0.6 * B)
     assert np.array_equal(out["iters"][stable], ref["iters"][stable]), (out["iters"], ref["iters"], stable)
     assert len(np.unique(ref["iters"][stable])) >= 5
     for b in np.flatnonzero(stable):

@@ -669,3 +669,51 @@ def test_mapping_variants_are_bit_identical(with_xtraj):
     for v in (_abi.VARIANT_LANE_PER_TRAJ, _abi.VARIANT_WARP_PER_TRAJ):
         for a, b in zip(ref, res[v]):
             assert np.array_equal(a, b, equal_nan=True), v
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_streamer_with_x_traj_equals_batch_solves(device):
+    """fit's keyword argument x_traj (src/forward_pass.jl:151: the running cost is l(x̄ − x_traj, ū), :190) through the
+    streamer: batches with and without an x_traj mixed in one stream (the rounds switch to the x_traj variant of the
+    kernel at the first such batch; trajectories without one get zeros).  Each batch bit-identical to ilqr_solve."""
+    import torch
+    H, Bb, nb, slots, max_iter = 60, 64, 5, 96, 25
+    _, xa, ua = config2_batch(200, H, seed=61)
+    _, xb, ub = stress_batch(120, H, seed=62)
+    x = np.concatenate([xa, xb], axis=2); u = np.concatenate([ua, ub], axis=2)
+    perm = np.random.default_rng(3).permutation(nb * Bb)
+    x = np.asfortranarray(x[:, :, perm]); u = np.asfortranarray(u[:, :, perm])
+    xt = np.asfortranarray(0.1 * np.random.default_rng(4).normal(size=x.shape))
+    has_xt = [False, True, True, False, True]
+    refs = []
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, Bb)) as s:
+        for b in range(nb):
+            sl = slice(b * Bb, (b + 1) * Bb)
+            refs.append(s.solve(np.asfortranarray(x[:, :, sl]), np.asfortranarray(u[:, :, sl]),
+                                np.asfortranarray(xt[:, :, sl]) if has_xt[b] else None, max_iter=max_iter, tol=1e-6))
+    assert not np.array_equal(refs[1]["cost"], refs[0]["cost"])
+
+    def mk(a):
+        t = torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0)))
+        return t.cuda() if device else t.pin_memory()
+
+    ins, outs = [], []
+    for b in range(nb):
+        sl = slice(b * Bb, (b + 1) * Bb)
+        o = [torch.zeros((Bb, 4, H + 1), dtype=torch.float64), torch.zeros((Bb, 2, H), dtype=torch.float64), torch.zeros(Bb, dtype=torch.float64),
+             torch.zeros(Bb, dtype=torch.int32), torch.zeros(Bb, dtype=torch.int32)]
+        outs.append([t.cuda() if device else t.pin_memory() for t in o])
+        ins.append((mk(x[:, :, sl]), mk(u[:, :, sl]), mk(xt[:, :, sl]) if has_xt[b] else None))
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, slots), Bb, ring=2, max_iter=max_iter, tol=1e-6) as st:
+        tickets = [st.submit_ptrs(ins[b][0].data_ptr(), ins[b][1].data_ptr(), *[t.data_ptr() for t in outs[b]], device=device,
+                                  x_traj=None if ins[b][2] is None else ins[b][2].data_ptr()) for b in range(nb)]
+        for t in tickets:
+            st.wait(t)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        ox, ou, oc, oi, os_ = [t.cpu().numpy() for t in outs[b]]
+        assert np.array_equal(oi, refs[b]["iters"]), b
+        assert np.array_equal(os_, refs[b]["status"]), b
+        assert np.array_equal(oc, refs[b]["cost"]), b
+        assert np.array_equal(ox.transpose(2, 1, 0), refs[b]["x"]), b
+        assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b
