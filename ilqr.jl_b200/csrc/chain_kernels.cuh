@@ -468,7 +468,7 @@ template <int NQ> struct RicSmem : RiccatiSmem<2 * NQ, NQ> {
 };
 
 template <int NQ>
-__global__ void __launch_bounds__(kCW * 32)
+__global__ void __launch_bounds__(kCW * 32, 3)
 ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, const __grid_constant__ CostP cost,
           const double* __restrict__ scratch, int slot0, int nchunk, int Hb) {
   using IT = chain_lin::StageItems<NQ>;
@@ -517,8 +517,8 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
       double tp[n], tsum[n];
 #pragma unroll
       for (int i = 0; i < n; ++i) { tp[i] = 0.0; tsum[i] = 0.0; }
-#pragma unroll 1
-      for (int stg = 0; stg < 4; ++stg) {
+#pragma unroll
+      for (int stg = 0; stg < 4; ++stg) {   // unrolled: the next stage's loads overlap this stage's substitutions
         const double2* it = reinterpret_cast<const double2*>(sm.blk) + (size_t)stg * IT::kPairs * kLinSteps + kk;   // pair p at it[kLinSteps·p]
         const double cin = (stg == 0) ? 0.0 : (stg == 3 ? 1.0 : 0.5), wgt = (stg == 1 || stg == 2) ? 2.0 : 1.0;
         double dq[NQ], dv[NQ], y[NQ];
