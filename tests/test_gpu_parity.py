@@ -642,8 +642,9 @@ def test_mapping_variants_are_bit_identical(with_xtraj):
     """ilqr_variant: AUTO, LANE_PER_TRAJ (one thread per trajectory) and WARP_PER_TRAJ (BASELINE's sketch: lanes cooperate
     on a trajectory — time-parallel linearisation, 4-lane Riccati, and a forward pass whose 32 lanes roll out all step
     sizes α = 2⁻ʲ at once instead of halving sequentially, src/forward_pass.jl:70-86) must return the same bits: gains,
-    accepted step sizes, costs, candidates, whole fits.  Stress inputs, so that step sizes down to 2⁻⁵ are selected;
-    n_alpha = 40 > 32 exercises the second block of candidates of the warp-wide search."""
+    accepted step sizes, costs, candidates, whole fits.  Stress inputs, so that step sizes below 1 are selected in the fits; the second forward pass asks for a cost
+    just below the α = 1 candidate's, which only a few trajectories reach at α = ½ and the rest never do: with
+    n_alpha = 40 > 32 those run through both blocks of candidates of the warp-wide search before giving up."""
     B, H = 160, 60
     _, xa, ua = config2_batch(B // 2, H, seed=51)
     _, xb_, ub_ = stress_batch(B // 2, H, seed=52)
@@ -665,7 +666,7 @@ def test_mapping_variants_are_bit_identical(with_xtraj):
             res[v] = first + second + (s.download(_abi.X), s.download(_abi.U), s.download(_abi.ITERS), s.download(_abi.STATUS),
                                        s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE))
     ref = res[_abi.VARIANT_AUTO]
-    assert np.sum(ref[8] < 1.0) > B // 2 and np.nanmin(ref[-1]) <= 2.0 ** -3
+    assert np.sum(ref[8] < 1.0) > B // 2 and np.nanmin(ref[-1]) <= 0.5
     for v in (_abi.VARIANT_LANE_PER_TRAJ, _abi.VARIANT_WARP_PER_TRAJ):
         for a, b in zip(ref, res[v]):
             assert np.array_equal(a, b, equal_nan=True), v
