@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "iLQR solves/sec (batched 2-link arm, H=200)"
-NCU_ROUND_FILE = "ncu_full_r1_round.txt"     # tools/ncu_summary.py of one full-width launch of the round kernel (profiles/)
+NCU_ROUND_FILE = "ncu_full_r2_round.txt"     # tools/ncu_summary.py of one full-width launch of the round kernel (profiles/); header: rounds_in_launch=R
 UNIT = "solves/s"
 H, B_PER_GPU, MAX_ITER, TOL = 200, 65536, 100, 1e-6
 N_, M_ = 4, 2
@@ -352,9 +352,13 @@ def ncu_file_metrics(name, kernel_tag):
     file under profiles/ (ncu --set full, one launch): {traffic, ms, fp64_pipe_pct, file} or None."""
     path = os.path.join(ROOT, "profiles", name)
     try:
-        blocks = open(path).read().split("-----")
+        text = open(path).read()
     except Exception:
         return None
+    import re
+    mr = re.search(r"rounds_in_launch=(\d+)", text)
+    rounds_in_launch = int(mr.group(1)) if mr else 1
+    blocks = text.split("-----")
     for b in blocks:
         if kernel_tag not in b:
             continue
@@ -370,7 +374,8 @@ def ncu_file_metrics(name, kernel_tag):
             tu = {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}
             ms = float(val["gpu__time_duration.sum"][0]) * tu[val["gpu__time_duration.sum"][1]]
             pipe = float(val["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"][0])
-            return {"traffic": rd + wr, "ms": ms, "fp64_pipe_pct": pipe, "file": "profiles/" + name}
+            cyc = float(val["sm__cycles_elapsed.avg"][0]) if "sm__cycles_elapsed.avg" in val else None
+            return {"cycles": cyc, "traffic": rd + wr, "ms": ms, "fp64_pipe_pct": pipe, "file": "profiles/" + name, "rounds_in_launch": rounds_in_launch}
         except Exception:
             return None
     return None
@@ -506,7 +511,6 @@ def run_b200(args):
     s = ilqr_b200.BatchSolver(prob)
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     round_warps = int(os.environ.get("ILQR_ROUND_WARPS", "12"))
-    rounds_per_launch = int(os.environ.get("ILQR_ROUND_MULTI", "1"))
     SLOTS = n_sm * (16 if round_warps >= 16 else 12) * 32   # one block of 12 (or 16) warps per SM (csrc/kernels_round.cu)
     RING = args.ring
     streamer = ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, SLOTS, device=local), B, ring=RING, max_iter=MAX_ITER, tol=TOL)
@@ -669,7 +673,8 @@ def run_b200(args):
     FP64_ROUND, FP64_ROUND_TRUE = instr(round_tag)
     traj_iters_total = mean_iters * B * args.steps            # every step solves the same batch
     share = rounds_timed / rounds_total if rounds_total else 0.0
-    avg_launch_ms = round_ms / rounds_timed if rounds_timed else None
+    avg_round_ms = round_ms / rounds_timed if rounds_timed else None
+    rounds_per_launch = rounds_total / launches if launches else None     # measured: 8 per launch mid-stream, 1 while draining
     ach = ITER_BYTES * traj_iters_total * share / (round_ms * 1e-3) / 1e9 if round_ms else 0.0
     per_s = traj_iters_total * share * H / (round_ms * 1e-3) if round_ms else None      # trajectory-steps per second
     slot_tf = 2.0 * FP64_ROUND * per_s / 1e12 if (per_s and FP64_ROUND) else None
@@ -689,8 +694,11 @@ def run_b200(args):
         operand = {"fp64_instructions_by_vector_register_sources": mixv, "pipe_cycles_per_instruction": cyc,
                    "mean_pipe_cycles_per_fp64_instruction": mean_cyc, "operand_limited_peak_tflops": ceil_tf,
                    "frac_of_operand_limited_peak": slot_tf / ceil_tf,
-                   "note": "tools/sass_operands.py + tools/fp64_peak.cu: a full-width launch needs slots/128 warps per scheduler x H steps x "
-                           "sum(count x cycles) pipe cycles; profiles/ncu_full_r1_round.txt shows 1.94 M elapsed cycles against 1.97 M predicted"}
+                   "predicted_cycles_per_round": SLOTS / (n_sm * 128.0) * H * tot * mean_cyc,
+                   "ncu_cycles_per_round": (ncu_round["cycles"] / ncu_round["rounds_in_launch"]) if (ncu_round and ncu_round.get("cycles")) else None,
+                   "note": "tools/sass_operands.py + tools/fp64_peak.cu: a full-width round needs slots/(SMs x 128) warps per scheduler x H steps x "
+                           "sum(count x cycles) pipe cycles (predicted_cycles_per_round); ncu_cycles_per_round = sm__cycles_elapsed of the "
+                           "committed capture / its rounds"}
     kname = "round_lpt_two_link<%s> (backward sweep + forward sweep + accept / converge test + retirement + admission; the only " \
             "kernel launched in the timed region)" % ("16, 3" if round_warps >= 16 else "12, 4")
     roofline = {
@@ -705,13 +713,20 @@ def run_b200(args):
         "hbm": {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_trajectory_iteration": ITER_BYTES},
         "traffic": ncu_round["traffic"] if ncu_round else None,
-        "traffic_note": ("dram read + write of one full-width launch under ncu --set full (%s: %.3f ms, FP64 pipe %.1f %% active); algorithmic "
-                         "%.3e B for %d slots" % (ncu_round["file"], ncu_round["ms"], ncu_round["fp64_pipe_pct"], ITER_BYTES * SLOTS, SLOTS))
+        "traffic_per_round": ncu_round["traffic"] / ncu_round["rounds_in_launch"] if ncu_round else None,
+        "traffic_note": ("dram read + write of one full-width launch of %d rounds (whole iterations) under ncu --set full (%s: %.3f ms, FP64 pipe "
+                         "%.1f %% active); algorithmic %.3e B per round of %d slots, %.3e B for the captured launch"
+                         % (ncu_round["rounds_in_launch"], ncu_round["file"], ncu_round["ms"], ncu_round["fp64_pipe_pct"], ITER_BYTES * SLOTS,
+                            SLOTS, ITER_BYTES * SLOTS * ncu_round["rounds_in_launch"]))
                         if ncu_round else "no ncu capture committed for this kernel",
-        "avg_launch_ms": avg_launch_ms, "launches_timed": rounds_timed,
-        "launches_in_timed_region": rounds_total, "slots": SLOTS, "rounds_per_launch": rounds_per_launch,
-        "trajectory_iterations_per_launch": traj_iters_total / rounds_total if rounds_total else None,
-        "measured_on": "the K timed steps (resident arm): CUDA events on the streamer's stream around every group of back-to-back launches; "
+        "avg_round_ms": avg_round_ms, "rounds_timed": rounds_timed, "rounds_in_timed_region": rounds_total,
+        "launches_in_timed_region": int(launches), "rounds_per_launch": rounds_per_launch,
+        "avg_launch_ms": avg_round_ms * rounds_per_launch if (avg_round_ms and rounds_per_launch) else None,
+        "slots": SLOTS,
+        "trajectory_iterations_per_round": traj_iters_total / rounds_total if rounds_total else None,
+        "note_rounds": "one launch runs several rounds (a round = one whole iLQR iteration of every slot: backward + forward sweep + loop tail) "
+                       "without a grid barrier between them; rates are per round, a launch is rounds_per_launch of them",
+        "measured_on": "the K timed steps (resident arm): CUDA events on the streamer's stream around every group of back-to-back launches (8 rounds); "
                        "includes the final drain, whose launches run on the stragglers only",
         "reference_formulation_flops_per_trajectory_step": 9619,   # oracle/count_ops.cpp (+ 180 sin/cos): dual-number Jacobians / Hessians
         "batch_path_kernels": {"fwd_lpt_two_link": kernel_roofline("fwd"), "backward_pass": kernel_roofline("bwd")},

@@ -665,11 +665,20 @@ def test_mapping_variants_are_bit_identical(with_xtraj):
             s.fit(40, 1e-6)
             res[v] = first + second + (s.download(_abi.X), s.download(_abi.U), s.download(_abi.ITERS), s.download(_abi.STATUS),
                                        s.download(_abi.COST_TRACE), s.download(_abi.ALPHA_TRACE))
+    names = ["duff", "K", "xbar", "ubar", "new_cost", "alpha", "du2", "xbar2", "alpha2", "new_cost2", "x", "u", "iters", "status",
+             "cost_trace", "alpha_trace"]
     ref = res[_abi.VARIANT_AUTO]
     assert np.sum(ref[8] < 1.0) > B // 2 and np.nanmin(ref[-1]) <= 0.5
+    ok2 = ref[8] > 0.0        # second pass: the candidate of an exhausted search (α = 0) is whatever was rolled out last — not a result
+    assert 0 < np.sum(ok2) < B
+    bad = []
     for v in (_abi.VARIANT_LANE_PER_TRAJ, _abi.VARIANT_WARP_PER_TRAJ):
-        for a, b in zip(ref, res[v]):
-            assert np.array_equal(a, b, equal_nan=True), v
+        for nm, a, b in zip(names, ref, res[v]):
+            if nm == "xbar2":
+                a, b = a[:, :, ok2], b[:, :, ok2]
+            if not np.array_equal(a, b, equal_nan=True):
+                bad.append((v, nm))
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("device", [False, True])
