@@ -253,12 +253,14 @@ def aux_chain(device, cpu_too, rank=0, world=1, dist=None):
     return out
 
 
-def aux_mpc(device, rank=0, world=1, dist=None, B_total=4096, steps=500, max_iter=3):
+def aux_mpc(device, rank=0, world=1, dist=None, B_total=4096, steps=500, max_iter=3, weak=False):
     """BASELINE configs[4]: receding-horizon MPC — 4,096 closed-loop 2-link rollouts IN TOTAL sharded over the ranks, every
     plant step: <= max_iter warm-started iLQR iterations, apply u[0] to the plant, shift (ilqr_mpc_step); 500 steps.
     control-steps/s = B_total * steps / max-over-ranks wall time (each step returns its controls to the host)."""
     import ilqr_b200
     from ilqr_b200.sharding import shard_range
+    if weak:      # B_total rollouts PER GPU: the plant step is latency-bound (200 sequential time steps per pass), so a
+        B_total *= world   # fleet grows with the GPU count at constant step time
     lo, hi = shard_range(B_total, rank, world)
     x0 = np.asfortranarray(np.random.default_rng(5).random((B_total, 4))[lo:hi].T)
     with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, hi - lo, device=device)) as s:
@@ -280,7 +282,7 @@ def aux_mpc(device, rank=0, world=1, dist=None, B_total=4096, steps=500, max_ite
     return {"workload": "configs[4]: MPC, %d closed-loop 2-link rollouts in total on %d GPU(s) (%d per GPU), H=200, <= %d warm-started "
                         "iLQR iterations per plant step, %d plant steps" % (B_total, world, hi - lo, max_iter, steps),
             "value": B_total * steps / dt, "unit": "control-steps/s", "ms_per_plant_step": 1e3 * dt / steps, "n_gpus": world,
-            "scaling": "strong", "max_joint_error_after_run": err}
+            "scaling": "weak" if weak else "strong", "max_joint_error_after_run": err}
 
 
 def aux_configs(rank, world, local, dist, cpu_too):
@@ -288,9 +290,12 @@ def aux_configs(rank, world, local, dist, cpu_too):
     out = {}
     c3 = aux_chain(local, cpu_too, rank, world, dist)
     c5 = aux_mpc(local, rank, world, dist)
+    c5w = aux_mpc(local, rank, world, dist, steps=200, weak=True) if world > 1 else None
     if rank == 0:
         out["configs[3]"] = c3
         out["configs[4]"] = c5
+        if c5w:
+            out["configs[4] weak"] = c5w
         if world == 1:
             out["configs[2]"] = aux_floating(local)
     return out

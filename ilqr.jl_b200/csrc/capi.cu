@@ -41,7 +41,7 @@ void free_all(ilqr_handle* h) {
   cudaFree(s.r_status); cudaFree(s.r_iters); cudaFree(s.r_active);
   cudaFree(s.blocks_done); cudaFree(s.retry_list); cudaFree(s.n_retry);
   cudaFree(s.retire_list); cudaFree(s.move_src); cudaFree(s.move_dst); cudaFree(s.n_move);
-  cudaFree(h->ab_scratch); cudaFree(h->lin_scratch); cudaFree(h->round_xt); cudaFree(h->plant); cudaFree(h->u_applied);
+  cudaFree(h->ab_scratch); cudaFree(h->lin_scratch); cudaFree(h->lin_private); cudaFree(h->round_xt); cudaFree(h->plant); cudaFree(h->u_applied);
   cudaFree(h->stage_x); cudaFree(h->stage_u); cudaFree(h->stage_big); cudaFree(h->scratch_b);
   if (h->pinned_i32) cudaFreeHost(h->pinned_i32);
   cudaFree(h->round_ctr); cudaFree(h->round_traj); cudaFree(h->round_tab); cudaFree(h->round_done);
@@ -481,8 +481,9 @@ static int32_t backward_async(ilqr_handle* h) {
       const size_t nchunks = std::max<size_t>(1, (size_t)std::ceil((double)total / (budget_gb * 1e9)));
       h->lin_chunk = (int32_t)((((size_t)h->st.S + nchunks - 1) / nchunks + 31) / 32 * 32);
       CK(h, cudaMalloc((void**)&h->lin_scratch, per * (size_t)h->lin_chunk));
+      CK(h, cudaMalloc((void**)&h->lin_private, chain_split_private_bytes(h->prob.nq)));
     }
-    launch_bwd_chain_split(h->st, h->chain, h->cp, h->lin_scratch, h->lin_chunk, h->stream);
+    launch_bwd_chain_split(h->st, h->chain, h->cp, h->lin_scratch, h->lin_private, h->lin_chunk, h->stream);
   }
   else if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
   else if (split) launch_bwd_split_two_link(h->st, h->mp, h->cp, h->ab_scratch, coop, h->stream);

@@ -415,16 +415,31 @@ bwd_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
 constexpr int kLinThreads = 64;
 constexpr int kLinSteps = 2;    // time steps per scratch block (two neighbouring lin_chain lanes fill one 32-byte sector)
 
-template <int NQ> struct LinStore {   // per-link state in shared memory, [pair of items][thread][2]: 128-bit accesses
+// Per-thread link state.  S, Ψ̇, c (18 doubles per link: read in the inner loops) and the stage's q, q̇, v̇ live in shared
+// memory, [pair of items][thread][2]: 128-bit accesses.  The link inertias (10 doubles per link: written base → tip, read
+// once per tip → base sweep) live in a block-private global scratch that stays in L2 — the blocks are persistent, so the
+// scratch is grid × 64 threads × 560 B ≈ 32 MB however large the batch is.  With all 28 doubles in shared memory
+// (100 KB per block) an SM held 4 warps, one per scheduler, and every dependent-issue bubble was exposed; now 6.
+constexpr int kLinkSmemDoubles = 18, kLinkInertiaPairs = (chain_lin::kLinkDoubles - kLinkSmemDoubles) / 2;
+template <int NQ> struct LinStore {
   double2* base;                      // = smem + threadIdx.x
+  double* vbase;                      // the stage's q, q̇, v̇: [which][joint][thread], behind the link items
+  double2* inertia;                   // = private global scratch of this block + threadIdx.x, [link][pair][thread]
   __device__ __forceinline__ void get2(int i, int o, double& v0, double& v1) const {
-    const double2 t = base[((i * chain_lin::kLinkDoubles + o) >> 1) * kLinThreads];
+    // thread-private data: the default (L1-allocating) load is coherent with this thread's own earlier stores
+    const double2 t = (o >= kLinkSmemDoubles) ? inertia[(i * kLinkInertiaPairs + ((o - kLinkSmemDoubles) >> 1)) * kLinThreads]
+                                              : base[((i * kLinkSmemDoubles + o) >> 1) * kLinThreads];
     v0 = t.x; v1 = t.y;
   }
   __device__ __forceinline__ void put2(int i, int o, double v0, double v1) {
-    base[((i * chain_lin::kLinkDoubles + o) >> 1) * kLinThreads] = make_double2(v0, v1);
+    if (o >= kLinkSmemDoubles) inertia[(i * kLinkInertiaPairs + ((o - kLinkSmemDoubles) >> 1)) * kLinThreads] = make_double2(v0, v1);
+    else base[((i * kLinkSmemDoubles + o) >> 1) * kLinThreads] = make_double2(v0, v1);
   }
+  __device__ __forceinline__ double getv(int k, int i) const { return vbase[(k * NQ + i) * kLinThreads]; }
+  __device__ __forceinline__ void putv(int k, int i, double v) { vbase[(k * NQ + i) * kLinThreads] = v; }
 };
+template <int NQ> constexpr size_t kLinSmemBytes = sizeof(double) * kLinThreads * (NQ * kLinkSmemDoubles + 3 * NQ);
+template <int NQ> constexpr size_t kLinPrivateBytesPerBlock = sizeof(double2) * kLinThreads * NQ * kLinkInertiaPairs;
 template <int NQ> struct LinOut {
   double* blk; double* cur;   // blk: this (trajectory, 4-step block)'s scratch + 2·(step mod 4)
   __device__ __forceinline__ void stage(int s) { cur = blk + (size_t)s * chain_lin::StageItems<NQ>::kPairs * (2 * kLinSteps); }
@@ -436,29 +451,30 @@ template <int NQ> constexpr int kLinBlockDoubles = 4 * chain_lin::StageItems<NQ>
 
 template <int NQ>
 __global__ void __launch_bounds__(kLinThreads)
-lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, double* __restrict__ scratch, int slot0,
-          int nchunk, int Hb) {
+lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, double* __restrict__ scratch,
+          double2* __restrict__ priv, int slot0, int nchunk, int Hb) {
   extern __shared__ __align__(16) double lin_smem[];
   constexpr int n = 2 * NQ, m = NQ;
-  const long long t = (long long)blockIdx.x * kLinThreads + threadIdx.x;
   const int Hp = Hb * kLinSteps;
-  const int sl = (int)(t / Hp), k = (int)(t - (long long)sl * Hp);
-  if (sl >= nchunk || k >= st.H) return;
-  const int s = slot0 + sl;
-  if (!st.active[s]) return;
-  const int cur = st.cur[s];
-  const double* xp = st.x[cur] + ((int64_t)k * st.S + s) * n;
-  const double* up = st.u[cur] + ((int64_t)k * st.S + s) * m;
-  double x[n], u[m];
-#pragma unroll
-  for (int i = 0; i < n; ++i) x[i] = xp[i];
-#pragma unroll
-  for (int i = 0; i < m; ++i) u[i] = up[i];
-  LinStore<NQ> store{reinterpret_cast<double2*>(lin_smem) + threadIdx.x};
-  LinOut<NQ> out;
-  out.blk = scratch + ((size_t)sl * Hb + (k / kLinSteps)) * kLinBlockDoubles<NQ> + 2 * (k % kLinSteps);
-  out.cur = out.blk;
-  chain_lin::step_derivatives<NQ>(cp, x, u, store, out);
+  const long long total = (long long)nchunk * Hp;
+  LinStore<NQ> store{reinterpret_cast<double2*>(lin_smem) + threadIdx.x,
+                     lin_smem + kLinThreads * NQ * kLinkSmemDoubles + threadIdx.x,
+                     priv + (size_t)blockIdx.x * (kLinThreads * NQ * kLinkInertiaPairs) + threadIdx.x};
+  // persistent blocks: work item t = (trajectory of the chunk, time step), time step fastest
+#pragma unroll 1
+  for (long long t = (long long)blockIdx.x * kLinThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kLinThreads) {
+    const int sl = (int)(t / Hp), k = (int)(t - (long long)sl * Hp);
+    if (k >= st.H) continue;
+    const int s = slot0 + sl;
+    if (!st.active[s]) continue;
+    const int cur = st.cur[s];
+    const double* xp = st.x[cur] + ((int64_t)k * st.S + s) * n;
+    const double* up = st.u[cur] + ((int64_t)k * st.S + s) * m;
+    LinOut<NQ> out;
+    out.blk = scratch + ((size_t)sl * Hb + (k / kLinSteps)) * kLinBlockDoubles<NQ> + 2 * (k % kLinSteps);
+    out.cur = out.blk;
+    chain_lin::step_derivatives<NQ>(cp, xp, up, store, out);
+  }
 }
 
 template <int NQ> struct RicSmem : RiccatiSmem<2 * NQ, NQ> {
@@ -492,11 +508,16 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   uint32_t phase = 0;
   bool bad = false;
   const int udir = lane - n;
+  double xnext = (lane < n) ? X[((int64_t)(H - 1) * S + s) * n + lane] : 0.0;   // x, u one step ahead of their use
+  double unext = (lane < m) ? U[((int64_t)(H - 1) * S + s) * m + lane] : 0.0;
 #pragma unroll 1
   for (int k = H - 1; k >= 0; --k) {
     const int kk = k % kLinSteps;
-    const double xk = (lane < n) ? X[((int64_t)k * S + s) * n + lane] : 0.0;
-    const double uk = (lane < m) ? U[((int64_t)k * S + s) * m + lane] : 0.0;
+    const double xk = xnext, uk = unext;
+    if (k > 0) {
+      if (lane < n) xnext = X[((int64_t)(k - 1) * S + s) * n + lane];
+      if (lane < m) unext = U[((int64_t)(k - 1) * S + s) * m + lane];
+    }
     __syncwarp();   // the previous step is done with xs / us / blk
     if (lane < n) sm.xs[lane] = xk;
     if (lane < m) sm.us[lane] = uk;
@@ -528,22 +549,21 @@ ric_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
           dv[i] = fma(cin, tp[NQ + i], (lane == NQ + i) ? 1.0 : 0.0);
         }
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) {   // δu − ∂ID·(δq, δq̇)
-          double a = (udir == i) ? 1.0 : 0.0;
+        for (int i = 0; i < NQ; ++i) y[i] = (udir == i) ? 1.0 : 0.0;
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) {
+        for (int j = 0; j < NQ; ++j)     // δu − ∂ID·(δq, δq̇): column by column, NQ independent accumulators
+#pragma unroll
+          for (int i = 0; i < NQ; ++i) {
             const double2 J = it[kLinSteps * (i * NQ + j)];
-            a = fma(-J.x, dq[j], fma(-J.y, dv[j], a));
+            y[i] = fma(-J.x, dq[j], fma(-J.y, dv[j], y[i]));
           }
-          y[i] = a;
-        }
         double ld[2 * IT::kLDPairs];     // L and 1/d, read once for both substitutions
 #pragma unroll
         for (int p = 0; p < IT::kLDPairs; ++p) { const double2 t = it[kLinSteps * (NQ * NQ + p)]; ld[2 * p] = t.x; ld[2 * p + 1] = t.y; }
 #pragma unroll
-        for (int i = 1; i < NQ; ++i)     // M⁻¹ = L⁻ᵀ D⁻¹ L⁻¹
+        for (int j = 0; j < NQ - 1; ++j)   // M⁻¹ = L⁻ᵀ D⁻¹ L⁻¹; column-oriented: the updates of one column are independent
 #pragma unroll
-          for (int j = 0; j < i; ++j) y[i] = fma(-ld[IT::L(i, j)], y[j], y[i]);
+          for (int i = j + 1; i < NQ; ++i) y[i] = fma(-ld[IT::L(i, j)], y[j], y[i]);
 #pragma unroll
         for (int i = NQ - 1; i >= 0; --i) {
           double a = y[i] * ld[IT::Dinv(i)];
@@ -700,20 +720,29 @@ template <int NQ, bool FL> void run_bwd(const DevState& st, const ChainP& cp, co
   bwd_chain<NQ, FL><<<grid_for(st.nslots, kCW), kCW * 32, sizeof(BwdSmem<NQ, FL>) * kCW, s>>>(st, cp, cost);
 }
 template <int NQ> void set_attr_split() {
-  cudaFuncSetAttribute(lin_chain<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(sizeof(double) * kLinThreads * NQ * chain_lin::kLinkDoubles));
+  cudaFuncSetAttribute(lin_chain<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLinSmemBytes<NQ>);
   cudaFuncSetAttribute(ric_chain<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(RicSmem<NQ>) * kCW));
 }
 // bytes of linearisation scratch per trajectory
 template <int NQ> size_t split_scratch_bytes(int H) { return (size_t)((H + kLinSteps - 1) / kLinSteps) * kLinBlockDoubles<NQ> * sizeof(double); }
+// persistent grid of lin_chain: every SM filled once; its block-private scratch (link inertias)
+template <int NQ> int lin_grid() {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lin_chain<NQ>, kLinThreads, kLinSmemBytes<NQ>);
+  return std::max(1, sms) * std::max(1, per_sm);
+}
+template <int NQ> size_t split_private_bytes() { return (size_t)lin_grid<NQ>() * kLinPrivateBytesPerBlock<NQ>; }
 template <int NQ>
-void run_bwd_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, int chunk, cudaStream_t s) {
+void run_bwd_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, double* priv, int chunk, cudaStream_t s) {
   const int Hb = (st.H + kLinSteps - 1) / kLinSteps;
+  const int max_grid = lin_grid<NQ>();
   for (int slot0 = 0; slot0 < st.nslots; slot0 += chunk) {
     const int cnt = std::min(chunk, st.nslots - slot0);
     const long long items = (long long)cnt * Hb * kLinSteps;
-    lin_chain<NQ><<<(unsigned)((items + kLinThreads - 1) / kLinThreads), kLinThreads,
-                    sizeof(double) * kLinThreads * NQ * chain_lin::kLinkDoubles, s>>>(st, cp, scratch, slot0, cnt, Hb);
+    const int grid = (int)std::min<long long>((items + kLinThreads - 1) / kLinThreads, max_grid);
+    lin_chain<NQ><<<grid, kLinThreads, kLinSmemBytes<NQ>, s>>>(st, cp, scratch, reinterpret_cast<double2*>(priv), slot0, cnt, Hb);
     ric_chain<NQ><<<grid_for(cnt, kCW), kCW * 32, sizeof(RicSmem<NQ>) * kCW, s>>>(st, cp, cost, scratch, slot0, cnt, Hb);
   }
 }

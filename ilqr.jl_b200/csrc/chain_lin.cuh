@@ -22,7 +22,10 @@
 // Output per (trajectory, time step): for each RK4 stage the 126 numbers [(∂ID/∂q, ∂ID/∂q̇) pairs (7×7) | L, 1/d of
 // M = L·diag(d)·Lᵀ], consumed by ric_chain (chain_kernels.cuh), which applies M⁻¹, chains the four stages and runs the
 // Riccati step, one warp per trajectory.  Per-link state (S, Ψ̇, c, I: 28 doubles per link) lives in shared memory,
-// [item][thread]; link velocities and accelerations are re-derived on the way back (v_{i−1} = v_i − S_i q̇_i).
+// [item][thread]; link velocities and accelerations are re-derived on the way back (v_{i−1} = v_i − S_i q̇_i).  The stage's
+// q, q̇, v̇ are parked there as well (St::putv / getv): the link loops are rolled, and a register array indexed by the loop
+// counter would live in local memory, whose loads miss the small L1 left beside 200 KB of shared memory (ncu: 23 % of
+// the kernel's stall samples were long-scoreboard waits on exactly those loads).
 #pragma once
 #include "chain_params.cuh"
 #include "fastmath.cuh"
@@ -106,10 +109,10 @@ template <int NQ> struct StageItems {
   static ILQR_CLC int Dinv(int i) { return NQ * (NQ - 1) / 2 + i; }
 };
 
-// One RK4 stage at (q, qd) with control u: v̇ → vdot, the stage's items → out.put(item, value).
+// One RK4 stage at (q, qd) = st.getv(0 / 1, i) with control u: v̇ → st.putv(2, i, ·), the stage's items → out.put(item, value).
+constexpr int kVQ = 0, kVQd = 1, kVVdot = 2;
 template <int NQ, class St, class Out>
-ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const double (&qd)[NQ], const double (&u)[NQ], St& st,
-                               Out& out, double (&vdot)[NQ]) {
+ILQR_CL void stage_derivatives(const ChainP& cp, const double* __restrict__ u, St& st, Out& out) {
   using IT = StageItems<NQ>;
   const sv zero6 = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
   // ---- pass A (base → tip): kinematics, joint axes, world inertias, Ψ̇; running v, a⁰ (acceleration with q̈ = 0)
@@ -123,7 +126,8 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
                  R[3] * cp.xyz[i][0] + R[4] * cp.xyz[i][1] + R[5] * cp.xyz[i][2],
                  R[6] * cp.xyz[i][0] + R[7] * cp.xyz[i][1] + R[8] * cp.xyz[i][2]};
       double s, c;
-      sincos_bf(q[i], &s, &c);
+      sincos_bf(st.getv(kVQ, i), &s, &c);
+      const double qdi = st.getv(kVQd, i);
       double T[9];   // R·Rf
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -157,8 +161,8 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
       I.J[3] = rirt(1, 1) + m * (cc - cw.y * cw.y); I.J[4] = rirt(1, 2) - m * cw.y * cw.z;
       I.J[5] = rirt(2, 2) + m * (cc - cw.z * cw.z);
       const sv Pd = crm(v, S);
-      v = fma6(qd[i], S, v);
-      a0 = fma6(qd[i], Pd, a0);
+      v = fma6(qdi, S, v);
+      a0 = fma6(qdi, Pd, a0);
       st6(st, i, 0, S); st6(st, i, 6, Pd);
       stI(st, i, I);
     }
@@ -173,14 +177,15 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
     for (int i = NQ - 1; i >= 0; --i) {
       const sv S = ld6(st, i, 0), Pd = ld6(st, i, 6);
       const si I = ldI(st, i);
+      const double qdi = st.getv(kVQd, i);
       iadd(IC, I);
       FC = FC + imul(I, a0) + crf(v, imul(I, v));
       rhs[i] = u[i] - dot6(S, FC);
       const sv U = imul(IC, S);
 #pragma unroll
       for (int j = 0; j <= i; ++j) M[i][j] = dot6(U, ld6(st, j, 0));
-      v = fma6(-qd[i], S, v);
-      a0 = fma6(-qd[i], Pd, a0);
+      v = fma6(-qdi, S, v);
+      a0 = fma6(-qdi, Pd, a0);
     }
   }
   // ---- M = L·diag(d)·Lᵀ (symmetric positive definite: no pivoting), v̇ = M⁻¹(u − bias)
@@ -217,6 +222,7 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
 #pragma unroll
     for (int p = 0; p < IT::kLDPairs; ++p) out.put_pair(NQ * NQ + p, ld[2 * p], ld[2 * p + 1]);
   }
+  double vdot[NQ];
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {   // L y = rhs
     double a = rhs[i];
@@ -231,14 +237,17 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
     for (int j = i + 1; j < NQ; ++j) a = fm_fma(-M[j][i], vdot[j], a);
     vdot[i] = a;
   }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) st.putv(kVVdot, i, vdot[i]);
   // ---- pass C (base → tip): accelerations with q̈ = v̇, c_i = a_i × S_i − Ψ̇_i × v_i
   v = zero6;
   sv a = {{0.0, 0.0, 0.0}, {-cp.g[0], -cp.g[1], -cp.g[2]}};
 #pragma unroll 1
   for (int i = 0; i < NQ; ++i) {
     const sv S = ld6(st, i, 0), Pd = ld6(st, i, 6);
-    v = fma6(qd[i], S, v);
-    a = fma6(vdot[i], S, fma6(qd[i], Pd, a));
+    const double qdi = st.getv(kVQd, i), vdi = st.getv(kVVdot, i);
+    v = fma6(qdi, S, v);
+    a = fma6(vdi, S, fma6(qdi, Pd, a));
     st6(st, i, 12, crm(a, S) - crm(Pd, v));
   }
   // ---- pass D (tip → base): composites I^C, D^C (D11: 9 numbers + Σf: 3), f^C; the entries of ∂ID/∂q, ∂ID/∂q̇
@@ -247,10 +256,13 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
     sv FC = zero6;
     double D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // D11, row-major
     v3 Fl = {0.0, 0.0, 0.0};
+    // software pipeline: the inertia of link i − 1 is requested (block-private global scratch: an L2 round trip) before
+    // the entry loop of link i and consumed after it; v and a step back early for the same reason
+    si I = ldI(st, NQ - 1);
 #pragma unroll 1
     for (int i = NQ - 1; i >= 0; --i) {
       const sv S = ld6(st, i, 0), Pd = ld6(st, i, 6), C = ld6(st, i, 12);
-      const si I = ldI(st, i);
+      const double qdi = st.getv(kVQd, i), vdi = st.getv(kVVdot, i);
       const sv hv = imul(I, v);   // (n, f)
       {
         // D11 += −[n]× + [ω]×J − J[ω]× − ([v]×[h]× + [h]×[v]×);   [a]×[b]× = b aᵀ − (a·b) 1
@@ -276,6 +288,9 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
       Fl = Fl + hv.b;
       iadd(IC, I);
       FC = FC + imul(I, a) + crf(v, hv);
+      v = fma6(-qdi, S, v);
+      a = fma6(-vdi, S, fma6(-qdi, Pd, a));
+      if (i > 0) I = ldI(st, i - 1);
       auto Dmul = [&](sv x) -> sv {   // D^C x = [D11 x_ω ; −2 F × x_ω]
         return {{D[0] * x.a.x + D[1] * x.a.y + D[2] * x.a.z, D[3] * x.a.x + D[4] * x.a.y + D[5] * x.a.z, D[6] * x.a.x + D[7] * x.a.y + D[8] * x.a.z},
                 (-2.0) * cross(Fl, x.a)};
@@ -293,29 +308,28 @@ ILQR_CL void stage_derivatives(const ChainP& cp, const double (&q)[NQ], const do
         out.put_pair(i * NQ + j, dot6(U, Cj) + dot(T.a, Pj.a), 2.0 * dot6(U, Pj) + dot(T.a, Sj.a));
         if (j < i) out.put_pair(j * NQ + i, dot6(Sj, gv), dot6(Sj, hq));
       }
-      v = fma6(-qd[i], S, v);
-      a = fma6(-vdot[i], S, fma6(-qd[i], Pd, a));
     }
   }
   (void)v_tip; (void)a0_tip;
 }
 
 // All four stages of the RK4 step at (x, u) (RBD_helper_functions.jl:72-79); Out::stage(s) selects the stage's block.
+// x and u are re-read through their pointers at every stage and the RK4 increments k = Δt·(q̇, v̇) are rebuilt from the
+// previous stage's q̇, v̇ in the store, so nothing but the two pointers stays in registers across a stage.
 template <int NQ, class St, class Out>
-ILQR_CL void step_derivatives(const ChainP& cp, const double (&x)[2 * NQ], const double (&u)[NQ], St& st, Out& out) {
-  double kq[NQ], kv[NQ];
+ILQR_CL void step_derivatives(const ChainP& cp, const double* __restrict__ x, const double* __restrict__ u, St& st, Out& out) {
 #pragma unroll
-  for (int i = 0; i < NQ; ++i) { kq[i] = 0.0; kv[i] = 0.0; }
+  for (int i = 0; i < NQ; ++i) { st.putv(kVQd, i, 0.0); st.putv(kVVdot, i, 0.0); }
 #pragma unroll 1
   for (int stg = 0; stg < 4; ++stg) {
     const double cin = (stg == 0) ? 0.0 : (stg == 3 ? 1.0 : 0.5);
-    double q[NQ], qd[NQ], vdot[NQ];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) { q[i] = fm_fma(cin, kq[i], x[i]); qd[i] = fm_fma(cin, kv[i], x[NQ + i]); }
+    for (int i = 0; i < NQ; ++i) {
+      const double kq = cp.dt * st.getv(kVQd, i), kv = cp.dt * st.getv(kVVdot, i);
+      st.putv(kVQ, i, fm_fma(cin, kq, x[i])); st.putv(kVQd, i, fm_fma(cin, kv, x[NQ + i]));
+    }
     out.stage(stg);
-    stage_derivatives<NQ>(cp, q, qd, u, st, out, vdot);
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) { kq[i] = cp.dt * qd[i]; kv[i] = cp.dt * vdot[i]; }
+    stage_derivatives<NQ>(cp, u, st, out);
   }
 }
 

@@ -88,7 +88,8 @@ void launch_bwd_chain(const DevState& st, const ChainP& cp, bool floating, const
 // split backward pass for fixed-base chains: lin_chain (thread per (trajectory, time step), analytic inverse-dynamics
 // derivatives → scratch) + ric_chain (warp per trajectory); chunk = trajectories the scratch holds
 size_t chain_split_scratch_bytes(int nq, int H);
-void launch_bwd_chain_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, int chunk, cudaStream_t s);
+size_t chain_split_private_bytes(int nq);
+void launch_bwd_chain_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, double* priv, int chunk, cudaStream_t s);
 void launch_fwd_chain(const DevState& st, const ChainP& cp, bool floating, const CostP& cost, cudaStream_t s);
 void launch_rollout_init_chain(const DevState& st, const ChainP& cp, bool floating, const double* d_x0 /*[slot][n]*/,
                                cudaStream_t s);

@@ -33,9 +33,15 @@ size_t chain_split_scratch_bytes(int nq, int H) {
   ILQR_CHAIN_DISPATCH(nq, return split_scratch_bytes<NQ>(H);)
   return 0;
 }
-void launch_bwd_chain_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, int chunk, cudaStream_t s) {
+// block-private scratch of the persistent lin_chain grid (link inertias, L2 resident), per handle
+size_t chain_split_private_bytes(int nq) {
+  ILQR_CHAIN_DISPATCH(nq, return split_private_bytes<NQ>();)
+  return 0;
+}
+void launch_bwd_chain_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, double* priv, int chunk,
+                            cudaStream_t s) {
   if (st.nslots <= 0) return;
-  ILQR_CHAIN_DISPATCH(cp.nq, run_bwd_split<NQ>(st, cp, cost, scratch, chunk, s);)
+  ILQR_CHAIN_DISPATCH(cp.nq, run_bwd_split<NQ>(st, cp, cost, scratch, priv, chunk, s);)
 }
 
 bool chain_supported(int nq, bool floating) { return floating ? (nq == 1 || nq == 2) : (nq == 2 || nq == 3 || nq == 6 || nq == 7); }

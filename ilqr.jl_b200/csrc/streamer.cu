@@ -183,6 +183,7 @@ struct ilqr_streamer {
   int64_t prof_rounds = 0;
   std::vector<char> done_flags;   // by sequence number
   bool stop = false;
+  bool generic = false;           // rigid-body / NVRTC models: batch-at-a-time engine (streamer_main_generic)
   int32_t rc = 0;
   std::string err;
 };
@@ -348,6 +349,106 @@ void streamer_main(ilqr_streamer* s) {
   cudaStreamSynchronize(h->stream);
 }
 
+// Models without a fused round kernel (serial-chain rigid bodies, NVRTC user models): the same submit / wait interface
+// on top of the streaming-admission loop of ilqr_stream_solve_device (capi.cu).  The worker solves the submitted batches
+// in order — each as one stream through the handle's slots, so a batch larger than the slot count keeps every launch
+// full — while the uploads of the batches behind it and the copy-backs of the batches before it run on the copy streams.
+// Per-trajectory arithmetic is that of ilqr_solve: results are bit-identical.
+void streamer_main_generic(ilqr_streamer* s) {
+  ilqr_handle* h = s->h;
+  cudaSetDevice(h->device);
+  const size_t N = h->prob.H + 1, H = h->prob.H, n = h->prob.n, m = h->prob.m, Bb = (size_t)s->Bb;
+  int64_t uploaded = 0, solved = 0;
+  int32_t rc = streamer_alloc_staging(s, true, true);
+  cudaEvent_t ev_solved = nullptr;
+  if (rc == 0 && cudaEventCreateWithFlags(&ev_solved, cudaEventDisableTiming) != cudaSuccess) rc = fail(h, ILQR_ERR_CUDA, "event");
+  auto finish = [&](std::vector<int64_t>& fin) {
+    if (fin.empty()) return;
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      for (int64_t q : fin) {
+        s->work[q % s->R].busy = false; s->ring[q % s->R].busy = false;
+        s->done_flags[(size_t)q] = 1; ++s->completed;
+      }
+    }
+    s->cv_done.notify_all();
+    fin.clear();
+  };
+  while (rc == 0) {
+    int64_t sub;
+    {
+      std::unique_lock<std::mutex> lk(s->mu);
+      s->cv_work.wait(lk, [&] { return s->stop || s->submitted > s->completed; });
+      if (s->submitted == s->completed) break;
+      sub = s->submitted;
+    }
+    // 1. uploads of every batch submitted so far (copy stream)
+    for (; uploaded < sub && rc == 0; ++uploaded) {
+      ilqr_streamer::Entry& e = s->work[uploaded % s->R];
+      {
+        std::lock_guard<std::mutex> lk(s->mu);
+        e = s->ring[uploaded % s->R];
+      }
+      if (e.host) {
+        const size_t slot = (size_t)(uploaded % s->R);
+        if (cudaMemcpyAsync(s->sx + slot * Bb * N * n, e.x, sizeof(double) * Bb * N * n, cudaMemcpyHostToDevice, s->cs_in) != cudaSuccess ||
+            cudaMemcpyAsync(s->su + slot * Bb * H * m, e.u, sizeof(double) * Bb * H * m, cudaMemcpyHostToDevice, s->cs_in) != cudaSuccess ||
+            cudaEventRecord(e.ev_in, s->cs_in) != cudaSuccess)
+          rc = fail(h, ILQR_ERR_CUDA, "streamer upload");
+      }
+      e.stage = 1;
+    }
+    std::vector<int64_t> fin;
+    // 2. solve the oldest batch that has not been solved yet
+    if (rc == 0 && solved < uploaded) {
+      ilqr_streamer::Entry& e = s->work[solved % s->R];
+      const size_t slot = (size_t)(solved % s->R);
+      if (e.host && cudaEventSynchronize(e.ev_in) != cudaSuccess) rc = fail(h, ILQR_ERR_CUDA, "streamer upload");
+      const double* in_x = e.host ? s->sx + slot * Bb * N * n : e.x;
+      const double* in_u = e.host ? s->su + slot * Bb * H * m : e.u;
+      // the solve needs x and u outputs; what the caller did not ask for lands in the staging ring and stays there
+      double* ox = (e.host || !e.xo) ? s->sox + slot * Bb * N * n : e.xo;
+      double* ou = (e.host || !e.uo) ? s->sou + slot * Bb * H * m : e.uo;
+      double* oc = e.host ? s->scost + slot * Bb : e.cost;
+      int32_t* oi = e.host ? s->siters + slot * Bb : e.iters;
+      int32_t* os = e.host ? s->sstatus + slot * Bb : e.status;
+      if (rc == 0) rc = ilqr_stream_solve_device(h, (int64_t)Bb, in_x, in_u, s->max_iter, s->tol, ox, ou, oc, oi, os, nullptr);
+      if (rc == 0 && e.host) {
+        bool ok = cudaEventRecord(ev_solved, h->stream) == cudaSuccess && cudaStreamWaitEvent(s->cs_out, ev_solved, 0) == cudaSuccess;
+        if (ok && e.xo) ok = cudaMemcpyAsync(e.xo, ox, sizeof(double) * Bb * N * n, cudaMemcpyDeviceToHost, s->cs_out) == cudaSuccess;
+        if (ok && e.uo) ok = cudaMemcpyAsync(e.uo, ou, sizeof(double) * Bb * H * m, cudaMemcpyDeviceToHost, s->cs_out) == cudaSuccess;
+        if (ok && e.cost) ok = cudaMemcpyAsync(e.cost, oc, sizeof(double) * Bb, cudaMemcpyDeviceToHost, s->cs_out) == cudaSuccess;
+        if (ok && e.iters) ok = cudaMemcpyAsync(e.iters, oi, sizeof(int32_t) * Bb, cudaMemcpyDeviceToHost, s->cs_out) == cudaSuccess;
+        if (ok && e.status) ok = cudaMemcpyAsync(e.status, os, sizeof(int32_t) * Bb, cudaMemcpyDeviceToHost, s->cs_out) == cudaSuccess;
+        ok = ok && cudaEventRecord(e.ev_out, s->cs_out) == cudaSuccess;
+        if (!ok) rc = fail(h, ILQR_ERR_CUDA, "streamer copy-back");
+        e.stage = 3;
+      } else if (rc == 0) {
+        fin.push_back(e.seq);
+      }
+      ++solved;
+    }
+    // 3. copy-backs that have landed; with nothing left to solve, wait for the oldest one instead of spinning
+    for (int i = 0; i < s->R && rc == 0; ++i) {
+      ilqr_streamer::Entry& e = s->work[i];
+      if (!e.busy || e.stage != 3) continue;
+      if (solved == sub && cudaEventSynchronize(e.ev_out) != cudaSuccess) rc = fail(h, ILQR_ERR_CUDA, "streamer copy-back");
+      if (rc == 0 && cudaEventQuery(e.ev_out) == cudaSuccess) { e.stage = 4; fin.push_back(e.seq); }
+    }
+    finish(fin);
+  }
+  if (rc != 0) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->rc = rc; s->err = h->err;
+    s->completed = s->submitted;
+    for (auto& f : s->done_flags) f = 1;
+    for (auto& e : s->ring) e.busy = false;
+  }
+  s->cv_done.notify_all();
+  cudaStreamSynchronize(h->stream);
+  if (ev_solved) cudaEventDestroy(ev_solved);
+}
+
 }  // namespace
 
 extern "C" {
@@ -358,13 +459,14 @@ int32_t ilqr_streamer_create(const ilqr_problem* prob, int32_t batch_size, int32
   *out = nullptr;
   ilqr_handle* h = nullptr;
   if (int32_t rc = ilqr_create(prob, &h)) { g_streamer_err = ilqr_last_error(nullptr); return rc; }
-  if (h->is_chain || h->is_custom || h->prob.trace_iters != 0) {
+  if (h->prob.trace_iters != 0) {
     ilqr_destroy(h);
-    g_streamer_err = "ilqr_streamer: the fused rounds exist for ILQR_MODEL_TWO_LINK (trace_iters = 0) only";
+    g_streamer_err = "ilqr_streamer: trace_iters must be 0 (per-iteration traces are a batch-path feature)";
     return ILQR_ERR_INVALID;
   }
   ilqr_streamer* s = new ilqr_streamer();
   s->h = h; s->Bb = batch_size; s->R = ring; s->max_iter = max_iter; s->tol = tol;
+  s->generic = !fused_stream_ok(h);   // rigid-body and NVRTC models: no fused round kernel, batch-at-a-time engine
   bool ok = cudaSetDevice(h->device) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&s->cs_in, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&s->cs_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -376,7 +478,7 @@ int32_t ilqr_streamer_create(const ilqr_problem* prob, int32_t batch_size, int32
     ilqr_destroy(h); delete s;
     return ILQR_ERR_CUDA;
   }
-  s->worker = std::thread(streamer_main, s);
+  s->worker = std::thread(s->generic ? streamer_main_generic : streamer_main, s);
   *out = s;
   return ILQR_OK;
 }
@@ -404,6 +506,11 @@ const char* ilqr_streamer_last_error(const ilqr_streamer* s) { return s ? s->err
 static int64_t streamer_submit(ilqr_streamer* s, bool host, bool x0mode, const double* x, const double* u, double* xo, double* uo,
                                double* cost, int32_t* iters, int32_t* status, const double* xt = nullptr) {
   if (!s || !x || (!u && !x0mode)) return ILQR_ERR_INVALID;   // every output is nullable
+  if (s->generic && (x0mode || xt)) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->err = "ilqr_streamer: x0 and x_traj submissions exist for ILQR_MODEL_TWO_LINK only (other models: x_init, u_init)";
+    return ILQR_ERR_INVALID;
+  }
   int64_t seq;
   {
     std::unique_lock<std::mutex> lk(s->mu);

@@ -12,7 +12,10 @@ namespace ilqr {
 template <int n, int m> struct RiccatiSmem {
   // 16-byte aligned so that the broadcast reads of a column (even n: pairs of rows) can be 128-bit loads
   alignas(16) double S[n * n];              // value Hessian, column-major
-  alignas(16) double AB[n * (n + m)];       // [A | B], column-major
+  static constexpr int NCp = (n + m + 1) & ~1;   // row stride of [A | B]: n + m rounded up to even
+  alignas(16) double AB[n * NCp];           // [A | B], ROW-major (element (r, c) at c + NCp·r): what a lane reads of it is a run
+                                            // of one row (all A columns, or all B columns), so the products below walk the
+                                            // rows in the outer loop and keep n (or m) independent accumulators going
   alignas(16) double GH[m * (n + m + 1)];   // [G | H | g], unregularised
   alignas(16) double Kd[m * (n + 1)];       // [K | δu]
   alignas(16) double U[m * m];              // upper factor of H_reg (row-permuted)
@@ -61,7 +64,7 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
   // ---- optimal_controller_param (src/backward_pass.jl:177-186) in column-owner form
   if (lane < n + m) {
 #pragma unroll
-    for (int r = 0; r < n; ++r) sm.AB[r + n * lane] = ab[r];
+    for (int r = 0; r < n; ++r) sm.AB[lane + RiccatiSmem<n, m>::NCp * r] = ab[r];
   }
   __syncwarp();
   double w[n];   // S·(own column of [A|B]); the affine lane carries s itself
@@ -75,10 +78,14 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
   }
   double gh[m];   // own column of [G | H | g] = Bᵀ·w (+ cost terms)
 #pragma unroll
-  for (int i = 0; i < m; ++i) {
-    double a = 0.0;
+  for (int i = 0; i < m; ++i) gh[i] = 0.0;
 #pragma unroll
-    for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * (n + i)], w[r], a);
+  for (int r = 0; r < n; ++r)
+#pragma unroll
+    for (int i = 0; i < m; ++i) gh[i] = fma(sm.AB[n + i + RiccatiSmem<n, m>::NCp * r], w[r], gh[i]);
+#pragma unroll
+  for (int i = 0; i < m; ++i) {
+    double a = gh[i];
     if constexpr (GENERAL) {
       if (lane < NC) a += cu[i];                         // 𝐏 (x lanes), 𝐑 (u lanes), 𝐫 (affine lane)
     } else {
@@ -138,17 +145,20 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
   {
     double t[m];
 #pragma unroll
-    for (int i = 0; i < m; ++i) {
-      double a = gh[i];
+    for (int i = 0; i < m; ++i) t[i] = gh[i];
 #pragma unroll
-      for (int l = 0; l < m; ++l) a = fma(sm.GH[i + m * (n + l)], kc[l], a);
-      t[i] = a;
-    }
+    for (int l = 0; l < m; ++l)
+#pragma unroll
+      for (int i = 0; i < m; ++i) t[i] = fma(sm.GH[i + m * (n + l)], kc[l], t[i]);
+#pragma unroll
+    for (int i = 0; i < n; ++i) nw[i] = 0.0;
+#pragma unroll
+    for (int r = 0; r < n; ++r)       // Aᵀ·w, row by row: n independent accumulators
+#pragma unroll
+      for (int i = 0; i < n; ++i) nw[i] = fma(sm.AB[i + RiccatiSmem<n, m>::NCp * r], w[r], nw[i]);
 #pragma unroll
     for (int i = 0; i < n; ++i) {
-      double a = 0.0;
-#pragma unroll
-      for (int r = 0; r < n; ++r) a = fma(sm.AB[r + n * i], w[r], a);
+      double a = nw[i];
 #pragma unroll
       for (int l = 0; l < m; ++l) a = fma(sm.Kd[l + m * i], t[l], a);
 #pragma unroll

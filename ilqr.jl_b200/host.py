@@ -445,7 +445,8 @@ class SolverPool:
 
 
 class Streamer:
-    """ilqr_streamer: continuous batching over the fused rounds (2-link model).  `problem.B` is the number of SLOTS
+    """ilqr_streamer: continuous batching — over the fused rounds for the 2-link model, over the streaming-admission loop
+    (one submitted batch at a time) for the rigid-body and NVRTC models.  `problem.B` is the number of SLOTS
     (size it to the machine: 148 SMs x 12 warps x 32 = 56,832 on B200), `batch_size` the number of trajectories in
     every submitted batch; up to `ring` batches are in flight (submit blocks while the ring is full)."""
 

@@ -312,7 +312,12 @@ int64_t ilqr_pool_launch_count(const ilqr_pool* pool);
  * submit blocks while the ring is full.  Host submissions are uploaded on a copy stream while the rounds run and
  * copied back as soon as the batch's last trajectory has retired.  Every trajectory comes out bit-identical to
  * ilqr_solve / ilqr_fit on its batch.  Size p->B to the machine (148 SMs x 12 warps x 32 lanes = 56,832 on B200),
- * not to the batch.  Buffers must stay valid until the ticket has been waited for. */
+ * not to the batch.  Buffers must stay valid until the ticket has been waited for.
+ * Other models (ILQR_MODEL_SERIAL_CHAIN, _FLOATING_CHAIN, _CUSTOM) have no fused round kernel: the same calls run a
+ * batch-at-a-time engine on the streaming-admission loop of ilqr_stream_solve_device (each submitted batch is one stream
+ * through the p->B slots; uploads of the batches behind it and copy-backs of those before it overlap the solve; results
+ * bit-identical to ilqr_solve).  For them only the x_init / u_init submissions exist: ilqr_streamer_submit_x0* and
+ * ilqr_streamer_submit_traj* return ILQR_ERR_INVALID. */
 typedef struct ilqr_streamer ilqr_streamer;
 int32_t ilqr_streamer_create(const ilqr_problem* p, int32_t batch_size, int32_t ring, int32_t max_iter, double tol,
                              ilqr_streamer** out);

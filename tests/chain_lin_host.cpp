@@ -15,6 +15,9 @@ template <int NQ> struct HostStore {
   double a[NQ * chain_lin::kLinkDoubles];
   void get2(int i, int o, double& v0, double& v1) const { v0 = a[i * chain_lin::kLinkDoubles + o]; v1 = a[i * chain_lin::kLinkDoubles + o + 1]; }
   void put2(int i, int o, double v0, double v1) { a[i * chain_lin::kLinkDoubles + o] = v0; a[i * chain_lin::kLinkDoubles + o + 1] = v1; }
+  double v[3 * NQ];
+  double getv(int k, int i) const { return v[k * NQ + i]; }
+  void putv(int k, int i, double x) { v[k * NQ + i] = x; }
 };
 template <int NQ> struct HostOut {
   double* base; double* cur;

@@ -342,6 +342,59 @@ def test_stream_admission_on_a_rigid_body_model():
     assert np.array_equal(ox.cpu().numpy().transpose(2, 1, 0), ref["x"]) and np.array_equal(ou.cpu().numpy().transpose(2, 1, 0), ref["u"])
 
 
+@pytest.mark.parametrize("device", [False, True])
+def test_streamer_on_a_rigid_body_model_equals_batch_solves(device):
+    """ilqr_streamer_* for a model without a fused round kernel (3-joint chain): batches of 48 trajectories through 32
+    slots, host submissions (upload / copy-back on the copy streams, nullable outputs) and device submissions; every
+    batch bit-identical to ilqr_solve.  x0 / x_traj submissions are 2-link features and must be refused, not misread."""
+    import torch
+    Bb, nb, slots, H = 48, 4, 32, 12
+    spec, prob_all, x0, x, u = _setup(3, True, Bb * nb, H, 903, (0.0, 0.0, -9.81), hard=(1000.0, 0.05))
+    refs = []
+    pb = ilqr_b200.Problem.from_buffer_copy(prob_all); pb.B = Bb; pb.trace_iters = 0
+    with ilqr_b200.BatchSolver(pb) as s:
+        for b in range(nb):
+            sl = slice(b * Bb, (b + 1) * Bb)
+            refs.append(s.solve(np.asfortranarray(x[:, :, sl]), np.asfortranarray(u[:, :, sl]), max_iter=25, tol=1e-8))
+    assert len(set(np.concatenate([r["iters"] for r in refs]).tolist())) > 3
+    ps = ilqr_b200.Problem.from_buffer_copy(prob_all); ps.B = slots; ps.trace_iters = 0
+
+    def mk(a):
+        t = torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0)))
+        return t.cuda() if device else t.pin_memory()
+
+    n = x.shape[1]; m = u.shape[1]
+    ins, outs = [], []
+    for b in range(nb):
+        sl = slice(b * Bb, (b + 1) * Bb)
+        o = [torch.zeros((Bb, n, H + 1), dtype=torch.float64), torch.zeros((Bb, m, H), dtype=torch.float64), torch.zeros(Bb, dtype=torch.float64),
+             torch.zeros(Bb, dtype=torch.int32), torch.zeros(Bb, dtype=torch.int32)]
+        outs.append([t.cuda() if device else t.pin_memory() for t in o])
+        ins.append((mk(x[:, :, sl]), mk(u[:, :, sl])))
+    with ilqr_b200.Streamer(ps, Bb, ring=2, max_iter=25, tol=1e-8) as st:
+        with pytest.raises(ilqr_b200.IlqrError):
+            st.submit_ptrs(ins[0][0].data_ptr(), None, *[t.data_ptr() for t in outs[0]], device=device, x0=True)
+        tickets = []
+        for b in range(nb):
+            ptrs = [t.data_ptr() for t in outs[b]]
+            if b == 2:
+                ptrs[0] = None          # the caller wants ū and the scalars only
+            tickets.append(st.submit_ptrs(ins[b][0].data_ptr(), ins[b][1].data_ptr(), *ptrs, device=device))
+        for t in tickets:
+            st.wait(t)
+        assert st.launch_count() > 0
+    torch.cuda.synchronize()
+    for b in range(nb):
+        ox, ou, oc, oi, os_ = [t.cpu().numpy() for t in outs[b]]
+        assert np.array_equal(oi, refs[b]["iters"]) and np.array_equal(os_, refs[b]["status"]), b
+        assert np.array_equal(oc, refs[b]["cost"]), b
+        assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b
+        if b == 2:
+            assert not ox.any()
+        else:
+            assert np.array_equal(ox.transpose(2, 1, 0), refs[b]["x"]), b
+
+
 @pytest.mark.parametrize("nq,general,gravity,H", [(7, True, (0.2, -0.1, -9.81), 15), (3, True, (0.0, 0.0, -9.81), 13), (2, True, (0, 0, 0), 1),
                                                  (6, False, (0.0, 0.0, -9.81), 6)])
 def test_split_backward_pass_chunked_and_against_the_dual_number_kernel(monkeypatch, nq, general, gravity, H):
