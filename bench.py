@@ -229,15 +229,18 @@ def aux_chain(device, cpu_too, rank=0, world=1, dist=None):
         t = torch.tensor(stats, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); stats = t.cpu().numpy()
         t = torch.tensor(sums, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); sums = t.cpu().numpy()
     dt, bwd_ms, fwd_ms = (float(v) for v in stats)
-    sass = (sass_counts() or {}).get("bwd_chain7")
+    sass_all = sass_counts() or {}
     out = {"workload": "configs[3]: synthetic 7-DoF serial chain (n=14, m=7), B=262144 in total, H=100, fp64, sharded over %d GPU(s) "
                        "(%d trajectories per GPU)" % (world, hi - lo),
            "value": Bc / dt, "unit": "solves/s", "n_gpus": world, "scaling": "strong", "fit_s": dt, "mean_iterations": sums[0] / Bc,
            "converged_fraction": sums[1] / Bc,
            "bwd_chain_ms_first_iteration": bwd_ms, "fwd_chain_ms_first_iteration": fwd_ms,
            "bwd_chain_ms_full_batch": bwd_ms * (Bc / (hi - lo)),
-           "bwd_chain_static_fp64_instructions": sass["fp64"] if sass else None,
-           "note": "bwd_chain_ms_full_batch = first-iteration backward time scaled to 262,144 trajectories (= the measured time at 1 GPU)"}
+           "backward_kernels": "lin_chain<7> (closed-form inverse-dynamics derivatives, one thread per (trajectory, time step), persistent blocks) "
+                               "+ ric_chain<7> (M^-1, RK4 chaining and the Riccati step, one warp per trajectory)",
+           "static_fp64_instructions": {k: (sass_all[k]["fp64"] if sass_all.get(k) else None) for k in ("lin_chain7", "ric_chain7")},
+           "note": "bwd_chain_ms_full_batch = first-iteration backward time (lin_chain + ric_chain over all chunks) scaled to 262,144 "
+                   "trajectories (= the measured time at 1 GPU); round 1: 877 ms with one dual-number pass per tangent direction"}
     if cpu_too:
         from oracle import oracle_py as orc
         cores = os.cpu_count() or 1
@@ -349,7 +352,8 @@ def sass_counts():
                 return v
         return None
     return {"round": pick("round_lpt_two_linkILi12ELi4"), "round16": pick("round_lpt_two_linkILi16"),
-            "bwd": pick("bwd_lpt_two_link"), "fwd": pick("fwd_lpt_two_linkILb0"), "bwd_chain7": pick("bwd_chainILi7ELb0")}
+            "bwd": pick("bwd_lpt_two_link"), "fwd": pick("fwd_lpt_two_linkILb0"), "bwd_chain7": pick("bwd_chainILi7ELb0"),
+            "lin_chain7": pick("lin_chainILi7"), "ric_chain7": pick("ric_chainILi7")}
 
 
 def ncu_file_metrics(name, kernel_tag):
