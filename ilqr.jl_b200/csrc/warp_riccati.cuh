@@ -16,8 +16,10 @@ template <int n, int m> struct RiccatiSmem {
   alignas(16) double AB[n * NCp];           // [A | B], ROW-major (element (r, c) at c + NCp·r): what a lane reads of it is a run
                                             // of one row (all A columns, or all B columns), so the products below walk the
                                             // rows in the outer loop and keep n (or m) independent accumulators going
-  alignas(16) double GH[m * (n + m + 1)];   // [G | H | g], unregularised
-  alignas(16) double Kd[m * (n + 1)];       // [K | δu]
+  static constexpr int GS = (n + m + 2) & ~1;   // row stride of [G | H | g] (n + m + 1 columns, rounded up to even)
+  static constexpr int KS = (n + 2) & ~1;       // row stride of [K | δu] (n + 1 columns)
+  alignas(16) double GH[m * GS];            // [G | H | g], unregularised, ROW-major like AB (element (l, c) at c + GS·l)
+  alignas(16) double Kd[m * KS];            // [K | δu], ROW-major (element (l, c) at c + KS·l)
   alignas(16) double U[m * m];              // upper factor of H_reg (row-permuted)
   alignas(16) double sv[n];
 };
@@ -96,7 +98,7 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
   }
   if (lane < NC) {
 #pragma unroll
-    for (int i = 0; i < m; ++i) sm.GH[i + m * lane] = gh[i];
+    for (int i = 0; i < m; ++i) sm.GH[lane + RiccatiSmem<n, m>::GS * i] = gh[i];
   }
 
   // ---- feedback_parameters (src/backward_pass.jl:207-218): (H + reg·I) \ [G | g], partial-pivot LU.
@@ -135,7 +137,7 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
   const int kcolidx = isAff ? n : lane;
   if (isX || isAff) {
 #pragma unroll
-    for (int i = 0; i < m; ++i) { sm.Kd[i + m * kcolidx] = kc[i]; bad |= isnan(kc[i]); }
+    for (int i = 0; i < m; ++i) { sm.Kd[kcolidx + RiccatiSmem<n, m>::KS * i] = kc[i]; bad |= isnan(kc[i]); }
   }
   __syncwarp();
 
@@ -145,11 +147,12 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
   {
     double t[m];
 #pragma unroll
-    for (int i = 0; i < m; ++i) t[i] = gh[i];
+    for (int i = 0; i < m; ++i) {     // row i of H is a contiguous run
+      double a = gh[i];
 #pragma unroll
-    for (int l = 0; l < m; ++l)
-#pragma unroll
-      for (int i = 0; i < m; ++i) t[i] = fma(sm.GH[i + m * (n + l)], kc[l], t[i]);
+      for (int l = 0; l < m; ++l) a = fma(sm.GH[n + l + RiccatiSmem<n, m>::GS * i], kc[l], a);
+      t[i] = a;
+    }
 #pragma unroll
     for (int i = 0; i < n; ++i) nw[i] = 0.0;
 #pragma unroll
@@ -157,12 +160,16 @@ __device__ __forceinline__ bool riccati_column_step(RiccatiSmem<n, m>& sm, int l
 #pragma unroll
       for (int i = 0; i < n; ++i) nw[i] = fma(sm.AB[i + RiccatiSmem<n, m>::NCp * r], w[r], nw[i]);
 #pragma unroll
+    for (int l = 0; l < m; ++l)       // + Kᵀ·t, then + Gᵀ·(own column of K): row by row again, same order per output
+#pragma unroll
+      for (int i = 0; i < n; ++i) nw[i] = fma(sm.Kd[i + RiccatiSmem<n, m>::KS * l], t[l], nw[i]);
+#pragma unroll
+    for (int l = 0; l < m; ++l)
+#pragma unroll
+      for (int i = 0; i < n; ++i) nw[i] = fma(sm.GH[i + RiccatiSmem<n, m>::GS * l], kc[l], nw[i]);
+#pragma unroll
     for (int i = 0; i < n; ++i) {
       double a = nw[i];
-#pragma unroll
-      for (int l = 0; l < m; ++l) a = fma(sm.Kd[l + m * i], t[l], a);
-#pragma unroll
-      for (int l = 0; l < m; ++l) a = fma(sm.GH[l + m * i], kc[l], a);
       // immediate_cost_quadratization (src/backward_pass.jl:81-109) of the diagonal quadratic cost
       if constexpr (GENERAL) {
         if (isX || isAff) a += cx[i];                    // 𝐐 (x lanes), 𝐪 (affine lane)
