@@ -469,10 +469,7 @@ static int32_t backward_async(ilqr_handle* h) {
                      (variant == ILQR_VARIANT_WARP_PER_TRAJ || h->st.nslots <= h->split_below);
   const bool coop = variant == ILQR_VARIANT_WARP_PER_TRAJ || h->st.nslots <= h->coop_below;
   if (split && !h->ab_scratch) CK(h, dalloc(&h->ab_scratch, (size_t)h->prob.H * 20 * (size_t)h->st.S));
-  const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
-  cudaEventRecord(h->ev[e][0], h->stream);
-  if (h->is_custom) launch_bwd_custom(h->cmod, h->st, h->cparams, h->cp, h->stream);
-  else if (h->is_chain && !h->floating && h->chain_analytic) {
+  if (h->is_chain && !h->floating && h->chain_analytic) {   // before the timing event: cudaMalloc blocks the host
     if (!h->lin_scratch) {   // sized once: the whole batch, or chunks of it that keep the scratch below the budget
       const size_t per = chain_split_scratch_bytes(h->prob.nq, h->prob.H);
       double budget_gb = 28.0;
@@ -483,6 +480,11 @@ static int32_t backward_async(ilqr_handle* h) {
       CK(h, cudaMalloc((void**)&h->lin_scratch, per * (size_t)h->lin_chunk));
       CK(h, cudaMalloc((void**)&h->lin_private, chain_split_private_bytes(h->prob.nq)));
     }
+  }
+  const int e = h->n_pending < ilqr_handle::kMaxBurst ? h->n_pending : ilqr_handle::kMaxBurst - 1;
+  cudaEventRecord(h->ev[e][0], h->stream);
+  if (h->is_custom) launch_bwd_custom(h->cmod, h->st, h->cparams, h->cp, h->stream);
+  else if (h->is_chain && !h->floating && h->chain_analytic) {
     launch_bwd_chain_split(h->st, h->chain, h->cp, h->lin_scratch, h->lin_private, h->lin_chunk, h->stream);
   }
   else if (h->is_chain) launch_bwd_chain(h->st, h->chain, h->floating, h->cp, h->stream);
