@@ -405,7 +405,8 @@ def fp64_peak_inrun(device):
                 "lat_dfma_cycles": d.get("lat_dfma_cycles"), "sm_mhz_before": float(q) if q else None,
                 # the DFMA rate depends on how many of the three sources are vector registers (register-file bandwidth)
                 "tflops_by_vector_register_sources": {"1": d["fp64_dfma_tflops"], "2": d.get("fp64_dfma_2reg_tflops"),
-                                                      "3": d.get("fp64_dfma_3reg_tflops")}}
+                                                      "3": d.get("fp64_dfma_3reg_tflops"),
+                                                      "3r": d.get("fp64_dfma_3reg_shared_operand_tflops")}}
     except Exception as e:
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
@@ -689,25 +690,26 @@ def run_b200(args):
     slot_tf = 2.0 * FP64_ROUND * per_s / 1e12 if (per_s and FP64_ROUND) else None
     true_tf = FP64_ROUND_TRUE * per_s / 1e12 if (per_s and FP64_ROUND_TRUE) else None
     ncu_round = ncu_file_metrics(NCU_ROUND_FILE, "round_lpt_two_link")
-    # Operand-limited ceiling: the FP64 pipe issues a warp instruction every 2.0 / 2.6 / 3.75 cycles with 1 / 2 / 3 vector-
-    # register sources (measured in-run); weighting the kernel's own instruction mix (SASS) gives the rate the pipe can
-    # sustain on THIS instruction stream — the ceiling that extra warps cannot lift.
+    # Operand-adjusted ceiling: a DFMA with three distinct vector-register sources issues every 2.7 cycles instead of 2.0
+    # (2.2 when one of them comes from the operand-reuse cache; one or two register sources: 2.0) — measured in-run by
+    # tools/fp64_peak.cu.  Weighting the kernel's own instruction mix (SASS) gives the rate the pipe can sustain on THIS
+    # instruction stream.
     operand = None
     mixv = (sass.get(round_tag) or {}).get("fp64_by_vector_register_sources")
     rates = fp64_peak.get("tflops_by_vector_register_sources") or {}
-    if mixv and all(rates.get(k) for k in ("1", "2", "3")) and slot_tf:
-        cyc = {k: 2.0 * rates["1"] / rates[k] for k in ("1", "2", "3")}
+    if mixv and all(rates.get(k) for k in ("1", "2", "3", "3r")) and slot_tf:
+        cyc = {k: max(2.0, 2.0 * rates["1"] / rates[k]) for k in ("1", "2", "3", "3r")}
         tot = sum(mixv.values())
         mean_cyc = sum(mixv.get(k, 0) * cyc[k] for k in cyc) / tot
         ceil_tf = rates["1"] * 2.0 / mean_cyc
         operand = {"fp64_instructions_by_vector_register_sources": mixv, "pipe_cycles_per_instruction": cyc,
-                   "mean_pipe_cycles_per_fp64_instruction": mean_cyc, "operand_limited_peak_tflops": ceil_tf,
-                   "frac_of_operand_limited_peak": slot_tf / ceil_tf,
+                   "mean_pipe_cycles_per_fp64_instruction": mean_cyc, "operand_adjusted_peak_tflops": ceil_tf,
+                   "frac_of_operand_adjusted_peak": slot_tf / ceil_tf,
                    "predicted_cycles_per_round": SLOTS / (n_sm * 128.0) * H * tot * mean_cyc,
                    "ncu_cycles_per_round": (ncu_round["cycles"] / ncu_round["rounds_in_launch"]) if (ncu_round and ncu_round.get("cycles")) else None,
-                   "note": "tools/sass_operands.py + tools/fp64_peak.cu: a full-width round needs slots/(SMs x 128) warps per scheduler x H steps x "
-                           "sum(count x cycles) pipe cycles (predicted_cycles_per_round); ncu_cycles_per_round = sm__cycles_elapsed of the "
-                           "committed capture / its rounds"}
+                   "note": "'3r' = three register sources, one flagged .reuse.  predicted_cycles_per_round = the FP64 pipe's busy cycles for a "
+                           "full-width round: slots/(SMs x 128) warps per scheduler x H steps x sum(count x cycles); ncu_cycles_per_round = "
+                           "sm__cycles_elapsed of the committed capture / its rounds (elapsed >= busy)"}
     kname = "round_lpt_two_link<%s> (backward sweep + forward sweep + accept / converge test + retirement + admission; the only " \
             "kernel launched in the timed region)" % ("16, 3" if round_warps >= 16 else "12, 4")
     roofline = {

@@ -20,45 +20,35 @@ __global__ void dfma_throughput(double* out, int iters, double a, double b, int 
   if (s == 12345.678) out[0] = s;
 }
 
-// The same with three distinct VECTOR register operands per DFMA (what real code issues: the loop above multiplies by two
-// uniform values, i.e. one register operand per instruction) — the register-file side of the FP64 pipe's peak.
-template <int ILP>
-__global__ void dfma3_throughput(double* out, int iters, double a, double b) {
-  double acc[ILP], x[ILP], y[ILP];
-#pragma unroll
-  for (int i = 0; i < ILP; ++i) { acc[i] = threadIdx.x * 1e-3 + i; x[i] = a + 1e-12 * (threadIdx.x + i); y[i] = b + 1e-13 * (threadIdx.x * 3 + i); }
-  for (int it = 0; it < iters; ++it) {
-#pragma unroll
-    for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], x[(i + 3) % ILP], y[(i + 5) % ILP]);
-    if (it == iters - 7) { x[0] += 1e-15; y[1] += 1e-15; }   // keeps x, y in registers as live, non-constant values
-  }
-  double s = 0;
-#pragma unroll
-  for (int i = 0; i < ILP; ++i) s += acc[i];
-  if (s == 12345.678) out[0] = s;
-}
-
-// Operand mix of a DFMA stream, MODE: 0 = fma(acc, x_vec, b_uniform) (two vector register operands),
-// 1 = fma(x_i, y_j, acc) with x_i shared by two consecutive instructions (what a small matrix product issues: the
-// compiler can mark it .reuse), 2 = DMUL + DADD pairs on vector registers.
+// Operand side of the FP64 pipe: the same DFMA stream with 2 or 3 distinct VECTOR-register sources per instruction.  The
+// operands are loop invariant and loaded from memory (nothing for the compiler to fold), the loop body is 32 DFMAs and a
+// branch — check with `cuobjdump -sass tools/fp64_peak`.  (The first version of this probe perturbed its operands inside the
+// loop; the compiler turned that into a stream that was half MOV / ISETP / predicated DADD, and the rates it reported —
+// 26.5 and 18.2 TFLOP/s — measured that, not the operand path.)
+//   MODE 2: fma(acc, x_j, b_uniform)        two vector sources
+//   MODE 3: fma(acc, x_j, y_k)              three distinct vector sources
+//   MODE 5: fma(x_r, y_k, acc), x_r shared by eight consecutive instructions (what a small matrix product issues: .reuse)
 template <int MODE>
-__global__ void dfma_mix_throughput(double* out, int iters, double a, double b) {
+__global__ void __launch_bounds__(512) dfma_operands(double* out, const double* __restrict__ in, int iters) {
   double acc[8], x[8], y[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { acc[i] = threadIdx.x * 1e-3 + i; x[i] = a + 1e-12 * (threadIdx.x + i); y[i] = b + 1e-13 * (threadIdx.x * 3 + i); }
+  for (int i = 0; i < 8; ++i) { acc[i] = in[threadIdx.x + 32 * i]; x[i] = in[1024 + threadIdx.x + 32 * i]; y[i] = in[2048 + threadIdx.x + 32 * i]; }
+  const double ub = in[4097];
+#pragma unroll 1
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (MODE == 0) acc[i] = fma(acc[i], x[(i + 3) % 8], b);
-      if (MODE == 1) acc[i] = fma(x[i / 2], y[(i + 5) % 8], acc[i]);
-      if (MODE == 2) acc[i] = (i & 1) ? acc[i] * x[(i + 3) % 8] : acc[i] + y[(i + 5) % 8];
-    }
-    if (it == iters - 7) { x[0] += 1e-15; y[1] += 1e-15; }
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE == 2) acc[i] = fma(acc[i], x[(i + 3 + r) % 8], ub);
+        if (MODE == 3) acc[i] = fma(acc[i], x[(i + 3 + r) % 8], y[(i + 5 + 2 * r) % 8]);
+        if (MODE == 5) acc[i] = fma(x[r], y[(i + 5 + 2 * r) % 8], acc[i]);
+      }
   }
   double s = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += acc[i];
-  if (s == 12345.678) out[0] = s;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 __global__ void latency_kernel(double* out, long long* cycles, int iters, double a, double b, int mode) {
@@ -105,34 +95,33 @@ int main() {
     }
     printf(", \"ms_lanes%d\": %.4f", lanes, b2);
   }
-  // three register operands; full occupancy and the round kernel's residency (one block of 12 warps per SM)
-  for (int cfg = 0; cfg < 2; ++cfg) {
-    const int bl = cfg == 0 ? blocks : p.multiProcessorCount, th = cfg == 0 ? threads : 384;
-    float b3 = 1e30f;
-    for (int rep = 0; rep < 4; ++rep) {
-      cudaEventRecord(e0);
-      dfma3_throughput<8><<<bl, th>>>(out, iters, 1.0000001, 1e-9);
-      cudaEventRecord(e1); cudaEventSynchronize(e1);
-      float ms; cudaEventElapsedTime(&ms, e0, e1);
-      if (rep > 0 && ms < b3) b3 = ms;
-    }
-    printf(", \"%s\": %.3f", cfg == 0 ? "fp64_dfma_3reg_tflops" : "fp64_dfma_3reg_12warps_tflops", 2.0 * 8 * iters * (double)bl * th / (b3 * 1e-3) / 1e12);
-  }
+  // operand count: full occupancy, and the round kernel's residency (one block of 12 warps per SM) for the three-source case
   {
-    const char* mix[3] = {"fp64_dfma_2reg_tflops", "fp64_dfma_3reg_shared_operand_tflops", "fp64_dmul_dadd_2reg_slot_tflops"};
-    for (int mode = 0; mode < 3; ++mode) {
+    double* in; cudaMalloc(&in, 1 << 16);
+    double* h = new double[8192];
+    for (int i = 0; i < 8192; ++i) h[i] = 1.0 + 1e-9 * i;
+    h[4096] = 1.0000001; h[4097] = 1e-9;
+    cudaMemcpy(in, h, 8192 * sizeof(double), cudaMemcpyHostToDevice);
+    delete[] h;
+    const int it2 = 1 << 12;
+    auto time_mode = [&](int mode, int bl, int th) {
       float bm = 1e30f;
       for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        if (mode == 0) dfma_mix_throughput<0><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
-        if (mode == 1) dfma_mix_throughput<1><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
-        if (mode == 2) dfma_mix_throughput<2><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        if (mode == 2) dfma_operands<2><<<bl, th>>>(out, in, it2);
+        if (mode == 3) dfma_operands<3><<<bl, th>>>(out, in, it2);
+        if (mode == 5) dfma_operands<5><<<bl, th>>>(out, in, it2);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0 && ms < bm) bm = ms;
       }
-      printf(", \"%s\": %.3f", mix[mode], 2.0 * 8 * iters * (double)blocks * threads / (bm * 1e-3) / 1e12);
-    }
+      return 2.0 * 32 * it2 * (double)bl * th / (bm * 1e-3) / 1e12;
+    };
+    printf(", \"fp64_dfma_2reg_tflops\": %.3f", time_mode(2, blocks, threads));
+    printf(", \"fp64_dfma_3reg_tflops\": %.3f", time_mode(3, blocks, threads));
+    printf(", \"fp64_dfma_3reg_12warps_tflops\": %.3f", time_mode(3, p.multiProcessorCount, 384));
+    printf(", \"fp64_dfma_3reg_shared_operand_tflops\": %.3f", time_mode(5, blocks, threads));
+    cudaFree(in);
   }
   const char* names[5] = {"dfma", "sincos", "div", "dadd", "dmul"};
   for (int mode = 0; mode < 5; ++mode) {
