@@ -217,6 +217,8 @@ def aux_chain(device, cpu_too, rank=0, world=1, dist=None):
     x0 = np.asfortranarray(x0[:, lo:hi]); u = np.asfortranarray(u[:, :, lo:hi])
     with ilqr_b200.BatchSolver(prob) as s:
         s.upload_x0(x0, u)
+        s.backward_pass(); s.forward_pass()      # warm-up: kernel load and the one-time scratch allocation stay out of the timed fit
+        s.upload_x0(x0, u)
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter(); s.fit(MAX_ITER, TOL); dt = time.perf_counter() - t0
