@@ -281,10 +281,19 @@ round_lpt_two_link(const __grid_constant__ RoundP rp, const __grid_constant__ Tw
               }
               double kv[NK];
 #pragma unroll
-              for (int i = 0; i < NU; ++i) {
-                bad |= isnan(d[i]);
+              for (int i = 0; i < NU; ++i)
 #pragma unroll
-                for (int j = 0; j < NX; ++j) { kv[i + NU * j] = Kk[i][j]; bad |= isnan(Kk[i][j]); }
+                for (int j = 0; j < NX; ++j) kv[i + NU * j] = Kk[i][j];
+              // `!any(isnan, K)` (src/backward_pass.jl:353-354) is decided by the gains of time step 0: a NaN in δu or K
+              // at any step enters 𝐬 / 𝐒 (0·NaN = NaN) and with them every gain computed after it, so ten FP64
+              // comparisons per step collapse into ten per sweep
+              if (k == 0) {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) {
+                  bad |= isnan(d[i]);
+#pragma unroll
+                  for (int j = 0; j < NX; ++j) bad |= isnan(Kk[i][j]);
+                }
               }
               stv<NU>(rp.duff + ((int64_t)k * S + s) * NU, d);
               stv<NK>(rp.K + ((int64_t)k * S + s) * NK, kv);

@@ -727,3 +727,33 @@ def test_streamer_with_x_traj_equals_batch_solves(device):
         assert np.array_equal(oc, refs[b]["cost"]), b
         assert np.array_equal(ox.transpose(2, 1, 0), refs[b]["x"]), b
         assert np.array_equal(ou.transpose(2, 1, 0), refs[b]["u"]), b
+
+
+def test_nan_inputs_flag_nan_gains_on_every_path():
+    """`@assert !any(isnan, K)` (src/backward_pass.jl:353-354) as a per-trajectory status bit: a NaN planted in x_init or
+    u_init at the first, a middle or the last time step must set NAN_GAINS for that trajectory — on the batch path and
+    in the fused rounds (whose backward sweep decides it from the gains of time step 0: a NaN entering 𝐬 / 𝐒 anywhere
+    reaches them) — and must leave every other trajectory bit-identical to a clean solve."""
+    B, H = 64, 40
+    _, x, u = config2_batch(B, H, seed=71)
+    clean_x, clean_u = x.copy(order="F"), u.copy(order="F")
+    poisoned = {5: ("x", 0), 20: ("u", 17), 33: ("x", H - 1), 47: ("u", H - 1), 60: ("x", H)}
+    for b, (which, k) in poisoned.items():
+        if which == "x":
+            x[k, 1, b] = np.nan
+        else:
+            u[k, 0, b] = np.nan
+    with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(H, B)) as s:
+        clean = s.solve(clean_x, clean_u, max_iter=30, tol=1e-6)
+        ref = s.solve(x, u, max_iter=30, tol=1e-6)
+    out = dict(x=np.zeros_like(x), u=np.zeros_like(u), cost=np.zeros(B), iters=np.zeros(B, dtype=np.int32), status=np.zeros(B, dtype=np.int32))
+    with ilqr_b200.Streamer(ilqr_b200.two_link_problem(H, 64), B, ring=2, max_iter=30, tol=1e-6) as st:
+        st.wait(st.submit(x, u, out))
+    ok = np.array([b not in poisoned for b in range(B)])
+    for res in (ref, out):
+        for b in poisoned:
+            assert res["status"][b] & _abi.STATUS_NAN_GAINS, (b, res["status"][b])
+        assert not np.any(res["status"][ok] & _abi.STATUS_NAN_GAINS)
+        assert np.array_equal(res["iters"][ok], clean["iters"][ok]) and np.array_equal(res["x"][:, :, ok], clean["x"][:, :, ok])
+        assert np.array_equal(res["u"][:, :, ok], clean["u"][:, :, ok]) and np.array_equal(res["cost"][ok], clean["cost"][ok])
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["iters"], ref["iters"])
