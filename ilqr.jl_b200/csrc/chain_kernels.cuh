@@ -452,7 +452,7 @@ template <int NQ> constexpr int kLinBlockDoubles = 4 * chain_lin::StageItems<NQ>
 template <int NQ>
 __global__ void __launch_bounds__(kLinThreads)
 lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp, double* __restrict__ scratch,
-          double2* __restrict__ priv, int slot0, int nchunk, int Hb) {
+          double2* __restrict__ priv, unsigned long long* __restrict__ work, int slot0, int nchunk, int Hb) {
   extern __shared__ __align__(16) double lin_smem[];
   constexpr int n = 2 * NQ, m = NQ;
   const int Hp = Hb * kLinSteps;
@@ -460,9 +460,18 @@ lin_chain(const __grid_constant__ DevState st, const __grid_constant__ ChainP cp
   LinStore<NQ> store{reinterpret_cast<double2*>(lin_smem) + threadIdx.x,
                      lin_smem + kLinThreads * NQ * kLinkSmemDoubles + threadIdx.x,
                      priv + (size_t)blockIdx.x * (kLinThreads * NQ * kLinkInertiaPairs) + threadIdx.x};
-  // persistent blocks: work item t = (trajectory of the chunk, time step), time step fastest
+  // persistent blocks: work item t = (trajectory of the chunk, time step), time step fastest.  A warp takes the next 32
+  // items from a global counter: 6 warps on 4 schedulers means two schedulers carry two warps and two carry one, and with a
+  // static stride the lone warps would finish early and idle while the shared ones still had a third of their items left.
+  const int lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (long long t = (long long)blockIdx.x * kLinThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kLinThreads) {
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(work, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((long long)base >= total) break;
+    const long long t = (long long)base + lane;
+    if (t >= total) continue;
     const int sl = (int)(t / Hp), k = (int)(t - (long long)sl * Hp);
     if (k >= st.H) continue;
     const int s = slot0 + sl;
@@ -733,7 +742,7 @@ template <int NQ> int lin_grid() {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lin_chain<NQ>, kLinThreads, kLinSmemBytes<NQ>);
   return std::max(1, sms) * std::max(1, per_sm);
 }
-template <int NQ> size_t split_private_bytes() { return (size_t)lin_grid<NQ>() * kLinPrivateBytesPerBlock<NQ>; }
+template <int NQ> size_t split_private_bytes() { return (size_t)lin_grid<NQ>() * kLinPrivateBytesPerBlock<NQ> + 16; }   // + the work counter
 template <int NQ>
 void run_bwd_split(const DevState& st, const ChainP& cp, const CostP& cost, double* scratch, double* priv, int chunk, cudaStream_t s) {
   const int Hb = (st.H + kLinSteps - 1) / kLinSteps;
@@ -742,7 +751,9 @@ void run_bwd_split(const DevState& st, const ChainP& cp, const CostP& cost, doub
     const int cnt = std::min(chunk, st.nslots - slot0);
     const long long items = (long long)cnt * Hb * kLinSteps;
     const int grid = (int)std::min<long long>((items + kLinThreads - 1) / kLinThreads, max_grid);
-    lin_chain<NQ><<<grid, kLinThreads, kLinSmemBytes<NQ>, s>>>(st, cp, scratch, reinterpret_cast<double2*>(priv), slot0, cnt, Hb);
+    unsigned long long* work = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(priv) + (size_t)max_grid * kLinPrivateBytesPerBlock<NQ>);
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), s);
+    lin_chain<NQ><<<grid, kLinThreads, kLinSmemBytes<NQ>, s>>>(st, cp, scratch, reinterpret_cast<double2*>(priv), work, slot0, cnt, Hb);
     ric_chain<NQ><<<grid_for(cnt, kCW), kCW * 32, sizeof(RicSmem<NQ>) * kCW, s>>>(st, cp, cost, scratch, slot0, cnt, Hb);
   }
 }
