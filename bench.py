@@ -128,7 +128,9 @@ def parity_report(ref, n, gpu, traced):
     ex, eu = rel(gpu["x"][..., :n], ref["x"][..., :n]), rel(gpu["u"][..., :n], ref["u"][..., :n])
     last = ref["cost"][np.maximum(it_r, 1) - 1, np.arange(n)]
     ec = np.abs(gpu["cost"][:n] - last) / np.abs(last)
-    out = {"n": int(n), "against": "oracle (CPU restatement of iLQR.jl; the reference ships no golden vectors and Julia is absent: parity unpinned)",
+    out = {"n": int(n), "against": "oracle (CPU restatement of iLQR.jl; pinned to pixel accuracy, ~0.01 rad, against the joint angles read back from "
+                                   "the five animations the reference ships — tests/test_reference_gif_cpu.py; below that no number of the "
+                                   "Julia package exists and Julia is absent: parity unpinned in the strict sense)",
            "iters_mismatch": int(np.sum(~same)), "converged_flag_mismatch": int(np.sum(conv_g != ref["converged"][:n])),
            "max_rel_x": float(ex[same].max()), "max_rel_u": float(eu[same].max()), "max_rel_cost": float(ec[same].max()),
            "tolerance": {"x_u_per_iterate_cost": 1e-9, "converged_cost": 1e-8},

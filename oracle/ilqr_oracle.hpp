@@ -5,13 +5,18 @@
 // cpu_baseline / --impl reference legs may use anything under oracle/.
 // The product path (libilqr_b200.so) never links, calls or falls back to it.
 //
-// PARITY PINNING: the reference ships no golden vectors and Julia is not
-// available in this image, so this oracle is pinned against (i) an
-// independently written closed-form NumPy restatement (tests/np_restatement.py),
-// (ii) central-difference derivative checks, (iii) the discrete-LQR
-// known-answer test and (iv) the cost traces recorded in SURVEY.md §6 (which
-// came from a third restatement).  "parity unpinned" in the strict sense: no
-// output of the Julia package itself is available.
+// PARITY PINNING.  The reference ships no golden vectors and Julia is not available in this image, but it does ship
+// OUTPUTS OF ITS OWN RUNS: five animations (test/2_link_example/figures/iLQR_2_link*.gif, docs/extras) that
+// animate_2_link.jl:27-41 drew from `iLQR.fit`'s result — every 10th knot point of an H = 900 solve, one target tool
+// location per quadrant.  tests/golden/make_gif_angles.py reads the joint angles back from the frames
+// (tests/golden/reference_gif_angles.json, ±0.01 rad: a pixel is 0.011 units) and tests/test_reference_gif_cpu.py holds
+// this oracle to them: rms 0.002-0.006 rad, max 0.012-0.025 rad over 91 frames x 2 angles x 5 animations, while the same
+// solver with textbook Coriolis terms instead of the reference's single-index sum misses by 0.016 / 0.053.  That pins
+// the dynamics, costs, target kinematics, horizon bookkeeping and the solver's fixed point against the real package —
+// to pixel accuracy.  Below that ("parity unpinned" in the strict sense: no NUMBER printed by the Julia package
+// exists) the oracle rests on (i) an independently written closed-form NumPy restatement (tests/np_restatement.py,
+// 1e-12), (ii) central-difference derivative checks, (iii) the discrete-LQR known-answer test and (iv) the cost traces
+// recorded in SURVEY.md §6 (which came from a third restatement).
 //
 // Reference lines followed (paths relative to /root/reference):
 //   src/backward_pass.jl:25-40    linearize_dynamics

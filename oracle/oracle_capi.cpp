@@ -173,6 +173,20 @@ void oracle_two_link_fit_batch(int B, int H, double* x, double* u, const double*
   for (auto& t : th) t.join();
 }
 
+// One fit of the 2-link plugin with another target tool location (2_link_helper_functions.jl:16-26: `target_tool_loc`,
+// θ* = InverseKinematics(target)) — the reference's shipped animations were made with targets in all four quadrants
+// (tests/golden/make_gif_angles.py reads their frames back; tests/test_reference_gif_cpu.py compares).
+int oracle_two_link_fit_target(double tx, double ty, int H, double* x, double* u, int max_iter, double tol, double reg,
+                               int jmax, int32_t* status) {
+  TwoLink p = plugin();
+  p.target_tool_loc[0] = tx; p.target_tool_loc[1] = ty;
+  p.inverse_kinematics(p.target_tool_loc, p.target_joint);
+  S2 s(p); s.reg = reg; s.jmax = jmax;
+  auto tr = s.fit(H, x, u, nullptr, max_iter, tol);
+  if (status) *status = tr.status;
+  return tr.iters;
+}
+
 // ---- the 2-link arm with the tool-point cost + a cross term (TwoLinkToolCost): generic cost quadratisation incl. 𝐏 ----
 static TwoLinkToolCost tool_plugin(double w_tool, double w_final, double gamma) {
   TwoLinkToolCost p; p.w_tool = w_tool; p.w_final = w_final; p.gamma = gamma; return p;

@@ -174,6 +174,19 @@ def fit_batch(x_init, u_init, x_traj=None, max_iter=100, tol=1e-6, reg=0.01, jma
     return dict(x=x, u=u, cost=cost, alpha=alpha, du2=du2, iters=iters, converged=conv.astype(bool), status=status)
 
 
+def fit_target(x_init, u_init, target, max_iter=100, tol=1e-6, reg=0.01, jmax=32):
+    """One trajectory of the 2-link plugin with target tool location `target` = (x, y) (2_link_helper_functions.jl:16).
+    x_init (N,4), u_init (H,2).  Returns (x, u, iterations, status)."""
+    u = _f(u_init).copy(order="F"); H = u.shape[0]
+    x = _f(x_init, (H + 1, 4)).copy(order="F")
+    st = ctypes.c_int32(0)
+    fn = lib().oracle_two_link_fit_target
+    fn.restype = ctypes.c_int
+    it = fn(ctypes.c_double(target[0]), ctypes.c_double(target[1]), H, _p(x), _p(u), max_iter, ctypes.c_double(tol),
+            ctypes.c_double(reg), jmax, ctypes.byref(st))
+    return x, u, int(it), int(st.value)
+
+
 # ---- the 2-link arm with the FK tool-point cost + a cross term (oracle TwoLinkToolCost): generic quadratisation incl. 𝐏
 _cd = ctypes.c_double
 

@@ -757,3 +757,32 @@ def test_nan_inputs_flag_nan_gains_on_every_path():
         assert np.array_equal(res["iters"][ok], clean["iters"][ok]) and np.array_equal(res["x"][:, :, ok], clean["x"][:, :, ok])
         assert np.array_equal(res["u"][:, :, ok], clean["u"][:, :, ok]) and np.array_equal(res["cost"][ok], clean["cost"][ok])
     assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["iters"], ref["iters"])
+
+
+def test_gpu_reproduces_the_reference_animations():
+    """The CUDA path against outputs of the reference itself: the four problems behind the animations iLQR.jl ships
+    (tests/test_reference_gif_cpu.py, tests/golden/reference_gif_angles.json: H = 900, x₀ = [.1, −.1, 0, 0], target tool
+    location in each quadrant) — the GPU solution must sit on the frames to pixel accuracy like the oracle's, and on the
+    oracle's to 1e-9."""
+    import json
+    import os
+    import np_restatement as npr
+    fix = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_gif_angles.json")))["gifs"]
+    targets = {"iLQR_2_link_quad_1.gif": (0.6, 0.5), "iLQR_2_link_quad_2.gif": (-0.6, 0.5), "iLQR_2_link_quad_3.gif": (-0.6, -0.5),
+               "iLQR_2_link_quad_4.gif": (0.6, -0.5)}
+    H = 900
+    u = np.zeros((H, 2), order="F")
+    x = orc.rollout(np.array([0.1, -0.1, 0.0, 0.0]), u)
+    for name, tgt in targets.items():
+        prob = ilqr_b200.two_link_problem(H, 1)
+        q = npr.inverse_kinematics(tgt)                    # 2_link_helper_functions.jl:19-26
+        prob.x_target[0], prob.x_target[1] = float(q[0]), float(q[1])
+        with ilqr_b200.BatchSolver(prob) as s:
+            out = s.solve(np.asfortranarray(x.reshape(H + 1, 4, 1)), np.asfortranarray(u.reshape(H, 2, 1)), max_iter=300, tol=1e-6)
+        xs, us, iters, status = orc.fit_target(x, u, tgt, max_iter=300, tol=1e-6)
+        assert out["iters"][0] == iters, name
+        assert rel_err(out["x"][:, :, 0], xs) <= RTOL and rel_err(out["u"][:, :, 0], us) <= RTOL, name
+        ang = np.array(fix[name]["theta1_theta12"])
+        g = out["x"][::10, :, 0]
+        d = (ang - np.stack([g[:, 0], g[:, 0] + g[:, 1]], axis=1) + np.pi) % (2 * np.pi) - np.pi
+        assert np.sqrt(np.mean(d ** 2)) < 0.008 and np.abs(d).max() < 0.035, (name, np.sqrt(np.mean(d ** 2)), np.abs(d).max())

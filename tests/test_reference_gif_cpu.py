@@ -1,0 +1,111 @@
+"""The CPU oracle against OUTPUTS OF THE REFERENCE ITSELF: the five animations iLQR.jl ships
+(/root/reference/test/2_link_example/figures/iLQR_2_link*.gif, drawn by animate_2_link.jl:27-41 from `iLQR.fit`'s
+result, every 10th knot point of an H = 900 solve from x₀ = [.1, −.1, 0, 0], one target tool location per quadrant).
+tests/golden/make_gif_angles.py read the joint angles back from the frames (≈ ±0.01 rad: one pixel is 0.011 units);
+tests/golden/reference_gif_angles.json holds them.  No other number produced by the reference exists anywhere, so this is
+what pins the restatement: dynamics (incl. the single-index Coriolis sum), costs, inverse kinematics of the target,
+horizon / knot bookkeeping and the solver's fixed point.  It cannot see rounding-level detail — that is what the
+restatement-vs-restatement and GPU-vs-oracle tests at 1e-9 … 1e-12 are for."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import np_restatement as npr
+from oracle import oracle_py as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = json.load(open(os.path.join(HERE, "golden", "reference_gif_angles.json")))["gifs"]
+TARGETS = {"iLQR_2_link.gif": (0.6, -0.5), "iLQR_2_link_quad_1.gif": (0.6, 0.5), "iLQR_2_link_quad_2.gif": (-0.6, 0.5),
+           "iLQR_2_link_quad_3.gif": (-0.6, -0.5), "iLQR_2_link_quad_4.gif": (0.6, -0.5)}
+H = 900
+RMS_TOL, MAX_TOL = 0.008, 0.035          # observed: rms ≤ 0.0057, max ≤ 0.025 rad (frames are 400 × 400 pixels for 4 × 4 units)
+
+
+def frames_error(x, name):
+    ang = np.array(FIX[name]["theta1_theta12"])
+    mine = np.stack([x[::10, 0], x[::10, 0] + x[::10, 1]], axis=1)        # Julia t = 1:10:901 ⇒ knots 0, 10, …, 900
+    d = (ang - mine + np.pi) % (2 * np.pi) - np.pi
+    return float(np.sqrt(np.mean(d ** 2))), float(np.abs(d).max())
+
+
+def initial_guess():
+    x0 = np.array([0.1, -0.1, 0.0, 0.0])                                   # animate_2_link.jl:13
+    u = np.zeros((H, 2), order="F")
+    return orc.rollout(x0, u), u
+
+
+def test_fixture_is_what_the_script_describes():
+    assert set(FIX) == set(TARGETS)
+    for name, g in FIX.items():
+        a = np.array(g["theta1_theta12"])
+        assert a.shape == (91, 2) and g["knot_stride"] == 10
+        assert abs(a[0, 0] - 0.1) < 0.01 and abs(a[0, 1] - 0.0) < 0.01, name          # x₀ = [.1, −.1, ·, ·]: θ₁ = .1, θ₁ + θ₂ = 0
+        # the last frame sits at the target's inverse-kinematics solution (2_link_helper_functions.jl:19-26)
+        q = npr.inverse_kinematics(TARGETS[name])
+        d = (a[-1] - np.array([q[0], q[0] + q[1]]) + np.pi) % (2 * np.pi) - np.pi
+        assert np.abs(d).max() < 0.02, (name, d)
+
+
+@pytest.mark.parametrize("name", sorted(TARGETS))
+def test_oracle_reproduces_the_reference_animation(name):
+    x, u = initial_guess()
+    xs, us, iters, status = orc.fit_target(x, u, TARGETS[name], max_iter=300, tol=1e-6)   # the script runs max_iter = 1e6
+    assert status == 0 and iters < 300
+    rms, worst = frames_error(xs, name)
+    assert rms < RMS_TOL and worst < MAX_TOL, (name, rms, worst)
+
+
+def test_anchor_config_through_the_same_entry_point():
+    """quad_4 is the problem animate_2_link.jl sets up today: the survey's anchor (7 iterations) through fit_target"""
+    x, u = initial_guess()
+    xs, us, iters, status = orc.fit_target(x, u, (0.6, -0.5), max_iter=100, tol=1e-6)
+    ref = orc.fit(x, u, max_iter=100, tol=1e-6)
+    assert iters == 7 and np.array_equal(xs, ref["x"])
+
+
+def test_the_frames_tell_the_reference_dynamics_from_textbook_dynamics(monkeypatch):
+    """How sharp the pin is: the independent NumPy restatement matches the frames as the oracle does, and misses them by
+    several times more once the reference's single-index Coriolis sum (`k in length(θ)`, 2_link_helper_functions.jl:36-47)
+    is replaced by the textbook Christoffel terms h = −β sinθ₂ (2θ̇₁θ̇₂ + θ̇₂², −θ̇₁²)."""
+    name = "iLQR_2_link_quad_4.gif"
+    x0 = np.array([0.1, -0.1, 0.0, 0.0]); u = np.zeros((H, 2))
+    xs, _, tr = npr.fit(npr.open_loop_rollout(x0, u), u, max_iter=30, tol=1e-6)
+    rms_ref, _ = frames_error(xs, name)
+    assert tr["converged"] and rms_ref < 0.005
+
+    def fc_textbook(s, uu):
+        c2, s2 = math.cos(s[1]), math.sin(s[1])
+        M = np.array([[npr.ALPHA + 2 * npr.BETA * c2, npr.DELTA + npr.BETA * c2], [npr.DELTA + npr.BETA * c2, npr.DELTA]])
+        h = -npr.BETA * s2 * np.array([2 * s[2] * s[3] + s[3] * s[3], -s[2] * s[2]])
+        return np.concatenate([s[2:4], np.linalg.solve(M, uu - h)])
+
+    def jac_fd(s, uu):
+        Phi, Psi, e = np.zeros((4, 4)), np.zeros((4, 2)), 1e-6
+        for i in range(4):
+            d = np.zeros(4); d[i] = e
+            Phi[:, i] = (fc_textbook(s + d, uu) - fc_textbook(s - d, uu)) / (2 * e)
+        for i in range(2):
+            d = np.zeros(2); d[i] = e
+            Psi[:, i] = (fc_textbook(s, uu + d) - fc_textbook(s, uu - d)) / (2 * e)
+        return Phi, Psi
+
+    monkeypatch.setattr(npr, "fc", fc_textbook)
+    monkeypatch.setattr(npr, "fc_jac", jac_fd)
+    xs2, _, tr2 = npr.fit(npr.open_loop_rollout(x0, u), u, max_iter=30, tol=1e-6)
+    rms_tb, worst_tb = frames_error(xs2, name)
+    assert rms_tb > 3 * rms_ref and worst_tb > 0.04, (rms_ref, rms_tb, worst_tb)
+
+
+def test_fixture_regenerates_from_the_reference_when_it_is_there():
+    """Here (not on the GPU box) the reference tree exists: the committed angles are what the script reads today."""
+    if not os.path.isdir("/root/reference/test/2_link_example/figures"):
+        pytest.skip("no reference tree on this machine")
+    pytest.importorskip("PIL")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_gif_angles", os.path.join(HERE, "golden", "make_gif_angles.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    ang, _ = m.angles_of("/root/reference/test/2_link_example/figures/iLQR_2_link_quad_1.gif")
+    assert np.allclose(np.array(ang), np.array(FIX["iLQR_2_link_quad_1.gif"]["theta1_theta12"]), atol=1e-12)
