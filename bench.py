@@ -861,6 +861,20 @@ def run_b200(args):
         except Exception as e:
             traced = None
         parity = parity_report(ref, n_s, gpu, traced)
+        try:   # configs[0] through the product path against the joint angles of the reference's own animation of it
+            fixture = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_gif_angles.json")))["gifs"]["iLQR_2_link_quad_4.gif"]
+            with ilqr_b200.BatchSolver(ilqr_b200.two_link_problem(900, 1, device=local)) as sg:
+                sg.upload_x0(np.asfortranarray(np.array([[0.1], [-0.1], [0.0], [0.0]])), np.zeros((900, M_, 1), order="F"))
+                sg.fit(MAX_ITER, TOL)
+                xg, itg = sg.download(_abi.X)[::10, :, 0], int(sg.download(_abi.ITERS)[0])
+            dg = (np.array(fixture["theta1_theta12"]) - np.stack([xg[:, 0], xg[:, 0] + xg[:, 1]], axis=1) + np.pi) % (2 * np.pi) - np.pi
+            parity["reference_animation"] = {
+                "what": "configs[0] (x0 = [.1, -.1, 0, 0], H = 900) solved on the GPU vs the joint angles read back from the frames of "
+                        "test/2_link_example/figures/iLQR_2_link_quad_4.gif, which iLQR.jl drew from its own fit of this problem "
+                        "(tests/golden/make_gif_angles.py; pixel accuracy ~0.01 rad)",
+                "frames": 91, "iterations": itg, "rms_rad": float(np.sqrt(np.mean(dg ** 2))), "max_rad": float(np.abs(dg).max())}
+        except Exception as e:
+            parity["reference_animation"] = {"error": repr(e)}
     s.close()
     del douts
     other = None
