@@ -5,6 +5,9 @@ exist anywhere, so they pin the CPU oracle against the real thing — to pixel a
 
     python tests/golden/make_gif_angles.py  →  tests/golden/reference_gif_angles.json        (needs /root/reference)
 
+(docs/extras/iLQR_2_link.gif is not used: it starts from θ = (π/4, −π/2) and ends in the mirrored elbow configuration of
+the target (0.6, 0), which the joint-space cost of today's 2_link_helper_functions.jl cannot produce — it predates it.)
+
 Method: axes from the five grid / frame lines of the first frame (x, y = −2 … 2 ⇒ origin and pixels per unit), the arm from its colour
 (the only saturated pixels of a frame); per link a total-least-squares line through the pixels within 3.5 px of the link,
 started from the marker centroids (darker where line and markers overlap), iterated twice."""
