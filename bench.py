@@ -132,6 +132,9 @@ def parity_report(ref, n, gpu, traced):
                                    "the five animations the reference ships — tests/test_reference_gif_cpu.py; below that no number of the "
                                    "Julia package exists and Julia is absent: parity unpinned in the strict sense)",
            "iters_mismatch": int(np.sum(~same)), "converged_flag_mismatch": int(np.sum(conv_g != ref["converged"][:n])),
+           "decisions_note": "an iteration-count mismatch is what any flipped branch produces: the accept test prev - new > 0, or the "
+                             "convergence test sum((u_new - u)^2) <= tol, whose sum the kernels accumulate time step by time step (k-major) "
+                             "while Julia's sum over the H x m matrix runs column-major (src/forward_pass.jl:171)",
            "max_rel_x": float(ex[same].max()), "max_rel_u": float(eu[same].max()), "max_rel_cost": float(ec[same].max()),
            "tolerance": {"x_u_per_iterate_cost": 1e-9, "converged_cost": 1e-8},
            "within_tolerance": bool(np.all(same) and ex.max() < 1e-9 and eu.max() < 1e-9 and ec.max() < 1e-8)}
