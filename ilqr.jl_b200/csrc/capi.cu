@@ -303,6 +303,7 @@ int32_t ilqr_create(const ilqr_problem* p, ilqr_handle** out) {
   if (const char* e = getenv("ILQR_ROUND_SHIFT")) h->round_shift = atoi(e);
   if (const char* e = getenv("ILQR_ROUND_GROUP")) h->round_group = std::max(1, atoi(e));
   if (const char* e = getenv("ILQR_ROUND_MULTI")) h->round_multi = std::max(1, atoi(e));
+  if (const char* e = getenv("ILQR_MPC_SHIFT_X")) h->mpc_shift_x = atoi(e) != 0;
   if (const char* e = getenv("ILQR_CHAIN_ANALYTIC")) h->chain_analytic = atoi(e) != 0;
   if (const char* e = getenv("ILQR_STREAM_FUSED")) h->stream_fused = atoi(e) != 0;
   if (const char* e = getenv("ILQR_ROUND_DRAIN")) h->round_drain = atoi(e) != 0;
@@ -412,12 +413,22 @@ static int32_t mpc_reinit(ilqr_handle* h, int shift) {
   const ilqr_problem& p = h->prob;
   h->st.nslots = p.B;
   launch_reset_state(h->st, h->stream);
-  launch_tf_to_bf(h->plant, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
   launch_tf_to_bf(h->st.out_u, h->st.u[0], nullptr, p.B, p.H, p.m, h->st.S, h->stream, shift);
-  if (h->is_custom) launch_rollout_init_custom(h->cmod, h->st, h->cparams, h->st.x[1], h->stream);
-  else if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
-  else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
-  h->launches += 4;
+  const bool two_link = !h->is_chain && !h->is_custom;
+  if (two_link && shift == 1 && h->mpc_shift_x && p.H >= 2) {
+    // the previous solution is a rollout of its own controls and the plant moved along it (mpc_advance: the same tl_step
+    // on the same bits), so the shifted solution IS the rollout of the shifted controls up to its last state
+    launch_tf_to_bf(h->st.out_x, h->st.x[0], nullptr, p.B, p.H + 1, p.n, h->st.S, h->stream, 1);
+    launch_tf_to_bf(h->plant, h->st.x[0], nullptr, p.B, 1, p.n, h->st.S, h->stream);   // x[0] = the plant state (= x_sol[1])
+    launch_mpc_last_step_two_link(h->st, h->mp, h->stream);
+    h->launches += 5;
+  } else {
+    launch_tf_to_bf(h->plant, h->st.x[1], nullptr, p.B, 1, p.n, h->st.S, h->stream);
+    if (h->is_custom) launch_rollout_init_custom(h->cmod, h->st, h->cparams, h->st.x[1], h->stream);
+    else if (h->is_chain) launch_rollout_init_chain(h->st, h->chain, h->floating, h->st.x[1], h->stream);
+    else launch_rollout_init_two_link(h->st, h->mp, h->st.x[1], h->stream);
+    h->launches += 4;
+  }
   if (int32_t rc = check_launch(h, "mpc re-initialisation kernels")) return rc;
   h->loaded = true; h->have_gains = false; h->have_candidate = false;
   for (auto& v : h->prof) v = 0.0;

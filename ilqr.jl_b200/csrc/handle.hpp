@@ -52,6 +52,7 @@ struct ilqr_handle {
   bool pend_bwd = false, pend_fwd = false;
   // split backward pass of the fixed-base rigid-body models (chain_lin.cuh): linearisation scratch for `lin_chunk` trajectories
   double* lin_scratch = nullptr;
+  bool mpc_shift_x = true;                  // 2-link MPC warm start: shift the solution instead of rolling it out again (ILQR_MPC_SHIFT_X)
   double* lin_private = nullptr;            // block-private scratch of the persistent lin_chain grid (link inertias)
   int32_t lin_chunk = 0;
   bool chain_analytic = true;  // ILQR_CHAIN_ANALYTIC=0: the dual-number kernel bwd_chain

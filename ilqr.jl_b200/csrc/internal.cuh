@@ -122,6 +122,7 @@ void init_layout_attributes();   // opt-in dynamic shared memory; call once per 
 void launch_tf_to_bf(const double* tf, double* bf, const int32_t* slot_traj, int nslots, int T, int ncomp, int64_t S,
                      cudaStream_t s, int shift = 0);
 // MPC plant step: plant[t] ← f(plant[t], u_out[t][:,0]); u_applied[t] ← u_out[t][:,0]   (plant, u_applied: [B][n], [B][m])
+void launch_mpc_last_step_two_link(const DevState& st, const TwoLinkP& mp, cudaStream_t s);
 void launch_mpc_advance_two_link(const TwoLinkP& mp, const double* out_u, double* plant, double* u_applied, int B, int H,
                                  cudaStream_t s);
 // sel (nullable): per-slot choice between bf0 and bf1

@@ -1221,6 +1221,27 @@ void launch_fwd_wpt_two_link(const DevState& st, const TwoLinkP& mp, const CostP
 void launch_rollout_init_two_link(const DevState& st, const TwoLinkP& mp, const double* d_x0, cudaStream_t s) {
   rollout_init_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp, d_x0);
 }
+// Receding-horizon warm start without a fresh rollout: after the shifted copies x[k] ← x_sol[k+1], u[k] ← u_sol[k+1]
+// (u[H−1] = 0) only the last state is new, x[H] = f(x[H−1], u[H−1]).  The solution is a rollout of its own controls and
+// the plant is advanced with the same tl_step, so this is bit for bit what rollout_init_two_link would produce from the
+// plant state — one time step instead of H sequential ones on the critical path of a plant step.
+__global__ void __launch_bounds__(kBlock)
+mpc_last_step_two_link(const __grid_constant__ DevState st, const __grid_constant__ TwoLinkP mp) {
+  const int s = blockIdx.x * kBlock + threadIdx.x;
+  if (s >= st.nslots) return;
+  const int64_t S = st.S;
+  const int H = st.H, cur = st.cur[s];
+  double* __restrict__ X = st.x[cur];
+  const double* __restrict__ U = st.u[cur];
+  double xb[NX], ub[NU], xn[NX];
+  ldv<NX>(X + ((int64_t)(H - 1) * S + s) * NX, xb);
+  ldv<NU>(U + ((int64_t)(H - 1) * S + s) * NU, ub);
+  tl_step(mp, xb, ub, xn);
+  stv<NX>(X + ((int64_t)H * S + s) * NX, xn);
+}
+void launch_mpc_last_step_two_link(const DevState& st, const TwoLinkP& mp, cudaStream_t s) {
+  if (st.nslots > 0) mpc_last_step_two_link<<<grid_for(st.nslots, kBlock), kBlock, 0, s>>>(st, mp);
+}
 void launch_mpc_advance_two_link(const TwoLinkP& mp, const double* out_u, double* plant, double* u_applied, int B, int H,
                                  cudaStream_t s) {
   mpc_advance_two_link<<<grid_for(B, 128), 128, 0, s>>>(mp, out_u, plant, u_applied, B, H);
