@@ -654,8 +654,8 @@ def run_b200(args):
         return (v["fp64"], 2 * v["DFMA"] + v["DMUL"] + v["DADD"]) if v else (None, None)
 
     FP64_INSTR = {"bwd": instr("bwd")[0], "fwd": instr("fwd")[0]}
-    ncu_batch = {"bwd": ncu_file_metrics("ncu_full_r1_fullbatch.txt", "bwd_lpt_two_link"),
-                 "fwd": ncu_file_metrics("ncu_full_r1_fullbatch.txt", "fwd_lpt_two_link")}
+    ncu_batch = {"bwd": ncu_file_metrics("ncu_full_r2_fullbatch.txt", "bwd_lpt_two_link"),
+                 "fwd": ncu_file_metrics("ncu_full_r2_fullbatch.txt", "fwd_lpt_two_link")}
     NAMES = {"bwd": "backward pass: bwd_lpt_two_link (nslots > 20,000), lin_lpt + ric_lpt / ric_coop_two_link below",
              "fwd": "fwd_lpt_two_link (+ fwd_retry_two_link for rejected step sizes)"}
     pass_ms = prof_acc["bwd_ms"] + prof_acc["fwd_ms"]
