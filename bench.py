@@ -376,7 +376,7 @@ def ncu_file_metrics(name, kernel_tag):
     rounds_in_launch = int(mr.group(1)) if mr else 1
     blocks = text.split("-----")
     for b in blocks:
-        if kernel_tag not in b:
+        if kernel_tag not in b or "gpu__time_duration.sum" not in b:    # (a header comment may name the kernels too)
             continue
         val = {}
         for line in b.splitlines():
